@@ -1,0 +1,83 @@
+"""Build recipes for the in-tree native libraries (sm_100a only; no JIT cache, no fallbacks).
+
+  libgraftfem.so   CUDA kernels + C-ABI (include/graft_fem.h)           <- csrc/*.cu
+  libgraft_host.so C++ host mirror of the reference classes + mesh       <- host/*.cc
+The CPU oracle (oracle/liboracle.so) is test infrastructure and is built by oracle/Makefile.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+REPO_DIR = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+HOST = os.path.join(PKG_DIR, "host")
+INCLUDE = os.path.join(REPO_DIR, "include")
+
+LIB_CUDA = os.path.join(PKG_DIR, "libgraftfem.so")
+LIB_HOST = os.path.join(PKG_DIR, "libgraft_host.so")
+LIB_ORACLE = os.path.join(REPO_DIR, "oracle", "liboracle.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
+]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd, log=None):
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if log:
+        with open(log, "w") as f:
+            f.write(" ".join(cmd) + "\n" + res.stdout)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout)
+        raise RuntimeError("build failed: " + " ".join(cmd))
+    return res.stdout
+
+
+def _sources(d, exts):
+    return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(exts))
+
+
+def build_cuda(force=False):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    srcs = _sources(CSRC, (".cu",))
+    deps = srcs + _sources(CSRC, (".h", ".cuh")) + _sources(INCLUDE, (".h",))
+    if force or _newer(LIB_CUDA, deps):
+        _run([nvcc] + NVCC_FLAGS + ["-shared", "-I", INCLUDE, "-I", CSRC, "-o", LIB_CUDA] + srcs
+             + ["-lcudart", "-ldl"], log=os.path.join(PKG_DIR, "csrc", "build.log"))
+    return LIB_CUDA
+
+
+def build_host(force=False):
+    srcs = _sources(HOST, (".cc",))
+    srcs = [s for s in srcs if not s.endswith("elasticity.cc")]
+    deps = srcs + _sources(HOST, (".h",)) + _sources(INCLUDE, (".h",))
+    if force or _newer(LIB_HOST, deps):
+        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", INCLUDE, "-I", HOST,
+              "-o", LIB_HOST] + srcs + ["-ldl", "-lpthread"])
+    return LIB_HOST
+
+
+def build_oracle(force=False):
+    d = os.path.join(REPO_DIR, "oracle")
+    if force:
+        _run(["make", "-C", d, "clean"])
+    _run(["make", "-C", d])
+    return LIB_ORACLE
+
+
+def build_all(force=False):
+    return build_host(force), build_cuda(force), build_oracle(force)
+
+
+if __name__ == "__main__":
+    print(build_all(force="--force" in sys.argv))

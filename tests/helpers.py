@@ -1,0 +1,52 @@
+"""Shared problem builders for the tests (parameter values: parameters.prm:26-60)."""
+import numpy as np
+
+from dealii_adapter_b200.problem import SolverParameters, make_problem
+
+
+def nl_params(**kw):
+    d = dict(model="neo-Hookean", type_lin="CG", poly_degree=2, scenario="PF", delta_t=0.01,
+             mu=0.5e6, nu=0.4, rho=1000.0, tol_lin=1e-6, max_iterations_lin=2.0)
+    d.update(kw)
+    return SolverParameters(**d)
+
+
+def lin_params(**kw):
+    d = dict(model="linear", type_lin="CG", poly_degree=2, scenario="PF", delta_t=0.005,
+             mu=0.5e6, nu=0.4, rho=1000.0, max_iterations_lin=2.0)
+    d.update(kw)
+    return SolverParameters(**d)
+
+
+def smooth_field(problem, amp, seed=0):
+    """Deterministic smooth displacement-like field on the dofs (zero on constrained dofs)."""
+    x = problem.mesh.support_points
+    dim = problem.dim
+    n_nodes_lookup = np.zeros(problem.n_dofs)
+    rng = np.random.RandomState(seed)
+    k = rng.uniform(1.0, 3.0, size=(dim, dim))
+    ph = rng.uniform(0, 1.0, size=dim)
+    # component of each dof: recover from iface-independent rule via cell_dofs local order
+    comp = np.zeros(problem.n_dofs, dtype=np.int64)
+    cd = problem.mesh.cell_dofs.reshape(-1, problem.mesh.dofs_per_cell)
+    for c in range(dim):
+        comp[cd[:, c::dim].reshape(-1)] = c
+    L = np.array(problem.mesh.p1) - np.array(problem.mesh.p0)
+    xi = (x - np.array(problem.mesh.p0)) / L
+    for c in range(dim):
+        sel = comp == c
+        n_nodes_lookup[sel] = amp * np.sin(ph[c] + (xi[sel] * k[c]).sum(axis=1)) * xi[sel, 1]
+    n_nodes_lookup[problem.constrained != 0] = 0.0
+    return n_nodes_lookup
+
+
+def dof_components(problem):
+    comp = np.zeros(problem.n_dofs, dtype=np.int64)
+    cd = problem.mesh.cell_dofs.reshape(-1, problem.mesh.dofs_per_cell)
+    for c in range(problem.dim):
+        comp[cd[:, c::problem.dim].reshape(-1)] = c
+    return comp
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
