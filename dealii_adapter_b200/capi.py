@@ -1,0 +1,316 @@
+"""ctypes binding of the C-ABI in include/graft_fem.h (libgraftfem.so, sm_100a CUDA).
+
+There is no CPU fallback: loading fails loudly when the library is missing, and every call
+raises GraftError with the library's message on a non-zero status.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build
+
+GF_OK = 0
+GF_ERR_INVALID_ARG, GF_ERR_CUDA, GF_ERR_NOT_CONVERGED, GF_ERR_DET_F, GF_ERR_NCCL, GF_ERR_UNSUPPORTED = range(1, 7)
+
+# vector ids
+NL_TOTAL_DISPLACEMENT, NL_TOTAL_DISPLACEMENT_OLD, NL_VELOCITY, NL_VELOCITY_OLD, NL_ACCELERATION, \
+    NL_ACCELERATION_OLD, NL_EXTERNAL_STRESS, NL_SYSTEM_RHS, NL_SOLUTION_DELTA, NL_NEWTON_UPDATE = range(10)
+LIN_OLD_VELOCITY, LIN_VELOCITY, LIN_OLD_DISPLACEMENT, LIN_DISPLACEMENT, LIN_OLD_STRESS, LIN_STRESS, \
+    LIN_SYSTEM_RHS, LIN_BODY_FORCE = range(16, 24)
+VEC_SCRATCH0, VEC_SCRATCH1 = 28, 29
+MAT_TANGENT, MAT_STIFFNESS, MAT_MASS, MAT_SYSTEM = range(4)
+PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI = range(3)
+OPT_PRECONDITIONER, OPT_CG_CHECK_INTERVAL, OPT_PROFILE, OPT_OPERATOR = range(4)
+
+EXPORTED_SYMBOLS = [
+    "gf_create", "gf_destroy", "gf_last_error", "gf_set_option", "gf_comm_unique_id",
+    "gf_comm_create", "gf_comm_destroy", "gf_set_traction", "gf_get_interface_displacement",
+    "gf_state_save", "gf_state_restore", "gf_nl_begin_step", "gf_nl_newton_assemble",
+    "gf_nl_newton_solve", "gf_nl_end_step", "gf_lin_assemble_once", "gf_lin_step", "gf_get_vector",
+    "gf_set_vector", "gf_nnz", "gf_export_csr", "gf_spmv", "gf_spmv_timed", "gf_profile_get",
+    "gf_synchronize",
+]
+
+
+class GraftError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("graft_fem error %d: %s" % (code, msg))
+        self.code = code
+
+
+class GfDesc(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32), ("degree", C.c_int32), ("model", C.c_int32),
+        ("n_dofs", C.c_int64), ("n_cells", C.c_int64),
+        ("cell_dofs", C.c_void_p), ("cell_vertices", C.c_void_p), ("constrained", C.c_void_p),
+        ("n_iface_faces", C.c_int64), ("iface_cell", C.c_void_p), ("iface_face_no", C.c_void_p),
+        ("n_iface_nodes", C.c_int64), ("iface_dofs", C.c_void_p),
+        ("mu", C.c_double), ("nu", C.c_double), ("rho", C.c_double),
+        ("body_force", C.c_double * 3),
+        ("beta", C.c_double), ("gamma", C.c_double), ("theta", C.c_double), ("delta_t", C.c_double),
+        ("data_consistent", C.c_int32), ("device", C.c_int32),
+        ("n_owned_dofs", C.c_int64), ("comm", C.c_void_p),
+        ("n_neighbors", C.c_int32), ("nbr_rank", C.c_void_p),
+        ("send_ptr", C.c_void_p), ("send_dofs", C.c_void_p),
+        ("recv_ptr", C.c_void_p), ("recv_dofs", C.c_void_p),
+    ]
+
+
+class GfProfile(C.Structure):
+    _fields_ = [(n, C.c_double) for n in
+                ("assemble_cells_ms", "assemble_faces_ms", "scatter_ms", "spmv_ms", "cg_vector_ms",
+                 "update_ms", "halo_ms")] + \
+               [(n, C.c_int64) for n in
+                ("assemble_cells_launches", "assemble_faces_launches", "scatter_launches",
+                 "spmv_launches", "cg_vector_launches", "update_launches", "halo_launches")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    """Load libgraftfem.so (built in-tree by build.build_cuda()). No fallback."""
+    global _lib
+    if _lib is None:
+        path = build.LIB_CUDA
+        if not os.path.exists(path):
+            raise ImportError(
+                "libgraftfem.so is missing (%s). Build it with `python -m dealii_adapter_b200.build` "
+                "or __graft_entry__.build(); there is no CPU fallback." % path)
+        L = C.CDLL(path)
+        vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+        L.gf_create.argtypes = [C.POINTER(GfDesc), C.POINTER(vp)]
+        L.gf_destroy.argtypes = [vp]
+        L.gf_destroy.restype = None
+        L.gf_last_error.argtypes = [vp]
+        L.gf_last_error.restype = C.c_char_p
+        L.gf_set_option.argtypes = [vp, i32, i64]
+        L.gf_comm_unique_id.argtypes = [vp]
+        L.gf_comm_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
+        L.gf_comm_destroy.argtypes = [vp]
+        L.gf_comm_destroy.restype = None
+        L.gf_set_traction.argtypes = [vp, vp]
+        L.gf_get_interface_displacement.argtypes = [vp, vp]
+        for n in ("gf_state_save", "gf_state_restore", "gf_nl_begin_step", "gf_nl_end_step",
+                  "gf_lin_assemble_once", "gf_synchronize"):
+            getattr(L, n).argtypes = [vp]
+        L.gf_nl_newton_assemble.argtypes = [vp, C.POINTER(dbl)]
+        L.gf_nl_newton_solve.argtypes = [vp, i32, dbl, dbl, C.POINTER(C.c_uint32), C.POINTER(dbl),
+                                         C.POINTER(dbl)]
+        L.gf_lin_step.argtypes = [vp, i32, dbl, C.POINTER(C.c_uint32), C.POINTER(dbl)]
+        L.gf_get_vector.argtypes = [vp, i32, vp]
+        L.gf_set_vector.argtypes = [vp, i32, vp]
+        L.gf_nnz.argtypes = [vp]
+        L.gf_nnz.restype = i64
+        L.gf_export_csr.argtypes = [vp, i32, vp, vp, vp]
+        L.gf_spmv.argtypes = [vp, i32, i32, i32]
+        L.gf_spmv_timed.argtypes = [vp, i32, i32, C.POINTER(dbl), C.POINTER(dbl)]
+        L.gf_profile_get.argtypes = [vp, C.POINTER(GfProfile), i32]
+        _lib = L
+    return _lib
+
+
+class Comm:
+    """NCCL communicator handle for the partitioned path; the 128-byte id is broadcast by the host
+    (torch.distributed in bench.py / tests)."""
+
+    def __init__(self, unique_id: bytes, rank: int, n_ranks: int, device: int):
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        rc = lib().gf_comm_create(buf, rank, n_ranks, device, C.byref(h))
+        if rc != GF_OK:
+            raise GraftError(rc, "gf_comm_create failed")
+        self._h = h
+        self.rank, self.n_ranks = rank, n_ranks
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = lib().gf_comm_unique_id(buf)
+        if rc != GF_OK:
+            raise GraftError(rc, "gf_comm_unique_id failed")
+        return bytes(buf)
+
+    def close(self):
+        if self._h:
+            lib().gf_comm_destroy(self._h)
+            self._h = None
+
+
+class Handle:
+    """Owns one gf_handle. `problem` is a dealii_adapter_b200.problem.Problem; `partition` an
+    optional mesh.MeshPartition with `comm`."""
+
+    def __init__(self, problem, device=0, partition=None, comm=None):
+        L = lib()
+        p = problem.params
+        self.problem = problem
+        self.partition = partition
+        d = GfDesc()
+        d.dim, d.degree, d.model = problem.dim, problem.degree, problem.model
+        if partition is None:
+            cell_dofs = problem.mesh.cell_dofs
+            cell_vertices = problem.mesh.cell_vertices
+            constrained = problem.constrained
+            iface_cell, iface_face_no = problem.iface_cell, problem.iface_face_no
+            iface_dofs = problem.iface_dofs
+            n_dofs = n_owned = problem.n_dofs
+            n_cells = problem.mesh.n_cells
+            self.local_to_global = None
+        else:
+            l2g = partition.local_to_global
+            g2l = -np.ones(problem.n_dofs, dtype=np.int64)
+            g2l[l2g] = np.arange(len(l2g))
+            cell_dofs, cell_vertices = partition.cell_dofs, partition.cell_vertices
+            constrained = problem.constrained[l2g]
+            gc2l = -np.ones(problem.mesh.n_cells, dtype=np.int64)
+            gc2l[partition.local_cell_global] = np.arange(partition.n_local_cells)
+            keep = gc2l[problem.iface_cell] >= 0
+            iface_cell = gc2l[problem.iface_cell][keep].astype(np.int32)
+            iface_face_no = problem.iface_face_no[keep]
+            # interface nodes visible on this rank, in the caller's (global) IndexSet order
+            vis = g2l[problem.iface_dofs[0]] >= 0
+            iface_dofs = g2l[problem.iface_dofs[:, vis]].astype(np.int32)
+            self.iface_visible = vis
+            n_dofs, n_owned = partition.n_local_dofs, partition.n_owned_dofs
+            n_cells = partition.n_local_cells
+            self.local_to_global = l2g
+        self.n_dofs, self.n_owned = int(n_dofs), int(n_owned)
+        self.n_iface_nodes = int(iface_dofs.shape[1])
+        keep_alive = [np.ascontiguousarray(cell_dofs, dtype=np.int32),
+                      np.ascontiguousarray(cell_vertices, dtype=np.float64),
+                      np.ascontiguousarray(constrained, dtype=np.uint8),
+                      np.ascontiguousarray(iface_cell, dtype=np.int32),
+                      np.ascontiguousarray(iface_face_no, dtype=np.int32),
+                      np.ascontiguousarray(iface_dofs, dtype=np.int32)]
+        d.n_dofs, d.n_cells = n_dofs, n_cells
+        d.cell_dofs, d.cell_vertices, d.constrained = (a.ctypes.data for a in keep_alive[:3])
+        d.n_iface_faces = len(keep_alive[3])
+        d.iface_cell, d.iface_face_no = keep_alive[3].ctypes.data, keep_alive[4].ctypes.data
+        d.n_iface_nodes = self.n_iface_nodes
+        d.iface_dofs = keep_alive[5].ctypes.data
+        d.mu, d.nu, d.rho = p.mu, p.nu, p.rho
+        d.body_force = (C.c_double * 3)(*p.body_force)
+        d.beta, d.gamma, d.theta, d.delta_t = p.beta, p.gamma, p.theta, p.delta_t
+        d.data_consistent = 1 if p.data_consistent else 0
+        d.device = device
+        d.n_owned_dofs = n_owned
+        if partition is not None and comm is not None:
+            d.comm = comm._h
+            d.n_neighbors = len(partition.nbr_rank)
+            keep_alive += [np.ascontiguousarray(partition.nbr_rank, dtype=np.int32),
+                           np.ascontiguousarray(partition.send_ptr, dtype=np.int64),
+                           np.ascontiguousarray(partition.send_dofs, dtype=np.int32),
+                           np.ascontiguousarray(partition.recv_ptr, dtype=np.int64),
+                           np.ascontiguousarray(partition.recv_dofs, dtype=np.int32)]
+            d.nbr_rank, d.send_ptr, d.send_dofs, d.recv_ptr, d.recv_dofs = (
+                a.ctypes.data for a in keep_alive[6:11])
+        h = C.c_void_p()
+        rc = L.gf_create(C.byref(d), C.byref(h))
+        if rc != GF_OK:
+            raise GraftError(rc, L.gf_last_error(None).decode())
+        self._h = h
+
+    # -- plumbing
+    def _check(self, rc):
+        if rc != GF_OK:
+            raise GraftError(rc, lib().gf_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().gf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_option(self, opt, value):
+        self._check(lib().gf_set_option(self._h, opt, int(value)))
+
+    # -- Adapter bodies
+    def set_traction(self, iface_buf):
+        buf = np.ascontiguousarray(iface_buf, dtype=np.float64)
+        assert buf.size == self.n_iface_nodes * self.problem.dim
+        self._check(lib().gf_set_traction(self._h, buf.ctypes.data))
+
+    def get_interface_displacement(self):
+        out = np.zeros(self.n_iface_nodes * self.problem.dim)
+        self._check(lib().gf_get_interface_displacement(self._h, out.ctypes.data))
+        return out
+
+    def state_save(self):
+        self._check(lib().gf_state_save(self._h))
+
+    def state_restore(self):
+        self._check(lib().gf_state_restore(self._h))
+
+    # -- Solid
+    def nl_begin_step(self):
+        self._check(lib().gf_nl_begin_step(self._h))
+
+    def nl_newton_assemble(self):
+        r = C.c_double()
+        self._check(lib().gf_nl_newton_assemble(self._h, C.byref(r)))
+        return r.value
+
+    def nl_newton_solve(self, type_lin, tol_lin, max_iterations_lin):
+        it, res, upd = C.c_uint32(), C.c_double(), C.c_double()
+        self._check(lib().gf_nl_newton_solve(self._h, type_lin, tol_lin, max_iterations_lin,
+                                             C.byref(it), C.byref(res), C.byref(upd)))
+        return it.value, res.value, upd.value
+
+    def nl_end_step(self):
+        self._check(lib().gf_nl_end_step(self._h))
+
+    # -- ElastoDynamics
+    def lin_assemble_once(self):
+        self._check(lib().gf_lin_assemble_once(self._h))
+
+    def lin_step(self, type_lin, max_iterations_lin):
+        it, res = C.c_uint32(), C.c_double()
+        self._check(lib().gf_lin_step(self._h, type_lin, max_iterations_lin, C.byref(it),
+                                      C.byref(res)))
+        return it.value, res.value
+
+    # -- data access
+    def get_vector(self, which):
+        out = np.zeros(self.n_dofs)
+        self._check(lib().gf_get_vector(self._h, which, out.ctypes.data))
+        return out
+
+    def set_vector(self, which, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        assert v.shape == (self.n_dofs,)
+        self._check(lib().gf_set_vector(self._h, which, v.ctypes.data))
+
+    def nnz(self):
+        return lib().gf_nnz(self._h)
+
+    def export_csr(self, which):
+        nnz = self.nnz()
+        rowptr = np.zeros(self.n_owned + 1, dtype=np.int64)
+        col = np.zeros(nnz, dtype=np.int32)
+        val = np.zeros(nnz)
+        self._check(lib().gf_export_csr(self._h, which, rowptr.ctypes.data, col.ctypes.data,
+                                        val.ctypes.data))
+        return rowptr, col, val
+
+    def spmv(self, which_matrix, which_x, which_y):
+        self._check(lib().gf_spmv(self._h, which_matrix, which_x, which_y))
+
+    def spmv_timed(self, which_matrix, n_reps):
+        ms, nbytes = C.c_double(), C.c_double()
+        self._check(lib().gf_spmv_timed(self._h, which_matrix, n_reps, C.byref(ms), C.byref(nbytes)))
+        return ms.value, nbytes.value
+
+    def profile(self, reset=False):
+        p = GfProfile()
+        self._check(lib().gf_profile_get(self._h, C.byref(p), 1 if reset else 0))
+        return p.as_dict()
+
+    def synchronize(self):
+        self._check(lib().gf_synchronize(self._h))

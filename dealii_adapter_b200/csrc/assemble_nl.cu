@@ -1,0 +1,595 @@
+// K1: batched neo-Hookean tangent + residual per cell; K2: interface traction (Neumann) term.
+//
+// Replaces Assembler<dim,double>::assemble_system_tangent_residual_one_cell
+// (nonlinear_elasticity.cc:872-1036), the material closed forms
+// (compressible_neo_hook_material.h:62-138) and assemble_neumann_contribution_one_cell
+// (nonlinear_elasticity.cc:791-859). Output is the element matrix K_e (row-major dpc x dpc) and
+// r_e per cell; the constrained, deterministic scatter is scatter.cu.
+//
+// Per cell (one CTA, persistent grid-stride loop; tables staged once in shared memory):
+//   phase A  one thread per quadrature point: H = grad u, F, J, F^-1, b_bar, tau, Jc (Voigt D),
+//            all scaled by JxW                                              (:902-934,:958-961)
+//   phase B  one thread per (q, node a): spatial gradient g_a = grad_X N_a F^-1 (:946-947),
+//            T_a = B_a^T (JxW D)  (dim x V) and t_a = JxW tau g_a           (pre-contraction the
+//            reference repeats per (i,j) at :1011-1012)
+//   phase C  warp <-> group of 3 nodes a, lane <-> node b: K_ab += T_a B_b (material, :1011),
+//            S_ab += t_a . g_b (geometric, :1018-1019); FP64 FMA pipe bound
+//   end      K_ab diag += S_ab + rho alpha_1 detJ M_ab (mass, :1020-1021); r_e from t_a, body
+//            force and inertia (:984-995)
+// Algorithmic flops / q-point (3D Q2): 729 node pairs * 30 FMA = 43.7 kflop (full matrix).
+#include "gf_context.h"
+#include "kernel_utils.cuh"
+
+namespace gf
+{
+  namespace
+  {
+    template <int DIM, int P>
+    struct NLCfg
+    {
+      static constexpr int NPC  = ipow(P + 1, DIM);
+      static constexpr int DPC  = NPC * DIM;
+      static constexpr int NQ1  = P + 2;
+      static constexpr int NQ   = ipow(NQ1, DIM);
+      static constexpr int NQF  = NQ / NQ1;
+      static constexpr int VO   = DIM * (DIM + 1) / 2;
+      static constexpr int TS   = (DIM * VO + DIM + 1) & ~1; // T (DIM x VO) + t (DIM), even
+      static constexpr int NPCP = NPC <= 4 ? 4 : (NPC <= 8 ? 8 : (NPC <= 16 ? 16 : 32));
+      static constexpr int NSUB = 32 / NPCP;
+      static constexpr int AT   = 3;                   // nodes a per (warp, sub) unit
+      static constexpr int NG   = (NPC + AT - 1) / AT; // a-groups
+      static constexpr int NW   = (DIM == 3 && P == 2) ? 9 : 4;
+      static constexpr int NT   = NW * 32;
+      static constexpr int QC   = (DIM == 3 && P == 2) ? 16 : NQ; // q-points per chunk
+      static constexpr int QS   = DIM * DIM + VO * VO + VO + DIM + 2; // per-q scalars
+      static_assert(NW * NSUB >= NG, "every a-group needs its own unit");
+      static_assert(NQ % QC == 0, "chunking");
+      static_assert(NT >= NQ && NT >= DPC, "thread count");
+      // shared memory (doubles)
+      static constexpr int OFF_N   = 0;
+      static constexpr int OFF_DN  = OFF_N + NQ * NPC;
+      static constexpr int OFF_U   = OFF_DN + NQ * NPC * DIM;
+      static constexpr int OFF_ACC = OFF_U + DPC;
+      static constexpr int OFF_Q   = OFF_ACC + DPC;          // [NQ][QS]
+      static constexpr int OFF_T   = OFF_Q + NQ * QS;        // [QC][NPC][TS]
+      static constexpr int OFF_G   = OFF_T + QC * NPC * TS;  // [QC][DIM][NPCP]
+      static constexpr int SMEM_D  = OFF_G + QC * DIM * NPCP;
+      static constexpr size_t SMEM_BYTES = size_t(SMEM_D) * sizeof(double);
+      // offsets inside a per-q record
+      static constexpr int Q_C   = 0;                 // C = Jinv * Finv            [DIM*DIM]
+      static constexpr int Q_D   = Q_C + DIM * DIM;   // JxW * Jc (Voigt)           [VO*VO]
+      static constexpr int Q_TAU = Q_D + VO * VO;     // JxW * tau (Voigt)          [VO]
+      static constexpr int Q_A   = Q_TAU + VO;        // rho * JxW * sumN * acc     [DIM]
+      static constexpr int Q_W   = Q_A + DIM;         // JxW
+      static constexpr int Q_X   = Q_W + 1;           // spare
+    };
+
+    struct NLParams
+    {
+      double kappa, mu, rho, alpha_1;
+      double body_force[3];
+    };
+
+    // compressible_neo_hook_material.h:37-49 in Voigt storage (SymmetricTensor order)
+    template <int DIM>
+    __device__ __forceinline__ void neo_hooke(const double kappa, const double mu, const double J,
+                                              const double (&bbar)[DIM * (DIM + 1) / 2],
+                                              double (&tau)[DIM * (DIM + 1) / 2],
+                                              double (&D)[DIM * (DIM + 1) / 2][DIM * (DIM + 1) / 2])
+    {
+      constexpr int VO    = DIM * (DIM + 1) / 2;
+      const double  dPsi  = (kappa / 2.0) * (J - 1.0 / J);         // :74-78
+      const double  d2Psi = (kappa / 2.0) * (1.0 + 1.0 / (J * J)); // :100-104
+      // tau_bar = 2 c_1 b_bar = mu b_bar ; tau_iso = dev_P : tau_bar  (:87-98)
+      double tr = 0;
+#pragma unroll
+      for (int i = 0; i < DIM; ++i)
+        tr += mu * bbar[i];
+      double tau_iso[VO];
+#pragma unroll
+      for (int k = 0; k < VO; ++k)
+        tau_iso[k] = mu * bbar[k] - (k < DIM ? tr / DIM : 0.0);
+      const double tv = dPsi * J; // tau_vol = dPsi J I  (:80-85)
+#pragma unroll
+      for (int k = 0; k < VO; ++k)
+        tau[k] = tau_iso[k] + (k < DIM ? tv : 0.0);
+      // Jc_vol = J[(dPsi + J d2Psi) IxI - 2 dPsi S]  (:106-114)
+      // Jc_iso = (2/dim) tr(tau_bar) dev_P - (2/dim)(tau_iso x I + I x tau_iso)  (:116-133)
+      const double c_IxI = J * (dPsi + J * d2Psi) - (2.0 / DIM) * tr / DIM;
+      const double c_S   = -J * (2.0 * dPsi) + (2.0 / DIM) * tr;
+#pragma unroll
+      for (int k = 0; k < VO; ++k)
+#pragma unroll
+        for (int l = 0; l < VO; ++l)
+          {
+            double v = 0;
+            if (k < DIM && l < DIM)
+              v += c_IxI;
+            if (k == l)
+              v += (k < DIM ? 1.0 : 0.5) * c_S;
+            if (l < DIM)
+              v -= (2.0 / DIM) * tau_iso[k];
+            if (k < DIM)
+              v -= (2.0 / DIM) * tau_iso[l];
+            D[k][l] = v;
+          }
+    }
+
+    template <int DIM, int P>
+    __global__ void __launch_bounds__(NLCfg<DIM, P>::NT, 1)
+      nl_cells_kernel(const int64_t c0, const int64_t c1, const int32_t *__restrict__ cell_nodes,
+                      const double *__restrict__ geom, const double *__restrict__ u_total,
+                      const double *__restrict__ accel, const double *__restrict__ tabN,
+                      const double *__restrict__ tabdN, const double *__restrict__ tabw,
+                      const double *__restrict__ Mref, const NLParams prm,
+                      double *__restrict__ ke_buf, double *__restrict__ re_buf, int *err_flag)
+    {
+      using C = NLCfg<DIM, P>;
+      constexpr int NPC = C::NPC, DPC = C::DPC, NQ = C::NQ, VO = C::VO, TS = C::TS, QC = C::QC,
+                    QS = C::QS, NPCP = C::NPCP, AT = C::AT;
+      extern __shared__ __align__(16) double sm[];
+      double *sN = sm + C::OFF_N, *sdN = sm + C::OFF_DN, *su = sm + C::OFF_U,
+             *sacc = sm + C::OFF_ACC, *sQ = sm + C::OFF_Q, *sT = sm + C::OFF_T,
+             *sG = sm + C::OFF_G;
+      const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+      for (int i = tid; i < NQ * NPC; i += C::NT)
+        sN[i] = tabN[i];
+      for (int i = tid; i < NQ * NPC * DIM; i += C::NT)
+        sdN[i] = tabdN[i];
+      // unit = (warp, sub-warp); each unit owns one group of AT nodes a; lane-in-sub = node b
+      const int  sub = lane / NPCP, b = lane % NPCP;
+      const int  unit = warp * C::NSUB + sub;
+      const bool unit_active = unit < C::NG;
+      const int  a_base = unit_active ? unit * AT : 0;
+      const int  bb = b < NPC ? b : NPC - 1; // clamped for loads; results of b >= NPC discarded
+
+      for (int64_t cell = c0 + blockIdx.x; cell < c1; cell += gridDim.x)
+        {
+          __syncthreads(); // previous cell fully consumed
+          const double *gm = geom + cell * (DIM * DIM + 1);
+          double        Jinv[DIM][DIM];
+#pragma unroll
+          for (int i = 0; i < DIM; ++i)
+#pragma unroll
+            for (int j = 0; j < DIM; ++j)
+              Jinv[i][j] = gm[i * DIM + j];
+          const double detJ = gm[DIM * DIM];
+          if (tid < DPC)
+            {
+              const int32_t node = cell_nodes[cell * NPC + tid / DIM];
+              su[tid]            = u_total[int64_t(node) * DIM + tid % DIM];
+              sacc[tid]          = accel[int64_t(node) * DIM + tid % DIM];
+            }
+          __syncthreads();
+
+          // ---------------- phase A: kinematics + material per quadrature point -----------------
+          if (tid < NQ)
+            {
+              const int q = tid;
+              double    Hr[DIM][DIM], acc[DIM];
+              double    sumN = 0;
+#pragma unroll
+              for (int i = 0; i < DIM; ++i)
+                {
+                  acc[i] = 0;
+#pragma unroll
+                  for (int j = 0; j < DIM; ++j)
+                    Hr[i][j] = 0;
+                }
+              for (int a = 0; a < NPC; ++a)
+                {
+                  const double Na = sN[q * NPC + a];
+                  sumN += Na;
+#pragma unroll
+                  for (int cc = 0; cc < DIM; ++cc)
+                    {
+                      const double ua = su[a * DIM + cc];
+                      acc[cc] += sacc[a * DIM + cc] * Na;
+#pragma unroll
+                      for (int e = 0; e < DIM; ++e)
+                        Hr[cc][e] += ua * sdN[(q * NPC + a) * DIM + e];
+                    }
+                }
+              double F[DIM][DIM];
+#pragma unroll
+              for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                for (int j = 0; j < DIM; ++j)
+                  {
+                    double h = 0;
+#pragma unroll
+                    for (int e = 0; e < DIM; ++e)
+                      h += Hr[i][e] * Jinv[e][j];
+                    F[i][j] = (i == j ? 1.0 : 0.0) + h; // Kinematics::F :927
+                  }
+              const double detF = det<DIM>(F); // :929
+              if (!(detF > 0.0))
+                atomicExch(err_flag, 1); // Assert :935
+              double Finv[DIM][DIM];
+              inverse<DIM>(F, detF, Finv); // :934
+              const double s = pow(detF, -1.0 / DIM); // Kinematics::F_iso :930
+              double       bbar[VO];                  // Kinematics::b :932
+#pragma unroll
+              for (int k = 0; k < VO; ++k)
+                {
+                  const int i = voigt_i<DIM>(k), j = voigt_j<DIM>(k);
+                  double    v = 0;
+#pragma unroll
+                  for (int e = 0; e < DIM; ++e)
+                    v += (s * F[i][e]) * (s * F[j][e]);
+                  bbar[k] = v;
+                }
+              double tau[VO], D[VO][VO];
+              neo_hooke<DIM>(prm.kappa, prm.mu, detF, bbar, tau, D); // :958-961
+              const double JxW = detJ * tabw[q];
+              double *     rec = sQ + q * QS;
+#pragma unroll
+              for (int e = 0; e < DIM; ++e)
+#pragma unroll
+                for (int l = 0; l < DIM; ++l)
+                  {
+                    double v = 0;
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d)
+                      v += Jinv[e][d] * Finv[d][l];
+                    rec[C::Q_C + e * DIM + l] = v;
+                  }
+#pragma unroll
+              for (int k = 0; k < VO; ++k)
+                {
+                  rec[C::Q_TAU + k] = tau[k] * JxW;
+#pragma unroll
+                  for (int l = 0; l < VO; ++l)
+                    rec[C::Q_D + k * VO + l] = D[k][l] * JxW;
+                }
+#pragma unroll
+              for (int cc = 0; cc < DIM; ++cc)
+                rec[C::Q_A + cc] = prm.rho * sumN * acc[cc] * JxW; // :993-995 summed over j
+              rec[C::Q_W] = JxW;
+            }
+          __syncthreads();
+
+          double Kacc[AT][DIM][DIM], Sacc[AT];
+#pragma unroll
+          for (int ai = 0; ai < AT; ++ai)
+            {
+              Sacc[ai] = 0;
+#pragma unroll
+              for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                for (int j = 0; j < DIM; ++j)
+                  Kacc[ai][i][j] = 0;
+            }
+          double r_i = 0; // residual entry of local dof tid (tid < DPC)
+
+          for (int qc = 0; qc < NQ; qc += QC)
+            {
+              // -------------- phase B: g_a, T_a = B_a^T (JxW D), t_a = JxW tau g_a -------------
+              for (int item = tid; item < QC * NPC; item += C::NT)
+                {
+                  const int     ql = item / NPC, a = item % NPC, q = qc + ql;
+                  const double *rec = sQ + q * QS;
+                  double        g[DIM];
+#pragma unroll
+                  for (int l = 0; l < DIM; ++l)
+                    {
+                      double v = 0;
+#pragma unroll
+                      for (int e = 0; e < DIM; ++e)
+                        v += sdN[(q * NPC + a) * DIM + e] * rec[C::Q_C + e * DIM + l];
+                      g[l] = v;
+                      sG[(ql * DIM + l) * NPCP + a] = v;
+                    }
+                  double *T = sT + (ql * NPC + a) * TS;
+#pragma unroll
+                  for (int ci = 0; ci < DIM; ++ci)
+                    {
+                      // engineering strain of dof (a,ci): eps_(ci,l) = g[l]
+#pragma unroll
+                      for (int k = 0; k < VO; ++k)
+                        {
+                          double v = 0;
+#pragma unroll
+                          for (int l = 0; l < DIM; ++l)
+                            v += g[l] * rec[C::Q_D + voigt_index<DIM>(ci, l) * VO + k];
+                          T[ci * VO + k] = v;
+                        }
+                      double t = 0;
+#pragma unroll
+                      for (int l = 0; l < DIM; ++l)
+                        t += rec[C::Q_TAU + voigt_index<DIM>(ci, l)] * g[l];
+                      T[DIM * VO + ci] = t;
+                    }
+                }
+              __syncthreads();
+              // -------------- residual (:984-995), fixed q order --------------------------------
+              if (tid < DPC)
+                {
+                  const int a = tid / DIM, cc = tid % DIM;
+                  for (int ql = 0; ql < QC; ++ql)
+                    {
+                      const int     q   = qc + ql;
+                      const double *rec = sQ + q * QS;
+                      const double  Na  = sN[q * NPC + a];
+                      r_i -= (sT[(ql * NPC + a) * TS + DIM * VO + cc] -
+                              prm.body_force[cc] * prm.rho * Na * rec[C::Q_W]);
+                      r_i -= Na * rec[C::Q_A + cc];
+                    }
+                }
+              // -------------- phase C: K_ab += T_a B_b ; S_ab += t_a . g_b ----------------------
+              if (unit_active)
+                {
+#pragma unroll 2
+                  for (int ql = 0; ql < QC; ++ql)
+                    {
+                      double gb[DIM];
+#pragma unroll
+                      for (int l = 0; l < DIM; ++l)
+                        gb[l] = sG[(ql * DIM + l) * NPCP + bb];
+#pragma unroll
+                      for (int ai = 0; ai < AT; ++ai)
+                        {
+                          const int     a = min(a_base + ai, NPC - 1);
+                          const double *T = sT + (ql * NPC + a) * TS;
+                          double        Tl[TS];
+#pragma unroll
+                          for (int k = 0; k < TS; k += 2)
+                            {
+                              const double2 v = *reinterpret_cast<const double2 *>(T + k);
+                              Tl[k]           = v.x;
+                              Tl[k + 1]       = v.y;
+                            }
+#pragma unroll
+                          for (int ci = 0; ci < DIM; ++ci)
+#pragma unroll
+                            for (int cj = 0; cj < DIM; ++cj)
+                              {
+                                double v = Kacc[ai][ci][cj];
+#pragma unroll
+                                for (int l = 0; l < DIM; ++l)
+                                  v = fma(Tl[ci * VO + voigt_index<DIM>(cj, l)], gb[l], v);
+                                Kacc[ai][ci][cj] = v;
+                              }
+                          double sv = Sacc[ai];
+#pragma unroll
+                          for (int l = 0; l < DIM; ++l)
+                            sv = fma(Tl[DIM * VO + l], gb[l], sv);
+                          Sacc[ai] = sv;
+                        }
+                    }
+                }
+              __syncthreads();
+            }
+
+          // ---------------- write K_e (row-major) and r_e -----------------------------------------
+          double *ke = ke_buf + (cell - c0) * int64_t(DPC) * DPC;
+          if (unit_active && b < NPC)
+            {
+              const double mfac = prm.rho * prm.alpha_1 * detJ; // :1020-1021
+#pragma unroll
+              for (int ai = 0; ai < AT; ++ai)
+                {
+                  const int a = a_base + ai;
+                  if (a < NPC)
+                    {
+                      const double dd = Sacc[ai] + mfac * Mref[a * NPC + b];
+#pragma unroll
+                      for (int ci = 0; ci < DIM; ++ci)
+#pragma unroll
+                        for (int cj = 0; cj < DIM; ++cj)
+                          ke[(a * DIM + ci) * DPC + b * DIM + cj] =
+                            Kacc[ai][ci][cj] + (ci == cj ? dd : 0.0);
+                    }
+                }
+            }
+          if (tid < DPC)
+            re_buf[cell * DPC + tid] = r_i;
+        }
+    }
+
+    // K2: one CTA per cell that owns interface faces; faces in ascending face number
+    // (cell->face_iterators(), :804). Adds into r_e after the cell kernel (:755-756 order).
+    template <int DIM, int P>
+    __global__ void nl_faces_kernel(const int n_iface_cells, const int32_t *__restrict__ cell_list,
+                                    const int32_t *__restrict__ face_ptr,
+                                    const int32_t *__restrict__ face_no,
+                                    const int32_t *__restrict__ cell_nodes,
+                                    const double *__restrict__ geom,
+                                    const double *__restrict__ u_total,
+                                    const double *__restrict__ stress,
+                                    const double *__restrict__ tabdN,
+                                    const double *__restrict__ tabNf,
+                                    const double *__restrict__ tabwf, double *__restrict__ re_buf,
+                                    int *err_flag)
+    {
+      using C = NLCfg<DIM, P>;
+      constexpr int NPC = C::NPC, DPC = C::DPC, NQF = C::NQF;
+      __shared__ double su[DPC], ss[DPC];
+      __shared__ double sfac[NQF];          // ||det F F^-T N|| at "face" q (cell q index!)
+      __shared__ double strac[NQF][DIM];    // local_stress(q) * factor * JxW_f
+      const int ic = blockIdx.x;
+      if (ic >= n_iface_cells)
+        return;
+      const int     tid  = threadIdx.x;
+      const int64_t cell = cell_list[ic];
+      const double *gm   = geom + cell * (DIM * DIM + 1);
+      double        Jinv[DIM][DIM];
+#pragma unroll
+      for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int j = 0; j < DIM; ++j)
+          Jinv[i][j] = gm[i * DIM + j];
+      const double detJ = gm[DIM * DIM];
+      if (tid < DPC)
+        {
+          const int32_t node = cell_nodes[cell * NPC + tid / DIM];
+          su[tid]            = u_total[int64_t(node) * DIM + tid % DIM];
+          ss[tid]            = stress[int64_t(node) * DIM + tid % DIM];
+        }
+      __syncthreads();
+      double r_add = 0;
+      for (int fi = face_ptr[ic]; fi < face_ptr[ic + 1]; ++fi)
+        {
+          const int face = face_no[fi];
+          const int fd = face / 2;
+          // n da = det(J) J^-T n_ref dA_ref  (affine cell: constant per face)
+          double nrm[DIM], len = 0;
+#pragma unroll
+          for (int i = 0; i < DIM; ++i)
+            {
+              nrm[i] = detJ * Jinv[fd][i] * ((face & 1) ? 1.0 : -1.0);
+              len += nrm[i] * nrm[i];
+            }
+          len = sqrt(len);
+#pragma unroll
+          for (int i = 0; i < DIM; ++i)
+            nrm[i] /= len;
+          if (tid < NQF)
+            {
+              const int q = tid; // :825-827 — CELL quadrature gradient at index f_q_point
+              double    Hr[DIM][DIM];
+#pragma unroll
+              for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                for (int j = 0; j < DIM; ++j)
+                  Hr[i][j] = 0;
+              for (int a = 0; a < NPC; ++a)
+#pragma unroll
+                for (int cc = 0; cc < DIM; ++cc)
+#pragma unroll
+                  for (int e = 0; e < DIM; ++e)
+                    Hr[cc][e] += su[a * DIM + cc] * tabdN[(q * NPC + a) * DIM + e];
+              double F[DIM][DIM];
+#pragma unroll
+              for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                for (int j = 0; j < DIM; ++j)
+                  {
+                    double h = 0;
+#pragma unroll
+                    for (int e = 0; e < DIM; ++e)
+                      h += Hr[i][e] * Jinv[e][j];
+                    F[i][j] = (i == j ? 1.0 : 0.0) + h;
+                  }
+              const double detF = det<DIM>(F);
+              if (!(detF > 0.0))
+                atomicExch(err_flag, 1);
+              double Finv[DIM][DIM];
+              inverse<DIM>(F, detF, Finv);
+              // n_star = det F F^-T N  (:831-833)
+              double n2 = 0;
+#pragma unroll
+              for (int i = 0; i < DIM; ++i)
+                {
+                  double v = 0;
+#pragma unroll
+                  for (int j = 0; j < DIM; ++j)
+                    v += (detF * Finv[j][i]) * nrm[j];
+                  n2 += v * v;
+                }
+              const double fac = sqrt(n2);
+              // local_stress(q) = sum_k N_k(face q) sigma_k (:815-816)
+              double t[DIM];
+#pragma unroll
+              for (int cc = 0; cc < DIM; ++cc)
+                t[cc] = 0;
+              for (int a = 0; a < NPC; ++a)
+                {
+                  const double Na = tabNf[(face * NQF + q) * NPC + a];
+#pragma unroll
+                  for (int cc = 0; cc < DIM; ++cc)
+                    t[cc] += ss[a * DIM + cc] * Na;
+                }
+              sfac[q] = len * tabwf[q]; // JxW on the face
+#pragma unroll
+              for (int cc = 0; cc < DIM; ++cc)
+                strac[q][cc] = t[cc] * fac; // referential_stress :836-837
+            }
+          __syncthreads();
+          if (tid < DPC)
+            {
+              const int a = tid / DIM, cc = tid % DIM;
+              for (int q = 0; q < NQF; ++q) // :853-854
+                r_add += (tabNf[(face * NQF + q) * NPC + a] * strac[q][cc]) * sfac[q];
+            }
+          __syncthreads();
+        }
+      if (tid < DPC)
+        re_buf[cell * DPC + tid] += r_add;
+    }
+
+    template <int DIM, int P>
+    void launch_cells_t(gf_context &c, const double *u_total, const double *accel, int64_t c0,
+                        int64_t c1)
+    {
+      using C = NLCfg<DIM, P>;
+      static bool configured = false;
+      if (!configured)
+        {
+          GF_CUDA_CHECK(cudaFuncSetAttribute(nl_cells_kernel<DIM, P>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             int(C::SMEM_BYTES)));
+          configured = true;
+        }
+      NLParams prm;
+      prm.kappa   = (2.0 * c.desc.mu * (1.0 + c.desc.nu)) / (3.0 * (1.0 - 2.0 * c.desc.nu));
+      prm.mu      = c.desc.mu;
+      prm.rho     = c.desc.rho;
+      prm.alpha_1 = 1. / (c.desc.beta * c.desc.delta_t * c.desc.delta_t);
+      for (int k = 0; k < 3; ++k)
+        prm.body_force[k] = c.desc.body_force[k];
+      int blocks_per_sm = 1;
+      GF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &blocks_per_sm, nl_cells_kernel<DIM, P>, C::NT, C::SMEM_BYTES));
+      const int64_t n    = c1 - c0;
+      const int     grid = int(std::min<int64_t>(n, int64_t(c.sm_count) * std::max(1, blocks_per_sm)));
+      if (grid <= 0)
+        return;
+      nl_cells_kernel<DIM, P><<<grid, C::NT, C::SMEM_BYTES, c.stream>>>(
+        c0, c1, c.cell_nodes.p, c.geom.p, u_total, accel, c.tables.N.p, c.tables.dN.p,
+        c.tables.w.p, c.tables.Mref.p, prm, c.ke_buf.p, c.re_buf.p, c.err_flag.p);
+      GF_CUDA_CHECK(cudaGetLastError());
+    }
+
+    template <int DIM, int P>
+    void launch_faces_t(gf_context &c, const double *u_total, const double *stress)
+    {
+      using C = NLCfg<DIM, P>;
+      if (c.n_iface_cells == 0)
+        return;
+      const int nt = ((C::DPC + 31) / 32) * 32;
+      nl_faces_kernel<DIM, P><<<unsigned(c.n_iface_cells), nt, 0, c.stream>>>(
+        int(c.n_iface_cells), c.iface_cell_list.p, c.iface_face_ptr.p, c.iface_face_no.p,
+        c.cell_nodes.p, c.geom.p, u_total, stress, c.tables.dN.p, c.tables.Nf.p, c.tables.wf.p,
+        c.re_buf.p, c.err_flag.p);
+      GF_CUDA_CHECK(cudaGetLastError());
+    }
+  } // namespace
+
+  void launch_nl_cells(gf_context &c, const double *u_total, const double *accel, int64_t c0,
+                       int64_t c1)
+  {
+    ProfScope ps(c, Profile::ASM_CELLS);
+    if (c.dim == 3 && c.p == 2)
+      launch_cells_t<3, 2>(c, u_total, accel, c0, c1);
+    else if (c.dim == 3 && c.p == 1)
+      launch_cells_t<3, 1>(c, u_total, accel, c0, c1);
+    else if (c.dim == 2 && c.p == 2)
+      launch_cells_t<2, 2>(c, u_total, accel, c0, c1);
+    else
+      launch_cells_t<2, 1>(c, u_total, accel, c0, c1);
+  }
+
+  void launch_nl_faces(gf_context &c, const double *u_total, const double *stress)
+  {
+    ProfScope ps(c, Profile::ASM_FACES);
+    if (c.dim == 3 && c.p == 2)
+      launch_faces_t<3, 2>(c, u_total, stress);
+    else if (c.dim == 3 && c.p == 1)
+      launch_faces_t<3, 1>(c, u_total, stress);
+    else if (c.dim == 2 && c.p == 2)
+      launch_faces_t<2, 2>(c, u_total, stress);
+    else
+      launch_faces_t<2, 1>(c, u_total, stress);
+  }
+} // namespace gf

@@ -1,0 +1,303 @@
+// Internal context of the sm_100a structural hot-path library (C-ABI: include/graft_fem.h).
+//
+// HBM layout (all FP64 / int32, internal numbering = node blocks: dof = node*dim + comp,
+// owned nodes first):
+//   vectors      [n_local_dofs]                      state / work vectors, AoS per node
+//   BSR matrix   brow_ptr[n_rows+1], bcol[nblocks]   block rows = owned nodes, dim x dim blocks
+//                val: per block row A with nb blocks: dim "scalar rows", each nb*dim doubles padded
+//                to an even count -> val[val_ptr[A] + r*stride + blk*dim + c]; the three scalar
+//                rows of a node share one column-index stream (4 B per dim*dim values)
+//   scatter map  for every block the ordered list (ascending cell) of element-matrix blocks
+//                that sum into it: deterministic, atomic-free (nonlinear_elasticity.cc:760-774)
+//   element buf  K_e row-major [chunk_cells][dpc][dpc], r_e [n_cells][dpc]
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "graft_fem.h"
+
+namespace gf
+{
+  struct Error
+  {
+    int         code;
+    std::string msg;
+  };
+
+#define GF_CUDA_CHECK(call)                                                                      \
+  do                                                                                             \
+    {                                                                                            \
+      cudaError_t err__ = (call);                                                                \
+      if (err__ != cudaSuccess)                                                                  \
+        throw gf::Error{GF_ERR_CUDA, std::string(#call) + " failed: " +                          \
+                                       cudaGetErrorString(err__) + " (" + __FILE__ + ":" +       \
+                                       std::to_string(__LINE__) + ")"};                          \
+    }                                                                                            \
+  while (0)
+
+#define GF_REQUIRE(cond, code, message)                                                          \
+  do                                                                                             \
+    {                                                                                            \
+      if (!(cond))                                                                               \
+        throw gf::Error{code, std::string(message)};                                             \
+    }                                                                                            \
+  while (0)
+
+  template <typename T>
+  struct DevBuf
+  {
+    T *    p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release()
+    {
+      if (p)
+        cudaFree(p);
+      p = nullptr;
+      n = 0;
+    }
+    void alloc(size_t count)
+    {
+      release();
+      n = count;
+      if (count)
+        GF_CUDA_CHECK(cudaMalloc((void **)&p, count * sizeof(T)));
+    }
+    void alloc_zero(size_t count, cudaStream_t s)
+    {
+      alloc(count);
+      if (count)
+        GF_CUDA_CHECK(cudaMemsetAsync(p, 0, count * sizeof(T), s));
+    }
+    void upload(const T *host, size_t count, cudaStream_t s)
+    {
+      alloc(count);
+      if (count)
+        {
+          GF_CUDA_CHECK(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+          GF_CUDA_CHECK(cudaStreamSynchronize(s));
+        }
+    }
+    void download(T *host, cudaStream_t s) const
+    {
+      if (n)
+        {
+          GF_CUDA_CHECK(cudaMemcpyAsync(host, p, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+          GF_CUDA_CHECK(cudaStreamSynchronize(s));
+        }
+    }
+  };
+
+  constexpr int MAX_VECTORS = 32;
+  constexpr int N_MATRICES  = 4;
+
+  // reference-cell tables (device) shared by all kernels
+  struct FETables
+  {
+    int dim = 0, p = 0, npc = 0, dpc = 0, nq1 = 0, nq = 0, nqf = 0, nv = 0;
+    DevBuf<double> N;    // [nq][npc]
+    DevBuf<double> dN;   // [nq][npc][dim]  unit-cell gradients
+    DevBuf<double> w;    // [nq]
+    DevBuf<double> Nf;   // [2*dim][nqf][npc]
+    DevBuf<double> wf;   // [nqf]
+    DevBuf<double> Mref; // [npc][npc] sum_q w N_a N_b
+    std::vector<double> hN, hdN, hw, hNf, hwf;
+    std::vector<int>    local_lex; // [npc][3]
+  };
+
+  // CG scalars living on the device; the host polls `status` every check interval
+  struct CGScalars
+  {
+    double rz, rz_old, pAp, rr, alpha, beta, res, tol, res0;
+    int    it, maxit, status; // status: 0 iterate, 1 success, 2 failure
+    int    pad;
+  };
+
+  struct BsrMatrix
+  {
+    DevBuf<double> val;
+    bool           valid = false;
+  };
+
+  struct Comm; // comm.cu
+
+  struct Profile
+  {
+    enum Kind
+    {
+      ASM_CELLS = 0,
+      ASM_FACES,
+      SCATTER,
+      SPMV,
+      CG_VEC,
+      UPDATE,
+      HALO,
+      N_KINDS
+    };
+    bool                     enabled = false;
+    double                   ms[N_KINDS]{};
+    int64_t                  launches[N_KINDS]{};
+    std::vector<cudaEvent_t> pool;
+    struct Pending
+    {
+      int kind;
+      int e0, e1;
+    };
+    std::vector<Pending> pending;
+    size_t               next_event = 0;
+  };
+} // namespace gf
+
+struct gf_comm_s
+{
+  void *nccl_comm = nullptr;
+  int   rank = 0, n_ranks = 1, device = 0;
+};
+
+struct gf_context
+{
+  gf_desc      desc{}; // pointers inside are NOT valid after gf_create
+  std::string  last_error;
+  cudaStream_t stream = nullptr;
+  int          dim = 0, p = 0, npc = 0, dpc = 0, model = 0, device = 0;
+  int          sm_count = 148;
+
+  int64_t n_ext_dofs = 0;   // caller-visible dofs (owned + ghost)
+  int64_t n_ext_owned = 0;  // caller owned dofs
+  int64_t n_nodes = 0;      // local nodes (owned + ghost)
+  int64_t n_owned_nodes = 0;
+  int64_t n_local = 0;      // n_nodes*dim
+  int64_t n_owned = 0;      // n_owned_nodes*dim
+  int64_t n_cells = 0;
+  int64_t n_blocks = 0;     // BSR blocks
+  int64_t n_val = 0;        // doubles per BSR value array
+  int64_t n_cand = 0;       // scatter sources
+  int64_t ke_chunk_cells = 0;
+  int64_t n_global_dofs_for_maxit = 0; // global matrix size m() used for CG max iterations
+
+  gf::FETables tables;
+
+  // numbering
+  gf::DevBuf<int32_t> perm_e2i; // [n_ext_dofs]
+  gf::DevBuf<int32_t> perm_i2e; // [n_local]
+  std::vector<int32_t> h_perm_e2i, h_perm_i2e;
+  gf::DevBuf<uint8_t> constrained; // [n_local] internal numbering
+  gf::DevBuf<int32_t> cell_nodes;  // [n_cells*npc]
+  gf::DevBuf<double>  geom;        // [n_cells*(dim*dim+1)] : J^{-1} row-major, det J
+  // node -> (cell, local node) adjacency, ascending cell
+  gf::DevBuf<int64_t> nc_ptr; // [n_nodes+1]
+  gf::DevBuf<int32_t> nc_src; // [n_cells*npc] = cell*npc + a
+  // BSR pattern
+  gf::DevBuf<int32_t>  brow_ptr; // [n_owned_nodes+1]
+  gf::DevBuf<int32_t>  bcol;     // [n_blocks]
+  gf::DevBuf<int64_t>  val_ptr;  // [n_owned_nodes+1]
+  gf::DevBuf<int64_t>  cand_ptr; // [n_owned_nodes+1]
+  gf::DevBuf<int32_t>  row_src;  // [n_cand] = (cell*npc + a)*npc + b
+  gf::DevBuf<uint16_t> src_off;  // [n_blocks] offset of the block's sources in its row list
+  gf::BsrMatrix        mat[gf::N_MATRICES];
+  gf::DevBuf<double>   mass_blk; // linear: scalar mass value per block (M = m_ab delta_cd)
+  gf::DevBuf<double>   dinv;     // [n_owned_nodes*dim*dim] preconditioner blocks
+  // interface
+  int64_t             n_iface_nodes = 0, n_iface_cells = 0;
+  gf::DevBuf<int32_t> iface_dofs_i;    // [dim*n_iface_nodes] internal dof ids
+  gf::DevBuf<int32_t> iface_cell_list; // [n_iface_cells] cells owning >=1 interface face
+  gf::DevBuf<int32_t> iface_face_ptr;  // [n_iface_cells+1]
+  gf::DevBuf<int32_t> iface_face_no;   // faces grouped by cell, ascending face number
+  gf::DevBuf<double>  iface_buf;       // [dim*n_iface_nodes] staging
+  // element buffers
+  gf::DevBuf<double> ke_buf; // [ke_chunk_cells*dpc*dpc]
+  gf::DevBuf<double> me_buf; // linear: scalar mass blocks [ke_chunk_cells*npc*npc]
+  gf::DevBuf<double> re_buf; // [n_cells*dpc]
+  // vectors (internal numbering)
+  gf::DevBuf<double> vec[gf::MAX_VECTORS];
+  gf::DevBuf<double> saved[6];
+  bool               has_saved = false;
+  gf::DevBuf<double> cg_r, cg_p, cg_v, cg_z, tmp0, tmp1;
+  gf::DevBuf<double> io_buf; // [n_ext_dofs] permutation staging
+  // reductions
+  gf::DevBuf<double>        partials; // [3*max_blocks]
+  gf::DevBuf<gf::CGScalars> cg_scalars;
+  gf::CGScalars *           h_scalars = nullptr; // pinned
+  gf::DevBuf<double>        norm_out;            // [4]
+  double *                  h_norm = nullptr;    // pinned [4]
+  gf::DevBuf<int>           err_flag;            // det F <= 0 detection
+  int *                     h_err = nullptr;     // pinned
+  int                       max_red_blocks = 0;
+
+  // options
+  int  precond        = GF_PRECOND_BLOCK_JACOBI;
+  int  cg_check_every = 32;
+  int  operator_kind  = 0;
+  bool lin_assembled  = false;
+
+  // multi-GPU
+  gf_comm             comm = nullptr;
+  std::vector<int>    nbr_rank;
+  std::vector<int64_t> send_ptr, recv_ptr;
+  gf::DevBuf<int32_t> send_idx, recv_idx; // internal dof ids
+  gf::DevBuf<double>  send_buf, recv_buf;
+
+  gf::Profile prof;
+};
+
+namespace gf
+{
+  // fe_tables.cu
+  void build_tables(gf_context &c);
+  // pattern.cu
+  void build_numbering_and_pattern(gf_context &c, const gf_desc &d);
+  // assemble_nl.cu
+  void launch_nl_cells(gf_context &c, const double *u_total, const double *accel, int64_t c0,
+                       int64_t c1);
+  void launch_nl_faces(gf_context &c, const double *u_total, const double *stress);
+  // assemble_lin.cu
+  void launch_lin_cells(gf_context &c, int64_t c0, int64_t c1);
+  void launch_lin_faces(gf_context &c, const double *stress, double *rhs_out);
+  void launch_body_force(gf_context &c, double *out);
+  // scatter.cu
+  void launch_scatter_matrix(gf_context &c, double *val, int64_t c0, int64_t c1, bool first,
+                             bool apply_constraints);
+  void launch_scatter_mass(gf_context &c, int64_t c0, int64_t c1, bool first);
+  void launch_scatter_rhs(gf_context &c, double *rhs, bool mask_constrained);
+  void launch_build_system_matrix(gf_context &c, double factor);
+  void launch_build_precond(gf_context &c, const double *val);
+  // spmv.cu
+  void launch_spmv(gf_context &c, const double *val, const double *x, double *y,
+                   double *dot_partials);
+  void launch_spmv_mass(gf_context &c, const double *x, double *y);
+  double spmv_bytes(const gf_context &c);
+  // cg.cu
+  int cg_solve(gf_context &c, const double *val, double *x, const double *b, double tol,
+               bool tol_relative_to_rhs, int64_t maxit, uint32_t *last_step, double *last_value);
+  // vector_ops.cu
+  void   vec_permute_in(gf_context &c, const double *ext_host, double *dst);
+  void   vec_permute_out(gf_context &c, const double *src, double *ext_host);
+  void   vec_zero(gf_context &c, double *v);
+  void   vec_copy(gf_context &c, double *dst, const double *src);
+  void   vec_axpby(gf_context &c, double *y, double a, const double *x, double b); // y = a x + b y
+  void   vec_lincomb3(gf_context &c, double *out, double a, const double *x, double b,
+                      const double *y, double cc, const double *z);
+  double vec_masked_norm(gf_context &c, const double *v, bool mask_constrained);
+  void   vec_zero_constrained(gf_context &c, double *v);
+  void   iface_scatter(gf_context &c, const double *host_buf, double *vec);
+  void   iface_gather(gf_context &c, const double *vec, double *host_buf);
+  // comm.cu
+  void halo_exchange(gf_context &c, double *v);
+  void allreduce_sum(gf_context &c, double *dev_values, int count);
+  // profile helpers
+  struct ProfScope
+  {
+    gf_context &c;
+    int         idx = -1;
+    ProfScope(gf_context &ctx, int kind);
+    ~ProfScope();
+  };
+  void profile_collect(gf_context &c);
+} // namespace gf

@@ -1,0 +1,97 @@
+// Small device helpers shared by the kernels: compile-time index maps of deal.II's
+// SymmetricTensor storage order (00,11,[22],01,[02,12]), dim x dim determinant / inverse,
+// warp and block reductions with a fixed (deterministic) combination order.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace gf
+{
+  __host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
+
+  template <int DIM>
+  __host__ __device__ constexpr int voigt_index(int i, int j)
+  {
+    return i == j ? i : (DIM == 2 ? 2 : i + j + 2);
+  }
+  template <int DIM>
+  __host__ __device__ constexpr int voigt_i(int k)
+  {
+    return k < DIM ? k : (DIM == 2 ? 0 : (k == 5 ? 1 : 0));
+  }
+  template <int DIM>
+  __host__ __device__ constexpr int voigt_j(int k)
+  {
+    return k < DIM ? k : (DIM == 2 ? 1 : (k == 3 ? 1 : 2));
+  }
+
+  template <int DIM>
+  __device__ __forceinline__ double det(const double (&F)[DIM][DIM])
+  {
+    if constexpr (DIM == 2)
+      return F[0][0] * F[1][1] - F[1][0] * F[0][1];
+    else
+      return F[0][0] * (F[1][1] * F[2][2] - F[1][2] * F[2][1]) -
+             F[0][1] * (F[1][0] * F[2][2] - F[1][2] * F[2][0]) +
+             F[0][2] * (F[1][0] * F[2][1] - F[1][1] * F[2][0]);
+  }
+  template <int DIM>
+  __device__ __forceinline__ void inverse(const double (&t)[DIM][DIM], const double d,
+                                          double (&r)[DIM][DIM])
+  {
+    const double id = 1.0 / d;
+    if constexpr (DIM == 2)
+      {
+        r[0][0] = t[1][1] * id;
+        r[0][1] = -t[0][1] * id;
+        r[1][0] = -t[1][0] * id;
+        r[1][1] = t[0][0] * id;
+      }
+    else
+      {
+        r[0][0] = (t[1][1] * t[2][2] - t[1][2] * t[2][1]) * id;
+        r[0][1] = (t[0][2] * t[2][1] - t[0][1] * t[2][2]) * id;
+        r[0][2] = (t[0][1] * t[1][2] - t[0][2] * t[1][1]) * id;
+        r[1][0] = (t[1][2] * t[2][0] - t[1][0] * t[2][2]) * id;
+        r[1][1] = (t[0][0] * t[2][2] - t[0][2] * t[2][0]) * id;
+        r[1][2] = (t[0][2] * t[1][0] - t[0][0] * t[1][2]) * id;
+        r[2][0] = (t[1][0] * t[2][1] - t[1][1] * t[2][0]) * id;
+        r[2][1] = (t[0][1] * t[2][0] - t[0][0] * t[2][1]) * id;
+        r[2][2] = (t[0][0] * t[1][1] - t[0][1] * t[1][0]) * id;
+      }
+  }
+
+  __device__ __forceinline__ double warp_sum(double v)
+  {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+
+  // block-wide sum of up to N values per thread, result valid in thread 0; fixed order
+  template <int N>
+  __device__ __forceinline__ void block_sum(double (&v)[N], double *smem /* [N*32] */)
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      v[k] = warp_sum(v[k]);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        smem[k * 32 + warp] = v[k];
+    __syncthreads();
+    if (warp == 0)
+      {
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          {
+            double x = lane < nw ? smem[k * 32 + lane] : 0.0;
+            v[k]     = warp_sum(x);
+          }
+      }
+  }
+} // namespace gf

@@ -83,11 +83,13 @@ class Problem:
 
 
 def make_problem(params: SolverParameters, dim: int, reps=None, refinements: int = 0,
-                 numbering: str = "cellwise") -> Problem:
+                 numbering: str = "cellwise", box=None) -> Problem:
     """Grid + boundary roles of `make_grid` for params.scenario. `reps` overrides the hard-coded
     repetitions; `refinements` multiplies them by 2^r (refine_global, nonlinear:245-246)."""
     p0, p1, base_reps, clamped, interface, zclamp = scenario_geometry(
         params.scenario, dim, params.flap_location)
+    if box is not None:  # (p0, p1) override, e.g. a shortened / lengthened flap of equal cell size
+        p0, p1 = list(box[0]), list(box[1])
     reps = list(reps) if reps is not None else list(base_reps)
     reps = [r * (1 << refinements) for r in reps]
     mesh = StructuredMesh(dim, params.poly_degree, reps, p0, p1, numbering)
