@@ -54,38 +54,41 @@ namespace gf
           const int     s0 = src_off[b0 + blk];
           const int     s1 = blk + 1 < nb ? int(src_off[b0 + blk + 1]) : ctotal;
           const bool    is_diag = (B == A) && (r == cc);
-          double        sum = 0, abs_sum = 0;
-          for (int s = s0; s < s1; ++s)
-            {
-              const int32_t src  = row_src[cbase + s];
-              const int64_t cell = src / npc2;
-              if (cell < c0 || cell >= c1)
-                continue;
-              const int     ab = src - int32_t(cell) * npc2;
-              const int     a = ab / npc, b = ab - a * npc;
-              const double *ke = ke_buf + (cell - c0) * int64_t(dpc) * dpc;
-              const double  v  = ke[(a * DIM + r) * dpc + b * DIM + cc];
-              sum += v;
-              if (is_diag)
-                {
-                  double av = fabs(v);
-                  if (av == 0.0) // deal.II: fall back to the cell's average |diagonal|
-                    {
-                      for (int i = 0; i < dpc; ++i)
-                        av += fabs(ke[i * dpc + i]);
-                      av /= double(dpc);
-                    }
-                  abs_sum += av;
-                }
-            }
+          // constrained rows/columns are dropped; a constrained diagonal collects |K_e(i,i)|
+          bool drop = false, use_abs = false;
           if (apply_constraints)
             {
               const bool rc = constrained[A * DIM + r] != 0;
               const bool cn = constrained[int64_t(B) * DIM + cc] != 0;
-              if (rc || cn)
-                sum = (is_diag && rc) ? abs_sum : 0.0;
+              use_abs       = is_diag && rc;
+              drop          = (rc || cn) && !use_abs;
             }
-          val[vbase + idx] = first ? sum : val[vbase + idx] + sum;
+          // running value continues across element-buffer chunks: same order as one pass
+          double sum = first ? 0.0 : val[vbase + idx];
+          if (!drop)
+            for (int s = s0; s < s1; ++s)
+              {
+                const int32_t src  = row_src[cbase + s];
+                const int64_t cell = src / npc2;
+                if (cell < c0 || cell >= c1)
+                  continue;
+                const int     ab = src - int32_t(cell) * npc2;
+                const int     a = ab / npc, b = ab - a * npc;
+                const double *ke = ke_buf + (cell - c0) * int64_t(dpc) * dpc;
+                double        v  = ke[(a * DIM + r) * dpc + b * DIM + cc];
+                if (use_abs)
+                  {
+                    v = fabs(v);
+                    if (v == 0.0) // deal.II: fall back to the cell's average |diagonal|
+                      {
+                        for (int i = 0; i < dpc; ++i)
+                          v += fabs(ke[i * dpc + i]);
+                        v /= double(dpc);
+                      }
+                  }
+                sum += v;
+              }
+          val[vbase + idx] = sum;
         }
     }
 
@@ -111,7 +114,7 @@ namespace gf
         {
           const int s0 = src_off[b0 + blk];
           const int s1 = blk + 1 < nb ? int(src_off[b0 + blk + 1]) : ctotal;
-          double    sum = 0;
+          double    sum = first ? 0.0 : mass_blk[b0 + blk];
           for (int s = s0; s < s1; ++s)
             {
               const int32_t src  = row_src[cbase + s];
@@ -120,7 +123,7 @@ namespace gf
                 continue;
               sum += me_buf[(cell - c0) * npc2 + (src - int32_t(cell) * npc2)];
             }
-          mass_blk[b0 + blk] = first ? sum : mass_blk[b0 + blk] + sum;
+          mass_blk[b0 + blk] = sum;
         }
     }
 

@@ -145,15 +145,17 @@ def test_spmv_and_cg_match_oracle_matrix(libs, dim, reps):
     assert rel_err(y, A @ x) < 1e-13
     # CG (block Jacobi) to a tight tolerance against a sparse direct solve of the same matrix
     b = h.get_vector(capi.NL_SYSTEM_RHS)
+    xs = spla.spsolve(A.tocsc(), b)
     for precond in (capi.PRECOND_BLOCK_JACOBI, capi.PRECOND_JACOBI, capi.PRECOND_NONE):
         h.set_option(capi.OPT_PRECONDITIONER, precond)
+        h.set_vector(capi.NL_SOLUTION_DELTA, np.zeros(prob.n_dofs))  # same state => same A, b
         h.nl_newton_assemble()
         h.set_vector(capi.NL_NEWTON_UPDATE, np.zeros(prob.n_dofs))
         it, res, upd = h.nl_newton_solve(0, 1e-12, 10.0)
-        xs = spla.spsolve(A.tocsc(), b)
         assert it > 0 and res <= 1e-12 * np.linalg.norm(b)
         assert rel_err(h.get_vector(capi.NL_NEWTON_UPDATE), xs) < 1e-8
     # SolverControl semantics: failure at max iterations is an error, as in the reference
+    h.set_vector(capi.NL_SOLUTION_DELTA, np.zeros(prob.n_dofs))
     h.nl_newton_assemble()
     h.set_vector(capi.NL_NEWTON_UPDATE, np.zeros(prob.n_dofs))
     with pytest.raises(capi.GraftError) as e:
