@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py — Newton-step DoFs/s of the structural hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank/GPU)
+  python bench.py --impl reference --steps K --warmup W    (CPU arm: the oracle restatement of the
+                                                            reference's CPU path on a bounded sample)
+
+Workload (config.workload): BASELINE.json configs[2] — nonlinear_elasticity, perpendicular flap 3D,
+Q2 hexahedra 24x144x24 cells = 2,081,667 DoFs per GPU, neo-Hookean + Newmark, implicit coupling with
+checkpoint/restore (k=2 sub-iterations per window, FakeParticipant supplies a constant interface
+traction), CG rel. tol 1e-6 ("Residual"), block-Jacobi. It is the configuration the north_star target
+is quoted on and it fits one GPU. N>1: weak scaling, the flap is N times longer (24 x 144N x 24),
+slab-partitioned along y, ghost-DoF halo + dot-product all-reduce over NCCL.
+
+A "step" is one pass through the coupling loop body (save/restore checkpoint, read traction, Newton
+loop of assemble + CG solve, Newmark updates, write displacement).
+  value : DoFs * (Newton linear solves) / time with the traction already resident in HBM
+  e2e   : the same through Solid.step() / Adapter with HOST interface buffers (H2D traction, D2H
+          displacement every step)
+  roofline : dominant kernel = SpMV inside CG; achieved = bytes of the stored block-row format per
+          launch / average launch duration (CUDA events on the library stream, live in the timed
+          region); peak = MEASURED_PEAKS.json hbm_gbs
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CELLS_PER_GPU = (24, 144, 24)
+CPU_SAMPLE_LAYERS = 2          # oracle sample: 24 x 2 x 24 cells of the same size (33,075 DoFs)
+TRACTION = (2000.0, 0.0, 0.0)
+N_SUB = 2
+
+
+def params():
+    from dealii_adapter_b200.problem import SolverParameters
+    return SolverParameters(model="neo-Hookean", type_lin="CG", poly_degree=2, scenario="PF",
+                            delta_t=0.01, mu=0.5e6, nu=0.4, rho=1000.0, tol_lin=1e-6,
+                            max_iterations_lin=1.0, max_iterations_NR=10, tol_f=1e-9, tol_u=1e-6,
+                            end_time=1e9)
+
+
+def make_flap(n_layers_y, numbering="lexicographic"):
+    """PF flap with cells of the cfg3 size (0.1/24 x 1/144 x 0.3/24) and n_layers_y cell layers."""
+    from dealii_adapter_b200.problem import make_problem
+    p = params()
+    box = ([-0.05, 0.0, 0.0], [0.05, n_layers_y / 144.0, 0.3])
+    return make_problem(p, 3, reps=[CELLS_PER_GPU[0], n_layers_y, CELLS_PER_GPU[2]],
+                        numbering=numbering, box=box)
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                mx = max(mx, float(s[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                    "sw_power_cap"), s[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_run(n_steps, n_warmup):
+    """Oracle (CPU restatement of the reference's path: WorkStream-like threaded assembly, serial
+    SSOR-CG as in deal.II) on the bounded sample; returns DoFs/s and details."""
+    from oracle import oracle_py as orc
+    prob = make_flap(CPU_SAMPLE_LAYERS, numbering="cellwise")
+    o = orc.Oracle(prob)
+    buf = np.tile(TRACTION, prob.n_iface_nodes)
+    solves, t_total = 0, 0.0
+    for s in range(n_warmup + n_steps):
+        o.format_precice_to_deal(buf, orc.NL_EXTERNAL_STRESS)
+        if s % N_SUB == 0:
+            o.save_state()
+        t0 = time.perf_counter()
+        n, hist = o.nl_timestep()
+        dt = time.perf_counter() - t0
+        o.format_deal_to_precice(orc.NL_TOTAL_DISPLACEMENT)
+        if s % N_SUB != N_SUB - 1:
+            o.reload_state()
+        if s >= n_warmup:
+            solves += n
+            t_total += dt
+    return {"value": prob.n_dofs * solves / t_total, "unit": "DoFs/s", "cores": o.n_threads,
+            "kind": "port",
+            "sample": "oracle (C++ restatement; reference cannot be built: deal.II/preCICE absent) "
+                      "on a 24x%dx24-cell slab of the same flap (%d DoFs), %d step(s), %d Newton "
+                      "solves, SSOR-CG serial + assembly on %d threads" %
+                      (CPU_SAMPLE_LAYERS, prob.n_dofs, n_steps, solves, o.n_threads),
+            "seconds": t_total, "n_dofs": prob.n_dofs, "newton_solves": solves}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layers", type=int, default=CELLS_PER_GPU[1],
+                    help="cell layers per GPU along the flap (debug; default = the named workload)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = ("cfg3 nonlinear_elasticity PF 3D Q2 neo-Hookean, %dx%dx%d cells per GPU, implicit "
+                "coupling k=%d with checkpoint/restore, CG rel tol 1e-6 + block-Jacobi"
+                % (CELLS_PER_GPU[0], args.layers, CELLS_PER_GPU[2], N_SUB))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_run(max(1, args.steps), max(0, min(args.warmup, 1)))
+        line = {"impl": "reference", "metric": "newton_step_dofs_per_s", "value": r["value"],
+                "unit": "DoFs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * r["seconds"] / max(1, args.steps), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload, "cpu_sample": r["sample"]},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "DoFs/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from dealii_adapter_b200 import capi, solvers
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(capi.Comm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        comm = capi.Comm(bytes(idt.cpu().numpy().tobytes()), rank, world, local_rank)
+
+    prob = make_flap(args.layers * world)
+    part = prob.mesh.partition(1, world, rank) if world > 1 else None
+    h = capi.Handle(prob, device=local_rank, partition=part, comm=comm)
+    n_if = h.n_iface_nodes
+    buf = np.tile(TRACTION, n_if)
+    participant = solvers.FakeParticipant(3, 10 ** 9, prob.params.delta_t, lambda t, it: buf, N_SUB)
+    solid = solvers.Solid(prob, participant, handle=h)
+    solid.adapter.n_interface_nodes = n_if
+    solid.adapter.interface_nodes_ids = np.arange(n_if, dtype=np.int32)   # Adapter::initialize
+    n_dofs_global = prob.n_dofs
+
+    def barrier():
+        h.synchronize()
+        if world > 1:
+            dist.barrier()
+        h.synchronize()
+
+    def resident_pass(k):
+        # the same loop body with the traction already resident in HBM (no host buffers)
+        if k % N_SUB == 0:
+            h.state_save()
+        h.nl_begin_step()
+        solid.solve_nonlinear_timestep()
+        h.nl_end_step()
+        if k % N_SUB != N_SUB - 1:
+            h.state_restore()
+
+    for k in range(max(3, args.warmup)):
+        solid.step()
+
+    sampler = ClockSampler(local_rank)
+    # ---- timed region 1: device-resident inputs ("value"), profile events on ------------------
+    h.set_option(capi.OPT_PROFILE, 1)
+    h.profile(reset=True)
+    s0 = solid.newton_solves
+    barrier()
+    sampler.start()
+    h.event_record(0)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        resident_pass(k)
+    h.event_record(1)
+    barrier()
+    wall_value = time.perf_counter() - t0
+    dev_ms = h.event_elapsed_ms(0, 1)
+    prof = h.profile(reset=True)
+    solves_value = solid.newton_solves - s0
+    h.set_option(capi.OPT_PROFILE, 0)
+    # ---- timed region 2: through the public API with host buffers ("e2e") ---------------------
+    s0 = solid.newton_solves
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        solid.step()
+    barrier()
+    wall_e2e = time.perf_counter() - t0
+    clocks = sampler.stop()
+    solves_e2e = solid.newton_solves - s0
+    prof_e2e = h.profile(reset=True)
+
+    t_value = max(wall_value, dev_ms * 1e-3)
+    if world > 1:
+        t = torch.tensor([t_value, wall_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_value, wall_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        ms_spmv, spmv_bytes = h.spmv_timed(capi.MAT_TANGENT, 5)
+        spmv_avg_ms = prof["spmv_ms"] / max(1, prof["spmv_launches"])
+        achieved = spmv_bytes / (spmv_avg_ms * 1e-3) / 1e9
+        traffic_path = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+        traffic = json.load(open(traffic_path)).get("dram_bytes_per_launch") if os.path.exists(traffic_path) else None
+        line = {
+            "metric": "newton_step_dofs_per_s", "value": n_dofs_global * solves_value / t_value,
+            "unit": "DoFs/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": 1e3 * t_value / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "n_dofs": n_dofs_global, "n_dofs_per_gpu": h.n_owned,
+                       "nnz_scalar": h.nnz(), "newton_solves_in_timed_region": solves_value,
+                       "cg_iterations_in_timed_region": int(prof["spmv_launches"]),
+                       "l2_policy": "inputs larger than L2 (matrix %.2f GB per GPU streamed every "
+                                    "CG iteration)" % (spmv_bytes / 1e9),
+                       "device_ms": dev_ms, "parallelism": "slab%d" % world},
+            "clocks": clocks,
+            "e2e": {"value": n_dofs_global * solves_e2e / wall_e2e, "unit": "DoFs/s",
+                    "h2d_bytes_per_step": int(buf.nbytes), "d2h_bytes_per_step": int(buf.nbytes),
+                    "ms_per_step": 1e3 * wall_e2e / args.steps, "newton_solves": solves_e2e},
+            "gpu_launches": int(prof["kernel_launches"]),
+            "roofline": {"bound": "hbm", "kernel": "spmv_kernel<3,true> (CG vmult + fused dot)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": traffic,
+                         "bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_avg_ms,
+                         "launches": int(prof["spmv_launches"]),
+                         "standalone_launch_ms": ms_spmv,
+                         "share_of_step": prof["spmv_ms"] / (1e3 * t_value)},
+            "phase_ms": {k: v for k, v in prof.items() if k.endswith("_ms")},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_run(1, 0)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    h.close()
+    if world > 1:
+        comm.close()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

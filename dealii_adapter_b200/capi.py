@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "gf_state_save", "gf_state_restore", "gf_nl_begin_step", "gf_nl_newton_assemble",
     "gf_nl_newton_solve", "gf_nl_end_step", "gf_lin_assemble_once", "gf_lin_step", "gf_get_vector",
     "gf_set_vector", "gf_nnz", "gf_export_csr", "gf_spmv", "gf_spmv_timed", "gf_profile_get",
-    "gf_synchronize",
+    "gf_synchronize", "gf_event_record", "gf_event_elapsed_ms",
 ]
 
 
@@ -63,7 +63,8 @@ class GfProfile(C.Structure):
                  "update_ms", "halo_ms")] + \
                [(n, C.c_int64) for n in
                 ("assemble_cells_launches", "assemble_faces_launches", "scatter_launches",
-                 "spmv_launches", "cg_vector_launches", "update_launches", "halo_launches")]
+                 "spmv_launches", "cg_vector_launches", "update_launches", "halo_launches",
+                 "kernel_launches")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -110,6 +111,8 @@ def lib():
         L.gf_spmv.argtypes = [vp, i32, i32, i32]
         L.gf_spmv_timed.argtypes = [vp, i32, i32, C.POINTER(dbl), C.POINTER(dbl)]
         L.gf_profile_get.argtypes = [vp, C.POINTER(GfProfile), i32]
+        L.gf_event_record.argtypes = [vp, i32]
+        L.gf_event_elapsed_ms.argtypes = [vp, i32, i32, C.POINTER(dbl)]
         _lib = L
     return _lib
 
@@ -314,3 +317,11 @@ class Handle:
 
     def synchronize(self):
         self._check(lib().gf_synchronize(self._h))
+
+    def event_record(self, slot):
+        self._check(lib().gf_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, slot_begin, slot_end):
+        ms = C.c_double()
+        self._check(lib().gf_event_elapsed_ms(self._h, slot_begin, slot_end, C.byref(ms)))
+        return ms.value

@@ -195,11 +195,12 @@ namespace
 
 namespace gf
 {
-  ProfScope::ProfScope(gf_context &ctx, int kind)
+  ProfScope::ProfScope(gf_context &ctx, int kind, int n_kernels)
     : c(ctx)
   {
     Profile &p = c.prof;
     p.launches[kind]++;
+    p.kernel_launches += n_kernels;
     if (!p.enabled)
       return;
     if (p.next_event + 2 > p.pool.size())
@@ -334,6 +335,9 @@ extern "C"
       cudaStreamSynchronize(h->stream);
     for (auto e : h->prof.pool)
       cudaEventDestroy(e);
+    for (auto e : h->prof.user_events)
+      if (e)
+        cudaEventDestroy(e);
     if (h->h_scalars)
       cudaFreeHost(h->h_scalars);
     if (h->h_norm)
@@ -801,12 +805,40 @@ extern "C"
       out->cg_vector_launches      = p.launches[gf::Profile::CG_VEC];
       out->update_launches         = p.launches[gf::Profile::UPDATE];
       out->halo_launches           = p.launches[gf::Profile::HALO];
+      out->kernel_launches         = p.kernel_launches;
       if (reset)
-        for (int k = 0; k < gf::Profile::N_KINDS; ++k)
-          {
-            c.prof.ms[k]       = 0;
-            c.prof.launches[k] = 0;
-          }
+        {
+          for (int k = 0; k < gf::Profile::N_KINDS; ++k)
+            {
+              c.prof.ms[k]       = 0;
+              c.prof.launches[k] = 0;
+            }
+          c.prof.kernel_launches = 0;
+        }
+      return GF_OK;
+    });
+  }
+
+  int gf_event_record(gf_handle h, int slot)
+  {
+    return guarded(h, [&](gf_context &c) {
+      GF_REQUIRE(slot >= 0 && slot < 8, GF_ERR_INVALID_ARG, "event slot out of range");
+      if (!c.prof.user_events[slot])
+        GF_CUDA_CHECK(cudaEventCreate(&c.prof.user_events[slot]));
+      GF_CUDA_CHECK(cudaEventRecord(c.prof.user_events[slot], c.stream));
+      return GF_OK;
+    });
+  }
+  int gf_event_elapsed_ms(gf_handle h, int s0, int s1, double *ms)
+  {
+    return guarded(h, [&](gf_context &c) {
+      GF_REQUIRE(s0 >= 0 && s0 < 8 && s1 >= 0 && s1 < 8 && ms && c.prof.user_events[s0] &&
+                   c.prof.user_events[s1],
+                 GF_ERR_INVALID_ARG, "event slots not recorded");
+      GF_CUDA_CHECK(cudaEventSynchronize(c.prof.user_events[s1]));
+      float f = 0;
+      GF_CUDA_CHECK(cudaEventElapsedTime(&f, c.prof.user_events[s0], c.prof.user_events[s1]));
+      *ms = f;
       return GF_OK;
     });
   }

@@ -202,7 +202,7 @@ namespace gf
       halo_exchange(c, x);
     launch_spmv(c, val, x, c.cg_v.p, nullptr);
     {
-      ProfScope ps(c, Profile::CG_VEC);
+      ProfScope ps(c, Profile::CG_VEC, 3);
       if (c.dim == 3)
         cg_update_kernel<3, true><<<ug, VEC_THREADS, 0, s>>>(n_nodes, c.cg_scalars.p, b, nullptr,
                                                              c.cg_v.p, c.dinv.p, x, c.cg_r.p,
@@ -238,7 +238,7 @@ namespace gf
               halo_exchange(c, c.cg_p.p);
             launch_spmv(c, val, c.cg_p.p, c.cg_v.p, c.partials.p);
             {
-              ProfScope ps(c, Profile::CG_VEC);
+              ProfScope ps(c, Profile::CG_VEC, 5);
               reduce_and_scalar(c, sg_rows, 1, 1);
               if (c.dim == 3)
                 cg_update_kernel<3, false><<<ug, VEC_THREADS, 0, s>>>(

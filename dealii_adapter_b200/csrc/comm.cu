@@ -104,7 +104,7 @@ namespace gf
   {
     if (!c.comm || c.nbr_rank.empty())
       return;
-    ProfScope     ps(c, Profile::HALO);
+    ProfScope     ps(c, Profile::HALO, 2);
     NcclApi &     api = nccl();
     const int64_t ns = c.send_ptr.back(), nr = c.recv_ptr.back();
     if (ns)

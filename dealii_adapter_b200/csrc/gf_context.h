@@ -144,6 +144,8 @@ namespace gf
     bool                     enabled = false;
     double                   ms[N_KINDS]{};
     int64_t                  launches[N_KINDS]{};
+    int64_t                  kernel_launches = 0;
+    cudaEvent_t              user_events[8]{};
     std::vector<cudaEvent_t> pool;
     struct Pending
     {
@@ -296,7 +298,7 @@ namespace gf
   {
     gf_context &c;
     int         idx = -1;
-    ProfScope(gf_context &ctx, int kind);
+    ProfScope(gf_context &ctx, int kind, int n_kernels = 1);
     ~ProfScope();
   };
   void profile_collect(gf_context &c);

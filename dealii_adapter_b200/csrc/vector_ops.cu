@@ -159,7 +159,7 @@ namespace gf
   {
     const int g = grid_for(c, c.n_owned);
     {
-      ProfScope ps(c, Profile::UPDATE);
+      ProfScope ps(c, Profile::UPDATE, 2);
       norm_partials_kernel<<<g, NT, 0, c.stream>>>(c.n_owned, v, c.constrained.p, mask_constrained,
                                                    c.partials.p);
       norm_final_kernel<<<1, 1024, 0, c.stream>>>(c.partials.p, g, c.norm_out.p);

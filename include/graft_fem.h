@@ -133,6 +133,7 @@ extern "C"
       halo_ms;
     int64_t assemble_cells_launches, assemble_faces_launches, scatter_launches, spmv_launches,
       cg_vector_launches, update_launches, halo_launches;
+    int64_t kernel_launches; /* every kernel of this library launched since the last reset */
   } gf_profile;
 
   /* ---- life cycle -------------------------------------------------------------------------- */
@@ -204,6 +205,10 @@ extern "C"
                     double *bytes_per_launch);
   int gf_profile_get(gf_handle h, gf_profile *out, int reset);
   int gf_synchronize(gf_handle h);
+  /* CUDA events on the library's own stream (torch.cuda.Event only sees torch's stream):
+   * record slot 0..7, then elapsed milliseconds between two recorded slots (synchronises). */
+  int gf_event_record(gf_handle h, int slot);
+  int gf_event_elapsed_ms(gf_handle h, int slot_begin, int slot_end, double *ms);
 
 #ifdef __cplusplus
 }
