@@ -215,7 +215,9 @@ def main():
         if k % N_SUB != N_SUB - 1:
             h.state_restore()
 
-    for k in range(max(3, args.warmup)):
+    # >= 3 warm-up passes always, except under a profiler (GF_PROFILE_RUN=1: numbers not reported)
+    n_warm = args.warmup if os.environ.get("GF_PROFILE_RUN") == "1" else max(3, args.warmup)
+    for k in range(n_warm):
         solid.step()
 
     sampler = ClockSampler(local_rank)
@@ -262,7 +264,7 @@ def main():
         traffic = json.load(open(traffic_path)).get("dram_bytes_per_launch") if os.path.exists(traffic_path) else None
         line = {
             "metric": "newton_step_dofs_per_s", "value": n_dofs_global * solves_value / t_value,
-            "unit": "DoFs/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "unit": "DoFs/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": 1e3 * t_value / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "n_dofs": n_dofs_global, "n_dofs_per_gpu": h.n_owned,

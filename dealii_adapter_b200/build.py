@@ -58,13 +58,31 @@ def build_cuda(force=False):
 
 
 def build_host(force=False):
-    srcs = _sources(HOST, (".cc",))
-    srcs = [s for s in srcs if not s.endswith("elasticity.cc")]
-    deps = srcs + _sources(HOST, (".h",)) + _sources(INCLUDE, (".h",))
+    """Mesh/DoF scaffolding only (no CUDA dependency): used by the Python binding, tests, oracle."""
+    srcs = [os.path.join(HOST, "structured_mesh.cc")]
+    deps = srcs + [os.path.join(HOST, "structured_mesh.h")]
     if force or _newer(LIB_HOST, deps):
-        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", INCLUDE, "-I", HOST,
-              "-o", LIB_HOST] + srcs + ["-ldl", "-lpthread"])
+        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", HOST,
+              "-o", LIB_HOST] + srcs)
     return LIB_HOST
+
+
+def build_elasticity(force=False):
+    """The drop-in host driver (C++ mirror of elasticity.cc + Solid/ElastoDynamics/Adapter) linked
+    against libgraftfem.so; one executable per DIM like the reference's -DDIM build."""
+    build_cuda()
+    srcs = _sources(HOST, (".cc",))
+    deps = srcs + _sources(HOST, (".h",)) + _sources(os.path.join(HOST, "adapter"), (".h",)) \
+        + _sources(INCLUDE, (".h",)) + [LIB_CUDA]
+    outs = []
+    for dim in (2, 3):
+        exe = os.path.join(PKG_DIR, "elasticity_%dd" % dim)
+        if force or _newer(exe, deps):
+            _run(["g++", "-O2", "-std=c++17", "-Wall", "-DDIM=%d" % dim, "-I", INCLUDE, "-I", HOST,
+                  "-o", exe] + srcs + ["-L", PKG_DIR, "-lgraftfem", "-Wl,-rpath,$ORIGIN",
+                                       "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
+        outs.append(exe)
+    return outs
 
 
 def build_oracle(force=False):
@@ -76,7 +94,7 @@ def build_oracle(force=False):
 
 
 def build_all(force=False):
-    return build_host(force), build_cuda(force), build_oracle(force)
+    return build_host(force), build_cuda(force), build_elasticity(force), build_oracle(force)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,31 @@
+// Host-side set-up shared by the two solver classes: the part of make_grid / system_setup /
+// make_constraints that stays on the host (nonlinear_elasticity.cc:171-380,1094-1150;
+// linear_elasticity.cc:79-244,431-446) and fills the gf_desc handed to the device library.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "adapter/adapter.h"
+#include "adapter/parameters.h"
+#include "graft_fem.h"
+#include "structured_mesh.h"
+
+namespace gfh
+{
+  struct HostProblem
+  {
+    std::unique_ptr<StructuredMesh> mesh;
+    std::vector<uint8_t>            constrained;
+    std::vector<int32_t>            iface_cell, iface_face_no, iface_dofs;
+    Adapter::InterfaceDescription   interface;
+    gf_handle                       handle = nullptr;
+    double                          vol_reference = 0;
+
+    // scenario geometry + boundary roles; `reps_override` replaces the hard-coded repetitions
+    void make_grid(const Parameters::AllParameters &prm, int dim,
+                   const std::vector<int> &reps_override, int numbering);
+    void create_device(const Parameters::AllParameters &prm, int dim, int model);
+    ~HostProblem();
+  };
+} // namespace gfh
