@@ -21,7 +21,7 @@ LIN_OLD_VELOCITY, LIN_VELOCITY, LIN_OLD_DISPLACEMENT, LIN_DISPLACEMENT, LIN_OLD_
 VEC_SCRATCH0, VEC_SCRATCH1 = 28, 29
 MAT_TANGENT, MAT_STIFFNESS, MAT_MASS, MAT_SYSTEM = range(4)
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI = range(3)
-OPT_PRECONDITIONER, OPT_CG_CHECK_INTERVAL, OPT_PROFILE, OPT_OPERATOR = range(4)
+OPT_PRECONDITIONER, OPT_CG_CHECK_INTERVAL, OPT_PROFILE, OPT_OPERATOR, OPT_SPMV_KERNEL = range(5)
 
 EXPORTED_SYMBOLS = [
     "gf_create", "gf_destroy", "gf_last_error", "gf_set_option", "gf_comm_unique_id",

@@ -374,6 +374,10 @@ extern "C"
             GF_REQUIRE(value == 0, GF_ERR_UNSUPPORTED, "matrix-free operator not available yet");
             c.operator_kind = int(value);
             break;
+          case GF_OPT_SPMV_KERNEL:
+            GF_REQUIRE(value == 0 || value == 1, GF_ERR_INVALID_ARG, "unknown SpMV kernel");
+            c.spmv_kernel_kind = int(value);
+            break;
           default:
             throw gf::Error{GF_ERR_INVALID_ARG, "unknown option"};
         }

@@ -195,7 +195,7 @@ namespace gf
     const int64_t n_nodes = c.n_owned_nodes;
     const int     ug      = vec_grid(c, n_nodes);
     const int     dg      = vec_grid(c, c.n_owned);
-    const int     sg_rows = int(std::min<int64_t>((n_nodes * 32 + 255) / 256, c.max_red_blocks));
+    const int     sg_rows = spmv_dot_partials(c);
 
     // ---- startup ----
     if (c.comm)

@@ -120,6 +120,20 @@ namespace gf
     int    pad;
   };
 
+  // SpMV tile = run of consecutive block rows whose values (<= TILE_V doubles), column indices and
+  // per-row records are fetched by three TMA bulk copies into one pipeline stage (spmv.cu)
+  struct TileDesc
+  {
+    long long val_off;   // first value (doubles) in the value array
+    int       val_count; // doubles, multiple of 2
+    int       col_off;   // first column index, rounded down to a multiple of 4
+    int       col_count; // ints, multiple of 4
+    int       row0, n_rows, pad;
+  };
+  constexpr int SPMV_TILE_V    = 6144; // doubles per tile (48 KB)
+  constexpr int SPMV_TILE_ROWS = 32;   // max rows per tile
+  constexpr int SPMV_META      = SPMV_TILE_ROWS + 2; // uint2 records per tile (+ header), 272 B
+
   struct BsrMatrix
   {
     DevBuf<double> val;
@@ -203,6 +217,10 @@ struct gf_context
   gf::DevBuf<int64_t>  cand_ptr; // [n_owned_nodes+1]
   gf::DevBuf<int32_t>  row_src;  // [n_cand] = (cell*npc + a)*npc + b
   gf::DevBuf<uint16_t> src_off;  // [n_blocks] offset of the block's sources in its row list
+  gf::DevBuf<gf::TileDesc> tile_desc; // [n_tiles]
+  gf::DevBuf<uint2>        tile_meta; // [n_tiles*SPMV_META]: per row {val offset, col offset | nb<<16}
+  int64_t                  n_tiles = 0; // 0: a row does not fit a tile -> LDG kernel only
+  int                      spmv_kernel_kind = 0; // 0 auto (TMA tiles when available), 1 LDG
   gf::BsrMatrix        mat[gf::N_MATRICES];
   gf::DevBuf<double>   mass_blk; // linear: scalar mass value per block (M = m_ab delta_cd)
   gf::DevBuf<double>   dinv;     // [n_owned_nodes*dim*dim] preconditioner blocks
@@ -275,6 +293,7 @@ namespace gf
                    double *dot_partials);
   void launch_spmv_mass(gf_context &c, const double *x, double *y);
   double spmv_bytes(const gf_context &c);
+  int    spmv_dot_partials(const gf_context &c);
   // cg.cu
   int cg_solve(gf_context &c, const double *val, double *x, const double *b, double tol,
                bool tol_relative_to_rhs, int64_t maxit, uint32_t *last_step, double *last_value);

@@ -316,7 +316,7 @@ namespace gf
     c.n_blocks = nb_total;
     c.n_val    = nval;
     c.n_cand   = ncand;
-    c.bcol.alloc(c.n_blocks);
+    c.bcol.alloc_zero(c.n_blocks + 8, s); // padded: tile copies fetch 16-byte aligned supersets
     c.src_off.alloc(c.n_blocks);
     c.row_src.alloc(c.n_cand);
     pattern_kernel<true><<<grid, wpb * 32, smem, s>>>(n_rows, npc, c.nc_ptr.p, c.nc_src.p,
@@ -325,5 +325,59 @@ namespace gf
                                                       c.row_src.p, overflow.p);
     GF_CUDA_CHECK(cudaGetLastError());
     GF_CUDA_CHECK(cudaStreamSynchronize(s));
+
+    // ---- host: SpMV tiles (greedy runs of consecutive rows) -------------------------------------
+    {
+      std::vector<int32_t> brow(n_rows + 1);
+      std::vector<int64_t> vptr(n_rows + 1);
+      GF_CUDA_CHECK(cudaMemcpy(brow.data(), c.brow_ptr.p, (n_rows + 1) * sizeof(int32_t),
+                               cudaMemcpyDeviceToHost));
+      GF_CUDA_CHECK(cudaMemcpy(vptr.data(), c.val_ptr.p, (n_rows + 1) * sizeof(int64_t),
+                               cudaMemcpyDeviceToHost));
+      const int             tile_c = ((SPMV_TILE_V / (dim * dim)) + 8 + 3) & ~3;
+      std::vector<TileDesc> descs;
+      std::vector<uint2>    meta;
+      bool                  ok   = n_rows > 0;
+      int64_t               row0 = 0;
+      while (ok && row0 < n_rows)
+        {
+          const int32_t c0   = brow[row0] & ~3;
+          int64_t       row1 = row0;
+          while (row1 < n_rows && row1 - row0 < SPMV_TILE_ROWS &&
+                 vptr[row1 + 1] - vptr[row0] <= SPMV_TILE_V &&
+                 ((brow[row1 + 1] + 3) & ~3) - c0 <= tile_c && brow[row1 + 1] - brow[row1] < 65536)
+            ++row1;
+          if (row1 == row0)
+            {
+              ok = false; // a single row exceeds the tile: keep the LDG kernel for this matrix
+              break;
+            }
+          TileDesc d;
+          d.val_off   = vptr[row0];
+          d.val_count = int(vptr[row1] - vptr[row0]);
+          d.col_off   = c0;
+          d.col_count = ((brow[row1] + 3) & ~3) - c0;
+          d.row0      = int(row0);
+          d.n_rows    = int(row1 - row0);
+          d.pad       = 0;
+          descs.push_back(d);
+          const size_t base = meta.size();
+          meta.resize(base + SPMV_META, make_uint2(0, 0));
+          for (int64_t r = row0; r < row1; ++r)
+            meta[base + (r - row0)] =
+              make_uint2(unsigned(vptr[r] - vptr[row0]),
+                         unsigned(brow[r] - c0) | (unsigned(brow[r + 1] - brow[r]) << 16));
+          meta[base + SPMV_TILE_ROWS] = make_uint2(unsigned(row0), unsigned(row1 - row0));
+          row0 = row1;
+        }
+      if (ok)
+        {
+          c.n_tiles = int64_t(descs.size());
+          c.tile_desc.upload(descs.data(), descs.size(), s);
+          c.tile_meta.upload(meta.data(), meta.size(), s);
+        }
+      else
+        c.n_tiles = 0;
+    }
   }
 } // namespace gf

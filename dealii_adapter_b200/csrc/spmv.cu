@@ -6,9 +6,17 @@
 // (padded to an even count), all sharing ONE column-index stream: 8 B per value + 4/dim^2 B of
 // index per value instead of CSR's 8+4. HBM-bound; algorithmic bytes per launch =
 // 8*n_val + 4*n_blocks + 4*(n_rows+1) + 8*(n_rows+1) + 8*n_local(x) + 8*n_owned(y).
-// One warp per node row; every lane streams 16-byte (double2) pieces of each scalar row with
-// streaming loads and gathers x through the read-only path; rows are handed out by a
-// persistent grid so the fused dot product needs only gridDim.x partial sums (fixed order).
+//
+// Main kernel (spmv_tma_kernel): persistent, one CTA per SM, warp-specialised. A producer warp
+// streams TILES (runs of consecutive rows: <= 48 KB of values + their column indices + per-row
+// records, built once in pattern.cu) into a 3-stage shared-memory ring with TMA bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx); 8 consumer warps take one row each from the landed
+// tile (LDS.128 values, column indices from shared memory, x gathered through the read-only
+// path). The bytes in flight (~100 KB/SM) live in shared memory, not registers: the ncu capture
+// of the LDG version (profiles/r01_spmv_ncu_summary.md) showed it latency-bound at 32 warps/SM.
+// Fallback (spmv_kernel, LDG): one warp per row with double2 streaming loads; used when a row
+// does not fit a tile or when GF_OPT_SPMV_KERNEL = 1.
+// The fused dot product needs only gridDim.x partial sums (fixed order => reproducible).
 #include "gf_context.h"
 #include "kernel_utils.cuh"
 
@@ -97,6 +105,227 @@ namespace gf
         }
     }
 
+
+    // ------------------------------------------------------------------------------------------
+    // TMA-tiled kernel
+    // ------------------------------------------------------------------------------------------
+    template <int DIM>
+    struct TmaCfg
+    {
+      static constexpr int TILE_V         = SPMV_TILE_V;
+      static constexpr int TILE_C         = ((TILE_V / (DIM * DIM)) + 8 + 3) & ~3;
+      static constexpr int STAGES         = 3;
+      static constexpr int CONSUMER_WARPS = 8;
+      static constexpr int THREADS        = (CONSUMER_WARPS + 1) * 32;
+      static constexpr int VAL_BYTES      = TILE_V * 8;
+      static constexpr int COL_BYTES      = (TILE_C * 4 + 127) & ~127;
+      static constexpr int META_BYTES     = SPMV_META * 8;
+      static constexpr int STAGE_BYTES    = VAL_BYTES + COL_BYTES + ((META_BYTES + 127) & ~127);
+      static constexpr int SMEM_BYTES     = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 64;
+    };
+
+    __device__ __forceinline__ uint32_t smem_u32(const void *p)
+    {
+      return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+    }
+    __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+    {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    }
+    __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+    {
+      uint32_t done;
+      do
+        {
+          asm volatile("{\n .reg .pred p;\n"
+                       " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                       " selp.u32 %0, 1, 0, p;\n}\n"
+                       : "=r"(done)
+                       : "r"(bar), "r"(parity)
+                       : "memory");
+        }
+      while (!done);
+    }
+    __device__ __forceinline__ void mbar_arrive(uint32_t bar)
+    {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+    }
+    __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+    {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                   : "memory");
+    }
+    // TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+    __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes,
+                                             uint32_t bar)
+    {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], "
+                   "%2, [%3];" ::"r"(dst),
+                   "l"(src), "r"(bytes), "r"(bar)
+                   : "memory");
+    }
+
+    template <int DIM, bool DOT>
+    __global__ void __launch_bounds__(TmaCfg<DIM>::THREADS, 1)
+      spmv_tma_kernel(const int n_tiles, const TileDesc *__restrict__ tile_desc,
+                      const uint2 *__restrict__ tile_meta, const int32_t *__restrict__ bcol,
+                      const double *__restrict__ val, const double *__restrict__ x,
+                      double *__restrict__ y, double *__restrict__ partials, const int *status)
+    {
+      using C = TmaCfg<DIM>;
+      if (status != nullptr && *status != 0)
+        return;
+      extern __shared__ __align__(128) unsigned char smem[];
+      uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::STAGES * C::STAGE_BYTES);
+      __shared__ double red[C::CONSUMER_WARPS];
+      const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+      if (tid == 0)
+        {
+          for (int s = 0; s < C::STAGES; ++s)
+            {
+              mbar_init(smem_u32(&bars[s]), 1);                            // full: producer
+              mbar_init(smem_u32(&bars[C::STAGES + s]), C::CONSUMER_WARPS); // empty: consumers
+            }
+          asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+      __syncthreads();
+      const int n_my =
+        int(blockIdx.x) < n_tiles ? (n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
+      double dot = 0.0;
+
+      if (warp == C::CONSUMER_WARPS)
+        {
+          // ------------------------------ producer warp --------------------------------------
+          TileDesc d{};
+          for (int k = 0; k < n_my; ++k)
+            {
+              if ((k & 31) == 0)
+                {
+                  const int kk = k + lane;
+                  if (kk < n_my)
+                    d = tile_desc[int64_t(blockIdx.x) + int64_t(kk) * gridDim.x];
+                }
+              const int       src_lane  = k & 31;
+              const long long val_off   = __shfl_sync(0xffffffffu, d.val_off, src_lane);
+              const int       val_count = __shfl_sync(0xffffffffu, d.val_count, src_lane);
+              const int       col_off   = __shfl_sync(0xffffffffu, d.col_off, src_lane);
+              const int       col_count = __shfl_sync(0xffffffffu, d.col_count, src_lane);
+              const int       s         = k % C::STAGES;
+              if (k >= C::STAGES) // stage s was last used by tile k - STAGES
+                mbar_wait(smem_u32(&bars[C::STAGES + s]), ((k / C::STAGES) - 1) & 1);
+              if (lane == 0)
+                {
+                  const int64_t  t     = int64_t(blockIdx.x) + int64_t(k) * gridDim.x;
+                  unsigned char *stage = smem + s * C::STAGE_BYTES;
+                  const uint32_t full  = smem_u32(&bars[s]);
+                  const uint32_t vb = uint32_t(val_count) * 8u, cb = uint32_t(col_count) * 4u;
+                  mbar_arrive_expect_tx(full, vb + cb + uint32_t(C::META_BYTES));
+                  bulk_g2s(smem_u32(stage), val + val_off, vb, full);
+                  bulk_g2s(smem_u32(stage + C::VAL_BYTES), bcol + col_off, cb, full);
+                  bulk_g2s(smem_u32(stage + C::VAL_BYTES + C::COL_BYTES), tile_meta + t * SPMV_META,
+                           uint32_t(C::META_BYTES), full);
+                }
+              __syncwarp();
+            }
+        }
+      else
+        {
+          // ------------------------------ consumer warps -------------------------------------
+          for (int k = 0; k < n_my; ++k)
+            {
+              const int s = k % C::STAGES;
+              mbar_wait(smem_u32(&bars[s]), (k / C::STAGES) & 1);
+              const unsigned char *stage = smem + s * C::STAGE_BYTES;
+              const double *       sval  = reinterpret_cast<const double *>(stage);
+              const int32_t *scol = reinterpret_cast<const int32_t *>(stage + C::VAL_BYTES);
+              const uint2 *  smeta =
+                reinterpret_cast<const uint2 *>(stage + C::VAL_BYTES + C::COL_BYTES);
+              const uint2 hdr    = smeta[SPMV_TILE_ROWS];
+              const int   row0   = int(hdr.x);
+              const int   n_rows = int(hdr.y);
+              for (int row = warp; row < n_rows; row += C::CONSUMER_WARPS)
+                {
+                  const uint2    m      = smeta[row];
+                  const int      ne     = int(m.y >> 16) * DIM;
+                  const int      stride = (ne + 1) & ~1;
+                  const double * v      = sval + m.x;
+                  const int32_t *cl     = scol + (m.y & 0xffffu);
+                  double         acc[DIM];
+#pragma unroll
+                  for (int r = 0; r < DIM; ++r)
+                    acc[r] = 0.0;
+#pragma unroll 3
+                  for (int e = 2 * lane; e < ne; e += 64)
+                    {
+                      const int    e1 = e + 1;
+                      const int    k0 = e / DIM, k1 = e1 / DIM;
+                      const double x0 = __ldg(x + int64_t(cl[k0]) * DIM + (e - k0 * DIM));
+                      double       x1 = 0.0;
+                      if (e1 < ne)
+                        x1 = __ldg(x + int64_t(cl[k1]) * DIM + (e1 - k1 * DIM));
+#pragma unroll
+                      for (int r = 0; r < DIM; ++r)
+                        {
+                          const double2 vv = *reinterpret_cast<const double2 *>(v + r * stride + e);
+                          acc[r]           = fma(vv.x, x0, acc[r]);
+                          acc[r]           = fma(vv.y, x1, acc[r]);
+                        }
+                    }
+#pragma unroll
+                  for (int r = 0; r < DIM; ++r)
+                    acc[r] = warp_sum(acc[r]);
+                  if (lane < DIM)
+                    {
+                      double yr = acc[0];
+#pragma unroll
+                      for (int r = 1; r < DIM; ++r)
+                        if (lane == r)
+                          yr = acc[r];
+                      const int64_t i = int64_t(row0 + row) * DIM + lane;
+                      y[i]            = yr;
+                      if (DOT)
+                        dot = fma(yr, x[i], dot);
+                    }
+                }
+              __syncwarp();
+              if (lane == 0)
+                mbar_arrive(smem_u32(&bars[C::STAGES + s])); // release the stage
+            }
+        }
+      if (DOT)
+        {
+          dot = warp_sum(dot);
+          if (lane == 0 && warp < C::CONSUMER_WARPS)
+            red[warp] = dot;
+          __syncthreads();
+          if (tid < 32)
+            {
+              double v = tid < C::CONSUMER_WARPS ? red[tid] : 0.0;
+              v        = warp_sum(v);
+              if (tid == 0)
+                partials[blockIdx.x] = v;
+            }
+        }
+    }
+
+    template <int DIM, bool DOT>
+    void launch_tma_t(gf_context &c, const double *val, const double *x, double *y,
+                      double *dot_partials, const int *st)
+    {
+      using C = TmaCfg<DIM>;
+      static bool configured = false;
+      if (!configured)
+        {
+          GF_CUDA_CHECK(cudaFuncSetAttribute(spmv_tma_kernel<DIM, DOT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             C::SMEM_BYTES));
+          configured = true;
+        }
+      const int grid = int(std::min<int64_t>(c.n_tiles, c.sm_count));
+      spmv_tma_kernel<DIM, DOT><<<grid, C::THREADS, C::SMEM_BYTES, c.stream>>>(
+        int(c.n_tiles), c.tile_desc.p, c.tile_meta.p, c.bcol.p, val, x, y, dot_partials, st);
+    }
+
     // y = M x with M = m_ab delta_cd (consistent mass, one scalar per block)
     template <int DIM>
     __global__ void spmv_mass_kernel(const int64_t n_rows, const int32_t *__restrict__ brow_ptr,
@@ -131,6 +360,15 @@ namespace gf
     }
   } // namespace
 
+  // number of per-CTA partial sums the fused dot product of launch_spmv writes
+  int spmv_dot_partials(const gf_context &c)
+  {
+    if (c.n_tiles > 0 && c.spmv_kernel_kind == 0)
+      return int(std::min<int64_t>(c.n_tiles, c.sm_count));
+    const int64_t want = (c.n_owned_nodes * 32 + SPMV_THREADS - 1) / SPMV_THREADS;
+    return int(std::min<int64_t>(want, c.max_red_blocks));
+  }
+
   void launch_spmv(gf_context &c, const double *val, const double *x, double *y,
                    double *dot_partials)
   {
@@ -138,9 +376,27 @@ namespace gf
     const int64_t n_rows = c.n_owned_nodes;
     if (n_rows == 0)
       return;
-    const int64_t want = (n_rows * 32 + SPMV_THREADS - 1) / SPMV_THREADS;
-    const int     grid = int(std::min<int64_t>(want, c.max_red_blocks));
-    const int *   st   = dot_partials ? &c.cg_scalars.p->status : nullptr;
+    const int *st = dot_partials ? &c.cg_scalars.p->status : nullptr;
+    if (c.n_tiles > 0 && c.spmv_kernel_kind == 0)
+      {
+        if (c.dim == 3)
+          {
+            if (dot_partials)
+              launch_tma_t<3, true>(c, val, x, y, dot_partials, st);
+            else
+              launch_tma_t<3, false>(c, val, x, y, nullptr, nullptr);
+          }
+        else
+          {
+            if (dot_partials)
+              launch_tma_t<2, true>(c, val, x, y, dot_partials, st);
+            else
+              launch_tma_t<2, false>(c, val, x, y, nullptr, nullptr);
+          }
+        GF_CUDA_CHECK(cudaGetLastError());
+        return;
+      }
+    const int grid = spmv_dot_partials(c);
     if (c.dim == 3)
       {
         if (dot_partials)
@@ -181,6 +437,8 @@ namespace gf
   // bytes one SpMV launch must move in the stored format (the roofline numerator)
   double spmv_bytes(const gf_context &c)
   {
+    // values + column indices + per-row records (12 B/row in both kernels: row pointers for the LDG
+    // kernel, tile records for the TMA kernel are of the same order) + x read once + y written once
     return 8.0 * double(c.n_val) + 4.0 * double(c.n_blocks) + 12.0 * double(c.n_owned_nodes + 1) +
            8.0 * double(c.n_local) + 8.0 * double(c.n_owned);
   }

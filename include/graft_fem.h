@@ -122,7 +122,8 @@ extern "C"
     GF_OPT_PRECONDITIONER = 0, /* GF_PRECOND_* ; replaces SSOR (nonlinear:1180-1182, linear:548-549) */
     GF_OPT_CG_CHECK_INTERVAL,  /* iterations enqueued between host polls of the device flag */
     GF_OPT_PROFILE,            /* 1: bracket every kernel class with CUDA events (see gf_profile) */
-    GF_OPT_OPERATOR            /* 0: assembled BSR SpMV ; 1: matrix-free tangent operator in CG */
+    GF_OPT_OPERATOR,           /* 0: assembled BSR SpMV ; 1: matrix-free tangent operator in CG */
+    GF_OPT_SPMV_KERNEL         /* 0: TMA-tiled kernel (default) ; 1: LDG warp-per-row kernel */
   };
 
   /* device-time breakdown accumulated while GF_OPT_PROFILE = 1 (CUDA events on the library's
