@@ -682,7 +682,7 @@ extern "C"
     return guarded(h, [&](gf_context &c) {
       GF_REQUIRE(rowptr && col && val, GF_ERR_INVALID_ARG, "null buffer");
       const int            dim = c.dim;
-      std::vector<int32_t> brow(c.n_owned_nodes + 1), bcol(c.n_blocks);
+      std::vector<int32_t> brow(c.n_owned_nodes + 1), bcol(c.bcol.n); // bcol is padded (tiles)
       std::vector<int64_t> vptr(c.n_owned_nodes + 1);
       c.brow_ptr.download(brow.data(), c.stream);
       c.bcol.download(bcol.data(), c.stream);

@@ -130,7 +130,7 @@ namespace gf
     int       col_count; // ints, multiple of 4
     int       row0, n_rows, pad;
   };
-  constexpr int SPMV_TILE_V    = 6144; // doubles per tile (48 KB)
+  constexpr int spmv_tile_v(int dim) { return dim == 3 ? 6144 : 4096; } // value doubles per tile
   constexpr int SPMV_TILE_ROWS = 32;   // max rows per tile
   constexpr int SPMV_META      = SPMV_TILE_ROWS + 2; // uint2 records per tile (+ header), 272 B
 

@@ -334,7 +334,8 @@ namespace gf
                                cudaMemcpyDeviceToHost));
       GF_CUDA_CHECK(cudaMemcpy(vptr.data(), c.val_ptr.p, (n_rows + 1) * sizeof(int64_t),
                                cudaMemcpyDeviceToHost));
-      const int             tile_c = ((SPMV_TILE_V / (dim * dim)) + 8 + 3) & ~3;
+      const int             tile_v = spmv_tile_v(dim);
+      const int             tile_c = ((tile_v / (dim * dim)) + 8 + 3) & ~3;
       std::vector<TileDesc> descs;
       std::vector<uint2>    meta;
       bool                  ok   = n_rows > 0;
@@ -344,7 +345,7 @@ namespace gf
           const int32_t c0   = brow[row0] & ~3;
           int64_t       row1 = row0;
           while (row1 < n_rows && row1 - row0 < SPMV_TILE_ROWS &&
-                 vptr[row1 + 1] - vptr[row0] <= SPMV_TILE_V &&
+                 vptr[row1 + 1] - vptr[row0] <= tile_v &&
                  ((brow[row1 + 1] + 3) & ~3) - c0 <= tile_c && brow[row1 + 1] - brow[row1] < 65536)
             ++row1;
           if (row1 == row0)
@@ -367,7 +368,8 @@ namespace gf
             meta[base + (r - row0)] =
               make_uint2(unsigned(vptr[r] - vptr[row0]),
                          unsigned(brow[r] - c0) | (unsigned(brow[r + 1] - brow[r]) << 16));
-          meta[base + SPMV_TILE_ROWS] = make_uint2(unsigned(row0), unsigned(row1 - row0));
+          meta[base + SPMV_TILE_ROWS]     = make_uint2(unsigned(row0), unsigned(row1 - row0));
+          meta[base + SPMV_TILE_ROWS + 1] = make_uint2(unsigned(d.col_count), 0u);
           row0 = row1;
         }
       if (ok)

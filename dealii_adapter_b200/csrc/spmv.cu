@@ -10,9 +10,8 @@
 // Main kernel (spmv_tma_kernel): persistent, one CTA per SM, warp-specialised. A producer warp
 // streams TILES (runs of consecutive rows: <= 48 KB of values + their column indices + per-row
 // records, built once in pattern.cu) into a 3-stage shared-memory ring with TMA bulk copies
-// (cp.async.bulk ... mbarrier::complete_tx); 8 consumer warps take one row each from the landed
-// tile (LDS.128 values, column indices from shared memory, x gathered through the read-only
-// path). The bytes in flight (~100 KB/SM) live in shared memory, not registers: the ncu capture
+// (cp.async.bulk ... mbarrier::complete_tx); 8 gather warps pull x[col] for the whole tile into shared memory (many
+// independent read-only loads per lane), 8 consumer warps then do pure shared-memory FMAs. The bytes in flight (~100 KB/SM) live in shared memory, not registers: the ncu capture
 // of the LDG version (profiles/r01_spmv_ncu_summary.md) showed it latency-bound at 32 warps/SM.
 // Fallback (spmv_kernel, LDG): one warp per row with double2 streaming loads; used when a row
 // does not fit a tile or when GF_OPT_SPMV_KERNEL = 1.
@@ -107,21 +106,25 @@ namespace gf
 
 
     // ------------------------------------------------------------------------------------------
-    // TMA-tiled kernel
+    // TMA-tiled kernel: producer warp (TMA) -> gather warps (x) -> consumer warps (FMA)
     // ------------------------------------------------------------------------------------------
     template <int DIM>
     struct TmaCfg
     {
-      static constexpr int TILE_V         = SPMV_TILE_V;
-      static constexpr int TILE_C         = ((TILE_V / (DIM * DIM)) + 8 + 3) & ~3;
-      static constexpr int STAGES         = 3;
-      static constexpr int CONSUMER_WARPS = 8;
-      static constexpr int THREADS        = (CONSUMER_WARPS + 1) * 32;
-      static constexpr int VAL_BYTES      = TILE_V * 8;
-      static constexpr int COL_BYTES      = (TILE_C * 4 + 127) & ~127;
-      static constexpr int META_BYTES     = SPMV_META * 8;
-      static constexpr int STAGE_BYTES    = VAL_BYTES + COL_BYTES + ((META_BYTES + 127) & ~127);
-      static constexpr int SMEM_BYTES     = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 64;
+      static constexpr int TILE_V       = DIM == 3 ? 6144 : 4096; // doubles of values per tile
+      static constexpr int TILE_C       = ((TILE_V / (DIM * DIM)) + 8 + 3) & ~3; // column indices
+      static constexpr int STAGES       = 3;
+      static constexpr int GATHER_WARPS = 8;
+      static constexpr int CONS_WARPS   = 8;
+      static constexpr int THREADS      = (1 + GATHER_WARPS + CONS_WARPS) * 32;
+      static constexpr int VAL_BYTES    = TILE_V * 8;
+      static constexpr int COL_BYTES    = (TILE_C * 4 + 127) & ~127;
+      static constexpr int META_BYTES   = SPMV_META * 8; // bytes copied
+      static constexpr int META_PAD     = (META_BYTES + 127) & ~127;
+      static constexpr int XG_BYTES     = (TILE_C * DIM * 8 + 127) & ~127;
+      static constexpr int STAGE_BYTES  = VAL_BYTES + COL_BYTES + META_PAD + XG_BYTES;
+      static constexpr int SMEM_BYTES   = STAGES * STAGE_BYTES + 3 * STAGES * 8 + 64;
+      static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     };
 
     __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -176,15 +179,19 @@ namespace gf
       if (status != nullptr && *status != 0)
         return;
       extern __shared__ __align__(128) unsigned char smem[];
-      uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::STAGES * C::STAGE_BYTES);
-      __shared__ double red[C::CONSUMER_WARPS];
+      uint64_t *bars  = reinterpret_cast<uint64_t *>(smem + C::STAGES * C::STAGE_BYTES);
+      uint64_t *full  = bars;                 // TMA bytes landed          (count 1 + tx)
+      uint64_t *xfull = bars + C::STAGES;     // x gathered               (count GATHER_WARPS)
+      uint64_t *empty = bars + 2 * C::STAGES; // consumers done with tile (count CONS_WARPS)
+      __shared__ double red[C::CONS_WARPS];
       const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
       if (tid == 0)
         {
           for (int s = 0; s < C::STAGES; ++s)
             {
-              mbar_init(smem_u32(&bars[s]), 1);                            // full: producer
-              mbar_init(smem_u32(&bars[C::STAGES + s]), C::CONSUMER_WARPS); // empty: consumers
+              mbar_init(smem_u32(&full[s]), 1);
+              mbar_init(smem_u32(&xfull[s]), C::GATHER_WARPS);
+              mbar_init(smem_u32(&empty[s]), C::CONS_WARPS);
             }
           asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -193,9 +200,9 @@ namespace gf
         int(blockIdx.x) < n_tiles ? (n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
       double dot = 0.0;
 
-      if (warp == C::CONSUMER_WARPS)
+      if (warp == 0)
         {
-          // ------------------------------ producer warp --------------------------------------
+          // ------------------------------ producer warp: TMA ---------------------------------
           TileDesc d{};
           for (int k = 0; k < n_my; ++k)
             {
@@ -212,57 +219,88 @@ namespace gf
               const int       col_count = __shfl_sync(0xffffffffu, d.col_count, src_lane);
               const int       s         = k % C::STAGES;
               if (k >= C::STAGES) // stage s was last used by tile k - STAGES
-                mbar_wait(smem_u32(&bars[C::STAGES + s]), ((k / C::STAGES) - 1) & 1);
+                mbar_wait(smem_u32(&empty[s]), ((k / C::STAGES) - 1) & 1);
               if (lane == 0)
                 {
                   const int64_t  t     = int64_t(blockIdx.x) + int64_t(k) * gridDim.x;
                   unsigned char *stage = smem + s * C::STAGE_BYTES;
-                  const uint32_t full  = smem_u32(&bars[s]);
+                  const uint32_t fb    = smem_u32(&full[s]);
                   const uint32_t vb = uint32_t(val_count) * 8u, cb = uint32_t(col_count) * 4u;
-                  mbar_arrive_expect_tx(full, vb + cb + uint32_t(C::META_BYTES));
-                  bulk_g2s(smem_u32(stage), val + val_off, vb, full);
-                  bulk_g2s(smem_u32(stage + C::VAL_BYTES), bcol + col_off, cb, full);
+                  mbar_arrive_expect_tx(fb, vb + cb + uint32_t(C::META_BYTES));
+                  bulk_g2s(smem_u32(stage), val + val_off, vb, fb);
+                  bulk_g2s(smem_u32(stage + C::VAL_BYTES), bcol + col_off, cb, fb);
                   bulk_g2s(smem_u32(stage + C::VAL_BYTES + C::COL_BYTES), tile_meta + t * SPMV_META,
-                           uint32_t(C::META_BYTES), full);
+                           uint32_t(C::META_BYTES), fb);
                 }
               __syncwarp();
             }
         }
-      else
+      else if (warp <= C::GATHER_WARPS)
         {
-          // ------------------------------ consumer warps -------------------------------------
+          // ---------------- gather warps: x[col] -> shared, many independent loads per lane ----
+          const int g = (warp - 1) * 32 + lane;
           for (int k = 0; k < n_my; ++k)
             {
               const int s = k % C::STAGES;
-              mbar_wait(smem_u32(&bars[s]), (k / C::STAGES) & 1);
-              const unsigned char *stage = smem + s * C::STAGE_BYTES;
-              const double *       sval  = reinterpret_cast<const double *>(stage);
-              const int32_t *scol = reinterpret_cast<const int32_t *>(stage + C::VAL_BYTES);
+              mbar_wait(smem_u32(&full[s]), (k / C::STAGES) & 1);
+              unsigned char *stage = smem + s * C::STAGE_BYTES;
+              const int32_t *scol  = reinterpret_cast<const int32_t *>(stage + C::VAL_BYTES);
               const uint2 *  smeta =
                 reinterpret_cast<const uint2 *>(stage + C::VAL_BYTES + C::COL_BYTES);
+              double *sx =
+                reinterpret_cast<double *>(stage + C::VAL_BYTES + C::COL_BYTES + C::META_PAD);
+              const int nblk = int(smeta[SPMV_TILE_ROWS + 1].x);
+#pragma unroll 4
+              for (int j = g; j < nblk; j += C::GATHER_WARPS * 32)
+                {
+                  const int64_t col = scol[j];
+#pragma unroll
+                  for (int d0 = 0; d0 < DIM; ++d0)
+                    sx[j * DIM + d0] = __ldg(x + col * DIM + d0);
+                }
+              __syncwarp();
+              if (lane == 0)
+                mbar_arrive(smem_u32(&xfull[s]));
+            }
+        }
+      else
+        {
+          // ------------------------------ consumer warps: shared-memory FMA --------------------
+          const int cw = warp - 1 - C::GATHER_WARPS;
+          for (int k = 0; k < n_my; ++k)
+            {
+              const int s = k % C::STAGES;
+              mbar_wait(smem_u32(&full[s]), (k / C::STAGES) & 1);
+              mbar_wait(smem_u32(&xfull[s]), (k / C::STAGES) & 1);
+              const unsigned char *stage = smem + s * C::STAGE_BYTES;
+              const double *       sval  = reinterpret_cast<const double *>(stage);
+              const uint2 *        smeta =
+                reinterpret_cast<const uint2 *>(stage + C::VAL_BYTES + C::COL_BYTES);
+              const double *sx = reinterpret_cast<const double *>(stage + C::VAL_BYTES +
+                                                                  C::COL_BYTES + C::META_PAD);
               const uint2 hdr    = smeta[SPMV_TILE_ROWS];
               const int   row0   = int(hdr.x);
               const int   n_rows = int(hdr.y);
-              for (int row = warp; row < n_rows; row += C::CONSUMER_WARPS)
+              for (int row = cw; row < n_rows; row += C::CONS_WARPS)
                 {
-                  const uint2    m      = smeta[row];
-                  const int      ne     = int(m.y >> 16) * DIM;
-                  const int      stride = (ne + 1) & ~1;
-                  const double * v      = sval + m.x;
-                  const int32_t *cl     = scol + (m.y & 0xffffu);
-                  double         acc[DIM];
+                  const uint2   m      = smeta[row];
+                  const int     ne     = int(m.y >> 16) * DIM;
+                  const int     stride = (ne + 1) & ~1;
+                  const double *v      = sval + m.x;
+                  const double *xr     = sx + int(m.y & 0xffffu) * DIM; // x of this row, contiguous
+                  const int64_t i      = int64_t(row0 + row) * DIM + lane;
+                  double        xi     = 0.0;
+                  if (DOT && lane < DIM)
+                    xi = __ldg(x + i);
+                  double acc[DIM];
 #pragma unroll
                   for (int r = 0; r < DIM; ++r)
                     acc[r] = 0.0;
 #pragma unroll 3
                   for (int e = 2 * lane; e < ne; e += 64)
                     {
-                      const int    e1 = e + 1;
-                      const int    k0 = e / DIM, k1 = e1 / DIM;
-                      const double x0 = __ldg(x + int64_t(cl[k0]) * DIM + (e - k0 * DIM));
-                      double       x1 = 0.0;
-                      if (e1 < ne)
-                        x1 = __ldg(x + int64_t(cl[k1]) * DIM + (e1 - k1 * DIM));
+                      const double x0 = xr[e];
+                      const double x1 = (e + 1 < ne) ? xr[e + 1] : 0.0;
 #pragma unroll
                       for (int r = 0; r < DIM; ++r)
                         {
@@ -281,26 +319,26 @@ namespace gf
                       for (int r = 1; r < DIM; ++r)
                         if (lane == r)
                           yr = acc[r];
-                      const int64_t i = int64_t(row0 + row) * DIM + lane;
-                      y[i]            = yr;
+                      y[i] = yr;
                       if (DOT)
-                        dot = fma(yr, x[i], dot);
+                        dot = fma(yr, xi, dot);
                     }
                 }
               __syncwarp();
               if (lane == 0)
-                mbar_arrive(smem_u32(&bars[C::STAGES + s])); // release the stage
+                mbar_arrive(smem_u32(&empty[s])); // release the stage
             }
         }
       if (DOT)
         {
-          dot = warp_sum(dot);
-          if (lane == 0 && warp < C::CONSUMER_WARPS)
-            red[warp] = dot;
+          const int cw = warp - 1 - C::GATHER_WARPS;
+          dot          = warp_sum(dot);
+          if (lane == 0 && cw >= 0)
+            red[cw] = dot;
           __syncthreads();
           if (tid < 32)
             {
-              double v = tid < C::CONSUMER_WARPS ? red[tid] : 0.0;
+              double v = tid < C::CONS_WARPS ? red[tid] : 0.0;
               v        = warp_sum(v);
               if (tid == 0)
                 partials[blockIdx.x] = v;
