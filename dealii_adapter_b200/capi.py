@@ -20,8 +20,9 @@ LIN_OLD_VELOCITY, LIN_VELOCITY, LIN_OLD_DISPLACEMENT, LIN_DISPLACEMENT, LIN_OLD_
     LIN_SYSTEM_RHS, LIN_BODY_FORCE = range(16, 24)
 VEC_SCRATCH0, VEC_SCRATCH1 = 28, 29
 MAT_TANGENT, MAT_STIFFNESS, MAT_MASS, MAT_SYSTEM = range(4)
-PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI = range(3)
-OPT_PRECONDITIONER, OPT_CG_CHECK_INTERVAL, OPT_PROFILE, OPT_OPERATOR, OPT_SPMV_KERNEL = range(5)
+PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI, PRECOND_MULTIGRID = range(4)
+OPT_PRECONDITIONER, OPT_CG_CHECK_INTERVAL, OPT_PROFILE, OPT_OPERATOR, OPT_SPMV_KERNEL, \
+    OPT_MG_SMOOTHER_DEGREE, OPT_MG_COARSE_DEGREE = range(7)
 
 EXPORTED_SYMBOLS = [
     "gf_create", "gf_destroy", "gf_last_error", "gf_set_option", "gf_comm_unique_id",
@@ -29,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "gf_state_save", "gf_state_restore", "gf_nl_begin_step", "gf_nl_newton_assemble",
     "gf_nl_newton_solve", "gf_nl_end_step", "gf_lin_assemble_once", "gf_lin_step", "gf_get_vector",
     "gf_set_vector", "gf_nnz", "gf_export_csr", "gf_spmv", "gf_spmv_timed", "gf_profile_get",
-    "gf_synchronize", "gf_event_record", "gf_event_elapsed_ms",
+    "gf_synchronize", "gf_event_record", "gf_event_elapsed_ms", "gf_mg_attach", "gf_mg_vcycle",
 ]
 
 
@@ -113,6 +114,8 @@ def lib():
         L.gf_profile_get.argtypes = [vp, C.POINTER(GfProfile), i32]
         L.gf_event_record.argtypes = [vp, i32]
         L.gf_event_elapsed_ms.argtypes = [vp, i32, i32, C.POINTER(dbl)]
+        L.gf_mg_attach.argtypes = [vp, vp, vp]
+        L.gf_mg_vcycle.argtypes = [vp, i32, i32]
         _lib = L
     return _lib
 
@@ -233,6 +236,16 @@ class Handle:
 
     def set_option(self, opt, value):
         self._check(lib().gf_set_option(self._h, opt, int(value)))
+
+    def mg_attach(self, coarse, child_cells):
+        """Link `coarse` (a Handle of the next coarser refinement level) below this level;
+        child_cells[coarse_cell, k] = this level's local cell index of cell->child(k) or -1."""
+        cc = np.ascontiguousarray(child_cells, dtype=np.int32)
+        self._check(lib().gf_mg_attach(self._h, coarse._h, cc.ctypes.data))
+        self._mg_coarse = coarse  # keep the coarse handle alive as long as this one
+
+    def mg_vcycle(self, which_b, which_x):
+        self._check(lib().gf_mg_vcycle(self._h, which_b, which_x))
 
     # -- Adapter bodies
     def set_traction(self, iface_buf):

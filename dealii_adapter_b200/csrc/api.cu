@@ -198,7 +198,7 @@ namespace gf
   ProfScope::ProfScope(gf_context &ctx, int kind, int n_kernels)
     : c(ctx)
   {
-    Profile &p = c.prof;
+    Profile &p = *c.prof_sink;
     p.launches[kind]++;
     p.kernel_launches += n_kernels;
     if (!p.enabled)
@@ -223,11 +223,11 @@ namespace gf
   ProfScope::~ProfScope()
   {
     if (idx >= 0)
-      cudaEventRecord(c.prof.pool[c.prof.pending[idx].e1], c.stream);
+      cudaEventRecord(c.prof_sink->pool[c.prof_sink->pending[idx].e1], c.stream);
   }
   void profile_collect(gf_context &c)
   {
-    Profile &p = c.prof;
+    Profile &p = *c.prof_sink;
     if (p.pending.empty())
       return;
     cudaStreamSynchronize(c.stream);
@@ -239,6 +239,30 @@ namespace gf
       }
     p.pending.clear();
     p.next_event = 0;
+  }
+} // namespace gf
+
+namespace gf
+{
+  // ElastoDynamics::assemble_system (linear_elasticity.cc:248-374) for one level
+  void lin_assemble(gf_context &c)
+  {
+    for (int64_t c0 = 0; c0 < c.n_cells; c0 += c.ke_chunk_cells)
+      {
+        const int64_t c1 = std::min(c.n_cells, c0 + c.ke_chunk_cells);
+        launch_lin_cells(c, c0, c1);
+        launch_scatter_matrix(c, c.mat[GF_MAT_STIFFNESS].val.p, c0, c1, c0 == 0, false);
+        launch_scatter_mass(c, c0, c1, c0 == 0);
+      }
+    const double dt = c.desc.delta_t, theta = c.desc.theta;
+    launch_build_system_matrix(c, dt * dt * theta * theta); // :348-353, :426-451
+    launch_build_precond(c, c.mat[GF_MAT_SYSTEM].val.p);
+    double bn = 0;
+    for (int k = 0; k < 3; ++k)
+      bn += c.desc.body_force[k] * c.desc.body_force[k];
+    if (std::sqrt(bn) > 1e-15) // body_force_enabled :62
+      launch_body_force(c, c.vec[GF_LIN_BODY_FORCE].p);
+    c.lin_assembled = true;
   }
 } // namespace gf
 
@@ -331,8 +355,20 @@ extern "C"
     if (!h)
       return;
     cudaSetDevice(h->device);
-    if (h->stream)
-      cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->stream);
+    // unlink from a multigrid chain: the coarser levels below stop using this level's stream
+    if (h->mg_finer)
+      h->mg_finer->mg.coarse = nullptr;
+    if (h->mg.coarse)
+      {
+        h->mg.coarse->mg_finer = nullptr;
+        for (gf_context *l = h->mg.coarse; l != nullptr; l = l->mg.coarse)
+          if (l->stream == h->stream && !l->owns_stream)
+            {
+              l->stream    = nullptr; // legacy default stream; only used by its own gf_destroy
+              l->prof_sink = &l->prof;
+            }
+      }
     for (auto e : h->prof.pool)
       cudaEventDestroy(e);
     for (auto e : h->prof.user_events)
@@ -344,7 +380,7 @@ extern "C"
       cudaFreeHost(h->h_norm);
     if (h->h_err)
       cudaFreeHost(h->h_err);
-    cudaStream_t s = h->stream;
+    cudaStream_t s = h->owns_stream ? h->stream : nullptr;
     delete h;
     if (s)
       cudaStreamDestroy(s);
@@ -356,7 +392,7 @@ extern "C"
       switch (option)
         {
           case GF_OPT_PRECONDITIONER:
-            GF_REQUIRE(value >= GF_PRECOND_NONE && value <= GF_PRECOND_BLOCK_JACOBI,
+            GF_REQUIRE(value >= GF_PRECOND_NONE && value <= GF_PRECOND_MULTIGRID,
                        GF_ERR_INVALID_ARG, "unknown preconditioner");
             c.precond = int(value);
             if (c.model == GF_MODEL_LINEAR && c.lin_assembled)
@@ -376,11 +412,45 @@ extern "C"
             break;
           case GF_OPT_SPMV_KERNEL:
             GF_REQUIRE(value == 0 || value == 1, GF_ERR_INVALID_ARG, "unknown SpMV kernel");
-            c.spmv_kernel_kind = int(value);
+            for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
+              l->spmv_kernel_kind = int(value);
+            break;
+          case GF_OPT_MG_SMOOTHER_DEGREE:
+            GF_REQUIRE(value >= 1 && value <= 16, GF_ERR_INVALID_ARG, "bad smoother degree");
+            for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
+              l->mg_smoother_degree = int(value);
+            break;
+          case GF_OPT_MG_COARSE_DEGREE:
+            GF_REQUIRE(value >= 1 && value <= 1000, GF_ERR_INVALID_ARG, "bad coarse degree");
+            for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
+              l->mg_coarse_degree = int(value);
             break;
           default:
             throw gf::Error{GF_ERR_INVALID_ARG, "unknown option"};
         }
+      return GF_OK;
+    });
+  }
+
+  int gf_mg_attach(gf_handle fine, gf_handle coarse, const int32_t *child_cells)
+  {
+    return guarded(fine, [&](gf_context &c) {
+      GF_REQUIRE(coarse != nullptr, GF_ERR_INVALID_ARG, "null coarse handle");
+      gf::mg_attach(c, *coarse, child_cells);
+      coarse->mg_finer = &c;
+      return GF_OK;
+    });
+  }
+
+  int gf_mg_vcycle(gf_handle h, int which_b, int which_x)
+  {
+    return guarded(h, [&](gf_context &c) {
+      double *b = vec_ptr(c, which_b), *x = vec_ptr(c, which_x);
+      GF_REQUIRE(b != x, GF_ERR_INVALID_ARG, "b and x must differ");
+      GF_REQUIRE(c.mg.coarse != nullptr && c.mg_lmax > 0.0, GF_ERR_INVALID_ARG,
+                 "multigrid hierarchy not attached / operators not assembled");
+      gf::mg_vcycle(c, b, x);
+      GF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
       return GF_OK;
     });
   }
@@ -470,6 +540,8 @@ extern "C"
       gf::launch_nl_faces(c, c.tmp0.p, c.vec[GF_NL_EXTERNAL_STRESS].p);
       gf::launch_scatter_rhs(c, c.vec[GF_NL_SYSTEM_RHS].p, true);
       gf::launch_build_precond(c, K);
+      if (gf::mg_active(c))
+        gf::mg_update_operators(c, c.tmp0.p); // coarse tangents at the injected state + smoothers
       const double r = gf::vec_masked_norm(c, c.vec[GF_NL_SYSTEM_RHS].p, true); // :449
       GF_CUDA_CHECK(
         cudaMemcpyAsync(c.h_err, c.err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
@@ -556,23 +628,9 @@ extern "C"
   {
     return guarded(h, [&](gf_context &c) {
       GF_REQUIRE(c.model == GF_MODEL_LINEAR, GF_ERR_INVALID_ARG, "not a linear handle");
-      for (int64_t c0 = 0; c0 < c.n_cells; c0 += c.ke_chunk_cells)
-        {
-          const int64_t c1 = std::min(c.n_cells, c0 + c.ke_chunk_cells);
-          gf::launch_lin_cells(c, c0, c1);
-          gf::launch_scatter_matrix(c, c.mat[GF_MAT_STIFFNESS].val.p, c0, c1, c0 == 0, false);
-          gf::launch_scatter_mass(c, c0, c1, c0 == 0);
-        }
-      const double dt = c.desc.delta_t, theta = c.desc.theta;
-      gf::launch_build_system_matrix(c, dt * dt * theta * theta); // :348-353, :426-451
-      gf::launch_build_precond(c, c.mat[GF_MAT_SYSTEM].val.p);
-      double bn = 0;
-      for (int k = 0; k < 3; ++k)
-        bn += c.desc.body_force[k] * c.desc.body_force[k];
-      if (std::sqrt(bn) > 1e-15) // body_force_enabled :62
-        gf::launch_body_force(c, c.vec[GF_LIN_BODY_FORCE].p);
+      gf::lin_assemble(c);
+      gf::mg_update_operators(c, nullptr); // coarser levels (if linked) assemble their own A
       GF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
-      c.lin_assembled = true;
       return GF_OK;
     });
   }
@@ -810,6 +868,10 @@ extern "C"
       out->update_launches         = p.launches[gf::Profile::UPDATE];
       out->halo_launches           = p.launches[gf::Profile::HALO];
       out->kernel_launches         = p.kernel_launches;
+      out->mg_spmv_ms              = p.ms[gf::Profile::MG_SPMV];
+      out->mg_vector_ms            = p.ms[gf::Profile::MG_VEC];
+      out->mg_spmv_launches        = p.launches[gf::Profile::MG_SPMV];
+      out->mg_vector_launches      = p.launches[gf::Profile::MG_VEC];
       if (reset)
         {
           for (int k = 0; k < gf::Profile::N_KINDS; ++k)

@@ -61,6 +61,31 @@ namespace gf
           s->alpha = s->rz / s->pAp;
           return;
         }
+      if (phase == 3 || phase == 4) // multigrid CG: residual check BEFORE the preconditioner
+        {
+          const double rr = sums[0];
+          s->it           = phase == 3 ? 0 : s->it + 1;
+          if (phase == 3)
+            {
+              s->res0 = sqrt(fabs(rr));
+              s->beta = 0.0;
+              s->rz   = 0.0;
+            }
+          s->rr  = rr;
+          s->res = sqrt(fabs(rr));
+          if (s->res <= s->tol)
+            s->status = 1;
+          else if (s->it >= s->maxit || s->res != s->res)
+            s->status = 2;
+          return;
+        }
+      if (phase == 5) // multigrid CG: r.z after the V-cycle
+        {
+          const double rz = sums[0];
+          s->beta         = s->rz != 0.0 ? rz / s->rz : 0.0;
+          s->rz           = rz;
+          return;
+        }
       const double rr = sums[0], rz = sums[1];
       if (phase == 0)
         {
@@ -160,6 +185,21 @@ namespace gf
         p[i] = fma(beta, p[i], z[i]);
     }
 
+    // partial sums of a . b (owned entries)
+    __global__ void __launch_bounds__(VEC_THREADS)
+      dot_kernel(const int64_t n, const double *__restrict__ a, const double *__restrict__ b,
+                 double *__restrict__ partials)
+    {
+      __shared__ double sm[32];
+      double            acc[1] = {0.0};
+      for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n;
+           i += int64_t(gridDim.x) * blockDim.x)
+        acc[0] = fma(a[i], b[i], acc[0]);
+      block_sum<1>(acc, sm);
+      if (threadIdx.x == 0)
+        partials[blockIdx.x] = acc[0];
+    }
+
     int vec_grid(const gf_context &c, int64_t n)
     {
       const int64_t want = (n + VEC_THREADS - 1) / VEC_THREADS;
@@ -178,12 +218,100 @@ namespace gf
     }
   } // namespace
 
+  // The same recurrences with z = V-cycle(r). One CG iteration is now several milliseconds of
+  // device work, so the host reads the SolverControl state after every residual update (before
+  // the V-cycle is enqueued) instead of every cg_check_every iterations.
+  static int cg_solve_mg(gf_context &c, const double *val, double *x, const double *b, double tol,
+                         int64_t maxit, uint32_t *last_step, double *last_value)
+  {
+    GF_REQUIRE(mg_active(c), GF_ERR_INVALID_ARG,
+               "GF_PRECOND_MULTIGRID selected but no coarse level is attached (gf_mg_attach)");
+    for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
+      GF_REQUIRE(l->mg_lmax > 0.0, GF_ERR_INVALID_ARG,
+                 "multigrid operators not built: attach the levels before assembling");
+    cudaStream_t s = c.stream;
+    CGScalars    init{};
+    init.tol     = tol;
+    init.maxit   = int(std::min<int64_t>(maxit, 2147483647));
+    init.status  = 0;
+    *c.h_scalars = init;
+    GF_CUDA_CHECK(cudaMemcpyAsync(c.cg_scalars.p, c.h_scalars, sizeof(CGScalars),
+                                  cudaMemcpyHostToDevice, s));
+    GF_CUDA_CHECK(cudaMemsetAsync(c.cg_p.p, 0, c.n_local * sizeof(double), s));
+    const int64_t n_nodes = c.n_owned_nodes;
+    const int     ug = vec_grid(c, n_nodes), dg = vec_grid(c, c.n_owned);
+    const int     sg_rows = spmv_dot_partials(c);
+    auto update = [&](bool startup) {
+      ProfScope ps(c, Profile::CG_VEC, 3);
+      if (c.dim == 3)
+        {
+          if (startup)
+            cg_update_kernel<3, true><<<ug, VEC_THREADS, 0, s>>>(
+              n_nodes, c.cg_scalars.p, b, nullptr, c.cg_v.p, c.dinv.p, x, c.cg_r.p, c.cg_z.p,
+              c.partials.p, c.max_red_blocks);
+          else
+            cg_update_kernel<3, false><<<ug, VEC_THREADS, 0, s>>>(
+              n_nodes, c.cg_scalars.p, b, c.cg_p.p, c.cg_v.p, c.dinv.p, x, c.cg_r.p, c.cg_z.p,
+              c.partials.p, c.max_red_blocks);
+        }
+      else
+        {
+          if (startup)
+            cg_update_kernel<2, true><<<ug, VEC_THREADS, 0, s>>>(
+              n_nodes, c.cg_scalars.p, b, nullptr, c.cg_v.p, c.dinv.p, x, c.cg_r.p, c.cg_z.p,
+              c.partials.p, c.max_red_blocks);
+          else
+            cg_update_kernel<2, false><<<ug, VEC_THREADS, 0, s>>>(
+              n_nodes, c.cg_scalars.p, b, c.cg_p.p, c.cg_v.p, c.dinv.p, x, c.cg_r.p, c.cg_z.p,
+              c.partials.p, c.max_red_blocks);
+        }
+      reduce_and_scalar(c, ug, 1, startup ? 3 : 4); // r.r -> residual check
+    };
+    auto poll = [&]() {
+      GF_CUDA_CHECK(cudaMemcpyAsync(c.h_scalars, c.cg_scalars.p, sizeof(CGScalars),
+                                    cudaMemcpyDeviceToHost, s));
+      GF_CUDA_CHECK(cudaStreamSynchronize(s));
+      return c.h_scalars->status;
+    };
+    // ---- startup: r = b - A x ; check ----
+    if (c.comm)
+      halo_exchange(c, x);
+    launch_spmv(c, val, x, c.cg_v.p, nullptr);
+    update(true);
+    GF_CUDA_CHECK(cudaGetLastError());
+    while (poll() == 0)
+      {
+        mg_vcycle(c, c.cg_r.p, c.cg_z.p); // z = M^-1 r
+        {
+          ProfScope ps(c, Profile::CG_VEC, 4);
+          dot_kernel<<<dg, VEC_THREADS, 0, s>>>(c.n_owned, c.cg_r.p, c.cg_z.p, c.partials.p);
+          reduce_and_scalar(c, dg, 1, 5); // r.z, beta
+          cg_direction_kernel<<<dg, VEC_THREADS, 0, s>>>(c.n_owned, c.cg_scalars.p, c.cg_z.p,
+                                                         c.cg_p.p);
+        }
+        if (c.comm)
+          halo_exchange(c, c.cg_p.p);
+        launch_spmv(c, val, c.cg_p.p, c.cg_v.p, c.partials.p);
+        {
+          ProfScope ps(c, Profile::CG_VEC, 2);
+          reduce_and_scalar(c, sg_rows, 1, 1);
+        }
+        update(false);
+        GF_CUDA_CHECK(cudaGetLastError());
+      }
+    *last_step  = uint32_t(c.h_scalars->it);
+    *last_value = c.h_scalars->res;
+    return c.h_scalars->status == 1 ? GF_OK : GF_ERR_NOT_CONVERGED;
+  }
+
   int cg_solve(gf_context &c, const double *val, double *x, const double *b, double tol,
                bool tol_relative_to_rhs, int64_t maxit, uint32_t *last_step, double *last_value)
   {
     cudaStream_t s = c.stream;
     if (tol_relative_to_rhs)
       tol *= vec_masked_norm(c, b, false); // tol_lin * system_rhs.l2_norm() (:1171-1172)
+    if (c.precond == GF_PRECOND_MULTIGRID)
+      return cg_solve_mg(c, val, x, b, tol, maxit, last_step, last_value);
     CGScalars init{};
     init.tol    = tol;
     init.maxit  = int(std::min<int64_t>(maxit, 2147483647));

@@ -97,6 +97,15 @@ namespace gf
       if (k < n)
         v[idx[k]] = buf[k];
     }
+    // v[idx[k]] += buf[k] for ONE neighbour's list (its targets are distinct); the neighbours
+    // are processed by consecutive launches, i.e. in a fixed order
+    __global__ void unpack_add_kernel(int64_t n, const int32_t *__restrict__ idx,
+                                      const double *__restrict__ buf, double *__restrict__ v)
+    {
+      const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+      if (k < n)
+        v[idx[k]] += buf[k];
+    }
   } // namespace
 
   // exchange ghost values of v with the slab neighbours (grouped ncclSend/ncclRecv)
@@ -128,6 +137,45 @@ namespace gf
     if (nr)
       unpack_kernel<<<unsigned((nr + 255) / 256), 256, 0, c.stream>>>(nr, c.recv_idx.p,
                                                                      c.recv_buf.p, v);
+    GF_CUDA_CHECK(cudaGetLastError());
+  }
+
+  // reverse halo: every rank sends the values it accumulated on its GHOST dofs to their owners,
+  // which add them to their own value in neighbour order (fixed => reproducible). Used by the
+  // multigrid restriction, whose partial sums are taken over owned fine nodes only.
+  void halo_reduce_add(gf_context &c, double *v)
+  {
+    if (!c.comm || c.nbr_rank.empty())
+      return;
+    ProfScope     ps(c, Profile::HALO, 2);
+    NcclApi &     api = nccl();
+    const int64_t ns = c.send_ptr.back(), nr = c.recv_ptr.back();
+    if (nr)
+      pack_kernel<<<unsigned((nr + 255) / 256), 256, 0, c.stream>>>(nr, c.recv_idx.p, v,
+                                                                   c.recv_buf.p);
+    nccl_check(api.GroupStart(), "ncclGroupStart");
+    for (size_t k = 0; k < c.nbr_rank.size(); ++k)
+      {
+        const int64_t s0 = c.send_ptr[k], s1 = c.send_ptr[k + 1];
+        const int64_t r0 = c.recv_ptr[k], r1 = c.recv_ptr[k + 1];
+        if (r1 > r0)
+          nccl_check(api.Send(c.recv_buf.p + r0, size_t(r1 - r0), NCCL_FLOAT64, c.nbr_rank[k],
+                              c.comm->nccl_comm, c.stream),
+                     "ncclSend");
+        if (s1 > s0)
+          nccl_check(api.Recv(c.send_buf.p + s0, size_t(s1 - s0), NCCL_FLOAT64, c.nbr_rank[k],
+                              c.comm->nccl_comm, c.stream),
+                     "ncclRecv");
+      }
+    nccl_check(api.GroupEnd(), "ncclGroupEnd");
+    for (size_t k = 0; k < c.nbr_rank.size(); ++k)
+      {
+        const int64_t s0 = c.send_ptr[k], n = c.send_ptr[k + 1] - s0;
+        if (n)
+          unpack_add_kernel<<<unsigned((n + 255) / 256), 256, 0, c.stream>>>(
+            n, c.send_idx.p + s0, c.send_buf.p + s0, v);
+      }
+    (void)ns;
     GF_CUDA_CHECK(cudaGetLastError());
   }
 

@@ -142,6 +142,22 @@ namespace gf
 
   struct Comm; // comm.cu
 
+  // Geometric multigrid (multigrid.cu): data one level keeps about the next COARSER level.
+  struct MGTransfer
+  {
+    gf_context *        coarse = nullptr; // not owned (the host destroys every level handle)
+    int                 n_child = 0;      // 2^dim
+    DevBuf<int32_t>     parent;           // [n_cells] coarse_cell*n_child + child index
+    DevBuf<int32_t>     child_cells;      // [coarse n_cells*n_child] local fine cell or -1
+    DevBuf<uint8_t>     first_owner;      // [n_cells*npc] 1: this (cell, a) is the node's first
+                                          // appearance AND the node is owned by this rank
+    DevBuf<double>      E;                // [n_child][npc][npc] embedding N_b^coarse(node a of child k)
+    DevBuf<int32_t>     rl_ptr;           // [npc+1] per coarse local node b: non-zero (k, a) list
+    DevBuf<int32_t>     rl_ka;            // k*npc + a
+    DevBuf<double>      rl_w;             // E[k][a][b]
+    DevBuf<int32_t>     inj;              // [npc] k*npc + a of the fine node coinciding with b
+  };
+
   struct Profile
   {
     enum Kind
@@ -153,6 +169,8 @@ namespace gf
       CG_VEC,
       UPDATE,
       HALO,
+      MG_SPMV, // SpMV launches on the coarser multigrid levels
+      MG_VEC,  // multigrid smoother / transfer vector kernels (all levels)
       N_KINDS
     };
     bool                     enabled = false;
@@ -182,6 +200,7 @@ struct gf_context
   gf_desc      desc{}; // pointers inside are NOT valid after gf_create
   std::string  last_error;
   cudaStream_t stream = nullptr;
+  bool         owns_stream = true; // coarser multigrid levels run on the finest level's stream
   int          dim = 0, p = 0, npc = 0, dpc = 0, model = 0, device = 0;
   int          sm_count = 148;
 
@@ -264,7 +283,18 @@ struct gf_context
   gf::DevBuf<int32_t> send_idx, recv_idx; // internal dof ids
   gf::DevBuf<double>  send_buf, recv_buf;
 
-  gf::Profile prof;
+  // geometric multigrid preconditioner (multigrid.cu)
+  gf::MGTransfer     mg;             // link to the next coarser level (mg.coarse == nullptr: none)
+  gf_context *       mg_finer = nullptr; // back link (for safe destruction in any order)
+  int                mg_level = 0;   // 0 = finest
+  gf::DevBuf<double> mg_b, mg_x, mg_r, mg_d, mg_v, mg_e; // rhs, solution, residual, direction, A d, eigvec
+  double             mg_lmax = 0.0;  // estimate of lambda_max(D^-1 A) of the current operator
+  bool               mg_e_valid = false;
+  int                mg_smoother_degree = 3, mg_coarse_degree = 40;
+  double             mg_smoother_ratio = 20.0, mg_coarse_ratio = 1000.0;
+
+  gf::Profile  prof;
+  gf::Profile *prof_sink = &prof; // coarser multigrid levels account into the finest level
 };
 
 namespace gf
@@ -309,7 +339,15 @@ namespace gf
   void   vec_zero_constrained(gf_context &c, double *v);
   void   iface_scatter(gf_context &c, const double *host_buf, double *vec);
   void   iface_gather(gf_context &c, const double *vec, double *host_buf);
+  // api.cu: body of ElastoDynamics::assemble_system for one level
+  void lin_assemble(gf_context &c);
+  // multigrid.cu
+  void mg_attach(gf_context &fine, gf_context &coarse, const int32_t *child_cells);
+  void mg_update_operators(gf_context &c, const double *u_total); // after the finest assembly
+  void mg_vcycle(gf_context &c, const double *b, double *x);      // x = MG(b)
+  bool mg_active(const gf_context &c);
   // comm.cu
+  void halo_reduce_add(gf_context &c, double *v); // ghost partial sums -> owners (+=)
   void halo_exchange(gf_context &c, double *v);
   void allreduce_sum(gf_context &c, double *dev_values, int count);
   // profile helpers

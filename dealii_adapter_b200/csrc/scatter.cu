@@ -241,7 +241,7 @@ namespace gf
           for (int r = 0; r < DIM; ++r)
             R[r][r] = 1.0 / M[r][r];
         }
-      else if (kind == GF_PRECOND_BLOCK_JACOBI)
+      else if (kind >= GF_PRECOND_BLOCK_JACOBI) // multigrid smoothers use the block inverse too
         {
           // symmetrise before inverting so that the preconditioner is exactly symmetric
 #pragma unroll

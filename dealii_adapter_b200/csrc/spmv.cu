@@ -410,7 +410,7 @@ namespace gf
   void launch_spmv(gf_context &c, const double *val, const double *x, double *y,
                    double *dot_partials)
   {
-    ProfScope     ps(c, Profile::SPMV);
+    ProfScope     ps(c, c.mg_level > 0 ? Profile::MG_SPMV : Profile::SPMV);
     const int64_t n_rows = c.n_owned_nodes;
     if (n_rows == 0)
       return;

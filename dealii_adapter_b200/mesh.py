@@ -87,6 +87,7 @@ class StructuredMesh:
         self.dim, self.degree = dim, degree
         self.reps = list(reps)
         self.p0, self.p1 = list(p0), list(p1)
+        self.numbering = numbering
         r = (C.c_int * 3)(*(list(reps) + [1] * (3 - dim)))
         a = (C.c_double * 3)(*(list(p0) + [0.0] * (3 - dim)))
         b = (C.c_double * 3)(*(list(p1) + [0.0] * (3 - dim)))

@@ -1,0 +1,81 @@
+"""Host side of the geometric multigrid preconditioner (C-ABI: gf_mg_attach).
+
+In the reference the mesh is `subdivided_hyper_rectangle` followed by `refine_global(n)`
+(nonlinear_elasticity.cc:237-246, linear_elasticity.cc:143-151), so the host owns a refinement
+hierarchy: level cells and cell->child(k). This module builds the same information for the
+structured stand-in mesh: one Problem per level (the same box with halved repetitions, same
+boundary roles) and, per level pair, the child table in deal.II child order (k = kx + 2 ky + 4 kz).
+"""
+import numpy as np
+
+from . import capi
+from .problem import make_problem
+
+
+def coarsen_problem(problem):
+    """The next coarser level of `problem` (every direction halved) or None if a repetition is odd."""
+    mesh = problem.mesh
+    if any(r % 2 for r in mesh.reps) or min(mesh.reps) < 2:
+        return None
+    reps = [r // 2 for r in mesh.reps]
+    return make_problem(problem.params, problem.dim, reps=reps, numbering=mesh.numbering,
+                        box=(mesh.p0, mesh.p1))
+
+
+def child_table(coarse_mesh, fine_mesh):
+    """[n_coarse_cells, 2^dim] GLOBAL fine cell index of child k (cells are lexicographic)."""
+    dim = coarse_mesh.dim
+    rc = list(coarse_mesh.reps) + [1] * (3 - dim)
+    rf = list(fine_mesh.reps) + [1] * (3 - dim)
+    k, j, i = np.meshgrid(np.arange(rc[2]), np.arange(rc[1]), np.arange(rc[0]), indexing="ij")
+    i, j, k = i.reshape(-1), j.reshape(-1), k.reshape(-1)   # coarse cell index = (k*ry + j)*rx + i
+    out = np.zeros((len(i), 1 << dim), dtype=np.int64)
+    for c in range(1 << dim):
+        fi, fj = 2 * i + (c & 1), 2 * j + ((c >> 1) & 1)
+        fk = 2 * k + ((c >> 2) & 1) if dim == 3 else k
+        out[:, c] = (fk * rf[1] + fj) * rf[0] + fi
+    return out
+
+
+class Hierarchy:
+    """Handles of all levels (levels[0] = finest), linked with gf_mg_attach. For a partitioned run
+    every level is slab-partitioned with the same (axis, world, rank); the slab boundaries of all
+    levels must coincide (repetitions along the axis divisible by world * 2^(levels-1))."""
+
+    def __init__(self, problem, device=0, n_levels=None, world=1, rank=0, comm=None, axis=1,
+                 min_cells=1):
+        self.problems = [problem]
+        while n_levels is None or len(self.problems) < n_levels:
+            nxt = coarsen_problem(self.problems[-1])
+            if nxt is None or nxt.mesh.n_cells < min_cells or \
+                    (world > 1 and nxt.mesh.reps[axis] < world):
+                break
+            self.problems.append(nxt)
+        self.partitions = [p.mesh.partition(axis, world, rank) if world > 1 else None
+                           for p in self.problems]
+        self.handles = [capi.Handle(p, device=device, partition=part, comm=comm)
+                        for p, part in zip(self.problems, self.partitions)]
+        for l in range(len(self.handles) - 1):
+            fine, coarse = self.problems[l], self.problems[l + 1]
+            tab = child_table(coarse.mesh, fine.mesh)
+            if world > 1:
+                g2l = -np.ones(fine.mesh.n_cells, dtype=np.int64)
+                pf, pc = self.partitions[l], self.partitions[l + 1]
+                g2l[pf.local_cell_global] = np.arange(pf.n_local_cells)
+                tab = g2l[tab[pc.local_cell_global]]
+                covered = np.zeros(pf.n_local_cells, dtype=bool)
+                covered[tab[tab >= 0]] = True
+                if not covered.all():
+                    raise ValueError("slab boundaries of multigrid levels %d and %d do not coincide"
+                                     % (l, l + 1))
+            self.handles[l].mg_attach(self.handles[l + 1], tab)
+        self.fine = self.handles[0]
+        self.fine.set_option(capi.OPT_PRECONDITIONER, capi.PRECOND_MULTIGRID)
+
+    @property
+    def n_levels(self):
+        return len(self.handles)
+
+    def close(self):
+        for h in self.handles:
+            h.close()

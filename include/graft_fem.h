@@ -115,7 +115,9 @@ extern "C"
   {
     GF_PRECOND_NONE = 0,
     GF_PRECOND_JACOBI,
-    GF_PRECOND_BLOCK_JACOBI /* dim x dim node blocks (default) */
+    GF_PRECOND_BLOCK_JACOBI, /* dim x dim node blocks (default) */
+    GF_PRECOND_MULTIGRID     /* geometric V-cycle over the levels linked with gf_mg_attach;
+                                Chebyshev/block-Jacobi smoothers */
   };
   enum
   {
@@ -123,7 +125,9 @@ extern "C"
     GF_OPT_CG_CHECK_INTERVAL,  /* iterations enqueued between host polls of the device flag */
     GF_OPT_PROFILE,            /* 1: bracket every kernel class with CUDA events (see gf_profile) */
     GF_OPT_OPERATOR,           /* 0: assembled BSR SpMV ; 1: matrix-free tangent operator in CG */
-    GF_OPT_SPMV_KERNEL         /* 0: TMA-tiled kernel (default) ; 1: LDG warp-per-row kernel */
+    GF_OPT_SPMV_KERNEL,        /* 0: TMA-tiled kernel (default) ; 1: LDG warp-per-row kernel */
+    GF_OPT_MG_SMOOTHER_DEGREE, /* Chebyshev degree of the pre-/post-smoother (default 3) */
+    GF_OPT_MG_COARSE_DEGREE    /* Chebyshev degree of the coarsest-level solve (default 40) */
   };
 
   /* device-time breakdown accumulated while GF_OPT_PROFILE = 1 (CUDA events on the library's
@@ -135,6 +139,10 @@ extern "C"
     int64_t assemble_cells_launches, assemble_faces_launches, scatter_launches, spmv_launches,
       cg_vector_launches, update_launches, halo_launches;
     int64_t kernel_launches; /* every kernel of this library launched since the last reset */
+    /* multigrid: SpMV launches on the coarser levels (spmv_* counts the finest level only) and
+     * the smoother / transfer vector kernels of all levels */
+    double  mg_spmv_ms, mg_vector_ms;
+    int64_t mg_spmv_launches, mg_vector_launches;
   } gf_profile;
 
   /* ---- life cycle -------------------------------------------------------------------------- */
@@ -143,6 +151,22 @@ extern "C"
   void        gf_destroy(gf_handle h);
   const char *gf_last_error(gf_handle h); /* h may be NULL: error of the last failed gf_create */
   int         gf_set_option(gf_handle h, int option, int64_t value);
+
+  /* ---- geometric multigrid hierarchy ---------------------------------------------------------
+   * The host owns the refinement hierarchy (triangulation.refine_global, nonlinear_elasticity.cc:
+   * 245-246, linear_elasticity.cc:150-151; in deal.II terms: the level cells and
+   * cell->child(k)). Every level is an ordinary handle created by gf_create on that level's cells
+   * (same parameters); gf_mg_attach links `coarse` below `fine`:
+   *   child_cells[coarse_cell*2^dim + k] = index (in fine's cell list) of cell->child(k), deal.II
+   *   child order (k = kx + 2 ky + 4 kz), or -1 if that child is not in this rank's cell list.
+   * Attach before the first assembly. With GF_OPT_PRECONDITIONER = GF_PRECOND_MULTIGRID on the
+   * finest handle, the CG of gf_nl_newton_solve / gf_lin_step is preconditioned by a V-cycle; the
+   * coarse operators are re-discretised by the library after every finest-level assembly. The
+   * caller keeps ownership of all handles and destroys each of them. */
+  int gf_mg_attach(gf_handle fine, gf_handle coarse, const int32_t *child_cells);
+  /* x = one V-cycle applied to b (zero initial guess) with the current operators; measurement and
+   * tests (the preconditioner must be symmetric positive definite for CG) */
+  int gf_mg_vcycle(gf_handle h, int which_b, int which_x);
 
   /* ---- multi-GPU plumbing: one process per GPU, NCCL over NVLink --------------------------- */
   /* rank 0 fills a 128-byte id, the host broadcasts it (torch.distributed / MPI), all ranks init */
