@@ -65,7 +65,9 @@ class GfProfile(C.Structure):
                [(n, C.c_int64) for n in
                 ("assemble_cells_launches", "assemble_faces_launches", "scatter_launches",
                  "spmv_launches", "cg_vector_launches", "update_launches", "halo_launches",
-                 "kernel_launches")]
+                 "kernel_launches")] + \
+               [("mg_spmv_ms", C.c_double), ("mg_vector_ms", C.c_double),
+                ("mg_spmv_launches", C.c_int64), ("mg_vector_launches", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
