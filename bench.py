@@ -8,8 +8,9 @@
 Workload (config.workload): BASELINE.json configs[2] — nonlinear_elasticity, perpendicular flap 3D,
 Q2 hexahedra 24x144x24 cells = 2,081,667 DoFs per GPU, neo-Hookean + Newmark, implicit coupling with
 checkpoint/restore (k=2 sub-iterations per window, FakeParticipant supplies a constant interface
-traction), CG rel. tol 1e-6 ("Residual"), block-Jacobi. It is the configuration the north_star target
-is quoted on and it fits one GPU. N>1: weak scaling, the flap is N times longer (24 x 144N x 24),
+traction), CG rel. tol 1e-6 ("Residual") preconditioned by the geometric multigrid V-cycle over the
+4-level refinement hierarchy (3x18x3 -> 24x144x24 cells; `--precond jacobi` selects the plain
+block-Jacobi CG instead). It is the configuration the north_star target is quoted on and it fits one GPU. N>1: weak scaling, the flap is N times longer (24 x 144N x 24),
 slab-partitioned along y, ghost-DoF halo + dot-product all-reduce over NCCL.
 
 A "step" is one pass through the coupling loop body (save/restore checkpoint, read traction, Newton
@@ -149,13 +150,17 @@ def main():
     ap.add_argument("--layers", type=int, default=CELLS_PER_GPU[1],
                     help="cell layers per GPU along the flap (debug; default = the named workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precond", default="mg", choices=["mg", "jacobi"],
+                    help="CG preconditioner: geometric multigrid V-cycle (default) or block-Jacobi")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = ("cfg3 nonlinear_elasticity PF 3D Q2 neo-Hookean, %dx%dx%d cells per GPU, implicit "
-                "coupling k=%d with checkpoint/restore, CG rel tol 1e-6 + block-Jacobi"
-                % (CELLS_PER_GPU[0], args.layers, CELLS_PER_GPU[2], N_SUB))
+                "coupling k=%d with checkpoint/restore, CG rel tol 1e-6 + %s"
+                % (CELLS_PER_GPU[0], args.layers, CELLS_PER_GPU[2], N_SUB,
+                   "geometric multigrid V-cycle (Chebyshev/block-Jacobi smoothers)"
+                   if args.precond == "mg" else "block-Jacobi"))
 
     if args.impl == "reference":
         if rank != 0:
@@ -175,7 +180,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from dealii_adapter_b200 import capi, solvers
+    from dealii_adapter_b200 import capi, multigrid, solvers
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -189,8 +194,14 @@ def main():
         comm = capi.Comm(bytes(idt.cpu().numpy().tobytes()), rank, world, local_rank)
 
     prob = make_flap(args.layers * world)
-    part = prob.mesh.partition(1, world, rank) if world > 1 else None
-    h = capi.Handle(prob, device=local_rank, partition=part, comm=comm)
+    hierarchy = None
+    if args.precond == "mg":
+        hierarchy = multigrid.Hierarchy(prob, device=local_rank, world=world, rank=rank, comm=comm,
+                                        axis=1)
+        h = hierarchy.fine
+    else:
+        part = prob.mesh.partition(1, world, rank) if world > 1 else None
+        h = capi.Handle(prob, device=local_rank, partition=part, comm=comm)
     n_if = h.n_iface_nodes
     buf = np.tile(TRACTION, n_if)
     participant = solvers.FakeParticipant(3, 10 ** 9, prob.params.delta_t, lambda t, it: buf, N_SUB)
@@ -220,11 +231,15 @@ def main():
     for k in range(n_warm):
         solid.step()
 
+    def cg_iterations(first_step):
+        return int(sum(r[0] for rows in solid.history[first_step:] for r in rows))
+
     sampler = ClockSampler(local_rank)
     # ---- timed region 1: device-resident inputs ("value"), profile events on ------------------
     h.set_option(capi.OPT_PROFILE, 1)
     h.profile(reset=True)
     s0 = solid.newton_solves
+    h0 = len(solid.history)
     barrier()
     sampler.start()
     h.event_record(0)
@@ -237,6 +252,7 @@ def main():
     dev_ms = h.event_elapsed_ms(0, 1)
     prof = h.profile(reset=True)
     solves_value = solid.newton_solves - s0
+    cg_its_value = cg_iterations(h0)
     h.set_option(capi.OPT_PROFILE, 0)
     # ---- timed region 2: through the public API with host buffers ("e2e") ---------------------
     s0 = solid.newton_solves
@@ -269,7 +285,9 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "n_dofs": n_dofs_global, "n_dofs_per_gpu": h.n_owned,
                        "nnz_scalar": h.nnz(), "newton_solves_in_timed_region": solves_value,
-                       "cg_iterations_in_timed_region": int(prof["spmv_launches"]),
+                       "cg_iterations_in_timed_region": cg_its_value,
+                       "preconditioner": args.precond,
+                       "multigrid_levels": [q.mesh.reps for q in hierarchy.problems] if hierarchy else None,
                        "l2_policy": "inputs larger than L2 (matrix %.2f GB per GPU streamed every "
                                     "CG iteration)" % (spmv_bytes / 1e9),
                        "device_ms": dev_ms, "parallelism": "slab%d" % world},
@@ -278,7 +296,8 @@ def main():
                     "h2d_bytes_per_step": int(buf.nbytes), "d2h_bytes_per_step": int(buf.nbytes),
                     "ms_per_step": 1e3 * wall_e2e / args.steps, "newton_solves": solves_e2e},
             "gpu_launches": int(prof["kernel_launches"]),
-            "roofline": {"bound": "hbm", "kernel": "spmv_kernel<3,true> (CG vmult + fused dot)",
+            "roofline": {"bound": "hbm", "kernel": "spmv_tma_kernel<3> on the finest level (CG vmult with fused dot; "
+                                   "Chebyshev-smoother and residual vmults of the V-cycle)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic,
                          "bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_avg_ms,
@@ -291,7 +310,10 @@ def main():
             r = cpu_run(1, 0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
-    h.close()
+    if hierarchy:
+        hierarchy.close()
+    else:
+        h.close()
     if world > 1:
         comm.close()
         dist.destroy_process_group()

@@ -1,6 +1,8 @@
 #include "host_problem.h"
 
+#include <cstdlib>
 #include <stdexcept>
+#include <string>
 
 namespace gfh
 {
@@ -88,6 +90,47 @@ namespace gfh
     const int rc      = gf_create(&d, &handle);
     if (rc != GF_OK)
       throw std::runtime_error(gf_last_error(nullptr));
+  }
+
+  int HostProblem::create_multigrid(const Parameters::AllParameters &prm, int dim, int model)
+  {
+    const char *env = std::getenv("GF_PRECONDITIONER");
+    if (env && std::string(env) == "block-jacobi")
+      return 1;
+    HostProblem *fine = this;
+    while (true)
+      {
+        std::vector<int> reps(dim);
+        bool             ok = true;
+        for (int d = 0; d < dim; ++d)
+          {
+            ok      = ok && fine->mesh->reps[d] % 2 == 0;
+            reps[d] = fine->mesh->reps[d] / 2;
+          }
+        if (!ok)
+          break;
+        std::unique_ptr<HostProblem> co(new HostProblem);
+        co->make_grid(prm, dim, reps, fine->mesh->numbering);
+        co->create_device(prm, dim, model);
+        // cell->child(k), k = kx + 2 ky + 4 kz; cells are lexicographic
+        const int            nc = 1 << dim;
+        std::vector<int32_t> child(size_t(co->mesh->n_cells) * nc);
+        const int            rz = dim == 3 ? reps[2] : 1;
+        for (int k = 0; k < rz; ++k)
+          for (int j = 0; j < reps[1]; ++j)
+            for (int i = 0; i < reps[0]; ++i)
+              for (int c = 0; c < nc; ++c)
+                child[size_t(co->mesh->cell_index(i, j, k)) * nc + c] = int32_t(fine->mesh->cell_index(
+                  2 * i + (c & 1), 2 * j + ((c >> 1) & 1), dim == 3 ? 2 * k + ((c >> 2) & 1) : 0));
+        if (gf_mg_attach(fine->handle, co->handle, child.data()) != GF_OK)
+          throw std::runtime_error(gf_last_error(fine->handle));
+        coarse_levels.push_back(std::move(co));
+        fine = coarse_levels.back().get();
+      }
+    if (!coarse_levels.empty() &&
+        gf_set_option(handle, GF_OPT_PRECONDITIONER, GF_PRECOND_MULTIGRID) != GF_OK)
+      throw std::runtime_error(gf_last_error(handle));
+    return 1 + int(coarse_levels.size());
   }
 
   HostProblem::~HostProblem()

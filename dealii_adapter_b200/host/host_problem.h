@@ -26,6 +26,13 @@ namespace gfh
     void make_grid(const Parameters::AllParameters &prm, int dim,
                    const std::vector<int> &reps_override, int numbering);
     void create_device(const Parameters::AllParameters &prm, int dim, int model);
+    // Geometric multigrid preconditioner: the coarser levels of the refinement hierarchy (every
+    // repetition halved while all are even; in the reference: the levels of refine_global,
+    // nonlinear_elasticity.cc:245-246) become handles linked below `handle` with gf_mg_attach.
+    // Environment GF_PRECONDITIONER = multigrid (default when a coarser level exists) |
+    // block-jacobi. Returns the number of levels in use.
+    int create_multigrid(const Parameters::AllParameters &prm, int dim, int model);
+    std::vector<std::unique_ptr<HostProblem>> coarse_levels;
     ~HostProblem();
   };
 } // namespace gfh

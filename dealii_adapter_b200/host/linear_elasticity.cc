@@ -44,6 +44,11 @@ namespace Linear_Elasticity
               << "\n\t Polynomial degree: " << parameters.poly_degree
               << "\n\t Number of degrees of freedom: " << host.mesh->n_dofs << std::endl;
     host.create_device(parameters, dim, GF_MODEL_LINEAR);
+    const int n_mg_levels = host.create_multigrid(parameters, dim, GF_MODEL_LINEAR);
+    std::cout << "\t CG preconditioner: "
+              << (n_mg_levels > 1 ? "geometric multigrid, " + std::to_string(n_mg_levels) + " levels" :
+                                    std::string("block-Jacobi"))
+              << std::endl;
     auto vec         = [&](int id) { return VectorType{host.handle, id}; };
     old_velocity     = vec(GF_LIN_OLD_VELOCITY);
     velocity         = vec(GF_LIN_VELOCITY);

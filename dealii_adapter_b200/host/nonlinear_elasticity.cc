@@ -57,6 +57,11 @@ namespace Nonlinear_Elasticity
               << "\n\t Polynomial degree: " << parameters.poly_degree
               << "\n\t Number of degrees of freedom: " << host.mesh->n_dofs << std::endl;
     host.create_device(parameters, dim, GF_MODEL_NEO_HOOKEAN);
+    const int n_mg_levels = host.create_multigrid(parameters, dim, GF_MODEL_NEO_HOOKEAN);
+    std::cout << "\t CG preconditioner: "
+              << (n_mg_levels > 1 ? "geometric multigrid, " + std::to_string(n_mg_levels) + " levels" :
+                                    std::string("block-Jacobi"))
+              << std::endl;
     auto vec = [&](int id) { return VectorType{host.handle, id}; };
     total_displacement     = vec(GF_NL_TOTAL_DISPLACEMENT);
     total_displacement_old = vec(GF_NL_TOTAL_DISPLACEMENT_OLD);

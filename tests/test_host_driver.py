@@ -96,3 +96,39 @@ def test_coupled_nonlinear_run_matches_oracle_watchpoint(exes, tmp_path, native_
     # Newton iteration counts: one table row per linear solve
     rows = [l for l in r.stdout.splitlines() if " SLV " in l]
     assert len(rows) == sum(counts)
+
+
+@pytest.mark.gpu
+def test_coupled_run_on_refined_mesh_uses_multigrid_and_matches_oracle(exes, tmp_path, native_libs):
+    """FSI3 2D with one global refinement (36 x 6 cells): the C++ host links the two levels with
+    gf_mg_attach and the CG is multigrid-preconditioned; watch-point vs the oracle (tight solves)."""
+    from oracle import oracle_py as orc
+    shutil.copy(os.path.join(GOLDEN, "parameters_nonlinear_fsi3.prm"), tmp_path / "parameters.prm")
+    (tmp_path / "precice-config.fake").write_text(FAKE_CFG + "mesh-repetitions = 36,6\n")
+    r = run(exes[0], tmp_path)
+    assert r.returncode == 0, r.stderr + r.stdout[-2000:]
+    assert "geometric multigrid, 2 levels" in r.stdout
+    log = np.loadtxt(tmp_path / "watchpoint.log")
+    p = nl_params(poly_degree=2, scenario="FSI3", type_lin="Direct", delta_t=0.01,
+                  max_iterations_lin=2.0)
+    prob = make_problem(p, 2, reps=[36, 6], numbering="component_wise")
+    o = orc.Oracle(prob)
+    pos = prob.interface_positions().reshape(-1, 2)
+    k = np.argmin(((pos - np.array([0.6, 0.2])) ** 2).sum(axis=1))
+    counts = []
+    for step in range(4):
+        t = (step + 1) * 0.01
+        o.format_precice_to_deal(np.tile(np.array([0.0, -1500.0]) * min(1.0, t / 0.03),
+                                         prob.n_iface_nodes), orc.NL_EXTERNAL_STRESS)
+        n, _ = o.nl_timestep()
+        counts.append(n)
+        d = o.format_deal_to_precice(orc.NL_TOTAL_DISPLACEMENT).reshape(-1, 2)[k]
+        assert rel_err(log[step, 4:6], d) < 1e-8
+    rows = [l for l in r.stdout.splitlines() if " SLV " in l]
+    assert len(rows) == sum(counts)
+    # block-Jacobi on request
+    env = dict(os.environ, GF_PRECONDITIONER="block-jacobi")
+    r2 = subprocess.run([exes[0], "parameters.prm"], cwd=tmp_path, capture_output=True, text=True,
+                        timeout=600, env=env)
+    assert r2.returncode == 0 and "CG preconditioner: block-Jacobi" in r2.stdout
+    assert rel_err(np.loadtxt(tmp_path / "watchpoint.log")[:, 4:6], log[:, 4:6]) < 1e-8

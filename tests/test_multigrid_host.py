@@ -1,0 +1,61 @@
+"""CPU tests of the host side of the multigrid hierarchy (dealii_adapter_b200/multigrid.py): level
+problems, child tables (deal.II child order) and their restriction to slab partitions."""
+import numpy as np
+
+from helpers import nl_params
+from dealii_adapter_b200 import multigrid as mg
+from dealii_adapter_b200.problem import make_problem
+
+
+def test_coarsen_keeps_geometry_and_boundary_roles(native_libs):
+    p = nl_params(poly_degree=2)
+    fine = make_problem(p, 3, reps=[4, 8, 2], numbering="lexicographic")
+    coarse = mg.coarsen_problem(fine)
+    assert coarse.mesh.reps == [2, 4, 1]
+    assert coarse.mesh.p0 == fine.mesh.p0 and coarse.mesh.p1 == fine.mesh.p1
+    assert mg.coarsen_problem(coarse) is None          # a repetition is odd
+    # nested nodes: every coarse support point is a fine support point with the same constraint
+    fine_pts = {tuple(np.round(x, 12)): i for i, x in enumerate(fine.mesh.support_points[::3])}
+    fz = fine.constrained.reshape(-1, 3)
+    for i, x in enumerate(coarse.mesh.support_points[::3]):
+        j = fine_pts[tuple(np.round(x, 12))]
+        assert np.array_equal(fz[j], coarse.constrained.reshape(-1, 3)[i])
+    cz = coarse.constrained.reshape(-1, 3)
+    pts = coarse.mesh.support_points[::3]
+    assert np.all(cz[np.isclose(pts[:, 1], 0.0)] == 1)            # clamped bottom, all components
+
+
+def test_child_table_is_deal_ii_child_order(native_libs):
+    p = nl_params(poly_degree=1)
+    for dim, reps in ((2, [4, 6]), (3, [2, 4, 6])):
+        fine = make_problem(p, dim, reps=reps)
+        coarse = mg.coarsen_problem(fine)
+        tab = mg.child_table(coarse.mesh, fine.mesh)
+        assert sorted(tab.reshape(-1)) == list(range(fine.mesh.n_cells))
+        nv = 1 << dim
+        fv = fine.mesh.cell_vertices.reshape(-1, nv, dim)
+        cv = coarse.mesh.cell_vertices.reshape(-1, nv, dim)
+        for pc in range(coarse.mesh.n_cells):
+            lo, hi = cv[pc, 0], cv[pc, nv - 1]
+            for k in range(nv):
+                off = np.array([(k >> d) & 1 for d in range(dim)])
+                assert np.allclose(fv[tab[pc, k], 0], lo + 0.5 * off * (hi - lo))
+
+
+def test_partitioned_child_tables_cover_the_local_fine_cells(native_libs):
+    p = nl_params(poly_degree=2)
+    fine = make_problem(p, 3, reps=[2, 16, 2], numbering="lexicographic")
+    coarse = mg.coarsen_problem(fine)
+    tab = mg.child_table(coarse.mesh, fine.mesh)
+    world = 2
+    for rank in range(world):
+        pf, pc = fine.mesh.partition(1, world, rank), coarse.mesh.partition(1, world, rank)
+        g2l = -np.ones(fine.mesh.n_cells, dtype=np.int64)
+        g2l[pf.local_cell_global] = np.arange(pf.n_local_cells)
+        local = g2l[tab[pc.local_cell_global]]
+        covered = np.zeros(pf.n_local_cells, dtype=bool)
+        covered[local[local >= 0]] = True
+        assert covered.all()
+        # the coarse ghost layer spans two fine layers, only the first is local on the fine level
+        if rank == 0:
+            assert (local < 0).any()
