@@ -407,7 +407,15 @@ extern "C"
             c.prof.enabled = value != 0;
             break;
           case GF_OPT_OPERATOR:
-            GF_REQUIRE(value == 0, GF_ERR_UNSUPPORTED, "matrix-free operator not available yet");
+            GF_REQUIRE(value == 0 || value == 1, GF_ERR_INVALID_ARG, "unknown operator kind");
+            GF_REQUIRE(value == 0 || (c.model == GF_MODEL_NEO_HOOKEAN && c.dim == 3),
+                       GF_ERR_UNSUPPORTED,
+                       "the matrix-free operator is available for the 3D neo-Hookean model");
+            if (c.operator_kind != int(value))
+              {
+                c.mf_valid                     = false; // re-assemble before the next solve
+                c.mat[GF_MAT_TANGENT].valid    = false;
+              }
             c.operator_kind = int(value);
             break;
           case GF_OPT_SPMV_KERNEL:
@@ -531,15 +539,23 @@ extern "C"
       gf::vec_axpby(c, c.tmp0.p, 1.0, c.vec[GF_NL_SOLUTION_DELTA].p, 1.0);
       GF_CUDA_CHECK(cudaMemsetAsync(c.err_flag.p, 0, sizeof(int), c.stream));
       double *K = c.mat[GF_MAT_TANGENT].val.p;
-      for (int64_t c0 = 0; c0 < c.n_cells; c0 += c.ke_chunk_cells)
+      if (c.operator_kind == 1)
+        // matrix-free: quadrature-point data, r_e and the diagonal blocks; no element matrices
+        gf::mf_setup(c, c.tmp0.p, c.vec[GF_NL_ACCELERATION].p);
+      else
         {
-          const int64_t c1 = std::min(c.n_cells, c0 + c.ke_chunk_cells);
-          gf::launch_nl_cells(c, c.tmp0.p, c.vec[GF_NL_ACCELERATION].p, c0, c1);
-          gf::launch_scatter_matrix(c, K, c0, c1, c0 == 0, true);
+          for (int64_t c0 = 0; c0 < c.n_cells; c0 += c.ke_chunk_cells)
+            {
+              const int64_t c1 = std::min(c.n_cells, c0 + c.ke_chunk_cells);
+              gf::launch_nl_cells(c, c.tmp0.p, c.vec[GF_NL_ACCELERATION].p, c0, c1);
+              gf::launch_scatter_matrix(c, K, c0, c1, c0 == 0, true);
+            }
+          c.mat[GF_MAT_TANGENT].valid = true;
         }
       gf::launch_nl_faces(c, c.tmp0.p, c.vec[GF_NL_EXTERNAL_STRESS].p);
       gf::launch_scatter_rhs(c, c.vec[GF_NL_SYSTEM_RHS].p, true);
-      gf::launch_build_precond(c, K);
+      if (c.operator_kind == 0)
+        gf::launch_build_precond(c, K);
       if (gf::mg_active(c))
         gf::mg_update_operators(c, c.tmp0.p); // coarse tangents at the injected state + smoothers
       const double r = gf::vec_masked_norm(c, c.vec[GF_NL_SYSTEM_RHS].p, true); // :449
@@ -755,6 +771,8 @@ extern "C"
       else
         {
           mat_ptr(c, which);
+          GF_REQUIRE(which != GF_MAT_TANGENT || c.operator_kind == 0, GF_ERR_INVALID_ARG,
+                     "no assembled tangent in matrix-free mode (GF_OPT_OPERATOR = 1)");
           v.resize(c.n_val);
           c.mat[which].val.download(v.data(), c.stream);
         }
@@ -808,6 +826,8 @@ extern "C"
           GF_REQUIRE(c.mass_blk.p != nullptr, GF_ERR_INVALID_ARG, "no mass matrix for this model");
           gf::launch_spmv_mass(c, x, y);
         }
+      else if (which_matrix == GF_MAT_TANGENT)
+        gf::op_apply(c, mat_ptr(c, which_matrix), x, y, nullptr); // assembled or matrix-free
       else
         gf::launch_spmv(c, mat_ptr(c, which_matrix), x, y, nullptr);
       GF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
@@ -827,11 +847,12 @@ extern "C"
       GF_CUDA_CHECK(cudaEventCreate(&e1));
       const bool prof = c.prof.enabled;
       c.prof.enabled  = false;
+      const bool tangent = which_matrix == GF_MAT_TANGENT;
       for (int k = 0; k < 3; ++k)
-        gf::launch_spmv(c, A, x, y, nullptr);
+        tangent ? gf::op_apply(c, A, x, y, nullptr) : gf::launch_spmv(c, A, x, y, nullptr);
       GF_CUDA_CHECK(cudaEventRecord(e0, c.stream));
       for (int k = 0; k < n_reps; ++k)
-        gf::launch_spmv(c, A, x, y, nullptr);
+        tangent ? gf::op_apply(c, A, x, y, nullptr) : gf::launch_spmv(c, A, x, y, nullptr);
       GF_CUDA_CHECK(cudaEventRecord(e1, c.stream));
       GF_CUDA_CHECK(cudaEventSynchronize(e1));
       c.prof.enabled = prof;
@@ -842,7 +863,7 @@ extern "C"
       if (ms_per_launch)
         *ms_per_launch = double(ms) / n_reps;
       if (bytes_per_launch)
-        *bytes_per_launch = gf::spmv_bytes(c);
+        *bytes_per_launch = (tangent && c.operator_kind == 1) ? gf::mf_bytes(c) : gf::spmv_bytes(c);
       return GF_OK;
     });
   }

@@ -19,6 +19,7 @@
 // Algorithmic flops / q-point (3D Q2): 729 node pairs * 30 FMA = 43.7 kflop (full matrix).
 #include "gf_context.h"
 #include "kernel_utils.cuh"
+#include "nl_material.cuh"
 
 namespace gf
 {
@@ -63,57 +64,6 @@ namespace gf
       static constexpr int Q_W   = Q_A + DIM;         // JxW
       static constexpr int Q_X   = Q_W + 1;           // spare
     };
-
-    struct NLParams
-    {
-      double kappa, mu, rho, alpha_1;
-      double body_force[3];
-    };
-
-    // compressible_neo_hook_material.h:37-49 in Voigt storage (SymmetricTensor order)
-    template <int DIM>
-    __device__ __forceinline__ void neo_hooke(const double kappa, const double mu, const double J,
-                                              const double (&bbar)[DIM * (DIM + 1) / 2],
-                                              double (&tau)[DIM * (DIM + 1) / 2],
-                                              double (&D)[DIM * (DIM + 1) / 2][DIM * (DIM + 1) / 2])
-    {
-      constexpr int VO    = DIM * (DIM + 1) / 2;
-      const double  dPsi  = (kappa / 2.0) * (J - 1.0 / J);         // :74-78
-      const double  d2Psi = (kappa / 2.0) * (1.0 + 1.0 / (J * J)); // :100-104
-      // tau_bar = 2 c_1 b_bar = mu b_bar ; tau_iso = dev_P : tau_bar  (:87-98)
-      double tr = 0;
-#pragma unroll
-      for (int i = 0; i < DIM; ++i)
-        tr += mu * bbar[i];
-      double tau_iso[VO];
-#pragma unroll
-      for (int k = 0; k < VO; ++k)
-        tau_iso[k] = mu * bbar[k] - (k < DIM ? tr / DIM : 0.0);
-      const double tv = dPsi * J; // tau_vol = dPsi J I  (:80-85)
-#pragma unroll
-      for (int k = 0; k < VO; ++k)
-        tau[k] = tau_iso[k] + (k < DIM ? tv : 0.0);
-      // Jc_vol = J[(dPsi + J d2Psi) IxI - 2 dPsi S]  (:106-114)
-      // Jc_iso = (2/dim) tr(tau_bar) dev_P - (2/dim)(tau_iso x I + I x tau_iso)  (:116-133)
-      const double c_IxI = J * (dPsi + J * d2Psi) - (2.0 / DIM) * tr / DIM;
-      const double c_S   = -J * (2.0 * dPsi) + (2.0 / DIM) * tr;
-#pragma unroll
-      for (int k = 0; k < VO; ++k)
-#pragma unroll
-        for (int l = 0; l < VO; ++l)
-          {
-            double v = 0;
-            if (k < DIM && l < DIM)
-              v += c_IxI;
-            if (k == l)
-              v += (k < DIM ? 1.0 : 0.5) * c_S;
-            if (l < DIM)
-              v -= (2.0 / DIM) * tau_iso[k];
-            if (k < DIM)
-              v -= (2.0 / DIM) * tau_iso[l];
-            D[k][l] = v;
-          }
-    }
 
     template <int DIM, int P>
     __global__ void __launch_bounds__(NLCfg<DIM, P>::NT, 1)
@@ -531,13 +481,7 @@ namespace gf
                                              int(C::SMEM_BYTES)));
           configured = true;
         }
-      NLParams prm;
-      prm.kappa   = (2.0 * c.desc.mu * (1.0 + c.desc.nu)) / (3.0 * (1.0 - 2.0 * c.desc.nu));
-      prm.mu      = c.desc.mu;
-      prm.rho     = c.desc.rho;
-      prm.alpha_1 = 1. / (c.desc.beta * c.desc.delta_t * c.desc.delta_t);
-      for (int k = 0; k < 3; ++k)
-        prm.body_force[k] = c.desc.body_force[k];
+      const NLParams prm = make_nl_params(c.desc);
       int blocks_per_sm = 1;
       GF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
         &blocks_per_sm, nl_cells_kernel<DIM, P>, C::NT, C::SMEM_BYTES));

@@ -240,7 +240,7 @@ namespace gf
     GF_CUDA_CHECK(cudaMemsetAsync(c.cg_p.p, 0, c.n_local * sizeof(double), s));
     const int64_t n_nodes = c.n_owned_nodes;
     const int     ug = vec_grid(c, n_nodes), dg = vec_grid(c, c.n_owned);
-    const int     sg_rows = spmv_dot_partials(c);
+    const int     sg_rows = op_dot_partials(c);
     auto update = [&](bool startup) {
       ProfScope ps(c, Profile::CG_VEC, 3);
       if (c.dim == 3)
@@ -276,7 +276,7 @@ namespace gf
     // ---- startup: r = b - A x ; check ----
     if (c.comm)
       halo_exchange(c, x);
-    launch_spmv(c, val, x, c.cg_v.p, nullptr);
+    op_apply(c, val, x, c.cg_v.p, nullptr);
     update(true);
     GF_CUDA_CHECK(cudaGetLastError());
     while (poll() == 0)
@@ -291,7 +291,7 @@ namespace gf
         }
         if (c.comm)
           halo_exchange(c, c.cg_p.p);
-        launch_spmv(c, val, c.cg_p.p, c.cg_v.p, c.partials.p);
+        op_apply(c, val, c.cg_p.p, c.cg_v.p, c.partials.p);
         {
           ProfScope ps(c, Profile::CG_VEC, 2);
           reduce_and_scalar(c, sg_rows, 1, 1);
@@ -323,12 +323,12 @@ namespace gf
     const int64_t n_nodes = c.n_owned_nodes;
     const int     ug      = vec_grid(c, n_nodes);
     const int     dg      = vec_grid(c, c.n_owned);
-    const int     sg_rows = spmv_dot_partials(c);
+    const int     sg_rows = op_dot_partials(c);
 
     // ---- startup ----
     if (c.comm)
       halo_exchange(c, x);
-    launch_spmv(c, val, x, c.cg_v.p, nullptr);
+    op_apply(c, val, x, c.cg_v.p, nullptr);
     {
       ProfScope ps(c, Profile::CG_VEC, 3);
       if (c.dim == 3)
@@ -364,7 +364,7 @@ namespace gf
             }
             if (c.comm)
               halo_exchange(c, c.cg_p.p);
-            launch_spmv(c, val, c.cg_p.p, c.cg_v.p, c.partials.p);
+            op_apply(c, val, c.cg_p.p, c.cg_v.p, c.partials.p);
             {
               ProfScope ps(c, Profile::CG_VEC, 5);
               reduce_and_scalar(c, sg_rows, 1, 1);

@@ -139,6 +139,26 @@ namespace gf
         v *= lag(p, t.local_lex[a * 3 + d], xi[d]);
       return v;
     };
+    t.h1N.assign(nq1 * (p + 1), 0.);
+    t.h1D.assign(nq1 * (p + 1), 0.);
+    t.h1w = w1;
+    for (int q = 0; q < nq1; ++q)
+      for (int i = 0; i <= p; ++i)
+        {
+          t.h1N[q * (p + 1) + i] = lag(p, i, x1[q]);
+          t.h1D[q * (p + 1) + i] = dlag(p, i, x1[q]);
+        }
+    t.lex2hier.assign(npc, -1);
+    for (int a = 0; a < npc; ++a)
+      {
+        int l = 0, mul = 1;
+        for (int d = 0; d < dim; ++d)
+          {
+            l += t.local_lex[a * 3 + d] * mul;
+            mul *= (p + 1);
+          }
+        t.lex2hier[l] = a;
+      }
     t.hN.assign(nq * npc, 0.);
     t.hdN.assign(nq * npc * dim, 0.);
     t.hw.assign(nq, 0.);

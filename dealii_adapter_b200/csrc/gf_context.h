@@ -110,6 +110,9 @@ namespace gf
     DevBuf<double> Mref; // [npc][npc] sum_q w N_a N_b
     std::vector<double> hN, hdN, hw, hNf, hwf;
     std::vector<int>    local_lex; // [npc][3]
+    // 1D factors of the tensor-product tables (matrix-free sum factorisation, matfree.cu)
+    std::vector<double> h1N, h1D, h1w; // [nq1][p+1] values / derivatives at the 1D Gauss points, [nq1]
+    std::vector<int>    lex2hier;      // lexicographic local node -> FE_Q hierarchical local node
   };
 
   // CG scalars living on the device; the host polls `status` every check interval
@@ -283,6 +286,13 @@ struct gf_context
   gf::DevBuf<int32_t> send_idx, recv_idx; // internal dof ids
   gf::DevBuf<double>  send_buf, recv_buf;
 
+  // matrix-free tangent operator (matfree.cu), GF_OPT_OPERATOR = 1
+  gf::DevBuf<double> mf_qp;     // [n_cells][NF][nq]: C = J^-1 F^-1, JxW*Jc (upper Voigt), JxW*tau
+  gf::DevBuf<double> mf_ye;     // [n_cells][dpc] element results of one operator application
+  gf::DevBuf<double> mf_diag_e; // [n_cells][npc][dim*dim] diagonal node blocks of K_e
+  gf::DevBuf<double> mf_cdiag;  // [n_local] diagonal of the constrained dofs (sum |K_e(i,i)|)
+  bool               mf_valid = false;
+
   // geometric multigrid preconditioner (multigrid.cu)
   gf::MGTransfer     mg;             // link to the next coarser level (mg.coarse == nullptr: none)
   gf_context *       mg_finer = nullptr; // back link (for safe destruction in any order)
@@ -341,6 +351,15 @@ namespace gf
   void   iface_gather(gf_context &c, const double *vec, double *host_buf);
   // api.cu: body of ElastoDynamics::assemble_system for one level
   void lin_assemble(gf_context &c);
+  // matfree.cu
+  void mf_setup(gf_context &c, const double *u_total, const double *accel); // qp data, r_e, D^-1
+  void mf_apply(gf_context &c, const double *x, double *y, double *dot_partials);
+  int  mf_dot_partials(const gf_context &c);
+  double mf_bytes(const gf_context &c);
+  // operator of the CG / smoothers on this level: assembled SpMV or the matrix-free tangent
+  void   op_apply(gf_context &c, const double *val, const double *x, double *y,
+                  double *dot_partials);
+  int    op_dot_partials(const gf_context &c);
   // multigrid.cu
   void mg_attach(gf_context &fine, gf_context &coarse, const int32_t *child_cells);
   void mg_update_operators(gf_context &c, const double *u_total); // after the finest assembly

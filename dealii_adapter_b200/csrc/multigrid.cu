@@ -308,7 +308,7 @@ namespace gf
     {
       if (c.comm)
         halo_exchange(c, x);
-      launch_spmv(c, level_matrix(c), x, y, nullptr);
+      op_apply(c, level_matrix(c), x, y, nullptr);
     }
 
     template <int DIM>
