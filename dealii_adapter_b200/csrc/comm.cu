@@ -4,6 +4,23 @@
 // path needs: the ghost-DoF halo before a SpMV / assembly read and the scalar all-reduce of the
 // CG dot products and Newton norms. NCCL is resolved at run time (dlopen) so that single-GPU use
 // has no NCCL dependency.
+//
+// Two transports carry those exchanges:
+//   peer windows (default)  every rank owns one device "window" (mailboxes + flags), exported with
+//       cudaIpcGetMemHandle and mapped by all peers at gf_comm_create (the 64-byte handles travel
+//       through one ncclAllGather). A halo exchange is then two of OUR kernels: `halo_push_kernel`
+//       gathers the boundary values and stores them straight into the neighbour's mailbox over
+//       NVLink, followed by a system-scope release of the neighbour's flag; `halo_wait_kernel`
+//       acquires the local flag and unpacks the mailbox into the ghost entries. The scalar
+//       all-reduce is ONE single-CTA kernel: store my partial sums into every peer's slot, release
+//       the flags, acquire all local flags, add the slots in rank order (=> bitwise identical on
+//       all ranks, independent of arrival order). No NCCL call, no proxy thread, ~2 launch
+//       latencies instead of pack + grouped ncclSend/ncclRecv + unpack.
+//       Mailboxes and flags are double-buffered by the parity of a communicator-wide epoch: rank A
+//       can only push epoch e+2 after its wait of e+1, i.e. after B pushed e+1, which B's stream
+//       orders after B's unpack of e — so the parity-(e mod 2) mailbox is free again.
+//   NCCL (fallback, GF_COMM_P2P=0 or if IPC mapping fails on any rank): pack + grouped
+//       ncclSend/ncclRecv + unpack, ncclAllReduce.
 #include <dlfcn.h>
 
 #include <cstdlib>
@@ -24,10 +41,11 @@ namespace gf
     typedef int (*fn_CommInitRank)(ncclComm_t *, int, NcclUniqueId, int);
     typedef int (*fn_CommDestroy)(ncclComm_t);
     typedef int (*fn_AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+    typedef int (*fn_AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t);
     typedef int (*fn_SendRecv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
     typedef int (*fn_Group)(void);
     typedef const char *(*fn_ErrStr)(int);
-    constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+    constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MIN = 3, NCCL_CHAR = 0, NCCL_INT32 = 2;
 
     struct NcclApi
     {
@@ -36,6 +54,7 @@ namespace gf
       fn_CommInitRank CommInitRank = nullptr;
       fn_CommDestroy  CommDestroy = nullptr;
       fn_AllReduce    AllReduce = nullptr;
+      fn_AllGather    AllGather = nullptr;
       fn_SendRecv     Send = nullptr, Recv = nullptr;
       fn_Group        GroupStart = nullptr, GroupEnd = nullptr;
       fn_ErrStr       GetErrorString = nullptr;
@@ -62,6 +81,7 @@ namespace gf
       api.CommInitRank   = (fn_CommInitRank)dlsym(api.lib, "ncclCommInitRank");
       api.CommDestroy    = (fn_CommDestroy)dlsym(api.lib, "ncclCommDestroy");
       api.AllReduce      = (fn_AllReduce)dlsym(api.lib, "ncclAllReduce");
+      api.AllGather      = (fn_AllGather)dlsym(api.lib, "ncclAllGather");
       api.Send           = (fn_SendRecv)dlsym(api.lib, "ncclSend");
       api.Recv           = (fn_SendRecv)dlsym(api.lib, "ncclRecv");
       api.GroupStart     = (fn_Group)dlsym(api.lib, "ncclGroupStart");
