@@ -150,6 +150,8 @@ def main():
     ap.add_argument("--layers", type=int, default=CELLS_PER_GPU[1],
                     help="cell layers per GPU along the flap (debug; default = the named workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true",
+                    help="skip the matrix-free-operator variant measured after the main regions")
     ap.add_argument("--precond", default="mg", choices=["mg", "jacobi"],
                     help="CG preconditioner: geometric multigrid V-cycle (default) or block-Jacobi")
     args = ap.parse_args()
@@ -235,8 +237,10 @@ def main():
         return int(sum(r[0] for rows in solid.history[first_step:] for r in rows))
 
     sampler = ClockSampler(local_rank)
-    # ---- timed region 1: device-resident inputs ("value"), profile events on ------------------
-    h.set_option(capi.OPT_PROFILE, 1)
+    # ---- timed region 1: device-resident inputs ("value"). CUDA events bracket every finest-level
+    # SpMV launch live in this region (GF_OPT_PROFILE = 2: two events per SpMV launch only; the
+    # launch counters of all kernels always run) --------------------------------------------------
+    h.set_option(capi.OPT_PROFILE, 2)
     h.profile(reset=True)
     s0 = solid.newton_solves
     h0 = len(solid.history)
@@ -265,6 +269,48 @@ def main():
     clocks = sampler.stop()
     solves_e2e = solid.newton_solves - s0
     prof_e2e = h.profile(reset=True)
+    # ---- diagnostic pass (outside both timed regions): every kernel class bracketed with events
+    h.set_option(capi.OPT_PROFILE, 1)
+    h.profile(reset=True)
+    s0 = solid.newton_solves
+    for k in range(N_SUB):
+        resident_pass(k)
+    barrier()
+    prof_full = h.profile(reset=True)
+    solves_full = solid.newton_solves - s0
+    h.set_option(capi.OPT_PROFILE, 0)
+    # ---- variants benchmarked alongside (north_star: matrix-free operator beside the SpMV) ------
+    variants = {}
+    if not args.no_variants and world == 1 and os.environ.get("GF_PROFILE_RUN") != "1":
+        h.set_option(capi.OPT_OPERATOR, 1)
+        for k in range(N_SUB):
+            resident_pass(k)
+        s0 = solid.newton_solves
+        h0v = len(solid.history)
+        barrier()
+        h.event_record(2)
+        t0 = time.perf_counter()
+        for k in range(N_SUB):
+            resident_pass(k)
+        h.event_record(3)
+        barrier()
+        tv = max(time.perf_counter() - t0, 1e-3 * h.event_elapsed_ms(2, 3))
+        ms_mf, mf_bytes = h.spmv_timed(capi.MAT_TANGENT, 5)
+        variants["matrix_free_operator"] = {
+            "what": "sum-factorised matrix-free tangent (K11) on the finest level instead of the "
+                    "assembled BSR SpMV; coarser levels assembled; same CG + V-cycle",
+            "value": n_dofs_global * (solid.newton_solves - s0) / tv, "unit": "DoFs/s",
+            "steps": N_SUB, "newton_solves": solid.newton_solves - s0,
+            "cg_iterations": cg_iterations(h0v), "operator_apply_ms": ms_mf,
+            "operator_bytes_per_apply": mf_bytes}
+        h.set_option(capi.OPT_OPERATOR, 0)
+    comm_info = None
+    if world > 1:
+        kind, n_halo, n_ar = comm.transport()
+        halo_us, ar_us = h.comm_timed(50)
+        comm_info = {"transport": kind, "halo_exchange_us": halo_us, "allreduce_us": ar_us,
+                     "halo_exchanges_issued": n_halo, "allreduces_issued": n_ar,
+                     "halo_ms_per_newton_solve_diag": prof_full["halo_ms"] / max(1, solves_full)}
 
     t_value = max(wall_value, dev_ms * 1e-3)
     if world > 1:
@@ -304,8 +350,14 @@ def main():
                          "launches": int(prof["spmv_launches"]),
                          "standalone_launch_ms": ms_spmv,
                          "share_of_step": prof["spmv_ms"] / (1e3 * t_value)},
-            "phase_ms": {k: v for k, v in prof.items() if k.endswith("_ms")},
+            "phase_ms_per_newton_solve": dict(
+                {k: v / max(1, solves_full) for k, v in prof_full.items() if k.endswith("_ms")},
+                note="diagnostic pass of %d steps outside the timed regions, every kernel class "
+                     "bracketed with CUDA events (adds launch gaps to the small kernels)" % N_SUB),
+            "variants": variants,
         }
+        if comm_info:
+            line["comm"] = comm_info
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_run(1, 0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -48,12 +48,32 @@ def _sources(d, exts):
 
 
 def build_cuda(force=False):
+    """One object per .cu (compiled in parallel, only when the source or a header changed), then
+    one link: libgraftfem.so. Per-file ptxas -v output goes to csrc/build.log."""
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     srcs = _sources(CSRC, (".cu",))
-    deps = srcs + _sources(CSRC, (".h", ".cuh")) + _sources(INCLUDE, (".h",))
-    if force or _newer(LIB_CUDA, deps):
-        _run([nvcc] + NVCC_FLAGS + ["-shared", "-I", INCLUDE, "-I", CSRC, "-o", LIB_CUDA] + srcs
-             + ["-lcudart", "-ldl"], log=os.path.join(PKG_DIR, "csrc", "build.log"))
+    hdrs = _sources(CSRC, (".h", ".cuh")) + _sources(INCLUDE, (".h",))
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs = [os.path.join(objdir, os.path.basename(x)[:-3] + ".o") for x in srcs]
+    todo = [(x, o) for x, o in zip(srcs, objs) if force or _newer(o, [x] + hdrs)]
+
+    def compile_one(job):
+        src, obj = job
+        return _run([nvcc] + NVCC_FLAGS + ["-c", "-I", INCLUDE, "-I", CSRC, "-o", obj, src],
+                    log=obj[:-2] + ".log")
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=min(8, len(todo))) as ex:
+            list(ex.map(compile_one, todo))
+    if todo or force or _newer(LIB_CUDA, objs):
+        _run([nvcc, "-shared", "-o", LIB_CUDA] + objs + ["-lcudart", "-ldl"])
+        with open(os.path.join(CSRC, "build.log"), "w") as f:
+            for o in objs:
+                lg = o[:-2] + ".log"
+                if os.path.exists(lg):
+                    f.write(open(lg).read())
     return LIB_CUDA
 
 

@@ -22,7 +22,7 @@ VEC_SCRATCH0, VEC_SCRATCH1 = 28, 29
 MAT_TANGENT, MAT_STIFFNESS, MAT_MASS, MAT_SYSTEM = range(4)
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI, PRECOND_MULTIGRID = range(4)
 OPT_PRECONDITIONER, OPT_CG_CHECK_INTERVAL, OPT_PROFILE, OPT_OPERATOR, OPT_SPMV_KERNEL, \
-    OPT_MG_SMOOTHER_DEGREE, OPT_MG_COARSE_DEGREE = range(7)
+    OPT_MG_SMOOTHER_DEGREE, OPT_MG_COARSE_DEGREE, OPT_MG_SMOOTHER_RATIO = range(8)
 
 EXPORTED_SYMBOLS = [
     "gf_create", "gf_destroy", "gf_last_error", "gf_set_option", "gf_comm_unique_id",
@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = [
     "gf_nl_newton_solve", "gf_nl_end_step", "gf_lin_assemble_once", "gf_lin_step", "gf_get_vector",
     "gf_set_vector", "gf_nnz", "gf_export_csr", "gf_spmv", "gf_spmv_timed", "gf_profile_get",
     "gf_synchronize", "gf_event_record", "gf_event_elapsed_ms", "gf_mg_attach", "gf_mg_vcycle",
+    "gf_comm_transport", "gf_comm_timed",
 ]
 
 
@@ -142,6 +143,15 @@ class Comm:
         if rc != GF_OK:
             raise GraftError(rc, "gf_comm_unique_id failed")
         return bytes(buf)
+
+    def transport(self):
+        """("peer_windows" | "nccl", halo exchanges issued, all-reduces issued)."""
+        nh, na = C.c_int64(0), C.c_int64(0)
+        f = lib().gf_comm_transport
+        f.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        f.restype = C.c_int
+        t = f(self._h, C.byref(nh), C.byref(na))
+        return ("peer_windows" if t == 1 else "nccl"), nh.value, na.value
 
     def close(self):
         if self._h:
@@ -324,6 +334,15 @@ class Handle:
         ms, nbytes = C.c_double(), C.c_double()
         self._check(lib().gf_spmv_timed(self._h, which_matrix, n_reps, C.byref(ms), C.byref(nbytes)))
         return ms.value, nbytes.value
+
+    def comm_timed(self, n_reps):
+        """(halo exchange us, 2-scalar all-reduce us) averaged over n_reps; collective."""
+        a, b = C.c_double(), C.c_double()
+        f = lib().gf_comm_timed
+        f.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        f.restype = C.c_int
+        self._check(f(self._h, n_reps, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def profile(self, reset=False):
         p = GfProfile()

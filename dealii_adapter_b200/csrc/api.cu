@@ -201,7 +201,7 @@ namespace gf
     Profile &p = *c.prof_sink;
     p.launches[kind]++;
     p.kernel_launches += n_kernels;
-    if (!p.enabled)
+    if (!p.enabled || (p.only_kind >= 0 && kind != p.only_kind))
       return;
     if (p.next_event + 2 > p.pool.size())
       {
@@ -312,6 +312,7 @@ extern "C"
         gf::build_numbering_and_pattern(*c, *d);
         setup_interface(*c, *d);
         setup_halo(*c, *d);
+        gf::comm_setup_context(*c);
         allocate_state(*c);
         c->n_global_dofs_for_maxit = c->n_owned;
         if (c->comm)
@@ -381,6 +382,11 @@ extern "C"
     if (h->h_err)
       cudaFreeHost(h->h_err);
     cudaStream_t s = h->owns_stream ? h->stream : nullptr;
+    if (h->comm && h->stream)
+      {
+        cudaStreamSynchronize(h->stream);
+        gf::comm_forget_stream(h->comm, h->stream);
+      }
     delete h;
     if (s)
       cudaStreamDestroy(s);
@@ -404,7 +410,8 @@ extern "C"
             break;
           case GF_OPT_PROFILE:
             gf::profile_collect(c);
-            c.prof.enabled = value != 0;
+            c.prof.enabled   = value != 0;
+            c.prof.only_kind = value == 2 ? int(gf::Profile::SPMV) : -1;
             break;
           case GF_OPT_OPERATOR:
             GF_REQUIRE(value == 0 || value == 1, GF_ERR_INVALID_ARG, "unknown operator kind");
@@ -432,6 +439,11 @@ extern "C"
             GF_REQUIRE(value >= 1 && value <= 1000, GF_ERR_INVALID_ARG, "bad coarse degree");
             for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
               l->mg_coarse_degree = int(value);
+            break;
+          case GF_OPT_MG_SMOOTHER_RATIO:
+            GF_REQUIRE(value >= 2 && value <= 1000, GF_ERR_INVALID_ARG, "bad smoother ratio");
+            for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
+              l->mg_smoother_ratio = double(value);
             break;
           default:
             throw gf::Error{GF_ERR_INVALID_ARG, "unknown option"};
@@ -868,6 +880,47 @@ extern "C"
     });
   }
 
+  int gf_comm_timed(gf_handle h, int n_reps, double *halo_us, double *allreduce_us)
+  {
+    return guarded(h, [&](gf_context &c) {
+      GF_REQUIRE(n_reps >= 1, GF_ERR_INVALID_ARG, "n_reps must be >= 1");
+      GF_REQUIRE(c.comm != nullptr, GF_ERR_INVALID_ARG, "handle has no communicator");
+      double *    x = vec_ptr(c, GF_VEC_SCRATCH0);
+      cudaEvent_t e0, e1, e2;
+      GF_CUDA_CHECK(cudaEventCreate(&e0));
+      GF_CUDA_CHECK(cudaEventCreate(&e1));
+      GF_CUDA_CHECK(cudaEventCreate(&e2));
+      const bool prof = c.prof.enabled;
+      c.prof.enabled  = false;
+      for (int k = 0; k < 5; ++k)
+        {
+          gf::halo_exchange(c, x);
+          gf::allreduce_sum(c, c.norm_out.p + 2, 2);
+        }
+      GF_CUDA_CHECK(cudaEventRecord(e0, c.stream));
+      for (int k = 0; k < n_reps; ++k)
+        gf::halo_exchange(c, x);
+      GF_CUDA_CHECK(cudaEventRecord(e1, c.stream));
+      for (int k = 0; k < n_reps; ++k)
+        gf::allreduce_sum(c, c.norm_out.p + 2, 2);
+      GF_CUDA_CHECK(cudaEventRecord(e2, c.stream));
+      GF_CUDA_CHECK(cudaEventSynchronize(e2));
+      gf::comm_check(c);
+      c.prof.enabled = prof;
+      float ms_h = 0, ms_a = 0;
+      GF_CUDA_CHECK(cudaEventElapsedTime(&ms_h, e0, e1));
+      GF_CUDA_CHECK(cudaEventElapsedTime(&ms_a, e1, e2));
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      cudaEventDestroy(e2);
+      if (halo_us)
+        *halo_us = 1e3 * double(ms_h) / n_reps;
+      if (allreduce_us)
+        *allreduce_us = 1e3 * double(ms_a) / n_reps;
+      return GF_OK;
+    });
+  }
+
   int gf_profile_get(gf_handle h, gf_profile *out, int reset)
   {
     return guarded(h, [&](gf_context &c) {
@@ -934,6 +987,7 @@ extern "C"
   {
     return guarded(h, [&](gf_context &c) {
       GF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      gf::comm_check(c);
       return GF_OK;
     });
   }

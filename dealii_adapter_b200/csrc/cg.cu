@@ -271,6 +271,7 @@ namespace gf
       GF_CUDA_CHECK(cudaMemcpyAsync(c.h_scalars, c.cg_scalars.p, sizeof(CGScalars),
                                     cudaMemcpyDeviceToHost, s));
       GF_CUDA_CHECK(cudaStreamSynchronize(s));
+      comm_check(c);
       return c.h_scalars->status;
     };
     // ---- startup: r = b - A x ; check ----
@@ -351,6 +352,7 @@ namespace gf
         GF_CUDA_CHECK(cudaMemcpyAsync(c.h_scalars, c.cg_scalars.p, sizeof(CGScalars),
                                       cudaMemcpyDeviceToHost, s));
         GF_CUDA_CHECK(cudaStreamSynchronize(s));
+        comm_check(c);
         if (c.h_scalars->status != 0)
           break;
         GF_REQUIRE(enqueued <= int64_t(c.h_scalars->it) + c.cg_check_every, GF_ERR_CUDA,

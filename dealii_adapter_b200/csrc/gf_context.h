@@ -177,6 +177,7 @@ namespace gf
       N_KINDS
     };
     bool                     enabled = false;
+    int                      only_kind = -1; // >= 0: only this kind is bracketed with events
     double                   ms[N_KINDS]{};
     int64_t                  launches[N_KINDS]{};
     int64_t                  kernel_launches = 0;
@@ -192,10 +193,36 @@ namespace gf
   };
 } // namespace gf
 
+// peer-window layout (comm.cu): flags, all-reduce slots, halo mailboxes, all double-buffered by
+// the parity of the communicator-wide epoch
+namespace gf
+{
+  constexpr int    P2P_MAX_RANKS  = 8;
+  constexpr int    P2P_AR_MAX     = 8;       // doubles per all-reduce
+  constexpr size_t P2P_HALO_FLAG  = 0;       // uint64 [2][P2P_MAX_RANKS] indexed by SENDER rank
+  constexpr size_t P2P_AR_FLAG    = 256;     // uint64 [2][P2P_MAX_RANKS]
+  constexpr size_t P2P_AR_SLOT    = 1024;    // double [2][P2P_MAX_RANKS][P2P_AR_MAX]
+  constexpr size_t P2P_MAILBOX    = 4096;    // double [2][P2P_MAX_RANKS][P2P_HALO_CAP]
+  constexpr size_t P2P_HALO_CAP   = size_t(1) << 19; // doubles per (parity, sender): 4 MiB
+  constexpr size_t P2P_WINDOW_BYTES =
+    P2P_MAILBOX + 2 * size_t(P2P_MAX_RANKS) * P2P_HALO_CAP * sizeof(double);
+} // namespace gf
+
 struct gf_comm_s
 {
   void *nccl_comm = nullptr;
   int   rank = 0, n_ranks = 1, device = 0;
+  // ---- peer windows over NVLink (cudaIpc); p2p == false: NCCL transport ----
+  bool           p2p = false;
+  unsigned char *win[gf::P2P_MAX_RANKS] = {}; // win[rank] = own allocation, others IPC-mapped
+  unsigned long long halo_epoch[gf::P2P_MAX_RANKS] = {}; // per neighbour pair (symmetric counts)
+  unsigned long long ar_epoch = 0;
+  unsigned *     blk_counter = nullptr; // device [P2P_MAX_RANKS]: last-block detection of the push
+  int *          h_err = nullptr;       // mapped pinned: set by a kernel whose flag wait timed out
+  int *          d_err = nullptr;       // device alias of h_err
+  unsigned long long timeout_ns = 60ull * 1000000000ull;
+  cudaStream_t   last_stream = nullptr; // ops of one communicator are ordered on one stream
+  int64_t        n_halo = 0, n_allreduce = 0; // operations issued (diagnostics)
 };
 
 struct gf_context
@@ -285,6 +312,7 @@ struct gf_context
   std::vector<int64_t> send_ptr, recv_ptr;
   gf::DevBuf<int32_t> send_idx, recv_idx; // internal dof ids
   gf::DevBuf<double>  send_buf, recv_buf;
+  bool                halo_p2p = false; // this handle's halo lists fit the peer mailboxes
 
   // matrix-free tangent operator (matfree.cu), GF_OPT_OPERATOR = 1
   gf::DevBuf<double> mf_qp;     // [n_cells][NF][nq]: C = J^-1 F^-1, JxW*Jc (upper Voigt), JxW*tau
@@ -369,6 +397,9 @@ namespace gf
   void halo_reduce_add(gf_context &c, double *v); // ghost partial sums -> owners (+=)
   void halo_exchange(gf_context &c, double *v);
   void allreduce_sum(gf_context &c, double *dev_values, int count);
+  void comm_setup_context(gf_context &c);  // after setup_halo: agree on the transport (collective)
+  void comm_check(gf_context &c);          // throws if a peer-window wait timed out
+  void comm_forget_stream(gf_comm cm, cudaStream_t s); // before a stream is destroyed
   // profile helpers
   struct ProfScope
   {

@@ -420,7 +420,7 @@ namespace gf
     {
       const int     g = vec_grid(c, c.n_owned_nodes);
       const int64_t n = c.n_local;
-      int           n_it = 8;
+      int           n_it = 4; // warm start: the operator changed little since the last assembly
       if (!c.mg_e_valid)
         {
           ProfScope ps(c, Profile::MG_VEC);
@@ -569,6 +569,7 @@ namespace gf
         if (l != &f)
           {
             GF_CUDA_CHECK(cudaStreamSynchronize(l->stream));
+            comm_forget_stream(l->comm, l->stream);
             if (l->owns_stream && l->stream != f.stream)
               GF_CUDA_CHECK(cudaStreamDestroy(l->stream));
             l->stream      = f.stream;

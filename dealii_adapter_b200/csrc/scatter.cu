@@ -4,9 +4,9 @@
 // nonlinear_elasticity.cc:760-774; linear: stiffness_matrix.add :327-334 and
 // MatrixTools::apply_boundary_values :448-451).
 //
-// Gather formulation: every BSR entry owns the ordered (ascending cell = WorkStream copier
-// order, :1078-1084) list of element-matrix entries that sum into it; one warp per block row
-// streams its value array in storage order. HBM-bound: reads dpc^2*8 B per cell, writes the
+// Gather formulation: every BSR block owns the ordered (ascending cell = WorkStream copier
+// order, :1078-1084) list of element-matrix blocks that sum into it; one warp per block row, one
+// lane per dim x dim block. HBM-bound: reads dpc^2*8 B per cell, writes the
 // BSR values once.
 #include "gf_context.h"
 #include "kernel_utils.cuh"
@@ -40,55 +40,72 @@ namespace gf
       const int64_t cbase  = cand_ptr[A];
       const int     ctotal = int(cand_ptr[A + 1] - cbase);
       const int     npc2   = npc * npc;
-      for (int idx = lane; idx < DIM * stride; idx += 32)
+      bool          row_con[DIM];
+#pragma unroll
+      for (int r = 0; r < DIM; ++r)
+        row_con[r] = apply_constraints && constrained[A * DIM + r] != 0;
+      if (first && lane == 0 && stride > nb * DIM) // padding double of every scalar row
+#pragma unroll
+        for (int r = 0; r < DIM; ++r)
+          val[vbase + r * stride + nb * DIM] = 0.0;
+      // one lane per dim x dim block: the index arithmetic and the source-list walk are shared
+      // by the block's dim*dim entries; stores of consecutive lanes are contiguous per scalar row
+      for (int blk = lane; blk < nb; blk += 32)
         {
-          const int r = idx / stride, rem = idx - r * stride;
-          if (rem >= nb * DIM)
-            {
-              if (first)
-                val[vbase + idx] = 0.0; // padding
-              continue;
-            }
-          const int     blk = rem / DIM, cc = rem - blk * DIM;
           const int32_t B  = bcol[b0 + blk];
           const int     s0 = src_off[b0 + blk];
           const int     s1 = blk + 1 < nb ? int(src_off[b0 + blk + 1]) : ctotal;
-          const bool    is_diag = (B == A) && (r == cc);
-          // constrained rows/columns are dropped; a constrained diagonal collects |K_e(i,i)|
-          bool drop = false, use_abs = false;
-          if (apply_constraints)
-            {
-              const bool rc = constrained[A * DIM + r] != 0;
-              const bool cn = constrained[int64_t(B) * DIM + cc] != 0;
-              use_abs       = is_diag && rc;
-              drop          = (rc || cn) && !use_abs;
-            }
+          bool          col_con[DIM];
+#pragma unroll
+          for (int cc = 0; cc < DIM; ++cc)
+            col_con[cc] = apply_constraints && constrained[int64_t(B) * DIM + cc] != 0;
+          double sum[DIM][DIM];
           // running value continues across element-buffer chunks: same order as one pass
-          double sum = first ? 0.0 : val[vbase + idx];
-          if (!drop)
-            for (int s = s0; s < s1; ++s)
-              {
-                const int32_t src  = row_src[cbase + s];
-                const int64_t cell = src / npc2;
-                if (cell < c0 || cell >= c1)
-                  continue;
-                const int     ab = src - int32_t(cell) * npc2;
-                const int     a = ab / npc, b = ab - a * npc;
-                const double *ke = ke_buf + (cell - c0) * int64_t(dpc) * dpc;
-                double        v  = ke[(a * DIM + r) * dpc + b * DIM + cc];
-                if (use_abs)
+#pragma unroll
+          for (int r = 0; r < DIM; ++r)
+#pragma unroll
+            for (int cc = 0; cc < DIM; ++cc)
+              sum[r][cc] = first ? 0.0 : val[vbase + r * stride + blk * DIM + cc];
+          for (int s = s0; s < s1; ++s)
+            {
+              const int32_t src  = row_src[cbase + s];
+              const int64_t cell = src / npc2;
+              if (cell < c0 || cell >= c1)
+                continue;
+              const int     ab = src - int32_t(cell) * npc2;
+              const int     a = ab / npc, b = ab - a * npc;
+              const double *ke = ke_buf + (cell - c0) * int64_t(dpc) * dpc;
+              const double *kb = ke + (a * DIM) * dpc + b * DIM;
+#pragma unroll
+              for (int r = 0; r < DIM; ++r)
+#pragma unroll
+                for (int cc = 0; cc < DIM; ++cc)
                   {
-                    v = fabs(v);
-                    if (v == 0.0) // deal.II: fall back to the cell's average |diagonal|
+                    // constrained rows/columns are dropped; a constrained diagonal collects
+                    // |K_e(i,i)|
+                    const bool use_abs = (B == A) && (r == cc) && row_con[r];
+                    const bool drop    = (row_con[r] || col_con[cc]) && !use_abs;
+                    if (drop)
+                      continue;
+                    double v = kb[r * dpc + cc];
+                    if (use_abs)
                       {
-                        for (int i = 0; i < dpc; ++i)
-                          v += fabs(ke[i * dpc + i]);
-                        v /= double(dpc);
+                        v = fabs(v);
+                        if (v == 0.0) // deal.II: fall back to the cell's average |diagonal|
+                          {
+                            for (int i = 0; i < dpc; ++i)
+                              v += fabs(ke[i * dpc + i]);
+                            v /= double(dpc);
+                          }
                       }
+                    sum[r][cc] += v;
                   }
-                sum += v;
-              }
-          val[vbase + idx] = sum;
+            }
+#pragma unroll
+          for (int r = 0; r < DIM; ++r)
+#pragma unroll
+            for (int cc = 0; cc < DIM; ++cc)
+              val[vbase + r * stride + blk * DIM + cc] = sum[r][cc];
         }
     }
 

@@ -170,6 +170,7 @@ namespace gf
     GF_CUDA_CHECK(
       cudaMemcpyAsync(c.h_norm, c.norm_out.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     GF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    comm_check(c);
     return std::sqrt(c.h_norm[0]);
   }
   void iface_scatter(gf_context &c, const double *host_buf, double *vec)

@@ -123,11 +123,14 @@ extern "C"
   {
     GF_OPT_PRECONDITIONER = 0, /* GF_PRECOND_* ; replaces SSOR (nonlinear:1180-1182, linear:548-549) */
     GF_OPT_CG_CHECK_INTERVAL,  /* iterations enqueued between host polls of the device flag */
-    GF_OPT_PROFILE,            /* 1: bracket every kernel class with CUDA events (see gf_profile) */
+    GF_OPT_PROFILE,            /* 1: bracket every kernel class with CUDA events (see gf_profile);
+                                  2: only the finest-level SpMV launches (two events per launch,
+                                  cheap enough for a timed region); launch counters always run */
     GF_OPT_OPERATOR,           /* 0: assembled BSR SpMV ; 1: matrix-free tangent operator in CG */
     GF_OPT_SPMV_KERNEL,        /* 0: TMA-tiled kernel (default) ; 1: LDG warp-per-row kernel */
     GF_OPT_MG_SMOOTHER_DEGREE, /* Chebyshev degree of the pre-/post-smoother (default 3) */
-    GF_OPT_MG_COARSE_DEGREE    /* Chebyshev degree of the coarsest-level solve (default 40) */
+    GF_OPT_MG_COARSE_DEGREE,   /* Chebyshev degree of the coarsest-level solve (default 40) */
+    GF_OPT_MG_SMOOTHER_RATIO   /* smoothers damp the eigenvalues in [lmax/ratio, lmax] (default 20) */
   };
 
   /* device-time breakdown accumulated while GF_OPT_PROFILE = 1 (CUDA events on the library's
@@ -173,6 +176,14 @@ extern "C"
   int  gf_comm_unique_id(uint8_t id[128]);
   int  gf_comm_create(const uint8_t id[128], int rank, int n_ranks, int device, gf_comm *out);
   void gf_comm_destroy(gf_comm c);
+  /* which transport carries the halo exchange and the scalar all-reduce: peer windows = every
+   * rank's mailbox/flag window is mapped into all peers with cudaIpc and the library's own kernels
+   * store ghost values / partial sums straight into the neighbour's HBM over NVLink (default);
+   * NCCL = grouped ncclSend/ncclRecv + ncclAllReduce (GF_COMM_P2P=0, or IPC mapping unavailable).
+   * Also returns the number of halo exchanges and all-reduces issued so far (may be NULL). */
+#define GF_TRANSPORT_NCCL 0
+#define GF_TRANSPORT_PEER_WINDOWS 1
+  int gf_comm_transport(gf_comm c, int64_t *n_halo, int64_t *n_allreduce);
 
   /* ---- Adapter bodies (adapter.h) ---------------------------------------------------------- */
   /* format_precice_to_deal :421-443 — iface_buf = read_data_buffer [x0,y0,(z0),x1,...] scattered
@@ -228,6 +239,9 @@ extern "C"
    * bytes one launch streams in the stored format (values + indices + x + y) */
   int gf_spmv_timed(gf_handle h, int which_matrix, int n_reps, double *ms_per_launch,
                     double *bytes_per_launch);
+  /* collective: n_reps ghost-DoF halo exchanges of a scratch vector, then n_reps 2-scalar
+   * all-reduces, each batch bracketed by CUDA events; average microseconds per operation */
+  int gf_comm_timed(gf_handle h, int n_reps, double *halo_us, double *allreduce_us);
   int gf_profile_get(gf_handle h, gf_profile *out, int reset);
   int gf_synchronize(gf_handle h);
   /* CUDA events on the library's own stream (torch.cuda.Event only sees torch's stream):

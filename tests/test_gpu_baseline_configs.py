@@ -1,0 +1,158 @@
+"""GPU parity at BASELINE.json's named sizes.
+
+cfg1 (PF 2D linear Q2, 3x18 cells, 518 DoFs) is `test_linear_matrices_and_steps_match_oracle[2-2-
+reps0-cellwise]` in test_gpu_parity.py. Here:
+  cfg2  FSI3 2D Q2 neo-Hookean, 144x24 cells, 28,322 DoFs: Newton counts identical and interface /
+        watch-point displacement 1e-8 against the committed oracle fixture (tests/golden/).
+  cfg3  PF 3D Q2 neo-Hookean 24x144x24 cells, 2,081,667 DoFs (too large for the CPU oracle in a
+        test): size-independent properties — bitwise reproducible assembly, symmetry and linearity
+        of the operator, TMA kernel == LDG kernel bitwise, matrix-free == assembled to 1e-12,
+        checkpoint/restore replays a coupled timestep bit for bit."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import nl_params, rel_err, smooth_field
+from dealii_adapter_b200.problem import make_problem
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+
+@pytest.fixture(scope="module")
+def libs(native_libs):
+    from dealii_adapter_b200 import capi, multigrid, solvers
+    native_libs.build_cuda()
+    capi.lib()
+    return capi, solvers, multigrid
+
+
+def test_cfg2_newton_counts_and_watchpoint_match_golden(libs):
+    capi, solvers, mg = libs
+    import make_cfg2_golden as g
+    gold = np.load(os.path.join(HERE, "golden", "cfg2_fsi3_q2.npz"))
+    prob = g.cfg2_problem()
+    assert prob.n_dofs == int(gold["n_dofs"])
+    n_steps = len(gold["newton_counts"])
+    for use_mg in (False, True):
+        part = solvers.FakeParticipant(2, n_steps, prob.params.delta_t,
+                                       lambda t, it: g.traction(prob, int(round(t / 0.01)) - 1))
+        H = mg.Hierarchy(prob) if use_mg else None
+        solid = solvers.Solid(prob, part, handle=H.fine if H else None)
+        solid.run()
+        assert [len(r) for r in solid.history] == list(gold["newton_counts"])
+        tip = int(gold["watch_point_index"])
+        for (w, it, data), ref in zip(part.written, gold["interface_displacement"]):
+            assert rel_err(data, ref) < 1e-8
+            assert abs(data[2 * tip + 1] - ref[2 * tip + 1]) <= 1e-8 * abs(ref[2 * tip + 1])
+        (H or solid.handle).close()
+
+
+@pytest.fixture(scope="module")
+def cfg3(libs):
+    capi, solvers, mg = libs
+    p = nl_params(poly_degree=2, scenario="PF", type_lin="CG", delta_t=0.01, max_iterations_lin=1.0)
+    prob = make_problem(p, 3, reps=[24, 144, 24], numbering="lexicographic")
+    assert prob.n_dofs == 2081667 and prob.mesh.n_cells == 82944
+    H = mg.Hierarchy(prob)
+    yield prob, H
+    H.close()
+
+
+def _load_state(capi, h, prob, seed):
+    u = smooth_field(prob, 0.004, seed)
+    h.set_vector(capi.NL_TOTAL_DISPLACEMENT, u)
+    h.set_vector(capi.NL_VELOCITY_OLD, smooth_field(prob, 0.05, seed + 1))
+    h.set_vector(capi.NL_ACCELERATION_OLD, smooth_field(prob, 2.0, seed + 2))
+    h.set_traction(np.tile([1500.0, 0.0, 50.0], prob.n_iface_nodes))
+    h.nl_begin_step()
+
+
+def test_cfg3_assembly_is_bitwise_reproducible_and_operator_is_symmetric_linear(libs, cfg3):
+    capi, solvers, mg = libs
+    prob, H = cfg3
+    h = H.fine
+    assert h.nnz() == 386532873
+    rng = np.random.RandomState(3)
+    x, y = rng.uniform(-1, 1, prob.n_dofs), rng.uniform(-1, 1, prob.n_dofs)
+    free = prob.constrained == 0
+
+    def apply(v):
+        h.set_vector(capi.VEC_SCRATCH0, v)
+        h.spmv(capi.MAT_TANGENT, capi.VEC_SCRATCH0, capi.VEC_SCRATCH1)
+        return h.get_vector(capi.VEC_SCRATCH1)
+
+    _load_state(capi, h, prob, 5)
+    r1 = h.nl_newton_assemble()
+    rhs1, Ax1 = h.get_vector(capi.NL_SYSTEM_RHS), apply(x)
+    _load_state(capi, h, prob, 5)
+    r2 = h.nl_newton_assemble()
+    rhs2, Ax2 = h.get_vector(capi.NL_SYSTEM_RHS), apply(x)
+    assert r1 == r2 and np.array_equal(rhs1, rhs2) and np.array_equal(Ax1, Ax2)   # no FP atomics
+    Ay = apply(y)
+    # symmetry of the constrained tangent: x.Ay == y.Ax
+    a, b = float(x @ Ay), float(y @ Ax1)
+    assert abs(a - b) <= 1e-12 * np.sqrt(float(Ax1 @ Ax1) * float(y @ y))
+    # linearity
+    z = apply(2.5 * x - 0.75 * y)
+    assert rel_err(z, 2.5 * Ax1 - 0.75 * Ay) < 1e-13
+    # constrained rows are decoupled: (A x)_i = d_i x_i with d_i > 0
+    d = Ax1[~free] / x[~free]
+    xx = x.copy()
+    xx[free] = 0.0
+    assert np.all(d > 0) and rel_err(apply(xx)[~free], Ax1[~free]) < 1e-14
+    # the TMA-tiled kernel and the LDG warp-per-row kernel add in the same order
+    h.set_option(capi.OPT_SPMV_KERNEL, 1)
+    Ax_ldg = apply(x)
+    h.set_option(capi.OPT_SPMV_KERNEL, 0)
+    assert np.array_equal(Ax_ldg, Ax1)
+
+
+def test_cfg3_matrix_free_operator_matches_assembled(libs, cfg3):
+    capi, solvers, mg = libs
+    prob, H = cfg3
+    h = H.fine
+    x = np.random.RandomState(4).uniform(-1, 1, prob.n_dofs)
+    out = {}
+    for op in (0, 1):
+        h.set_option(capi.OPT_OPERATOR, op)
+        _load_state(capi, h, prob, 9)
+        res = h.nl_newton_assemble()
+        h.set_vector(capi.VEC_SCRATCH0, x)
+        h.spmv(capi.MAT_TANGENT, capi.VEC_SCRATCH0, capi.VEC_SCRATCH1)
+        out[op] = (res, h.get_vector(capi.NL_SYSTEM_RHS), h.get_vector(capi.VEC_SCRATCH1))
+    h.set_option(capi.OPT_OPERATOR, 0)
+    assert abs(out[0][0] - out[1][0]) <= 1e-12 * out[0][0]
+    assert rel_err(out[1][1], out[0][1]) < 1e-12
+    assert rel_err(out[1][2], out[0][2]) < 1e-12
+
+
+def test_cfg3_checkpoint_restore_replays_the_timestep_bit_for_bit(libs, cfg3):
+    """Implicit coupling at full size: save, step, restore, step again with the same traction ->
+    identical Newton/CG histories and bitwise identical interface displacement (the whole path is
+    deterministic: no FP atomics, fixed-order reductions)."""
+    capi, solvers, mg = libs
+    prob, H = cfg3
+    h = H.fine
+    for k in range(6):
+        h.set_vector(k, np.zeros(prob.n_dofs))
+    buf = np.tile([2000.0, 0.0, 0.0], prob.n_iface_nodes)
+    part = solvers.FakeParticipant(3, 10, prob.params.delta_t, lambda t, it: buf, 2)
+    solid = solvers.Solid(prob, part, handle=h)
+    solid.adapter.initialize(prob)
+    solid.step()     # sub-iteration 0: checkpoint written, state restored at the end
+    solid.step()     # sub-iteration 1: the same window again from the checkpoint
+    (w0, i0, d0), (w1, i1, d1) = part.written[0], part.written[1]
+    assert (w0, i0, w1, i1) == (0, 0, 0, 1)
+    assert solid.history[0] == solid.history[1]
+    assert 3 <= len(solid.history[0]) <= 6
+    assert np.array_equal(d0, d1)
+    assert np.isfinite(d0).all() and 1e-4 < np.abs(d0).max() < 0.2
+    # Newmark kinematics after the accepted step: v = a4*du + a5*v_old + a6*a_old with zero history
+    u = h.get_vector(capi.NL_TOTAL_DISPLACEMENT)
+    v = h.get_vector(capi.NL_VELOCITY)
+    dt, beta, gamma = prob.params.delta_t, prob.params.beta, prob.params.gamma
+    assert rel_err(v, gamma / (beta * dt) * u) < 1e-12
