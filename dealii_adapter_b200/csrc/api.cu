@@ -440,6 +440,16 @@ extern "C"
             for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
               l->mg_coarse_degree = int(value);
             break;
+          case GF_OPT_SPMV_PREFETCH:
+            GF_REQUIRE(value >= 0 && value <= 64, GF_ERR_INVALID_ARG, "bad prefetch distance");
+            for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
+              l->spmv_prefetch_tiles = int(value);
+            break;
+          case GF_OPT_SPMV_GATHER:
+            GF_REQUIRE(value == 0 || value == 1, GF_ERR_INVALID_ARG, "unknown gather mode");
+            for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
+              l->spmv_gather_mode = int(value);
+            break;
           case GF_OPT_MG_SMOOTHER_RATIO:
             GF_REQUIRE(value >= 2 && value <= 1000, GF_ERR_INVALID_ARG, "bad smoother ratio");
             for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
@@ -511,6 +521,17 @@ extern "C"
                                         c.n_local * sizeof(double), cudaMemcpyDeviceToDevice,
                                         c.stream));
         }
+      // hidden solver state: the warm-start vector of the smoothers' eigenvalue estimate, so
+      // that a restored window replays bit for bit
+      for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
+        if (l->mg_e.p)
+          {
+            if (!l->mg_e_saved.p)
+              l->mg_e_saved.alloc(l->n_local);
+            GF_CUDA_CHECK(cudaMemcpyAsync(l->mg_e_saved.p, l->mg_e.p, l->n_local * sizeof(double),
+                                          cudaMemcpyDeviceToDevice, c.stream));
+            l->mg_e_saved_valid = l->mg_e_valid;
+          }
       c.has_saved = true;
       return GF_OK;
     });
@@ -526,6 +547,13 @@ extern "C"
       for (int i = 0; i < n; ++i)
         GF_CUDA_CHECK(cudaMemcpyAsync(c.vec[first + i].p, c.saved[i].p, c.n_local * sizeof(double),
                                       cudaMemcpyDeviceToDevice, c.stream));
+      for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
+        if (l->mg_e.p && l->mg_e_saved.p)
+          {
+            GF_CUDA_CHECK(cudaMemcpyAsync(l->mg_e.p, l->mg_e_saved.p, l->n_local * sizeof(double),
+                                          cudaMemcpyDeviceToDevice, c.stream));
+            l->mg_e_valid = l->mg_e_saved_valid;
+          }
       return GF_OK;
     });
   }

@@ -6,7 +6,11 @@
 // (nonlinear_elasticity.cc:791-859). Output is the element matrix K_e (row-major dpc x dpc) and
 // r_e per cell; the constrained, deterministic scatter is scatter.cu.
 //
-// Per cell (one CTA, persistent grid-stride loop; tables staged once in shared memory):
+// One persistent CTA per SM, warp-specialised: PRODUCER warps run phases A and B for the chunk
+// (QC quadrature points) after the one the CONSUMER warps are contracting in phase C; the T/G
+// chunks travel through a 2-deep shared-memory ring guarded by mbarriers (full/empty), so the
+// FP64 FMA stream of phase C is not interrupted by the latency-bound set-up phases or by
+// CTA-wide barriers. Tables are staged once per CTA in shared memory.
 //   phase A  one thread per quadrature point: H = grad u, F, J, F^-1, b_bar, tau, Jc (Voigt D),
 //            all scaled by JxW                                              (:902-934,:958-961)
 //   phase B  one thread per (q, node a): spatial gradient g_a = grad_X N_a F^-1 (:946-947),
@@ -39,22 +43,26 @@ namespace gf
       static constexpr int NSUB = 32 / NPCP;
       static constexpr int AT   = 3;                   // nodes a per (warp, sub) unit
       static constexpr int NG   = (NPC + AT - 1) / AT; // a-groups
-      static constexpr int NW   = (DIM == 3 && P == 2) ? 9 : 4;
-      static constexpr int NT   = NW * 32;
-      static constexpr int QC   = (DIM == 3 && P == 2) ? 16 : NQ; // q-points per chunk
+      static constexpr int NW   = (DIM == 3 && P == 2) ? 9 : 4; // consumer warps (phase C)
+      static constexpr int NPW  = (DIM == 3 && P == 2) ? 3 : 1; // producer warps (phases A, B)
+      static constexpr int NT   = (NW + NPW) * 32;
+      static constexpr int RPT  = (DPC + NPW * 32 - 1) / (NPW * 32); // residual entries/producer
+      static constexpr int QC   = (DIM == 3 && P == 2) ? 8 : NQ; // q-points per chunk
       static constexpr int QS   = DIM * DIM + VO * VO + VO + DIM + 2; // per-q scalars
       static_assert(NW * NSUB >= NG, "every a-group needs its own unit");
       static_assert(NQ % QC == 0, "chunking");
-      static_assert(NT >= NQ && NT >= DPC, "thread count");
+
       // shared memory (doubles)
       static constexpr int OFF_N   = 0;
       static constexpr int OFF_DN  = OFF_N + NQ * NPC;
       static constexpr int OFF_U   = OFF_DN + NQ * NPC * DIM;
       static constexpr int OFF_ACC = OFF_U + DPC;
       static constexpr int OFF_Q   = OFF_ACC + DPC;          // [NQ][QS]
-      static constexpr int OFF_T   = OFF_Q + NQ * QS;        // [QC][NPC][TS]
-      static constexpr int OFF_G   = OFF_T + QC * NPC * TS;  // [QC][DIM][NPCP]
-      static constexpr int SMEM_D  = OFF_G + QC * DIM * NPCP;
+      static constexpr int OFF_T   = OFF_Q + NQ * QS;            // 2 x [QC][NPC][TS]
+      static constexpr int OFF_G   = OFF_T + 2 * QC * NPC * TS;  // 2 x [QC][DIM][NPCP]
+      static constexpr int OFF_BAR = OFF_G + 2 * QC * DIM * NPCP; // 4 mbarriers
+      static constexpr int SMEM_D  = OFF_BAR + 4;
+      static_assert(SMEM_D * 8 <= 227 * 1024, "shared memory budget");
       static constexpr size_t SMEM_BYTES = size_t(SMEM_D) * sizeof(double);
       // offsets inside a per-q record
       static constexpr int Q_C   = 0;                 // C = Jinv * Finv            [DIM*DIM]
@@ -76,264 +84,316 @@ namespace gf
     {
       using C = NLCfg<DIM, P>;
       constexpr int NPC = C::NPC, DPC = C::DPC, NQ = C::NQ, VO = C::VO, TS = C::TS, QC = C::QC,
-                    QS = C::QS, NPCP = C::NPCP, AT = C::AT;
+                    QS = C::QS, NPCP = C::NPCP, AT = C::AT, NCT = C::NW * 32, NPT = C::NPW * 32;
       extern __shared__ __align__(16) double sm[];
       double *sN = sm + C::OFF_N, *sdN = sm + C::OFF_DN, *su = sm + C::OFF_U,
-             *sacc = sm + C::OFF_ACC, *sQ = sm + C::OFF_Q, *sT = sm + C::OFF_T,
-             *sG = sm + C::OFF_G;
+             *sacc = sm + C::OFF_ACC, *sQ = sm + C::OFF_Q;
+      uint64_t *bars = reinterpret_cast<uint64_t *>(sm + C::OFF_BAR);
+      uint64_t *full = bars, *empty = bars + 2; // per T/G buffer
       const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
       for (int i = tid; i < NQ * NPC; i += C::NT)
         sN[i] = tabN[i];
       for (int i = tid; i < NQ * NPC * DIM; i += C::NT)
         sdN[i] = tabdN[i];
-      // unit = (warp, sub-warp); each unit owns one group of AT nodes a; lane-in-sub = node b
-      const int  sub = lane / NPCP, b = lane % NPCP;
-      const int  unit = warp * C::NSUB + sub;
-      const bool unit_active = unit < C::NG;
-      const int  a_base = unit_active ? unit * AT : 0;
-      const int  bb = b < NPC ? b : NPC - 1; // clamped for loads; results of b >= NPC discarded
-
-      for (int64_t cell = c0 + blockIdx.x; cell < c1; cell += gridDim.x)
+      if (tid == 0)
         {
-          __syncthreads(); // previous cell fully consumed
-          const double *gm = geom + cell * (DIM * DIM + 1);
-          double        Jinv[DIM][DIM];
-#pragma unroll
-          for (int i = 0; i < DIM; ++i)
-#pragma unroll
-            for (int j = 0; j < DIM; ++j)
-              Jinv[i][j] = gm[i * DIM + j];
-          const double detJ = gm[DIM * DIM];
-          if (tid < DPC)
+          for (int k = 0; k < 2; ++k)
             {
-              const int32_t node = cell_nodes[cell * NPC + tid / DIM];
-              su[tid]            = u_total[int64_t(node) * DIM + tid % DIM];
-              sacc[tid]          = accel[int64_t(node) * DIM + tid % DIM];
+              mbar_init(smem_u32(&full[k]), C::NPW);  // one arrive per producer warp
+              mbar_init(smem_u32(&empty[k]), C::NW);  // one arrive per consumer warp
             }
-          __syncthreads();
+          asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+      __syncthreads();
 
-          // ---------------- phase A: kinematics + material per quadrature point -----------------
-          if (tid < NQ)
+      if (warp >= C::NW)
+        {
+          // =============================== producer warps ======================================
+          // phase A (per cell), phase B + residual (per chunk of QC q-points) into the T/G ring
+          const int ptid = tid - NCT;
+          int       it   = 0; // chunks produced by this CTA so far
+          for (int64_t cell = c0 + blockIdx.x; cell < c1; cell += gridDim.x)
             {
-              const int q = tid;
-              double    Hr[DIM][DIM], acc[DIM];
-              double    sumN = 0;
-#pragma unroll
-              for (int i = 0; i < DIM; ++i)
-                {
-                  acc[i] = 0;
-#pragma unroll
-                  for (int j = 0; j < DIM; ++j)
-                    Hr[i][j] = 0;
-                }
-              for (int a = 0; a < NPC; ++a)
-                {
-                  const double Na = sN[q * NPC + a];
-                  sumN += Na;
-#pragma unroll
-                  for (int cc = 0; cc < DIM; ++cc)
-                    {
-                      const double ua = su[a * DIM + cc];
-                      acc[cc] += sacc[a * DIM + cc] * Na;
-#pragma unroll
-                      for (int e = 0; e < DIM; ++e)
-                        Hr[cc][e] += ua * sdN[(q * NPC + a) * DIM + e];
-                    }
-                }
-              double F[DIM][DIM];
+              named_bar_sync(1, NPT); // previous cell's su / sQ fully consumed by the producers
+              const double *gm = geom + cell * (DIM * DIM + 1);
+              double        Jinv[DIM][DIM];
 #pragma unroll
               for (int i = 0; i < DIM; ++i)
 #pragma unroll
                 for (int j = 0; j < DIM; ++j)
-                  {
-                    double h = 0;
-#pragma unroll
-                    for (int e = 0; e < DIM; ++e)
-                      h += Hr[i][e] * Jinv[e][j];
-                    F[i][j] = (i == j ? 1.0 : 0.0) + h; // Kinematics::F :927
-                  }
-              const double detF = det<DIM>(F); // :929
-              if (!(detF > 0.0))
-                atomicExch(err_flag, 1); // Assert :935
-              double Finv[DIM][DIM];
-              inverse<DIM>(F, detF, Finv); // :934
-              const double s = pow(detF, -1.0 / DIM); // Kinematics::F_iso :930
-              double       bbar[VO];                  // Kinematics::b :932
-#pragma unroll
-              for (int k = 0; k < VO; ++k)
+                  Jinv[i][j] = gm[i * DIM + j];
+              const double detJ = gm[DIM * DIM];
+              for (int i = ptid; i < DPC; i += NPT)
                 {
-                  const int i = voigt_i<DIM>(k), j = voigt_j<DIM>(k);
-                  double    v = 0;
+                  const int32_t node = cell_nodes[cell * NPC + i / DIM];
+                  su[i]              = u_total[int64_t(node) * DIM + i % DIM];
+                  sacc[i]            = accel[int64_t(node) * DIM + i % DIM];
+                }
+              named_bar_sync(1, NPT);
+              // ------------- phase A: kinematics + material per quadrature point ---------------
+              for (int q = ptid; q < NQ; q += NPT)
+                {
+                  double Hr[DIM][DIM], acc[DIM];
+                  double sumN = 0;
+#pragma unroll
+                  for (int i = 0; i < DIM; ++i)
+                    {
+                      acc[i] = 0;
+#pragma unroll
+                      for (int j = 0; j < DIM; ++j)
+                        Hr[i][j] = 0;
+                    }
+                  for (int a = 0; a < NPC; ++a)
+                    {
+                      const double Na = sN[q * NPC + a];
+                      sumN += Na;
+#pragma unroll
+                      for (int cc = 0; cc < DIM; ++cc)
+                        {
+                          const double ua = su[a * DIM + cc];
+                          acc[cc] += sacc[a * DIM + cc] * Na;
+#pragma unroll
+                          for (int e = 0; e < DIM; ++e)
+                            Hr[cc][e] += ua * sdN[(q * NPC + a) * DIM + e];
+                        }
+                    }
+                  double F[DIM][DIM];
+#pragma unroll
+                  for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                    for (int j = 0; j < DIM; ++j)
+                      {
+                        double h = 0;
+#pragma unroll
+                        for (int e = 0; e < DIM; ++e)
+                          h += Hr[i][e] * Jinv[e][j];
+                        F[i][j] = (i == j ? 1.0 : 0.0) + h; // Kinematics::F :927
+                      }
+                  const double detF = det<DIM>(F); // :929
+                  if (!(detF > 0.0))
+                    atomicExch(err_flag, 1); // Assert :935
+                  double Finv[DIM][DIM];
+                  inverse<DIM>(F, detF, Finv); // :934
+                  const double s = pow(detF, -1.0 / DIM); // Kinematics::F_iso :930
+                  double       bbar[VO];                  // Kinematics::b :932
+#pragma unroll
+                  for (int k = 0; k < VO; ++k)
+                    {
+                      const int i = voigt_i<DIM>(k), j = voigt_j<DIM>(k);
+                      double    v = 0;
+#pragma unroll
+                      for (int e = 0; e < DIM; ++e)
+                        v += (s * F[i][e]) * (s * F[j][e]);
+                      bbar[k] = v;
+                    }
+                  double tau[VO], D[VO][VO];
+                  neo_hooke<DIM>(prm.kappa, prm.mu, detF, bbar, tau, D); // :958-961
+                  const double JxW = detJ * tabw[q];
+                  double *     rec = sQ + q * QS;
 #pragma unroll
                   for (int e = 0; e < DIM; ++e)
-                    v += (s * F[i][e]) * (s * F[j][e]);
-                  bbar[k] = v;
-                }
-              double tau[VO], D[VO][VO];
-              neo_hooke<DIM>(prm.kappa, prm.mu, detF, bbar, tau, D); // :958-961
-              const double JxW = detJ * tabw[q];
-              double *     rec = sQ + q * QS;
 #pragma unroll
-              for (int e = 0; e < DIM; ++e)
+                    for (int l = 0; l < DIM; ++l)
+                      {
+                        double v = 0;
 #pragma unroll
-                for (int l = 0; l < DIM; ++l)
-                  {
-                    double v = 0;
+                        for (int d = 0; d < DIM; ++d)
+                          v += Jinv[e][d] * Finv[d][l];
+                        rec[C::Q_C + e * DIM + l] = v;
+                      }
 #pragma unroll
-                    for (int d = 0; d < DIM; ++d)
-                      v += Jinv[e][d] * Finv[d][l];
-                    rec[C::Q_C + e * DIM + l] = v;
-                  }
-#pragma unroll
-              for (int k = 0; k < VO; ++k)
-                {
-                  rec[C::Q_TAU + k] = tau[k] * JxW;
-#pragma unroll
-                  for (int l = 0; l < VO; ++l)
-                    rec[C::Q_D + k * VO + l] = D[k][l] * JxW;
-                }
-#pragma unroll
-              for (int cc = 0; cc < DIM; ++cc)
-                rec[C::Q_A + cc] = prm.rho * sumN * acc[cc] * JxW; // :993-995 summed over j
-              rec[C::Q_W] = JxW;
-            }
-          __syncthreads();
-
-          double Kacc[AT][DIM][DIM], Sacc[AT];
-#pragma unroll
-          for (int ai = 0; ai < AT; ++ai)
-            {
-              Sacc[ai] = 0;
-#pragma unroll
-              for (int i = 0; i < DIM; ++i)
-#pragma unroll
-                for (int j = 0; j < DIM; ++j)
-                  Kacc[ai][i][j] = 0;
-            }
-          double r_i = 0; // residual entry of local dof tid (tid < DPC)
-
-          for (int qc = 0; qc < NQ; qc += QC)
-            {
-              // -------------- phase B: g_a, T_a = B_a^T (JxW D), t_a = JxW tau g_a -------------
-              for (int item = tid; item < QC * NPC; item += C::NT)
-                {
-                  const int     ql = item / NPC, a = item % NPC, q = qc + ql;
-                  const double *rec = sQ + q * QS;
-                  double        g[DIM];
-#pragma unroll
-                  for (int l = 0; l < DIM; ++l)
+                  for (int k = 0; k < VO; ++k)
                     {
-                      double v = 0;
+                      rec[C::Q_TAU + k] = tau[k] * JxW;
 #pragma unroll
-                      for (int e = 0; e < DIM; ++e)
-                        v += sdN[(q * NPC + a) * DIM + e] * rec[C::Q_C + e * DIM + l];
-                      g[l] = v;
-                      sG[(ql * DIM + l) * NPCP + a] = v;
+                      for (int l = 0; l < VO; ++l)
+                        rec[C::Q_D + k * VO + l] = D[k][l] * JxW;
                     }
-                  double *T = sT + (ql * NPC + a) * TS;
 #pragma unroll
-                  for (int ci = 0; ci < DIM; ++ci)
+                  for (int cc = 0; cc < DIM; ++cc)
+                    rec[C::Q_A + cc] = prm.rho * sumN * acc[cc] * JxW; // :993-995 summed over j
+                  rec[C::Q_W] = JxW;
+                }
+              named_bar_sync(1, NPT);
+
+              double r_i[C::RPT]; // residual entries ptid, ptid + NPT, ... of this cell
+#pragma unroll
+              for (int k = 0; k < C::RPT; ++k)
+                r_i[k] = 0;
+              for (int qc = 0; qc < NQ; qc += QC, ++it)
+                {
+                  const int buf = it & 1;
+                  double *  sT  = sm + C::OFF_T + buf * (QC * NPC * TS);
+                  double *  sG  = sm + C::OFF_G + buf * (QC * DIM * NPCP);
+                  if (it >= 2) // the consumers released this buffer (chunk it - 2)
+                    mbar_wait(smem_u32(&empty[buf]), ((it >> 1) - 1) & 1);
+                  // ---------- phase B: g_a, T_a = B_a^T (JxW D), t_a = JxW tau g_a -------------
+                  for (int item = ptid; item < QC * NPC; item += NPT)
                     {
-                      // engineering strain of dof (a,ci): eps_(ci,l) = g[l]
+                      const int     ql = item / NPC, a = item % NPC, q = qc + ql;
+                      const double *rec = sQ + q * QS;
+                      double        g[DIM];
 #pragma unroll
-                      for (int k = 0; k < VO; ++k)
+                      for (int l = 0; l < DIM; ++l)
                         {
                           double v = 0;
 #pragma unroll
-                          for (int l = 0; l < DIM; ++l)
-                            v += g[l] * rec[C::Q_D + voigt_index<DIM>(ci, l) * VO + k];
-                          T[ci * VO + k] = v;
+                          for (int e = 0; e < DIM; ++e)
+                            v += sdN[(q * NPC + a) * DIM + e] * rec[C::Q_C + e * DIM + l];
+                          g[l] = v;
+                          sG[(ql * DIM + l) * NPCP + a] = v;
                         }
-                      double t = 0;
+                      double *T = sT + (ql * NPC + a) * TS;
 #pragma unroll
-                      for (int l = 0; l < DIM; ++l)
-                        t += rec[C::Q_TAU + voigt_index<DIM>(ci, l)] * g[l];
-                      T[DIM * VO + ci] = t;
-                    }
-                }
-              __syncthreads();
-              // -------------- residual (:984-995), fixed q order --------------------------------
-              if (tid < DPC)
-                {
-                  const int a = tid / DIM, cc = tid % DIM;
-                  for (int ql = 0; ql < QC; ++ql)
-                    {
-                      const int     q   = qc + ql;
-                      const double *rec = sQ + q * QS;
-                      const double  Na  = sN[q * NPC + a];
-                      r_i -= (sT[(ql * NPC + a) * TS + DIM * VO + cc] -
-                              prm.body_force[cc] * prm.rho * Na * rec[C::Q_W]);
-                      r_i -= Na * rec[C::Q_A + cc];
-                    }
-                }
-              // -------------- phase C: K_ab += T_a B_b ; S_ab += t_a . g_b ----------------------
-              if (unit_active)
-                {
-#pragma unroll 2
-                  for (int ql = 0; ql < QC; ++ql)
-                    {
-                      double gb[DIM];
-#pragma unroll
-                      for (int l = 0; l < DIM; ++l)
-                        gb[l] = sG[(ql * DIM + l) * NPCP + bb];
-#pragma unroll
-                      for (int ai = 0; ai < AT; ++ai)
+                      for (int ci = 0; ci < DIM; ++ci)
                         {
-                          const int     a = min(a_base + ai, NPC - 1);
-                          const double *T = sT + (ql * NPC + a) * TS;
-                          double        Tl[TS];
+                          // engineering strain of dof (a,ci): eps_(ci,l) = g[l]
 #pragma unroll
-                          for (int k = 0; k < TS; k += 2)
+                          for (int k = 0; k < VO; ++k)
                             {
-                              const double2 v = *reinterpret_cast<const double2 *>(T + k);
-                              Tl[k]           = v.x;
-                              Tl[k + 1]       = v.y;
+                              double v = 0;
+#pragma unroll
+                              for (int l = 0; l < DIM; ++l)
+                                v += g[l] * rec[C::Q_D + voigt_index<DIM>(ci, l) * VO + k];
+                              T[ci * VO + k] = v;
                             }
+                          double t = 0;
+#pragma unroll
+                          for (int l = 0; l < DIM; ++l)
+                            t += rec[C::Q_TAU + voigt_index<DIM>(ci, l)] * g[l];
+                          T[DIM * VO + ci] = t;
+                        }
+                    }
+                  __syncwarp();
+                  if (lane == 0)
+                    mbar_arrive(smem_u32(&full[buf])); // release: this warp's part of the chunk
+                  named_bar_sync(1, NPT);              // all producer warps wrote the chunk
+                  // ---------- residual (:984-995), fixed q order ----------------------------------
+#pragma unroll
+                  for (int k = 0; k < C::RPT; ++k)
+                    {
+                      const int i = ptid + k * NPT;
+                      if (i < DPC)
+                        {
+                          const int a = i / DIM, cc = i % DIM;
+                          double    r = r_i[k];
+                          for (int ql = 0; ql < QC; ++ql)
+                            {
+                              const int     q   = qc + ql;
+                              const double *rec = sQ + q * QS;
+                              const double  Na  = sN[q * NPC + a];
+                              r -= (sT[(ql * NPC + a) * TS + DIM * VO + cc] -
+                                    prm.body_force[cc] * prm.rho * Na * rec[C::Q_W]);
+                              r -= Na * rec[C::Q_A + cc];
+                            }
+                          r_i[k] = r;
+                        }
+                    }
+                }
+#pragma unroll
+              for (int k = 0; k < C::RPT; ++k)
+                if (ptid + k * NPT < DPC)
+                  re_buf[cell * DPC + ptid + k * NPT] = r_i[k];
+            }
+        }
+      else
+        {
+          // =============================== consumer warps ======================================
+          // phase C: K_ab += T_a B_b (material, :1011) ; S_ab += t_a . g_b (geometric, :1018-1019)
+          // unit = (warp, sub-warp); each unit owns one group of AT nodes a; lane-in-sub = node b
+          const int  sub = lane / NPCP, b = lane % NPCP;
+          const int  unit = warp * C::NSUB + sub;
+          const bool unit_active = unit < C::NG;
+          const int  a_base = unit_active ? unit * AT : 0;
+          const int  bb = b < NPC ? b : NPC - 1; // clamped for loads; results of b >= NPC discarded
+          int        it = 0;
+          for (int64_t cell = c0 + blockIdx.x; cell < c1; cell += gridDim.x)
+            {
+              double Kacc[AT][DIM][DIM], Sacc[AT];
+#pragma unroll
+              for (int ai = 0; ai < AT; ++ai)
+                {
+                  Sacc[ai] = 0;
+#pragma unroll
+                  for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                    for (int j = 0; j < DIM; ++j)
+                      Kacc[ai][i][j] = 0;
+                }
+              for (int qc = 0; qc < NQ; qc += QC, ++it)
+                {
+                  const int     buf = it & 1;
+                  const double *sT  = sm + C::OFF_T + buf * (QC * NPC * TS);
+                  const double *sG  = sm + C::OFF_G + buf * (QC * DIM * NPCP);
+                  mbar_wait(smem_u32(&full[buf]), (it >> 1) & 1);
+                  if (unit_active)
+                    {
+#pragma unroll 2
+                      for (int ql = 0; ql < QC; ++ql)
+                        {
+                          double gb[DIM];
+#pragma unroll
+                          for (int l = 0; l < DIM; ++l)
+                            gb[l] = sG[(ql * DIM + l) * NPCP + bb];
+#pragma unroll
+                          for (int ai = 0; ai < AT; ++ai)
+                            {
+                              const int     a = min(a_base + ai, NPC - 1);
+                              const double *T = sT + (ql * NPC + a) * TS;
+                              double        Tl[TS];
+#pragma unroll
+                              for (int k = 0; k < TS; k += 2)
+                                {
+                                  const double2 v = *reinterpret_cast<const double2 *>(T + k);
+                                  Tl[k]           = v.x;
+                                  Tl[k + 1]       = v.y;
+                                }
+#pragma unroll
+                              for (int ci = 0; ci < DIM; ++ci)
+#pragma unroll
+                                for (int cj = 0; cj < DIM; ++cj)
+                                  {
+                                    double v = Kacc[ai][ci][cj];
+#pragma unroll
+                                    for (int l = 0; l < DIM; ++l)
+                                      v = fma(Tl[ci * VO + voigt_index<DIM>(cj, l)], gb[l], v);
+                                    Kacc[ai][ci][cj] = v;
+                                  }
+                              double sv = Sacc[ai];
+#pragma unroll
+                              for (int l = 0; l < DIM; ++l)
+                                sv = fma(Tl[DIM * VO + l], gb[l], sv);
+                              Sacc[ai] = sv;
+                            }
+                        }
+                    }
+                  __syncwarp();
+                  if (lane == 0)
+                    mbar_arrive(smem_u32(&empty[buf])); // this warp is done with the buffer
+                }
+              // ------------- write K_e (row-major); mass term :1020-1021 ------------------------
+              if (unit_active && b < NPC)
+                {
+                  const double detJ = geom[cell * (DIM * DIM + 1) + DIM * DIM];
+                  const double mfac = prm.rho * prm.alpha_1 * detJ;
+                  double *     ke   = ke_buf + (cell - c0) * int64_t(DPC) * DPC;
+#pragma unroll
+                  for (int ai = 0; ai < AT; ++ai)
+                    {
+                      const int a = a_base + ai;
+                      if (a < NPC)
+                        {
+                          const double dd = Sacc[ai] + mfac * Mref[a * NPC + b];
 #pragma unroll
                           for (int ci = 0; ci < DIM; ++ci)
 #pragma unroll
                             for (int cj = 0; cj < DIM; ++cj)
-                              {
-                                double v = Kacc[ai][ci][cj];
-#pragma unroll
-                                for (int l = 0; l < DIM; ++l)
-                                  v = fma(Tl[ci * VO + voigt_index<DIM>(cj, l)], gb[l], v);
-                                Kacc[ai][ci][cj] = v;
-                              }
-                          double sv = Sacc[ai];
-#pragma unroll
-                          for (int l = 0; l < DIM; ++l)
-                            sv = fma(Tl[DIM * VO + l], gb[l], sv);
-                          Sacc[ai] = sv;
+                              ke[(a * DIM + ci) * DPC + b * DIM + cj] =
+                                Kacc[ai][ci][cj] + (ci == cj ? dd : 0.0);
                         }
                     }
                 }
-              __syncthreads();
             }
-
-          // ---------------- write K_e (row-major) and r_e -----------------------------------------
-          double *ke = ke_buf + (cell - c0) * int64_t(DPC) * DPC;
-          if (unit_active && b < NPC)
-            {
-              const double mfac = prm.rho * prm.alpha_1 * detJ; // :1020-1021
-#pragma unroll
-              for (int ai = 0; ai < AT; ++ai)
-                {
-                  const int a = a_base + ai;
-                  if (a < NPC)
-                    {
-                      const double dd = Sacc[ai] + mfac * Mref[a * NPC + b];
-#pragma unroll
-                      for (int ci = 0; ci < DIM; ++ci)
-#pragma unroll
-                        for (int cj = 0; cj < DIM; ++cj)
-                          ke[(a * DIM + ci) * DPC + b * DIM + cj] =
-                            Kacc[ai][ci][cj] + (ci == cj ? dd : 0.0);
-                    }
-                }
-            }
-          if (tid < DPC)
-            re_buf[cell * DPC + tid] = r_i;
         }
     }
 

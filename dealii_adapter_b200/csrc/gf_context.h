@@ -270,6 +270,8 @@ struct gf_context
   gf::DevBuf<uint2>        tile_meta; // [n_tiles*SPMV_META]: per row {val offset, col offset | nb<<16}
   int64_t                  n_tiles = 0; // 0: a row does not fit a tile -> LDG kernel only
   int                      spmv_kernel_kind = 0; // 0 auto (TMA tiles when available), 1 LDG
+  int                      spmv_prefetch_tiles = 0; // L2 prefetch distance of the TMA kernel (tiles)
+  int                      spmv_gather_mode = 0;    // 0 lane per block, 1 lane per scalar
   gf::BsrMatrix        mat[gf::N_MATRICES];
   gf::DevBuf<double>   mass_blk; // linear: scalar mass value per block (M = m_ab delta_cd)
   gf::DevBuf<double>   dinv;     // [n_owned_nodes*dim*dim] preconditioner blocks
@@ -328,6 +330,8 @@ struct gf_context
   gf::DevBuf<double> mg_b, mg_x, mg_r, mg_d, mg_v, mg_e; // rhs, solution, residual, direction, A d, eigvec
   double             mg_lmax = 0.0;  // estimate of lambda_max(D^-1 A) of the current operator
   bool               mg_e_valid = false;
+  gf::DevBuf<double> mg_e_saved;     // checkpoint copy of mg_e (gf_state_save / gf_state_restore)
+  bool               mg_e_saved_valid = false;
   int                mg_smoother_degree = 3, mg_coarse_degree = 40;
   double             mg_smoother_ratio = 20.0, mg_coarse_ratio = 1000.0;
 

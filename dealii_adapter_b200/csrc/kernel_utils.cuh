@@ -62,6 +62,44 @@ namespace gf
       }
   }
 
+  // ---- shared-memory mbarriers (producer/consumer pipelines: spmv.cu, assemble_nl.cu) -----------
+  __device__ __forceinline__ uint32_t smem_u32(const void *p)
+  {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  }
+  __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  }
+  __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+  {
+    uint32_t done;
+    do
+      {
+        asm volatile("{\n .reg .pred p;\n"
+                     " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     " selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+      }
+    while (!done);
+  }
+  __device__ __forceinline__ void mbar_arrive(uint32_t bar)
+  {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+  }
+  __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+  {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+  }
+  // named barrier among a subset of the CTA's warps (all `count` threads call it)
+  __device__ __forceinline__ void named_bar_sync(int id, int count)
+  {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+  }
+
   __device__ __forceinline__ double warp_sum(double v)
   {
 #pragma unroll

@@ -127,37 +127,6 @@ namespace gf
       static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     };
 
-    __device__ __forceinline__ uint32_t smem_u32(const void *p)
-    {
-      return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-    }
-    __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-    {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-    }
-    __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-    {
-      uint32_t done;
-      do
-        {
-          asm volatile("{\n .reg .pred p;\n"
-                       " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-                       " selp.u32 %0, 1, 0, p;\n}\n"
-                       : "=r"(done)
-                       : "r"(bar), "r"(parity)
-                       : "memory");
-        }
-      while (!done);
-    }
-    __device__ __forceinline__ void mbar_arrive(uint32_t bar)
-    {
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-    }
-    __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
-    {
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-                   : "memory");
-    }
     // TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
     __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes,
                                              uint32_t bar)
@@ -168,12 +137,20 @@ namespace gf
                    : "memory");
     }
 
+    // ask the memory system to bring a future tile into L2 (no destination, no completion):
+    // DRAM latency is then hidden by L2 capacity instead of by the shared-memory ring depth
+    __device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
+    {
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+    }
+
     template <int DIM, bool DOT>
     __global__ void __launch_bounds__(TmaCfg<DIM>::THREADS, 1)
       spmv_tma_kernel(const int n_tiles, const TileDesc *__restrict__ tile_desc,
                       const uint2 *__restrict__ tile_meta, const int32_t *__restrict__ bcol,
                       const double *__restrict__ val, const double *__restrict__ x,
-                      double *__restrict__ y, double *__restrict__ partials, const int *status)
+                      double *__restrict__ y, double *__restrict__ partials, const int *status,
+                      const int prefetch_tiles, const int gather_mode)
     {
       using C = TmaCfg<DIM>;
       if (status != nullptr && *status != 0)
@@ -211,6 +188,19 @@ namespace gf
                   const int kk = k + lane;
                   if (kk < n_my)
                     d = tile_desc[int64_t(blockIdx.x) + int64_t(kk) * gridDim.x];
+                  // L2 prefetch, `prefetch_tiles` tiles ahead of the TMA loads: every lane
+                  // prefetches one of the next 32 tiles of this CTA
+                  if (prefetch_tiles > 0)
+                    {
+                      const int kp = k + prefetch_tiles + lane;
+                      if (kp < n_my)
+                        {
+                          const TileDesc dp =
+                            tile_desc[int64_t(blockIdx.x) + int64_t(kp) * gridDim.x];
+                          bulk_prefetch_l2(val + dp.val_off, uint32_t(dp.val_count) * 8u);
+                          bulk_prefetch_l2(bcol + dp.col_off, uint32_t(dp.col_count) * 4u);
+                        }
+                    }
                 }
               const int       src_lane  = k & 31;
               const long long val_off   = __shfl_sync(0xffffffffu, d.val_off, src_lane);
@@ -250,13 +240,29 @@ namespace gf
               double *sx =
                 reinterpret_cast<double *>(stage + C::VAL_BYTES + C::COL_BYTES + C::META_PAD);
               const int nblk = int(smeta[SPMV_TILE_ROWS + 1].x);
-#pragma unroll 4
-              for (int j = g; j < nblk; j += C::GATHER_WARPS * 32)
+              if (gather_mode == 1)
                 {
-                  const int64_t col = scol[j];
+                  // lane <-> scalar of the flattened [block][component] list: the dim values of a
+                  // node and the nodes of a run of consecutive column indices are adjacent in
+                  // memory, so one request touches few sectors
+#pragma unroll 4
+                  for (int j = g; j < nblk * DIM; j += C::GATHER_WARPS * 32)
+                    {
+                      const int     blk = j / DIM, d0 = j - blk * DIM;
+                      const int64_t col = scol[blk];
+                      sx[j]             = __ldg(x + col * DIM + d0);
+                    }
+                }
+              else
+                {
+#pragma unroll 4
+                  for (int j = g; j < nblk; j += C::GATHER_WARPS * 32)
+                    {
+                      const int64_t col = scol[j];
 #pragma unroll
-                  for (int d0 = 0; d0 < DIM; ++d0)
-                    sx[j * DIM + d0] = __ldg(x + col * DIM + d0);
+                      for (int d0 = 0; d0 < DIM; ++d0)
+                        sx[j * DIM + d0] = __ldg(x + col * DIM + d0);
+                    }
                 }
               __syncwarp();
               if (lane == 0)
@@ -361,7 +367,8 @@ namespace gf
         }
       const int grid = int(std::min<int64_t>(c.n_tiles, c.sm_count));
       spmv_tma_kernel<DIM, DOT><<<grid, C::THREADS, C::SMEM_BYTES, c.stream>>>(
-        int(c.n_tiles), c.tile_desc.p, c.tile_meta.p, c.bcol.p, val, x, y, dot_partials, st);
+        int(c.n_tiles), c.tile_desc.p, c.tile_meta.p, c.bcol.p, val, x, y, dot_partials, st,
+        c.spmv_prefetch_tiles, c.spmv_gather_mode);
     }
 
     // y = M x with M = m_ab delta_cd (consistent mass, one scalar per block)

@@ -16,15 +16,18 @@ fp = solvers.FakeParticipant(3, 10 ** 9, prob.params.delta_t, lambda t, it: buf,
 s = solvers.Solid(prob, fp, handle=h)
 s.adapter.n_interface_nodes = h.n_iface_nodes
 s.adapter.interface_nodes_ids = np.arange(h.n_iface_nodes, dtype=np.int32)
-for k in range(2):
+for k in range(8):
     s.step()
+h.state_save()                  # every configuration starts from the same state
 rows = []
-configs = [(3, 20, 40)] + [(d, r, c) for d in (2, 3, 4) for r in (10, 20, 40) for c in (10, 40)]
+configs = [(3, 20, 40), (2, 40, 40), (2, 80, 40), (2, 40, 80), (2, 80, 80), (1, 20, 40), (1, 40, 40),
+           (1, 80, 40), (1, 40, 80), (2, 30, 60), (3, 40, 40), (3, 20, 80), (2, 160, 40)]
 for deg, ratio, cdeg in configs:
     h.set_option(capi.OPT_MG_SMOOTHER_DEGREE, deg)
     h.set_option(capi.OPT_MG_SMOOTHER_RATIO, ratio)
     h.set_option(capi.OPT_MG_COARSE_DEGREE, cdeg)
-    s.step(); s.step()          # settle (one coupling window)
+    h.state_restore()
+    fp.window, fp.iteration = 4, 0
     h0, n0 = len(s.history), s.newton_solves
     h.synchronize(); t0 = time.perf_counter()
     s.step(); s.step()

@@ -1,4 +1,4 @@
-"""Multi-GPU parity check, launched with torchrun (one rank per GPU): the slab-partitioned NCCL path
+"""Multi-GPU parity check, launched with torchrun (one rank per GPU): the slab-partitioned path
 (halo exchange + all-reduced dots/norms) must reproduce the single-GPU run — same Newton counts,
 interface displacement to 1e-9 relative."""
 import os, sys
@@ -71,5 +71,7 @@ for model, type_lin, precond in (("neo-Hookean", "CG", "jacobi"), ("linear", "CG
               [[r[0] for r in x] for x in ss.history] if model == "neo-Hookean" else ss.history))
         (Hs or hs).close()
     (H or h).close()
+if rank == 0:
+    print("mgpu_check transport:", comm.transport())
 comm.close()
 dist.destroy_process_group()
