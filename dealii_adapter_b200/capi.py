@@ -22,8 +22,7 @@ VEC_SCRATCH0, VEC_SCRATCH1 = 28, 29
 MAT_TANGENT, MAT_STIFFNESS, MAT_MASS, MAT_SYSTEM = range(4)
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI, PRECOND_MULTIGRID = range(4)
 OPT_PRECONDITIONER, OPT_CG_CHECK_INTERVAL, OPT_PROFILE, OPT_OPERATOR, OPT_SPMV_KERNEL, \
-    OPT_MG_SMOOTHER_DEGREE, OPT_MG_COARSE_DEGREE, OPT_MG_SMOOTHER_RATIO, OPT_SPMV_PREFETCH, \
-    OPT_SPMV_GATHER = range(10)
+    OPT_MG_SMOOTHER_DEGREE, OPT_MG_COARSE_DEGREE, OPT_MG_SMOOTHER_RATIO = range(8)
 
 EXPORTED_SYMBOLS = [
     "gf_create", "gf_destroy", "gf_last_error", "gf_set_option", "gf_comm_unique_id",

@@ -440,16 +440,6 @@ extern "C"
             for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
               l->mg_coarse_degree = int(value);
             break;
-          case GF_OPT_SPMV_PREFETCH:
-            GF_REQUIRE(value >= 0 && value <= 64, GF_ERR_INVALID_ARG, "bad prefetch distance");
-            for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
-              l->spmv_prefetch_tiles = int(value);
-            break;
-          case GF_OPT_SPMV_GATHER:
-            GF_REQUIRE(value == 0 || value == 1, GF_ERR_INVALID_ARG, "unknown gather mode");
-            for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
-              l->spmv_gather_mode = int(value);
-            break;
           case GF_OPT_MG_SMOOTHER_RATIO:
             GF_REQUIRE(value >= 2 && value <= 1000, GF_ERR_INVALID_ARG, "bad smoother ratio");
             for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)

@@ -270,8 +270,6 @@ struct gf_context
   gf::DevBuf<uint2>        tile_meta; // [n_tiles*SPMV_META]: per row {val offset, col offset | nb<<16}
   int64_t                  n_tiles = 0; // 0: a row does not fit a tile -> LDG kernel only
   int                      spmv_kernel_kind = 0; // 0 auto (TMA tiles when available), 1 LDG
-  int                      spmv_prefetch_tiles = 0; // L2 prefetch distance of the TMA kernel (tiles)
-  int                      spmv_gather_mode = 0;    // 0 lane per block, 1 lane per scalar
   gf::BsrMatrix        mat[gf::N_MATRICES];
   gf::DevBuf<double>   mass_blk; // linear: scalar mass value per block (M = m_ab delta_cd)
   gf::DevBuf<double>   dinv;     // [n_owned_nodes*dim*dim] preconditioner blocks
@@ -332,8 +330,8 @@ struct gf_context
   bool               mg_e_valid = false;
   gf::DevBuf<double> mg_e_saved;     // checkpoint copy of mg_e (gf_state_save / gf_state_restore)
   bool               mg_e_saved_valid = false;
-  int                mg_smoother_degree = 3, mg_coarse_degree = 40;
-  double             mg_smoother_ratio = 20.0, mg_coarse_ratio = 1000.0;
+  int                mg_smoother_degree = 3, mg_coarse_degree = 80;
+  double             mg_smoother_ratio = 40.0, mg_coarse_ratio = 1000.0;
 
   gf::Profile  prof;
   gf::Profile *prof_sink = &prof; // coarser multigrid levels account into the finest level

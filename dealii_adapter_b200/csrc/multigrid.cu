@@ -9,8 +9,8 @@
 //              them with gf_mg_attach(fine, coarse, child_cells)
 //   operators  re-discretised on every level by the SAME assembly kernels (K1/K10 + scatter):
 //              nonlinear tangent at the injected state u_l (nested nodes), linear M + th^2 dt^2 K
-//   smoother   Chebyshev polynomial of block-Jacobi, degree 3 on [lmax/20, 1.2 lmax]; lmax by a
-//              warm-started power iteration after every assembly; coarsest level: degree 40 on
+//   smoother   Chebyshev polynomial of block-Jacobi, degree 3 on [lmax/40, 1.2 lmax]; lmax by a
+//              warm-started power iteration after every assembly; coarsest level: degree 80 on
 //              [lmax/1000, 1.2 lmax]. Polynomial smoothers are symmetric => the V-cycle is SPD
 //              and plain CG applies. Only SpMV (K4) + streaming vector kernels: HBM-bound.
 //   transfer   matrix-free FE embedding: prolongation evaluates the coarse shape functions at the

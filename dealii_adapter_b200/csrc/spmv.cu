@@ -137,20 +137,12 @@ namespace gf
                    : "memory");
     }
 
-    // ask the memory system to bring a future tile into L2 (no destination, no completion):
-    // DRAM latency is then hidden by L2 capacity instead of by the shared-memory ring depth
-    __device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
-    {
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-    }
-
     template <int DIM, bool DOT>
     __global__ void __launch_bounds__(TmaCfg<DIM>::THREADS, 1)
       spmv_tma_kernel(const int n_tiles, const TileDesc *__restrict__ tile_desc,
                       const uint2 *__restrict__ tile_meta, const int32_t *__restrict__ bcol,
                       const double *__restrict__ val, const double *__restrict__ x,
-                      double *__restrict__ y, double *__restrict__ partials, const int *status,
-                      const int prefetch_tiles, const int gather_mode)
+                      double *__restrict__ y, double *__restrict__ partials, const int *status)
     {
       using C = TmaCfg<DIM>;
       if (status != nullptr && *status != 0)
@@ -188,19 +180,6 @@ namespace gf
                   const int kk = k + lane;
                   if (kk < n_my)
                     d = tile_desc[int64_t(blockIdx.x) + int64_t(kk) * gridDim.x];
-                  // L2 prefetch, `prefetch_tiles` tiles ahead of the TMA loads: every lane
-                  // prefetches one of the next 32 tiles of this CTA
-                  if (prefetch_tiles > 0)
-                    {
-                      const int kp = k + prefetch_tiles + lane;
-                      if (kp < n_my)
-                        {
-                          const TileDesc dp =
-                            tile_desc[int64_t(blockIdx.x) + int64_t(kp) * gridDim.x];
-                          bulk_prefetch_l2(val + dp.val_off, uint32_t(dp.val_count) * 8u);
-                          bulk_prefetch_l2(bcol + dp.col_off, uint32_t(dp.col_count) * 4u);
-                        }
-                    }
                 }
               const int       src_lane  = k & 31;
               const long long val_off   = __shfl_sync(0xffffffffu, d.val_off, src_lane);
@@ -240,29 +219,13 @@ namespace gf
               double *sx =
                 reinterpret_cast<double *>(stage + C::VAL_BYTES + C::COL_BYTES + C::META_PAD);
               const int nblk = int(smeta[SPMV_TILE_ROWS + 1].x);
-              if (gather_mode == 1)
-                {
-                  // lane <-> scalar of the flattened [block][component] list: the dim values of a
-                  // node and the nodes of a run of consecutive column indices are adjacent in
-                  // memory, so one request touches few sectors
 #pragma unroll 4
-                  for (int j = g; j < nblk * DIM; j += C::GATHER_WARPS * 32)
-                    {
-                      const int     blk = j / DIM, d0 = j - blk * DIM;
-                      const int64_t col = scol[blk];
-                      sx[j]             = __ldg(x + col * DIM + d0);
-                    }
-                }
-              else
+              for (int j = g; j < nblk; j += C::GATHER_WARPS * 32)
                 {
-#pragma unroll 4
-                  for (int j = g; j < nblk; j += C::GATHER_WARPS * 32)
-                    {
-                      const int64_t col = scol[j];
+                  const int64_t col = scol[j];
 #pragma unroll
-                      for (int d0 = 0; d0 < DIM; ++d0)
-                        sx[j * DIM + d0] = __ldg(x + col * DIM + d0);
-                    }
+                  for (int d0 = 0; d0 < DIM; ++d0)
+                    sx[j * DIM + d0] = __ldg(x + col * DIM + d0);
                 }
               __syncwarp();
               if (lane == 0)
@@ -367,8 +330,7 @@ namespace gf
         }
       const int grid = int(std::min<int64_t>(c.n_tiles, c.sm_count));
       spmv_tma_kernel<DIM, DOT><<<grid, C::THREADS, C::SMEM_BYTES, c.stream>>>(
-        int(c.n_tiles), c.tile_desc.p, c.tile_meta.p, c.bcol.p, val, x, y, dot_partials, st,
-        c.spmv_prefetch_tiles, c.spmv_gather_mode);
+        int(c.n_tiles), c.tile_desc.p, c.tile_meta.p, c.bcol.p, val, x, y, dot_partials, st);
     }
 
     // y = M x with M = m_ab delta_cd (consistent mass, one scalar per block)

@@ -129,10 +129,8 @@ extern "C"
     GF_OPT_OPERATOR,           /* 0: assembled BSR SpMV ; 1: matrix-free tangent operator in CG */
     GF_OPT_SPMV_KERNEL,        /* 0: TMA-tiled kernel (default) ; 1: LDG warp-per-row kernel */
     GF_OPT_MG_SMOOTHER_DEGREE, /* Chebyshev degree of the pre-/post-smoother (default 3) */
-    GF_OPT_MG_COARSE_DEGREE,   /* Chebyshev degree of the coarsest-level solve (default 40) */
-    GF_OPT_MG_SMOOTHER_RATIO,  /* smoothers damp the eigenvalues in [lmax/ratio, lmax] (default 20) */
-    GF_OPT_SPMV_PREFETCH,      /* TMA SpMV: L2 prefetch distance in tiles (0 = off) */
-    GF_OPT_SPMV_GATHER         /* TMA SpMV x gather: 0 lane per block, 1 lane per scalar */
+    GF_OPT_MG_COARSE_DEGREE,   /* Chebyshev degree of the coarsest-level solve (default 80) */
+    GF_OPT_MG_SMOOTHER_RATIO   /* smoothers damp the eigenvalues in [lmax/ratio, lmax] (default 40) */
   };
 
   /* device-time breakdown accumulated while GF_OPT_PROFILE = 1 (CUDA events on the library's
