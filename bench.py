@@ -141,7 +141,25 @@ def cpu_run(n_steps, n_warmup):
             "seconds": t_total, "n_dofs": prob.n_dofs, "newton_solves": solves}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints (NCCL's
+    version banner, torchrun notices) was redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
@@ -177,7 +195,7 @@ def main():
                 "e2e": {"value": r["value"], "unit": "DoFs/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -361,7 +379,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_run(1, 0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        emit(line)
     if hierarchy:
         hierarchy.close()
     else:
