@@ -352,6 +352,7 @@ def main():
                        "cg_iterations_in_timed_region": cg_its_value,
                        "preconditioner": args.precond,
                        "multigrid_levels": [q.mesh.reps for q in hierarchy.problems] if hierarchy else None,
+                       "multigrid_levels_replicated": hierarchy.replicated if hierarchy else None,
                        "l2_policy": "inputs larger than L2 (matrix %.2f GB per GPU streamed every "
                                     "CG iteration)" % (spmv_bytes / 1e9),
                        "device_ms": dev_ms, "parallelism": "slab%d" % world},

@@ -40,16 +40,21 @@ namespace gf
       static constexpr int VO   = DIM * (DIM + 1) / 2;
       static constexpr int TS   = (DIM * VO + DIM + 1) & ~1; // T (DIM x VO) + t (DIM), even
       static constexpr int NPCP = NPC <= 4 ? 4 : (NPC <= 8 ? 8 : (NPC <= 16 ? 16 : 32));
-      static constexpr int NSUB = 32 / NPCP;
-      static constexpr int AT   = 3;                   // nodes a per (warp, sub) unit
+      static constexpr int AT   = 4;                   // nodes a per lane (register tile rows)
+      static constexpr int BT   = 2;                   // nodes b per lane (register tile columns)
       static constexpr int NG   = (NPC + AT - 1) / AT; // a-groups
-      static constexpr int NW   = (DIM == 3 && P == 2) ? 9 : 4; // consumer warps (phase C)
-      static constexpr int NPW  = (DIM == 3 && P == 2) ? 3 : 1; // producer warps (phases A, B)
+      static constexpr int NBG  = (NPC + BT - 1) / BT; // b-pairs
+      static constexpr int NBGP = NBG <= 2 ? 2 : (NBG <= 4 ? 4 : (NBG <= 8 ? 8 : 16));
+      static constexpr int NSUB = 32 / NBGP;           // a-groups per consumer warp
+      static constexpr int NW   = (NG + NSUB - 1) / NSUB; // consumer warps (phase C)
+      static constexpr int NPW  = (DIM == 3 && P == 2) ? 4 : 1; // producer warps (phases A, B)
       static constexpr int NT   = (NW + NPW) * 32;
       static constexpr int RPT  = (DPC + NPW * 32 - 1) / (NPW * 32); // residual entries/producer
       static constexpr int QC   = (DIM == 3 && P == 2) ? 8 : NQ; // q-points per chunk
+      static_assert(NBG <= 16 && BT * NBGP <= NPCP + BT, "b-pair mapping");
       static constexpr int QS   = DIM * DIM + VO * VO + VO + DIM + 2; // per-q scalars
       static_assert(NW * NSUB >= NG, "every a-group needs its own unit");
+      static_assert((TS % 2) == 0 && (NPCP % 2) == 0, "16-byte aligned rows");
       static_assert(NQ % QC == 0, "chunking");
 
       // shared memory (doubles)
@@ -84,7 +89,8 @@ namespace gf
     {
       using C = NLCfg<DIM, P>;
       constexpr int NPC = C::NPC, DPC = C::DPC, NQ = C::NQ, VO = C::VO, TS = C::TS, QC = C::QC,
-                    QS = C::QS, NPCP = C::NPCP, AT = C::AT, NCT = C::NW * 32, NPT = C::NPW * 32;
+                    QS = C::QS, NPCP = C::NPCP, AT = C::AT, BT = C::BT, NCT = C::NW * 32,
+                    NPT = C::NPW * 32;
       extern __shared__ __align__(16) double sm[];
       double *sN = sm + C::OFF_N, *sdN = sm + C::OFF_DN, *su = sm + C::OFF_U,
              *sacc = sm + C::OFF_ACC, *sQ = sm + C::OFF_Q;
@@ -300,26 +306,32 @@ namespace gf
         {
           // =============================== consumer warps ======================================
           // phase C: K_ab += T_a B_b (material, :1011) ; S_ab += t_a . g_b (geometric, :1018-1019)
-          // unit = (warp, sub-warp); each unit owns one group of AT nodes a; lane-in-sub = node b
-          const int  sub = lane / NPCP, b = lane % NPCP;
+          // Register tile: every lane owns AT nodes a x BT nodes b (4 x 2 x dim x dim accumulators).
+          // unit = (warp, sub-warp) <-> group of AT nodes a, lane-in-sub <-> pair of nodes b: the
+          // T_a rows are broadcast loads inside a sub-warp and serve AT*BT pairs per lane, the
+          // g_b pair is one 16-byte load - shared-memory traffic per FMA is half that of a
+          // 3 x 1 tile, which left the kernel bound by the LDS pipe (ncu: 76 % LSU, 39 % FP64)
+          const int  sub = lane / C::NBGP, bg = lane % C::NBGP;
           const int  unit = warp * C::NSUB + sub;
-          const bool unit_active = unit < C::NG;
-          const int  a_base = unit_active ? unit * AT : 0;
-          const int  bb = b < NPC ? b : NPC - 1; // clamped for loads; results of b >= NPC discarded
+          const bool unit_active = unit < C::NG && bg < C::NBG;
+          const int  a_base = unit < C::NG ? unit * AT : 0;
+          const int  bgc = bg < C::NBG ? bg : C::NBG - 1; // clamped for loads
           int        it = 0;
           for (int64_t cell = c0 + blockIdx.x; cell < c1; cell += gridDim.x)
             {
-              double Kacc[AT][DIM][DIM], Sacc[AT];
+              double Kacc[AT][BT][DIM][DIM], Sacc[AT][BT];
 #pragma unroll
               for (int ai = 0; ai < AT; ++ai)
-                {
-                  Sacc[ai] = 0;
 #pragma unroll
-                  for (int i = 0; i < DIM; ++i)
+                for (int bi = 0; bi < BT; ++bi)
+                  {
+                    Sacc[ai][bi] = 0;
 #pragma unroll
-                    for (int j = 0; j < DIM; ++j)
-                      Kacc[ai][i][j] = 0;
-                }
+                    for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                      for (int j = 0; j < DIM; ++j)
+                        Kacc[ai][bi][i][j] = 0;
+                  }
               for (int qc = 0; qc < NQ; qc += QC, ++it)
                 {
                   const int     buf = it & 1;
@@ -328,42 +340,70 @@ namespace gf
                   mbar_wait(smem_u32(&full[buf]), (it >> 1) & 1);
                   if (unit_active)
                     {
-#pragma unroll 2
+#pragma unroll 1
                       for (int ql = 0; ql < QC; ++ql)
                         {
-                          double gb[DIM];
+                          double gb[BT][DIM];
 #pragma unroll
                           for (int l = 0; l < DIM; ++l)
-                            gb[l] = sG[(ql * DIM + l) * NPCP + bb];
+                            {
+                              static_assert(BT == 2, "g_b pairs are fetched as one double2");
+                              const double2 v = *reinterpret_cast<const double2 *>(
+                                sG + (ql * DIM + l) * NPCP + BT * bgc);
+                              gb[0][l] = v.x;
+                              gb[1][l] = v.y;
+                            }
 #pragma unroll
                           for (int ai = 0; ai < AT; ++ai)
                             {
                               const int     a = min(a_base + ai, NPC - 1);
                               const double *T = sT + (ql * NPC + a) * TS;
-                              double        Tl[TS];
-#pragma unroll
-                              for (int k = 0; k < TS; k += 2)
-                                {
-                                  const double2 v = *reinterpret_cast<const double2 *>(T + k);
-                                  Tl[k]           = v.x;
-                                  Tl[k + 1]       = v.y;
-                                }
 #pragma unroll
                               for (int ci = 0; ci < DIM; ++ci)
+                                {
+                                  double Tr[VO]; // row ci of T_a
+                                  if constexpr ((VO % 2) == 0)
+                                    {
 #pragma unroll
-                                for (int cj = 0; cj < DIM; ++cj)
-                                  {
-                                    double v = Kacc[ai][ci][cj];
+                                      for (int k = 0; k < VO; k += 2)
+                                        {
+                                          const double2 v =
+                                            *reinterpret_cast<const double2 *>(T + ci * VO + k);
+                                          Tr[k]     = v.x;
+                                          Tr[k + 1] = v.y;
+                                        }
+                                    }
+                                  else
+                                    {
 #pragma unroll
-                                    for (int l = 0; l < DIM; ++l)
-                                      v = fma(Tl[ci * VO + voigt_index<DIM>(cj, l)], gb[l], v);
-                                    Kacc[ai][ci][cj] = v;
-                                  }
-                              double sv = Sacc[ai];
+                                      for (int k = 0; k < VO; ++k)
+                                        Tr[k] = T[ci * VO + k];
+                                    }
+#pragma unroll
+                                  for (int bi = 0; bi < BT; ++bi)
+#pragma unroll
+                                    for (int cj = 0; cj < DIM; ++cj)
+                                      {
+                                        double v = Kacc[ai][bi][ci][cj];
+#pragma unroll
+                                        for (int l = 0; l < DIM; ++l)
+                                          v = fma(Tr[voigt_index<DIM>(cj, l)], gb[bi][l], v);
+                                        Kacc[ai][bi][ci][cj] = v;
+                                      }
+                                }
+                              double tl[DIM];
 #pragma unroll
                               for (int l = 0; l < DIM; ++l)
-                                sv = fma(Tl[DIM * VO + l], gb[l], sv);
-                              Sacc[ai] = sv;
+                                tl[l] = T[DIM * VO + l];
+#pragma unroll
+                              for (int bi = 0; bi < BT; ++bi)
+                                {
+                                  double sv = Sacc[ai][bi];
+#pragma unroll
+                                  for (int l = 0; l < DIM; ++l)
+                                    sv = fma(tl[l], gb[bi][l], sv);
+                                  Sacc[ai][bi] = sv;
+                                }
                             }
                         }
                     }
@@ -372,7 +412,7 @@ namespace gf
                     mbar_arrive(smem_u32(&empty[buf])); // this warp is done with the buffer
                 }
               // ------------- write K_e (row-major); mass term :1020-1021 ------------------------
-              if (unit_active && b < NPC)
+              if (unit_active)
                 {
                   const double detJ = geom[cell * (DIM * DIM + 1) + DIM * DIM];
                   const double mfac = prm.rho * prm.alpha_1 * detJ;
@@ -383,13 +423,21 @@ namespace gf
                       const int a = a_base + ai;
                       if (a < NPC)
                         {
-                          const double dd = Sacc[ai] + mfac * Mref[a * NPC + b];
 #pragma unroll
-                          for (int ci = 0; ci < DIM; ++ci)
+                          for (int bi = 0; bi < BT; ++bi)
+                            {
+                              const int b = BT * bg + bi;
+                              if (b < NPC)
+                                {
+                                  const double dd = Sacc[ai][bi] + mfac * Mref[a * NPC + b];
 #pragma unroll
-                            for (int cj = 0; cj < DIM; ++cj)
-                              ke[(a * DIM + ci) * DPC + b * DIM + cj] =
-                                Kacc[ai][ci][cj] + (ci == cj ? dd : 0.0);
+                                  for (int ci = 0; ci < DIM; ++ci)
+#pragma unroll
+                                    for (int cj = 0; cj < DIM; ++cj)
+                                      ke[(a * DIM + ci) * DPC + b * DIM + cj] =
+                                        Kacc[ai][bi][ci][cj] + (ci == cj ? dd : 0.0);
+                                }
+                            }
                         }
                     }
                 }

@@ -482,6 +482,20 @@ namespace gf
                "ncclAllReduce");
   }
 
+  // sum of a long vector over all ranks (multigrid: restriction onto a replicated coarse level).
+  // ncclAllReduce delivers the same bits to every rank, which the redundant coarse solves rely on.
+  void allreduce_sum_vector(gf_context &c, double *dev_values, int64_t count)
+  {
+    if (!c.comm || count <= 0)
+      return;
+    ProfScope ps(c, Profile::HALO, 1);
+    comm_use_stream(c);
+    ++c.comm->n_allreduce;
+    nccl_check(nccl().AllReduce(dev_values, dev_values, size_t(count), NCCL_FLOAT64, NCCL_SUM,
+                                c.comm->nccl_comm, c.stream),
+               "ncclAllReduce");
+  }
+
   namespace
   {
     // map every rank's window into this process (cudaIpc over NVLink peer access); collective

@@ -399,6 +399,7 @@ namespace gf
   void halo_reduce_add(gf_context &c, double *v); // ghost partial sums -> owners (+=)
   void halo_exchange(gf_context &c, double *v);
   void allreduce_sum(gf_context &c, double *dev_values, int count);
+  void allreduce_sum_vector(gf_context &c, double *dev_values, int64_t count); // long vectors
   void comm_setup_context(gf_context &c);  // after setup_halo: agree on the transport (collective)
   void comm_check(gf_context &c);          // throws if a peer-window wait timed out
   void comm_forget_stream(gf_comm cm, cudaStream_t s); // before a stream is destroyed

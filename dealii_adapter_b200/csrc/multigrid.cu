@@ -16,8 +16,12 @@
 //   transfer   matrix-free FE embedding: prolongation evaluates the coarse shape functions at the
 //              child-cell nodes; restriction is its transpose in gather form (fixed summation
 //              order, no FP atomics => reproducible).
-//   multi-GPU  every level has its own slab partition and halo lists; restriction sums over owned
-//              fine nodes and sends the ghost partial sums to the owner (halo_reduce_add).
+//   multi-GPU  partitioned levels have their own slab partition and halo lists; restriction sums
+//              over owned fine nodes and sends the ghost partial sums to the owner
+//              (halo_reduce_add). Small levels are REPLICATED: every rank holds the whole coarse
+//              mesh, restriction and state injection end in one all-reduce over the coarse vector
+//              and everything below (smoothing, the 80-step coarsest solve, re-discretisation)
+//              runs redundantly with no communication at all.
 #include <cmath>
 
 #include "gf_context.h"
@@ -65,11 +69,16 @@ namespace gf
                                   const int32_t *__restrict__ child_cells,
                                   const int32_t *__restrict__ inj,
                                   const int32_t *__restrict__ cell_nodes_f,
+                                  const int64_t n_owned_nodes_f, const bool owned_only,
                                   const double *__restrict__ u_f, double *__restrict__ u_c)
     {
       const int64_t B = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
       if (B >= n_coarse_nodes)
         return;
+      if (owned_only) // replicated coarse level: exactly one rank contributes, the others add 0
+#pragma unroll
+        for (int cc = 0; cc < DIM; ++cc)
+          u_c[B * DIM + cc] = 0.0;
       for (int64_t s = nc_ptr_c[B]; s < nc_ptr_c[B + 1]; ++s)
         {
           const int32_t src = nc_src_c[s];
@@ -79,6 +88,8 @@ namespace gf
           if (fc < 0)
             continue;
           const int64_t nf = cell_nodes_f[int64_t(fc) * npc + ka % npc];
+          if (owned_only && nf >= n_owned_nodes_f)
+            return; // the same fine node in every adjacent cell: its owner injects it
 #pragma unroll
           for (int cc = 0; cc < DIM; ++cc)
             u_c[B * DIM + cc] = u_f[nf * DIM + cc];
@@ -354,9 +365,11 @@ namespace gf
       gf_context &co = *f.mg.coarse;
       {
         ProfScope ps(f, Profile::MG_VEC);
-        // multi-GPU: partial sums for all local coarse nodes (ghosts go to their owner below)
-        const int64_t n    = co.comm ? co.n_nodes : co.n_owned_nodes;
-        const bool    mask = !co.comm;
+        // multi-GPU: partial sums for all local coarse nodes (ghosts go to their owner below;
+        // replicated coarse level: all its nodes, summed over the ranks below)
+        const bool    replicated = f.comm != nullptr && co.comm == nullptr;
+        const int64_t n    = (co.comm || replicated) ? co.n_nodes : co.n_owned_nodes;
+        const bool    mask = !co.comm && !replicated;
         const unsigned grid = blocks_for(n * 32);
         if (f.dim == 3)
           restrict_kernel<3><<<grid, NT, 0, f.stream>>>(
@@ -373,6 +386,11 @@ namespace gf
       if (co.comm)
         {
           halo_reduce_add(co, b_c);
+          vec_zero_constrained(co, b_c);
+        }
+      else if (f.comm)
+        {
+          allreduce_sum_vector(f, b_c, co.n_local);
           vec_zero_constrained(co, b_c);
         }
     }
@@ -401,18 +419,21 @@ namespace gf
       {
         ProfScope ps(f, Profile::MG_VEC);
         const int64_t n = co.n_nodes;
+        const bool    replicated = f.comm != nullptr && co.comm == nullptr;
         if (f.dim == 3)
           inject_kernel<3><<<blocks_for(n), NT, 0, f.stream>>>(
             n, f.npc, f.mg.n_child, co.nc_ptr.p, co.nc_src.p, f.mg.child_cells.p, f.mg.inj.p,
-            f.cell_nodes.p, u_f, u_c);
+            f.cell_nodes.p, f.n_owned_nodes, replicated, u_f, u_c);
         else
           inject_kernel<2><<<blocks_for(n), NT, 0, f.stream>>>(
             n, f.npc, f.mg.n_child, co.nc_ptr.p, co.nc_src.p, f.mg.child_cells.p, f.mg.inj.p,
-            f.cell_nodes.p, u_f, u_c);
+            f.cell_nodes.p, f.n_owned_nodes, replicated, u_f, u_c);
         GF_CUDA_CHECK(cudaGetLastError());
       }
       if (co.comm)
         halo_exchange(co, u_c);
+      else if (f.comm)
+        allreduce_sum_vector(f, u_c, co.n_local);
     }
 
     // lambda_max(D^-1 A) by power iteration, warm-started from the previous operator's vector
@@ -481,8 +502,11 @@ namespace gf
     GF_REQUIRE(f.dim == co.dim && f.p == co.p && f.model == co.model && f.device == co.device,
                GF_ERR_INVALID_ARG,
                "multigrid levels must share dim, degree, model and device");
-    GF_REQUIRE((f.comm == nullptr) == (co.comm == nullptr), GF_ERR_INVALID_ARG,
-               "multigrid levels must all be partitioned or all be serial");
+    // a partitioned level may sit on top of a REPLICATED (serial, whole-mesh on every rank) coarse
+    // level: restriction / injection all-reduce over the whole coarse vector, everything below runs
+    // redundantly without communication
+    GF_REQUIRE(f.comm != nullptr || co.comm == nullptr, GF_ERR_INVALID_ARG,
+               "a serial multigrid level cannot have a partitioned coarse level");
     GF_REQUIRE(child_cells != nullptr, GF_ERR_INVALID_ARG, "null child_cells");
     GF_REQUIRE(f.mg.coarse == nullptr, GF_ERR_INVALID_ARG, "level already has a coarse level");
     const int dim = f.dim, p = f.p, npc = f.npc, n_child = 1 << dim;

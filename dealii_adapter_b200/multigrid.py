@@ -38,31 +38,45 @@ def child_table(coarse_mesh, fine_mesh):
 
 
 class Hierarchy:
-    """Handles of all levels (levels[0] = finest), linked with gf_mg_attach. For a partitioned run
-    every level is slab-partitioned with the same (axis, world, rank); the slab boundaries of all
-    levels must coincide (repetitions along the axis divisible by world * 2^(levels-1))."""
+    """Handles of all levels (levels[0] = finest), linked with gf_mg_attach.
+
+    Partitioned run (world > 1): the fine levels are slab-partitioned with the same (axis, world,
+    rank) — their slab boundaries must coincide, i.e. the layers per rank stay even — and the
+    remaining small levels are REPLICATED: every rank holds the whole coarse mesh as a serial
+    handle, so the coarse smoothing / coarsest solve need no halo exchange (the library
+    all-reduces the restricted residual). A level is replicated when it has at most
+    `replicate_below_dofs` DoFs or when its slabs could not be aligned any more."""
 
     def __init__(self, problem, device=0, n_levels=None, world=1, rank=0, comm=None, axis=1,
-                 min_cells=1):
+                 min_cells=1, replicate_below_dofs=300000):
         self.problems = [problem]
+        self.replicated = [False]
         while n_levels is None or len(self.problems) < n_levels:
             nxt = coarsen_problem(self.problems[-1])
-            if nxt is None or nxt.mesh.n_cells < min_cells or \
-                    (world > 1 and nxt.mesh.reps[axis] < world):
+            if nxt is None or nxt.mesh.n_cells < min_cells:
                 break
+            if world > 1:
+                aligned = (not self.replicated[-1]) and \
+                    self.problems[-1].mesh.reps[axis] % (2 * world) == 0
+                self.replicated.append(self.replicated[-1] or not aligned
+                                       or nxt.n_dofs <= replicate_below_dofs)
+            else:
+                self.replicated.append(False)
             self.problems.append(nxt)
-        self.partitions = [p.mesh.partition(axis, world, rank) if world > 1 else None
-                           for p in self.problems]
-        self.handles = [capi.Handle(p, device=device, partition=part, comm=comm)
+        self.partitions = [p.mesh.partition(axis, world, rank) if (world > 1 and not rep) else None
+                           for p, rep in zip(self.problems, self.replicated)]
+        self.handles = [capi.Handle(p, device=device, partition=part,
+                                    comm=comm if part is not None else None)
                         for p, part in zip(self.problems, self.partitions)]
         for l in range(len(self.handles) - 1):
             fine, coarse = self.problems[l], self.problems[l + 1]
             tab = child_table(coarse.mesh, fine.mesh)
-            if world > 1:
+            pf, pc = self.partitions[l], self.partitions[l + 1]
+            if pf is not None:
                 g2l = -np.ones(fine.mesh.n_cells, dtype=np.int64)
-                pf, pc = self.partitions[l], self.partitions[l + 1]
                 g2l[pf.local_cell_global] = np.arange(pf.n_local_cells)
-                tab = g2l[tab[pc.local_cell_global]]
+                # replicated coarse level: all coarse cells, children that are not local -> -1
+                tab = g2l[tab[pc.local_cell_global]] if pc is not None else g2l[tab]
                 covered = np.zeros(pf.n_local_cells, dtype=bool)
                 covered[tab[tab >= 0]] = True
                 if not covered.all():

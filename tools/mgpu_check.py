@@ -17,8 +17,12 @@ if rank == 0:
     idt.copy_(torch.frombuffer(bytearray(capi.Comm.unique_id()), dtype=torch.uint8))
 dist.broadcast(idt, 0)
 comm = capi.Comm(bytes(idt.cpu().numpy().tobytes()), rank, world, lr)
+# "mg": all coarse levels slab-partitioned (halo exchanges on every level);
+# "mg-replicated": the small levels replicated on every rank (the default of multigrid.Hierarchy)
 for model, type_lin, precond in (("neo-Hookean", "CG", "jacobi"), ("linear", "CG", "jacobi"),
-                                 ("neo-Hookean", "CG", "mg"), ("linear", "CG", "mg")):
+                                 ("neo-Hookean", "CG", "mg"), ("linear", "CG", "mg"),
+                                 ("neo-Hookean", "CG", "mg-replicated"),
+                                 ("linear", "CG", "mg-replicated")):
     p = SolverParameters(model=model, type_lin=type_lin, poly_degree=2, scenario="PF", delta_t=0.01,
                          mu=0.5e6, nu=0.4, rho=1000.0, tol_lin=1e-8, max_iterations_lin=2.0)
     reps = [3, 4 * world, 2] if precond == "jacobi" else [4, 8 * world, 4]
@@ -26,8 +30,9 @@ for model, type_lin, precond in (("neo-Hookean", "CG", "jacobi"), ("linear", "CG
     n = prob.n_iface_nodes
     load = np.array([1500.0, 0.0, 100.0])
     H = None
-    if precond == "mg":
-        H = multigrid.Hierarchy(prob, device=lr, world=world, rank=rank, comm=comm, axis=1)
+    if precond.startswith("mg"):
+        H = multigrid.Hierarchy(prob, device=lr, world=world, rank=rank, comm=comm, axis=1,
+                                replicate_below_dofs=0 if precond == "mg" else 300000)
         h = H.fine
     else:
         part = prob.mesh.partition(1, world, rank)
@@ -48,7 +53,7 @@ for model, type_lin, precond in (("neo-Hookean", "CG", "jacobi"), ("linear", "CG
     allv = [None] * world
     dist.all_gather_object(allv, mine)
     if rank == 0:
-        Hs = multigrid.Hierarchy(prob, device=lr) if precond == "mg" else None
+        Hs = multigrid.Hierarchy(prob, device=lr) if precond.startswith("mg") else None
         hs = Hs.fine if Hs else capi.Handle(prob, device=lr)
         bufs = np.tile(load, n)
         fps = solvers.FakeParticipant(3, 3, p.delta_t, lambda t, it: bufs)
@@ -65,8 +70,8 @@ for model, type_lin, precond in (("neo-Hookean", "CG", "jacobi"), ("linear", "CG
             assert err < (1e-9 if precond == "jacobi" else 1e-7), (model, precond, r, err)
         if model == "neo-Hookean":
             assert [len(x) for x in s.history] == [len(x) for x in ss.history], (s.history, ss.history)
-        print("mgpu_check %s %s world=%d levels=%d OK (history %s | single-GPU %s)" % (
-              model, precond, world, H.n_levels if H else 1,
+        print("mgpu_check %s %s world=%d levels=%d replicated=%s OK (history %s | single-GPU %s)" % (
+              model, precond, world, H.n_levels if H else 1, H.replicated if H else None,
               [[r[0] for r in x] for x in s.history] if model == "neo-Hookean" else s.history,
               [[r[0] for r in x] for x in ss.history] if model == "neo-Hookean" else ss.history))
         (Hs or hs).close()
