@@ -16,7 +16,7 @@ namespace gf
   namespace
   {
     template <int DIM>
-    __global__ void scatter_matrix_kernel(const int64_t n_rows, const int npc,
+    __global__ void __launch_bounds__(256, 3) scatter_matrix_kernel(const int64_t n_rows, const int npc,
                                           const int32_t *__restrict__ brow_ptr,
                                           const int64_t *__restrict__ val_ptr,
                                           const int64_t *__restrict__ cand_ptr,
@@ -44,6 +44,10 @@ namespace gf
 #pragma unroll
       for (int r = 0; r < DIM; ++r)
         row_con[r] = apply_constraints && constrained[A * DIM + r] != 0;
+      bool row_any = false;
+#pragma unroll
+      for (int r = 0; r < DIM; ++r)
+        row_any |= row_con[r];
       if (first && lane == 0 && stride > nb * DIM) // padding double of every scalar row
 #pragma unroll
         for (int r = 0; r < DIM; ++r)
@@ -66,41 +70,66 @@ namespace gf
 #pragma unroll
             for (int cc = 0; cc < DIM; ++cc)
               sum[r][cc] = first ? 0.0 : val[vbase + r * stride + blk * DIM + cc];
-          for (int s = s0; s < s1; ++s)
+          bool col_any = false;
+#pragma unroll
+          for (int cc = 0; cc < DIM; ++cc)
+            col_any |= col_con[cc];
+          if (!row_any && !col_any)
             {
-              const int32_t src  = row_src[cbase + s];
-              const int64_t cell = src / npc2;
-              if (cell < c0 || cell >= c1)
-                continue;
-              const int     ab = src - int32_t(cell) * npc2;
-              const int     a = ab / npc, b = ab - a * npc;
-              const double *ke = ke_buf + (cell - c0) * int64_t(dpc) * dpc;
-              const double *kb = ke + (a * DIM) * dpc + b * DIM;
+              // fast path (all but the clamped nodes): plain ordered sums of the source blocks
+              for (int s = s0; s < s1; ++s)
+                {
+                  const int32_t src  = row_src[cbase + s];
+                  const int64_t cell = src / npc2;
+                  if (cell < c0 || cell >= c1)
+                    continue;
+                  const int     ab = src - int32_t(cell) * npc2;
+                  const int     a = ab / npc, b = ab - a * npc;
+                  const double *kb =
+                    ke_buf + (cell - c0) * int64_t(dpc) * dpc + (a * DIM) * dpc + b * DIM;
 #pragma unroll
-              for (int r = 0; r < DIM; ++r)
+                  for (int r = 0; r < DIM; ++r)
 #pragma unroll
-                for (int cc = 0; cc < DIM; ++cc)
-                  {
-                    // constrained rows/columns are dropped; a constrained diagonal collects
-                    // |K_e(i,i)|
-                    const bool use_abs = (B == A) && (r == cc) && row_con[r];
-                    const bool drop    = (row_con[r] || col_con[cc]) && !use_abs;
-                    if (drop)
-                      continue;
-                    double v = kb[r * dpc + cc];
-                    if (use_abs)
-                      {
-                        v = fabs(v);
-                        if (v == 0.0) // deal.II: fall back to the cell's average |diagonal|
-                          {
-                            for (int i = 0; i < dpc; ++i)
-                              v += fabs(ke[i * dpc + i]);
-                            v /= double(dpc);
-                          }
-                      }
-                    sum[r][cc] += v;
-                  }
+                    for (int cc = 0; cc < DIM; ++cc)
+                      sum[r][cc] += __ldg(kb + r * dpc + cc);
+                }
             }
+          else
+            for (int s = s0; s < s1; ++s)
+              {
+                const int32_t src  = row_src[cbase + s];
+                const int64_t cell = src / npc2;
+                if (cell < c0 || cell >= c1)
+                  continue;
+                const int     ab = src - int32_t(cell) * npc2;
+                const int     a = ab / npc, b = ab - a * npc;
+                const double *ke = ke_buf + (cell - c0) * int64_t(dpc) * dpc;
+                const double *kb = ke + (a * DIM) * dpc + b * DIM;
+#pragma unroll
+                for (int r = 0; r < DIM; ++r)
+#pragma unroll
+                  for (int cc = 0; cc < DIM; ++cc)
+                    {
+                      // constrained rows/columns are dropped; a constrained diagonal collects
+                      // |K_e(i,i)|
+                      const bool use_abs = (B == A) && (r == cc) && row_con[r];
+                      const bool drop    = (row_con[r] || col_con[cc]) && !use_abs;
+                      if (drop)
+                        continue;
+                      double v = kb[r * dpc + cc];
+                      if (use_abs)
+                        {
+                          v = fabs(v);
+                          if (v == 0.0) // deal.II: fall back to the cell's average |diagonal|
+                            {
+                              for (int i = 0; i < dpc; ++i)
+                                v += fabs(ke[i * dpc + i]);
+                              v /= double(dpc);
+                            }
+                        }
+                      sum[r][cc] += v;
+                    }
+              }
 #pragma unroll
           for (int r = 0; r < DIM; ++r)
 #pragma unroll
