@@ -37,6 +37,25 @@ def child_table(coarse_mesh, fine_mesh):
     return out
 
 
+def plan_levels(problem, n_levels=None, world=1, axis=1, min_cells=1, replicate_below_dofs=300000):
+    """Levels of the hierarchy below `problem` and, for a partitioned run, which of them are
+    replicated on every rank instead of slab-partitioned: ([problems], [replicated flags]).
+    A level can stay partitioned only while the slabs of consecutive levels coincide (the finer
+    level's layers per rank are even); once a level is replicated, all coarser ones are."""
+    problems, replicated = [problem], [False]
+    while n_levels is None or len(problems) < n_levels:
+        nxt = coarsen_problem(problems[-1])
+        if nxt is None or nxt.mesh.n_cells < min_cells:
+            break
+        if world > 1:
+            aligned = (not replicated[-1]) and problems[-1].mesh.reps[axis] % (2 * world) == 0
+            replicated.append(replicated[-1] or not aligned or nxt.n_dofs <= replicate_below_dofs)
+        else:
+            replicated.append(False)
+        problems.append(nxt)
+    return problems, replicated
+
+
 class Hierarchy:
     """Handles of all levels (levels[0] = finest), linked with gf_mg_attach.
 
@@ -49,20 +68,8 @@ class Hierarchy:
 
     def __init__(self, problem, device=0, n_levels=None, world=1, rank=0, comm=None, axis=1,
                  min_cells=1, replicate_below_dofs=300000):
-        self.problems = [problem]
-        self.replicated = [False]
-        while n_levels is None or len(self.problems) < n_levels:
-            nxt = coarsen_problem(self.problems[-1])
-            if nxt is None or nxt.mesh.n_cells < min_cells:
-                break
-            if world > 1:
-                aligned = (not self.replicated[-1]) and \
-                    self.problems[-1].mesh.reps[axis] % (2 * world) == 0
-                self.replicated.append(self.replicated[-1] or not aligned
-                                       or nxt.n_dofs <= replicate_below_dofs)
-            else:
-                self.replicated.append(False)
-            self.problems.append(nxt)
+        self.problems, self.replicated = plan_levels(problem, n_levels, world, axis, min_cells,
+                                                     replicate_below_dofs)
         self.partitions = [p.mesh.partition(axis, world, rank) if (world > 1 and not rep) else None
                            for p, rep in zip(self.problems, self.replicated)]
         self.handles = [capi.Handle(p, device=device, partition=part,

@@ -59,3 +59,31 @@ def test_partitioned_child_tables_cover_the_local_fine_cells(native_libs):
         # the coarse ghost layer spans two fine layers, only the first is local on the fine level
         if rank == 0:
             assert (local < 0).any()
+
+
+def test_level_plan_for_partitioned_runs_replicates_the_small_levels(native_libs):
+    """world > 1: levels stay slab-partitioned while the slabs of consecutive levels coincide and the
+    level is large; the small levels are replicated on every rank (no coarse halo exchanges)."""
+    from dealii_adapter_b200 import multigrid as mg
+    p = nl_params(poly_degree=2, scenario="PF")
+    prob = make_problem(p, 3, reps=[8, 32, 8])
+    # serial: nothing is replicated, coarsening stops at the first odd repetition
+    probs, rep = mg.plan_levels(prob)
+    assert [q.mesh.reps for q in probs] == [[8, 32, 8], [4, 16, 4], [2, 8, 2], [1, 4, 1]]
+    assert rep == [False] * 4
+    # 2 ranks, everything below 20k dofs replicated
+    probs, rep = mg.plan_levels(prob, world=2, axis=1, replicate_below_dofs=20000)
+    assert [q.n_dofs for q in probs][1] == 9 * 33 * 9 * 3 and rep == [False, True, True, True]
+    # 4 ranks, no size threshold: 32 -> 16 -> 8 -> 4 layers = 8, 4, 2, 1 per rank: all aligned
+    probs, rep = mg.plan_levels(prob, world=4, axis=1, replicate_below_dofs=0)
+    assert rep == [False, False, False, False]
+    # 8 ranks: 4 -> 2 -> 1 layers per rank are aligned, half a layer per rank is not
+    probs, rep = mg.plan_levels(prob, world=8, axis=1, replicate_below_dofs=0)
+    assert rep == [False, False, False, True]
+    # 3 ranks: 32 layers cannot be cut into aligned slabs at all -> every coarse level replicated
+    probs, rep = mg.plan_levels(prob, world=3, axis=1, replicate_below_dofs=0)
+    assert rep == [False, True, True, True]
+    # once replicated, always replicated
+    for w in (2, 3, 4, 8):
+        _, rep = mg.plan_levels(prob, world=w, axis=1)
+        assert rep == sorted(rep)
