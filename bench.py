@@ -6,12 +6,14 @@
                                                             reference's CPU path on a bounded sample)
 
 Workload (config.workload): BASELINE.json configs[2] — nonlinear_elasticity, perpendicular flap 3D,
-Q2 hexahedra 24x144x24 cells = 2,081,667 DoFs per GPU, neo-Hookean + Newmark, implicit coupling with
+Q2 hexahedra 24x144x24 cells = 2,081,667 DoFs, neo-Hookean + Newmark, implicit coupling with
 checkpoint/restore (k=2 sub-iterations per window, FakeParticipant supplies a constant interface
 traction), CG rel. tol 1e-6 ("Residual") preconditioned by the geometric multigrid V-cycle over the
-4-level refinement hierarchy (3x18x3 -> 24x144x24 cells; `--precond jacobi` selects the plain
-block-Jacobi CG instead). It is the configuration the north_star target is quoted on and it fits one GPU. N>1: weak scaling, the flap is N times longer (24 x 144N x 24),
-slab-partitioned along y, ghost-DoF halo + dot-product all-reduce over NCCL.
+refinement hierarchy (3x18x3 -> 24x144x24 cells; `--precond jacobi` selects the plain block-Jacobi
+CG instead). It is the configuration the north_star target is quoted on and it fits one GPU.
+N>1: weak scaling — the same flap refined to ~2.05 M DoFs per GPU (WEAK_REPS; N=8: 48x288x48 cells,
+16.3 M DoFs), slab-partitioned along y; ghost-DoF halo and dot-product all-reduce by the library's
+own kernels over NVLink peer windows (NCCL as fallback); small multigrid levels replicated.
 
 A "step" is one pass through the coupling loop body (save/restore checkpoint, read traction, Newton
 loop of assemble + CG solve, Newmark updates, write displacement).
@@ -36,6 +38,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CELLS_PER_GPU = (24, 144, 24)
+# weak scaling: the SAME flap (0.1 x 1 x 0.3) refined so that every GPU keeps ~2.05 M DoFs; at
+# N = 8 this is one uniform refinement of the N = 1 mesh (16.3 M DoFs, BASELINE configs[4] size
+# class) and the multigrid hierarchy simply gains a level: the coarsest grid stays 3 x 18 x 3
+WEAK_REPS = {1: (24, 144, 24), 2: (24, 144, 48), 4: (48, 144, 48), 8: (48, 288, 48)}
 CPU_SAMPLE_LAYERS = 2          # oracle sample: 24 x 2 x 24 cells of the same size (33,075 DoFs)
 TRACTION = (2000.0, 0.0, 0.0)
 N_SUB = 2
@@ -56,6 +62,13 @@ def make_flap(n_layers_y, numbering="lexicographic"):
     box = ([-0.05, 0.0, 0.0], [0.05, n_layers_y / 144.0, 0.3])
     return make_problem(p, 3, reps=[CELLS_PER_GPU[0], n_layers_y, CELLS_PER_GPU[2]],
                         numbering=numbering, box=box)
+
+
+def make_flap_reps(reps, numbering="lexicographic"):
+    """The perpendicular flap 0.1 x 1 x 0.3 (nonlinear_elasticity.cc:215-219) with `reps` cells."""
+    from dealii_adapter_b200.problem import make_problem
+    return make_problem(params(), 3, reps=list(reps), numbering=numbering,
+                        box=([-0.05, 0.0, 0.0], [0.05, 1.0, 0.3]))
 
 
 class ClockSampler:
@@ -167,6 +180,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=CELLS_PER_GPU[1],
                     help="cell layers per GPU along the flap (debug; default = the named workload)")
+    ap.add_argument("--reps", default=None,
+                    help="a,b,c: cells of the whole flap 0.1 x 1 x 0.3 (debug: run a multi-GPU "
+                         "weak-scaling mesh on fewer GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true",
                     help="skip the matrix-free-operator variant measured after the main regions")
@@ -176,9 +192,17 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = ("cfg3 nonlinear_elasticity PF 3D Q2 neo-Hookean, %dx%dx%d cells per GPU, implicit "
-                "coupling k=%d with checkpoint/restore, CG rel tol 1e-6 + %s"
-                % (CELLS_PER_GPU[0], args.layers, CELLS_PER_GPU[2], N_SUB,
+    if args.reps:
+        reps = tuple(int(x) for x in args.reps.split(","))
+    elif args.layers != CELLS_PER_GPU[1] or world not in WEAK_REPS:
+        reps = None      # flap of the cfg3 cell size, world * layers cell layers long
+    else:
+        reps = WEAK_REPS[world]
+    workload = ("cfg3 nonlinear_elasticity PF 3D Q2 neo-Hookean, %s cells on %d GPU(s) "
+                "(2,081,667 DoFs at N=1; weak scaling: the same flap refined, ~2.05M DoFs per GPU), "
+                "implicit coupling k=%d with checkpoint/restore, CG rel tol 1e-6 + %s"
+                % ("x".join(map(str, reps)) if reps else "24x%dx24" % (args.layers * world), world,
+                   N_SUB,
                    "geometric multigrid V-cycle (Chebyshev/block-Jacobi smoothers)"
                    if args.precond == "mg" else "block-Jacobi"))
 
@@ -213,7 +237,7 @@ def main():
         dist.broadcast(idt, 0)
         comm = capi.Comm(bytes(idt.cpu().numpy().tobytes()), rank, world, local_rank)
 
-    prob = make_flap(args.layers * world)
+    prob = make_flap_reps(reps) if reps else make_flap(args.layers * world)
     hierarchy = None
     if args.precond == "mg":
         hierarchy = multigrid.Hierarchy(prob, device=local_rank, world=world, rank=rank, comm=comm,

@@ -40,7 +40,7 @@ namespace gf
       static constexpr int VO   = DIM * (DIM + 1) / 2;
       static constexpr int TS   = (DIM * VO + DIM + 1) & ~1; // T (DIM x VO) + t (DIM), even
       static constexpr int NPCP = NPC <= 4 ? 4 : (NPC <= 8 ? 8 : (NPC <= 16 ? 16 : 32));
-      static constexpr int AT   = 4;                   // nodes a per lane (register tile rows)
+      static constexpr int AT   = 2;                   // nodes a per lane (register tile rows)
       static constexpr int BT   = 2;                   // nodes b per lane (register tile columns)
       static constexpr int NG   = (NPC + AT - 1) / AT; // a-groups
       static constexpr int NBG  = (NPC + BT - 1) / BT; // b-pairs
@@ -306,7 +306,9 @@ namespace gf
         {
           // =============================== consumer warps ======================================
           // phase C: K_ab += T_a B_b (material, :1011) ; S_ab += t_a . g_b (geometric, :1018-1019)
-          // Register tile: every lane owns AT nodes a x BT nodes b (4 x 2 x dim x dim accumulators).
+          // Register tile: every lane owns AT nodes a x BT nodes b (2 x 2 x dim x dim accumulators;
+          // the shared-memory traffic per FMA depends on BT only, and the small AT leaves room for two
+          // consumer warps per scheduler, which hides the dependent-DFMA latency).
           // unit = (warp, sub-warp) <-> group of AT nodes a, lane-in-sub <-> pair of nodes b: the
           // T_a rows are broadcast loads inside a sub-warp and serve AT*BT pairs per lane, the
           // g_b pair is one 16-byte load - shared-memory traffic per FMA is half that of a

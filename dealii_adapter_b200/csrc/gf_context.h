@@ -333,6 +333,13 @@ struct gf_context
   int                mg_smoother_degree = 3, mg_coarse_degree = 80;
   double             mg_smoother_ratio = 40.0, mg_coarse_ratio = 1000.0;
 
+  // single-launch coarsest-level solver (coarse_solve.cu)
+  bool   cs_planned = false, cs_enabled = false, cs_stage = false;
+  int    cs_rows_per_cta = 0, cs_grid = 0;
+  size_t cs_smem = 0;
+  gf::DevBuf<unsigned long long> cs_counter;
+  unsigned long long             cs_arrivals = 0;
+
   gf::Profile  prof;
   gf::Profile *prof_sink = &prof; // coarser multigrid levels account into the finest level
 };
@@ -395,6 +402,9 @@ namespace gf
   void mg_update_operators(gf_context &c, const double *u_total); // after the finest assembly
   void mg_vcycle(gf_context &c, const double *b, double *x);      // x = MG(b)
   bool mg_active(const gf_context &c);
+  // coarse_solve.cu
+  bool coarse_solve_single_launch(gf_context &c, const double *val, const double *b, double *x,
+                                  int degree, double ratio);
   // comm.cu
   void halo_reduce_add(gf_context &c, double *v); // ghost partial sums -> owners (+=)
   void halo_exchange(gf_context &c, double *v);

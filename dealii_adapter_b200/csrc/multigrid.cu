@@ -641,7 +641,11 @@ namespace gf
   {
     if (!c.mg.coarse)
       {
-        smooth(c, b, x, true, c.mg_coarse_degree, c.mg_coarse_ratio);
+        // coarsest level: one persistent cooperative kernel when it applies (small, not
+        // partitioned), else the same Chebyshev iteration launch by launch
+        if (!coarse_solve_single_launch(c, level_matrix(c), b, x, c.mg_coarse_degree,
+                                        c.mg_coarse_ratio))
+          smooth(c, b, x, true, c.mg_coarse_degree, c.mg_coarse_ratio);
         return;
       }
     gf_context &co = *c.mg.coarse;

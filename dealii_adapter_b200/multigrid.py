@@ -37,7 +37,7 @@ def child_table(coarse_mesh, fine_mesh):
     return out
 
 
-def plan_levels(problem, n_levels=None, world=1, axis=1, min_cells=1, replicate_below_dofs=300000):
+def plan_levels(problem, n_levels=None, world=1, axis=1, min_cells=1, replicate_below_dofs=80000):
     """Levels of the hierarchy below `problem` and, for a partitioned run, which of them are
     replicated on every rank instead of slab-partitioned: ([problems], [replicated flags]).
     A level can stay partitioned only while the slabs of consecutive levels coincide (the finer
@@ -67,7 +67,7 @@ class Hierarchy:
     `replicate_below_dofs` DoFs or when its slabs could not be aligned any more."""
 
     def __init__(self, problem, device=0, n_levels=None, world=1, rank=0, comm=None, axis=1,
-                 min_cells=1, replicate_below_dofs=300000):
+                 min_cells=1, replicate_below_dofs=80000):
         self.problems, self.replicated = plan_levels(problem, n_levels, world, axis, min_cells,
                                                      replicate_below_dofs)
         self.partitions = [p.mesh.partition(axis, world, rank) if (world > 1 and not rep) else None

@@ -32,7 +32,7 @@ for model, type_lin, precond in (("neo-Hookean", "CG", "jacobi"), ("linear", "CG
     H = None
     if precond.startswith("mg"):
         H = multigrid.Hierarchy(prob, device=lr, world=world, rank=rank, comm=comm, axis=1,
-                                replicate_below_dofs=0 if precond == "mg" else 300000)
+                                replicate_below_dofs=0 if precond == "mg" else 80000)
         h = H.fine
     else:
         part = prob.mesh.partition(1, world, rank)
