@@ -41,7 +41,7 @@ CELLS_PER_GPU = (24, 144, 24)
 # weak scaling: the SAME flap (0.1 x 1 x 0.3) refined so that every GPU keeps ~2.05 M DoFs; at
 # N = 8 this is one uniform refinement of the N = 1 mesh (16.3 M DoFs, BASELINE configs[4] size
 # class) and the multigrid hierarchy simply gains a level: the coarsest grid stays 3 x 18 x 3
-WEAK_REPS = {1: (24, 144, 24), 2: (24, 144, 48), 4: (48, 144, 48), 8: (48, 288, 48)}
+WEAK_REPS = {1: (24, 144, 24), 2: (24, 144, 48), 4: (24, 288, 48), 8: (48, 288, 48)}
 CPU_SAMPLE_LAYERS = 2          # oracle sample: 24 x 2 x 24 cells of the same size (33,075 DoFs)
 TRACTION = (2000.0, 0.0, 0.0)
 N_SUB = 2

@@ -156,8 +156,18 @@ namespace
         c.mass_blk.alloc_zero(c.n_blocks, s);
       }
     // element buffers; K_e is chunked so that huge meshes never materialise all element matrices
-    const char * env       = getenv("GF_KE_BUDGET_MB");
-    const double budget_mb = env ? atof(env) : 8192.0;
+    // default budget: 8 GB, or up to 35 % of the memory still free on a large mesh (every extra
+    // chunk makes the scatter re-walk the whole value array)
+    const char *env       = getenv("GF_KE_BUDGET_MB");
+    double      budget_mb = 8192.0;
+    if (env)
+      budget_mb = atof(env);
+    else
+      {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+          budget_mb = std::max(budget_mb, 0.35 * double(free_b) / 1048576.0);
+      }
     const double per_cell  = double(c.dpc) * c.dpc * 8.0;
     c.ke_chunk_cells =
       std::max<int64_t>(1, std::min<int64_t>(c.n_cells, int64_t(budget_mb * 1048576.0 / per_cell)));
