@@ -11,8 +11,8 @@ checkpoint/restore (k=2 sub-iterations per window, FakeParticipant supplies a co
 traction), CG rel. tol 1e-6 ("Residual") preconditioned by the geometric multigrid V-cycle over the
 refinement hierarchy (3x18x3 -> 24x144x24 cells; `--precond jacobi` selects the plain block-Jacobi
 CG instead). It is the configuration the north_star target is quoted on and it fits one GPU.
-N>1: weak scaling — the same flap refined to ~2.05 M DoFs per GPU (WEAK_REPS; N=8: 48x288x48 cells,
-16.3 M DoFs), slab-partitioned along y; ghost-DoF halo and dot-product all-reduce by the library's
+N>1: weak scaling — the same flap refined to ~2.05 M DoFs per GPU (WEAK_REPS; N=8: 24x288x96 cells,
+16.4 M DoFs), slab-partitioned along y; ghost-DoF halo and dot-product all-reduce by the library's
 own kernels over NVLink peer windows (NCCL as fallback); small multigrid levels replicated.
 
 A "step" is one pass through the coupling loop body (save/restore checkpoint, read traction, Newton
@@ -38,10 +38,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CELLS_PER_GPU = (24, 144, 24)
-# weak scaling: the SAME flap (0.1 x 1 x 0.3) refined so that every GPU keeps ~2.05 M DoFs; at
-# N = 8 this is one uniform refinement of the N = 1 mesh (16.3 M DoFs, BASELINE configs[4] size
-# class) and the multigrid hierarchy simply gains a level: the coarsest grid stays 3 x 18 x 3
-WEAK_REPS = {1: (24, 144, 24), 2: (24, 144, 48), 4: (24, 288, 48), 8: (48, 288, 48)}
+# weak scaling: the SAME flap (0.1 x 1 x 0.3) refined so that every GPU keeps ~2.05 M DoFs. Rule:
+# each doubling of N halves the LONGEST cell edge (N=1 cells 4.2 x 6.9 x 12.5 mm -> z; 4.2 x 6.9 x
+# 6.25 -> y; 4.2 x 3.5 x 6.25 -> z; N=8: 4.2 x 3.5 x 3.1 mm, 16.4 M DoFs = BASELINE configs[4] size
+# class). CG iteration counts per Newton solve on these meshes (measured on one GPU, profiles/
+# r01_bench_n1_weak_mesh_*.json): 16.5, 13.5, 11.5, 10.8 - the meshes get more isotropic.
+WEAK_REPS = {1: (24, 144, 24), 2: (24, 144, 48), 4: (24, 288, 48), 8: (24, 288, 96)}
 CPU_SAMPLE_LAYERS = 2          # oracle sample: 24 x 2 x 24 cells of the same size (33,075 DoFs)
 TRACTION = (2000.0, 0.0, 0.0)
 N_SUB = 2
