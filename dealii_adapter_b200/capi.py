@@ -19,10 +19,11 @@ NL_TOTAL_DISPLACEMENT, NL_TOTAL_DISPLACEMENT_OLD, NL_VELOCITY, NL_VELOCITY_OLD, 
 LIN_OLD_VELOCITY, LIN_VELOCITY, LIN_OLD_DISPLACEMENT, LIN_DISPLACEMENT, LIN_OLD_STRESS, LIN_STRESS, \
     LIN_SYSTEM_RHS, LIN_BODY_FORCE = range(16, 24)
 VEC_SCRATCH0, VEC_SCRATCH1 = 28, 29
-MAT_TANGENT, MAT_STIFFNESS, MAT_MASS, MAT_SYSTEM = range(4)
+MAT_TANGENT, MAT_STIFFNESS, MAT_MASS, MAT_SYSTEM, MAT_MG_F32 = range(5)
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI, PRECOND_MULTIGRID = range(4)
 OPT_PRECONDITIONER, OPT_CG_CHECK_INTERVAL, OPT_PROFILE, OPT_OPERATOR, OPT_SPMV_KERNEL, \
-    OPT_MG_SMOOTHER_DEGREE, OPT_MG_COARSE_DEGREE, OPT_MG_SMOOTHER_RATIO = range(8)
+    OPT_MG_SMOOTHER_DEGREE, OPT_MG_COARSE_DEGREE, OPT_MG_SMOOTHER_RATIO, \
+    OPT_MG_MATRIX_PRECISION = range(9)
 
 EXPORTED_SYMBOLS = [
     "gf_create", "gf_destroy", "gf_last_error", "gf_set_option", "gf_comm_unique_id",
@@ -31,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "gf_nl_newton_solve", "gf_nl_end_step", "gf_lin_assemble_once", "gf_lin_step", "gf_get_vector",
     "gf_set_vector", "gf_nnz", "gf_export_csr", "gf_spmv", "gf_spmv_timed", "gf_profile_get",
     "gf_synchronize", "gf_event_record", "gf_event_elapsed_ms", "gf_mg_attach", "gf_mg_vcycle",
-    "gf_comm_transport", "gf_comm_timed",
+    "gf_comm_transport", "gf_comm_timed", "gf_postprocess",
 ]
 
 
@@ -119,6 +120,7 @@ def lib():
         L.gf_event_elapsed_ms.argtypes = [vp, i32, i32, C.POINTER(dbl)]
         L.gf_mg_attach.argtypes = [vp, vp, vp]
         L.gf_mg_vcycle.argtypes = [vp, i32, i32]
+        L.gf_postprocess.argtypes = [vp, i32, vp]
         _lib = L
     return _lib
 
@@ -206,6 +208,7 @@ class Handle:
                       np.ascontiguousarray(iface_face_no, dtype=np.int32),
                       np.ascontiguousarray(iface_dofs, dtype=np.int32)]
         d.n_dofs, d.n_cells = n_dofs, n_cells
+        self.n_cells = n_cells
         d.cell_dofs, d.cell_vertices, d.constrained = (a.ctypes.data for a in keep_alive[:3])
         d.n_iface_faces = len(keep_alive[3])
         d.iface_cell, d.iface_face_no = keep_alive[3].ctypes.data, keep_alive[4].ctypes.data
@@ -326,6 +329,15 @@ class Handle:
         self._check(lib().gf_export_csr(self._h, which, rowptr.ctypes.data, col.ctypes.data,
                                         val.ctypes.data))
         return rowptr, col, val
+
+    def postprocess(self, which_vector):
+        """Output-step fields of DataOut + Postprocessor (postprocessor.h:44-76):
+        [n_cells, (p+1)^dim patch points, dim + dim*dim] = displacement, then strain (d*dim+e)."""
+        dim = self.problem.dim
+        npts = (self.problem.params.poly_degree + 1) ** dim
+        out = np.zeros((self.n_cells, npts, dim + dim * dim))
+        self._check(lib().gf_postprocess(self._h, which_vector, out.ctypes.data))
+        return out
 
     def spmv(self, which_matrix, which_x, which_y):
         self._check(lib().gf_spmv(self._h, which_matrix, which_x, which_y))

@@ -455,6 +455,21 @@ extern "C"
             for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
               l->mg_smoother_ratio = double(value);
             break;
+          case GF_OPT_MG_MATRIX_PRECISION:
+            GF_REQUIRE(value == 0 || value == 1, GF_ERR_INVALID_ARG,
+                       "matrix precision of the V-cycle: 0 (FP64) or 1 (FP32 copy)");
+            for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
+              {
+                l->mg_matrix_precision = int(value);
+                if (value == 0)
+                  {
+                    l->mg_val32_valid = false;
+                    l->mg_val32.release();
+                  }
+              }
+            if (value == 1)
+              gf::mg_refresh_f32(c); // operators that are already assembled; else at assembly
+            break;
           default:
             throw gf::Error{GF_ERR_INVALID_ARG, "unknown option"};
         }
@@ -854,6 +869,39 @@ extern "C"
   }
 
   // ------------------------------------------------------------------------------------------
+  int gf_postprocess(gf_handle h, int which_vector, double *fields)
+  {
+    return guarded(h, [&](gf_context &c) {
+      GF_REQUIRE(fields != nullptr, GF_ERR_INVALID_ARG, "null buffer");
+      double *u = vec_ptr(c, which_vector);
+      if (c.comm)
+        gf::halo_exchange(c, u);
+      const int64_t per_cell = int64_t(c.npc) * (c.dim + c.dim * c.dim);
+      // staging buffer of at most 256 MB: output volumes of large meshes go out in chunks
+      const int64_t chunk =
+        std::max<int64_t>(1, std::min<int64_t>(c.n_cells, (int64_t(32) << 20) / per_cell));
+      gf::DevBuf<double> stage;
+      stage.alloc(size_t(chunk * per_cell));
+      GF_CUDA_CHECK(cudaMemsetAsync(c.err_flag.p, 0, sizeof(int), c.stream));
+      for (int64_t c0 = 0; c0 < c.n_cells; c0 += chunk)
+        {
+          const int64_t c1 = std::min(c.n_cells, c0 + chunk);
+          gf::launch_postprocess(c, u, c0, c1, stage.p);
+          GF_CUDA_CHECK(cudaMemcpyAsync(fields + c0 * per_cell, stage.p,
+                                        size_t((c1 - c0) * per_cell) * sizeof(double),
+                                        cudaMemcpyDeviceToHost, c.stream));
+          GF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        }
+      GF_CUDA_CHECK(
+        cudaMemcpyAsync(c.h_err, c.err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+      GF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      GF_REQUIRE(*c.h_err == 0, GF_ERR_DET_F,
+                 "output: the displaced (MappingQEulerian) cell is inverted at a patch point");
+      return GF_OK;
+    });
+  }
+
+  // ------------------------------------------------------------------------------------------
   int gf_spmv(gf_handle h, int which_matrix, int which_x, int which_y)
   {
     return guarded(h, [&](gf_context &c) {
@@ -865,6 +913,12 @@ extern "C"
         {
           GF_REQUIRE(c.mass_blk.p != nullptr, GF_ERR_INVALID_ARG, "no mass matrix for this model");
           gf::launch_spmv_mass(c, x, y);
+        }
+      else if (which_matrix == GF_MAT_MG_F32)
+        {
+          GF_REQUIRE(c.mg_val32_valid, GF_ERR_INVALID_ARG,
+                     "no FP32 operator copy (GF_OPT_MG_MATRIX_PRECISION = 1, then assemble)");
+          gf::launch_spmv_f32(c, c.mg_val32.p, x, y);
         }
       else if (which_matrix == GF_MAT_TANGENT)
         gf::op_apply(c, mat_ptr(c, which_matrix), x, y, nullptr); // assembled or matrix-free
@@ -880,7 +934,10 @@ extern "C"
   {
     return guarded(h, [&](gf_context &c) {
       GF_REQUIRE(n_reps >= 1, GF_ERR_INVALID_ARG, "n_reps must be >= 1");
-      double *A = mat_ptr(c, which_matrix);
+      const bool f32 = which_matrix == GF_MAT_MG_F32;
+      GF_REQUIRE(!f32 || c.mg_val32_valid, GF_ERR_INVALID_ARG,
+                 "no FP32 operator copy (GF_OPT_MG_MATRIX_PRECISION = 1, then assemble)");
+      double *A = f32 ? nullptr : mat_ptr(c, which_matrix);
       double *x = vec_ptr(c, GF_VEC_SCRATCH0), *y = vec_ptr(c, GF_VEC_SCRATCH1);
       cudaEvent_t e0, e1;
       GF_CUDA_CHECK(cudaEventCreate(&e0));
@@ -888,11 +945,19 @@ extern "C"
       const bool prof = c.prof.enabled;
       c.prof.enabled  = false;
       const bool tangent = which_matrix == GF_MAT_TANGENT;
+      auto       apply   = [&]() {
+        if (f32)
+          gf::launch_spmv_f32(c, c.mg_val32.p, x, y);
+        else if (tangent)
+          gf::op_apply(c, A, x, y, nullptr);
+        else
+          gf::launch_spmv(c, A, x, y, nullptr);
+      };
       for (int k = 0; k < 3; ++k)
-        tangent ? gf::op_apply(c, A, x, y, nullptr) : gf::launch_spmv(c, A, x, y, nullptr);
+        apply();
       GF_CUDA_CHECK(cudaEventRecord(e0, c.stream));
       for (int k = 0; k < n_reps; ++k)
-        tangent ? gf::op_apply(c, A, x, y, nullptr) : gf::launch_spmv(c, A, x, y, nullptr);
+        apply();
       GF_CUDA_CHECK(cudaEventRecord(e1, c.stream));
       GF_CUDA_CHECK(cudaEventSynchronize(e1));
       c.prof.enabled = prof;
@@ -903,7 +968,9 @@ extern "C"
       if (ms_per_launch)
         *ms_per_launch = double(ms) / n_reps;
       if (bytes_per_launch)
-        *bytes_per_launch = (tangent && c.operator_kind == 1) ? gf::mf_bytes(c) : gf::spmv_bytes(c);
+        *bytes_per_launch = f32 ? gf::spmv_bytes_f32(c) :
+                                  ((tangent && c.operator_kind == 1) ? gf::mf_bytes(c) :
+                                                                       gf::spmv_bytes(c));
       return GF_OK;
     });
   }

@@ -330,6 +330,10 @@ struct gf_context
   bool               mg_e_valid = false;
   gf::DevBuf<double> mg_e_saved;     // checkpoint copy of mg_e (gf_state_save / gf_state_restore)
   bool               mg_e_saved_valid = false;
+  // FP32 copy of this level's operator for the V-cycle (GF_OPT_MG_MATRIX_PRECISION = 1)
+  int                mg_matrix_precision = 0; // 0: FP64 values, 1: FP32 copy inside the V-cycle
+  gf::DevBuf<float>  mg_val32;                // [n_val + 4]
+  bool               mg_val32_valid = false;
   int                mg_smoother_degree = 3, mg_coarse_degree = 80;
   double             mg_smoother_ratio = 40.0, mg_coarse_ratio = 1000.0;
 
@@ -339,6 +343,9 @@ struct gf_context
   size_t cs_smem = 0;
   gf::DevBuf<unsigned long long> cs_counter;
   unsigned long long             cs_arrivals = 0;
+
+  // output-path post-processing (postprocess.cu): shape tables at the patch points
+  gf::DevBuf<double> pp_N, pp_dN;
 
   gf::Profile  prof;
   gf::Profile *prof_sink = &prof; // coarser multigrid levels account into the finest level
@@ -368,8 +375,11 @@ namespace gf
   // spmv.cu
   void launch_spmv(gf_context &c, const double *val, const double *x, double *y,
                    double *dot_partials);
+  void launch_spmv_f32(gf_context &c, const float *val32, const double *x, double *y);
+  void launch_convert_f32(gf_context &c, const double *val, float *val32);
   void launch_spmv_mass(gf_context &c, const double *x, double *y);
   double spmv_bytes(const gf_context &c);
+  double spmv_bytes_f32(const gf_context &c);
   int    spmv_dot_partials(const gf_context &c);
   // cg.cu
   int cg_solve(gf_context &c, const double *val, double *x, const double *b, double tol,
@@ -401,10 +411,14 @@ namespace gf
   void mg_attach(gf_context &fine, gf_context &coarse, const int32_t *child_cells);
   void mg_update_operators(gf_context &c, const double *u_total); // after the finest assembly
   void mg_vcycle(gf_context &c, const double *b, double *x);      // x = MG(b)
+  void mg_refresh_f32(gf_context &c); // FP32 operator copies of all levels below and incl. c
   bool mg_active(const gf_context &c);
   // coarse_solve.cu
   bool coarse_solve_single_launch(gf_context &c, const double *val, const double *b, double *x,
                                   int degree, double ratio);
+  // postprocess.cu
+  void launch_postprocess(gf_context &c, const double *u, int64_t c0, int64_t c1,
+                          double *fields_dev);
   // comm.cu
   void halo_reduce_add(gf_context &c, double *v); // ghost partial sums -> owners (+=)
   void halo_exchange(gf_context &c, double *v);

@@ -315,11 +315,20 @@ namespace gf
                                                c.mat[GF_MAT_SYSTEM].val.p;
     }
 
+    // does this level apply its operator from the assembled matrix (not matrix-free)?
+    bool level_is_assembled(const gf_context &c)
+    {
+      return !(c.operator_kind == 1 && c.mg_level == 0 && c.model == GF_MODEL_NEO_HOOKEAN);
+    }
+
     void apply_operator(gf_context &c, double *x, double *y)
     {
       if (c.comm)
         halo_exchange(c, x);
-      op_apply(c, level_matrix(c), x, y, nullptr);
+      if (c.mg_matrix_precision == 1 && c.mg_val32_valid && level_is_assembled(c))
+        launch_spmv_f32(c, c.mg_val32.p, x, y);
+      else
+        op_apply(c, level_matrix(c), x, y, nullptr);
     }
 
     template <int DIM>
@@ -488,8 +497,39 @@ namespace gf
           launch_scatter_matrix(c, K, c0, c1, c0 == 0, true);
         }
       launch_build_precond(c, K);
+      c.mat[GF_MAT_TANGENT].valid = true;
     }
   } // namespace
+
+  // (re)build the FP32 operator copies the V-cycle streams when GF_OPT_MG_MATRIX_PRECISION = 1.
+  // The outer CG keeps applying the FP64 matrix, so the solve converges to the same tolerance on
+  // the same residual; only the (fixed, SPD) preconditioner changes. A level whose copy does not
+  // fit the free memory simply stays FP64.
+  void mg_refresh_f32(gf_context &c)
+  {
+    for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
+      {
+        l->mg_val32_valid = false;
+        if (l->mg_matrix_precision != 1 || !level_is_assembled(*l))
+          continue;
+        const double *A = level_matrix(*l);
+        if (A == nullptr || l->n_val == 0)
+          continue;
+        if (l->model == GF_MODEL_NEO_HOOKEAN ? !l->mat[GF_MAT_TANGENT].valid : !l->lin_assembled)
+          continue;
+        if (!l->mg_val32.p)
+          {
+            size_t free_b = 0, total_b = 0;
+            GF_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+            const size_t need = size_t(l->n_val + 4) * sizeof(float);
+            if (need + (size_t(1) << 30) > free_b)
+              continue;
+            l->mg_val32.alloc_zero(size_t(l->n_val + 4), l->stream);
+          }
+        launch_convert_f32(*l, A, l->mg_val32.p);
+        l->mg_val32_valid = true;
+      }
+  }
 
   bool mg_active(const gf_context &c)
   {
@@ -599,6 +639,7 @@ namespace gf
             l->stream      = f.stream;
             l->owns_stream = false;
             l->prof_sink   = f.prof_sink;
+            l->mg_matrix_precision = f.mg_matrix_precision;
           }
         if (!l->mg_r.p)
           {
@@ -632,6 +673,7 @@ namespace gf
         else
           lin_assemble(co);
       }
+    mg_refresh_f32(c);
     for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
       estimate_lmax(*l);
   }

@@ -369,7 +369,9 @@ namespace gf
               make_uint2(unsigned(vptr[r] - vptr[row0]),
                          unsigned(brow[r] - c0) | (unsigned(brow[r + 1] - brow[r]) << 16));
           meta[base + SPMV_TILE_ROWS]     = make_uint2(unsigned(row0), unsigned(row1 - row0));
-          meta[base + SPMV_TILE_ROWS + 1] = make_uint2(unsigned(d.col_count), 0u);
+          // .y: elements the FP32 bulk copy of this tile starts early to be 16-byte aligned
+          meta[base + SPMV_TILE_ROWS + 1] =
+            make_uint2(unsigned(d.col_count), unsigned(vptr[row0] & 3));
           row0 = row1;
         }
       if (ok)

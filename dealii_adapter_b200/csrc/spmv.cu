@@ -16,6 +16,12 @@
 // Fallback (spmv_kernel, LDG): one warp per row with double2 streaming loads; used when a row
 // does not fit a tile or when GF_OPT_SPMV_KERNEL = 1.
 // The fused dot product needs only gridDim.x partial sums (fixed order => reproducible).
+//
+// Value type VT: double for every operator application whose result the reference defines (CG
+// vmult, assemble_rhs vmults). VT = float streams a single-precision COPY of the same array
+// (same indexing, 4 B per value) and is used ONLY inside the multigrid V-cycle when
+// GF_OPT_MG_MATRIX_PRECISION = 1: the preconditioner replaces the reference's SSOR and may be
+// any fixed SPD operator; vectors, accumulation and the outer CG stay FP64.
 #include "gf_context.h"
 #include "kernel_utils.cuh"
 
@@ -29,12 +35,27 @@ namespace gf
     {
       return __ldcs(reinterpret_cast<const double2 *>(p));
     }
+    __device__ __forceinline__ double2 ld_stream2(const float *p)
+    {
+      const float2 v = __ldcs(reinterpret_cast<const float2 *>(p));
+      return make_double2(double(v.x), double(v.y));
+    }
+    // two consecutive values from shared memory, widened to FP64
+    __device__ __forceinline__ double2 lds2(const double *p)
+    {
+      return *reinterpret_cast<const double2 *>(p);
+    }
+    __device__ __forceinline__ double2 lds2(const float *p)
+    {
+      const float2 v = *reinterpret_cast<const float2 *>(p);
+      return make_double2(double(v.x), double(v.y));
+    }
 
-    template <int DIM, bool DOT>
+    template <int DIM, bool DOT, typename VT>
     __global__ void __launch_bounds__(SPMV_THREADS)
       spmv_kernel(const int64_t n_rows, const int32_t *__restrict__ brow_ptr,
                   const int64_t *__restrict__ val_ptr, const int32_t *__restrict__ bcol,
-                  const double *__restrict__ val, const double *__restrict__ x,
+                  const VT *__restrict__ val, const double *__restrict__ x,
                   double *__restrict__ y, double *__restrict__ partials, const int *status)
     {
       if (status != nullptr && *status != 0)
@@ -50,7 +71,7 @@ namespace gf
           const int     ne     = (brow_ptr[A + 1] - b0) * DIM;
           const int64_t vbase  = val_ptr[A];
           const int     stride = int((val_ptr[A + 1] - vbase) / DIM);
-          const double *vrow   = val + vbase;
+          const VT *    vrow   = val + vbase;
           const int32_t *crow  = bcol + b0;
           double        acc[DIM];
 #pragma unroll
@@ -108,16 +129,19 @@ namespace gf
     // ------------------------------------------------------------------------------------------
     // TMA-tiled kernel: producer warp (TMA) -> gather warps (x) -> consumer warps (FMA)
     // ------------------------------------------------------------------------------------------
-    template <int DIM>
+    template <int DIM, typename VT>
     struct TmaCfg
     {
-      static constexpr int TILE_V       = DIM == 3 ? 6144 : 4096; // doubles of values per tile
+      static constexpr int TILE_V       = DIM == 3 ? 6144 : 4096; // values per tile
       static constexpr int TILE_C       = ((TILE_V / (DIM * DIM)) + 8 + 3) & ~3; // column indices
-      static constexpr int STAGES       = 3;
+      // FP32 stages are half the size: one more stage keeps the same bytes in flight per SM
+      static constexpr int STAGES       = sizeof(VT) == 4 ? 4 : 3;
       static constexpr int GATHER_WARPS = 8;
       static constexpr int CONS_WARPS   = 8;
       static constexpr int THREADS      = (1 + GATHER_WARPS + CONS_WARPS) * 32;
-      static constexpr int VAL_BYTES    = TILE_V * 8;
+      // FP32: a tile starts at an even element, i.e. 8-byte but not always 16-byte aligned; the
+      // bulk copy then starts up to 2 elements early (skew) and is rounded up to 16 bytes
+      static constexpr int VAL_BYTES    = (TILE_V * int(sizeof(VT)) + (sizeof(VT) == 4 ? 16 : 0) + 127) & ~127;
       static constexpr int COL_BYTES    = (TILE_C * 4 + 127) & ~127;
       static constexpr int META_BYTES   = SPMV_META * 8; // bytes copied
       static constexpr int META_PAD     = (META_BYTES + 127) & ~127;
@@ -137,14 +161,14 @@ namespace gf
                    : "memory");
     }
 
-    template <int DIM, bool DOT>
-    __global__ void __launch_bounds__(TmaCfg<DIM>::THREADS, 1)
+    template <int DIM, bool DOT, typename VT>
+    __global__ void __launch_bounds__(TmaCfg<DIM, VT>::THREADS, 1)
       spmv_tma_kernel(const int n_tiles, const TileDesc *__restrict__ tile_desc,
                       const uint2 *__restrict__ tile_meta, const int32_t *__restrict__ bcol,
-                      const double *__restrict__ val, const double *__restrict__ x,
+                      const VT *__restrict__ val, const double *__restrict__ x,
                       double *__restrict__ y, double *__restrict__ partials, const int *status)
     {
-      using C = TmaCfg<DIM>;
+      using C = TmaCfg<DIM, VT>;
       if (status != nullptr && *status != 0)
         return;
       extern __shared__ __align__(128) unsigned char smem[];
@@ -194,9 +218,14 @@ namespace gf
                   const int64_t  t     = int64_t(blockIdx.x) + int64_t(k) * gridDim.x;
                   unsigned char *stage = smem + s * C::STAGE_BYTES;
                   const uint32_t fb    = smem_u32(&full[s]);
-                  const uint32_t vb = uint32_t(val_count) * 8u, cb = uint32_t(col_count) * 4u;
+                  // 16-byte aligned source and size: FP64 tiles are (even offset and count),
+                  // FP32 tiles start `skew` elements early (consumers add the same skew)
+                  const int      skew = sizeof(VT) == 4 ? int(val_off & 3) : 0;
+                  const uint32_t vb =
+                    (uint32_t(skew + val_count) * uint32_t(sizeof(VT)) + 15u) & ~15u;
+                  const uint32_t cb = uint32_t(col_count) * 4u;
                   mbar_arrive_expect_tx(fb, vb + cb + uint32_t(C::META_BYTES));
-                  bulk_g2s(smem_u32(stage), val + val_off, vb, fb);
+                  bulk_g2s(smem_u32(stage), val + (val_off - skew), vb, fb);
                   bulk_g2s(smem_u32(stage + C::VAL_BYTES), bcol + col_off, cb, fb);
                   bulk_g2s(smem_u32(stage + C::VAL_BYTES + C::COL_BYTES), tile_meta + t * SPMV_META,
                            uint32_t(C::META_BYTES), fb);
@@ -242,9 +271,11 @@ namespace gf
               mbar_wait(smem_u32(&full[s]), (k / C::STAGES) & 1);
               mbar_wait(smem_u32(&xfull[s]), (k / C::STAGES) & 1);
               const unsigned char *stage = smem + s * C::STAGE_BYTES;
-              const double *       sval  = reinterpret_cast<const double *>(stage);
               const uint2 *        smeta =
                 reinterpret_cast<const uint2 *>(stage + C::VAL_BYTES + C::COL_BYTES);
+              // FP32: the copy started smeta[..+1].y = (tile val_off & 3) elements early
+              const VT *sval = reinterpret_cast<const VT *>(stage) +
+                               (sizeof(VT) == 4 ? int(smeta[SPMV_TILE_ROWS + 1].y) : 0);
               const double *sx = reinterpret_cast<const double *>(stage + C::VAL_BYTES +
                                                                   C::COL_BYTES + C::META_PAD);
               const uint2 hdr    = smeta[SPMV_TILE_ROWS];
@@ -255,7 +286,7 @@ namespace gf
                   const uint2   m      = smeta[row];
                   const int     ne     = int(m.y >> 16) * DIM;
                   const int     stride = (ne + 1) & ~1;
-                  const double *v      = sval + m.x;
+                  const VT *    v      = sval + m.x;
                   const double *xr     = sx + int(m.y & 0xffffu) * DIM; // x of this row, contiguous
                   const int64_t i      = int64_t(row0 + row) * DIM + lane;
                   double        xi     = 0.0;
@@ -273,7 +304,7 @@ namespace gf
 #pragma unroll
                       for (int r = 0; r < DIM; ++r)
                         {
-                          const double2 vv = *reinterpret_cast<const double2 *>(v + r * stride + e);
+                          const double2 vv = lds2(v + r * stride + e);
                           acc[r]           = fma(vv.x, x0, acc[r]);
                           acc[r]           = fma(vv.y, x1, acc[r]);
                         }
@@ -315,22 +346,34 @@ namespace gf
         }
     }
 
-    template <int DIM, bool DOT>
-    void launch_tma_t(gf_context &c, const double *val, const double *x, double *y,
+    template <int DIM, bool DOT, typename VT>
+    void launch_tma_t(gf_context &c, const VT *val, const double *x, double *y,
                       double *dot_partials, const int *st)
     {
-      using C = TmaCfg<DIM>;
+      using C = TmaCfg<DIM, VT>;
       static bool configured = false;
       if (!configured)
         {
-          GF_CUDA_CHECK(cudaFuncSetAttribute(spmv_tma_kernel<DIM, DOT>,
+          GF_CUDA_CHECK(cudaFuncSetAttribute(spmv_tma_kernel<DIM, DOT, VT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              C::SMEM_BYTES));
           configured = true;
         }
       const int grid = int(std::min<int64_t>(c.n_tiles, c.sm_count));
-      spmv_tma_kernel<DIM, DOT><<<grid, C::THREADS, C::SMEM_BYTES, c.stream>>>(
+      spmv_tma_kernel<DIM, DOT, VT><<<grid, C::THREADS, C::SMEM_BYTES, c.stream>>>(
         int(c.n_tiles), c.tile_desc.p, c.tile_meta.p, c.bcol.p, val, x, y, dot_partials, st);
+    }
+
+    // FP64 array -> FP32 copy with the same indexing (n even: every scalar row is padded)
+    __global__ void convert_f32_kernel(const int64_t n_pairs, const double2 *__restrict__ in,
+                                       float2 *__restrict__ out)
+    {
+      for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n_pairs;
+           i += int64_t(gridDim.x) * blockDim.x)
+        {
+          const double2 v = __ldcs(in + i);
+          out[i]          = make_float2(float(v.x), float(v.y));
+        }
     }
 
     // y = M x with M = m_ab delta_cd (consistent mass, one scalar per block)
@@ -389,16 +432,16 @@ namespace gf
         if (c.dim == 3)
           {
             if (dot_partials)
-              launch_tma_t<3, true>(c, val, x, y, dot_partials, st);
+              launch_tma_t<3, true, double>(c, val, x, y, dot_partials, st);
             else
-              launch_tma_t<3, false>(c, val, x, y, nullptr, nullptr);
+              launch_tma_t<3, false, double>(c, val, x, y, nullptr, nullptr);
           }
         else
           {
             if (dot_partials)
-              launch_tma_t<2, true>(c, val, x, y, dot_partials, st);
+              launch_tma_t<2, true, double>(c, val, x, y, dot_partials, st);
             else
-              launch_tma_t<2, false>(c, val, x, y, nullptr, nullptr);
+              launch_tma_t<2, false, double>(c, val, x, y, nullptr, nullptr);
           }
         GF_CUDA_CHECK(cudaGetLastError());
         return;
@@ -407,21 +450,60 @@ namespace gf
     if (c.dim == 3)
       {
         if (dot_partials)
-          spmv_kernel<3, true><<<grid, SPMV_THREADS, 0, c.stream>>>(
+          spmv_kernel<3, true, double><<<grid, SPMV_THREADS, 0, c.stream>>>(
             n_rows, c.brow_ptr.p, c.val_ptr.p, c.bcol.p, val, x, y, dot_partials, st);
         else
-          spmv_kernel<3, false><<<grid, SPMV_THREADS, 0, c.stream>>>(
+          spmv_kernel<3, false, double><<<grid, SPMV_THREADS, 0, c.stream>>>(
             n_rows, c.brow_ptr.p, c.val_ptr.p, c.bcol.p, val, x, y, nullptr, nullptr);
       }
     else
       {
         if (dot_partials)
-          spmv_kernel<2, true><<<grid, SPMV_THREADS, 0, c.stream>>>(
+          spmv_kernel<2, true, double><<<grid, SPMV_THREADS, 0, c.stream>>>(
             n_rows, c.brow_ptr.p, c.val_ptr.p, c.bcol.p, val, x, y, dot_partials, st);
         else
-          spmv_kernel<2, false><<<grid, SPMV_THREADS, 0, c.stream>>>(
+          spmv_kernel<2, false, double><<<grid, SPMV_THREADS, 0, c.stream>>>(
             n_rows, c.brow_ptr.p, c.val_ptr.p, c.bcol.p, val, x, y, nullptr, nullptr);
       }
+    GF_CUDA_CHECK(cudaGetLastError());
+  }
+
+  // y = A32 x: the FP32 copy of a level operator inside the multigrid V-cycle (no fused dot)
+  void launch_spmv_f32(gf_context &c, const float *val32, const double *x, double *y)
+  {
+    ProfScope     ps(c, c.mg_level > 0 ? Profile::MG_SPMV : Profile::SPMV);
+    const int64_t n_rows = c.n_owned_nodes;
+    if (n_rows == 0)
+      return;
+    if (c.n_tiles > 0 && c.spmv_kernel_kind == 0)
+      {
+        if (c.dim == 3)
+          launch_tma_t<3, false, float>(c, val32, x, y, nullptr, nullptr);
+        else
+          launch_tma_t<2, false, float>(c, val32, x, y, nullptr, nullptr);
+      }
+    else
+      {
+        const int grid = spmv_dot_partials(c);
+        if (c.dim == 3)
+          spmv_kernel<3, false, float><<<grid, SPMV_THREADS, 0, c.stream>>>(
+            n_rows, c.brow_ptr.p, c.val_ptr.p, c.bcol.p, val32, x, y, nullptr, nullptr);
+        else
+          spmv_kernel<2, false, float><<<grid, SPMV_THREADS, 0, c.stream>>>(
+            n_rows, c.brow_ptr.p, c.val_ptr.p, c.bcol.p, val32, x, y, nullptr, nullptr);
+      }
+    GF_CUDA_CHECK(cudaGetLastError());
+  }
+
+  void launch_convert_f32(gf_context &c, const double *val, float *val32)
+  {
+    ProfScope     ps(c, Profile::MG_VEC);
+    const int64_t n_pairs = c.n_val / 2; // n_val is even (padded scalar rows)
+    if (n_pairs == 0)
+      return;
+    const int grid = int(std::min<int64_t>((n_pairs + 255) / 256, int64_t(c.sm_count) * 16));
+    convert_f32_kernel<<<grid, 256, 0, c.stream>>>(
+      n_pairs, reinterpret_cast<const double2 *>(val), reinterpret_cast<float2 *>(val32));
     GF_CUDA_CHECK(cudaGetLastError());
   }
 
@@ -448,5 +530,10 @@ namespace gf
     // kernel, tile records for the TMA kernel are of the same order) + x read once + y written once
     return 8.0 * double(c.n_val) + 4.0 * double(c.n_blocks) + 12.0 * double(c.n_owned_nodes + 1) +
            8.0 * double(c.n_local) + 8.0 * double(c.n_owned);
+  }
+  // the same with the FP32 value copy (vectors stay FP64)
+  double spmv_bytes_f32(const gf_context &c)
+  {
+    return spmv_bytes(c) - 4.0 * double(c.n_val);
   }
 } // namespace gf

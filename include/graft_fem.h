@@ -109,7 +109,9 @@ extern "C"
     GF_MAT_TANGENT = 0, /* Solid::tangent_matrix */
     GF_MAT_STIFFNESS,   /* ElastoDynamics::stiffness_matrix */
     GF_MAT_MASS,        /* ElastoDynamics::mass_matrix */
-    GF_MAT_SYSTEM       /* ElastoDynamics::system_matrix (= constrained stepping matrix) */
+    GF_MAT_SYSTEM,      /* ElastoDynamics::system_matrix (= constrained stepping matrix) */
+    GF_MAT_MG_F32       /* gf_spmv / gf_spmv_timed only: the FP32 copy of this level's operator that
+                           the V-cycle streams when GF_OPT_MG_MATRIX_PRECISION = 1 */
   };
   enum
   {
@@ -130,7 +132,13 @@ extern "C"
     GF_OPT_SPMV_KERNEL,        /* 0: TMA-tiled kernel (default) ; 1: LDG warp-per-row kernel */
     GF_OPT_MG_SMOOTHER_DEGREE, /* Chebyshev degree of the pre-/post-smoother (default 3) */
     GF_OPT_MG_COARSE_DEGREE,   /* Chebyshev degree of the coarsest-level solve (default 80) */
-    GF_OPT_MG_SMOOTHER_RATIO   /* smoothers damp the eigenvalues in [lmax/ratio, lmax] (default 40) */
+    GF_OPT_MG_SMOOTHER_RATIO,  /* smoothers damp the eigenvalues in [lmax/ratio, lmax] (default 40) */
+    GF_OPT_MG_MATRIX_PRECISION /* 0 (default): the V-cycle streams the FP64 level matrices;
+                                  1: it streams FP32 copies of them (half the HBM bytes per smoother
+                                  / residual application). Vectors, accumulation and the outer CG
+                                  (operator, residual, tolerance: nonlinear:1171-1187,
+                                  linear:540-552) stay FP64, so the solve converges to the same
+                                  tolerance; only the SSOR replacement changes. */
   };
 
   /* device-time breakdown accumulated while GF_OPT_PROFILE = 1 (CUDA events on the library's
@@ -231,6 +239,16 @@ extern "C"
   int64_t gf_nnz(gf_handle h); /* scalar non-zeros of the pattern incl. explicit zeros */
   /* scalar CSR (ascending columns) of one matrix in the caller's numbering, owned rows only */
   int gf_export_csr(gf_handle h, int which_matrix, int64_t *rowptr, int32_t *col, double *val);
+
+  /* Output-step post-processing: what DataOut::build_patches(MappingQEulerian, degree) +
+   * Postprocessor::evaluate_vector_field compute (nonlinear:1215-1254 / linear:590-629,
+   * postprocessor.h:44-76). For every local cell (order of desc.cell_dofs) and every one of its
+   * (degree+1)^dim equidistant patch points (lexicographic, x fastest, as DataOutBase::Patch):
+   *   fields[(cell*npts + pt)*(dim+dim*dim) + ...] = u_0..u_{dim-1}, strain_00, strain_01, ...
+   * with strain = sym(grad_x u) taken on the DISPLACED configuration (MappingQEulerian). The host
+   * adds X(patch point) + u for the patch vertices and writes the VTK file. which_vector:
+   * GF_NL_TOTAL_DISPLACEMENT / GF_LIN_DISPLACEMENT (or any DoF vector). */
+  int gf_postprocess(gf_handle h, int which_vector, double *fields);
 
   /* ---- kernels exposed for measurement ------------------------------------------------------ */
   /* y = A x on the library stream (vmult; nonlinear:1184, linear:411-419,551) */

@@ -1531,6 +1531,85 @@ namespace
           d[i] += dt * (1 - theta) * V(ORC_LIN_OLD_VELOCITY)[i];
         }
     }
+
+    // ----------------------------------------------------------------------------------------
+    // Output path: output_results (nonlinear_elasticity.cc:1215-1254, linear_elasticity.cc:
+    // 590-629) = DataOut::build_patches(MappingQEulerian(degree, dof_handler, displacement),
+    // degree, curved_boundary) + Postprocessor::evaluate_vector_field (postprocessor.h:44-76).
+    // [deal.II] build_patches evaluates solution values and gradients at the (degree+1)^dim
+    // equidistant patch points (lexicographic, x fastest) with FEValues on the GIVEN mapping;
+    // MappingQEulerian maps xi -> X(xi) + u_h(xi), so gradients are taken with respect to the
+    // displaced coordinates: J_e = J + grad_xi u, grad_x u = grad_xi u . J_e^-1.
+    //   fields[(cell*npts + pt)*(dim+dim*dim) + ...] = u, then strain unrolled (d*dim + e)
+    //   points[(cell*npts + pt)*dim + ...]           = X + u (patch vertices on the displaced grid)
+    // ----------------------------------------------------------------------------------------
+    void postprocess(int which, double *points, double *fields) const
+    {
+      const std::vector<double> &sol = vecs[which];
+      const int                  nv = 1 << dim, nf = dim + dim * dim;
+      std::vector<double>        u_local(dpc);
+      for (int64_t cell = 0; cell < desc.n_cells; ++cell)
+        {
+          const double * verts = &cell_vertices[cell * nv * dim];
+          const int32_t *ldi   = &cell_dofs[cell * dpc];
+          for (int k = 0; k < dpc; ++k)
+            u_local[k] = sol[ldi[k]];
+          for (int pt = 0; pt < npc; ++pt)
+            {
+              double xi[3] = {0, 0, 0};
+              int    rem   = pt;
+              for (int d = 0; d < dim; ++d)
+                {
+                  xi[d] = double(rem % (p + 1)) / p;
+                  rem /= (p + 1);
+                }
+              // reference position and Jacobian of the Q1 geometry
+              double X[3] = {0, 0, 0}, J[3][3];
+              std::vector<double> dphi(nv * dim);
+              for (int v = 0; v < nv; ++v)
+                {
+                  vertex_grad(v, xi, &dphi[v * dim]);
+                  double phi = 1;
+                  for (int l = 0; l < dim; ++l)
+                    phi *= ((v >> l) & 1) ? xi[l] : 1.0 - xi[l];
+                  for (int i = 0; i < dim; ++i)
+                    X[i] += phi * verts[v * dim + i];
+                }
+              jacobian(verts, dphi.data(), J);
+              // solution value and unit-cell gradient
+              double    val[3] = {0, 0, 0};
+              Ten2<dim> Gxi, Je;
+              for (int a = 0; a < npc; ++a)
+                {
+                  const double Na = shape(a, xi);
+                  double       g[3];
+                  shape_grad(a, xi, g);
+                  for (int c = 0; c < dim; ++c)
+                    {
+                      val[c] += Na * u_local[a * dim + c];
+                      for (int k = 0; k < dim; ++k)
+                        Gxi.d[c][k] += g[k] * u_local[a * dim + c];
+                    }
+                }
+              for (int i = 0; i < dim; ++i)
+                for (int j = 0; j < dim; ++j)
+                  Je.d[i][j] = J[i][j] + Gxi.d[i][j];
+              if (!(determinant(Je) > 0))
+                throw std::runtime_error("oracle: inverted MappingQEulerian cell in output");
+              const Ten2<dim> grad_u = matmul(Gxi, invert(Je));
+              double *        out    = fields + (cell * npc + pt) * nf;
+              for (int d = 0; d < dim; ++d) // postprocessor.h:61-72
+                {
+                  out[d] = val[d];
+                  for (int e = 0; e < dim; ++e)
+                    out[dim + d * dim + e] = (grad_u.d[d][e] + grad_u.d[e][d]) / 2;
+                }
+              if (points)
+                for (int d = 0; d < dim; ++d)
+                  points[(cell * npc + pt) * dim + d] = X[d] + val[d];
+            }
+        }
+    }
   };
 
   template <typename F>
@@ -1750,6 +1829,10 @@ extern "C"
                                                   cell_matrix, cell_rhs, u_local, acc_local);
       return 0;
     });
+  }
+  void orc_postprocess(void *h, int which, double *points, double *fields)
+  {
+    dispatch(h, [&](auto &c) { c.postprocess(which, points, fields); return 0; });
   }
   void orc_vmult(void *h, int which, const double *x, double *y)
   {

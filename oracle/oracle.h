@@ -122,6 +122,12 @@ extern "C"
   void orc_save_state(void *h);   /* :457-462 */
   void orc_reload_state(void *h); /* :482-487 */
 
+  /* ---- output path: output_results (nonlinear:1215-1254, linear:590-629) + Postprocessor
+     (postprocessor.h:44-76): per cell and (degree+1)^dim lexicographic patch point,
+     fields = [u | strain(d*dim+e)] on the MappingQEulerian (displaced) configuration,
+     points = X + u (may be NULL) ---- */
+  void orc_postprocess(void *h, int which, double *points, double *fields);
+
   /* ---- pieces exposed for known-answer tests ---- */
   /* material.h:37-49,62-138 : tau (n_indep) and Jc (n_indep^2) from det_F and b_bar (n_indep);
      deal.II SymmetricTensor component order (00,11,[22],01,[02,12]) */

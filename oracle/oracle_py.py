@@ -71,6 +71,8 @@ def lib():
                                    C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_nl_cell.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_vmult.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_postprocess.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_postprocess.restype = None
         L.orc_threads_available.restype = C.c_int
         _lib = L
     return _lib
@@ -215,6 +217,17 @@ class Oracle:
 
     def save_state(self): lib().orc_save_state(self._h)
     def reload_state(self): lib().orc_reload_state(self._h)
+
+    def postprocess(self, which):
+        """output_results + Postprocessor: (points [n_cells, npts, dim] = X + u on the displaced
+        grid, fields [n_cells, npts, dim + dim*dim] = u | strain(d*dim+e))."""
+        dim = self.problem.dim
+        npts = (self.problem.params.poly_degree + 1) ** dim
+        nc = self.problem.mesh.n_cells
+        pts = np.zeros((nc, npts, dim))
+        fld = np.zeros((nc, npts, dim + dim * dim))
+        lib().orc_postprocess(self._h, which, pts.ctypes.data, fld.ctypes.data)
+        return pts, fld
 
     def vmult(self, which, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
