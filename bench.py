@@ -373,6 +373,17 @@ def main():
                 "cg_iterations": cg_iterations(h0v), "operator_apply_ms": ms32,
                 "operator_bytes_per_apply": bytes32,
                 "operator_gbs": bytes32 / ms32 / 1e6}
+            # the same two arrays through the two-ring SpMV (GF_OPT_SPMV_KERNEL = 2: value ring and
+            # column/x ring decoupled, two tiles gathered concurrently)
+            h.set_option(capi.OPT_SPMV_KERNEL, 2)
+            ms64_2, bytes64 = h.spmv_timed(capi.MAT_TANGENT, 5)
+            ms32_2, _ = h.spmv_timed(capi.MAT_MG_F32, 5)
+            h.set_option(capi.OPT_SPMV_KERNEL, 0)
+            variants["spmv_two_ring_kernel"] = {
+                "what": "stand-alone launches of GF_OPT_SPMV_KERNEL = 2 on the FP64 tangent and on "
+                        "its FP32 copy (bitwise equal results to the default kernel)",
+                "fp64_ms": ms64_2, "fp64_gbs": bytes64 / ms64_2 / 1e6,
+                "fp32_copy_ms": ms32_2, "fp32_copy_gbs": bytes32 / ms32_2 / 1e6}
             h.set_option(capi.OPT_MG_MATRIX_PRECISION, 0)
             for k in range(N_SUB):      # FP64 operators again for the stand-alone SpMV timing
                 resident_pass(k)

@@ -346,6 +346,294 @@ namespace gf
         }
     }
 
+    // ------------------------------------------------------------------------------------------
+    // Two-ring variant (GF_OPT_SPMV_KERNEL = 2). In the kernel above one stage carries a tile
+    // through TMA -> x gather -> FMA, so a stage is busy for the SUM of the three latencies and
+    // the bytes in flight per SM are bounded by STAGES / (that sum): the FP32 copy of the same
+    // matrix ran in 0.60 ms against 0.62 ms for FP64 (profiles/r01_f32_vcycle_probe_single_ring
+    // .json) - latency, not bytes. Here the small per-tile data (column indices, row records,
+    // gathered x: ~20 KB) live in their own, deeper ring that runs LEAD tiles ahead of the value
+    // ring: the x gather of tile k overlaps the TMA flight of tile k's values, and a value stage
+    // is busy only for TMA + FMA.
+    //   producer order per step i: cols(i), then values(i - LEAD). cols(i) needs tile i - XSTAGES
+    //   consumed, values(j) tile j - VSTAGES; with LEAD = XSTAGES - VSTAGES both waits are for the
+    //   same tile, so neither stream throttles the other and the in-order producer cannot deadlock
+    //   (everything a waited-for tile needs was issued in an earlier step).
+    // ------------------------------------------------------------------------------------------
+    template <int DIM, typename VT>
+    struct Tma2Cfg
+    {
+      using B = TmaCfg<DIM, VT>;
+      static constexpr int VSTAGES      = sizeof(VT) == 4 ? 4 : 3;
+      static constexpr int XSTAGES      = sizeof(VT) == 4 ? 6 : 4;
+      static constexpr int LEAD         = XSTAGES - VSTAGES;
+      // gather groups = tiles gathered concurrently. Must divide XSTAGES: a group then meets the
+      // phases of "its" stages consecutively (a skipped phase would alias in the parity wait)
+      static constexpr int GROUPS       = 2;
+      static_assert(XSTAGES % GROUPS == 0 && TmaCfg<DIM, VT>::GATHER_WARPS % GROUPS == 0, "groups");
+      static constexpr int XSTAGE_BYTES = B::COL_BYTES + B::META_PAD + B::XG_BYTES;
+      static constexpr int RING_BYTES   = VSTAGES * B::VAL_BYTES + XSTAGES * XSTAGE_BYTES;
+      static constexpr int N_BARS       = 2 * VSTAGES + 3 * XSTAGES;
+      static constexpr int SMEM_BYTES   = RING_BYTES + N_BARS * 8 + 64;
+      static_assert(SMEM_BYTES + 64 <= 227 * 1024, "shared memory budget");
+    };
+
+    template <int DIM, bool DOT, typename VT>
+    __global__ void __launch_bounds__(TmaCfg<DIM, VT>::THREADS, 1)
+      spmv_tma2_kernel(const int n_tiles, const TileDesc *__restrict__ tile_desc,
+                       const uint2 *__restrict__ tile_meta, const int32_t *__restrict__ bcol,
+                       const VT *__restrict__ val, const double *__restrict__ x,
+                       double *__restrict__ y, double *__restrict__ partials, const int *status)
+    {
+      using B = TmaCfg<DIM, VT>;
+      using C = Tma2Cfg<DIM, VT>;
+      if (status != nullptr && *status != 0)
+        return;
+      extern __shared__ __align__(128) unsigned char smem[];
+      unsigned char *vring  = smem;
+      unsigned char *xring  = smem + C::VSTAGES * B::VAL_BYTES;
+      uint64_t *     bars   = reinterpret_cast<uint64_t *>(smem + C::RING_BYTES);
+      uint64_t *     vfull  = bars;                               // values landed   (1 + tx)
+      uint64_t *     vempty = bars + C::VSTAGES;                  // consumers done  (CONS_WARPS)
+      uint64_t *     cfull  = bars + 2 * C::VSTAGES;              // cols + records  (1 + tx)
+      uint64_t *     xfull  = bars + 2 * C::VSTAGES + C::XSTAGES; // x gathered (warps of a group)
+      uint64_t *     xempty = bars + 2 * C::VSTAGES + 2 * C::XSTAGES; // consumers done
+      __shared__ double red[B::CONS_WARPS];
+      const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+      if (tid == 0)
+        {
+          for (int s = 0; s < C::VSTAGES; ++s)
+            {
+              mbar_init(smem_u32(&vfull[s]), 1);
+              mbar_init(smem_u32(&vempty[s]), B::CONS_WARPS);
+            }
+          for (int s = 0; s < C::XSTAGES; ++s)
+            {
+              mbar_init(smem_u32(&cfull[s]), 1);
+              mbar_init(smem_u32(&xfull[s]), B::GATHER_WARPS / C::GROUPS);
+              mbar_init(smem_u32(&xempty[s]), B::CONS_WARPS);
+            }
+          asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+      __syncthreads();
+      const int n_my =
+        int(blockIdx.x) < n_tiles ? (n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
+      double dot = 0.0;
+
+      if (warp == 0)
+        {
+          // ------------------------------ producer warp: TMA ---------------------------------
+          TileDesc dc{}, dv{}; // lane l caches the descriptor of tile (batch start + l)
+          for (int i = 0; i < n_my + C::LEAD; ++i)
+            {
+              // ---- column indices + row records of tile i ----
+              if (i < n_my)
+                {
+                  if ((i & 31) == 0)
+                    {
+                      const int kk = i + lane;
+                      if (kk < n_my)
+                        dc = tile_desc[int64_t(blockIdx.x) + int64_t(kk) * gridDim.x];
+                    }
+                  const int col_off   = __shfl_sync(0xffffffffu, dc.col_off, i & 31);
+                  const int col_count = __shfl_sync(0xffffffffu, dc.col_count, i & 31);
+                  const int sx        = i % C::XSTAGES;
+                  if (i >= C::XSTAGES)
+                    mbar_wait(smem_u32(&xempty[sx]), ((i / C::XSTAGES) - 1) & 1);
+                  if (lane == 0)
+                    {
+                      const int64_t  t     = int64_t(blockIdx.x) + int64_t(i) * gridDim.x;
+                      unsigned char *stage = xring + sx * C::XSTAGE_BYTES;
+                      const uint32_t fb    = smem_u32(&cfull[sx]);
+                      const uint32_t cb    = uint32_t(col_count) * 4u;
+                      mbar_arrive_expect_tx(fb, cb + uint32_t(B::META_BYTES));
+                      bulk_g2s(smem_u32(stage), bcol + col_off, cb, fb);
+                      bulk_g2s(smem_u32(stage + B::COL_BYTES), tile_meta + t * SPMV_META,
+                               uint32_t(B::META_BYTES), fb);
+                    }
+                  __syncwarp();
+                }
+              // ---- values of tile j = i - LEAD ----
+              const int j = i - C::LEAD;
+              if (j >= 0)
+                {
+                  if ((j & 31) == 0)
+                    {
+                      const int kk = j + lane;
+                      if (kk < n_my)
+                        dv = tile_desc[int64_t(blockIdx.x) + int64_t(kk) * gridDim.x];
+                    }
+                  const long long val_off   = __shfl_sync(0xffffffffu, dv.val_off, j & 31);
+                  const int       val_count = __shfl_sync(0xffffffffu, dv.val_count, j & 31);
+                  const int       sv        = j % C::VSTAGES;
+                  if (j >= C::VSTAGES)
+                    mbar_wait(smem_u32(&vempty[sv]), ((j / C::VSTAGES) - 1) & 1);
+                  if (lane == 0)
+                    {
+                      const uint32_t fb   = smem_u32(&vfull[sv]);
+                      const int      skew = sizeof(VT) == 4 ? int(val_off & 3) : 0;
+                      const uint32_t vb =
+                        (uint32_t(skew + val_count) * uint32_t(sizeof(VT)) + 15u) & ~15u;
+                      mbar_arrive_expect_tx(fb, vb);
+                      bulk_g2s(smem_u32(vring + sv * B::VAL_BYTES), val + (val_off - skew), vb, fb);
+                    }
+                  __syncwarp();
+                }
+            }
+        }
+      else if (warp <= B::GATHER_WARPS)
+        {
+          // ---------------- gather warps: x[col] -> shared --------------------------------------
+          // The gather of one tile is ONE round trip to L2 (~1 us under the streaming load), so
+          // tiles must overlap: GROUPS groups of warps work on consecutive tiles concurrently, and
+          // a lane issues ALL loads of its blocks (UB blocks, fully unrolled) before the first
+          // store, so a tile costs a group exactly one round trip.
+          constexpr int GL = B::GATHER_WARPS * 32 / C::GROUPS; // lanes per group
+          constexpr int UB = (B::TILE_C + GL - 1) / GL;        // blocks per lane and tile
+          const int     grp = (warp - 1) / (B::GATHER_WARPS / C::GROUPS);
+          const int     g   = ((warp - 1) % (B::GATHER_WARPS / C::GROUPS)) * 32 + lane;
+          for (int k = grp; k < n_my; k += C::GROUPS)
+            {
+              const int sx = k % C::XSTAGES;
+              mbar_wait(smem_u32(&cfull[sx]), (k / C::XSTAGES) & 1);
+              unsigned char *stage = xring + sx * C::XSTAGE_BYTES;
+              const int32_t *scol  = reinterpret_cast<const int32_t *>(stage);
+              const uint2 *  smeta = reinterpret_cast<const uint2 *>(stage + B::COL_BYTES);
+              double *       sxv = reinterpret_cast<double *>(stage + B::COL_BYTES + B::META_PAD);
+              const int      nblk = int(smeta[SPMV_TILE_ROWS + 1].x);
+              double         r[UB][DIM];
+#pragma unroll
+              for (int u = 0; u < UB; ++u)
+                {
+                  const int j = g + u * GL;
+                  if (j < nblk)
+                    {
+                      const int64_t col = scol[j];
+#pragma unroll
+                      for (int d0 = 0; d0 < DIM; ++d0)
+                        r[u][d0] = __ldg(x + col * DIM + d0);
+                    }
+                }
+#pragma unroll
+              for (int u = 0; u < UB; ++u)
+                {
+                  const int j = g + u * GL;
+                  if (j < nblk)
+#pragma unroll
+                    for (int d0 = 0; d0 < DIM; ++d0)
+                      sxv[j * DIM + d0] = r[u][d0];
+                }
+              __syncwarp();
+              if (lane == 0)
+                mbar_arrive(smem_u32(&xfull[sx]));
+            }
+        }
+      else
+        {
+          // ------------------------------ consumer warps: shared-memory FMA --------------------
+          const int cw = warp - 1 - B::GATHER_WARPS;
+          for (int k = 0; k < n_my; ++k)
+            {
+              const int sv = k % C::VSTAGES, sx = k % C::XSTAGES;
+              // cfull too: the row records arrive through the async proxy, observe their barrier
+              mbar_wait(smem_u32(&cfull[sx]), (k / C::XSTAGES) & 1);
+              mbar_wait(smem_u32(&xfull[sx]), (k / C::XSTAGES) & 1);
+              mbar_wait(smem_u32(&vfull[sv]), (k / C::VSTAGES) & 1);
+              const unsigned char *xs    = xring + sx * C::XSTAGE_BYTES;
+              const uint2 *        smeta = reinterpret_cast<const uint2 *>(xs + B::COL_BYTES);
+              const VT *sval = reinterpret_cast<const VT *>(vring + sv * B::VAL_BYTES) +
+                               (sizeof(VT) == 4 ? int(smeta[SPMV_TILE_ROWS + 1].y) : 0);
+              const double *sxv =
+                reinterpret_cast<const double *>(xs + B::COL_BYTES + B::META_PAD);
+              const uint2 hdr    = smeta[SPMV_TILE_ROWS];
+              const int   row0   = int(hdr.x);
+              const int   n_rows = int(hdr.y);
+              for (int row = cw; row < n_rows; row += B::CONS_WARPS)
+                {
+                  const uint2   m      = smeta[row];
+                  const int     ne     = int(m.y >> 16) * DIM;
+                  const int     stride = (ne + 1) & ~1;
+                  const VT *    v      = sval + m.x;
+                  const double *xr     = sxv + int(m.y & 0xffffu) * DIM;
+                  const int64_t i      = int64_t(row0 + row) * DIM + lane;
+                  double        xi     = 0.0;
+                  if (DOT && lane < DIM)
+                    xi = __ldg(x + i);
+                  double acc[DIM];
+#pragma unroll
+                  for (int r = 0; r < DIM; ++r)
+                    acc[r] = 0.0;
+#pragma unroll 3
+                  for (int e = 2 * lane; e < ne; e += 64)
+                    {
+                      const double x0 = xr[e];
+                      const double x1 = (e + 1 < ne) ? xr[e + 1] : 0.0;
+#pragma unroll
+                      for (int r = 0; r < DIM; ++r)
+                        {
+                          const double2 vv = lds2(v + r * stride + e);
+                          acc[r]           = fma(vv.x, x0, acc[r]);
+                          acc[r]           = fma(vv.y, x1, acc[r]);
+                        }
+                    }
+#pragma unroll
+                  for (int r = 0; r < DIM; ++r)
+                    acc[r] = warp_sum(acc[r]);
+                  if (lane < DIM)
+                    {
+                      double yr = acc[0];
+#pragma unroll
+                      for (int r = 1; r < DIM; ++r)
+                        if (lane == r)
+                          yr = acc[r];
+                      y[i] = yr;
+                      if (DOT)
+                        dot = fma(yr, xi, dot);
+                    }
+                }
+              __syncwarp();
+              if (lane == 0)
+                {
+                  mbar_arrive(smem_u32(&vempty[sv])); // release both stages
+                  mbar_arrive(smem_u32(&xempty[sx]));
+                }
+            }
+        }
+      if (DOT)
+        {
+          const int cw = warp - 1 - B::GATHER_WARPS;
+          dot          = warp_sum(dot);
+          if (lane == 0 && cw >= 0)
+            red[cw] = dot;
+          __syncthreads();
+          if (tid < 32)
+            {
+              double v = tid < B::CONS_WARPS ? red[tid] : 0.0;
+              v        = warp_sum(v);
+              if (tid == 0)
+                partials[blockIdx.x] = v;
+            }
+        }
+    }
+
+    template <int DIM, bool DOT, typename VT>
+    void launch_tma2_t(gf_context &c, const VT *val, const double *x, double *y,
+                       double *dot_partials, const int *st)
+    {
+      using C = Tma2Cfg<DIM, VT>;
+      static bool configured = false;
+      if (!configured)
+        {
+          GF_CUDA_CHECK(cudaFuncSetAttribute(spmv_tma2_kernel<DIM, DOT, VT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             C::SMEM_BYTES));
+          configured = true;
+        }
+      const int grid = int(std::min<int64_t>(c.n_tiles, c.sm_count));
+      spmv_tma2_kernel<DIM, DOT, VT><<<grid, TmaCfg<DIM, VT>::THREADS, C::SMEM_BYTES, c.stream>>>(
+        int(c.n_tiles), c.tile_desc.p, c.tile_meta.p, c.bcol.p, val, x, y, dot_partials, st);
+    }
+
     template <int DIM, bool DOT, typename VT>
     void launch_tma_t(gf_context &c, const VT *val, const double *x, double *y,
                       double *dot_partials, const int *st)
@@ -413,7 +701,7 @@ namespace gf
   // number of per-CTA partial sums the fused dot product of launch_spmv writes
   int spmv_dot_partials(const gf_context &c)
   {
-    if (c.n_tiles > 0 && c.spmv_kernel_kind == 0)
+    if (c.n_tiles > 0 && c.spmv_kernel_kind != 1)
       return int(std::min<int64_t>(c.n_tiles, c.sm_count));
     const int64_t want = (c.n_owned_nodes * 32 + SPMV_THREADS - 1) / SPMV_THREADS;
     return int(std::min<int64_t>(want, c.max_red_blocks));
@@ -427,6 +715,25 @@ namespace gf
     if (n_rows == 0)
       return;
     const int *st = dot_partials ? &c.cg_scalars.p->status : nullptr;
+    if (c.n_tiles > 0 && c.spmv_kernel_kind == 2)
+      {
+        if (c.dim == 3)
+          {
+            if (dot_partials)
+              launch_tma2_t<3, true, double>(c, val, x, y, dot_partials, st);
+            else
+              launch_tma2_t<3, false, double>(c, val, x, y, nullptr, nullptr);
+          }
+        else
+          {
+            if (dot_partials)
+              launch_tma2_t<2, true, double>(c, val, x, y, dot_partials, st);
+            else
+              launch_tma2_t<2, false, double>(c, val, x, y, nullptr, nullptr);
+          }
+        GF_CUDA_CHECK(cudaGetLastError());
+        return;
+      }
     if (c.n_tiles > 0 && c.spmv_kernel_kind == 0)
       {
         if (c.dim == 3)
@@ -475,7 +782,14 @@ namespace gf
     const int64_t n_rows = c.n_owned_nodes;
     if (n_rows == 0)
       return;
-    if (c.n_tiles > 0 && c.spmv_kernel_kind == 0)
+    if (c.n_tiles > 0 && c.spmv_kernel_kind == 2)
+      {
+        if (c.dim == 3)
+          launch_tma2_t<3, false, float>(c, val32, x, y, nullptr, nullptr);
+        else
+          launch_tma2_t<2, false, float>(c, val32, x, y, nullptr, nullptr);
+      }
+    else if (c.n_tiles > 0 && c.spmv_kernel_kind == 0)
       {
         if (c.dim == 3)
           launch_tma_t<3, false, float>(c, val32, x, y, nullptr, nullptr);

@@ -129,7 +129,8 @@ extern "C"
                                   2: only the finest-level SpMV launches (two events per launch,
                                   cheap enough for a timed region); launch counters always run */
     GF_OPT_OPERATOR,           /* 0: assembled BSR SpMV ; 1: matrix-free tangent operator in CG */
-    GF_OPT_SPMV_KERNEL,        /* 0: TMA-tiled kernel (default) ; 1: LDG warp-per-row kernel */
+    GF_OPT_SPMV_KERNEL,        /* 0: TMA-tiled kernel (default) ; 1: LDG warp-per-row kernel ;
+                                  2: TMA-tiled kernel with separate value / gather rings */
     GF_OPT_MG_SMOOTHER_DEGREE, /* Chebyshev degree of the pre-/post-smoother (default 3) */
     GF_OPT_MG_COARSE_DEGREE,   /* Chebyshev degree of the coarsest-level solve (default 80) */
     GF_OPT_MG_SMOOTHER_RATIO,  /* smoothers damp the eigenvalues in [lmax/ratio, lmax] (default 40) */

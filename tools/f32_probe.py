@@ -46,13 +46,17 @@ def main():
                 "newton_solves": solves, "cg_iterations": its,
                 "iface_disp_max": float(np.abs(part.written[-1][2]).max())}
 
-    r64 = run(0)
-    r32 = run(1)
-    ms64, b64 = h.spmv_timed(capi.MAT_TANGENT, 20)
-    ms32, b32 = h.spmv_timed(capi.MAT_MG_F32, 20)
-    out.update({"fp64_vcycle": r64, "fp32_vcycle": r32,
-                "spmv_fp64": {"ms": ms64, "bytes": b64, "gbs": b64 / ms64 / 1e6},
-                "spmv_fp32_copy": {"ms": ms32, "bytes": b32, "gbs": b32 / ms32 / 1e6}})
+    kinds = [int(k) for k in os.environ.get("GF_PROBE_KINDS", "0,2").split(",")]
+    for kind in kinds:
+        h.set_option(capi.OPT_SPMV_KERNEL, kind)
+        r64 = run(0)
+        r32 = run(1)
+        ms64, b64 = h.spmv_timed(capi.MAT_TANGENT, 20)
+        ms32, b32 = h.spmv_timed(capi.MAT_MG_F32, 20)
+        out["spmv_kernel_%d" % kind] = {
+            "fp64_vcycle": r64, "fp32_vcycle": r32,
+            "spmv_fp64": {"ms": ms64, "bytes": b64, "gbs": b64 / ms64 / 1e6},
+            "spmv_fp32_copy": {"ms": ms32, "bytes": b32, "gbs": b32 / ms32 / 1e6}}
     print(json.dumps(out))
     H.close()
 
