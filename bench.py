@@ -373,17 +373,20 @@ def main():
                 "cg_iterations": cg_iterations(h0v), "operator_apply_ms": ms32,
                 "operator_bytes_per_apply": bytes32,
                 "operator_gbs": bytes32 / ms32 / 1e6}
-            # the same two arrays through the two-ring SpMV (GF_OPT_SPMV_KERNEL = 2: value ring and
-            # column/x ring decoupled, two tiles gathered concurrently)
-            h.set_option(capi.OPT_SPMV_KERNEL, 2)
-            ms64_2, bytes64 = h.spmv_timed(capi.MAT_TANGENT, 5)
-            ms32_2, _ = h.spmv_timed(capi.MAT_MG_F32, 5)
+            # stand-alone launches of every TMA kernel kind on the FP64 tangent and its FP32 copy
+            # (5: single ring; 2 / 3 / 4: two rings with 8+8 / 8+16 / 4+16 gather+consumer warps;
+            # the default takes 3 for plain launches and 5 for the fused-dot CG vmult)
+            kinds = {}
+            for kind in (5, 2, 3, 4):
+                h.set_option(capi.OPT_SPMV_KERNEL, kind)
+                m64, b64 = h.spmv_timed(capi.MAT_TANGENT, 5)
+                m32, b32 = h.spmv_timed(capi.MAT_MG_F32, 5)
+                kinds[str(kind)] = {"fp64_ms": m64, "fp64_gbs": b64 / m64 / 1e6,
+                                    "fp32_copy_ms": m32, "fp32_copy_gbs": b32 / m32 / 1e6}
             h.set_option(capi.OPT_SPMV_KERNEL, 0)
-            variants["spmv_two_ring_kernel"] = {
-                "what": "stand-alone launches of GF_OPT_SPMV_KERNEL = 2 on the FP64 tangent and on "
-                        "its FP32 copy (bitwise equal results to the default kernel)",
-                "fp64_ms": ms64_2, "fp64_gbs": bytes64 / ms64_2 / 1e6,
-                "fp32_copy_ms": ms32_2, "fp32_copy_gbs": bytes32 / ms32_2 / 1e6}
+            variants["spmv_kernel_kinds"] = dict(
+                kinds, what="GF_OPT_SPMV_KERNEL: stand-alone y = A x launches (no fused dot), "
+                            "bitwise equal results for all kinds")
             h.set_option(capi.OPT_MG_MATRIX_PRECISION, 0)
             for k in range(N_SUB):      # FP64 operators again for the stand-alone SpMV timing
                 resident_pass(k)
@@ -426,8 +429,11 @@ def main():
                     "h2d_bytes_per_step": int(buf.nbytes), "d2h_bytes_per_step": int(buf.nbytes),
                     "ms_per_step": 1e3 * wall_e2e / args.steps, "newton_solves": solves_e2e},
             "gpu_launches": int(prof["kernel_launches"]),
-            "roofline": {"bound": "hbm", "kernel": "spmv_tma_kernel<3> on the finest level (CG vmult with fused dot; "
-                                   "Chebyshev-smoother and residual vmults of the V-cycle)",
+            "roofline": {"bound": "hbm",
+                         "kernel": "finest-level SpMV launches of the timed region: spmv_tma2_kernel<3> "
+                                   "(two rings, 16 consumer warps) for the Chebyshev-smoother and "
+                                   "residual vmults of the V-cycle, spmv_tma_kernel<3> for the CG "
+                                   "vmult with fused dot",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic,
                          "bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_avg_ms,

@@ -269,7 +269,8 @@ struct gf_context
   gf::DevBuf<gf::TileDesc> tile_desc; // [n_tiles]
   gf::DevBuf<uint2>        tile_meta; // [n_tiles*SPMV_META]: per row {val offset, col offset | nb<<16}
   int64_t                  n_tiles = 0; // 0: a row does not fit a tile -> LDG kernel only
-  int                      spmv_kernel_kind = 0; // 0 auto (TMA tiles when available), 1 LDG
+  int                      spmv_kernel_kind = 0; // GF_OPT_SPMV_KERNEL: 0 auto, 1 LDG, 2-4 two-ring
+                                                 // TMA variants, 5 single-ring TMA (spmv.cu)
   gf::BsrMatrix        mat[gf::N_MATRICES];
   gf::DevBuf<double>   mass_blk; // linear: scalar mass value per block (M = m_ab delta_cd)
   gf::DevBuf<double>   dinv;     // [n_owned_nodes*dim*dim] preconditioner blocks

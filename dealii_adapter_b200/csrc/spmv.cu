@@ -360,17 +360,21 @@ namespace gf
     //   same tile, so neither stream throttles the other and the in-order producer cannot deadlock
     //   (everything a waited-for tile needs was issued in an earlier step).
     // ------------------------------------------------------------------------------------------
-    template <int DIM, typename VT>
+    template <int DIM, typename VT, int GW, int GG, int CW>
     struct Tma2Cfg
     {
       using B = TmaCfg<DIM, VT>;
+      static constexpr int GATHER_WARPS = GW; // gather warps in total
+      static constexpr int CONS_WARPS   = CW; // consumer warps
+      static constexpr int THREADS      = (1 + GW + CW) * 32;
       static constexpr int VSTAGES      = sizeof(VT) == 4 ? 4 : 3;
       static constexpr int XSTAGES      = sizeof(VT) == 4 ? 6 : 4;
       static constexpr int LEAD         = XSTAGES - VSTAGES;
       // gather groups = tiles gathered concurrently. Must divide XSTAGES: a group then meets the
       // phases of "its" stages consecutively (a skipped phase would alias in the parity wait)
-      static constexpr int GROUPS       = 2;
-      static_assert(XSTAGES % GROUPS == 0 && TmaCfg<DIM, VT>::GATHER_WARPS % GROUPS == 0, "groups");
+      static constexpr int GROUPS       = GG;
+      static_assert(XSTAGES % GROUPS == 0 && GW % GROUPS == 0, "groups");
+      static_assert(CW <= 32, "the dot-product tail reduces the consumer warps in one warp");
       static constexpr int XSTAGE_BYTES = B::COL_BYTES + B::META_PAD + B::XG_BYTES;
       static constexpr int RING_BYTES   = VSTAGES * B::VAL_BYTES + XSTAGES * XSTAGE_BYTES;
       static constexpr int N_BARS       = 2 * VSTAGES + 3 * XSTAGES;
@@ -378,15 +382,15 @@ namespace gf
       static_assert(SMEM_BYTES + 64 <= 227 * 1024, "shared memory budget");
     };
 
-    template <int DIM, bool DOT, typename VT>
-    __global__ void __launch_bounds__(TmaCfg<DIM, VT>::THREADS, 1)
+    template <int DIM, bool DOT, typename VT, int GW, int GG, int CW>
+    __global__ void __launch_bounds__((1 + GW + CW) * 32, 1)
       spmv_tma2_kernel(const int n_tiles, const TileDesc *__restrict__ tile_desc,
                        const uint2 *__restrict__ tile_meta, const int32_t *__restrict__ bcol,
                        const VT *__restrict__ val, const double *__restrict__ x,
                        double *__restrict__ y, double *__restrict__ partials, const int *status)
     {
       using B = TmaCfg<DIM, VT>;
-      using C = Tma2Cfg<DIM, VT>;
+      using C = Tma2Cfg<DIM, VT, GW, GG, CW>;
       if (status != nullptr && *status != 0)
         return;
       extern __shared__ __align__(128) unsigned char smem[];
@@ -398,20 +402,20 @@ namespace gf
       uint64_t *     cfull  = bars + 2 * C::VSTAGES;              // cols + records  (1 + tx)
       uint64_t *     xfull  = bars + 2 * C::VSTAGES + C::XSTAGES; // x gathered (warps of a group)
       uint64_t *     xempty = bars + 2 * C::VSTAGES + 2 * C::XSTAGES; // consumers done
-      __shared__ double red[B::CONS_WARPS];
+      __shared__ double red[C::CONS_WARPS];
       const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
       if (tid == 0)
         {
           for (int s = 0; s < C::VSTAGES; ++s)
             {
               mbar_init(smem_u32(&vfull[s]), 1);
-              mbar_init(smem_u32(&vempty[s]), B::CONS_WARPS);
+              mbar_init(smem_u32(&vempty[s]), C::CONS_WARPS);
             }
           for (int s = 0; s < C::XSTAGES; ++s)
             {
               mbar_init(smem_u32(&cfull[s]), 1);
-              mbar_init(smem_u32(&xfull[s]), B::GATHER_WARPS / C::GROUPS);
-              mbar_init(smem_u32(&xempty[s]), B::CONS_WARPS);
+              mbar_init(smem_u32(&xfull[s]), C::GATHER_WARPS / C::GROUPS);
+              mbar_init(smem_u32(&xempty[s]), C::CONS_WARPS);
             }
           asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -481,17 +485,17 @@ namespace gf
                 }
             }
         }
-      else if (warp <= B::GATHER_WARPS)
+      else if (warp <= C::GATHER_WARPS)
         {
           // ---------------- gather warps: x[col] -> shared --------------------------------------
           // The gather of one tile is ONE round trip to L2 (~1 us under the streaming load), so
           // tiles must overlap: GROUPS groups of warps work on consecutive tiles concurrently, and
           // a lane issues ALL loads of its blocks (UB blocks, fully unrolled) before the first
           // store, so a tile costs a group exactly one round trip.
-          constexpr int GL = B::GATHER_WARPS * 32 / C::GROUPS; // lanes per group
+          constexpr int GL = C::GATHER_WARPS * 32 / C::GROUPS; // lanes per group
           constexpr int UB = (B::TILE_C + GL - 1) / GL;        // blocks per lane and tile
-          const int     grp = (warp - 1) / (B::GATHER_WARPS / C::GROUPS);
-          const int     g   = ((warp - 1) % (B::GATHER_WARPS / C::GROUPS)) * 32 + lane;
+          const int     grp = (warp - 1) / (C::GATHER_WARPS / C::GROUPS);
+          const int     g   = ((warp - 1) % (C::GATHER_WARPS / C::GROUPS)) * 32 + lane;
           for (int k = grp; k < n_my; k += C::GROUPS)
             {
               const int sx = k % C::XSTAGES;
@@ -531,7 +535,7 @@ namespace gf
       else
         {
           // ------------------------------ consumer warps: shared-memory FMA --------------------
-          const int cw = warp - 1 - B::GATHER_WARPS;
+          const int cw = warp - 1 - C::GATHER_WARPS;
           for (int k = 0; k < n_my; ++k)
             {
               const int sv = k % C::VSTAGES, sx = k % C::XSTAGES;
@@ -548,7 +552,7 @@ namespace gf
               const uint2 hdr    = smeta[SPMV_TILE_ROWS];
               const int   row0   = int(hdr.x);
               const int   n_rows = int(hdr.y);
-              for (int row = cw; row < n_rows; row += B::CONS_WARPS)
+              for (int row = cw; row < n_rows; row += C::CONS_WARPS)
                 {
                   const uint2   m      = smeta[row];
                   const int     ne     = int(m.y >> 16) * DIM;
@@ -601,14 +605,14 @@ namespace gf
         }
       if (DOT)
         {
-          const int cw = warp - 1 - B::GATHER_WARPS;
+          const int cw = warp - 1 - C::GATHER_WARPS;
           dot          = warp_sum(dot);
           if (lane == 0 && cw >= 0)
             red[cw] = dot;
           __syncthreads();
           if (tid < 32)
             {
-              double v = tid < B::CONS_WARPS ? red[tid] : 0.0;
+              double v = tid < C::CONS_WARPS ? red[tid] : 0.0;
               v        = warp_sum(v);
               if (tid == 0)
                 partials[blockIdx.x] = v;
@@ -616,22 +620,50 @@ namespace gf
         }
     }
 
-    template <int DIM, bool DOT, typename VT>
-    void launch_tma2_t(gf_context &c, const VT *val, const double *x, double *y,
+    template <int DIM, bool DOT, typename VT, int GW, int GG, int CW>
+    void launch_tma2_w(gf_context &c, const VT *val, const double *x, double *y,
                        double *dot_partials, const int *st)
     {
-      using C = Tma2Cfg<DIM, VT>;
+      using C = Tma2Cfg<DIM, VT, GW, GG, CW>;
       static bool configured = false;
       if (!configured)
         {
-          GF_CUDA_CHECK(cudaFuncSetAttribute(spmv_tma2_kernel<DIM, DOT, VT>,
+          GF_CUDA_CHECK(cudaFuncSetAttribute(spmv_tma2_kernel<DIM, DOT, VT, GW, GG, CW>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              C::SMEM_BYTES));
           configured = true;
         }
       const int grid = int(std::min<int64_t>(c.n_tiles, c.sm_count));
-      spmv_tma2_kernel<DIM, DOT, VT><<<grid, TmaCfg<DIM, VT>::THREADS, C::SMEM_BYTES, c.stream>>>(
+      spmv_tma2_kernel<DIM, DOT, VT, GW, GG, CW><<<grid, C::THREADS, C::SMEM_BYTES, c.stream>>>(
         int(c.n_tiles), c.tile_desc.p, c.tile_meta.p, c.bcol.p, val, x, y, dot_partials, st);
+    }
+    // warp split of the two-ring kernel by GF_OPT_SPMV_KERNEL:
+    //   2: 8 gather warps in 2 groups + 8 consumer warps (the split of the single-ring kernel)
+    //   3: 8 gather warps in 2 groups + 16 consumer warps   } ncu (profiles/r01_spmv_variants_ncu.md):
+    //   4: 4 gather warps in 1 group  + 16 consumer warps   } the 8 consumer warps are the busy role
+    template <int DIM, bool DOT, typename VT>
+    void launch_tma2_t(gf_context &c, int kind, const VT *val, const double *x, double *y,
+                       double *dot_partials, const int *st)
+    {
+      if (kind == 3)
+        launch_tma2_w<DIM, DOT, VT, 8, 2, 16>(c, val, x, y, dot_partials, st);
+      else if (kind == 4)
+        launch_tma2_w<DIM, DOT, VT, 4, 1, 16>(c, val, x, y, dot_partials, st);
+      else
+        launch_tma2_w<DIM, DOT, VT, 8, 2, 8>(c, val, x, y, dot_partials, st);
+    }
+
+    // GF_OPT_SPMV_KERNEL = 0 (default) picks per launch type what has been MEASURED on the B200
+    // (profiles/r01_spmv_kernel_kinds.jsonl): plain y = A x launches (smoother / residual
+    // applications of the V-cycle, assemble_rhs vmults: 6 of 7 launches per CG iteration) take
+    // the two-ring kernel with 16 consumer warps (0.549 ms = 6.05 TB/s on the cfg3 tangent,
+    // bitwise equal y); launches with the fused dot product (the CG vmult) stay on the
+    // single-ring kernel until the 16-warp dot variant has run on hardware.
+    int effective_kind(const gf_context &c, bool fused_dot)
+    {
+      if (c.spmv_kernel_kind == 0)
+        return fused_dot ? 5 : 3;
+      return c.spmv_kernel_kind;
     }
 
     template <int DIM, bool DOT, typename VT>
@@ -714,27 +746,28 @@ namespace gf
     const int64_t n_rows = c.n_owned_nodes;
     if (n_rows == 0)
       return;
-    const int *st = dot_partials ? &c.cg_scalars.p->status : nullptr;
-    if (c.n_tiles > 0 && c.spmv_kernel_kind == 2)
+    const int *st   = dot_partials ? &c.cg_scalars.p->status : nullptr;
+    const int  kind = effective_kind(c, dot_partials != nullptr);
+    if (c.n_tiles > 0 && kind >= 2 && kind <= 4)
       {
         if (c.dim == 3)
           {
             if (dot_partials)
-              launch_tma2_t<3, true, double>(c, val, x, y, dot_partials, st);
+              launch_tma2_t<3, true, double>(c, kind, val, x, y, dot_partials, st);
             else
-              launch_tma2_t<3, false, double>(c, val, x, y, nullptr, nullptr);
+              launch_tma2_t<3, false, double>(c, kind, val, x, y, nullptr, nullptr);
           }
         else
           {
             if (dot_partials)
-              launch_tma2_t<2, true, double>(c, val, x, y, dot_partials, st);
+              launch_tma2_t<2, true, double>(c, kind, val, x, y, dot_partials, st);
             else
-              launch_tma2_t<2, false, double>(c, val, x, y, nullptr, nullptr);
+              launch_tma2_t<2, false, double>(c, kind, val, x, y, nullptr, nullptr);
           }
         GF_CUDA_CHECK(cudaGetLastError());
         return;
       }
-    if (c.n_tiles > 0 && c.spmv_kernel_kind == 0)
+    if (c.n_tiles > 0 && kind == 5)
       {
         if (c.dim == 3)
           {
@@ -782,14 +815,15 @@ namespace gf
     const int64_t n_rows = c.n_owned_nodes;
     if (n_rows == 0)
       return;
-    if (c.n_tiles > 0 && c.spmv_kernel_kind == 2)
+    const int kind = effective_kind(c, false);
+    if (c.n_tiles > 0 && kind >= 2 && kind <= 4)
       {
         if (c.dim == 3)
-          launch_tma2_t<3, false, float>(c, val32, x, y, nullptr, nullptr);
+          launch_tma2_t<3, false, float>(c, kind, val32, x, y, nullptr, nullptr);
         else
-          launch_tma2_t<2, false, float>(c, val32, x, y, nullptr, nullptr);
+          launch_tma2_t<2, false, float>(c, kind, val32, x, y, nullptr, nullptr);
       }
-    else if (c.n_tiles > 0 && c.spmv_kernel_kind == 0)
+    else if (c.n_tiles > 0 && kind == 5)
       {
         if (c.dim == 3)
           launch_tma_t<3, false, float>(c, val32, x, y, nullptr, nullptr);

@@ -129,8 +129,14 @@ extern "C"
                                   2: only the finest-level SpMV launches (two events per launch,
                                   cheap enough for a timed region); launch counters always run */
     GF_OPT_OPERATOR,           /* 0: assembled BSR SpMV ; 1: matrix-free tangent operator in CG */
-    GF_OPT_SPMV_KERNEL,        /* 0: TMA-tiled kernel (default) ; 1: LDG warp-per-row kernel ;
-                                  2: TMA-tiled kernel with separate value / gather rings */
+    GF_OPT_SPMV_KERNEL,        /* all kinds give bitwise identical y = A x (same per-row summation order):
+                                  0 (default): per launch type the fastest kernel verified on the
+                                     B200 - two-ring TMA kernel with 16 consumer warps for plain
+                                     y = A x, single-ring TMA kernel for the fused-dot CG vmult;
+                                  1: LDG warp-per-row kernel;
+                                  2 / 3 / 4: two-ring TMA kernel (value ring decoupled from the
+                                     column/x ring) with 8+8 / 8+16 / 4+16 gather+consumer warps,
+                                     for every launch; 5: single-ring TMA kernel for every launch */
     GF_OPT_MG_SMOOTHER_DEGREE, /* Chebyshev degree of the pre-/post-smoother (default 3) */
     GF_OPT_MG_COARSE_DEGREE,   /* Chebyshev degree of the coarsest-level solve (default 80) */
     GF_OPT_MG_SMOOTHER_RATIO,  /* smoothers damp the eigenvalues in [lmax/ratio, lmax] (default 40) */
