@@ -79,8 +79,8 @@ def build_cuda(force=False):
 
 def build_host(force=False):
     """Mesh/DoF scaffolding only (no CUDA dependency): used by the Python binding, tests, oracle."""
-    srcs = [os.path.join(HOST, "structured_mesh.cc")]
-    deps = srcs + [os.path.join(HOST, "structured_mesh.h")]
+    srcs = [os.path.join(HOST, "structured_mesh.cc"), os.path.join(HOST, "vtk_output.cc")]
+    deps = srcs + [os.path.join(HOST, "structured_mesh.h"), os.path.join(HOST, "vtk_output.h")]
     if force or _newer(LIB_HOST, deps):
         _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", HOST,
               "-o", LIB_HOST] + srcs)

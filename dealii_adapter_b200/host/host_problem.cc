@@ -1,8 +1,12 @@
 #include "host_problem.h"
 
+#include <cstdio>
 #include <cstdlib>
+#include <iostream>
 #include <stdexcept>
 #include <string>
+
+#include "vtk_output.h"
 
 namespace gfh
 {
@@ -131,6 +135,36 @@ namespace gfh
         gf_set_option(handle, GF_OPT_PRECONDITIONER, GF_PRECOND_MULTIGRID) != GF_OK)
       throw std::runtime_error(gf_last_error(handle));
     return 1 + int(coarse_levels.size());
+  }
+
+  void HostProblem::output_results(int which_vector, const std::string &folder,
+                                   unsigned index) const
+  {
+    const int dim = mesh->dim, p = mesh->degree, nf = dim + dim * dim;
+    std::vector<double> fields(size_t(mesh->n_cells) * mesh->nodes_per_cell * nf);
+    if (gf_postprocess(handle, which_vector, fields.data()) != GF_OK)
+      throw std::runtime_error(gf_last_error(handle));
+    // DataOut::curved_boundary: only cells at the boundary take their inner patch points from
+    // the (Eulerian) mapping
+    std::vector<uint8_t> at_boundary(size_t(mesh->n_cells), 0);
+    const int            rz = dim == 3 ? mesh->reps[2] : 1;
+    for (int k = 0; k < rz; ++k)
+      for (int j = 0; j < mesh->reps[1]; ++j)
+        for (int i = 0; i < mesh->reps[0]; ++i)
+          at_boundary[size_t(mesh->cell_index(i, j, k))] =
+            (i == 0 || i == mesh->reps[0] - 1 || j == 0 || j == mesh->reps[1] - 1 ||
+             (dim == 3 && (k == 0 || k == rz - 1))) ?
+              1 :
+              0;
+    std::vector<double> points;
+    patch_points(dim, p, mesh->n_cells, mesh->cell_vertices.data(), fields.data(),
+                 at_boundary.data(), points);
+    char name[32];
+    std::snprintf(name, sizeof name, "solution-%03u.vtk", index); // Utilities::int_to_string(n, 3)
+    const std::string path = (folder.empty() ? std::string(".") : folder) + "/" + name;
+    if (!write_vtk(path, dim, p, mesh->n_cells, points.data(), fields.data()))
+      throw std::runtime_error("cannot write " + path);
+    std::cout << "\t Output written to " << name << " \n" << std::endl;
   }
 
   HostProblem::~HostProblem()

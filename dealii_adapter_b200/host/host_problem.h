@@ -33,6 +33,10 @@ namespace gfh
     // block-jacobi. Returns the number of levels in use.
     int create_multigrid(const Parameters::AllParameters &prm, int dim, int model);
     std::vector<std::unique_ptr<HostProblem>> coarse_levels;
+    // output_results (nonlinear_elasticity.cc:1215-1254, linear_elasticity.cc:590-629): patch
+    // fields from the device (gf_postprocess), points + VTK file on the host (vtk_output.h).
+    // Writes <folder>/solution-<index, 3 digits>.vtk and prints the reference's message.
+    void output_results(int which_vector, const std::string &folder, unsigned index) const;
     ~HostProblem();
   };
 } // namespace gfh

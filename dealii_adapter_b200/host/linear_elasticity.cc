@@ -99,7 +99,11 @@ namespace Linear_Elasticity
 
   template <int dim>
   void ElastoDynamics<dim>::output_results() const
-  {} // VTK output stays with deal.II's DataOut (:590-629): out of scope
+  {
+    // DataOut + Postprocessor on the displaced grid (:590-629), file index as in :616-619
+    host.output_results(GF_LIN_DISPLACEMENT, parameters.output_folder,
+                        time.get_timestep() / parameters.output_interval);
+  }
 
   template <int dim>
   void ElastoDynamics<dim>::run()

@@ -194,8 +194,10 @@ namespace Nonlinear_Elasticity
   template <int dim, typename NumberType>
   void Solid<dim, NumberType>::output_results() const
   {
-    // VTK output (DataOut + Postprocessor, :1215-1254) is host/deal.II territory and out of scope;
-    // the displacement is available through gf_get_vector(GF_NL_TOTAL_DISPLACEMENT) at output steps.
+    // DataOut + Postprocessor on the displaced grid (:1215-1254): patch fields on the device, file
+    // on the host; file index as in :1240-1243
+    host.output_results(GF_NL_TOTAL_DISPLACEMENT, parameters.output_folder,
+                        time.get_timestep() / parameters.output_interval);
   }
 
   template <int dim, typename NumberType>

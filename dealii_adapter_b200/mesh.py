@@ -50,6 +50,11 @@ def host_lib():
         lib.gfh_partition_size.argtypes = [C.c_void_p, C.c_int]
         lib.gfh_partition_array.restype = C.c_void_p
         lib.gfh_partition_array.argtypes = [C.c_void_p, C.c_int]
+        lib.gfh_write_vtk.restype = C.c_int
+        lib.gfh_write_vtk.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]
+        lib.gfh_vtk_point_index_from_ijk.restype = C.c_int
+        lib.gfh_vtk_point_index_from_ijk.argtypes = [C.c_int] * 6
         _lib = lib
     return _lib
 
@@ -110,6 +115,28 @@ class StructuredMesh:
         if getattr(self, "_h", None):
             host_lib().gfh_mesh_destroy(self._h)
             self._h = None
+
+    def cells_at_boundary(self):
+        """uint8 [n_cells]: 1 for cells with a face on the boundary (DataOut::curved_boundary)."""
+        r = list(self.reps) + [1] * (3 - self.dim)
+        k, j, i = np.meshgrid(np.arange(r[2]), np.arange(r[1]), np.arange(r[0]), indexing="ij")
+        at = (i == 0) | (i == r[0] - 1) | (j == 0) | (j == r[1] - 1)
+        if self.dim == 3:
+            at |= (k == 0) | (k == r[2] - 1)
+        return np.ascontiguousarray(at.reshape(-1), dtype=np.uint8)
+
+    def write_vtk(self, filename, fields, curved_boundary=True):
+        """solution-*.vtk as output_results writes it (nonlinear_elasticity.cc:1215-1254): `fields`
+        is the [n_cells, npts, dim + dim*dim] array of gf_postprocess; the C++ host writer
+        (host/vtk_output.cc) builds the displaced patch points and the file."""
+        f = np.ascontiguousarray(fields, dtype=np.float64)
+        v = np.ascontiguousarray(self.cell_vertices, dtype=np.float64)
+        at = self.cells_at_boundary() if curved_boundary else None
+        rc = host_lib().gfh_write_vtk(str(filename).encode(), self.dim, self.degree, self.n_cells,
+                                      v.ctypes.data, f.ctypes.data,
+                                      at.ctypes.data if at is not None else None)
+        if rc != 0:
+            raise IOError("cannot write %s" % filename)
 
     def boundary_dof_mask(self, face_mask, comp_mask, mask=None):
         if mask is None:

@@ -19,6 +19,7 @@ class SolverParameters:
     end_time: float = 1.0
     delta_t: float = 0.1
     output_interval: int = 1
+    output_folder: str = ""        # "Output folder"; empty: the Python mirror writes no VTK files
     # System properties
     nu: float = 0.3
     mu: float = 1538462.0

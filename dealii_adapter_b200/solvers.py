@@ -228,10 +228,27 @@ class Solid:
         a.advance(t.get_delta_t())
         a.reload_old_state_if_required(t)
 
+    def output_results(self):  # :1215-1254
+        """solution-<n>.vtk in parameters.output_folder (skipped when no folder is configured):
+        patch fields from the device (gf_postprocess), points and file by the C++ host writer."""
+        folder = getattr(self.parameters, "output_folder", "")
+        if not folder:
+            return None
+        import os
+        os.makedirs(folder, exist_ok=True)
+        name = os.path.join(folder, "solution-%03d.vtk"
+                            % (self.time.get_timestep() // self.parameters.output_interval))
+        self.problem.mesh.write_vtk(name, self.handle.postprocess(capi.NL_TOTAL_DISPLACEMENT))
+        return name
+
     def run(self):  # :99-167
+        self.output_results()  # :103
         self.adapter.initialize(self.problem)
         while self.adapter.precice.isCouplingOngoing():
             self.step()
+            if self.adapter.precice.isTimeWindowComplete() and \
+                    self.time.get_timestep() % self.parameters.output_interval == 0:  # :150-153
+                self.output_results()
         self.adapter.precice.finalize()
 
 
@@ -260,9 +277,24 @@ class ElastoDynamics:
         a.advance(t.get_delta_t())
         a.reload_old_state_if_required(t)
 
+    def output_results(self):  # :590-629
+        folder = getattr(self.parameters, "output_folder", "")
+        if not folder:
+            return None
+        import os
+        os.makedirs(folder, exist_ok=True)
+        name = os.path.join(folder, "solution-%03d.vtk"
+                            % (self.time.get_timestep() // self.parameters.output_interval))
+        self.problem.mesh.write_vtk(name, self.handle.postprocess(capi.LIN_DISPLACEMENT))
+        return name
+
     def run(self):  # :634-716
+        self.output_results()  # :640
         self.handle.lin_assemble_once()  # assemble_system :642
         self.adapter.initialize(self.problem)
         while self.adapter.precice.isCouplingOngoing():
             self.step()
+            if self.adapter.precice.isTimeWindowComplete() and \
+                    self.time.get_timestep() % self.parameters.output_interval == 0:  # :699-702
+                self.output_results()
         self.adapter.precice.finalize()

@@ -74,6 +74,11 @@ def test_coupled_nonlinear_run_matches_oracle_watchpoint(exes, tmp_path, native_
     r = run(exes[0], tmp_path)
     assert r.returncode == 0, r.stderr + r.stdout[-2000:]
     assert "CONVERGED!" in r.stdout and "LIN_IT" in r.stdout
+    # output_results before the first step (:103): DataOut patches on the (still undisplaced) grid,
+    # one Lagrange quadrilateral of order 2 per cell, 18 x 3 cells
+    assert "Output written to solution-000.vtk" in r.stdout
+    vtk = (tmp_path / "dealii-output" / "solution-000.vtk").read_text()
+    assert "POINTS %d double" % (54 * 9) in vtk and "SCALARS strain_xy double 1" in vtk
     log = np.loadtxt(tmp_path / "watchpoint.log")
     assert log.shape == (4, 6)
     # oracle: same scenario (FSI3 2D Q2 18x3 cells), Direct stand-in, ramped traction
