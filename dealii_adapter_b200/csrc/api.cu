@@ -456,8 +456,8 @@ extern "C"
               l->mg_smoother_ratio = double(value);
             break;
           case GF_OPT_MG_MATRIX_PRECISION:
-            GF_REQUIRE(value == 0 || value == 1, GF_ERR_INVALID_ARG,
-                       "matrix precision of the V-cycle: 0 (FP64) or 1 (FP32 copy)");
+            GF_REQUIRE(value >= 0 && value <= 2, GF_ERR_INVALID_ARG,
+                       "matrix precision of the V-cycle: 0 (FP64), 1 (FP32 copy) or 2 (all FP32)");
             for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
               {
                 l->mg_matrix_precision = int(value);
@@ -467,7 +467,7 @@ extern "C"
                     l->mg_val32.release();
                   }
               }
-            if (value == 1)
+            if (value != 0)
               gf::mg_refresh_f32(c); // operators that are already assembled; else at assembly
             break;
           default:
@@ -918,7 +918,11 @@ extern "C"
         {
           GF_REQUIRE(c.mg_val32_valid, GF_ERR_INVALID_ARG,
                      "no FP32 operator copy (GF_OPT_MG_MATRIX_PRECISION = 1, then assemble)");
-          gf::launch_spmv_f32(c, c.mg_val32.p, x, y);
+          // the kernel the V-cycle would launch at the current GF_OPT_MG_MATRIX_PRECISION
+          if (c.mg_matrix_precision == 2)
+            gf::launch_spmv_f32x(c, c.mg_val32.p, x, y);
+          else
+            gf::launch_spmv_f32(c, c.mg_val32.p, x, y);
         }
       else if (which_matrix == GF_MAT_TANGENT)
         gf::op_apply(c, mat_ptr(c, which_matrix), x, y, nullptr); // assembled or matrix-free
@@ -946,7 +950,9 @@ extern "C"
       c.prof.enabled  = false;
       const bool tangent = which_matrix == GF_MAT_TANGENT;
       auto       apply   = [&]() {
-        if (f32)
+        if (f32 && c.mg_matrix_precision == 2)
+          gf::launch_spmv_f32x(c, c.mg_val32.p, x, y);
+        else if (f32)
           gf::launch_spmv_f32(c, c.mg_val32.p, x, y);
         else if (tangent)
           gf::op_apply(c, A, x, y, nullptr);

@@ -332,7 +332,8 @@ struct gf_context
   gf::DevBuf<double> mg_e_saved;     // checkpoint copy of mg_e (gf_state_save / gf_state_restore)
   bool               mg_e_saved_valid = false;
   // FP32 copy of this level's operator for the V-cycle (GF_OPT_MG_MATRIX_PRECISION = 1)
-  int                mg_matrix_precision = 0; // 0: FP64 values, 1: FP32 copy inside the V-cycle
+  int                mg_matrix_precision = 0; // 0: FP64 values; 1: FP32 copy inside the V-cycle;
+                                              // 2: FP32 copy, x staged / accumulated in FP32 too
   gf::DevBuf<float>  mg_val32;                // [n_val + 4]
   bool               mg_val32_valid = false;
   int                mg_smoother_degree = 3, mg_coarse_degree = 80;
@@ -377,6 +378,7 @@ namespace gf
   void launch_spmv(gf_context &c, const double *val, const double *x, double *y,
                    double *dot_partials);
   void launch_spmv_f32(gf_context &c, const float *val32, const double *x, double *y);
+  void launch_spmv_f32x(gf_context &c, const float *val32, const double *x, double *y);
   void launch_convert_f32(gf_context &c, const double *val, float *val32);
   void launch_spmv_mass(gf_context &c, const double *x, double *y);
   double spmv_bytes(const gf_context &c);

@@ -325,7 +325,9 @@ namespace gf
     {
       if (c.comm)
         halo_exchange(c, x);
-      if (c.mg_matrix_precision == 1 && c.mg_val32_valid && level_is_assembled(c))
+      if (c.mg_matrix_precision == 2 && c.mg_val32_valid && level_is_assembled(c))
+        launch_spmv_f32x(c, c.mg_val32.p, x, y);
+      else if (c.mg_matrix_precision == 1 && c.mg_val32_valid && level_is_assembled(c))
         launch_spmv_f32(c, c.mg_val32.p, x, y);
       else
         op_apply(c, level_matrix(c), x, y, nullptr);
@@ -510,7 +512,7 @@ namespace gf
     for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
       {
         l->mg_val32_valid = false;
-        if (l->mg_matrix_precision != 1 || !level_is_assembled(*l))
+        if (l->mg_matrix_precision == 0 || !level_is_assembled(*l))
           continue;
         const double *A = level_matrix(*l);
         if (A == nullptr || l->n_val == 0)

@@ -382,7 +382,10 @@ namespace gf
       static_assert(SMEM_BYTES + 64 <= 227 * 1024, "shared memory budget");
     };
 
-    template <int DIM, bool DOT, typename VT, int GW, int GG, int CW>
+    // XT = type of the staged x values and of the accumulators: double everywhere except the
+    // all-single-precision operator of the V-cycle (GF_OPT_MG_MATRIX_PRECISION = 2: VT = XT = float,
+    // FFMA with two accumulators per scalar row; y is written back as double)
+    template <int DIM, bool DOT, typename VT, typename XT, int GW, int GG, int CW>
     __global__ void __launch_bounds__((1 + GW + CW) * 32, 1)
       spmv_tma2_kernel(const int n_tiles, const TileDesc *__restrict__ tile_desc,
                        const uint2 *__restrict__ tile_meta, const int32_t *__restrict__ bcol,
@@ -391,6 +394,8 @@ namespace gf
     {
       using B = TmaCfg<DIM, VT>;
       using C = Tma2Cfg<DIM, VT, GW, GG, CW>;
+      static_assert(sizeof(XT) == 8 || (sizeof(VT) == 4 && !DOT),
+                    "single-precision x staging only with the FP32 copy and without the fused dot");
       if (status != nullptr && *status != 0)
         return;
       extern __shared__ __align__(128) unsigned char smem[];
@@ -503,7 +508,7 @@ namespace gf
               unsigned char *stage = xring + sx * C::XSTAGE_BYTES;
               const int32_t *scol  = reinterpret_cast<const int32_t *>(stage);
               const uint2 *  smeta = reinterpret_cast<const uint2 *>(stage + B::COL_BYTES);
-              double *       sxv = reinterpret_cast<double *>(stage + B::COL_BYTES + B::META_PAD);
+              XT *           sxv = reinterpret_cast<XT *>(stage + B::COL_BYTES + B::META_PAD);
               const int      nblk = int(smeta[SPMV_TILE_ROWS + 1].x);
               double         r[UB][DIM];
 #pragma unroll
@@ -525,7 +530,7 @@ namespace gf
                   if (j < nblk)
 #pragma unroll
                     for (int d0 = 0; d0 < DIM; ++d0)
-                      sxv[j * DIM + d0] = r[u][d0];
+                      sxv[j * DIM + d0] = XT(r[u][d0]);
                 }
               __syncwarp();
               if (lane == 0)
@@ -547,8 +552,7 @@ namespace gf
               const uint2 *        smeta = reinterpret_cast<const uint2 *>(xs + B::COL_BYTES);
               const VT *sval = reinterpret_cast<const VT *>(vring + sv * B::VAL_BYTES) +
                                (sizeof(VT) == 4 ? int(smeta[SPMV_TILE_ROWS + 1].y) : 0);
-              const double *sxv =
-                reinterpret_cast<const double *>(xs + B::COL_BYTES + B::META_PAD);
+              const XT *sxv = reinterpret_cast<const XT *>(xs + B::COL_BYTES + B::META_PAD);
               const uint2 hdr    = smeta[SPMV_TILE_ROWS];
               const int   row0   = int(hdr.x);
               const int   n_rows = int(hdr.y);
@@ -558,8 +562,50 @@ namespace gf
                   const int     ne     = int(m.y >> 16) * DIM;
                   const int     stride = (ne + 1) & ~1;
                   const VT *    v      = sval + m.x;
-                  const double *xr     = sxv + int(m.y & 0xffffu) * DIM;
+                  const XT *    xr     = sxv + int(m.y & 0xffffu) * DIM;
                   const int64_t i      = int64_t(row0 + row) * DIM + lane;
+                  if constexpr (sizeof(XT) == 4)
+                    {
+                      // all-FP32 row: values, x and accumulation in single precision; the .x and
+                      // .y products go to separate accumulators (two independent FFMA chains)
+                      float a0[DIM], a1[DIM];
+#pragma unroll
+                      for (int r = 0; r < DIM; ++r)
+                        a0[r] = a1[r] = 0.f;
+#pragma unroll 3
+                      for (int e = 2 * lane; e < ne; e += 64)
+                        {
+                          const float x0 = xr[e];
+                          const float x1 = (e + 1 < ne) ? xr[e + 1] : 0.f;
+#pragma unroll
+                          for (int r = 0; r < DIM; ++r)
+                            {
+                              const float2 vv =
+                                *reinterpret_cast<const float2 *>(v + r * stride + e);
+                              a0[r] = fmaf(vv.x, x0, a0[r]);
+                              a1[r] = fmaf(vv.y, x1, a1[r]);
+                            }
+                        }
+#pragma unroll
+                      for (int r = 0; r < DIM; ++r)
+                        {
+                          float t = a0[r] + a1[r];
+#pragma unroll
+                          for (int o = 16; o > 0; o >>= 1)
+                            t += __shfl_xor_sync(0xffffffffu, t, o);
+                          a0[r] = t;
+                        }
+                      if (lane < DIM)
+                        {
+                          float yr = a0[0];
+#pragma unroll
+                          for (int r = 1; r < DIM; ++r)
+                            if (lane == r)
+                              yr = a0[r];
+                          y[i] = double(yr);
+                        }
+                      continue;
+                    }
                   double        xi     = 0.0;
                   if (DOT && lane < DIM)
                     xi = __ldg(x + i);
@@ -620,7 +666,7 @@ namespace gf
         }
     }
 
-    template <int DIM, bool DOT, typename VT, int GW, int GG, int CW>
+    template <int DIM, bool DOT, typename VT, typename XT, int GW, int GG, int CW>
     void launch_tma2_w(gf_context &c, const VT *val, const double *x, double *y,
                        double *dot_partials, const int *st)
     {
@@ -628,13 +674,13 @@ namespace gf
       static bool configured = false;
       if (!configured)
         {
-          GF_CUDA_CHECK(cudaFuncSetAttribute(spmv_tma2_kernel<DIM, DOT, VT, GW, GG, CW>,
+          GF_CUDA_CHECK(cudaFuncSetAttribute(spmv_tma2_kernel<DIM, DOT, VT, XT, GW, GG, CW>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              C::SMEM_BYTES));
           configured = true;
         }
       const int grid = int(std::min<int64_t>(c.n_tiles, c.sm_count));
-      spmv_tma2_kernel<DIM, DOT, VT, GW, GG, CW><<<grid, C::THREADS, C::SMEM_BYTES, c.stream>>>(
+      spmv_tma2_kernel<DIM, DOT, VT, XT, GW, GG, CW><<<grid, C::THREADS, C::SMEM_BYTES, c.stream>>>(
         int(c.n_tiles), c.tile_desc.p, c.tile_meta.p, c.bcol.p, val, x, y, dot_partials, st);
     }
     // warp split of the two-ring kernel by GF_OPT_SPMV_KERNEL:
@@ -646,11 +692,11 @@ namespace gf
                        double *dot_partials, const int *st)
     {
       if (kind == 3)
-        launch_tma2_w<DIM, DOT, VT, 8, 2, 16>(c, val, x, y, dot_partials, st);
+        launch_tma2_w<DIM, DOT, VT, double, 8, 2, 16>(c, val, x, y, dot_partials, st);
       else if (kind == 4)
-        launch_tma2_w<DIM, DOT, VT, 4, 1, 16>(c, val, x, y, dot_partials, st);
+        launch_tma2_w<DIM, DOT, VT, double, 4, 1, 16>(c, val, x, y, dot_partials, st);
       else
-        launch_tma2_w<DIM, DOT, VT, 8, 2, 8>(c, val, x, y, dot_partials, st);
+        launch_tma2_w<DIM, DOT, VT, double, 8, 2, 8>(c, val, x, y, dot_partials, st);
     }
 
     // GF_OPT_SPMV_KERNEL = 0 (default) picks per launch type what has been MEASURED on the B200
@@ -840,6 +886,23 @@ namespace gf
           spmv_kernel<2, false, float><<<grid, SPMV_THREADS, 0, c.stream>>>(
             n_rows, c.brow_ptr.p, c.val_ptr.p, c.bcol.p, val32, x, y, nullptr, nullptr);
       }
+    GF_CUDA_CHECK(cudaGetLastError());
+  }
+
+  // y = A32 x with x staged and accumulated in FP32 as well (GF_OPT_MG_MATRIX_PRECISION = 2);
+  // matrices without tiles fall back to the FP32-value / FP64-accumulate kernels
+  void launch_spmv_f32x(gf_context &c, const float *val32, const double *x, double *y)
+  {
+    if (c.n_tiles == 0 || c.spmv_kernel_kind == 1 || c.n_owned_nodes == 0)
+      {
+        launch_spmv_f32(c, val32, x, y);
+        return;
+      }
+    ProfScope ps(c, c.mg_level > 0 ? Profile::MG_SPMV : Profile::SPMV);
+    if (c.dim == 3)
+      launch_tma2_w<3, false, float, float, 8, 2, 16>(c, val32, x, y, nullptr, nullptr);
+    else
+      launch_tma2_w<2, false, float, float, 8, 2, 16>(c, val32, x, y, nullptr, nullptr);
     GF_CUDA_CHECK(cudaGetLastError());
   }
 

@@ -142,10 +142,12 @@ extern "C"
     GF_OPT_MG_SMOOTHER_RATIO,  /* smoothers damp the eigenvalues in [lmax/ratio, lmax] (default 40) */
     GF_OPT_MG_MATRIX_PRECISION /* 0 (default): the V-cycle streams the FP64 level matrices;
                                   1: it streams FP32 copies of them (half the HBM bytes per smoother
-                                  / residual application). Vectors, accumulation and the outer CG
-                                  (operator, residual, tolerance: nonlinear:1171-1187,
-                                  linear:540-552) stay FP64, so the solve converges to the same
-                                  tolerance; only the SSOR replacement changes. */
+                                  / residual application), accumulating in FP64;
+                                  2 (experimental, not yet run on hardware): FP32 copies, x staged
+                                  and accumulated in FP32 as well (vectors stay FP64 in HBM).
+                                  The outer CG (operator, residual, tolerance: nonlinear:1171-1187,
+                                  linear:540-552) stays FP64 in every case, so the solve converges
+                                  to the same tolerance; only the SSOR replacement changes. */
   };
 
   /* device-time breakdown accumulated while GF_OPT_PROFILE = 1 (CUDA events on the library's

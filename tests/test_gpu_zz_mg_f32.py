@@ -142,3 +142,61 @@ def test_f32_vcycle_linear_model(libs):
     assert all(res <= 1e-10 for it, res in out[1][0])
     assert all(abs(a[0] - b[0]) <= 1 for a, b in zip(out[1][0], out[0][0]))
     assert np.abs(out[1][1] - out[0][1]).max() < 1e-9
+
+
+# ---- GF_OPT_MG_MATRIX_PRECISION = 2: x staged and accumulated in FP32 as well -----------------
+import os  # noqa: E402
+
+experimental = pytest.mark.skipif(
+    os.environ.get("GF_TEST_EXPERIMENTAL") != "1",
+    reason="the all-FP32 V-cycle operator was written after the round's GPU minutes ended; it is "
+           "opt-in (GF_OPT_MG_MATRIX_PRECISION = 2) and on no default path")
+
+
+@experimental
+@pytest.mark.parametrize("dim,degree,reps", [(3, 2, [4, 8, 4]), (3, 1, [6, 10, 4]), (2, 2, [8, 16])])
+def test_all_fp32_operator_is_a_single_precision_spmv(libs, dim, degree, reps):
+    capi, solvers, mg = libs
+    prob, H = assembled(libs, dim, reps, degree)
+    h = H.fine
+    h.set_option(capi.OPT_MG_MATRIX_PRECISION, 2)
+    x = np.random.RandomState(11).uniform(-1, 1, prob.n_dofs)
+    h.set_vector(capi.VEC_SCRATCH0, x)
+    h.spmv(capi.MAT_TANGENT, capi.VEC_SCRATCH0, capi.VEC_SCRATCH1)
+    y64 = h.get_vector(capi.VEC_SCRATCH1)
+    h.spmv(capi.MAT_MG_F32, capi.VEC_SCRATCH0, capi.VEC_SCRATCH1)
+    y32 = h.get_vector(capi.VEC_SCRATCH1)
+    rowptr, col, val = h.export_csr(capi.MAT_TANGENT)
+    import scipy.sparse as sp
+    absA = sp.csr_matrix((np.abs(val), col, rowptr), shape=(prob.n_dofs, prob.n_dofs))
+    n_max = np.diff(rowptr).max()
+    # rounding of A, of x, and of every partial sum (2 chains + 5 shuffle levels per lane)
+    bound = 2.0 ** -24 * (n_max / 32 + 12) * (absA @ np.abs(x)) + 1e-12 * np.abs(y64).max()
+    assert np.all(np.abs(y32 - y64) <= bound)
+    assert y32.astype(np.float32).astype(np.float64).tolist() == y32.tolist()   # FP32 results
+    H.close()
+
+
+@experimental
+def test_all_fp32_vcycle_keeps_newton_counts_and_displacements(libs):
+    capi, solvers, mg = libs
+    p = nl_params(poly_degree=2, scenario="PF", type_lin="CG", delta_t=0.01,
+                  max_iterations_lin=1.0)
+    prob = make_problem(p, 3, reps=[4, 16, 4], numbering="lexicographic")
+    n = prob.n_iface_nodes
+    traction = lambda t, it: np.tile(np.array([1500.0, 0.0, 0.0]) * min(1.0, t / 0.02), n)
+    out = {}
+    for prec in (0, 2):
+        H = mg.Hierarchy(prob)
+        H.fine.set_option(capi.OPT_MG_MATRIX_PRECISION, prec)
+        part = solvers.FakeParticipant(3, 3, p.delta_t, traction, 2)
+        solid = solvers.Solid(prob, part, handle=H.fine)
+        solid.run()
+        out[prec] = ([[r[0] for r in rows] for rows in solid.history],
+                     [d for (w, it, d) in part.written])
+        H.close()
+    assert [len(r) for r in out[2][0]] == [len(r) for r in out[0][0]]
+    for a, b in zip(out[2][0], out[0][0]):
+        assert all(abs(x - y) <= 2 for x, y in zip(a, b))
+    for d32, d64 in zip(out[2][1], out[0][1]):
+        assert rel_err(d32, d64) < 1e-7

@@ -57,4 +57,11 @@ for kind in KINDS:
     ms32, b32 = h.spmv_timed(capi.MAT_MG_F32, 10)
     print(json.dumps({"stage": "cfg3_timing", "kind": kind, "fp64_ms": ms64, "fp64_gbs": b64 / ms64 / 1e6,
                       "fp32_ms": ms32, "fp32_gbs": b32 / ms32 / 1e6}), flush=True)
+if os.environ.get("GF_TEST_EXPERIMENTAL") == "1":
+    # all-FP32 operator (GF_OPT_MG_MATRIX_PRECISION = 2), 8+16 warps
+    h.set_option(capi.OPT_SPMV_KERNEL, 0)
+    h.set_option(capi.OPT_MG_MATRIX_PRECISION, 2)
+    h.nl_newton_assemble()
+    ms32x, b32 = h.spmv_timed(capi.MAT_MG_F32, 10)
+    print(json.dumps({"stage": "cfg3_timing_all_fp32", "ms": ms32x, "gbs": b32 / ms32x / 1e6}), flush=True)
 H.close()
