@@ -171,7 +171,7 @@ def emit(line):
 
 
 def main():
-    global _REAL_STDOUT
+    global _REAL_STDOUT, N_SUB
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
@@ -185,12 +185,17 @@ def main():
     ap.add_argument("--reps", default=None,
                     help="a,b,c: cells of the whole flap 0.1 x 1 x 0.3 (debug: run a multi-GPU "
                          "weak-scaling mesh on fewer GPUs)")
+    ap.add_argument("--n-sub", type=int, default=N_SUB,
+                    help="coupling sub-iterations per time window (checkpoint at the first, restore "
+                         "after every non-final one); cfg5 of BASELINE.json: --reps 48,288,60 "
+                         "--n-sub 10 on 8 GPUs (tools/bench_cfg5.sh)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true",
                     help="skip the matrix-free-operator variant measured after the main regions")
     ap.add_argument("--precond", default="mg", choices=["mg", "jacobi"],
                     help="CG preconditioner: geometric multigrid V-cycle (default) or block-Jacobi")
     args = ap.parse_args()
+    N_SUB = max(1, args.n_sub)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
