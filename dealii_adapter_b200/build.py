@@ -113,6 +113,16 @@ def build_oracle(force=False):
     return LIB_ORACLE
 
 
+def build_oracle_ref():
+    """oracle/_ref/ref_driver: the header-only pieces of the reference that compile without the
+    real deal.II (material, Postprocessor, Time), taken in place from /root/reference. Only in the
+    build container; returns None where the reference tree does not exist (GPU box)."""
+    if not os.path.isdir("/root/reference"):
+        return None
+    _run(["make", "-C", os.path.join(REPO_DIR, "oracle"), "ref"])
+    return os.path.join(REPO_DIR, "oracle", "_ref", "ref_driver")
+
+
 def build_all(force=False):
     return build_host(force), build_cuda(force), build_elasticity(force), build_oracle(force)
 

@@ -4,9 +4,15 @@
  * checker by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg.
  * Nothing under dealii_adapter_b200/ may include, link or call this.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path, and
- * it cannot be built here (deal.II >= 9.2 [CI: 9.5.0] and preCICE >= 3.0 are absent, no
- * network). deal.II semantics (FE_Q local order, QGauss, QProjector face order,
+ * PARITY PINNED IN PART: the reference ships no tests, golden vectors or fixtures for this path,
+ * and as a whole it cannot be built here (deal.II >= 9.2 [CI: 9.5.0] and preCICE >= 3.0 are
+ * absent, no network). Three header-only pieces DO compile in place against a small stand-in
+ * (oracle/ref_shim, `make ref` -> oracle/_ref/ref_driver): the neo-Hookean material
+ * (compressible_neo_hook_material.h), the Postprocessor (postprocessor.h) and Time
+ * (time_handler.h); their outputs are committed as tests/golden/reference_vectors.npz and pin
+ * orc_material, orc_postprocess and the Time mirrors (tests/test_reference_pins.py).
+ * Everything else - the cell loop, the Neumann term, constraints, CG/SSOR, the theta scheme -
+ * remains UNPINNED by the reference itself: deal.II semantics (FE_Q local order, QGauss, QProjector face order,
  * AffineConstraints::distribute_local_to_global, SolverCG, precondition_SSOR,
  * MatrixTools::apply_boundary_values) are restated from the published deal.II 9.5 algorithms.
  * The substitutes for golden vectors are the analytic known-answer tests in

@@ -1,0 +1,1 @@
+#include <deal.II/base/dealii_min.h>
