@@ -1,0 +1,269 @@
+/* TEST INFRASTRUCTURE ONLY — what the reference's cell-assembly block
+ * (nonlinear_elasticity.cc:626-1036: Assembler_Base with PerTaskData_ASM / ScratchData_ASM /
+ * assemble_neumann_contribution_one_cell, Assembler<dim,double>::
+ * assemble_system_tangent_residual_one_cell) and PointHistory (nonlinear_elasticity.h:64-117) need
+ * around them to compile and run OUTSIDE deal.II. The two line ranges are cut out of the
+ * reference at build time into oracle/_ref/ as .inc files (never committed, see oracle/Makefile) because
+ * the structs live inside a translation unit whose other 1,000 lines need the real library.
+ *
+ * FEValues / FEFaceValues here do not compute anything: they hand out the shape-function tables,
+ * JxW and normals the driver was given (so the finite-element tables remain a restatement of
+ * deal.II - they come from tests/ref_formulas.py - while every line of arithmetic on them is the
+ * reference's own). `Solid` is a plain struct with the members the block reads through
+ * `data.solid->`. */
+#ifndef ASSEMBLY_SHIM_H
+#define ASSEMBLY_SHIM_H
+#include <deal.II/base/dealii_min.h>
+
+#include <memory>
+#include <stdexcept>
+#include <utility>
+
+#define AssertThrow(cond, exc)         \
+  do                                   \
+    {                                  \
+      if (!(cond))                     \
+        throw std::runtime_error(#cond); \
+    }                                  \
+  while (0)
+
+namespace dealii
+{
+  struct ExcPureFunctionCalled
+  {};
+  namespace types
+  {
+    using global_dof_index = unsigned int;
+  }
+  template <typename N>
+  class FullMatrix
+  {
+  public:
+    unsigned       m_, n_;
+    std::vector<N> a;
+    FullMatrix(unsigned m, unsigned n)
+      : m_(m)
+      , n_(n)
+      , a(size_t(m) * n, N(0))
+    {}
+    FullMatrix &operator=(const N s)
+    {
+      for (auto &x : a)
+        x = s;
+      return *this;
+    }
+    N &      operator()(unsigned i, unsigned j) { return a[size_t(i) * n_ + j]; }
+    const N &operator()(unsigned i, unsigned j) const { return a[size_t(i) * n_ + j]; }
+  };
+  template <typename N>
+  class BlockVector : public Vector<N>
+  {
+  public:
+    using Vector<N>::Vector;
+  };
+  template <typename N>
+  class BlockSparseMatrix
+  {};
+  template <typename N>
+  class AffineConstraints
+  {
+  public:
+    template <class M, class V, class I, class GM, class GV>
+    void distribute_local_to_global(const M &, const V &, const I &, GM &, GV &) const
+    {
+      throw std::runtime_error("not part of the stand-in");
+    }
+  };
+  template <int dim>
+  class FiniteElement
+  {
+  public:
+    unsigned dofs_per_cell = 0;
+    // FESystem(FE_Q(p), dim): one base element, dof i = node * dim + component
+    std::pair<std::pair<unsigned, unsigned>, unsigned> system_to_base_index(unsigned i) const
+    {
+      return {{0u, i % dim}, i / dim};
+    }
+    std::pair<unsigned, unsigned> system_to_component_index(unsigned i) const
+    {
+      return {i % dim, i / dim};
+    }
+  };
+  template <int dim>
+  class FESystem : public FiniteElement<dim>
+  {};
+  template <int dim>
+  class QGauss
+  {
+  public:
+    unsigned n = 0;
+    unsigned size() const { return n; }
+  };
+  namespace FEValuesExtractors
+  {
+    struct Vector
+    {
+      unsigned first_vector_component = 0;
+    };
+  } // namespace FEValuesExtractors
+
+  template <int dim>
+  class DoFHandler
+  {
+  public:
+    struct Face
+    {
+      bool     boundary = false;
+      unsigned id = 0, number = 0;
+      bool     at_boundary() const { return boundary; }
+      unsigned boundary_id() const { return id; }
+    };
+    struct Cell
+    {
+      std::vector<types::global_dof_index> dofs;
+      std::vector<Face>                    faces; // in deal.II face order 0..2*dim-1
+      void get_dof_indices(std::vector<types::global_dof_index> &v) const { v = dofs; }
+      std::vector<const Face *> face_iterators() const
+      {
+        std::vector<const Face *> r;
+        for (const auto &f : faces)
+          r.push_back(&f);
+        return r;
+      }
+    };
+    using active_cell_iterator = const Cell *;
+  };
+
+  // tables the driver provides for THE cell being assembled (real-space gradients of the scalar
+  // shape functions, JxW) and for each of its faces (values, JxW, unit normals)
+  template <int dim>
+  struct ShimTables
+  {
+    unsigned            nq = 0, nqf = 0, npc = 0;
+    std::vector<double> N, gradN, JxW;                 // [nq][npc], [nq][npc][dim], [nq]
+    std::vector<std::vector<double>> Nf, JxWf, normal; // per face: [nqf][npc], [nqf], [nqf][dim]
+    static ShimTables &get()
+    {
+      static ShimTables t;
+      return t;
+    }
+  };
+
+  template <int dim, bool face_values>
+  class FEValuesShim
+  {
+  public:
+    const FiniteElement<dim> &fe;
+    unsigned                  n_q;
+    UpdateFlags               flags;
+    unsigned                  dofs_per_cell;
+    unsigned                  n_quadrature_points;
+    QGauss<dim>               cell_q;
+    QGauss<dim - 1>           face_q;
+    const typename DoFHandler<dim>::Cell *cell = nullptr;
+    unsigned                              face = 0;
+
+    template <class Q>
+    FEValuesShim(const FiniteElement<dim> &fe, const Q &q, const UpdateFlags f)
+      : fe(fe)
+      , n_q(q.size())
+      , flags(f)
+      , dofs_per_cell(fe.dofs_per_cell)
+      , n_quadrature_points(q.size())
+    {
+      cell_q.n = q.size();
+      face_q.n = q.size();
+    }
+    const FiniteElement<dim> &get_fe() const { return fe; }
+    const auto &              get_quadrature() const
+    {
+      if constexpr (face_values)
+        return face_q;
+      else
+        return cell_q;
+    }
+    UpdateFlags get_update_flags() const { return flags; }
+    void        reinit(const typename DoFHandler<dim>::active_cell_iterator &c) { cell = c; }
+    void        reinit(const typename DoFHandler<dim>::active_cell_iterator &c,
+                       const typename DoFHandler<dim>::Face *                 f)
+    {
+      cell = c;
+      face = f->number;
+    }
+    double shape_value(unsigned i, unsigned q) const
+    {
+      const auto &t = ShimTables<dim>::get();
+      return face_values ? t.Nf[face][q * t.npc + i / dim] : t.N[q * t.npc + i / dim];
+    }
+    double JxW(unsigned q) const
+    {
+      const auto &t = ShimTables<dim>::get();
+      return face_values ? t.JxWf[face][q] : t.JxW[q];
+    }
+    Tensor<1, dim> normal_vector(unsigned q) const
+    {
+      const auto &   t = ShimTables<dim>::get();
+      Tensor<1, dim> n;
+      for (int d = 0; d < dim; ++d)
+        n[d] = t.normal[face][q * dim + d];
+      return n;
+    }
+    struct View
+    {
+      const FEValuesShim &fv;
+      // value / gradient of vector-valued shape function k: only component k % dim is non-zero
+      Tensor<1, dim> value(unsigned k, unsigned q) const
+      {
+        Tensor<1, dim> r;
+        r[k % dim] = fv.shape_value(k, q);
+        return r;
+      }
+      Tensor<2, dim> gradient(unsigned k, unsigned q) const
+      {
+        const auto &   t = ShimTables<dim>::get();
+        Tensor<2, dim> r;
+        for (int d = 0; d < dim; ++d)
+          r[k % dim][d] = t.gradN[(q * t.npc + k / dim) * dim + d];
+        return r;
+      }
+      template <class V>
+      void get_function_values(const V &global, std::vector<Tensor<1, dim>> &out) const
+      {
+        for (unsigned q = 0; q < out.size(); ++q)
+          {
+            out[q] = Tensor<1, dim>();
+            for (unsigned k = 0; k < fv.dofs_per_cell; ++k)
+              out[q][k % dim] += global(fv.cell->dofs[k]) * fv.shape_value(k, q);
+          }
+      }
+      template <class V>
+      void get_function_gradients(const V &global, std::vector<Tensor<2, dim>> &out) const
+      {
+        for (unsigned q = 0; q < out.size(); ++q)
+          {
+            out[q] = Tensor<2, dim>();
+            for (unsigned k = 0; k < fv.dofs_per_cell; ++k)
+              {
+                const Tensor<2, dim> g = gradient(k, q);
+                for (int d = 0; d < dim; ++d)
+                  out[q][k % dim][d] += global(fv.cell->dofs[k]) * g[k % dim][d];
+              }
+          }
+      }
+    };
+    View operator[](const FEValuesExtractors::Vector &) const { return View{*this}; }
+  };
+  template <int dim>
+  using FEValues = FEValuesShim<dim, false>;
+  template <int dim>
+  using FEFaceValues = FEValuesShim<dim, true>;
+} // namespace dealii
+
+namespace Parameters
+{
+  struct AllParameters
+  {
+    double mu = 0, nu = 0, rho = 0;
+  };
+} // namespace Parameters
+#endif

@@ -15,6 +15,9 @@
  *   StandardTensors<dim>: I = delta_ij ; S = (delta_ik delta_jl + delta_il delta_jk)/2 ;
  *                         IxI = I (x) I ; dev_P = S - IxI/dim
  *   Tensor<2,dim>::component_to_unrolled_index((d,e)) = d*dim + e
+ *   Tensor<1>*Tensor<1> scalar product; Tensor<1>*Tensor<2> / Tensor<2>*Tensor<1> / Tensor<2>*
+ *   Tensor<2> contract the adjacent indices; symmetrize(t) = (t + t^T)/2;
+ *   Kinematics::F(Grad_u) = I + Grad_u ; F_iso(F) = det(F)^(-1/dim) F ; b(F) = symmetrize(F F^T)
  */
 #ifndef DEALII_MIN_H
 #define DEALII_MIN_H
@@ -224,6 +227,12 @@ namespace dealii
       : data(n, Number(0))
     {}
     unsigned      size() const { return unsigned(data.size()); }
+    Vector &      operator=(const Number s)
+    {
+      for (auto &x : data)
+        x = s;
+      return *this;
+    }
     Number &      operator[](unsigned i) { return data[i]; }
     const Number &operator[](unsigned i) const { return data[i]; }
     Number &      operator()(unsigned i) { return data[i]; }
@@ -248,16 +257,191 @@ namespace dealii
     Number        v[dim] = {};
     Number &      operator[](unsigned i) { return v[i]; }
     const Number &operator[](unsigned i) const { return v[i]; }
+    Number        norm() const
+    {
+      Number s = Number(0);
+      for (int i = 0; i < dim; ++i)
+        s += v[i] * v[i];
+      return std::sqrt(s);
+    }
   };
   template <int dim, typename Number>
   class Tensor<2, dim, Number>
   {
   public:
+    Tensor<1, dim, Number> r[dim]; // rows
+    Tensor() = default;
+    Tensor(const SymmetricTensor<2, dim, Number> &s)
+    {
+      for (int i = 0; i < dim; ++i)
+        for (int j = 0; j < dim; ++j)
+          r[i][j] = s.v[i][j];
+    }
+    Tensor<1, dim, Number> &      operator[](unsigned i) { return r[i]; }
+    const Tensor<1, dim, Number> &operator[](unsigned i) const { return r[i]; }
     static unsigned component_to_unrolled_index(const TableIndices<2> &t)
     {
       return t.i[0] * dim + t.i[1]; // row-major unrolling
     }
   };
+  // ---- Tensor algebra used by the cell assembly (nonlinear_elasticity.cc:791-1036) ----------
+  template <int dim, typename N>
+  Tensor<1, dim, N> operator*(const Tensor<1, dim, N> &a, const double s)
+  {
+    Tensor<1, dim, N> r;
+    for (int i = 0; i < dim; ++i)
+      r[i] = a[i] * s;
+    return r;
+  }
+  template <int dim, typename N>
+  N operator*(const Tensor<1, dim, N> &a, const Tensor<1, dim, N> &b) // scalar product
+  {
+    N s = N(0);
+    for (int i = 0; i < dim; ++i)
+      s += a[i] * b[i];
+    return s;
+  }
+  template <int dim, typename N>
+  Tensor<2, dim, N> operator*(const Tensor<2, dim, N> &a, const Tensor<2, dim, N> &b)
+  {
+    Tensor<2, dim, N> r;
+    for (int i = 0; i < dim; ++i)
+      for (int j = 0; j < dim; ++j)
+        for (int k = 0; k < dim; ++k)
+          r[i][j] += a[i][k] * b[k][j];
+    return r;
+  }
+  template <int dim, typename N>
+  Tensor<1, dim, N> operator*(const Tensor<2, dim, N> &a, const Tensor<1, dim, N> &b)
+  {
+    Tensor<1, dim, N> r;
+    for (int i = 0; i < dim; ++i)
+      for (int k = 0; k < dim; ++k)
+        r[i] += a[i][k] * b[k];
+    return r;
+  }
+  template <int dim, typename N>
+  Tensor<1, dim, N> operator*(const Tensor<1, dim, N> &a, const Tensor<2, dim, N> &b)
+  {
+    Tensor<1, dim, N> r; // contraction over the last index of a and the first of b
+    for (int j = 0; j < dim; ++j)
+      for (int k = 0; k < dim; ++k)
+        r[j] += a[k] * b[k][j];
+    return r;
+  }
+  template <int dim, typename N>
+  Tensor<2, dim, N> operator*(const double s, const Tensor<2, dim, N> &a)
+  {
+    Tensor<2, dim, N> r;
+    for (int i = 0; i < dim; ++i)
+      for (int j = 0; j < dim; ++j)
+        r[i][j] = s * a[i][j];
+    return r;
+  }
+  template <typename N>
+  N determinant(const Tensor<2, 2, N> &t)
+  {
+    return t[0][0] * t[1][1] - t[1][0] * t[0][1];
+  }
+  template <typename N>
+  N determinant(const Tensor<2, 3, N> &t)
+  {
+    return t[0][0] * (t[1][1] * t[2][2] - t[1][2] * t[2][1]) -
+           t[0][1] * (t[1][0] * t[2][2] - t[1][2] * t[2][0]) +
+           t[0][2] * (t[1][0] * t[2][1] - t[1][1] * t[2][0]);
+  }
+  template <typename N>
+  Tensor<2, 2, N> invert(const Tensor<2, 2, N> &t)
+  {
+    const N         id = N(1) / determinant(t);
+    Tensor<2, 2, N> r;
+    r[0][0] = t[1][1] * id;
+    r[0][1] = -t[0][1] * id;
+    r[1][0] = -t[1][0] * id;
+    r[1][1] = t[0][0] * id;
+    return r;
+  }
+  template <typename N>
+  Tensor<2, 3, N> invert(const Tensor<2, 3, N> &t)
+  {
+    const N         id = N(1) / determinant(t);
+    Tensor<2, 3, N> r;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        {
+          // cofactor of t[j][i]
+          const int a = (j + 1) % 3, b = (j + 2) % 3, c = (i + 1) % 3, d = (i + 2) % 3;
+          r[i][j]     = (t[a][c] * t[b][d] - t[a][d] * t[b][c]) * id;
+        }
+    return r;
+  }
+  template <int dim, typename N>
+  Tensor<2, dim, N> transpose(const Tensor<2, dim, N> &t)
+  {
+    Tensor<2, dim, N> r;
+    for (int i = 0; i < dim; ++i)
+      for (int j = 0; j < dim; ++j)
+        r[i][j] = t[j][i];
+    return r;
+  }
+  template <int dim, typename N>
+  SymmetricTensor<2, dim, N> symmetrize(const Tensor<2, dim, N> &t)
+  {
+    SymmetricTensor<2, dim, N> r;
+    for (int i = 0; i < dim; ++i)
+      for (int j = 0; j < dim; ++j)
+        r.v[i][j] = (t[i][j] + t[j][i]) / 2;
+    return r;
+  }
+  // double contractions 2:2 -> scalar and 2:4 -> 2
+  template <int dim, typename N>
+  N operator*(const SymmetricTensor<2, dim, N> &a, const SymmetricTensor<2, dim, N> &b)
+  {
+    N s = N(0);
+    for (int i = 0; i < dim; ++i)
+      for (int j = 0; j < dim; ++j)
+        s += a.v[i][j] * b.v[i][j];
+    return s;
+  }
+  template <int dim, typename N>
+  SymmetricTensor<2, dim, N> operator*(const SymmetricTensor<2, dim, N> &a,
+                                       const SymmetricTensor<4, dim, N> &c)
+  {
+    SymmetricTensor<2, dim, N> r;
+    for (int i = 0; i < dim; ++i)
+      for (int j = 0; j < dim; ++j)
+        for (int k = 0; k < dim; ++k)
+          for (int l = 0; l < dim; ++l)
+            r.v[k][l] += a.v[i][j] * c.v[i][j][k][l];
+    return r;
+  }
+  namespace Physics
+  {
+    namespace Elasticity
+    {
+      namespace Kinematics
+      {
+        template <int dim, typename N>
+        Tensor<2, dim, N> F(const Tensor<2, dim, N> &Grad_u)
+        {
+          Tensor<2, dim, N> r = Grad_u;
+          for (int i = 0; i < dim; ++i)
+            r[i][i] += N(1);
+          return r;
+        }
+        template <int dim, typename N>
+        Tensor<2, dim, N> F_iso(const Tensor<2, dim, N> &F)
+        {
+          return std::pow(determinant(F), -1.0 / dim) * F;
+        }
+        template <int dim, typename N>
+        SymmetricTensor<2, dim, N> b(const Tensor<2, dim, N> &F)
+        {
+          return symmetrize(F * transpose(F));
+        }
+      } // namespace Kinematics
+    }   // namespace Elasticity
+  }     // namespace Physics
   namespace DataPostprocessorInputs
   {
     template <int dim>

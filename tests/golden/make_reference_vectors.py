@@ -20,6 +20,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+ASM_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_assembler_driver")
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 OUT = os.path.join(HERE, "reference_vectors.npz")
 
 
@@ -54,8 +56,92 @@ def material_cases():
     return cases
 
 
+def face_tables(dim, p, nq1, h, faces):
+    """Per face: shape values at the face quadrature points, JxW and the outward unit normal of a
+    Cartesian cell with edge lengths h. Face points in QProjector order (standard orientation;
+    3D y-faces run (z, x)), restated from deal.II as in the oracle."""
+    import ref_formulas as rf
+    x1, w1 = rf.gauss01(nq1)
+    nodes = rf.hierarchical_nodes(dim, p)
+    nqf = nq1 ** (dim - 1)
+    out = {}
+    for f in faces:
+        d, c = f // 2, float(f % 2)
+        Nf = np.zeros((nqf, len(nodes)))
+        JxWf = np.zeros(nqf)
+        for q in range(nqf):
+            fi = [(q // nq1 ** k) % nq1 for k in range(dim - 1)]
+            fq = [x1[i] for i in fi]
+            w = np.prod([w1[i] for i in fi])
+            xi = [0.0] * dim
+            if dim == 2:
+                xi[d], xi[1 - d] = c, fq[0]
+            elif d == 0:
+                xi = [c, fq[0], fq[1]]
+            elif d == 1:
+                xi = [fq[1], c, fq[0]]
+            else:
+                xi = [fq[0], fq[1], c]
+            v1 = [rf.lagrange_1d(p, xi[k])[0][0] for k in range(dim)]
+            for a, lex in enumerate(nodes):
+                Nf[q, a] = np.prod([v1[k][lex[k]] for k in range(dim)])
+            JxWf[q] = w * np.prod([h[k] for k in range(dim) if k != d])
+        normal = np.zeros((nqf, dim))
+        normal[:, d] = 1.0 if f % 2 else -1.0
+        out[f] = (Nf, JxWf, normal)
+    return out
+
+
+def assembly_cases():
+    """One Cartesian cell each: (dim, degree, edge lengths, interface faces, body force)."""
+    return [(2, 1, [0.1, 0.05], [0, 1, 3], (0.0, 0.0, 0.0)),
+            (2, 2, [0.02, 0.03], [0, 1, 3], (0.0, -9.81, 0.0)),
+            (3, 1, [0.1, 0.2, 0.15], [0, 1, 3], (0.0, 0.0, 0.0)),
+            (3, 2, [0.05, 0.04, 0.06], [0, 1, 3], (1.5, -9.81, 0.5)),
+            (3, 2, [0.004, 0.007, 0.0125], [], (0.0, 0.0, 0.0))]
+
+
+def run_assembly_case(k, dim, p, h, faces, body_force):
+    """Feeds the reference's assemble_system_one_cell (cut out of nonlinear_elasticity.cc at build
+    time) with numpy FE tables of tests/ref_formulas.py; returns inputs and its K_e, r_e."""
+    import ref_formulas as rf
+    rng = np.random.RandomState(100 + k)
+    nq1 = p + 2                                      # QGauss(degree + 2), nonlinear_elasticity.cc:74-75
+    N, dN, w = rf.cell_tables(dim, p, nq1)
+    npc, nq, nqf = N.shape[1], len(w), nq1 ** (dim - 1)
+    dpc = npc * dim
+    gradN = dN / np.asarray(h)[None, None, :]
+    JxW = w * np.prod(h)
+    mu, nu, rho, beta, dt = 0.5e6, 0.4, 1000.0, 0.25, 0.01
+    alpha_1 = 1.0 / (beta * dt * dt)
+    u = 0.15 * min(h) * rng.uniform(-1, 1, dpc)
+    acc = 50.0 * rng.uniform(-1, 1, dpc)
+    stress = 2000.0 * rng.uniform(-1, 1, dpc)
+    ft = face_tables(dim, p, nq1, h, faces)
+    words = [dim, npc, nq, nqf, len(faces), mu, nu, rho, alpha_1] + list(body_force) + [7]
+    words += list(N.reshape(-1)) + list(gradN.reshape(-1)) + list(JxW)
+    for f in faces:
+        Nf, JxWf, normal = ft[f]
+        words += [f, 7] + list(Nf.reshape(-1)) + list(JxWf) + list(normal.reshape(-1))
+    words += list(u) + list(acc) + list(stress)
+    text = " ".join(repr(float(x)) if isinstance(x, (float, np.floating)) else str(int(x)) for x in words)
+    res = subprocess.run([ASM_DRIVER], input=text, capture_output=True, text=True, check=True).stdout
+    rows = [l.split() for l in res.strip().split("\n")]
+    K = np.array(rows[:dpc], dtype=float)
+    r = np.array(rows[dpc], dtype=float)
+    meta = np.array([dim, p] + list(h) + [0.0] * (3 - dim) + list(body_force) + [mu, nu, rho, beta, dt])
+    return {"asm%d_meta" % k: meta, "asm%d_faces" % k: np.array(faces, dtype=np.int64),
+            "asm%d_u" % k: u, "asm%d_acc" % k: acc, "asm%d_stress" % k: stress,
+            "asm%d_K" % k: K, "asm%d_r" % k: r}
+
+
 def generate():
     out = {}
+    # ---- cell assembly: tangent, residual, Neumann term of one cell -------------------------
+    cases = assembly_cases()
+    for k, c in enumerate(cases):
+        out.update(run_assembly_case(k, *c))
+    out["n_assembly"] = np.array(len(cases))
     # ---- material -------------------------------------------------------------------------
     rows = []
     for k, (dim, mu, nu, J, bv) in enumerate(material_cases()):

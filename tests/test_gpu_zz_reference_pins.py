@@ -1,0 +1,60 @@
+"""CUDA path against outputs of THE REFERENCE'S OWN CODE: the element tangent / residual that the
+reference's assembly block (nonlinear_elasticity.cc:791-859, 872-1036, cut out and compiled against
+oracle/ref_shim in the build container; vectors in tests/golden/reference_vectors.npz) computes for
+one cell, against the device assembling the same one-cell problem through the C-ABI
+(gf_nl_newton_assemble -> cell kernel, face kernel, scatter). FP64, 1e-12 relative to the largest
+entry, as for the oracle parity tests."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import nl_params
+from dealii_adapter_b200.problem import make_problem
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def libs(native_libs):
+    from dealii_adapter_b200 import build, capi
+    build.build_cuda()
+    capi.lib()
+    return capi
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_device_cell_assembly_equals_the_reference_assembly_block(libs, case):
+    capi = libs
+    ref = np.load(os.path.join(GOLDEN, "reference_vectors.npz"))
+    meta = ref["asm%d_meta" % case]
+    dim, degree = int(meta[0]), int(meta[1])
+    h, body_force = meta[2:5], meta[5:8]
+    mu, nu, rho, beta, dt = meta[8:13]
+    assert sorted(ref["asm%d_faces" % case].tolist()) == [0, 1, 3]      # the PF interface faces
+    p = nl_params(poly_degree=degree, scenario="PF", mu=mu, nu=nu, rho=rho, beta=beta, delta_t=dt,
+                  body_force=tuple(body_force))
+    prob = make_problem(p, dim, reps=[1] * dim, numbering="cellwise",
+                        box=([0.0] * dim, list(h[:dim])))
+    prob.constrained = np.zeros_like(prob.constrained)
+    assert np.array_equal(prob.mesh.cell_dofs.reshape(-1), np.arange(prob.n_dofs))
+    hd = capi.Handle(prob)
+    hd.set_vector(capi.NL_TOTAL_DISPLACEMENT, ref["asm%d_u" % case])
+    hd.set_vector(capi.NL_EXTERNAL_STRESS, ref["asm%d_stress" % case])
+    # gf_nl_newton_assemble first runs update_acceleration (:592-599):
+    # a = alpha_1*0 - alpha_2*v_old - alpha_3*a_old with alpha_3 = (1-2 beta)/(2 beta)
+    alpha_3 = (1 - 2 * beta) / (2 * beta)
+    hd.set_vector(capi.NL_ACCELERATION_OLD, -ref["asm%d_acc" % case] / alpha_3)
+    hd.nl_begin_step()
+    hd.nl_newton_assemble()
+    assert np.abs(hd.get_vector(capi.NL_ACCELERATION) - ref["asm%d_acc" % case]).max() \
+        <= 1e-14 * np.abs(ref["asm%d_acc" % case]).max()
+    rowptr, col, val = hd.export_csr(capi.MAT_TANGENT)
+    import scipy.sparse as sp
+    K = sp.csr_matrix((val, col, rowptr), shape=(prob.n_dofs, prob.n_dofs)).toarray()
+    r = hd.get_vector(capi.NL_SYSTEM_RHS)
+    K_ref, r_ref = ref["asm%d_K" % case], ref["asm%d_r" % case]
+    assert np.abs(K - K_ref).max() <= 1e-12 * np.abs(K_ref).max()
+    assert np.abs(r - r_ref).max() <= 1e-12 * np.abs(r_ref).max()
+    hd.close()

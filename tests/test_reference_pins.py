@@ -78,3 +78,53 @@ def test_fixture_is_what_the_reference_produces():
     r = subprocess.run([sys.executable, os.path.join(GOLDEN, "make_reference_vectors.py"), "--check"],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def one_cell_oracle(orc, dim, degree, h, faces, body_force, mu, nu, rho, beta, dt):
+    """Oracle on a single unconstrained Cartesian cell whose interface faces are `faces`."""
+    p = nl_params(poly_degree=degree, scenario="PF", mu=mu, nu=nu, rho=rho, beta=beta, delta_t=dt,
+                  body_force=tuple(body_force))
+    prob = make_problem(p, dim, reps=[1] * dim, numbering="cellwise",
+                        box=([0.0] * dim, list(h[:dim])))
+    prob.constrained = np.zeros_like(prob.constrained)
+    # PF marks x-, x+, y+ (faces 0, 1, 3) as interface: keep or drop them all
+    assert sorted(prob.iface_face_no.tolist()) == [0, 1, 3]
+    if not len(faces):
+        prob.iface_cell = prob.iface_cell[:0]
+        prob.iface_face_no = prob.iface_face_no[:0]
+    assert np.array_equal(prob.mesh.cell_dofs.reshape(-1), np.arange(prob.n_dofs))   # global = local
+    return prob, orc.Oracle(prob, n_threads=1)
+
+
+def test_oracle_cell_assembly_equals_the_reference_assembly_block(native_libs, ref):
+    """K_e and r_e (tangent :1011-1023, residual :984-995, Neumann term incl. its cell-q-point
+    quirk :825-827, symmetric copy :1033-1035) computed by the reference's own lines on one cell,
+    against the oracle assembling the same one-cell problem."""
+    from oracle import oracle_py as orc
+    n = int(ref["n_assembly"])
+    assert n == 5
+    for k in range(n):
+        meta = ref["asm%d_meta" % k]
+        dim, degree = int(meta[0]), int(meta[1])
+        h, body_force = meta[2:5], meta[5:8]
+        mu, nu, rho, beta, dt = meta[8:13]
+        faces = ref["asm%d_faces" % k]
+        prob, o = one_cell_oracle(orc, dim, degree, h, faces, body_force, mu, nu, rho, beta, dt)
+        o.set(orc.NL_TOTAL_DISPLACEMENT, ref["asm%d_u" % k])
+        o.set(orc.NL_SOLUTION_DELTA, np.zeros(prob.n_dofs))
+        o.set(orc.NL_ACCELERATION, ref["asm%d_acc" % k])
+        o.set(orc.NL_EXTERNAL_STRESS, ref["asm%d_stress" % k])
+        o.nl_assemble_system()
+        K = o.csr(orc.MAT_TANGENT).toarray()
+        r = o.get(orc.NL_SYSTEM_RHS)
+        K_ref, r_ref = ref["asm%d_K" % k], ref["asm%d_r" % k]
+        assert np.abs(K - K_ref).max() <= 1e-12 * np.abs(K_ref).max(), k
+        assert np.abs(r - r_ref).max() <= 1e-12 * np.abs(r_ref).max(), k
+        assert np.array_equal(K_ref, K_ref.T)            # the reference mirrors the lower triangle
+        if len(faces):
+            # the Neumann term is really in there: without the faces the residual differs
+            prob2, o2 = one_cell_oracle(orc, dim, degree, h, [], body_force, mu, nu, rho, beta, dt)
+            o2.set(orc.NL_TOTAL_DISPLACEMENT, ref["asm%d_u" % k])
+            o2.set(orc.NL_ACCELERATION, ref["asm%d_acc" % k])
+            o2.nl_assemble_system()
+            assert np.abs(o2.get(orc.NL_SYSTEM_RHS) - r_ref).max() > 1e-6 * np.abs(r_ref).max()
