@@ -114,9 +114,11 @@ def build_oracle(force=False):
 
 
 def build_oracle_ref():
-    """oracle/_ref/ref_driver: the header-only pieces of the reference that compile without the
-    real deal.II (material, Postprocessor, Time), taken in place from /root/reference. Only in the
-    build container; returns None where the reference tree does not exist (GPU box)."""
+    """oracle/_ref/: the pieces of the reference that compile without the real deal.II against
+    oracle/ref_shim - the material, Postprocessor and Time headers in place, the cell-assembly
+    structs of nonlinear_elasticity.cc and two statement blocks of linear_elasticity.cc cut out by
+    marker at build time. Only in the build container; returns None where the reference tree does
+    not exist (GPU box)."""
     if not os.path.isdir("/root/reference"):
         return None
     _run(["make", "-C", os.path.join(REPO_DIR, "oracle"), "ref"])

@@ -195,6 +195,27 @@ namespace dealii
       const auto &t = ShimTables<dim>::get();
       return face_values ? t.Nf[face][q * t.npc + i / dim] : t.N[q * t.npc + i / dim];
     }
+    // gradient of the only non-zero component of shape function i (FEValues::shape_grad)
+    Tensor<1, dim> shape_grad(unsigned i, unsigned q) const
+    {
+      const auto &   t = ShimTables<dim>::get();
+      Tensor<1, dim> g;
+      for (int d = 0; d < dim; ++d)
+        g[d] = t.gradN[(q * t.npc + i / dim) * dim + d];
+      return g;
+    }
+    // FEValuesBase::get_function_values for a vector-valued element
+    template <class V>
+    void get_function_values(const V &global, std::vector<Vector<double>> &out) const
+    {
+      for (unsigned q = 0; q < out.size(); ++q)
+        {
+          for (int d = 0; d < dim; ++d)
+            out[q][d] = 0.0;
+          for (unsigned k = 0; k < dofs_per_cell; ++k)
+            out[q][k % dim] += global(cell->dofs[k]) * shape_value(k, q);
+        }
+    }
     double JxW(unsigned q) const
     {
       const auto &t = ShimTables<dim>::get();

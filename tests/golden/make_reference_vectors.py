@@ -21,6 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
 ASM_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_assembler_driver")
+LIN_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_linear_driver")
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 OUT = os.path.join(HERE, "reference_vectors.npz")
 
@@ -135,8 +136,47 @@ def run_assembly_case(k, dim, p, h, faces, body_force):
             "asm%d_K" % k: K, "asm%d_r" % k: r}
 
 
+def run_linear_case(k, dim, p, h, faces):
+    """The reference's local stiffness loops (linear_elasticity.cc:289-323) and the face loop of
+    assemble_consistent_loading (:487-512) on one cell; QGauss(degree + 1) (:61,252,465)."""
+    import ref_formulas as rf
+    rng = np.random.RandomState(200 + k)
+    nq1 = p + 1
+    N, dN, w = rf.cell_tables(dim, p, nq1)
+    npc, nq, nqf = N.shape[1], len(w), nq1 ** (dim - 1)
+    dpc = npc * dim
+    gradN = dN / np.asarray(h)[None, None, :]
+    JxW = w * np.prod(h)
+    mu, nu = 0.5e6, 0.4
+    lam = 2 * mu * nu / (1 - 2 * nu)                 # parameters.cc:189
+    stress = 2000.0 * rng.uniform(-1, 1, dpc)
+    ft = face_tables(dim, p, nq1, h, faces)
+    words = [dim, npc, nq, nqf, len(faces), lam, mu, 6]
+    words += list(gradN.reshape(-1)) + list(JxW)
+    for f in faces:
+        Nf, JxWf, normal = ft[f]
+        words += [f, 6] + list(Nf.reshape(-1)) + list(JxWf)
+    words += list(stress)
+    text = " ".join(repr(float(x)) if isinstance(x, (float, np.floating)) else str(int(x)) for x in words)
+    res = subprocess.run([LIN_DRIVER], input=text, capture_output=True, text=True, check=True).stdout
+    rows = [l.split() for l in res.strip().split("\n")]
+    meta = np.array([dim, p] + list(h) + [0.0] * (3 - dim) + [mu, nu])
+    return {"lin%d_meta" % k: meta, "lin%d_faces" % k: np.array(faces, dtype=np.int64),
+            "lin%d_stress" % k: stress, "lin%d_K" % k: np.array(rows[:dpc], dtype=float),
+            "lin%d_F" % k: np.array(rows[dpc], dtype=float)}
+
+
+def linear_cases():
+    return [(2, 1, [0.1, 0.05], [0, 1, 3]), (2, 2, [0.1 / 3, 1.0 / 18], [0, 1, 3]),
+            (3, 1, [0.1, 0.2, 0.15], [0, 1, 3]), (3, 2, [0.05, 0.04, 0.06], [0, 1, 3])]
+
+
 def generate():
     out = {}
+    lcases = linear_cases()
+    for k, c in enumerate(lcases):
+        out.update(run_linear_case(k, *c))
+    out["n_linear"] = np.array(len(lcases))
     # ---- cell assembly: tangent, residual, Neumann term of one cell -------------------------
     cases = assembly_cases()
     for k, c in enumerate(cases):

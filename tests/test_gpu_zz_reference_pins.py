@@ -58,3 +58,31 @@ def test_device_cell_assembly_equals_the_reference_assembly_block(libs, case):
     assert np.abs(K - K_ref).max() <= 1e-12 * np.abs(K_ref).max()
     assert np.abs(r - r_ref).max() <= 1e-12 * np.abs(r_ref).max()
     hd.close()
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_device_linear_stiffness_and_loading_equal_the_reference_loops(libs, case):
+    """linear_elasticity.cc:289-323 (local stiffness) and :487-512 (consistent loading): the
+    reference's own statements on one cell against gf_lin_assemble_once / gf_lin_step."""
+    capi = libs
+    from helpers import lin_params
+    ref = np.load(os.path.join(GOLDEN, "reference_vectors.npz"))
+    meta = ref["lin%d_meta" % case]
+    dim, degree, h, mu, nu = int(meta[0]), int(meta[1]), meta[2:5], meta[5], meta[6]
+    p = lin_params(poly_degree=degree, scenario="PF", mu=mu, nu=nu, type_lin="CG")
+    prob = make_problem(p, dim, reps=[1] * dim, numbering="cellwise",
+                        box=([0.0] * dim, list(h[:dim])))
+    prob.constrained = np.zeros_like(prob.constrained)
+    assert sorted(prob.iface_face_no.tolist()) == [0, 1, 3]
+    hd = capi.Handle(prob)
+    hd.lin_assemble_once()
+    rowptr, col, val = hd.export_csr(capi.MAT_STIFFNESS)
+    import scipy.sparse as sp
+    K = sp.csr_matrix((val, col, rowptr), shape=(prob.n_dofs, prob.n_dofs)).toarray()
+    K_ref, F_ref = ref["lin%d_K" % case], ref["lin%d_F" % case]
+    assert np.abs(K - K_ref).max() <= 1e-12 * np.abs(K_ref).max()
+    hd.set_vector(capi.LIN_STRESS, ref["lin%d_stress" % case])
+    hd.lin_step(0, 2.0)                      # old_stress <- the consistent loading (:405-409)
+    F = hd.get_vector(capi.LIN_OLD_STRESS)
+    assert np.abs(F - F_ref).max() <= 1e-12 * np.abs(F_ref).max()
+    hd.close()

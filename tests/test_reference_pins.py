@@ -128,3 +128,36 @@ def test_oracle_cell_assembly_equals_the_reference_assembly_block(native_libs, r
             o2.set(orc.NL_ACCELERATION, ref["asm%d_acc" % k])
             o2.nl_assemble_system()
             assert np.abs(o2.get(orc.NL_SYSTEM_RHS) - r_ref).max() > 1e-6 * np.abs(r_ref).max()
+
+
+def one_cell_linear_problem(dim, degree, h, mu, nu):
+    from helpers import lin_params
+    p = lin_params(poly_degree=degree, scenario="PF", mu=mu, nu=nu)
+    prob = make_problem(p, dim, reps=[1] * dim, numbering="cellwise",
+                        box=([0.0] * dim, list(h[:dim])))
+    prob.constrained = np.zeros_like(prob.constrained)
+    assert sorted(prob.iface_face_no.tolist()) == [0, 1, 3]
+    assert np.array_equal(prob.mesh.cell_dofs.reshape(-1), np.arange(prob.n_dofs))
+    return prob
+
+
+def test_oracle_linear_cell_matrix_and_loading_equal_the_reference_loops(native_libs, ref):
+    """linear_elasticity.cc:289-323 (local stiffness) and :487-512 (consistent loading on the
+    interface faces), the reference's own statements on one cell, against the oracle."""
+    from oracle import oracle_py as orc
+    assert int(ref["n_linear"]) == 4
+    for k in range(4):
+        meta = ref["lin%d_meta" % k]
+        dim, degree, h, mu, nu = int(meta[0]), int(meta[1]), meta[2:5], meta[5], meta[6]
+        prob = one_cell_linear_problem(dim, degree, h, mu, nu)
+        o = orc.Oracle(prob, n_threads=1)
+        o.lin_assemble_system()
+        K = o.csr(orc.MAT_STIFFNESS).toarray()
+        K_ref, F_ref = ref["lin%d_K" % k], ref["lin%d_F" % k]
+        assert np.abs(K - K_ref).max() <= 1e-12 * np.abs(K_ref).max(), k
+        o.set(orc.LIN_STRESS, ref["lin%d_stress" % k])
+        o.lin_assemble_rhs()                    # old_stress <- the consistent loading (:405-409)
+        F = o.get(orc.LIN_OLD_STRESS)
+        assert np.abs(F - F_ref).max() <= 1e-12 * np.abs(F_ref).max(), k
+        dt, theta = prob.params.delta_t, prob.params.theta
+        assert np.abs(o.get(orc.LIN_SYSTEM_RHS) - dt * theta * F_ref).max() <= 1e-12 * dt * theta * np.abs(F_ref).max()
