@@ -60,6 +60,31 @@ namespace dealii
   {
   public:
     using Vector<N>::Vector;
+    BlockVector() = default;
+    // BlockVector(block_sizes): the reference only ever has one block
+    explicit BlockVector(const std::vector<types::global_dof_index> &block_sizes)
+      : Vector<N>(block_sizes.at(0))
+    {}
+    Vector<N> &      block(unsigned) { return *this; }
+    const Vector<N> &block(unsigned) const { return *this; }
+  };
+  // dense stand-in for SparseMatrix: vmult only
+  template <typename N>
+  class SparseMatrix
+  {
+  public:
+    unsigned       n = 0;
+    std::vector<N> a;
+    void           vmult(Vector<N> &dst, const Vector<N> &src) const
+    {
+      for (unsigned i = 0; i < n; ++i)
+        {
+          N s = N(0);
+          for (unsigned j = 0; j < n; ++j)
+            s += a[size_t(i) * n + j] * src[j];
+          dst[i] = s;
+        }
+    }
   };
   template <typename N>
   class BlockSparseMatrix
@@ -68,6 +93,8 @@ namespace dealii
   class AffineConstraints
   {
   public:
+    std::vector<unsigned char> constrained;
+    bool is_constrained(unsigned i) const { return i < constrained.size() && constrained[i] != 0; }
     template <class M, class V, class I, class GM, class GV>
     void distribute_local_to_global(const M &, const V &, const I &, GM &, GV &) const
     {
@@ -285,6 +312,8 @@ namespace Parameters
   struct AllParameters
   {
     double mu = 0, nu = 0, rho = 0;
+    double beta = 0, gamma = 0, theta = 0, delta_t = 0;
+    bool   data_consistent = true;
   };
 } // namespace Parameters
 #endif

@@ -237,6 +237,43 @@ namespace dealii
     const Number &operator[](unsigned i) const { return data[i]; }
     Number &      operator()(unsigned i) { return data[i]; }
     const Number &operator()(unsigned i) const { return data[i]; }
+    // the BLAS-1 members the time-stepping code uses (Vector::equ / add / sadd-free subset)
+    void reinit(unsigned n) { data.assign(n, Number(0)); }
+    void equ(const Number a, const Vector &v)
+    {
+      data.resize(v.data.size());
+      for (size_t i = 0; i < data.size(); ++i)
+        data[i] = a * v.data[i];
+    }
+    void add(const Number a, const Vector &v)
+    {
+      for (size_t i = 0; i < data.size(); ++i)
+        data[i] += a * v.data[i];
+    }
+    void add(const Number a, const Vector &v, const Number b, const Vector &w)
+    {
+      for (size_t i = 0; i < data.size(); ++i)
+        data[i] += a * v.data[i] + b * w.data[i];
+    }
+    Vector &operator+=(const Vector &v)
+    {
+      for (size_t i = 0; i < data.size(); ++i)
+        data[i] += v.data[i];
+      return *this;
+    }
+    Vector &operator*=(const Number a)
+    {
+      for (auto &x : data)
+        x *= a;
+      return *this;
+    }
+    Number l2_norm() const
+    {
+      Number s = Number(0);
+      for (const auto &x : data)
+        s += x * x;
+      return std::sqrt(s);
+    }
   };
   template <int rank>
   struct TableIndices;

@@ -22,6 +22,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
 ASM_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_assembler_driver")
 LIN_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_linear_driver")
+UPD_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_updates_driver")
+sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 OUT = os.path.join(HERE, "reference_vectors.npz")
 
@@ -171,8 +173,77 @@ def linear_cases():
             (3, 1, [0.1, 0.2, 0.15], [0, 1, 3]), (3, 2, [0.05, 0.04, 0.06], [0, 1, 3])]
 
 
+def fmt(words):
+    return " ".join(w if isinstance(w, str) else
+                    (repr(float(w)) if isinstance(w, (float, np.floating)) else str(int(w))) for w in words)
+
+
+def run_update_cases():
+    """The reference's Newmark coefficients / updates / masked norms (nonlinear_elasticity.h:242-250,
+    .cc:549-622) and its theta-scheme right-hand side + displacement update (linear_elasticity.cc:
+    384-420, 579-586) on small vectors. The constraint mask and the K, M matrices of the linear case
+    are taken from a small structured problem (stored in the fixture)."""
+    from helpers import lin_params, nl_params
+    from dealii_adapter_b200.problem import make_problem
+    from oracle import oracle_py as orc
+    out = {}
+    for k, (beta, gamma, dt) in enumerate(((0.25, 0.5, 0.01), (0.3025, 0.6, 0.005))):
+        prob = make_problem(nl_params(poly_degree=1, beta=beta, gamma=gamma, delta_t=dt), 2, reps=[3, 2])
+        n = prob.n_dofs
+        rng = np.random.RandomState(300 + k)
+        vecs = [rng.uniform(-1, 1, n) * s for s in (1e-3, 1e-2, 0.5, 20.0, 1e3, 1e-4)]
+        words = ["nl", n, beta, gamma, dt] + [int(c) for c in prob.constrained]
+        for v in vecs:
+            words += list(v)
+        res = subprocess.run([UPD_DRIVER], input=fmt(words), capture_output=True, text=True,
+                             check=True).stdout.strip().split("\n")
+        out["upd%d_in" % k] = np.array([beta, gamma, dt])
+        out["upd%d_vecs" % k] = np.array(vecs)
+        out["upd%d_alpha" % k] = np.array(res[0].split(), dtype=float)
+        out["upd%d_acc" % k] = np.array(res[1].split(), dtype=float)
+        out["upd%d_vel" % k] = np.array(res[2].split(), dtype=float)
+        out["upd%d_total" % k] = np.array(res[3].split(), dtype=float)
+        out["upd%d_norms" % k] = np.array(res[4].split(), dtype=float)
+        assert res[5].strip() == "1"
+    for k, (consistent, bf) in enumerate(((False, (0.0, -9.81, 0.0)), (True, (0.0, 0.0, 0.0)))):
+        p = lin_params(poly_degree=1, theta=0.6 if k == 0 else 0.5, delta_t=0.005,
+                       read_data_name="Stress" if consistent else "Force", body_force=bf)
+        prob = make_problem(p, 2, reps=[3, 2])
+        n = prob.n_dofs
+        o = orc.Oracle(prob, n_threads=1)
+        o.lin_assemble_system()
+        K = o.csr(orc.MAT_STIFFNESS).toarray()
+        M = o.csr(orc.MAT_MASS).toarray()
+        rng = np.random.RandomState(400 + k)
+        stress, old_stress, vel, disp, new_vel = (rng.uniform(-1, 1, n) * s
+                                                  for s in (500.0, 400.0, 0.3, 1e-3, 0.25))
+        if consistent:      # what assemble_consistent_loading() leaves in system_rhs for `stress`
+            o2 = orc.Oracle(prob, n_threads=1)
+            o2.lin_assemble_system()
+            o2.set(orc.LIN_STRESS, stress)
+            o2.lin_assemble_rhs()
+            loading = o2.get(orc.LIN_OLD_STRESS)
+        else:
+            loading = np.zeros(n)
+        bfv = o.get(orc.LIN_BODY_FORCE)
+        words = ["lin", n, p.theta, p.delta_t, int(consistent), int(any(bf))]
+        words += list(K.reshape(-1)) + list(M.reshape(-1))
+        for v in (loading, stress, old_stress, vel, disp, bfv, new_vel):
+            words += list(v)
+        res = subprocess.run([UPD_DRIVER], input=fmt(words), capture_output=True, text=True,
+                             check=True).stdout.strip().split("\n")
+        out["rhs%d_in" % k] = np.array([p.theta, p.delta_t, float(consistent)] + list(bf))
+        out["rhs%d_K" % k], out["rhs%d_M" % k] = K, M
+        out["rhs%d_vecs" % k] = np.array([loading, stress, old_stress, vel, disp, bfv, new_vel])
+        for name, line in zip(("system_rhs", "old_stress", "old_velocity", "old_displacement",
+                               "displacement"), res):
+            out["rhs%d_%s" % (k, name)] = np.array(line.split(), dtype=float)
+    return out
+
+
 def generate():
     out = {}
+    out.update(run_update_cases())
     lcases = linear_cases()
     for k, c in enumerate(lcases):
         out.update(run_linear_case(k, *c))

@@ -86,3 +86,57 @@ def test_device_linear_stiffness_and_loading_equal_the_reference_loops(libs, cas
     F = hd.get_vector(capi.LIN_OLD_STRESS)
     assert np.abs(F - F_ref).max() <= 1e-12 * np.abs(F_ref).max()
     hd.close()
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_device_newmark_updates_equal_the_reference_members(libs, case):
+    """gf_nl_end_step against the reference's own update_acceleration / update_velocity /
+    update_old_variables lines (nonlinear_elasticity.cc:592-622, coefficients .h:242-250)."""
+    capi = libs
+    ref = np.load(os.path.join(GOLDEN, "reference_vectors.npz"))
+    beta, gamma, dt = ref["upd%d_in" % case]
+    prob = make_problem(nl_params(poly_degree=1, beta=beta, gamma=gamma, delta_t=dt), 2, reps=[3, 2])
+    delta, total, v_old, a_old, rhs, upd = ref["upd%d_vecs" % case]
+    hd = capi.Handle(prob)
+    hd.set_vector(capi.NL_SOLUTION_DELTA, delta)
+    hd.set_vector(capi.NL_TOTAL_DISPLACEMENT, total)
+    hd.set_vector(capi.NL_VELOCITY_OLD, v_old)
+    hd.set_vector(capi.NL_ACCELERATION_OLD, a_old)
+    hd.nl_end_step()          # :139-144
+    for which, name in ((capi.NL_ACCELERATION, "acc"), (capi.NL_VELOCITY, "vel"),
+                        (capi.NL_TOTAL_DISPLACEMENT, "total")):
+        w = ref["upd%d_%s" % (case, name)]
+        assert np.abs(hd.get_vector(which) - w).max() <= 4e-16 * np.abs(w).max(), name
+    assert np.array_equal(hd.get_vector(capi.NL_VELOCITY_OLD), hd.get_vector(capi.NL_VELOCITY))
+    assert np.array_equal(hd.get_vector(capi.NL_ACCELERATION_OLD), hd.get_vector(capi.NL_ACCELERATION))
+    hd.close()
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_device_theta_scheme_rhs_equals_the_reference_block(libs, case):
+    """gf_lin_step's right-hand side against the reference's own assemble_rhs algebra
+    (linear_elasticity.cc:384-420; 'Force' data + body force, and 'Stress' data)."""
+    capi = libs
+    from helpers import lin_params
+    ref = np.load(os.path.join(GOLDEN, "reference_vectors.npz"))
+    theta, dt, consistent = ref["rhs%d_in" % case][:3]
+    bf = tuple(ref["rhs%d_in" % case][3:6])
+    p = lin_params(poly_degree=1, theta=theta, delta_t=dt, type_lin="CG",
+                   read_data_name="Stress" if consistent else "Force", body_force=bf)
+    prob = make_problem(p, 2, reps=[3, 2])
+    loading, stress, old_stress, vel, disp, bfv, new_vel = ref["rhs%d_vecs" % case]
+    hd = capi.Handle(prob)
+    hd.lin_assemble_once()
+    hd.set_vector(capi.LIN_STRESS, stress)
+    hd.set_vector(capi.LIN_OLD_STRESS, old_stress)
+    hd.set_vector(capi.LIN_VELOCITY, vel)
+    hd.set_vector(capi.LIN_DISPLACEMENT, disp)
+    hd.lin_step(0, 2.0)
+    free = prob.constrained == 0
+    want = ref["rhs%d_system_rhs" % case]
+    assert np.abs(hd.get_vector(capi.LIN_SYSTEM_RHS) - want)[free].max() <= 1e-11 * np.abs(want).max()
+    for name, which in (("old_stress", capi.LIN_OLD_STRESS), ("old_velocity", capi.LIN_OLD_VELOCITY),
+                        ("old_displacement", capi.LIN_OLD_DISPLACEMENT)):
+        w = ref["rhs%d_%s" % (case, name)]
+        assert np.abs(hd.get_vector(which) - w).max() <= 1e-12 * np.abs(w).max(), name
+    hd.close()

@@ -161,3 +161,70 @@ def test_oracle_linear_cell_matrix_and_loading_equal_the_reference_loops(native_
         assert np.abs(F - F_ref).max() <= 1e-12 * np.abs(F_ref).max(), k
         dt, theta = prob.params.delta_t, prob.params.theta
         assert np.abs(o.get(orc.LIN_SYSTEM_RHS) - dt * theta * F_ref).max() <= 1e-12 * dt * theta * np.abs(F_ref).max()
+
+
+def test_oracle_newmark_updates_and_norms_equal_the_reference_members(native_libs, ref):
+    """nonlinear_elasticity.h:242-250 (alpha_1..6) and .cc:549-622 (get_error_residual,
+    get_total_solution, update_acceleration, update_velocity), the reference's own lines."""
+    from oracle import oracle_py as orc
+    for k in range(2):
+        beta, gamma, dt = ref["upd%d_in" % k]
+        prob = make_problem(nl_params(poly_degree=1, beta=beta, gamma=gamma, delta_t=dt), 2, reps=[3, 2])
+        delta, total, v_old, a_old, rhs, upd = ref["upd%d_vecs" % k]
+        a1, a2, a3, a4, a5, a6 = ref["upd%d_alpha" % k]
+        assert np.allclose([a1, a2, a3, a4, a5, a6],
+                           [1 / (beta * dt ** 2), 1 / (beta * dt), (1 - 2 * beta) / (2 * beta),
+                            gamma / (beta * dt), 1 - gamma / beta, (1 - gamma / (2 * beta)) * dt],
+                           rtol=1e-15)
+        o = orc.Oracle(prob, n_threads=1)
+        o.set(orc.NL_SOLUTION_DELTA, delta)
+        o.set(orc.NL_TOTAL_DISPLACEMENT, total)
+        o.set(orc.NL_VELOCITY_OLD, v_old)
+        o.set(orc.NL_ACCELERATION_OLD, a_old)
+        o.set(orc.NL_SYSTEM_RHS, rhs)
+        o.nl_update_acceleration()
+        o.nl_update_velocity()
+        assert np.abs(o.get(orc.NL_ACCELERATION) - ref["upd%d_acc" % k]).max() <= 1e-15 * np.abs(ref["upd%d_acc" % k]).max()
+        assert np.abs(o.get(orc.NL_VELOCITY) - ref["upd%d_vel" % k]).max() <= 1e-15 * np.abs(ref["upd%d_vel" % k]).max()
+        assert np.array_equal(total + delta, ref["upd%d_total" % k])
+        res_norm, upd_norm = ref["upd%d_norms" % k]
+        assert abs(o.nl_error_residual() - res_norm) <= 1e-14 * res_norm
+        free = prob.constrained == 0
+        assert (~free).any()
+        assert abs(np.linalg.norm(upd[free]) - upd_norm) <= 1e-14 * upd_norm
+        o.nl_update_old_variables()
+        assert np.array_equal(o.get(orc.NL_VELOCITY_OLD), o.get(orc.NL_VELOCITY))
+
+
+def test_oracle_theta_scheme_rhs_equals_the_reference_block(native_libs, ref):
+    """linear_elasticity.cc:384-420 (assemble_rhs algebra with 'Force' and 'Stress' data, body
+    force) and :579-586 (update_displacement), the reference's own statements."""
+    from helpers import lin_params
+    from oracle import oracle_py as orc
+    for k in range(2):
+        theta, dt, consistent = ref["rhs%d_in" % k][:3]
+        bf = tuple(ref["rhs%d_in" % k][3:6])
+        p = lin_params(poly_degree=1, theta=theta, delta_t=dt,
+                       read_data_name="Stress" if consistent else "Force", body_force=bf)
+        prob = make_problem(p, 2, reps=[3, 2])
+        loading, stress, old_stress, vel, disp, bfv, new_vel = ref["rhs%d_vecs" % k]
+        o = orc.Oracle(prob, n_threads=1)
+        o.lin_assemble_system()
+        assert np.array_equal(o.csr(orc.MAT_STIFFNESS).toarray(), ref["rhs%d_K" % k])
+        assert np.array_equal(o.csr(orc.MAT_MASS).toarray(), ref["rhs%d_M" % k])
+        o.set(orc.LIN_STRESS, stress)
+        o.set(orc.LIN_OLD_STRESS, old_stress)
+        o.set(orc.LIN_VELOCITY, vel)
+        o.set(orc.LIN_DISPLACEMENT, disp)
+        o.lin_assemble_rhs()
+        free = prob.constrained == 0            # apply_boundary_values (:448-451) touches the rest
+        want = ref["rhs%d_system_rhs" % k]
+        assert np.abs(o.get(orc.LIN_SYSTEM_RHS) - want)[free].max() <= 1e-13 * np.abs(want).max()
+        for name, which in (("old_stress", orc.LIN_OLD_STRESS), ("old_velocity", orc.LIN_OLD_VELOCITY),
+                            ("old_displacement", orc.LIN_OLD_DISPLACEMENT)):
+            w = ref["rhs%d_%s" % (k, name)]
+            assert np.abs(o.get(which) - w).max() <= 1e-14 * max(np.abs(w).max(), 1e-300), name
+        o.set(orc.LIN_VELOCITY, new_vel)
+        o.lin_update_displacement()
+        w = ref["rhs%d_displacement" % k]
+        assert np.abs(o.get(orc.LIN_DISPLACEMENT) - w).max() <= 1e-15 * np.abs(w).max()
