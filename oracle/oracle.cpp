@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle.h). PARITY UNPINNED (no reference goldens exist).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle.h). Pinned in part by the reference's own code run here (oracle/_ref, tests/test_reference_pins.py); the deal.II-internal parts stay unpinned.
 //
 // Literal CPU/FP64 restatement of the dealii-adapter structural hot path. File:line citations are
 // relative to /root/reference. deal.II (v9.5.0, CI pin .github/workflows/building.yml:27) is not

@@ -7,12 +7,15 @@
  * PARITY PINNED IN PART: the reference ships no tests, golden vectors or fixtures for this path,
  * and as a whole it cannot be built here (deal.II >= 9.2 [CI: 9.5.0] and preCICE >= 3.0 are
  * absent, no network). Three header-only pieces DO compile in place against a small stand-in
- * (oracle/ref_shim, `make ref` -> oracle/_ref/ref_driver): the neo-Hookean material
- * (compressible_neo_hook_material.h), the Postprocessor (postprocessor.h) and Time
- * (time_handler.h); their outputs are committed as tests/golden/reference_vectors.npz and pin
- * orc_material, orc_postprocess and the Time mirrors (tests/test_reference_pins.py).
- * Everything else - the cell loop, the Neumann term, constraints, CG/SSOR, the theta scheme -
- * remains UNPINNED by the reference itself: deal.II semantics (FE_Q local order, QGauss, QProjector face order,
+ * (oracle/ref_shim, `make ref` -> oracle/_ref/): the neo-Hookean material, the Postprocessor
+ * and Time headers in place, and - cut out of the .cc/.h by marker at build time - the
+ * cell-assembly structs (tangent, residual, Neumann term), PointHistory, the Newmark coefficients
+ * and update/norm members, the linear model's local stiffness loops, consistent-loading face
+ * loop, theta-scheme right-hand side and displacement update. Their outputs are committed as
+ * tests/golden/reference_vectors.npz and pin the oracle (tests/test_reference_pins.py) and the
+ * device (tests/test_gpu_zz_reference_pins.py).
+ * What lives INSIDE deal.II - FE tables, distribute_local_to_global, SolverCG/SSOR,
+ * apply_boundary_values, create_mass_matrix - remains UNPINNED by the reference itself: deal.II semantics (FE_Q local order, QGauss, QProjector face order,
  * AffineConstraints::distribute_local_to_global, SolverCG, precondition_SSOR,
  * MatrixTools::apply_boundary_values) are restated from the published deal.II 9.5 algorithms.
  * The substitutes for golden vectors are the analytic known-answer tests in

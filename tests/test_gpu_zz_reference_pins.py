@@ -106,7 +106,7 @@ def test_device_newmark_updates_equal_the_reference_members(libs, case):
     for which, name in ((capi.NL_ACCELERATION, "acc"), (capi.NL_VELOCITY, "vel"),
                         (capi.NL_TOTAL_DISPLACEMENT, "total")):
         w = ref["upd%d_%s" % (case, name)]
-        assert np.abs(hd.get_vector(which) - w).max() <= 4e-16 * np.abs(w).max(), name
+        assert np.abs(hd.get_vector(which) - w).max() <= 1e-14 * np.abs(w).max(), name
     assert np.array_equal(hd.get_vector(capi.NL_VELOCITY_OLD), hd.get_vector(capi.NL_VELOCITY))
     assert np.array_equal(hd.get_vector(capi.NL_ACCELERATION_OLD), hd.get_vector(capi.NL_ACCELERATION))
     hd.close()
