@@ -31,6 +31,7 @@ namespace dealii
 {
   struct ExcPureFunctionCalled
   {};
+  inline const char *ExcMessage(const char *m) { return m; }
   namespace types
   {
     using global_dof_index = unsigned int;
@@ -314,6 +315,8 @@ namespace Parameters
     double mu = 0, nu = 0, rho = 0;
     double beta = 0, gamma = 0, theta = 0, delta_t = 0;
     bool   data_consistent = true;
+    unsigned int max_iterations_NR = 10;
+    double       tol_f = 1e-9, tol_u = 1e-6;
   };
 } // namespace Parameters
 #endif

@@ -23,6 +23,7 @@ DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
 ASM_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_assembler_driver")
 LIN_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_linear_driver")
 UPD_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_updates_driver")
+NEWTON_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_newton_driver")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 OUT = os.path.join(HERE, "reference_vectors.npz")
@@ -241,9 +242,51 @@ def run_update_cases():
     return out
 
 
+def newton_scripts():
+    """(max_iterations_NR, tol_f, tol_u, residual norms per assembly, update norms per solve)."""
+    cases = [
+        (10, 1e-9, 1e-6, [1.0, 0.1, 1e-4, 1e-11, 1e-12], [0.5, 1e-3, 1e-8, 1e-13]),
+        (10, 1e-9, 1e-6, [0.0] * 4, [0.0] * 4),                       # nothing to do: norms of 0
+        (10, 1e-9, 1e-6, [1e-9, 4e-9, 4e-9], [1e-16, 5e-16, 5e-16]),  # absolute criteria only
+        (5, 1e-9, 1e-6, [1.0] * 6, [1.0] * 6),                        # never converges
+        (10, 1e-9, 1e-6, [3.0, 2.0, 1e-10, 1e-10, 1e-12], [1.0, 1e-9, 1e-3, 1e-9, 1e-9]),
+        (1, 1e-9, 1e-6, [1.0, 1e-12], [1e-12]),                       # one iteration allowed
+        (3, 1e-9, 1e-6, [1.0, 1e-3, 1e-12, 1e-13], [1.0, 1e-4, 1e-9]),  # converges at the last check
+        (10, 1e-6, 1e-3, [5.0, 4.9e-6, 1e-7], [2.0, 1.9e-3, 1e-7]),   # just inside the tolerances
+        (10, 1e-6, 1e-3, [5.0, 5.1e-6, 1e-7, 1e-8], [2.0, 2.1e-3, 1e-7, 1e-9]),  # just outside
+    ]
+    rng = np.random.RandomState(55)
+    for _ in range(8):
+        n = 12
+        res = np.abs(rng.lognormal(0, 1)) * 10.0 ** (-rng.uniform(0.5, 4.0, n).cumsum())
+        upd = np.abs(rng.lognormal(0, 1)) * 10.0 ** (-rng.uniform(0.5, 4.0, n).cumsum())
+        cases.append((10, 1e-9, 1e-6, [float(x) for x in res], [float(x) for x in upd]))
+    return cases
+
+
+def run_newton_scripts():
+    out = {}
+    cases = newton_scripts()
+    for k, (max_it, tol_f, tol_u, res, upd) in enumerate(cases):
+        n = max(len(res), len(upd), max_it + 1)
+        res = list(res) + [res[-1]] * (n - len(res))
+        upd = list(upd) + [upd[-1]] * (n - len(upd))
+        txt = subprocess.run([NEWTON_DRIVER], input=fmt([max_it, tol_f, tol_u, n] + res + upd),
+                             capture_output=True, text=True, check=True).stdout.split("\n")
+        solves, assemblies, converged = (int(x) for x in txt[0].split())
+        out["newton%02d_in" % k] = np.array([max_it, tol_f, tol_u])
+        out["newton%02d_res" % k] = np.array(res)
+        out["newton%02d_upd" % k] = np.array(upd)
+        out["newton%02d_out" % k] = np.array([solves, assemblies, converged])
+        out["newton%02d_last" % k] = np.array(txt[1].split(), dtype=float)
+    out["n_newton"] = np.array(len(cases))
+    return out
+
+
 def generate():
     out = {}
     out.update(run_update_cases())
+    out.update(run_newton_scripts())
     lcases = linear_cases()
     for k, c in enumerate(lcases):
         out.update(run_linear_case(k, *c))

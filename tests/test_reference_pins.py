@@ -228,3 +228,49 @@ def test_oracle_theta_scheme_rhs_equals_the_reference_block(native_libs, ref):
         o.lin_update_displacement()
         w = ref["rhs%d_displacement" % k]
         assert np.abs(o.get(orc.LIN_DISPLACEMENT) - w).max() <= 1e-15 * np.abs(w).max()
+
+
+class ScriptedHandle:
+    """Stands in for the device handle: hands out scripted residual / update norms."""
+
+    def __init__(self, res, upd):
+        self.res, self.upd, self.n_asm, self.n_solve = list(res), list(upd), 0, 0
+
+    def nl_newton_assemble(self):
+        self.n_asm += 1
+        return self.res[self.n_asm - 1]
+
+    def nl_newton_solve(self, type_lin, tol_lin, max_iterations_lin):
+        self.n_solve += 1
+        return 1, 0.0, self.upd[self.n_solve - 1]
+
+
+def test_newton_driver_mirror_follows_the_reference_control_flow(ref):
+    """Solid::solve_nonlinear_timestep (nonlinear_elasticity.cc:410-499) with its Errors struct, the
+    reference's own code fed with scripted norms (17 scripts: convergence by relative and by
+    absolute criteria, zero norms, no convergence, the last admissible iteration...), against the
+    host mirror that drives the device (dealii_adapter_b200/solvers.py)."""
+    from dealii_adapter_b200 import solvers
+    n = int(ref["n_newton"])
+    assert n == 17
+    outcomes = set()
+    for k in range(n):
+        max_it, tol_f, tol_u = ref["newton%02d_in" % k]
+        want_solves, want_asm, want_conv = (int(x) for x in ref["newton%02d_out" % k])
+        s = solvers.Solid.__new__(solvers.Solid)
+        s.parameters = nl_params(max_iterations_NR=int(max_it), tol_f=tol_f, tol_u=tol_u)
+        s.handle = ScriptedHandle(ref["newton%02d_res" % k], ref["newton%02d_upd" % k])
+        s.history, s.newton_solves, s.assemblies = [], 0, 0
+        try:
+            rows = s.solve_nonlinear_timestep()
+            converged = 1
+        except RuntimeError as e:
+            assert "No convergence in nonlinear solver!" in str(e)
+            converged, rows = 0, None
+        assert (s.handle.n_solve, s.handle.n_asm, converged) == (want_solves, want_asm, want_conv), k
+        outcomes.add((converged, want_solves))
+        if converged and rows:
+            # normalised errors of the last solve as the reference derived them
+            res_norm, res_abs, upd_norm, upd_abs = ref["newton%02d_last" % k]
+            assert rows[-1][4] == upd_norm and rows[-1][5] == upd_abs
+    assert {c for c, _ in outcomes} == {0, 1} and len(outcomes) >= 5
