@@ -24,6 +24,7 @@ ASM_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_assembler_driver")
 LIN_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_linear_driver")
 UPD_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_updates_driver")
 NEWTON_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_newton_driver")
+ADAPTER_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_adapter_driver")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 OUT = os.path.join(HERE, "reference_vectors.npz")
@@ -283,8 +284,33 @@ def run_newton_scripts():
     return out
 
 
+def run_adapter_cases():
+    """The reference's Adapter::format_deal_to_precice / format_precice_to_deal / checkpoint
+    members (adapter.h:389-489) on the interface index sets of two small problems, with
+    component_wise numbering (the reference renumbers component-wise, nonlinear:318)."""
+    from helpers import nl_params
+    from dealii_adapter_b200.problem import make_problem
+    out = {}
+    for k, (dim, reps, degree) in enumerate(((2, [3, 4], 2), (3, [2, 3, 2], 1))):
+        prob = make_problem(nl_params(poly_degree=degree), dim, reps=reps, numbering="component_wise")
+        n, ni = prob.n_dofs, prob.n_iface_nodes
+        rng = np.random.RandomState(500 + k)
+        vec = rng.uniform(-1, 1, n)
+        buf = rng.uniform(-1, 1, dim * ni)
+        words = [dim, n, ni] + [int(i) for i in prob.iface_dofs.reshape(-1)] + list(vec) + list(buf)
+        res = subprocess.run([ADAPTER_DRIVER], input=fmt(words), capture_output=True, text=True,
+                             check=True).stdout.strip().split("\n")
+        out["adp%d_meta" % k] = np.array([dim, degree] + reps)
+        out["adp%d_vec" % k], out["adp%d_buf" % k] = vec, buf
+        out["adp%d_write" % k] = np.array(res[0].split(), dtype=float)
+        out["adp%d_after_read" % k] = np.array(res[1].split(), dtype=float)
+        out["adp%d_checkpoint" % k] = np.array(" ".join(res[2:]).split(), dtype=float)
+    return out
+
+
 def generate():
     out = {}
+    out.update(run_adapter_cases())
     out.update(run_update_cases())
     out.update(run_newton_scripts())
     lcases = linear_cases()

@@ -140,3 +140,22 @@ def test_device_theta_scheme_rhs_equals_the_reference_block(libs, case):
         w = ref["rhs%d_%s" % (case, name)]
         assert np.abs(hd.get_vector(which) - w).max() <= 1e-12 * np.abs(w).max(), name
     hd.close()
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_device_adapter_bodies_equal_the_reference_members(libs, case):
+    """gf_get_interface_displacement / gf_set_traction against the reference's own
+    format_deal_to_precice / format_precice_to_deal (adapter.h:389-443), bit for bit."""
+    capi = libs
+    ref = np.load(os.path.join(GOLDEN, "reference_vectors.npz"))
+    meta = ref["adp%d_meta" % case]
+    dim, degree, reps = int(meta[0]), int(meta[1]), [int(x) for x in meta[2:]]
+    prob = make_problem(nl_params(poly_degree=degree), dim, reps=reps, numbering="component_wise")
+    vec, buf = ref["adp%d_vec" % case], ref["adp%d_buf" % case]
+    hd = capi.Handle(prob)
+    hd.set_vector(capi.NL_TOTAL_DISPLACEMENT, vec)
+    assert np.array_equal(hd.get_interface_displacement(), ref["adp%d_write" % case])
+    hd.set_vector(capi.NL_EXTERNAL_STRESS, vec)
+    hd.set_traction(buf)
+    assert np.array_equal(hd.get_vector(capi.NL_EXTERNAL_STRESS), ref["adp%d_after_read" % case])
+    hd.close()

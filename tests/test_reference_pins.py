@@ -274,3 +274,54 @@ def test_newton_driver_mirror_follows_the_reference_control_flow(ref):
             res_norm, res_abs, upd_norm, upd_abs = ref["newton%02d_last" % k]
             assert rows[-1][4] == upd_norm and rows[-1][5] == upd_abs
     assert {c for c, _ in outcomes} == {0, 1} and len(outcomes) >= 5
+
+
+def test_oracle_adapter_bodies_equal_the_reference_members(native_libs, ref):
+    """Adapter::format_deal_to_precice / format_precice_to_deal (adapter.h:389-443) on the
+    interface IndexSets of two problems, the reference's own member definitions; and its
+    checkpoint members (:447-489) against the host mirror's save / reload logic."""
+    from oracle import oracle_py as orc
+    from dealii_adapter_b200 import solvers
+    for k in range(2):
+        meta = ref["adp%d_meta" % k]
+        dim, degree, reps = int(meta[0]), int(meta[1]), [int(x) for x in meta[2:]]
+        prob = make_problem(nl_params(poly_degree=degree), dim, reps=reps, numbering="component_wise")
+        vec, buf = ref["adp%d_vec" % k], ref["adp%d_buf" % k]
+        o = orc.Oracle(prob, n_threads=1)
+        o.set(orc.NL_TOTAL_DISPLACEMENT, vec)
+        assert np.array_equal(o.format_deal_to_precice(orc.NL_TOTAL_DISPLACEMENT), ref["adp%d_write" % k])
+        o.set(orc.NL_EXTERNAL_STRESS, vec)
+        o.format_precice_to_deal(buf, orc.NL_EXTERNAL_STRESS)
+        assert np.array_equal(o.get(orc.NL_EXTERNAL_STRESS), ref["adp%d_after_read" % k])
+        # checkpoint script of oracle/ref_adapter_driver.cc replayed on the host mirror
+        cp = ref["adp%d_checkpoint" % k]
+
+        class Flags:
+            write = read = False
+            def requiresWritingCheckpoint(self): return self.write
+            def requiresReadingCheckpoint(self): return self.read
+
+        class CountingHandle:
+            saves = restores = 0
+            def state_save(self): self.saves += 1
+            def state_restore(self): self.restores += 1
+
+        a = solvers.Adapter.__new__(solvers.Adapter)
+        a.precice, a._h, a.old_time_value = Flags(), CountingHandle(), 0.0
+        t = solvers.Time(1e9, 0.01)
+        for _ in range(3):
+            t.increment()
+        a.save_current_state_if_required(t)
+        assert a._h.saves == int(cp[0]) == 0
+        a.precice.write = True
+        a.save_current_state_if_required(t)
+        a.precice.write = False
+        assert a._h.saves == 1 and int(cp[1]) == 2 and a.old_time_value == cp[2]
+        t.increment()
+        t.increment()
+        a.reload_old_state_if_required(t)
+        assert (t.get_timestep(), t.current(), a._h.restores) == (int(cp[3]), cp[4], 0)
+        a.precice.read = True
+        a.reload_old_state_if_required(t)
+        assert (t.get_timestep(), t.current(), a._h.restores) == (int(cp[6]), cp[7], 1)
+        assert int(cp[8]) == 1          # the reference restored exactly the checkpointed vectors
