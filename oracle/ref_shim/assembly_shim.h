@@ -16,6 +16,7 @@
 #include <deal.II/base/dealii_min.h>
 
 #include <memory>
+#include <string>
 #include <stdexcept>
 #include <utility>
 
@@ -315,6 +316,8 @@ namespace Parameters
     double mu = 0, nu = 0, rho = 0;
     double beta = 0, gamma = 0, theta = 0, delta_t = 0;
     bool   data_consistent = true;
+    std::string  scenario = "FSI3";
+    double       flap_location = 0.0;
     unsigned int max_iterations_NR = 10;
     double       tol_f = 1e-9, tol_u = 1e-6;
   };

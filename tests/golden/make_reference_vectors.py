@@ -25,6 +25,7 @@ LIN_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_linear_driver")
 UPD_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_updates_driver")
 NEWTON_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_newton_driver")
 ADAPTER_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_adapter_driver")
+GRID_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_grid_driver")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 OUT = os.path.join(HERE, "reference_vectors.npz")
@@ -308,8 +309,31 @@ def run_adapter_cases():
     return out
 
 
+def run_grid_cases():
+    """make_grid of both solvers (nonlinear_elasticity.cc:169-285, linear_elasticity.cc:79-187):
+    per (solver, dim, scenario): [volume, dim, refinements, interface id, clamped id, z-clamp id],
+    repetitions, box corners, and the boundary id each colorized face (x-,x+,y-,y+,z-,z+) gets."""
+    out = {}
+    k = 0
+    for solver in ("nl", "lin"):
+        for dim in (2, 3):
+            for scenario, flap in (("FSI3", 0.0), ("PF", 0.0), ("PF", 0.25)):
+                txt = subprocess.run([GRID_DRIVER, solver, str(dim), scenario, repr(flap)],
+                                     capture_output=True, text=True, check=True).stdout.split("\n")
+                out["grid%02d_key" % k] = np.array([solver, str(dim), scenario, repr(flap)])
+                out["grid%02d_head" % k] = np.array([float(txt[0])] + [float(x) for x in txt[1].split()])
+                out["grid%02d_reps" % k] = np.array(txt[2].split(), dtype=np.int64)
+                out["grid%02d_p0" % k] = np.array(txt[3].split(), dtype=float)
+                out["grid%02d_p1" % k] = np.array(txt[4].split(), dtype=float)
+                out["grid%02d_face_ids" % k] = np.array(txt[5].split(), dtype=np.int64)
+                k += 1
+    out["n_grid"] = np.array(k)
+    return out
+
+
 def generate():
     out = {}
+    out.update(run_grid_cases())
     out.update(run_adapter_cases())
     out.update(run_update_cases())
     out.update(run_newton_scripts())

@@ -325,3 +325,31 @@ def test_oracle_adapter_bodies_equal_the_reference_members(native_libs, ref):
         a.reload_old_state_if_required(t)
         assert (t.get_timestep(), t.current(), a._h.restores) == (int(cp[6]), cp[7], 1)
         assert int(cp[8]) == 1          # the reference restored exactly the checkpointed vectors
+
+
+def test_scenario_geometry_and_boundary_roles_equal_the_reference_make_grid(ref):
+    """make_grid of both solver classes (nonlinear_elasticity.cc:169-285, linear_elasticity.cc:
+    79-187), the reference's own member definitions run against a recording grid generator:
+    repetitions, box corners and which colorized face becomes clamped / interface / z-clamped,
+    against the host mirror's scenario table (dealii_adapter_b200/mesh.py; the C++ host uses the
+    same table, host/host_problem.cc)."""
+    from dealii_adapter_b200.mesh import scenario_geometry
+    n = int(ref["n_grid"])
+    assert n == 12
+    for k in range(n):
+        solver, dim, scenario, flap = ref["grid%02d_key" % k]
+        dim, flap = int(dim), float(flap)
+        vol, rdim, refinements, interface_id, clamped_id, zclamp_id = ref["grid%02d_head" % k]
+        assert (int(rdim), int(refinements)) == (dim, 0)
+        assert int(interface_id) == (7 if solver == "nl" else 6)
+        p0, p1, reps, clamped, interface, zclamp = scenario_geometry(scenario, dim, flap)
+        assert list(ref["grid%02d_reps" % k]) == list(reps)
+        assert np.array_equal(ref["grid%02d_p0" % k], np.array(p0, dtype=float))
+        assert np.array_equal(ref["grid%02d_p1" % k], np.array(p1, dtype=float))
+        ids = ref["grid%02d_face_ids" % k]          # final id of colorized face f = x-,x+,y-,y+,z-,z+
+        for f in range(2 * dim):
+            role = ("clamped" if (clamped >> f) & 1 else "interface" if (interface >> f) & 1
+                    else "zclamp" if (zclamp >> f) & 1 else "none")
+            want = {"clamped": clamped_id, "interface": interface_id, "zclamp": zclamp_id}[role]
+            assert ids[f] == want, (solver, dim, scenario, f)
+        assert abs(vol - np.prod(np.array(p1) - np.array(p0))) < 1e-15
