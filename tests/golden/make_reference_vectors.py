@@ -26,6 +26,7 @@ UPD_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_updates_driver")
 NEWTON_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_newton_driver")
 ADAPTER_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_adapter_driver")
 GRID_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_grid_driver")
+PRM_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_parameters_driver")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 OUT = os.path.join(HERE, "reference_vectors.npz")
@@ -331,8 +332,68 @@ def run_grid_cases():
     return out
 
 
+def prm_cases():
+    base = open(os.path.join(HERE, "parameters_nonlinear_fsi3.prm")).read()
+    linear = """# linear model, conservative data, body force, other scenario
+subsection Time
+  set End time        = 2.5
+  set Time step size  = 0.005   # trailing comment
+  set Output interval = 25
+  set Output folder   = out
+end
+subsection Discretization
+  set Polynomial degree = 1
+  set theta             = 0.6
+end
+subsection System properties
+  set Shear modulus   = 1.2e6
+  set Poisson's ratio = 0.25
+  set rho             = 3000
+  set body forces     = 0.0, -9.81, 0.5
+end
+subsection Solver
+  set Model                    = linear
+  set Solver type              = CG
+  set Max iteration multiplier = 1.5
+end
+subsection precice configuration
+  set Scenario         = PF
+  set Read data name   = Force-Data
+  set Flap location    = 1.5
+  set Participant name = Flap
+end
+"""
+    cases = [base, "", linear,
+             base.replace("set rho ", "set density "),                        # undeclared entry
+             base.replace("subsection Solver", "subsection Linear solver"),   # undeclared subsection
+             base.replace("= 0.4", "= 0.7"),                                  # nu outside [-1, 0.5]
+             base.replace("= neo-Hookean", "= hyperelastic"),                 # not in the selection
+             base.replace("= Stress", "= Pressure"),                          # neither Stress nor Force
+             base.replace("set beta                = 0.25", "set beta                = 0.7"),
+             base.replace("Output interval       = 10", "Output interval       = -1"),
+             linear.replace("0.0, -9.81, 0.5", "0.0, -9.81")]                # two body-force entries
+    return cases
+
+
+def run_prm_cases():
+    import tempfile
+    out = {}
+    cases = prm_cases()
+    for k, text in enumerate(cases):
+        with tempfile.NamedTemporaryFile("w", suffix=".prm", delete=False) as f:
+            f.write(text)
+        r = subprocess.run([PRM_DRIVER, f.name], capture_output=True, text=True)
+        os.unlink(f.name)
+        out["prm%02d_text" % k] = np.array(text)
+        out["prm%02d_exit" % k] = np.array(r.returncode)
+        out["prm%02d_out" % k] = np.array(r.stdout if r.returncode == 0 else "")
+    out["n_prm"] = np.array(len(cases))
+    return out
+
+
 def generate():
     out = {}
+    out.update(run_prm_cases())
     out.update(run_grid_cases())
     out.update(run_adapter_cases())
     out.update(run_update_cases())

@@ -353,3 +353,41 @@ def test_scenario_geometry_and_boundary_roles_equal_the_reference_make_grid(ref)
             want = {"clamped": clamped_id, "interface": interface_id, "zclamp": zclamp_id}[role]
             assert ids[f] == want, (solver, dim, scenario, f)
         assert abs(vol - np.prod(np.array(p1) - np.array(p0))) < 1e-15
+
+
+def test_host_parameter_parser_equals_the_reference_parameters(tmp_path, ref):
+    """Parameters::AllParameters of the reference (include/adapter/parameters.{h,cc}, compiled
+    unmodified against a ParameterHandler stand-in) and of the C++ host mirror
+    (dealii_adapter_b200/host/parameters.cc), printed by the SAME program
+    (oracle/ref_parameters_driver.cc), for 11 .prm files: every field equal for the valid ones
+    (defaults, derived lambda, 'Force' -> conservative data), exit code 1 for the rejected ones
+    (undeclared entry / subsection, out-of-pattern values, unknown read data type)."""
+    root = os.path.dirname(os.path.dirname(GOLDEN))
+    exe = tmp_path / "print_host_parameters"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(root, "dealii_adapter_b200", "host"),
+                           "-o", str(exe), os.path.join(root, "oracle", "ref_parameters_driver.cc"),
+                           os.path.join(root, "dealii_adapter_b200", "host", "parameters.cc")])
+    n = int(ref["n_prm"])
+    assert n == 11
+    n_ok = 0
+    for k in range(n):
+        f = tmp_path / ("case%02d.prm" % k)
+        f.write_text(str(ref["prm%02d_text" % k]))
+        r = subprocess.run([str(exe), str(f)], capture_output=True, text=True)
+        assert r.returncode == int(ref["prm%02d_exit" % k]), (k, r.stdout)
+        if r.returncode == 0:
+            assert r.stdout == str(ref["prm%02d_out" % k]), k
+            n_ok += 1
+    assert n_ok == 3
+    # the Python mirror's defaults are the reference's defaults (case 1: empty file)
+    from dealii_adapter_b200.problem import SolverParameters
+    d = dict(l.split(" = ", 1) for l in str(ref["prm01_out"]).strip().split("\n"))
+    p = SolverParameters()
+    for key in ("end_time", "delta_t", "nu", "mu", "rho", "tol_lin", "max_iterations_lin", "tol_f",
+                "tol_u", "theta", "beta", "gamma", "flap_location"):
+        assert getattr(p, key) == float(d[key]), key
+    assert (p.model, p.type_lin, p.scenario, p.read_data_name) == \
+        (d["model"], d["type_lin"], d["scenario"], d["read_data_name"])
+    assert (p.poly_degree, p.max_iterations_NR, p.output_interval) == \
+        (int(d["poly_degree"]), int(d["max_iterations_NR"]), int(d["output_interval"]))
+    assert abs(p.lam - float(d["lambda"])) <= 1e-9 * abs(float(d["lambda"]))
