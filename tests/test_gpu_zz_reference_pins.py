@@ -82,7 +82,7 @@ def test_device_linear_stiffness_and_loading_equal_the_reference_loops(libs, cas
     K_ref, F_ref = ref["lin%d_K" % case], ref["lin%d_F" % case]
     assert np.abs(K - K_ref).max() <= 1e-12 * np.abs(K_ref).max()
     hd.set_vector(capi.LIN_STRESS, ref["lin%d_stress" % case])
-    hd.lin_step(0, 2.0)                      # old_stress <- the consistent loading (:405-409)
+    hd.lin_step(0, 10.0)                      # old_stress <- the consistent loading (:405-409)
     F = hd.get_vector(capi.LIN_OLD_STRESS)
     assert np.abs(F - F_ref).max() <= 1e-12 * np.abs(F_ref).max()
     hd.close()
@@ -131,7 +131,7 @@ def test_device_theta_scheme_rhs_equals_the_reference_block(libs, case):
     hd.set_vector(capi.LIN_OLD_STRESS, old_stress)
     hd.set_vector(capi.LIN_VELOCITY, vel)
     hd.set_vector(capi.LIN_DISPLACEMENT, disp)
-    hd.lin_step(0, 2.0)
+    hd.lin_step(0, 10.0)
     free = prob.constrained == 0
     want = ref["rhs%d_system_rhs" % case]
     assert np.abs(hd.get_vector(capi.LIN_SYSTEM_RHS) - want)[free].max() <= 1e-11 * np.abs(want).max()
