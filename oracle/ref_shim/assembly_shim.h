@@ -316,6 +316,7 @@ namespace Parameters
     double mu = 0, nu = 0, rho = 0;
     double beta = 0, gamma = 0, theta = 0, delta_t = 0;
     bool   data_consistent = true;
+    int          output_interval = 1;
     std::string  scenario = "FSI3";
     double       flap_location = 0.0;
     unsigned int max_iterations_NR = 10;

@@ -27,6 +27,7 @@ NEWTON_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_newton_driver")
 ADAPTER_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_adapter_driver")
 GRID_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_grid_driver")
 PRM_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_parameters_driver")
+RUN_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_run_driver")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 OUT = os.path.join(HERE, "reference_vectors.npz")
@@ -391,8 +392,26 @@ def run_prm_cases():
     return out
 
 
+def run_loop_cases():
+    """Event order of the reference's own run() loops (nonlinear_elasticity.cc:96-167,
+    linear_elasticity.cc:632-716) under a scripted coupling scheme:
+    (solver, windows, sub-iterations, output interval, solver dt, preCICE window size)."""
+    cases = [("nl", 2, 1, 1, 0.01, 0.01), ("nl", 2, 3, 1, 0.01, 0.01), ("nl", 3, 2, 2, 0.01, 0.01),
+             ("lin", 3, 1, 1, 0.01, 0.01), ("lin", 2, 2, 1, 0.01, 0.01),
+             ("nl", 1, 1, 1, 0.01, 0.02), ("lin", 1, 1, 1, 0.01, 0.02)]
+    out = {}
+    for k, c in enumerate(cases):
+        r = subprocess.run([RUN_DRIVER] + [str(x) for x in c], capture_output=True, text=True)
+        out["loop%d_case" % k] = np.array([str(x) for x in c])
+        out["loop%d_exit" % k] = np.array(r.returncode)
+        out["loop%d_events" % k] = np.array(r.stdout.strip().split("\n"))
+    out["n_loop"] = np.array(len(cases))
+    return out
+
+
 def generate():
     out = {}
+    out.update(run_loop_cases())
     out.update(run_prm_cases())
     out.update(run_grid_cases())
     out.update(run_adapter_cases())

@@ -117,3 +117,81 @@ def test_linear_model_call_sequence(env, tmp_path):
     assert r.returncode == 0, r.stderr
     assert calls == ["create", "postprocess", "lin_assemble_once"] + \
         ["set_traction", "lin_step", "get_interface_displacement"] * 3 + ["destroy"]
+
+
+def expected_calls(events, newton):
+    """C-ABI calls the host mirror must issue for the event order of the reference's run()."""
+    out, k = [], 0
+    while k < len(events):
+        e = events[k]
+        if e in ("system_setup", "setup_system"):
+            out.append("create")
+        elif e.startswith("output_results@"):
+            out.append("postprocess")
+        elif e == "assemble_system":
+            out.append("lin_assemble_once")
+        elif e == "adapter.save_current_state_if_required:1":
+            out.append("state_save")
+        elif e == "adapter.reload_old_state_if_required:1":
+            out.append("state_restore")
+        elif e == "solution_delta=0":
+            out.append("nl_begin_step")
+        elif e.startswith("adapter.read_data"):
+            out.append("set_traction")
+        elif e == "solve_nonlinear_timestep":
+            out += newton
+        elif e == "total_displacement+=solution_delta":
+            assert events[k + 1:k + 4] == ["update_acceleration", "update_velocity", "update_old_variables"]
+            out.append("nl_end_step")
+            k += 3
+        elif e == "assemble_rhs":
+            assert events[k + 1:k + 3] == ["solve", "update_displacement"]
+            out.append("lin_step")
+            k += 2
+        elif e.startswith("adapter.advance"):
+            out.append("get_interface_displacement")
+        elif e == "precice.finalize":
+            out.append("destroy")
+        k += 1
+    return out
+
+
+@pytest.mark.parametrize("k", range(7))
+def test_coupling_loop_of_the_cxx_mirror_follows_the_reference_run(env, tmp_path, k):
+    """The order of events of the reference's own run() (nonlinear_elasticity.cc:96-167,
+    linear_elasticity.cc:632-716; cut out and run against recording stand-ins under a scripted
+    coupling scheme, tests/golden/reference_vectors.npz) against the C-ABI call log of the C++ host
+    under the same scheme: checkpoint save before the step, restore after advance, output only for
+    completed windows at the output interval, the constant-step-size error."""
+    ref = np.load(os.path.join(GOLDEN, "reference_vectors.npz"))
+    solver, windows, sub, interval, dt, dt_precice = (str(x) for x in ref["loop%d_case" % k])
+    events = [str(e) for e in ref["loop%d_events" % k]]
+    prm = nl_prm(**{"Output interval       = 10": "Output interval       = %s" % interval})
+    if solver == "lin":
+        prm = prm.replace("Model                     = neo-Hookean", "Model                     = linear")
+    n_pass = int(windows) * int(sub)
+    exes, lib = env
+    (tmp_path / "parameters.prm").write_text(prm)
+    (tmp_path / "precice-config.fake").write_text(
+        FAKE_CFG.format(windows=windows, sub=sub).replace("time-window-size = 0.01",
+                                                          "time-window-size = %s" % dt_precice))
+    (tmp_path / "script.txt").write_text(" ".join(["1.0", "1e-3", "1e-12"] * n_pass) + "\n" +
+                                         " ".join(["1.0", "1e-9"] * n_pass) + "\n")
+    e = dict(os.environ, LD_PRELOAD=lib, GF_FAKE_LOG=str(tmp_path / "calls.log"),
+             GF_FAKE_SCRIPT=str(tmp_path / "script.txt"), GF_PRECONDITIONER="block-jacobi")
+    r = subprocess.run([exes[0], "parameters.prm"], cwd=tmp_path, capture_output=True, text=True,
+                       timeout=120, env=e)
+    calls = [l.split()[0] for l in (tmp_path / "calls.log").read_text().splitlines()]
+    newton = ["nl_newton_assemble", "nl_newton_solve"] * 2 + ["nl_newton_assemble"]
+    want = expected_calls(events, newton)
+    if int(ref["loop%d_exit" % k]) == 0:
+        assert r.returncode == 0, r.stderr
+        assert calls == want
+        # output file indices = timestep / interval of every output_results event (:1240-1243)
+        idx = sorted({int(e.split("@")[1]) // int(interval) for e in events if e.startswith("output_results@")})
+        got = sorted(int(f.name[9:12]) for f in (tmp_path / "dealii-output").glob("solution-*.vtk"))
+        assert got == idx
+    else:
+        assert any(e.startswith("THROW:") for e in events)
+        assert r.returncode == 1 and "This solver supports only constant time-step sizes" in r.stderr
+        assert calls[:len(want)] == want          # everything up to the throw, then the destructor
