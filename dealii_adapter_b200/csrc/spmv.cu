@@ -7,21 +7,31 @@
 // index per value instead of CSR's 8+4. HBM-bound; algorithmic bytes per launch =
 // 8*n_val + 4*n_blocks + 4*(n_rows+1) + 8*(n_rows+1) + 8*n_local(x) + 8*n_owned(y).
 //
-// Main kernel (spmv_tma_kernel): persistent, one CTA per SM, warp-specialised. A producer warp
-// streams TILES (runs of consecutive rows: <= 48 KB of values + their column indices + per-row
-// records, built once in pattern.cu) into a 3-stage shared-memory ring with TMA bulk copies
-// (cp.async.bulk ... mbarrier::complete_tx); 8 gather warps pull x[col] for the whole tile into shared memory (many
-// independent read-only loads per lane), 8 consumer warps then do pure shared-memory FMAs. The bytes in flight (~100 KB/SM) live in shared memory, not registers: the ncu capture
-// of the LDG version (profiles/r01_spmv_ncu_summary.md) showed it latency-bound at 32 warps/SM.
-// Fallback (spmv_kernel, LDG): one warp per row with double2 streaming loads; used when a row
-// does not fit a tile or when GF_OPT_SPMV_KERNEL = 1.
+// Kernels (GF_OPT_SPMV_KERNEL; all return bitwise identical y: same tiles, same per-row
+// summation order). TILES are runs of consecutive rows (<= 6144 values + their column indices +
+// per-row records), built once in pattern.cu; every TMA kernel is persistent (one CTA per SM) and
+// warp-specialised, operands arrive by TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx,
+// SASS UBLKCP) in mbarrier-guarded shared-memory rings, so the bytes in flight live in shared
+// memory, not registers (the LDG version was latency-bound at 32 warps/SM,
+// profiles/r01_spmv_ncu_summary.md):
+//   5  spmv_tma_kernel: one 3-stage ring carries a tile through TMA -> x gather (8 warps) ->
+//      FMA (8 warps). 0.624 ms on the cfg3 tangent (5.33 TB/s).
+//   2/3/4  spmv_tma2_kernel<.., GW, GG, CW>: column indices / row records / gathered x in their own
+//      deeper ring running ahead of the value ring; GG groups of gather warps work on consecutive
+//      tiles; CW consumer warps. 8+16 warps (kind 3): 0.549 ms = 6.05 TB/s = 92 % of the measured
+//      copy peak - the consumer warps, not HBM or the gather, bounded the 8-consumer kernels
+//      (profiles/r01_spmv_variants_ncu.md).
+//   0  (default) kind 3 for plain launches, kind 5 for launches with the fused dot product.
+//   1  spmv_kernel (LDG): one warp per row with streaming loads; also the fallback when a row
+//      does not fit a tile.
 // The fused dot product needs only gridDim.x partial sums (fixed order => reproducible).
 //
 // Value type VT: double for every operator application whose result the reference defines (CG
 // vmult, assemble_rhs vmults). VT = float streams a single-precision COPY of the same array
 // (same indexing, 4 B per value) and is used ONLY inside the multigrid V-cycle when
 // GF_OPT_MG_MATRIX_PRECISION = 1: the preconditioner replaces the reference's SSOR and may be
-// any fixed SPD operator; vectors, accumulation and the outer CG stay FP64.
+// any fixed SPD operator; vectors, accumulation and the outer CG stay FP64
+// (GF_OPT_MG_MATRIX_PRECISION = 2, experimental: x staging and accumulation in FP32 as well).
 #include "gf_context.h"
 #include "kernel_utils.cuh"
 
