@@ -331,31 +331,8 @@ def main():
     # ---- variants benchmarked alongside (north_star: matrix-free operator beside the SpMV) ------
     variants = {}
     if not args.no_variants and world == 1 and os.environ.get("GF_PROFILE_RUN") != "1":
-        h.set_option(capi.OPT_OPERATOR, 1)
-        for k in range(N_SUB):
-            resident_pass(k)
-        s0 = solid.newton_solves
-        h0v = len(solid.history)
-        barrier()
-        h.event_record(2)
-        t0 = time.perf_counter()
-        for k in range(N_SUB):
-            resident_pass(k)
-        h.event_record(3)
-        barrier()
-        tv = max(time.perf_counter() - t0, 1e-3 * h.event_elapsed_ms(2, 3))
-        ms_mf, mf_bytes = h.spmv_timed(capi.MAT_TANGENT, 5)
-        variants["matrix_free_operator"] = {
-            "what": "sum-factorised matrix-free tangent (K11) on the finest level instead of the "
-                    "assembled BSR SpMV; coarser levels assembled; same CG + V-cycle",
-            "value": n_dofs_global * (solid.newton_solves - s0) / tv, "unit": "DoFs/s",
-            "steps": N_SUB, "newton_solves": solid.newton_solves - s0,
-            "cg_iterations": cg_iterations(h0v), "operator_apply_ms": ms_mf,
-            "operator_bytes_per_apply": mf_bytes}
-        h.set_option(capi.OPT_OPERATOR, 0)
-        if args.precond == "mg":
-            # the V-cycle streaming FP32 copies of the level matrices (outer CG stays FP64)
-            h.set_option(capi.OPT_MG_MATRIX_PRECISION, 1)
+        try:
+            h.set_option(capi.OPT_OPERATOR, 1)
             for k in range(N_SUB):
                 resident_pass(k)
             s0 = solid.newton_solves
@@ -368,33 +345,66 @@ def main():
             h.event_record(3)
             barrier()
             tv = max(time.perf_counter() - t0, 1e-3 * h.event_elapsed_ms(2, 3))
-            ms32, bytes32 = h.spmv_timed(capi.MAT_MG_F32, 5)
-            variants["vcycle_fp32_matrices"] = {
-                "what": "GF_OPT_MG_MATRIX_PRECISION = 1: smoother / residual applications inside "
-                        "the V-cycle stream FP32 copies of the level matrices (vectors, "
-                        "accumulation, the CG operator and its residual test stay FP64)",
+            ms_mf, mf_bytes = h.spmv_timed(capi.MAT_TANGENT, 5)
+            variants["matrix_free_operator"] = {
+                "what": "sum-factorised matrix-free tangent (K11) on the finest level instead of the "
+                        "assembled BSR SpMV; coarser levels assembled; same CG + V-cycle",
                 "value": n_dofs_global * (solid.newton_solves - s0) / tv, "unit": "DoFs/s",
                 "steps": N_SUB, "newton_solves": solid.newton_solves - s0,
-                "cg_iterations": cg_iterations(h0v), "operator_apply_ms": ms32,
-                "operator_bytes_per_apply": bytes32,
-                "operator_gbs": bytes32 / ms32 / 1e6}
-            # stand-alone launches of every TMA kernel kind on the FP64 tangent and its FP32 copy
-            # (5: single ring; 2 / 3 / 4: two rings with 8+8 / 8+16 / 4+16 gather+consumer warps;
-            # the default takes 3 for plain launches and 5 for the fused-dot CG vmult)
-            kinds = {}
-            for kind in (5, 2, 3, 4):
-                h.set_option(capi.OPT_SPMV_KERNEL, kind)
-                m64, b64 = h.spmv_timed(capi.MAT_TANGENT, 5)
-                m32, b32 = h.spmv_timed(capi.MAT_MG_F32, 5)
-                kinds[str(kind)] = {"fp64_ms": m64, "fp64_gbs": b64 / m64 / 1e6,
-                                    "fp32_copy_ms": m32, "fp32_copy_gbs": b32 / m32 / 1e6}
-            h.set_option(capi.OPT_SPMV_KERNEL, 0)
-            variants["spmv_kernel_kinds"] = dict(
-                kinds, what="GF_OPT_SPMV_KERNEL: stand-alone y = A x launches (no fused dot), "
-                            "bitwise equal results for all kinds")
-            h.set_option(capi.OPT_MG_MATRIX_PRECISION, 0)
-            for k in range(N_SUB):      # FP64 operators again for the stand-alone SpMV timing
-                resident_pass(k)
+                "cg_iterations": cg_iterations(h0v), "operator_apply_ms": ms_mf,
+                "operator_bytes_per_apply": mf_bytes}
+            h.set_option(capi.OPT_OPERATOR, 0)
+            if args.precond == "mg":
+                # the V-cycle streaming FP32 copies of the level matrices (outer CG stays FP64)
+                h.set_option(capi.OPT_MG_MATRIX_PRECISION, 1)
+                for k in range(N_SUB):
+                    resident_pass(k)
+                s0 = solid.newton_solves
+                h0v = len(solid.history)
+                barrier()
+                h.event_record(2)
+                t0 = time.perf_counter()
+                for k in range(N_SUB):
+                    resident_pass(k)
+                h.event_record(3)
+                barrier()
+                tv = max(time.perf_counter() - t0, 1e-3 * h.event_elapsed_ms(2, 3))
+                ms32, bytes32 = h.spmv_timed(capi.MAT_MG_F32, 5)
+                variants["vcycle_fp32_matrices"] = {
+                    "what": "GF_OPT_MG_MATRIX_PRECISION = 1: smoother / residual applications inside "
+                            "the V-cycle stream FP32 copies of the level matrices (vectors, "
+                            "accumulation, the CG operator and its residual test stay FP64)",
+                    "value": n_dofs_global * (solid.newton_solves - s0) / tv, "unit": "DoFs/s",
+                    "steps": N_SUB, "newton_solves": solid.newton_solves - s0,
+                    "cg_iterations": cg_iterations(h0v), "operator_apply_ms": ms32,
+                    "operator_bytes_per_apply": bytes32,
+                    "operator_gbs": bytes32 / ms32 / 1e6}
+                # stand-alone launches of every TMA kernel kind on the FP64 tangent and its FP32 copy
+                # (5: single ring; 2 / 3 / 4: two rings with 8+8 / 8+16 / 4+16 gather+consumer warps;
+                # the default takes 3 for plain launches and 5 for the fused-dot CG vmult)
+                kinds = {}
+                for kind in (5, 2, 3, 4):
+                    h.set_option(capi.OPT_SPMV_KERNEL, kind)
+                    m64, b64 = h.spmv_timed(capi.MAT_TANGENT, 5)
+                    m32, b32 = h.spmv_timed(capi.MAT_MG_F32, 5)
+                    kinds[str(kind)] = {"fp64_ms": m64, "fp64_gbs": b64 / m64 / 1e6,
+                                        "fp32_copy_ms": m32, "fp32_copy_gbs": b32 / m32 / 1e6}
+                h.set_option(capi.OPT_SPMV_KERNEL, 0)
+                variants["spmv_kernel_kinds"] = dict(
+                    kinds, what="GF_OPT_SPMV_KERNEL: stand-alone y = A x launches (no fused dot), "
+                                "bitwise equal results for all kinds")
+                h.set_option(capi.OPT_MG_MATRIX_PRECISION, 0)
+                for k in range(N_SUB):      # FP64 operators again for the stand-alone SpMV timing
+                    resident_pass(k)
+        except Exception as exc:      # a failing side measurement must not cost the main line
+            variants["error"] = "%s: %s" % (type(exc).__name__, exc)
+            for opt, val in ((capi.OPT_OPERATOR, 0), (capi.OPT_SPMV_KERNEL, 0),
+                             (capi.OPT_MG_MATRIX_PRECISION, 0)):
+                try:
+                    h.set_option(opt, val)
+                except Exception:
+                    pass
+
     comm_info = None
     if world > 1:
         kind, n_halo, n_ar = comm.transport()
