@@ -436,7 +436,7 @@ extern "C"
             c.operator_kind = int(value);
             break;
           case GF_OPT_SPMV_KERNEL:
-            GF_REQUIRE(value >= 0 && value <= 5, GF_ERR_INVALID_ARG, "unknown SpMV kernel");
+            GF_REQUIRE(value >= 0 && value <= 6, GF_ERR_INVALID_ARG, "unknown SpMV kernel");
             for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
               l->spmv_kernel_kind = int(value);
             break;

@@ -108,6 +108,40 @@ namespace gf
     return v;
   }
 
+  // Warp sums of DIM values at once by a TRANSPOSED butterfly: after the first exchanges every lane
+  // carries one value instead of DIM, so DIM = 3 needs 6 shuffle+add rounds (DIM = 2: 5) instead
+  // of 15 (10). Returns the sum of v[r] in the lanes [r*S, (r+1)*S), S = 8 (DIM 3) / 16 (DIM 2).
+  // The partial sums are combined in the same order as in warp_sum (xor 16, 8, 4, 2, 1), only in
+  // fewer lanes, so the result is BITWISE the one warp_sum(v[r]) gives
+  // (tests/test_warp_reduction_emulation.py emulates both on the CPU).
+  template <int DIM>
+  __device__ __forceinline__ double warp_sum_rows(const double (&v)[DIM], const int lane)
+  {
+    constexpr unsigned full = 0xffffffffu;
+    const bool         b4   = (lane & 16) != 0;
+    double             t;
+    if constexpr (DIM == 2)
+      {
+        const double keep = b4 ? v[1] : v[0], send = b4 ? v[0] : v[1];
+        t                 = keep + __shfl_xor_sync(full, send, 16);
+        t += __shfl_xor_sync(full, t, 8);
+      }
+    else
+      {
+        static_assert(DIM == 3, "warp_sum_rows: DIM 2 or 3");
+        const bool   b3    = (lane & 8) != 0;
+        const double keep0 = b4 ? v[2] : v[0], keep1 = b4 ? 0.0 : v[1];
+        const double send0 = b4 ? v[0] : v[2], send1 = b4 ? v[1] : 0.0;
+        const double r0    = keep0 + __shfl_xor_sync(full, send0, 16);
+        const double r1    = keep1 + __shfl_xor_sync(full, send1, 16);
+        t                  = (b3 ? r1 : r0) + __shfl_xor_sync(full, b3 ? r0 : r1, 8);
+      }
+    t += __shfl_xor_sync(full, t, 4);
+    t += __shfl_xor_sync(full, t, 2);
+    t += __shfl_xor_sync(full, t, 1);
+    return t;
+  }
+
   // block-wide sum of up to N values per thread, result valid in thread 0; fixed order
   template <int N>
   __device__ __forceinline__ void block_sum(double (&v)[N], double *smem /* [N*32] */)

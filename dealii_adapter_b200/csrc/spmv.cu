@@ -395,7 +395,9 @@ namespace gf
     // XT = type of the staged x values and of the accumulators: double everywhere except the
     // all-single-precision operator of the V-cycle (GF_OPT_MG_MATRIX_PRECISION = 2: VT = XT = float,
     // FFMA with two accumulators per scalar row; y is written back as double)
-    template <int DIM, bool DOT, typename VT, typename XT, int GW, int GG, int CW>
+    // TR: the three (two) scalar-row sums of a block row by ONE transposed butterfly
+    // (kernel_utils.cuh::warp_sum_rows, bitwise the same sums in 6 instead of 15 shuffle rounds)
+    template <int DIM, bool DOT, typename VT, typename XT, int GW, int GG, int CW, bool TR = false>
     __global__ void __launch_bounds__((1 + GW + CW) * 32, 1)
       spmv_tma2_kernel(const int n_tiles, const TileDesc *__restrict__ tile_desc,
                        const uint2 *__restrict__ tile_meta, const int32_t *__restrict__ bcol,
@@ -616,9 +618,14 @@ namespace gf
                         }
                       continue;
                     }
-                  double        xi     = 0.0;
-                  if (DOT && lane < DIM)
-                    xi = __ldg(x + i);
+                  // lanes that end up with a row sum: lane r (plain butterfly) or lane r*LS (TR)
+                  constexpr int LS      = TR ? (DIM == 3 ? 8 : 16) : 1;
+                  const int     r_mine  = lane / LS;
+                  const bool    i_store = (lane % LS) == 0 && r_mine < DIM;
+                  const int64_t i_mine  = int64_t(row0 + row) * DIM + r_mine;
+                  double        xi      = 0.0;
+                  if (DOT && i_store)
+                    xi = __ldg(x + i_mine);
                   double acc[DIM];
 #pragma unroll
                   for (int r = 0; r < DIM; ++r)
@@ -636,17 +643,23 @@ namespace gf
                           acc[r]           = fma(vv.y, x1, acc[r]);
                         }
                     }
-#pragma unroll
-                  for (int r = 0; r < DIM; ++r)
-                    acc[r] = warp_sum(acc[r]);
-                  if (lane < DIM)
+                  double yr;
+                  if constexpr (TR)
+                    yr = warp_sum_rows<DIM>(acc, lane);
+                  else
                     {
-                      double yr = acc[0];
+#pragma unroll
+                      for (int r = 0; r < DIM; ++r)
+                        acc[r] = warp_sum(acc[r]);
+                      yr = acc[0];
 #pragma unroll
                       for (int r = 1; r < DIM; ++r)
                         if (lane == r)
                           yr = acc[r];
-                      y[i] = yr;
+                    }
+                  if (i_store)
+                    {
+                      y[i_mine] = yr;
                       if (DOT)
                         dot = fma(yr, xi, dot);
                     }
@@ -676,7 +689,7 @@ namespace gf
         }
     }
 
-    template <int DIM, bool DOT, typename VT, typename XT, int GW, int GG, int CW>
+    template <int DIM, bool DOT, typename VT, typename XT, int GW, int GG, int CW, bool TR = false>
     void launch_tma2_w(gf_context &c, const VT *val, const double *x, double *y,
                        double *dot_partials, const int *st)
     {
@@ -684,13 +697,13 @@ namespace gf
       static bool configured = false;
       if (!configured)
         {
-          GF_CUDA_CHECK(cudaFuncSetAttribute(spmv_tma2_kernel<DIM, DOT, VT, XT, GW, GG, CW>,
+          GF_CUDA_CHECK(cudaFuncSetAttribute(spmv_tma2_kernel<DIM, DOT, VT, XT, GW, GG, CW, TR>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              C::SMEM_BYTES));
           configured = true;
         }
       const int grid = int(std::min<int64_t>(c.n_tiles, c.sm_count));
-      spmv_tma2_kernel<DIM, DOT, VT, XT, GW, GG, CW><<<grid, C::THREADS, C::SMEM_BYTES, c.stream>>>(
+      spmv_tma2_kernel<DIM, DOT, VT, XT, GW, GG, CW, TR><<<grid, C::THREADS, C::SMEM_BYTES, c.stream>>>(
         int(c.n_tiles), c.tile_desc.p, c.tile_meta.p, c.bcol.p, val, x, y, dot_partials, st);
     }
     // warp split of the two-ring kernel by GF_OPT_SPMV_KERNEL:
@@ -701,7 +714,9 @@ namespace gf
     void launch_tma2_t(gf_context &c, int kind, const VT *val, const double *x, double *y,
                        double *dot_partials, const int *st)
     {
-      if (kind == 3)
+      if (kind == 6) // experimental: kind 3 with the transposed row reduction
+        launch_tma2_w<DIM, DOT, VT, double, 8, 2, 16, true>(c, val, x, y, dot_partials, st);
+      else if (kind == 3)
         launch_tma2_w<DIM, DOT, VT, double, 8, 2, 16>(c, val, x, y, dot_partials, st);
       else if (kind == 4)
         launch_tma2_w<DIM, DOT, VT, double, 4, 1, 16>(c, val, x, y, dot_partials, st);
@@ -804,7 +819,7 @@ namespace gf
       return;
     const int *st   = dot_partials ? &c.cg_scalars.p->status : nullptr;
     const int  kind = effective_kind(c, dot_partials != nullptr);
-    if (c.n_tiles > 0 && kind >= 2 && kind <= 4)
+    if (c.n_tiles > 0 && ((kind >= 2 && kind <= 4) || kind == 6))
       {
         if (c.dim == 3)
           {
@@ -872,7 +887,7 @@ namespace gf
     if (n_rows == 0)
       return;
     const int kind = effective_kind(c, false);
-    if (c.n_tiles > 0 && kind >= 2 && kind <= 4)
+    if (c.n_tiles > 0 && ((kind >= 2 && kind <= 4) || kind == 6))
       {
         if (c.dim == 3)
           launch_tma2_t<3, false, float>(c, kind, val32, x, y, nullptr, nullptr);

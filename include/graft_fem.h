@@ -136,7 +136,9 @@ extern "C"
                                   1: LDG warp-per-row kernel;
                                   2 / 3 / 4: two-ring TMA kernel (value ring decoupled from the
                                      column/x ring) with 8+8 / 8+16 / 4+16 gather+consumer warps,
-                                     for every launch; 5: single-ring TMA kernel for every launch */
+                                     for every launch; 5: single-ring TMA kernel for every launch;
+                                  6 (experimental, not yet run on hardware): kind 3 with a
+                                     transposed warp reduction of the scalar-row sums */
     GF_OPT_MG_SMOOTHER_DEGREE, /* Chebyshev degree of the pre-/post-smoother (default 3) */
     GF_OPT_MG_COARSE_DEGREE,   /* Chebyshev degree of the coarsest-level solve (default 80) */
     GF_OPT_MG_SMOOTHER_RATIO,  /* smoothers damp the eigenvalues in [lmax/ratio, lmax] (default 40) */

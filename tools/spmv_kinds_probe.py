@@ -15,7 +15,8 @@ from helpers import nl_params, smooth_field  # noqa: E402
 from dealii_adapter_b200 import capi, multigrid  # noqa: E402
 from dealii_adapter_b200.problem import make_problem  # noqa: E402
 
-KINDS = [int(k) for k in os.environ.get("GF_PROBE_KINDS", "0,2,3,4").split(",")]
+KINDS = [int(k) for k in os.environ.get(
+    "GF_PROBE_KINDS", "0,2,3,4,6" if os.environ.get("GF_TEST_EXPERIMENTAL") == "1" else "0,2,3,4").split(",")]
 
 
 def assembled(prob, n_levels=2):
