@@ -16,6 +16,7 @@ namespace Linear_Elasticity
     , interface_boundary_id(6)
     , clamped_mesh_id(0)
     , out_of_plane_clamped_mesh_id(4)
+    , timer(std::cout)
     , time(parameters.end_time, parameters.delta_t)
     , adapter(parameters, interface_boundary_id)
   {}
@@ -73,7 +74,10 @@ namespace Linear_Elasticity
 
   template <int dim>
   void ElastoDynamics<dim>::assemble_rhs()
-  {} // fused into gf_lin_step (:378-454)
+  {
+    timer.enter_subsection("Assemble rhs"); // fused into gf_lin_step (:378-454)
+    timer.leave_subsection("Assemble rhs");
+  }
 
   template <int dim>
   void ElastoDynamics<dim>::update_displacement()
@@ -90,9 +94,12 @@ namespace Linear_Elasticity
       std::cout << "\t Direct solver: " << std::endl;
     else
       throw std::runtime_error("Linear solver type not implemented");
-    // assemble_rhs + solve + update_displacement (:680-686)
+    // assemble_rhs + solve + update_displacement (:680-686) are one device call; it is booked
+    // under the reference's "Solve system" section (:529), "Assemble rhs" (:382) stays empty
+    timer.enter_subsection("Solve system");
     gf_check(host.handle, gf_lin_step(host.handle, parameters.type_lin == "CG" ? 0 : 1,
                                       parameters.max_iterations_lin, &lin_it, &lin_res));
+    timer.leave_subsection("Solve system");
     std::cout << "\t     No of iterations:\t" << lin_it << "\n \t     Final residual:\t" << lin_res
               << std::endl;
   }
@@ -101,8 +108,10 @@ namespace Linear_Elasticity
   void ElastoDynamics<dim>::output_results() const
   {
     // DataOut + Postprocessor on the displaced grid (:590-629), file index as in :616-619
+    timer.enter_subsection("Output results");
     host.output_results(GF_LIN_DISPLACEMENT, parameters.output_folder,
                         time.get_timestep() / parameters.output_interval);
+    timer.leave_subsection("Output results");
   }
 
   template <int dim>
@@ -130,7 +139,9 @@ namespace Linear_Elasticity
         assemble_rhs();
         solve();
         update_displacement();
+        timer.enter_subsection("Advance adapter"); // :696-698
         adapter.advance(displacement, time.get_delta_t());
+        timer.leave_subsection("Advance adapter");
         adapter.reload_old_state_if_required(state_variables, time);
         if (adapter.precice.isTimeWindowComplete() &&
             time.get_timestep() % parameters.output_interval == 0)

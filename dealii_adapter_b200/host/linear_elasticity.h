@@ -8,6 +8,7 @@
 #include "adapter/adapter.h"
 #include "adapter/parameters.h"
 #include "adapter/time_handler.h"
+#include "adapter/timer_output.h"
 #include "host_problem.h"
 
 namespace Linear_Elasticity
@@ -35,6 +36,7 @@ namespace Linear_Elasticity
     const unsigned int        interface_boundary_id;
     unsigned int              clamped_mesh_id, out_of_plane_clamped_mesh_id;
     gfh::HostProblem          host;
+    mutable Adapter::TimerOutput timer; // TimerOutput(std::cout, summary, wall_times) :63
     Adapter::Time             time;
     Adapter::Adapter<dim, VectorType, Parameters::AllParameters> adapter;
     VectorType old_velocity, velocity, old_displacement, displacement, old_stress, stress,

@@ -20,6 +20,7 @@ namespace Nonlinear_Elasticity
     , vol_reference(0.0)
     , vol_current(0.0)
     , boundary_interface_id(7)
+    , timer(std::cout)
     , time(parameters.end_time, parameters.delta_t)
     , adapter(parameters, boundary_interface_id)
   {
@@ -52,6 +53,7 @@ namespace Nonlinear_Elasticity
   template <int dim, typename NumberType>
   void Solid<dim, NumberType>::system_setup()
   {
+    timer.enter_subsection("Setup system"); // :309
     std::cout << "Triangulation:"
               << "\n\t Number of active cells: " << host.mesh->n_cells
               << "\n\t Polynomial degree: " << parameters.poly_degree
@@ -73,6 +75,7 @@ namespace Nonlinear_Elasticity
     system_rhs             = vec(GF_NL_SYSTEM_RHS);
     state_variables = {&total_displacement, &total_displacement_old, &velocity, &velocity_old,
                        &acceleration,       &acceleration_old}; // :370-375
+    timer.leave_subsection();                                   // :379
   }
 
   template <int dim, typename NumberType>
@@ -98,13 +101,16 @@ namespace Nonlinear_Elasticity
   template <int dim, typename NumberType>
   void Solid<dim, NumberType>::assemble_system()
   {
+    timer.enter_subsection("Assemble linear system"); // :1051
     std::cout << " ASM " << std::flush;
     gf_check(host.handle, gf_nl_newton_assemble(host.handle, &error_residual.u)); // :446-449
+    timer.leave_subsection();                                                     // :1086
   }
 
   template <int dim, typename NumberType>
   std::pair<unsigned int, double> Solid<dim, NumberType>::solve_linear_system(VectorType &)
   {
+    timer.enter_subsection("Linear solver"); // :1165
     std::cout << " SLV " << std::flush;
     uint32_t lin_it  = 0;
     double   lin_res = 0.0;
@@ -114,6 +120,7 @@ namespace Nonlinear_Elasticity
              gf_nl_newton_solve(host.handle, parameters.type_lin == "CG" ? 0 : 1, parameters.tol_lin,
                                 parameters.max_iterations_lin, &lin_it, &lin_res,
                                 &last_update_norm)); // :1153-1211, :476, :487
+    timer.leave_subsection();                        // :1205
     return std::make_pair(lin_it, lin_res);
   }
 
@@ -196,8 +203,10 @@ namespace Nonlinear_Elasticity
   {
     // DataOut + Postprocessor on the displaced grid (:1215-1254): patch fields on the device, file
     // on the host; file index as in :1240-1243
+    timer.enter_subsection("Output results");
     host.output_results(GF_NL_TOTAL_DISPLACEMENT, parameters.output_folder,
                         time.get_timestep() / parameters.output_interval);
+    timer.leave_subsection("Output results");
   }
 
   template <int dim, typename NumberType>
@@ -223,7 +232,9 @@ namespace Nonlinear_Elasticity
         solve_nonlinear_timestep(solution_delta);
         // total_displacement += solution_delta and the Newmark updates (:139-144)
         gf_check(host.handle, gf_nl_end_step(host.handle));
+        timer.enter_subsection("Advance adapter"); // :149-154
         adapter.advance(total_displacement, time.get_delta_t());
+        timer.leave_subsection("Advance adapter");
         adapter.reload_old_state_if_required(state_variables, time);
         if (adapter.precice.isTimeWindowComplete() &&
             time.get_timestep() % parameters.output_interval == 0)

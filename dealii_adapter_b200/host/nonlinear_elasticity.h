@@ -9,6 +9,7 @@
 #include "adapter/adapter.h"
 #include "adapter/parameters.h"
 #include "adapter/time_handler.h"
+#include "adapter/timer_output.h"
 #include "host_problem.h"
 
 namespace Nonlinear_Elasticity
@@ -43,6 +44,7 @@ namespace Nonlinear_Elasticity
     double                          vol_reference, vol_current;
     gfh::HostProblem                host;
     const unsigned int              boundary_interface_id;
+    mutable Adapter::TimerOutput    timer; // TimerOutput(std::cout, summary, wall_times) :79
     Adapter::Time                   time;
     Adapter::Adapter<dim, VectorType, Parameters::AllParameters> adapter;
 

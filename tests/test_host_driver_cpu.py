@@ -195,3 +195,22 @@ def test_coupling_loop_of_the_cxx_mirror_follows_the_reference_run(env, tmp_path
         assert any(e.startswith("THROW:") for e in events)
         assert r.returncode == 1 and "This solver supports only constant time-step sizes" in r.stderr
         assert calls[:len(want)] == want          # everything up to the throw, then the destructor
+
+
+def test_timer_summary_keeps_the_reference_sections(env, tmp_path):
+    """TimerOutput(std::cout, summary, wall_times) (nonlinear_elasticity.cc:79, linear:63): the
+    section names of the reference and their call counts, printed when the solver is destroyed."""
+    r, calls = run(env, tmp_path, nl_prm(), windows=2, res=[1.0, 1e-3, 1e-12] * 2, upd=[1.0, 1e-9] * 2)
+    assert r.returncode == 0, r.stderr
+    rows = {l.split("|")[1].strip(): int(l.split("|")[2]) for l in r.stdout.splitlines()
+            if l.startswith("| ") and l.count("|") == 5 and l.split("|")[2].strip().isdigit()}
+    assert rows == {"Setup system": 1, "Output results": 1, "Assemble linear system": 6,
+                    "Linear solver": 4, "Advance adapter": 2}
+    assert "Total wallclock time elapsed since start" in r.stdout
+    d = tmp_path / "lin"
+    d.mkdir()
+    prm = nl_prm(**{"Model                     = neo-Hookean": "Model                     = linear"})
+    r, calls = run(env, d, prm, windows=3)
+    rows = {l.split("|")[1].strip(): int(l.split("|")[2]) for l in r.stdout.splitlines()
+            if l.startswith("| ") and l.count("|") == 5 and l.split("|")[2].strip().isdigit()}
+    assert rows == {"Output results": 1, "Assemble rhs": 3, "Solve system": 3, "Advance adapter": 3}
