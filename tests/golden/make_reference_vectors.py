@@ -28,6 +28,7 @@ ADAPTER_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_adapter_driver")
 GRID_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_grid_driver")
 PRM_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_parameters_driver")
 RUN_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_run_driver")
+CONSTRAINTS_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_constraints_driver")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 OUT = os.path.join(HERE, "reference_vectors.npz")
@@ -409,8 +410,24 @@ def run_loop_cases():
     return out
 
 
+def run_constraint_cases():
+    """Dirichlet sets the reference requests (make_constraints nonlinear_elasticity.cc:1094-1150 for
+    Newton iterations 0, 1, 2; linear_elasticity.cc:429-446): lines `call boundary_id mask-bits`."""
+    out = {}
+    cases = [("nl", 2, 0), ("nl", 2, 1), ("nl", 2, 2), ("nl", 3, 0), ("nl", 3, 1), ("nl", 3, 2),
+             ("lin", 2), ("lin", 3)]
+    for k, c in enumerate(cases):
+        r = subprocess.run([CONSTRAINTS_DRIVER] + [str(x) for x in c], capture_output=True, text=True,
+                           check=True)
+        out["cst%d_case" % k] = np.array([str(x) for x in c])
+        out["cst%d_calls" % k] = np.array(r.stdout.strip().split("\n") if r.stdout.strip() else [])
+    out["n_cst"] = np.array(len(cases))
+    return out
+
+
 def generate():
     out = {}
+    out.update(run_constraint_cases())
     out.update(run_loop_cases())
     out.update(run_prm_cases())
     out.update(run_grid_cases())

@@ -391,3 +391,40 @@ def test_host_parameter_parser_equals_the_reference_parameters(tmp_path, ref):
     assert (p.poly_degree, p.max_iterations_NR, p.output_interval) == \
         (int(d["poly_degree"]), int(d["max_iterations_NR"]), int(d["output_interval"]))
     assert abs(p.lam - float(d["lambda"])) <= 1e-9 * abs(float(d["lambda"]))
+
+
+def test_dirichlet_sets_equal_what_the_reference_requests(ref):
+    """Solid::make_constraints (nonlinear_elasticity.cc:1094-1150) and the boundary-value block of
+    ElastoDynamics::assemble_rhs (linear_elasticity.cc:429-446), the reference's own code against a
+    recording VectorTools::interpolate_boundary_values: the clamped id is fixed in every component,
+    the out-of-plane id only in z and only in 3D, nothing changes after Newton iteration 1 —
+    against the constrained-DoF mask of the host mirror (problem.make_problem)."""
+    from helpers import lin_params
+    from dealii_adapter_b200.mesh import scenario_geometry
+    for k in range(int(ref["n_cst"])):
+        case = [str(x) for x in ref["cst%d_case" % k]]
+        solver, dim = case[0], int(case[1])
+        calls = [str(x) for x in ref["cst%d_calls" % k]]
+        if solver == "nl" and int(case[2]) > 1:
+            assert calls == []                      # :1100-1101: the set is static from then on
+            continue
+        sets = [(int(c.split()[1]), int(c.split()[2])) for c in calls
+                if c.startswith("interpolate_boundary_values")]
+        clamped_id, zclamp_id = (1, 8) if solver == "nl" else (0, 4)
+        want = [(clamped_id, (1 << dim) - 1)] + ([(zclamp_id, 1 << 2)] if dim == 3 else [])
+        assert sets == want
+        if solver == "nl":
+            assert calls[0] == "clear" and calls[-1] == "close"
+        # the host mirror's mask: all components on the clamped face, z on the z faces in 3D
+        for scenario in ("FSI3", "PF"):
+            p = nl_params(poly_degree=1, scenario=scenario) if solver == "nl" else \
+                lin_params(poly_degree=1, scenario=scenario)
+            prob = make_problem(p, dim, reps=[2] * dim)
+            p0, p1, reps, clamped, interface, zclamp = scenario_geometry(scenario, dim)
+            comp = dof_components(prob)
+            X = prob.mesh.support_points
+            on = lambda mask: np.any([np.isclose(X[:, f // 2], (p1 if f % 2 else p0)[f // 2])
+                                      for f in range(2 * dim) if (mask >> f) & 1], axis=0) \
+                if mask else np.zeros(prob.n_dofs, dtype=bool)
+            expected = on(clamped) | (on(zclamp) & (comp == 2) if dim == 3 else False)
+            assert np.array_equal(prob.constrained != 0, expected), (solver, dim, scenario)
