@@ -1,13 +1,23 @@
 """Golden vectors produced by THE REFERENCE'S OWN CODE, run in this container.
 
-Three header-only pieces of /root/reference compile without the real deal.II against the small
-stand-in oracle/ref_shim (`make -C oracle ref` -> oracle/_ref/ref_driver, sources taken in place):
-  source/nonlinear_elasticity/include/compressible_neo_hook_material.h  (Psi, tau, Jc)
-  source/nonlinear_elasticity/include/postprocessor.h                   (evaluate_vector_field)
-  include/adapter/time_handler.h                                        (Time)
+The pieces of /root/reference that carry the arithmetic and the control flow of the hot path
+compile without the real deal.II against the small stand-in oracle/ref_shim (`make -C oracle ref`
+-> oracle/_ref/*, sources taken in place; blocks that live inside the big translation units are cut
+out by marker at build time and never committed):
+  ref_driver             compressible_neo_hook_material.h (Psi, tau, Jc), postprocessor.h, time_handler.h
+  ref_assembler_driver   Assembler_Base / Assembler<dim,double> + PointHistory: K_e, r_e, Neumann term
+  ref_linear_driver      local stiffness loops and consistent-loading face loop of linear_elasticity.cc
+  ref_updates_driver     Newmark coefficients / updates / masked norms; theta-scheme rhs + update
+  ref_newton_driver      Solid::solve_nonlinear_timestep + Errors with scripted norms
+  ref_run_driver         Solid::run() / ElastoDynamics::run() against recording stand-ins
+  ref_adapter_driver     Adapter::format_* and checkpoint members
+  ref_grid_driver        make_grid of both solvers against a recording grid generator
+  ref_constraints_driver make_constraints / boundary-value block against a recording VectorTools
+  ref_parameters_driver  include/adapter/parameters.{h,cc} unmodified, against a ParameterHandler stand-in
 This script runs them on deterministic inputs and writes tests/golden/reference_vectors.npz;
-tests/test_reference_pins.py checks the oracle (and the host Time mirror) against the file, and —
-where /root/reference exists — that the file is what the reference produces.
+tests/test_reference_pins.py, tests/test_host_driver_cpu.py and tests/test_gpu_zz_reference_pins.py
+check the oracle, the host mirrors and the device against the file, and — where /root/reference
+exists — that the file is what the reference produces.
 
 usage: python tests/golden/make_reference_vectors.py [--check]
 """
