@@ -13,6 +13,7 @@ out by marker at build time and never committed):
   ref_adapter_driver     Adapter::format_* and checkpoint members
   ref_grid_driver        make_grid of both solvers against a recording grid generator
   ref_constraints_driver make_constraints / boundary-value block against a recording VectorTools
+  ref_solver_driver      solve_linear_system / solve against recording SolverControl / SolverCG
   ref_parameters_driver  include/adapter/parameters.{h,cc} unmodified, against a ParameterHandler stand-in
 This script runs them on deterministic inputs and writes tests/golden/reference_vectors.npz;
 tests/test_reference_pins.py, tests/test_host_driver_cpu.py and tests/test_gpu_zz_reference_pins.py
@@ -39,6 +40,7 @@ GRID_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_grid_driver")
 PRM_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_parameters_driver")
 RUN_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_run_driver")
 CONSTRAINTS_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_constraints_driver")
+SOLVER_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_solver_driver")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 OUT = os.path.join(HERE, "reference_vectors.npz")
@@ -435,8 +437,26 @@ def run_constraint_cases():
     return out
 
 
+def run_solver_setup_cases():
+    """What the reference hands to SolverControl / the preconditioner (nonlinear_elasticity.cc:
+    1153-1211, linear_elasticity.cc:525-575): (solver, type, n_dofs, multiplier, tol_lin, |rhs|)."""
+    cases = [("nl", "CG", 2081667, 1.0, 1e-6, 350.5), ("nl", "CG", 7, 1.5, 1e-6, 2.0),
+             ("nl", "CG", 518, 2.0, 1e-8, 0.0), ("nl", "Direct", 100, 1.0, 1e-6, 3.0),
+             ("lin", "CG", 7, 1.5, 0.0, 0.0), ("lin", "CG", 51171075, 1.0, 0.0, 0.0),
+             ("lin", "Direct", 7, 1.5, 0.0, 0.0)]
+    out = {}
+    for k, c in enumerate(cases):
+        r = subprocess.run([SOLVER_DRIVER] + [repr(x) if isinstance(x, float) else str(x) for x in c],
+                           capture_output=True, text=True, check=True)
+        out["slv%d_case" % k] = np.array([str(x) for x in c])
+        out["slv%d_lines" % k] = np.array(r.stdout.strip().split("\n"))
+    out["n_slv"] = np.array(len(cases))
+    return out
+
+
 def generate():
     out = {}
+    out.update(run_solver_setup_cases())
     out.update(run_constraint_cases())
     out.update(run_loop_cases())
     out.update(run_prm_cases())

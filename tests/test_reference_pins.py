@@ -428,3 +428,40 @@ def test_dirichlet_sets_equal_what_the_reference_requests(ref):
                 if mask else np.zeros(prob.n_dofs, dtype=bool)
             expected = on(clamped) | (on(zclamp) & (comp == 2) if dim == 3 else False)
             assert np.array_equal(prob.constrained != 0, expected), (solver, dim, scenario)
+
+
+def test_linear_solver_setup_equals_what_the_reference_configures(native_libs, ref):
+    """Solid::solve_linear_system (nonlinear_elasticity.cc:1153-1211) and ElastoDynamics::solve
+    (linear_elasticity.cc:525-575), the reference's own code against recording SolverControl /
+    preconditioner stand-ins: iteration limit = int(m() * multiplier) (truncated), tolerance =
+    tol_lin * ||rhs|| (nonlinear) or 1e-10 absolute (linear), SSOR with omega 0.65 / 1.2, and
+    (1, 0) reported for 'Direct'. The oracle must stop at exactly that limit."""
+    from oracle import oracle_py as orc
+    seen = set()
+    for k in range(int(ref["n_slv"])):
+        solver, typ, n, mult, tol_lin, rhs_norm = [str(x) for x in ref["slv%d_case" % k]]
+        n, mult, tol_lin, rhs_norm = int(n), float(mult), float(tol_lin), float(rhs_norm)
+        lines = [str(x) for x in ref["slv%d_lines" % k]]
+        if typ == "CG":
+            ctl = lines[0].split()
+            assert ctl[0] == "SolverControl" and int(ctl[1]) == int(n * mult)
+            assert float(ctl[2]) == (tol_lin * rhs_norm if solver == "nl" else 1e-10)
+            assert lines[1] == ("PreconditionSelector ssor 0.65000000000000002" if solver == "nl"
+                                else "PreconditionSSOR 1.2")
+            assert lines[2] == "SolverCG::solve" and lines[3] == "constraints.distribute"
+        else:
+            assert lines[:3] == ["SparseDirectUMFPACK::initialize", "SparseDirectUMFPACK::vmult",
+                                 "constraints.distribute"]
+            if solver == "nl":
+                assert lines[3] == "returns 1 0"            # :1198-1199
+        seen.add((solver, typ))
+    assert seen == {("nl", "CG"), ("nl", "Direct"), ("lin", "CG"), ("lin", "Direct")}
+    # behaviour of the oracle at the limit: a multiplier that cannot converge stops at int(n * mult)
+    p = nl_params(poly_degree=1, type_lin="CG", max_iterations_lin=0.05, tol_lin=1e-12)
+    prob = make_problem(p, 2, reps=[6, 8])
+    o = orc.Oracle(prob, n_threads=1)
+    o.format_precice_to_deal(np.tile([0.0, -1500.0], prob.n_iface_nodes), orc.NL_EXTERNAL_STRESS)
+    o.nl_update_acceleration()
+    o.nl_assemble_system()
+    status, lin_it, lin_res = o.nl_solve_linear_system()
+    assert status == 1 and lin_it == int(prob.n_dofs * 0.05)
