@@ -28,6 +28,22 @@ namespace Adapter
     bool write_checkpoint = false, read_checkpoint = false;
     bool requiresWritingCheckpoint() const { return write_checkpoint; }
     bool requiresReadingCheckpoint() const { return read_checkpoint; }
+    // read_data / advance (adapter.h:346-385): record the calls and their arguments
+    void readData(const std::string &mesh, const std::string &data, const std::vector<int> &ids,
+                  double relative_read_time, std::vector<double> &values) const
+    {
+      printf("EVENT readData %s %s %zu %.17g\n", mesh.c_str(), data.c_str(), ids.size(),
+             relative_read_time);
+      for (size_t i = 0; i < values.size(); ++i)
+        values[i] = 100.0 + double(i);
+    }
+    void writeData(const std::string &mesh, const std::string &data, const std::vector<int> &ids,
+                   const std::vector<double> &values)
+    {
+      printf("EVENT writeData %s %s %zu %.17g\n", mesh.c_str(), data.c_str(), ids.size(),
+             values.empty() ? 0.0 : values.back());
+    }
+    void advance(double dt) { printf("EVENT advance %.17g\n", dt); }
   };
   template <int dim, typename VectorType, typename ParameterClass>
   class Adapter
@@ -39,12 +55,17 @@ namespace Adapter
     std::vector<double>     read_data_buffer, write_data_buffer;
     std::vector<VectorType> old_state_data;
     double                  old_time_value = 0;
+    std::string mesh_name = "dealii-mesh", read_data_name = "Stress", write_data_name = "Displacement";
+    std::vector<int>        interface_nodes_ids;
+    void                    read_data(double relative_read_time, VectorType &precice_to_deal);
+    void                    advance(const VectorType &deal_to_precice, const double computed_timestep_length);
     void                    format_deal_to_precice(const VectorType &deal_to_precice);
     void                    format_precice_to_deal(VectorType &precice_to_deal) const;
     void save_current_state_if_required(const std::vector<VectorType *> &state_variables,
                                         Time &                           time_class);
     void reload_old_state_if_required(std::vector<VectorType *> &state_variables, Time &time_class);
   };
+#include "adapter_io_extract.inc"
 #include "adapter_extract.inc"
 } // namespace Adapter
 
@@ -109,6 +130,12 @@ int run(unsigned n_dofs, unsigned n_iface)
   for (unsigned i = 0; i < n_dofs; ++i)
     same = same && s0[i] == v[i] && s1[i] == w[i];
   printf("%d\n", same ? 1 : 0);
+  // read_data / advance: order of the preCICE calls around the format functions
+  a.interface_nodes_ids.assign(n_iface, 0);
+  Vector<double> target(n_dofs);
+  a.read_data(0.01, target);
+  printf("EVENT read_value %.17g\n", target[*a.coupling_dofs_x_comp.begin()]);
+  a.advance(v, 0.01);
   return 0;
 }
 

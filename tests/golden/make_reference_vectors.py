@@ -320,7 +320,9 @@ def run_adapter_cases():
         out["adp%d_vec" % k], out["adp%d_buf" % k] = vec, buf
         out["adp%d_write" % k] = np.array(res[0].split(), dtype=float)
         out["adp%d_after_read" % k] = np.array(res[1].split(), dtype=float)
-        out["adp%d_checkpoint" % k] = np.array(" ".join(res[2:]).split(), dtype=float)
+        out["adp%d_checkpoint" % k] = np.array(
+            " ".join(l for l in res[2:] if not l.startswith("EVENT")).split(), dtype=float)
+        out["adp%d_events" % k] = np.array([l[6:] for l in res if l.startswith("EVENT")])
     return out
 
 

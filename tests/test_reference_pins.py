@@ -465,3 +465,43 @@ def test_linear_solver_setup_equals_what_the_reference_configures(native_libs, r
     o.nl_assemble_system()
     status, lin_it, lin_res = o.nl_solve_linear_system()
     assert status == 1 and lin_it == int(prob.n_dofs * 0.05)
+
+
+def test_adapter_read_data_and_advance_follow_the_reference_members(ref):
+    """Adapter::read_data / advance (adapter.h:346-385), the reference's own member definitions
+    against a recording participant: readData fills the buffer BEFORE it is formatted into the DoF
+    vector; advance formats, writes, then advances preCICE. The host mirror must issue the same
+    calls in the same order (the device calls sit where the format functions are)."""
+    from dealii_adapter_b200 import solvers
+    events = [str(e) for e in ref["adp0_events"]]
+    assert [e.split()[0] for e in events] == ["readData", "read_value", "writeData", "advance"]
+    assert events[0].split()[1:3] == ["dealii-mesh", "Stress"] and float(events[0].split()[4]) == 0.01
+    assert float(events[1].split()[1]) == 100.0          # the value readData delivered reached the vector
+    assert events[2].split()[1:3] == ["dealii-mesh", "Displacement"] and float(events[3].split()[1]) == 0.01
+    log = []
+
+    class Participant:
+        def readData(self, mesh, data, ids, t):
+            log.append(("readData", mesh, data, t))
+            return np.full(4, 100.0)
+        def writeData(self, mesh, data, ids, values):
+            log.append(("writeData", mesh, data))
+        def advance(self, dt):
+            log.append(("advance", dt))
+
+    class Handle:
+        def set_traction(self, buf):
+            log.append(("set_traction", float(buf[0])))
+        def get_interface_displacement(self):
+            log.append(("get_interface_displacement",))
+            return np.zeros(4)
+
+    a = solvers.Adapter.__new__(solvers.Adapter)
+    a.precice, a._h = Participant(), Handle()
+    a.mesh_name, a.read_data_name, a.write_data_name = "dealii-mesh", "Stress", "Displacement"
+    a.interface_nodes_ids = np.zeros(2, dtype=np.int32)
+    a.read_data(0.01)
+    a.advance(0.01)
+    assert log == [("readData", "dealii-mesh", "Stress", 0.01), ("set_traction", 100.0),
+                   ("get_interface_displacement",), ("writeData", "dealii-mesh", "Displacement"),
+                   ("advance", 0.01)]
