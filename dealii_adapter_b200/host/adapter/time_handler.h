@@ -1,5 +1,7 @@
-// Adapter::Time — host-side time bookkeeping with the interface of the reference
-// (include/adapter/time_handler.h:21-84); stays on the host, values cross the C-ABI by value.
+// Adapter::Time of the host mirror: step counter and current time with the accessors the solver
+// classes and the Adapter use (reference: include/adapter/time_handler.h:21-84). It never leaves
+// the host; the C-ABI receives delta_t by value. tests/test_reference_pins.py compares it with the
+// reference's own class on increment / reset sequences.
 #pragma once
 #include <cmath>
 
@@ -7,35 +9,34 @@ namespace Adapter
 {
   class Time
   {
+    unsigned int n_steps = 0;
+    double       now     = 0.0;
+    const double t_end, dt;
+
   public:
     Time(const double time_end, const double delta_t)
-      : timestep(0)
-      , time_current(0.0)
-      , time_end(time_end)
-      , delta_t(delta_t)
+      : t_end(time_end)
+      , dt(delta_t)
     {}
-    virtual ~Time() {}
-    double       current() const { return time_current; }
-    double       end() const { return time_end; }
-    double       get_delta_t() const { return delta_t; }
-    unsigned int get_timestep() const { return timestep; }
-    // used when a checkpoint is reloaded: the step counter is recomputed from the absolute time
-    void set_absolute_time(const double new_time)
-    {
-      const double factor = std::pow(10, 10);
-      timestep            = (unsigned int)(std::round((new_time / delta_t) * factor) / factor);
-      time_current        = new_time;
-    }
+    virtual ~Time() = default;
+
+    unsigned int get_timestep() const { return n_steps; }
+    double       current() const { return now; }
+    double       end() const { return t_end; }
+    double       get_delta_t() const { return dt; }
+
     void increment()
     {
-      time_current += delta_t;
-      ++timestep;
+      ++n_steps;
+      now += dt;
     }
-
-  private:
-    unsigned int timestep;
-    double       time_current;
-    const double time_end;
-    const double delta_t;
+    // checkpoint reload: jump to an absolute time; the step counter follows from it (the ratio is
+    // rounded at the 10th decimal first, as the reference does, then truncated)
+    void set_absolute_time(const double new_time)
+    {
+      const double scale = std::pow(10, 10);
+      n_steps            = static_cast<unsigned int>(std::round((new_time / dt) * scale) / scale);
+      now                = new_time;
+    }
   };
 } // namespace Adapter
