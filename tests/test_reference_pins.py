@@ -505,3 +505,82 @@ def test_adapter_read_data_and_advance_follow_the_reference_members(ref):
     assert log == [("readData", "dealii-mesh", "Stress", 0.01), ("set_traction", 100.0),
                    ("get_interface_displacement",), ("writeData", "dealii-mesh", "Displacement"),
                    ("advance", 0.01)]
+
+
+class RecordingHandle(ScriptedHandle):
+    """Device handle stand-in that logs the C-ABI calls of the Python mirror."""
+
+    def __init__(self, res, upd, log, n_iface=3, dim=2):
+        super().__init__(res, upd)
+        self.log, self.n_iface_nodes, self.dim = log, n_iface, dim
+
+    def nl_newton_assemble(self):
+        self.log.append("nl_newton_assemble")
+        return super().nl_newton_assemble()
+
+    def nl_newton_solve(self, *a):
+        self.log.append("nl_newton_solve")
+        return super().nl_newton_solve(*a)
+
+    def __getattr__(self, name):
+        if name in ("state_save", "state_restore", "nl_begin_step", "nl_end_step", "lin_assemble_once"):
+            return lambda *a: self.log.append(name)
+        if name == "set_traction":
+            return lambda buf: self.log.append("set_traction")
+        if name == "lin_step":
+            return lambda *a: (self.log.append("lin_step"), (3, 1e-11))[1]
+        if name == "get_interface_displacement":
+            return lambda: (self.log.append("get_interface_displacement"),
+                            np.zeros(self.n_iface_nodes * self.dim))[1]
+        raise AttributeError(name)
+
+
+@pytest.mark.parametrize("k", range(5))
+def test_coupling_loop_of_the_python_mirror_follows_the_reference_run(ref, k):
+    """The event order of the reference's own run() loops (see tests/test_host_driver_cpu.py for
+    the C++ driver) against the C-ABI calls of the Python mirror (solvers.Solid / ElastoDynamics
+    with the scripted participant) under the same coupling scheme."""
+    from dealii_adapter_b200 import solvers
+    from helpers import lin_params
+    solver, windows, sub, interval, dt, dt_precice = (str(x) for x in ref["loop%d_case" % k])
+    assert int(ref["loop%d_exit" % k]) == 0
+    events = [str(e) for e in ref["loop%d_events" % k]]
+    n_pass = int(windows) * int(sub)
+    log = []
+    h = RecordingHandle([1.0, 1e-3, 1e-12] * n_pass, [1.0, 1e-9] * n_pass, log)
+    part = solvers.FakeParticipant(2, int(windows), float(dt), lambda t, it: np.zeros(6), int(sub))
+    p = (nl_params if solver == "nl" else lin_params)(poly_degree=1, delta_t=float(dt))
+    prob = make_problem(p, 2, reps=[2, 2])
+    cls = solvers.Solid if solver == "nl" else solvers.ElastoDynamics
+    s = cls(prob, part, handle=h)
+    s.adapter.initialize = lambda problem: None        # DoF extraction: host/deal.II territory
+    s.adapter.n_interface_nodes = 3
+    s.adapter.interface_nodes_ids = np.arange(3, dtype=np.int32)
+    s.run()
+    newton = ["nl_newton_assemble", "nl_newton_solve"] * 2 + ["nl_newton_assemble"]
+    want = []
+    i = 0
+    while i < len(events):
+        e = events[i]
+        if e == "assemble_system":
+            want.append("lin_assemble_once")
+        elif e == "adapter.save_current_state_if_required:1":
+            want.append("state_save")
+        elif e == "adapter.reload_old_state_if_required:1":
+            want.append("state_restore")
+        elif e == "solution_delta=0":
+            want.append("nl_begin_step")
+        elif e.startswith("adapter.read_data"):
+            want.append("set_traction")
+        elif e == "solve_nonlinear_timestep":
+            want += newton
+        elif e == "total_displacement+=solution_delta":
+            want.append("nl_end_step")
+            i += 3
+        elif e == "assemble_rhs":
+            want.append("lin_step")
+            i += 2
+        elif e.startswith("adapter.advance"):
+            want.append("get_interface_displacement")
+        i += 1
+    assert log == want
