@@ -189,6 +189,12 @@ def main():
                     help="coupling sub-iterations per time window (checkpoint at the first, restore "
                          "after every non-final one); cfg5 of BASELINE.json: --reps 48,288,60 "
                          "--n-sub 10 on 8 GPUs (tools/bench_cfg5.sh)")
+    ap.add_argument("--spmv-kernel", type=int, default=0,
+                    help="GF_OPT_SPMV_KERNEL for the whole run (0 = library default; 3 / 6 put the "
+                         "fused-dot launches on the 16-consumer-warp kernels as well)")
+    ap.add_argument("--mg-precision", type=int, default=0,
+                    help="GF_OPT_MG_MATRIX_PRECISION for the whole run (0 FP64 level matrices in the "
+                         "V-cycle, 1 FP32 copies, 2 all-FP32 operator)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true",
                     help="skip the matrix-free-operator variant measured after the main regions")
@@ -253,6 +259,10 @@ def main():
     else:
         part = prob.mesh.partition(1, world, rank) if world > 1 else None
         h = capi.Handle(prob, device=local_rank, partition=part, comm=comm)
+    if args.spmv_kernel:
+        h.set_option(capi.OPT_SPMV_KERNEL, args.spmv_kernel)
+    if args.mg_precision and args.precond == "mg":
+        h.set_option(capi.OPT_MG_MATRIX_PRECISION, args.mg_precision)
     n_if = h.n_iface_nodes
     buf = np.tile(TRACTION, n_if)
     participant = solvers.FakeParticipant(3, 10 ** 9, prob.params.delta_t, lambda t, it: buf, N_SUB)
@@ -393,13 +403,13 @@ def main():
                 variants["spmv_kernel_kinds"] = dict(
                     kinds, what="GF_OPT_SPMV_KERNEL: stand-alone y = A x launches (no fused dot), "
                                 "bitwise equal results for all kinds")
-                h.set_option(capi.OPT_MG_MATRIX_PRECISION, 0)
-                for k in range(N_SUB):      # FP64 operators again for the stand-alone SpMV timing
+                h.set_option(capi.OPT_MG_MATRIX_PRECISION, args.mg_precision)
+                for k in range(N_SUB):      # the run's operators again for the stand-alone SpMV timing
                     resident_pass(k)
         except Exception as exc:      # a failing side measurement must not cost the main line
             variants["error"] = "%s: %s" % (type(exc).__name__, exc)
-            for opt, val in ((capi.OPT_OPERATOR, 0), (capi.OPT_SPMV_KERNEL, 0),
-                             (capi.OPT_MG_MATRIX_PRECISION, 0)):
+            for opt, val in ((capi.OPT_OPERATOR, 0), (capi.OPT_SPMV_KERNEL, args.spmv_kernel),
+                             (capi.OPT_MG_MATRIX_PRECISION, args.mg_precision)):
                 try:
                     h.set_option(opt, val)
                 except Exception:
@@ -434,6 +444,7 @@ def main():
                        "nnz_scalar": h.nnz(), "newton_solves_in_timed_region": solves_value,
                        "cg_iterations_in_timed_region": cg_its_value,
                        "preconditioner": args.precond,
+                       "spmv_kernel_option": args.spmv_kernel, "mg_matrix_precision": args.mg_precision,
                        "multigrid_levels": [q.mesh.reps for q in hierarchy.problems] if hierarchy else None,
                        "multigrid_levels_replicated": hierarchy.replicated if hierarchy else None,
                        "l2_policy": "inputs larger than L2 (matrix %.2f GB per GPU streamed every "
