@@ -399,7 +399,7 @@ def main():
                     m32, b32 = h.spmv_timed(capi.MAT_MG_F32, 5)
                     kinds[str(kind)] = {"fp64_ms": m64, "fp64_gbs": b64 / m64 / 1e6,
                                         "fp32_copy_ms": m32, "fp32_copy_gbs": b32 / m32 / 1e6}
-                h.set_option(capi.OPT_SPMV_KERNEL, 0)
+                h.set_option(capi.OPT_SPMV_KERNEL, args.spmv_kernel)
                 variants["spmv_kernel_kinds"] = dict(
                     kinds, what="GF_OPT_SPMV_KERNEL: stand-alone y = A x launches (no fused dot), "
                                 "bitwise equal results for all kinds")
