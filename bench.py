@@ -195,6 +195,9 @@ def main():
     ap.add_argument("--mg-precision", type=int, default=0,
                     help="GF_OPT_MG_MATRIX_PRECISION for the whole run (0 FP64 level matrices in the "
                          "V-cycle, 1 FP32 copies, 2 all-FP32 operator)")
+    ap.add_argument("--mg-refresh", type=int, default=1,
+                    help="GF_OPT_MG_REFRESH_INTERVAL: rebuild the coarse multigrid operators at every "
+                         "k-th assembly only (1 = always)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true",
                     help="skip the matrix-free-operator variant measured after the main regions")
@@ -263,6 +266,8 @@ def main():
         h.set_option(capi.OPT_SPMV_KERNEL, args.spmv_kernel)
     if args.mg_precision and args.precond == "mg":
         h.set_option(capi.OPT_MG_MATRIX_PRECISION, args.mg_precision)
+    if args.mg_refresh > 1 and args.precond == "mg":
+        h.set_option(capi.OPT_MG_REFRESH_INTERVAL, args.mg_refresh)
     n_if = h.n_iface_nodes
     buf = np.tile(TRACTION, n_if)
     participant = solvers.FakeParticipant(3, 10 ** 9, prob.params.delta_t, lambda t, it: buf, N_SUB)
@@ -445,6 +450,7 @@ def main():
                        "cg_iterations_in_timed_region": cg_its_value,
                        "preconditioner": args.precond,
                        "spmv_kernel_option": args.spmv_kernel, "mg_matrix_precision": args.mg_precision,
+                       "mg_refresh_interval": args.mg_refresh,
                        "multigrid_levels": [q.mesh.reps for q in hierarchy.problems] if hierarchy else None,
                        "multigrid_levels_replicated": hierarchy.replicated if hierarchy else None,
                        "l2_policy": "inputs larger than L2 (matrix %.2f GB per GPU streamed every "

@@ -455,6 +455,11 @@ extern "C"
             for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
               l->mg_smoother_ratio = double(value);
             break;
+          case GF_OPT_MG_REFRESH_INTERVAL:
+            GF_REQUIRE(value >= 1 && value <= 64, GF_ERR_INVALID_ARG, "bad refresh interval");
+            c.mg_refresh_interval = int(value);
+            c.mg_since_refresh    = 0;
+            break;
           case GF_OPT_MG_MATRIX_PRECISION:
             GF_REQUIRE(value >= 0 && value <= 2, GF_ERR_INVALID_ARG,
                        "matrix precision of the V-cycle: 0 (FP64), 1 (FP32 copy) or 2 (all FP32)");
@@ -547,7 +552,8 @@ extern "C"
                                           cudaMemcpyDeviceToDevice, c.stream));
             l->mg_e_saved_valid = l->mg_e_valid;
           }
-      c.has_saved = true;
+      c.mg_since_refresh = 0; // the window starts with fresh coarse operators (and so does its replay)
+      c.has_saved        = true;
       return GF_OK;
     });
   }
@@ -569,6 +575,7 @@ extern "C"
                                           cudaMemcpyDeviceToDevice, c.stream));
             l->mg_e_valid = l->mg_e_saved_valid;
           }
+      c.mg_since_refresh = 0;
       return GF_OK;
     });
   }

@@ -142,7 +142,7 @@ extern "C"
     GF_OPT_MG_SMOOTHER_DEGREE, /* Chebyshev degree of the pre-/post-smoother (default 3) */
     GF_OPT_MG_COARSE_DEGREE,   /* Chebyshev degree of the coarsest-level solve (default 80) */
     GF_OPT_MG_SMOOTHER_RATIO,  /* smoothers damp the eigenvalues in [lmax/ratio, lmax] (default 40) */
-    GF_OPT_MG_MATRIX_PRECISION /* 0 (default): the V-cycle streams the FP64 level matrices;
+    GF_OPT_MG_MATRIX_PRECISION,/* 0 (default): the V-cycle streams the FP64 level matrices;
                                   1: it streams FP32 copies of them (half the HBM bytes per smoother
                                   / residual application), accumulating in FP64;
                                   2 (experimental, not yet run on hardware): FP32 copies, x staged
@@ -150,6 +150,10 @@ extern "C"
                                   The outer CG (operator, residual, tolerance: nonlinear:1171-1187,
                                   linear:540-552) stays FP64 in every case, so the solve converges
                                   to the same tolerance; only the SSOR replacement changes. */
+    GF_OPT_MG_REFRESH_INTERVAL /* k >= 1 (default 1): re-discretise the coarse levels and re-estimate the
+                                  smoother eigenvalues at every k-th finest-level assembly (always at
+                                  the first one after gf_state_save / gf_state_restore); experimental
+                                  for k > 1, not yet measured */
   };
 
   /* device-time breakdown accumulated while GF_OPT_PROFILE = 1 (CUDA events on the library's

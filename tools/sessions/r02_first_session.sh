@@ -11,7 +11,8 @@ timeout 60 python tools/spmv_kinds_probe.py > gpurun_out/r02a_kinds.jsonl 2> gpu
 # 3) the bench line with candidate defaults (short runs)
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-variants"
 for cfg in "--spmv-kernel 0 --mg-precision 0" "--spmv-kernel 3 --mg-precision 0" "--spmv-kernel 6 --mg-precision 0" \
-           "--spmv-kernel 6 --mg-precision 1" "--spmv-kernel 6 --mg-precision 2" "--spmv-kernel 3 --mg-precision 2"; do
+           "--spmv-kernel 6 --mg-precision 1" "--spmv-kernel 6 --mg-precision 2" "--spmv-kernel 3 --mg-precision 2" \
+           "--spmv-kernel 0 --mg-refresh 2" "--spmv-kernel 0 --mg-refresh 4"; do
   tag=$(echo $cfg | tr -d ' -' )
   timeout 90 $B $cfg > gpurun_out/r02a_bench_$tag.json 2> gpurun_out/r02a_bench_$tag.err
   python - <<PY
