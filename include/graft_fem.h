@@ -262,7 +262,9 @@ extern "C"
    *   fields[(cell*npts + pt)*(dim+dim*dim) + ...] = u_0..u_{dim-1}, strain_00, strain_01, ...
    * with strain = sym(grad_x u) taken on the DISPLACED configuration (MappingQEulerian). The host
    * adds X(patch point) + u for the patch vertices and writes the VTK file. which_vector:
-   * GF_NL_TOTAL_DISPLACEMENT / GF_LIN_DISPLACEMENT (or any DoF vector). */
+   * GF_NL_TOTAL_DISPLACEMENT / GF_LIN_DISPLACEMENT (or any DoF vector). Partitioned handles return
+   * all LOCAL cells of desc.cell_dofs, i.e. including the redundantly assembled ghost cell layer
+   * (ghost DoFs are refreshed first); a rank writes the cells it owns. */
   int gf_postprocess(gf_handle h, int which_vector, double *fields);
 
   /* ---- kernels exposed for measurement ------------------------------------------------------ */
