@@ -195,9 +195,6 @@ def main():
     ap.add_argument("--mg-precision", type=int, default=0,
                     help="GF_OPT_MG_MATRIX_PRECISION for the whole run (0 FP64 level matrices in the "
                          "V-cycle, 1 FP32 copies, 2 all-FP32 operator)")
-    ap.add_argument("--mg-refresh", type=int, default=1,
-                    help="GF_OPT_MG_REFRESH_INTERVAL: rebuild the coarse multigrid operators at every "
-                         "k-th assembly only (1 = always)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true",
                     help="skip the matrix-free-operator variant measured after the main regions")
@@ -266,8 +263,6 @@ def main():
         h.set_option(capi.OPT_SPMV_KERNEL, args.spmv_kernel)
     if args.mg_precision and args.precond == "mg":
         h.set_option(capi.OPT_MG_MATRIX_PRECISION, args.mg_precision)
-    if args.mg_refresh > 1 and args.precond == "mg":
-        h.set_option(capi.OPT_MG_REFRESH_INTERVAL, args.mg_refresh)
     n_if = h.n_iface_nodes
     buf = np.tile(TRACTION, n_if)
     participant = solvers.FakeParticipant(3, 10 ** 9, prob.params.delta_t, lambda t, it: buf, N_SUB)
@@ -395,10 +390,10 @@ def main():
                     "operator_bytes_per_apply": bytes32,
                     "operator_gbs": bytes32 / ms32 / 1e6}
                 # stand-alone launches of every TMA kernel kind on the FP64 tangent and its FP32 copy
-                # (5: single ring; 2 / 3 / 4: two rings with 8+8 / 8+16 / 4+16 gather+consumer warps;
-                # the default takes 3 for plain launches and 5 for the fused-dot CG vmult)
+                # (5: single ring; 3: two rings with 8 gather + 16 consumer warps; 6 = default: 3 with
+                # the transposed row reduction)
                 kinds = {}
-                for kind in (5, 2, 3, 4):
+                for kind in (5, 3, 6):
                     h.set_option(capi.OPT_SPMV_KERNEL, kind)
                     m64, b64 = h.spmv_timed(capi.MAT_TANGENT, 5)
                     m32, b32 = h.spmv_timed(capi.MAT_MG_F32, 5)
@@ -450,7 +445,6 @@ def main():
                        "cg_iterations_in_timed_region": cg_its_value,
                        "preconditioner": args.precond,
                        "spmv_kernel_option": args.spmv_kernel, "mg_matrix_precision": args.mg_precision,
-                       "mg_refresh_interval": args.mg_refresh,
                        "multigrid_levels": [q.mesh.reps for q in hierarchy.problems] if hierarchy else None,
                        "multigrid_levels_replicated": hierarchy.replicated if hierarchy else None,
                        "l2_policy": "inputs larger than L2 (matrix %.2f GB per GPU streamed every "

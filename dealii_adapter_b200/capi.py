@@ -23,7 +23,7 @@ MAT_TANGENT, MAT_STIFFNESS, MAT_MASS, MAT_SYSTEM, MAT_MG_F32 = range(5)
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI, PRECOND_MULTIGRID = range(4)
 OPT_PRECONDITIONER, OPT_CG_CHECK_INTERVAL, OPT_PROFILE, OPT_OPERATOR, OPT_SPMV_KERNEL, \
     OPT_MG_SMOOTHER_DEGREE, OPT_MG_COARSE_DEGREE, OPT_MG_SMOOTHER_RATIO, \
-    OPT_MG_MATRIX_PRECISION, OPT_MG_REFRESH_INTERVAL = range(10)
+    OPT_MG_MATRIX_PRECISION = range(9)
 
 EXPORTED_SYMBOLS = [
     "gf_create", "gf_destroy", "gf_last_error", "gf_set_option", "gf_comm_unique_id",

@@ -436,7 +436,8 @@ extern "C"
             c.operator_kind = int(value);
             break;
           case GF_OPT_SPMV_KERNEL:
-            GF_REQUIRE(value >= 0 && value <= 6, GF_ERR_INVALID_ARG, "unknown SpMV kernel");
+            GF_REQUIRE(value == 0 || value == 1 || value == 3 || value == 5 || value == 6,
+                       GF_ERR_INVALID_ARG, "unknown SpMV kernel");
             for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
               l->spmv_kernel_kind = int(value);
             break;
@@ -454,11 +455,6 @@ extern "C"
             GF_REQUIRE(value >= 2 && value <= 1000, GF_ERR_INVALID_ARG, "bad smoother ratio");
             for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
               l->mg_smoother_ratio = double(value);
-            break;
-          case GF_OPT_MG_REFRESH_INTERVAL:
-            GF_REQUIRE(value >= 1 && value <= 64, GF_ERR_INVALID_ARG, "bad refresh interval");
-            c.mg_refresh_interval = int(value);
-            c.mg_since_refresh    = 0;
             break;
           case GF_OPT_MG_MATRIX_PRECISION:
             GF_REQUIRE(value >= 0 && value <= 2, GF_ERR_INVALID_ARG,
@@ -552,7 +548,6 @@ extern "C"
                                           cudaMemcpyDeviceToDevice, c.stream));
             l->mg_e_saved_valid = l->mg_e_valid;
           }
-      c.mg_since_refresh = 0; // the window starts with fresh coarse operators (and so does its replay)
       c.has_saved        = true;
       return GF_OK;
     });
@@ -575,7 +570,6 @@ extern "C"
                                           cudaMemcpyDeviceToDevice, c.stream));
             l->mg_e_valid = l->mg_e_saved_valid;
           }
-      c.mg_since_refresh = 0;
       return GF_OK;
     });
   }

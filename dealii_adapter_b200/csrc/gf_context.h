@@ -336,7 +336,6 @@ struct gf_context
                                               // 2: FP32 copy, x staged / accumulated in FP32 too
   gf::DevBuf<float>  mg_val32;                // [n_val + 4]
   bool               mg_val32_valid = false;
-  int                mg_refresh_interval = 1, mg_since_refresh = 0; // GF_OPT_MG_REFRESH_INTERVAL
   int                mg_smoother_degree = 3, mg_coarse_degree = 80;
   double             mg_smoother_ratio = 40.0, mg_coarse_ratio = 1000.0;
 

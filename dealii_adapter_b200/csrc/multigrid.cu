@@ -662,34 +662,22 @@ namespace gf
   {
     if (!c.mg.coarse)
       return;
-    // GF_OPT_MG_REFRESH_INTERVAL = k > 1: the tangent changes little from one Newton iteration to
-    // the next, so the coarse operators and the eigenvalue estimates are rebuilt only at every
-    // k-th assembly (and always at the first one after a checkpoint save / restore, which keeps a
-    // restored window a bit-for-bit replay); in between the V-cycle keeps the previous coarse
-    // levels and only the finest-level pieces (block-Jacobi inverse, FP32 copy) follow the matrix.
-    const bool refresh = c.mg_refresh_interval <= 1 || c.mg_since_refresh == 0 || c.mg_lmax == 0.0 ||
-                         c.mg.coarse->mg_lmax == 0.0;
-    c.mg_since_refresh = (c.mg_since_refresh + 1) % std::max(1, c.mg_refresh_interval);
-    if (refresh)
+    const double *u = u_total;
+    for (gf_context *l = &c; l->mg.coarse != nullptr; l = l->mg.coarse)
       {
-        const double *u = u_total;
-        for (gf_context *l = &c; l->mg.coarse != nullptr; l = l->mg.coarse)
+        gf_context &co = *l->mg.coarse;
+        if (c.model == GF_MODEL_NEO_HOOKEAN)
           {
-            gf_context &co = *l->mg.coarse;
-            if (c.model == GF_MODEL_NEO_HOOKEAN)
-              {
-                inject_state(*l, u, co.tmp0.p);
-                assemble_level_tangent(co, co.tmp0.p);
-                u = co.tmp0.p;
-              }
-            else
-              lin_assemble(co);
+            inject_state(*l, u, co.tmp0.p);
+            assemble_level_tangent(co, co.tmp0.p);
+            u = co.tmp0.p;
           }
+        else
+          lin_assemble(co);
       }
     mg_refresh_f32(c);
-    if (refresh)
-      for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
-        estimate_lmax(*l);
+    for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
+      estimate_lmax(*l);
   }
 
   // x = V-cycle(b), zero initial guess; b and x are level vectors of `c` (x != b)

@@ -16,12 +16,15 @@
 // profiles/r01_spmv_ncu_summary.md):
 //   5  spmv_tma_kernel: one 3-stage ring carries a tile through TMA -> x gather (8 warps) ->
 //      FMA (8 warps). 0.624 ms on the cfg3 tangent (5.33 TB/s).
-//   2/3/4  spmv_tma2_kernel<.., GW, GG, CW>: column indices / row records / gathered x in their own
+//   3  spmv_tma2_kernel<.., GW, GG, CW>: column indices / row records / gathered x in their own
 //      deeper ring running ahead of the value ring; GG groups of gather warps work on consecutive
 //      tiles; CW consumer warps. 8+16 warps (kind 3): 0.549 ms = 6.05 TB/s = 92 % of the measured
 //      copy peak - the consumer warps, not HBM or the gather, bounded the 8-consumer kernels
 //      (profiles/r01_spmv_variants_ncu.md).
-//   0  (default) kind 3 for plain launches, kind 5 for launches with the fused dot product.
+//   6  kind 3 with the three (two) scalar-row sums of a block row reduced by ONE transposed
+//      butterfly (kernel_utils.cuh::warp_sum_rows; bitwise the same sums): 0.517 ms = 6.43 TB/s =
+//      98 % of the measured copy peak (profiles/r02_spmv_kernel_kinds.jsonl).
+//   0  (default) kind 6 for every launch, with and without the fused dot product.
 //   1  spmv_kernel (LDG): one warp per row with streaming loads; also the fallback when a row
 //      does not fit a tile.
 // The fused dot product needs only gridDim.x partial sums (fixed order => reproducible).
@@ -706,35 +709,27 @@ namespace gf
       spmv_tma2_kernel<DIM, DOT, VT, XT, GW, GG, CW, TR><<<grid, C::THREADS, C::SMEM_BYTES, c.stream>>>(
         int(c.n_tiles), c.tile_desc.p, c.tile_meta.p, c.bcol.p, val, x, y, dot_partials, st);
     }
-    // warp split of the two-ring kernel by GF_OPT_SPMV_KERNEL:
-    //   2: 8 gather warps in 2 groups + 8 consumer warps (the split of the single-ring kernel)
-    //   3: 8 gather warps in 2 groups + 16 consumer warps   } ncu (profiles/r01_spmv_variants_ncu.md):
-    //   4: 4 gather warps in 1 group  + 16 consumer warps   } the 8 consumer warps are the busy role
+    // two-ring kernel: 8 gather warps in 2 groups + 16 consumer warps (kinds 3 and 6). The splits
+    // 8+8 and 4+16 of round 1 measured slower (0.600 / 0.572 ms against 0.544 ms,
+    // profiles/r02_spmv_kernel_kinds.jsonl) and were removed.
     template <int DIM, bool DOT, typename VT>
     void launch_tma2_t(gf_context &c, int kind, const VT *val, const double *x, double *y,
                        double *dot_partials, const int *st)
     {
-      if (kind == 6) // experimental: kind 3 with the transposed row reduction
+      if (kind == 6) // kind 3 with the transposed row reduction (the default)
         launch_tma2_w<DIM, DOT, VT, double, 8, 2, 16, true>(c, val, x, y, dot_partials, st);
-      else if (kind == 3)
-        launch_tma2_w<DIM, DOT, VT, double, 8, 2, 16>(c, val, x, y, dot_partials, st);
-      else if (kind == 4)
-        launch_tma2_w<DIM, DOT, VT, double, 4, 1, 16>(c, val, x, y, dot_partials, st);
       else
-        launch_tma2_w<DIM, DOT, VT, double, 8, 2, 8>(c, val, x, y, dot_partials, st);
+        launch_tma2_w<DIM, DOT, VT, double, 8, 2, 16>(c, val, x, y, dot_partials, st);
     }
 
-    // GF_OPT_SPMV_KERNEL = 0 (default) picks per launch type what has been MEASURED on the B200
-    // (profiles/r01_spmv_kernel_kinds.jsonl): plain y = A x launches (smoother / residual
-    // applications of the V-cycle, assemble_rhs vmults: 6 of 7 launches per CG iteration) take
-    // the two-ring kernel with 16 consumer warps (0.549 ms = 6.05 TB/s on the cfg3 tangent,
-    // bitwise equal y); launches with the fused dot product (the CG vmult) stay on the
-    // single-ring kernel until the 16-warp dot variant has run on hardware.
-    int effective_kind(const gf_context &c, bool fused_dot)
+    // GF_OPT_SPMV_KERNEL = 0 (default) is what has been MEASURED fastest on the B200
+    // (profiles/r02_spmv_kernel_kinds.jsonl): the two-ring kernel with 16 consumer warps and the
+    // transposed row reduction (kind 6) for every launch, with or without the fused dot product:
+    // 0.517 ms = 6.43 TB/s on the cfg3 tangent (98 % of the measured copy peak), bitwise the y of
+    // every other kind.
+    int effective_kind(const gf_context &c, bool /*fused_dot*/)
     {
-      if (c.spmv_kernel_kind == 0)
-        return fused_dot ? 5 : 3;
-      return c.spmv_kernel_kind;
+      return c.spmv_kernel_kind == 0 ? 6 : c.spmv_kernel_kind;
     }
 
     template <int DIM, bool DOT, typename VT>
@@ -819,7 +814,7 @@ namespace gf
       return;
     const int *st   = dot_partials ? &c.cg_scalars.p->status : nullptr;
     const int  kind = effective_kind(c, dot_partials != nullptr);
-    if (c.n_tiles > 0 && ((kind >= 2 && kind <= 4) || kind == 6))
+    if (c.n_tiles > 0 && (kind == 3 || kind == 6))
       {
         if (c.dim == 3)
           {
@@ -887,7 +882,7 @@ namespace gf
     if (n_rows == 0)
       return;
     const int kind = effective_kind(c, false);
-    if (c.n_tiles > 0 && ((kind >= 2 && kind <= 4) || kind == 6))
+    if (c.n_tiles > 0 && (kind == 3 || kind == 6))
       {
         if (c.dim == 3)
           launch_tma2_t<3, false, float>(c, kind, val32, x, y, nullptr, nullptr);

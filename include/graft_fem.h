@@ -130,30 +130,26 @@ extern "C"
                                   cheap enough for a timed region); launch counters always run */
     GF_OPT_OPERATOR,           /* 0: assembled BSR SpMV ; 1: matrix-free tangent operator in CG */
     GF_OPT_SPMV_KERNEL,        /* all kinds give bitwise identical y = A x (same per-row summation order):
-                                  0 (default): per launch type the fastest kernel verified on the
-                                     B200 - two-ring TMA kernel with 16 consumer warps for plain
-                                     y = A x, single-ring TMA kernel for the fused-dot CG vmult;
-                                  1: LDG warp-per-row kernel;
-                                  2 / 3 / 4: two-ring TMA kernel (value ring decoupled from the
-                                     column/x ring) with 8+8 / 8+16 / 4+16 gather+consumer warps,
-                                     for every launch; 5: single-ring TMA kernel for every launch;
-                                  6 (experimental, not yet run on hardware): kind 3 with a
-                                     transposed warp reduction of the scalar-row sums */
+                                  0 (default): the fastest kernel measured on the B200 = kind 6 for
+                                     every launch (0.517 ms = 6.43 TB/s on the cfg3 tangent);
+                                  1: LDG warp-per-row kernel (also the fallback for rows that do
+                                     not fit a tile);
+                                  3: two-ring TMA kernel (value ring decoupled from the column/x
+                                     ring), 8 gather + 16 consumer warps;
+                                  5: single-ring TMA kernel (8 + 8 warps);
+                                  6: kind 3 with a transposed warp reduction of the scalar-row
+                                     sums of a block row */
     GF_OPT_MG_SMOOTHER_DEGREE, /* Chebyshev degree of the pre-/post-smoother (default 3) */
     GF_OPT_MG_COARSE_DEGREE,   /* Chebyshev degree of the coarsest-level solve (default 80) */
     GF_OPT_MG_SMOOTHER_RATIO,  /* smoothers damp the eigenvalues in [lmax/ratio, lmax] (default 40) */
-    GF_OPT_MG_MATRIX_PRECISION,/* 0 (default): the V-cycle streams the FP64 level matrices;
+    GF_OPT_MG_MATRIX_PRECISION /* 0 (default): the V-cycle streams the FP64 level matrices;
                                   1: it streams FP32 copies of them (half the HBM bytes per smoother
                                   / residual application), accumulating in FP64;
-                                  2 (experimental, not yet run on hardware): FP32 copies, x staged
-                                  and accumulated in FP32 as well (vectors stay FP64 in HBM).
+                                  2: FP32 copies, x staged and accumulated in FP32 as well (vectors
+                                  stay FP64 in HBM).
                                   The outer CG (operator, residual, tolerance: nonlinear:1171-1187,
                                   linear:540-552) stays FP64 in every case, so the solve converges
                                   to the same tolerance; only the SSOR replacement changes. */
-    GF_OPT_MG_REFRESH_INTERVAL /* k >= 1 (default 1): re-discretise the coarse levels and re-estimate the
-                                  smoother eigenvalues at every k-th finest-level assembly (always at
-                                  the first one after gf_state_save / gf_state_restore); experimental
-                                  for k > 1, not yet measured */
   };
 
   /* device-time breakdown accumulated while GF_OPT_PROFILE = 1 (CUDA events on the library's

@@ -145,15 +145,8 @@ def test_f32_vcycle_linear_model(libs):
 
 
 # ---- GF_OPT_MG_MATRIX_PRECISION = 2: x staged and accumulated in FP32 as well -----------------
-import os  # noqa: E402
-
-experimental = pytest.mark.skipif(
-    os.environ.get("GF_TEST_EXPERIMENTAL") != "1",
-    reason="the all-FP32 V-cycle operator was written after the round's GPU minutes ended; it is "
-           "opt-in (GF_OPT_MG_MATRIX_PRECISION = 2) and on no default path")
 
 
-@experimental
 @pytest.mark.parametrize("dim,degree,reps", [(3, 2, [4, 8, 4]), (3, 1, [6, 10, 4]), (2, 2, [8, 16])])
 def test_all_fp32_operator_is_a_single_precision_spmv(libs, dim, degree, reps):
     capi, solvers, mg = libs
@@ -177,7 +170,6 @@ def test_all_fp32_operator_is_a_single_precision_spmv(libs, dim, degree, reps):
     H.close()
 
 
-@experimental
 def test_all_fp32_vcycle_keeps_newton_counts_and_displacements(libs):
     capi, solvers, mg = libs
     p = nl_params(poly_degree=2, scenario="PF", type_lin="CG", delta_t=0.01,
@@ -200,37 +192,3 @@ def test_all_fp32_vcycle_keeps_newton_counts_and_displacements(libs):
         assert all(abs(x - y) <= 2 for x, y in zip(a, b))
     for d32, d64 in zip(out[2][1], out[0][1]):
         assert rel_err(d32, d64) < 1e-7
-
-
-@experimental
-def test_coarse_operator_refresh_interval_keeps_newton_counts_and_replays(libs):
-    """GF_OPT_MG_REFRESH_INTERVAL = 3: coarse operators rebuilt at every third assembly (and at the
-    first one after a checkpoint save / restore). Newton counts and displacements must not move,
-    and an implicit window must still replay bit for bit."""
-    capi, solvers, mg = libs
-    p = nl_params(poly_degree=2, scenario="PF", type_lin="CG", delta_t=0.01,
-                  max_iterations_lin=1.0)
-    prob = make_problem(p, 3, reps=[4, 16, 4], numbering="lexicographic")
-    n = prob.n_iface_nodes
-    traction = lambda t, it: np.tile(np.array([1500.0, 0.0, 0.0]) * min(1.0, t / 0.02), n)
-    out = {}
-    for interval in (1, 3, 3):
-        H = mg.Hierarchy(prob)
-        H.fine.set_option(capi.OPT_MG_REFRESH_INTERVAL, interval)
-        part = solvers.FakeParticipant(3, 3, p.delta_t, traction, 2)
-        solid = solvers.Solid(prob, part, handle=H.fine)
-        solid.run()
-        res = ([[r[0] for r in rows] for rows in solid.history], [d for (w, it, d) in part.written])
-        if interval in out:                              # run-to-run: bitwise
-            assert res[0] == out[interval][0]
-            assert all(np.array_equal(a, b) for a, b in zip(res[1], out[interval][1]))
-        out[interval] = res
-        H.close()
-    assert [len(r) for r in out[3][0]] == [len(r) for r in out[1][0]]
-    for a, b in zip(out[3][0], out[1][0]):
-        assert all(abs(x - y) <= 3 for x, y in zip(a, b))
-    for d3, d1 in zip(out[3][1], out[1][1]):
-        assert rel_err(d3, d1) < 1e-7
-    # the two passes of a window (same traction, restored state) give the same displacement
-    # whatever the interval: the restore resets the refresh counter
-    assert rel_err(out[3][1][1], out[3][1][0]) < 1e-7

@@ -1,10 +1,11 @@
-"""GPU tests of the SpMV kernel kinds (GF_OPT_SPMV_KERNEL): the two-ring TMA kernels (2: 8+8,
-3: 8+16, 4: 4+16 gather+consumer warps) use the same tiles and the same per-row summation order as
-the single-ring TMA kernel (5) and the LDG kernel (1), so y = A x (vmult inside SolverCG,
-nonlinear_elasticity.cc:1184, linear_elasticity.cc:551) must be BITWISE identical, for the FP64
-matrix and for its FP32 V-cycle copy. The default (0) takes kind 3 for plain launches and kind 5
-for the fused-dot CG vmult; kinds with 8 consumer warps also keep the order of the fused dot
-product, so whole coupled runs reproduce the CG history bit for bit."""
+"""GPU tests of the SpMV kernel kinds (GF_OPT_SPMV_KERNEL): the two-ring TMA kernels (3: 8 gather +
+16 consumer warps; 6: the same with the transposed row reduction = the default 0) use the same
+tiles and the same per-row summation order as the single-ring TMA kernel (5) and the LDG kernel
+(1), so y = A x (vmult inside SolverCG, nonlinear_elasticity.cc:1184, linear_elasticity.cc:551)
+must be BITWISE identical, for the FP64 matrix and for its FP32 V-cycle copy. The fused dot
+product of the CG vmult is summed over the consumer warps of a CTA, so kinds with a different warp
+count / lane layout may move the CG history in the last bits (never the iteration counts);
+a kind always reproduces itself bit for bit."""
 import os
 
 import numpy as np
@@ -44,9 +45,7 @@ def test_two_ring_kernel_is_bitwise_equal(libs, dim, degree, reps, numbering):
     h.set_vector(capi.VEC_SCRATCH0, rng.uniform(-1, 1, prob.n_dofs))
     for mat in (capi.MAT_TANGENT, capi.MAT_MG_F32):
         ys = []
-        kinds = (5, 0, 1, 2, 2, 3, 4)         # twice: the rings are re-initialised per launch
-        if os.environ.get("GF_TEST_EXPERIMENTAL") == "1":
-            kinds += (6,)                     # transposed row reduction: not yet run on hardware
+        kinds = (5, 0, 1, 3, 3, 6)            # twice: the rings are re-initialised per launch
         for kind in kinds:
             h.set_option(capi.OPT_SPMV_KERNEL, kind)
             h.spmv(mat, capi.VEC_SCRATCH0, capi.VEC_SCRATCH1)
@@ -65,7 +64,7 @@ def test_two_ring_kernel_reproduces_a_coupled_run_bit_for_bit(libs):
     n = prob.n_iface_nodes
     traction = lambda t, it: np.tile(np.array([1500.0, 0.0, 0.0]) * min(1.0, t / 0.02), n)
     out = {}
-    for kind in (5, 0, 2):
+    for kind in (6, 0, 0):
         for prec in (0, 1):
             H = mg.Hierarchy(prob)
             H.fine.set_option(capi.OPT_SPMV_KERNEL, kind)
@@ -73,21 +72,21 @@ def test_two_ring_kernel_reproduces_a_coupled_run_bit_for_bit(libs):
             part = solvers.FakeParticipant(3, 2, p.delta_t, traction, 2)
             solid = solvers.Solid(prob, part, handle=H.fine)
             solid.run()
-            out[kind, prec] = (np.array([r for rows in solid.history for r in rows]),
-                               np.array([d for (w, it, d) in part.written]))
+            res = (np.array([r for rows in solid.history for r in rows]),
+                   np.array([d for (w, it, d) in part.written]))
             H.close()
-    for prec in (0, 1):
-        for kind in (0, 2):
-            assert np.array_equal(out[kind, prec][0], out[5, prec][0])   # Newton table incl. residuals
-            assert np.array_equal(out[kind, prec][1], out[5, prec][1])
+            if (kind, prec) in out:     # the default twice: run-to-run bitwise
+                assert np.array_equal(res[0], out[kind, prec][0])
+                assert np.array_equal(res[1], out[kind, prec][1])
+            out[kind, prec] = res
+    for prec in (0, 1):                 # default == kind 6
+        assert np.array_equal(out[0, prec][0], out[6, prec][0])   # Newton table incl. residuals
+        assert np.array_equal(out[0, prec][1], out[6, prec][1])
 
 
-@pytest.mark.skipif(os.environ.get("GF_TEST_EXPERIMENTAL") != "1",
-                    reason="the fused-dot variant with 16 consumer warps has not run on hardware "
-                           "yet (round 1 ran out of GPU time); it is not on any default path")
 def test_sixteen_consumer_warps_with_fused_dot(libs):
-    """Kinds 3 / 4 for EVERY launch: the dot partials are summed over 16 instead of 8 warps, so
-    the CG history may differ in the last bits but nothing else may change."""
+    """Kinds 3 / 6 (= the default) against the single-ring kernel: the dot partials are summed over
+    16 instead of 8 warps, so the CG history may differ in the last bits but nothing else may."""
     capi, solvers, mg = libs
     p = nl_params(poly_degree=2, scenario="PF", type_lin="CG", delta_t=0.01,
                   max_iterations_lin=1.0)
@@ -95,7 +94,7 @@ def test_sixteen_consumer_warps_with_fused_dot(libs):
     n = prob.n_iface_nodes
     traction = lambda t, it: np.tile(np.array([1500.0, 0.0, 0.0]) * min(1.0, t / 0.02), n)
     out = {}
-    for kind in (5, 3, 4, 6):
+    for kind in (5, 3, 6, 0):
         H = mg.Hierarchy(prob)
         H.fine.set_option(capi.OPT_SPMV_KERNEL, kind)
         part = solvers.FakeParticipant(3, 2, p.delta_t, traction, 2)
@@ -104,7 +103,7 @@ def test_sixteen_consumer_warps_with_fused_dot(libs):
         out[kind] = (np.array([r for rows in solid.history for r in rows]),
                      np.array([d for (w, it, d) in part.written]))
         H.close()
-    for kind in (3, 4, 6):
+    for kind in (3, 6, 0):
         assert out[kind][0].shape == out[5][0].shape                   # same Newton counts
         assert np.array_equal(out[kind][0][:, 0], out[5][0][:, 0])     # same CG iteration counts
         assert np.abs(out[kind][1] - out[5][1]).max() <= 1e-11 * np.abs(out[5][1]).max()
@@ -116,7 +115,7 @@ def test_two_ring_kernel_linear_model(libs):
     prob = make_problem(p, 3, reps=[6, 20, 6])
     buf = np.tile([300.0, -100.0, 50.0], prob.n_iface_nodes)
     out = {}
-    for kind in (5, 0, 2):
+    for kind in (5, 0, 3, 6):
         h = capi.Handle(prob)
         h.set_option(capi.OPT_SPMV_KERNEL, kind)
         part = solvers.FakeParticipant(3, 3, p.delta_t, lambda t, it: buf)
@@ -124,6 +123,7 @@ def test_two_ring_kernel_linear_model(libs):
         ed.run()
         out[kind] = (np.array(ed.history), part.written[-1][2])
         h.close()
-    for kind in (0, 2):
-        assert np.array_equal(out[kind][0], out[5][0])
-        assert np.array_equal(out[kind][1], out[5][1])
+    assert np.array_equal(out[0][0], out[6][0]) and np.array_equal(out[0][1], out[6][1])
+    for kind in (3, 6):
+        assert np.array_equal(out[kind][0][:, 0], out[5][0][:, 0])     # CG iteration counts
+        assert np.abs(out[kind][1] - out[5][1]).max() <= 1e-11 * np.abs(out[5][1]).max()

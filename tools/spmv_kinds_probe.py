@@ -1,4 +1,4 @@
-"""Seconds-long probe of the SpMV kernel kinds (GF_OPT_SPMV_KERNEL 0..4): bitwise equality of
+"""Seconds-long probe of the SpMV kernel kinds (GF_OPT_SPMV_KERNEL 0, 1, 3, 5, 6): bitwise equality of
 y = A x against kind 0 on a small 3D Q2 and a 2D Q2 problem, then launch times on the cfg3 tangent
 (FP64 and FP32 copy). Prints one JSON line per stage so that a cut-off run still reports."""
 import json
@@ -15,8 +15,7 @@ from helpers import nl_params, smooth_field  # noqa: E402
 from dealii_adapter_b200 import capi, multigrid  # noqa: E402
 from dealii_adapter_b200.problem import make_problem  # noqa: E402
 
-KINDS = [int(k) for k in os.environ.get(
-    "GF_PROBE_KINDS", "0,2,3,4,6" if os.environ.get("GF_TEST_EXPERIMENTAL") == "1" else "0,2,3,4").split(",")]
+KINDS = [int(k) for k in os.environ.get("GF_PROBE_KINDS", "0,1,3,5,6").split(",")]
 
 
 def assembled(prob, n_levels=2):
@@ -58,11 +57,10 @@ for kind in KINDS:
     ms32, b32 = h.spmv_timed(capi.MAT_MG_F32, 10)
     print(json.dumps({"stage": "cfg3_timing", "kind": kind, "fp64_ms": ms64, "fp64_gbs": b64 / ms64 / 1e6,
                       "fp32_ms": ms32, "fp32_gbs": b32 / ms32 / 1e6}), flush=True)
-if os.environ.get("GF_TEST_EXPERIMENTAL") == "1":
-    # all-FP32 operator (GF_OPT_MG_MATRIX_PRECISION = 2), 8+16 warps
-    h.set_option(capi.OPT_SPMV_KERNEL, 0)
-    h.set_option(capi.OPT_MG_MATRIX_PRECISION, 2)
-    h.nl_newton_assemble()
-    ms32x, b32 = h.spmv_timed(capi.MAT_MG_F32, 10)
-    print(json.dumps({"stage": "cfg3_timing_all_fp32", "ms": ms32x, "gbs": b32 / ms32x / 1e6}), flush=True)
+# all-FP32 operator (GF_OPT_MG_MATRIX_PRECISION = 2), 8+16 warps
+h.set_option(capi.OPT_SPMV_KERNEL, 0)
+h.set_option(capi.OPT_MG_MATRIX_PRECISION, 2)
+h.nl_newton_assemble()
+ms32x, b32 = h.spmv_timed(capi.MAT_MG_F32, 10)
+print(json.dumps({"stage": "cfg3_timing_all_fp32", "ms": ms32x, "gbs": b32 / ms32x / 1e6}), flush=True)
 H.close()
