@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "gf_nl_newton_solve", "gf_nl_end_step", "gf_lin_assemble_once", "gf_lin_step", "gf_get_vector",
     "gf_set_vector", "gf_nnz", "gf_export_csr", "gf_spmv", "gf_spmv_timed", "gf_profile_get",
     "gf_synchronize", "gf_event_record", "gf_event_elapsed_ms", "gf_mg_attach", "gf_mg_vcycle",
-    "gf_comm_transport", "gf_comm_timed", "gf_postprocess",
+    "gf_comm_transport", "gf_comm_timed", "gf_postprocess", "gf_export_rows",
 ]
 
 
@@ -113,6 +113,7 @@ def lib():
         L.gf_nnz.argtypes = [vp]
         L.gf_nnz.restype = i64
         L.gf_export_csr.argtypes = [vp, i32, vp, vp, vp]
+        L.gf_export_rows.argtypes = [vp, i32, i64, vp, vp, vp, vp]
         L.gf_spmv.argtypes = [vp, i32, i32, i32]
         L.gf_spmv_timed.argtypes = [vp, i32, i32, C.POINTER(dbl), C.POINTER(dbl)]
         L.gf_profile_get.argtypes = [vp, C.POINTER(GfProfile), i32]
@@ -328,6 +329,19 @@ class Handle:
         val = np.zeros(nnz)
         self._check(lib().gf_export_csr(self._h, which, rowptr.ctypes.data, col.ctypes.data,
                                         val.ctypes.data))
+        return rowptr, col, val
+
+    def export_rows(self, which, rows):
+        """Selected owned rows (caller dof ids) of one matrix: (rowptr, col, val), ascending
+        caller columns per row."""
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        rowptr = np.zeros(len(rows) + 1, dtype=np.int64)
+        self._check(lib().gf_export_rows(self._h, which, len(rows), rows.ctypes.data,
+                                         rowptr.ctypes.data, None, None))
+        col = np.zeros(rowptr[-1], dtype=np.int32)
+        val = np.zeros(rowptr[-1])
+        self._check(lib().gf_export_rows(self._h, which, len(rows), rows.ctypes.data,
+                                         rowptr.ctypes.data, col.ctypes.data, val.ctypes.data))
         return rowptr, col, val
 
     def postprocess(self, which_vector):

@@ -869,6 +869,84 @@ extern "C"
     });
   }
 
+  int gf_export_rows(gf_handle h, int which, int64_t n_rows, const int32_t *rows, int64_t *rowptr,
+                     int32_t *col, double *val)
+  {
+    return guarded(h, [&](gf_context &c) {
+      GF_REQUIRE(n_rows >= 0 && rows && rowptr, GF_ERR_INVALID_ARG, "null buffer");
+      GF_REQUIRE((col == nullptr) == (val == nullptr), GF_ERR_INVALID_ARG,
+                 "col and val must both be given or both be NULL");
+      const int dim = c.dim;
+      if (which == GF_MAT_MASS)
+        GF_REQUIRE(c.mass_blk.p != nullptr, GF_ERR_INVALID_ARG, "no mass matrix for this model");
+      else
+        {
+          mat_ptr(c, which);
+          GF_REQUIRE(which != GF_MAT_TANGENT || c.operator_kind == 0, GF_ERR_INVALID_ARG,
+                     "no assembled tangent in matrix-free mode (GF_OPT_OPERATOR = 1)");
+        }
+      GF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      std::vector<int32_t>                    bcol;
+      std::vector<double>                     v;
+      std::vector<std::pair<int32_t, double>> row;
+      int64_t                                 pos = 0;
+      rowptr[0]                                   = 0;
+      for (int64_t k = 0; k < n_rows; ++k)
+        {
+          const int32_t e = rows[k];
+          GF_REQUIRE(e >= 0 && e < c.n_ext_owned, GF_ERR_INVALID_ARG, "row is not an owned dof");
+          const int32_t i = c.h_perm_e2i[e];
+          const int64_t A = i / dim;
+          const int     r = i % dim;
+          int32_t       b[2];
+          int64_t       vp[2];
+          GF_CUDA_CHECK(cudaMemcpy(b, c.brow_ptr.p + A, sizeof(b), cudaMemcpyDeviceToHost));
+          GF_CUDA_CHECK(cudaMemcpy(vp, c.val_ptr.p + A, sizeof(vp), cudaMemcpyDeviceToHost));
+          const int nb = b[1] - b[0];
+          if (col != nullptr)
+            {
+              const int64_t stride = (vp[1] - vp[0]) / dim;
+              bcol.resize(nb);
+              GF_CUDA_CHECK(cudaMemcpy(bcol.data(), c.bcol.p + b[0], nb * sizeof(int32_t),
+                                       cudaMemcpyDeviceToHost));
+              if (which == GF_MAT_MASS)
+                {
+                  v.resize(nb);
+                  GF_CUDA_CHECK(cudaMemcpy(v.data(), c.mass_blk.p + b[0], nb * sizeof(double),
+                                           cudaMemcpyDeviceToHost));
+                }
+              else
+                {
+                  v.resize(size_t(nb) * dim);
+                  GF_CUDA_CHECK(cudaMemcpy(v.data(), c.mat[which].val.p + vp[0] + r * stride,
+                                           size_t(nb) * dim * sizeof(double),
+                                           cudaMemcpyDeviceToHost));
+                }
+              row.clear();
+              for (int blk = 0; blk < nb; ++blk)
+                for (int cc = 0; cc < dim; ++cc)
+                  row.emplace_back(c.h_perm_i2e[bcol[blk] * dim + cc],
+                                   which == GF_MAT_MASS ? (r == cc ? v[blk] : 0.0) :
+                                                          v[size_t(blk) * dim + cc]);
+              std::sort(row.begin(), row.end(),
+                        [](const std::pair<int32_t, double> &x, const std::pair<int32_t, double> &y) {
+                          return x.first < y.first;
+                        });
+              for (auto &kv : row)
+                {
+                  col[pos] = kv.first;
+                  val[pos] = kv.second;
+                  ++pos;
+                }
+            }
+          else
+            pos += int64_t(nb) * dim;
+          rowptr[k + 1] = pos;
+        }
+      return GF_OK;
+    });
+  }
+
   // ------------------------------------------------------------------------------------------
   int gf_postprocess(gf_handle h, int which_vector, double *fields)
   {

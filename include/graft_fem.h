@@ -251,6 +251,12 @@ extern "C"
   /* scalar CSR (ascending columns) of one matrix in the caller's numbering, owned rows only */
   int gf_export_csr(gf_handle h, int which_matrix, int64_t *rowptr, int32_t *col, double *val);
 
+  /* the same for n_rows selected owned rows (caller dof ids, any order): rowptr[n_rows+1] is always
+   * filled; col / val may both be NULL to query the sizes first. Parity tests at BASELINE's full
+   * sizes compare sampled rows (a whole-matrix export of cfg3 is 4.6 GB, of cfg4 49 GB). */
+  int gf_export_rows(gf_handle h, int which_matrix, int64_t n_rows, const int32_t *rows,
+                     int64_t *rowptr, int32_t *col, double *val);
+
   /* Output-step post-processing: what DataOut::build_patches(MappingQEulerian, degree) +
    * Postprocessor::evaluate_vector_field compute (nonlinear:1215-1254 / linear:590-629,
    * postprocessor.h:44-76). For every local cell (order of desc.cell_dofs) and every one of its

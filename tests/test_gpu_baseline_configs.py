@@ -4,10 +4,13 @@ cfg1 (PF 2D linear Q2, 3x18 cells, 518 DoFs) is `test_linear_matrices_and_steps_
 reps0-cellwise]` in test_gpu_parity.py. Here:
   cfg2  FSI3 2D Q2 neo-Hookean, 144x24 cells, 28,322 DoFs: Newton counts identical and interface /
         watch-point displacement 1e-8 against the committed oracle fixture (tests/golden/).
-  cfg3  PF 3D Q2 neo-Hookean 24x144x24 cells, 2,081,667 DoFs (too large for the CPU oracle in a
-        test): size-independent properties — bitwise reproducible assembly, symmetry and linearity
-        of the operator, TMA kernel == LDG kernel bitwise, matrix-free == assembled to 1e-12,
-        checkpoint/restore replays a coupled timestep bit for bit."""
+  cfg3  PF 3D Q2 neo-Hookean 24x144x24 cells, 2,081,667 DoFs: ~1000 sampled tangent rows and
+        residual entries against the ORACLE (sub-mesh device of tests/sampled_rows.py, run live
+        and compared with the committed fixture), 1e-12 row-relative; plus size-independent
+        properties — bitwise reproducible assembly, symmetry and linearity of the operator, TMA
+        kernel == LDG kernel bitwise, matrix-free == assembled to 1e-12, checkpoint/restore
+        replays a coupled timestep bit for bit.
+  cfg4  (51 M DoFs) lives in tests/test_gpu_baseline_cfg4.py."""
 import os
 import sys
 
@@ -68,6 +71,38 @@ def _load_state(capi, h, prob, seed):
     h.set_vector(capi.NL_VELOCITY_OLD, smooth_field(prob, 0.05, seed + 1))
     h.set_vector(capi.NL_ACCELERATION_OLD, smooth_field(prob, 2.0, seed + 2))
     h.set_traction(np.tile([1500.0, 0.0, 50.0], prob.n_iface_nodes))
+    h.nl_begin_step()
+
+
+def test_cfg3_sampled_rows_and_residual_match_oracle(libs, cfg3):
+    """Matrix entries 1e-12 (row-relative) and residual entries at the bench size: 1026 rows of the
+    cfg3 tangent incl. clamped-face, z-clamped, interface, edge/corner and slab-cut rows."""
+    capi, solvers, mg = libs
+    prob, H = cfg3
+    h = H.fine
+    import make_sampled_rows as g
+    import sampled_rows as sr
+    ref = g.cfg3_oracle_rows(prob)                  # the oracle, live (sub-mesh of 885 cells)
+    gold = np.load(os.path.join(HERE, "golden", "sampled_rows_cfg3.npz"))
+    assert np.array_equal(ref["rows"], gold["rows"]) and np.array_equal(ref["col"], gold["col"])
+    assert rel_err(ref["val"], gold["val"]) < 1e-13 and rel_err(ref["rhs"], gold["rhs"]) < 1e-13
+    assert len(ref["rows"]) >= 1000
+    s = g.cfg3_state(prob)
+    h.set_vector(capi.NL_TOTAL_DISPLACEMENT, s["u"])
+    h.set_vector(capi.NL_SOLUTION_DELTA, s["du"])
+    h.set_vector(capi.NL_VELOCITY_OLD, s["v_old"])
+    h.set_vector(capi.NL_ACCELERATION_OLD, s["a_old"])
+    h.set_traction(s["traction"])
+    h.nl_newton_assemble()
+    err = sr.assert_rows_close(h.export_rows(capi.MAT_TANGENT, ref["rows"]), ref["rowptr"],
+                               ref["col"], ref["val"], 1e-12)
+    rhs = h.get_vector(capi.NL_SYSTEM_RHS)
+    assert np.abs(rhs[ref["rows"]] - ref["rhs"]).max() <= 1e-12 * np.abs(ref["rhs"]).max()
+    con = prob.constrained[ref["rows"]] != 0
+    assert con.sum() > 50 and np.all(rhs[ref["rows"]][con] == 0.0)
+    print("cfg3 sampled rows: %d rows, max row-relative error %.2e" % (len(ref["rows"]), err))
+    for k in range(6):                      # leave a clean state for the tests below
+        h.set_vector(k, np.zeros(prob.n_dofs))
     h.nl_begin_step()
 
 
