@@ -32,7 +32,8 @@ EXPORTED_SYMBOLS = [
     "gf_nl_newton_solve", "gf_nl_end_step", "gf_lin_assemble_once", "gf_lin_step", "gf_get_vector",
     "gf_set_vector", "gf_nnz", "gf_export_csr", "gf_spmv", "gf_spmv_timed", "gf_profile_get",
     "gf_synchronize", "gf_event_record", "gf_event_elapsed_ms", "gf_mg_attach", "gf_mg_vcycle",
-    "gf_comm_transport", "gf_comm_timed", "gf_postprocess", "gf_export_rows",
+    "gf_comm_transport", "gf_comm_timed", "gf_postprocess", "gf_export_rows", "gf_comm_ipc_begin",
+    "gf_comm_ipc_finish",
 ]
 
 
@@ -57,6 +58,7 @@ class GfDesc(C.Structure):
         ("n_neighbors", C.c_int32), ("nbr_rank", C.c_void_p),
         ("send_ptr", C.c_void_p), ("send_dofs", C.c_void_p),
         ("recv_ptr", C.c_void_p), ("recv_dofs", C.c_void_p),
+        ("dof_global", C.c_void_p), ("slab_axis", C.c_int32),
     ]
 
 
@@ -99,6 +101,8 @@ def lib():
         L.gf_comm_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
         L.gf_comm_destroy.argtypes = [vp]
         L.gf_comm_destroy.restype = None
+        L.gf_comm_ipc_begin.argtypes = [i32, i32, i32, C.POINTER(vp), vp]
+        L.gf_comm_ipc_finish.argtypes = [vp, vp]
         L.gf_set_traction.argtypes = [vp, vp]
         L.gf_get_interface_displacement.argtypes = [vp, vp]
         for n in ("gf_state_save", "gf_state_restore", "gf_nl_begin_step", "gf_nl_end_step",
@@ -139,6 +143,27 @@ class Comm:
         self._h = h
         self.rank, self.n_ranks = rank, n_ranks
 
+    @classmethod
+    def from_ipc(cls, rank: int, n_ranks: int, device: int, all_gather):
+        """Communicator without NCCL (gf_comm_ipc_begin / _finish): `all_gather(bytes) -> [bytes]`
+        moves every rank's 64-byte window handle over the host's own channel (e.g.
+        torch.distributed with the gloo backend). Ranks may share a device."""
+        self = cls.__new__(cls)
+        h = C.c_void_p()
+        mine = (C.c_uint8 * 64)()
+        rc = lib().gf_comm_ipc_begin(rank, n_ranks, device, C.byref(h), mine)
+        if rc != GF_OK:
+            raise GraftError(rc, "gf_comm_ipc_begin failed")
+        handles = all_gather(bytes(mine))
+        assert len(handles) == n_ranks and all(len(x) == 64 for x in handles)
+        buf = (C.c_uint8 * (64 * n_ranks)).from_buffer_copy(b"".join(handles))
+        rc = lib().gf_comm_ipc_finish(h, buf)
+        if rc != GF_OK:
+            raise GraftError(rc, "gf_comm_ipc_finish failed (cudaIpcOpenMemHandle)")
+        self._h = h
+        self.rank, self.n_ranks = rank, n_ranks
+        return self
+
     @staticmethod
     def unique_id() -> bytes:
         buf = (C.c_uint8 * 128)()
@@ -164,9 +189,11 @@ class Comm:
 
 class Handle:
     """Owns one gf_handle. `problem` is a dealii_adapter_b200.problem.Problem; `partition` an
-    optional mesh.MeshPartition with `comm`."""
+    optional mesh.MeshPartition with `comm`. `slab_axis` (0, 1, 2 or None): the axis the mesh is
+    (or would be) cut along - with it every dot product / norm / restriction sums over a
+    partition-independent tree, so a run gives the same bits for any number of ranks (gf_desc)."""
 
-    def __init__(self, problem, device=0, partition=None, comm=None):
+    def __init__(self, problem, device=0, partition=None, comm=None, slab_axis=None):
         L = lib()
         p = problem.params
         self.problem = problem
@@ -221,6 +248,12 @@ class Handle:
         d.data_consistent = 1 if p.data_consistent else 0
         d.device = device
         d.n_owned_dofs = n_owned
+        if slab_axis is None and partition is not None:
+            slab_axis = partition.axis
+        d.slab_axis = 0 if slab_axis is None else slab_axis + 1
+        if partition is not None:
+            keep_alive.append(np.ascontiguousarray(partition.local_to_global, dtype=np.int64))
+            d.dof_global = keep_alive[-1].ctypes.data
         if partition is not None and comm is not None:
             d.comm = comm._h
             d.n_neighbors = len(partition.nbr_rank)
@@ -230,7 +263,7 @@ class Handle:
                            np.ascontiguousarray(partition.recv_ptr, dtype=np.int64),
                            np.ascontiguousarray(partition.recv_dofs, dtype=np.int32)]
             d.nbr_rank, d.send_ptr, d.send_dofs, d.recv_ptr, d.recv_dofs = (
-                a.ctypes.data for a in keep_alive[6:11])
+                a.ctypes.data for a in keep_alive[-5:])
         h = C.c_void_p()
         rc = L.gf_create(C.byref(d), C.byref(h))
         if rc != GF_OK:

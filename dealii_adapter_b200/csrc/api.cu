@@ -5,7 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "gf_context.h"
+#include "reduce.cuh"
 
 namespace
 {
@@ -140,7 +140,6 @@ namespace
     c.io_buf.alloc(c.n_ext_dofs);
     c.dinv.alloc_zero(size_t(c.n_owned_nodes) * c.dim * c.dim, s);
     c.max_red_blocks = c.sm_count * 8;
-    c.partials.alloc_zero(3 * size_t(c.max_red_blocks) + 8, s);
     c.cg_scalars.alloc_zero(1, s);
     c.norm_out.alloc_zero(4, s);
     c.err_flag.alloc_zero(1, s);
@@ -336,6 +335,7 @@ extern "C"
             GF_CUDA_CHECK(cudaStreamSynchronize(c->stream));
             c->n_global_dofs_for_maxit = int64_t(*c->h_norm + 0.5);
           }
+        gf::build_reduction_plan(*c); // chunk size is a function of the GLOBAL size
         // the pointers inside desc are caller-owned: never dereference them after create
         c->desc.cell_dofs = nullptr;
         c->desc.cell_vertices = nullptr;
@@ -343,6 +343,7 @@ extern "C"
         c->desc.iface_cell = c->desc.iface_face_no = c->desc.iface_dofs = nullptr;
         c->desc.nbr_rank = c->desc.send_dofs = c->desc.recv_dofs = nullptr;
         c->desc.send_ptr = c->desc.recv_ptr = nullptr;
+        c->desc.dof_global = nullptr;
         GF_CUDA_CHECK(cudaStreamSynchronize(c->stream));
         *out = c;
         return GF_OK;
@@ -391,6 +392,8 @@ extern "C"
       cudaFreeHost(h->h_norm);
     if (h->h_err)
       cudaFreeHost(h->h_err);
+    if (h->h_lmax)
+      cudaFreeHost(h->h_lmax);
     cudaStream_t s = h->owns_stream ? h->stream : nullptr;
     if (h->comm && h->stream)
       {
@@ -493,7 +496,7 @@ extern "C"
     return guarded(h, [&](gf_context &c) {
       double *b = vec_ptr(c, which_b), *x = vec_ptr(c, which_x);
       GF_REQUIRE(b != x, GF_ERR_INVALID_ARG, "b and x must differ");
-      GF_REQUIRE(c.mg.coarse != nullptr && c.mg_lmax > 0.0, GF_ERR_INVALID_ARG,
+      GF_REQUIRE(c.mg.coarse != nullptr && c.mg_ops_valid, GF_ERR_INVALID_ARG,
                  "multigrid hierarchy not attached / operators not assembled");
       gf::mg_vcycle(c, b, x);
       GF_CUDA_CHECK(cudaStreamSynchronize(c.stream));

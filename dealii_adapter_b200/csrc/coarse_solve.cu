@@ -54,12 +54,15 @@ namespace gf
                          const int32_t *__restrict__ bcol, const double *__restrict__ val,
                          const double *__restrict__ dinv, const double *__restrict__ b,
                          double *__restrict__ x_out, double *d0, double *d1, const int degree,
-                         const double theta, const double delta, const double sigma,
+                         const double *__restrict__ lmax, const double ratio,
                          unsigned long long *counter, const unsigned long long counter_base,
                          const int stage_in_smem)
     {
       extern __shared__ __align__(16) unsigned char cs_smem[];
       const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = CS_THREADS / 32;
+      // Chebyshev interval [lmax/ratio, lmax] from the device-resident eigenvalue estimate
+      const double bb = *lmax, aa = bb / ratio;
+      const double theta = 0.5 * (bb + aa), delta = 0.5 * (bb - aa), sigma = theta / delta;
       const int row_begin = blockIdx.x * rows_per_cta;
       const int row_end   = min(n_rows, row_begin + rows_per_cta);
       const int n_my      = max(0, row_end - row_begin);
@@ -226,8 +229,7 @@ namespace gf
     if (!c.cs_enabled || c.operator_kind != 0)
       return false;
     ProfScope    ps(c, Profile::MG_SPMV);
-    const double bb = c.mg_lmax, aa = bb / ratio;
-    double       theta = 0.5 * (bb + aa), delta = 0.5 * (bb - aa), sigma = theta / delta;
+    const double *lmax = c.mg_lmax_dev.p;
     int          n_rows = int(c.n_owned_nodes), rows_per_cta = c.cs_rows_per_cta,
         stage = c.cs_stage ? 1 : 0;
     const int32_t *brow = c.brow_ptr.p, *bcol = c.bcol.p;
@@ -236,7 +238,7 @@ namespace gf
     double *       d0 = c.mg_d.p, *d1 = c.mg_v.p;
     unsigned long long *counter = c.cs_counter.p, base = c.cs_arrivals;
     void *args[] = {&n_rows, &rows_per_cta, &brow, &vptr, &bcol, &val, &dinv, &b, &x, &d0, &d1,
-                    &degree, &theta, &delta, &sigma, &counter, &base, &stage};
+                    &degree, &lmax, &ratio, &counter, &base, &stage};
     const void *fn = c.dim == 3 ? (const void *)coarse_cheb_kernel<3> : (const void *)coarse_cheb_kernel<2>;
     GF_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(c.cs_grid), dim3(CS_THREADS), args,
                                               c.cs_smem, c.stream));

@@ -26,7 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "gf_context.h"
+#include "reduce.cuh"
 
 namespace gf
 {
@@ -274,6 +274,136 @@ namespace gf
         }
     }
 
+    // Second stage of a partition-independent reduction across ranks (reduce.cuh) in ONE launch:
+    // store my chunk partials into every rank's gather window at their GLOBAL positions, release
+    // the flags, acquire the flags of all ranks, then run the fixed tree over the whole global
+    // chunk list (every rank computes the same bits) and, for the CG, the scalar step.
+    __global__ void __launch_bounds__(TREE_THREADS)
+      p2p_gather_tree_kernel(const ArArgs a, const double *__restrict__ partials, const int stride,
+                             const int n_local, const long long base, const int n_global,
+                             const int n_sums, double *__restrict__ sums, CGScalars *s,
+                             const int phase, const bool check_status,
+                             unsigned long long *epoch_counter, int *err,
+                             const unsigned long long timeout_ns)
+    {
+      // NB: a rank that skipped this launch would deadlock its peers; the CG status is replicated
+      // (every rank computes it from the same sums), so all ranks skip together
+      if (check_status && s->status != 0)
+        return;
+      __shared__ double sm[32];
+      // The epoch counts EXECUTED gathers and lives on the device: a host-side counter would also
+      // count the launches skipped above, two consecutive executed gathers could then share a
+      // parity and a fast rank could overwrite a window its peer is still summing.
+      const unsigned long long epoch = *epoch_counter + 1ull;
+      const int t = threadIdx.x, par = int(epoch & 1ull);
+      for (int idx = t; idx < n_sums * n_local; idx += TREE_THREADS)
+        {
+          const int    k = idx / n_local, j = idx - k * n_local;
+          const double v = partials[size_t(k) * stride + j];
+          for (int r = 0; r < a.n_ranks; ++r)
+            reinterpret_cast<double *>(a.win[r] + P2P_GATHER)[(size_t(par) * 3 + k) * P2P_GATHER_MAX +
+                                                              size_t(base) + j] = v;
+        }
+      __threadfence_system();
+      __syncthreads();
+      if (t < a.n_ranks)
+        {
+          st_release_sys(reinterpret_cast<unsigned long long *>(a.win[t] + P2P_GATHER_FLAG) +
+                           par * P2P_MAX_RANKS + a.rank,
+                         epoch);
+          wait_flag(reinterpret_cast<const unsigned long long *>(a.win[a.rank] + P2P_GATHER_FLAG) +
+                      par * P2P_MAX_RANKS + t,
+                    epoch, err, timeout_ns);
+        }
+      __syncthreads();
+      const double *mine = reinterpret_cast<const double *>(a.win[a.rank] + P2P_GATHER) +
+                           size_t(par) * 3 * P2P_GATHER_MAX;
+      for (int k = 0; k < n_sums; ++k)
+        {
+          const double w = tree_sum_1024(mine + size_t(k) * P2P_GATHER_MAX, n_global, sm);
+          if (t == 0)
+            sums[k] = w;
+        }
+      if (t == 0)
+        {
+          *epoch_counter = epoch;
+          if (phase >= 0)
+            cg_scalar_step(s, sums, phase);
+        }
+    }
+
+    // NCCL transport: the padded all-gather result [rank][k][pad] -> the same fixed tree
+    __global__ void __launch_bounds__(TREE_THREADS)
+      gathered_tree_kernel(const double *__restrict__ gathered, double *__restrict__ scratch,
+                           const int pad, const int n_ranks, const int *__restrict__ rank_off,
+                           const int n_global, const int n_sums, double *__restrict__ sums,
+                           CGScalars *s, const int phase, const bool check_status)
+    {
+      if (check_status && s->status != 0)
+        return;
+      __shared__ double sm[32];
+      for (int k = 0; k < n_sums; ++k)
+        {
+          for (int r = 0; r < n_ranks; ++r)
+            for (int j = threadIdx.x; j < rank_off[r + 1] - rank_off[r]; j += TREE_THREADS)
+              scratch[rank_off[r] + j] = gathered[(size_t(r) * 3 + k) * pad + j];
+          __threadfence_block();
+          __syncthreads();
+          const double w = tree_sum_1024(scratch, n_global, sm);
+          if (threadIdx.x == 0)
+            sums[k] = w;
+          __syncthreads();
+        }
+      if (phase >= 0 && threadIdx.x == 0)
+        cg_scalar_step(s, sums, phase);
+    }
+
+    // sum of a vector over all ranks through the halo mailboxes (count <= P2P_HALO_CAP): push my
+    // vector into every peer's mailbox, then add the mailboxes in rank order (mine in its place)
+    __global__ void __launch_bounds__(PUSH_THREADS)
+      vec_push_kernel(const HaloArgs a, const long long n, const double *__restrict__ v,
+                      unsigned *counters)
+    {
+      const int k   = blockIdx.y;
+      double *  dst = a.mbox[k];
+      for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+           i += (long long)gridDim.x * blockDim.x)
+        dst[i] = v[i];
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0)
+        {
+          const unsigned old = atomicAdd(&counters[k], 1u);
+          if (old == gridDim.x - 1)
+            {
+              counters[k] = 0;
+              __threadfence_system();
+              st_release_sys(a.flag[k], a.epoch[k]);
+            }
+        }
+    }
+    __global__ void __launch_bounds__(PUSH_THREADS)
+      vec_sum_kernel(const HaloArgs a, const int n_peers, const int my_slot, const long long n,
+                     double *__restrict__ v, int *err, const unsigned long long timeout_ns)
+    {
+      if (threadIdx.x < n_peers)
+        wait_flag(a.flag[threadIdx.x], a.epoch[threadIdx.x], err, timeout_ns);
+      __syncthreads();
+      for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+           i += (long long)gridDim.x * blockDim.x)
+        {
+          double s = 0.0;
+          for (int k = 0; k <= n_peers; ++k) // rank order: peers below me, me, peers above me
+            {
+              if (k == my_slot)
+                s += v[i];
+              if (k < n_peers)
+                s += __ldcg(a.mbox[k] + i);
+            }
+          v[i] = s;
+        }
+    }
+
     // operations of one communicator must be ordered: if another handle used it on a different
     // stream, drain that stream first (multigrid levels share the finest level's stream)
     void comm_use_stream(gf_context &c)
@@ -364,6 +494,20 @@ namespace gf
       }
     if (int(c.nbr_rank.size()) > P2P_MAX_RANKS)
       fits = 0;
+    if (c.comm->nccl_comm == nullptr)
+      {
+        // host-bootstrapped communicator (gf_comm_ipc_*): no NCCL fallback transport exists, so
+        // the number of ranks whose lists do NOT fit is agreed through the peer-window all-reduce
+        double         bad = fits ? 0.0 : 1.0;
+        DevBuf<double> d;
+        d.upload(&bad, 1, c.stream);
+        allreduce_sum(c, d.p, 1);
+        d.download(&bad, c.stream);
+        GF_REQUIRE(bad < 0.5, GF_ERR_UNSUPPORTED,
+                   "halo lists exceed the peer mailboxes and the communicator has no NCCL transport");
+        c.halo_p2p = true;
+        return;
+      }
     DevBuf<int> d;
     d.upload(&fits, 1, c.stream);
     comm_use_stream(c);
@@ -371,6 +515,55 @@ namespace gf
                "ncclAllReduce");
     d.download(&fits, c.stream);
     c.halo_p2p = fits != 0;
+  }
+
+  // second stage of a reduction across ranks (reduce.cuh)
+  void comm_reduce_sums(gf_context &c, int n_sums, int cg_phase, bool check_status)
+  {
+    gf_comm cm = c.comm;
+    comm_use_stream(c);
+    ++cm->n_allreduce;
+    if (cm->p2p)
+      {
+        ArArgs a{};
+        for (int r = 0; r < cm->n_ranks; ++r)
+          a.win[r] = cm->win[r];
+        a.rank    = cm->rank;
+        a.n_ranks = cm->n_ranks;
+        p2p_gather_tree_kernel<<<1, TREE_THREADS, 0, c.stream>>>(
+          a, c.partials.p, c.red_stride, c.n_red_chunks, (long long)c.red_chunk_base,
+          int(c.n_red_chunks_global), n_sums, red_sums(c), c.cg_scalars.p, cg_phase, check_status,
+          cm->gather_epoch_dev, cm->d_err, cm->timeout_ns);
+        GF_CUDA_CHECK(cudaGetLastError());
+        return;
+      }
+    // NCCL transport: all-gather of the (padded) partials, then the same tree
+    NcclApi & api = nccl();
+    const int P   = cm->n_ranks;
+    int       pad = 1;
+    for (int r = 0; r < P; ++r)
+      pad = std::max(pad, c.red_rank_chunks[r]);
+    if (!c.red_gather.p)
+      {
+        c.red_gather.alloc_zero(size_t(P + 1) * 3 * pad + size_t(c.n_red_chunks_global) + 8, c.stream);
+        std::vector<int> off(P + 1, 0);
+        for (int r = 0; r < P; ++r)
+          off[r + 1] = off[r] + c.red_rank_chunks[r];
+        c.red_rank_off.upload(off.data(), off.size(), c.stream);
+      }
+    double *send    = c.red_gather.p + size_t(P) * 3 * pad;
+    double *scratch = send + size_t(3) * pad;
+    for (int k = 0; k < n_sums; ++k)
+      GF_CUDA_CHECK(cudaMemcpyAsync(send + size_t(k) * pad, c.partials.p + size_t(k) * c.red_stride,
+                                    size_t(c.n_red_chunks) * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, c.stream));
+    nccl_check(api.AllGather(send, c.red_gather.p, size_t(3) * pad, NCCL_FLOAT64, cm->nccl_comm,
+                             c.stream),
+               "ncclAllGather");
+    gathered_tree_kernel<<<1, TREE_THREADS, 0, c.stream>>>(
+      c.red_gather.p, scratch, pad, P, c.red_rank_off.p, int(c.n_red_chunks_global), n_sums,
+      red_sums(c), c.cg_scalars.p, cg_phase, check_status);
+    GF_CUDA_CHECK(cudaGetLastError());
   }
 
   // exchange ghost values of v with the slab neighbours
@@ -476,6 +669,8 @@ namespace gf
         GF_CUDA_CHECK(cudaGetLastError());
         return;
       }
+    GF_REQUIRE(cm->nccl_comm != nullptr, GF_ERR_UNSUPPORTED,
+               "all-reduce of more than 8 values without an NCCL transport");
     NcclApi &api = nccl();
     nccl_check(api.AllReduce(dev_values, dev_values, size_t(count), NCCL_FLOAT64, NCCL_SUM,
                              cm->nccl_comm, c.stream),
@@ -488,11 +683,48 @@ namespace gf
   {
     if (!c.comm || count <= 0)
       return;
-    ProfScope ps(c, Profile::HALO, 1);
+    ProfScope ps(c, Profile::HALO, 2);
     comm_use_stream(c);
-    ++c.comm->n_allreduce;
+    gf_comm cm = c.comm;
+    ++cm->n_allreduce;
+    if (cm->p2p && size_t(count) <= P2P_HALO_CAP)
+      {
+        // every pair (me, r) exchanges: the pair epochs advance exactly as in a halo exchange
+        // with all ranks as neighbours, so the parity double-buffering argument carries over
+        HaloArgs push{}, wait{};
+        int      np = 0, my_slot = 0;
+        for (int r = 0; r < cm->n_ranks; ++r)
+          {
+            if (r == cm->rank)
+              {
+                my_slot = np;
+                continue;
+              }
+            const unsigned long long e   = ++cm->halo_epoch[r];
+            const size_t             par = size_t(e & 1ull);
+            push.mbox[np] = reinterpret_cast<double *>(cm->win[r] + P2P_MAILBOX) +
+                            (par * P2P_MAX_RANKS + size_t(cm->rank)) * P2P_HALO_CAP;
+            push.flag[np] = reinterpret_cast<unsigned long long *>(cm->win[r] + P2P_HALO_FLAG) +
+                            par * P2P_MAX_RANKS + size_t(cm->rank);
+            wait.mbox[np] = reinterpret_cast<double *>(cm->win[cm->rank] + P2P_MAILBOX) +
+                            (par * P2P_MAX_RANKS + size_t(r)) * P2P_HALO_CAP;
+            wait.flag[np] = reinterpret_cast<unsigned long long *>(cm->win[cm->rank] + P2P_HALO_FLAG) +
+                            par * P2P_MAX_RANKS + size_t(r);
+            push.epoch[np] = wait.epoch[np] = e;
+            ++np;
+          }
+        const int blocks = int(std::min<int64_t>(32, (count + PUSH_THREADS - 1) / PUSH_THREADS));
+        vec_push_kernel<<<dim3(blocks, np), PUSH_THREADS, 0, c.stream>>>(push, count, dev_values,
+                                                                         cm->blk_counter);
+        vec_sum_kernel<<<blocks, PUSH_THREADS, 0, c.stream>>>(wait, np, my_slot, count, dev_values,
+                                                              cm->d_err, cm->timeout_ns);
+        GF_CUDA_CHECK(cudaGetLastError());
+        return;
+      }
+    GF_REQUIRE(cm->nccl_comm != nullptr, GF_ERR_UNSUPPORTED,
+               "vector all-reduce exceeds the peer mailboxes and the communicator has no NCCL");
     nccl_check(nccl().AllReduce(dev_values, dev_values, size_t(count), NCCL_FLOAT64, NCCL_SUM,
-                                c.comm->nccl_comm, c.stream),
+                                cm->nccl_comm, c.stream),
                "ncclAllReduce");
   }
 
@@ -565,6 +797,10 @@ namespace gf
                        cudaSuccess ||
                      cudaMemset(cm->blk_counter, 0, P2P_MAX_RANKS * sizeof(unsigned)) !=
                        cudaSuccess ||
+                     cudaMalloc((void **)&cm->gather_epoch_dev, sizeof(unsigned long long)) !=
+                       cudaSuccess ||
+                     cudaMemset(cm->gather_epoch_dev, 0, sizeof(unsigned long long)) !=
+                       cudaSuccess ||
                      cudaHostAlloc((void **)&cm->h_err, sizeof(int), cudaHostAllocMapped) !=
                        cudaSuccess))
             {
@@ -613,6 +849,8 @@ namespace gf
       cudaFree(cm->win[cm->rank]);
     if (cm->blk_counter)
       cudaFree(cm->blk_counter);
+    if (cm->gather_epoch_dev)
+      cudaFree(cm->gather_epoch_dev);
     if (cm->h_err)
       cudaFreeHost(cm->h_err);
     cm->p2p = false;
@@ -651,6 +889,80 @@ extern "C"
                        "ncclCommInitRank");
         gf::comm_p2p_setup(cm);
         *out = cm;
+        return GF_OK;
+      }
+    catch (gf::Error &e)
+      {
+        fprintf(stderr, "graft_fem: %s\n", e.msg.c_str());
+        return e.code;
+      }
+  }
+  // NCCL-free bootstrap of the peer-window transport: the host moves the 64-byte cudaIpc handles
+  // through whatever channel it has (MPI, torch.distributed/gloo, a file). Also the only way to
+  // run several ranks on ONE device (tests: NCCL refuses two ranks per GPU).
+  int gf_comm_ipc_begin(int rank, int n_ranks, int device, gf_comm *out, uint8_t handle[64])
+  {
+    gf_comm_s *cm = nullptr;
+    try
+      {
+        GF_REQUIRE(out && handle && n_ranks >= 2 && n_ranks <= gf::P2P_MAX_RANKS && rank >= 0 &&
+                     rank < n_ranks,
+                   GF_ERR_INVALID_ARG, "gf_comm_ipc_begin: 2..8 ranks");
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+        GF_CUDA_CHECK(cudaSetDevice(device));
+        cm          = new gf_comm_s;
+        cm->rank    = rank;
+        cm->n_ranks = n_ranks;
+        cm->device  = device;
+        if (const char *t = getenv("GF_P2P_TIMEOUT_S"))
+          cm->timeout_ns = (unsigned long long)(atof(t) * 1e9);
+        unsigned char *mine = nullptr;
+        GF_CUDA_CHECK(cudaMalloc((void **)&mine, gf::P2P_WINDOW_BYTES));
+        cm->win[rank] = mine;
+        GF_CUDA_CHECK(cudaMemset(mine, 0, gf::P2P_WINDOW_BYTES));
+        GF_CUDA_CHECK(cudaDeviceSynchronize());
+        cudaIpcMemHandle_t h;
+        GF_CUDA_CHECK(cudaIpcGetMemHandle(&h, mine));
+        memcpy(handle, &h, 64);
+        *out = cm;
+        return GF_OK;
+      }
+    catch (gf::Error &e)
+      {
+        fprintf(stderr, "graft_fem: %s\n", e.msg.c_str());
+        if (cm)
+          {
+            if (cm->win[rank])
+              cudaFree(cm->win[rank]);
+            delete cm;
+          }
+        return e.code;
+      }
+  }
+  int gf_comm_ipc_finish(gf_comm cm, const uint8_t *all_handles)
+  {
+    try
+      {
+        GF_REQUIRE(cm && all_handles && !cm->p2p, GF_ERR_INVALID_ARG, "gf_comm_ipc_finish");
+        GF_CUDA_CHECK(cudaSetDevice(cm->device));
+        for (int r = 0; r < cm->n_ranks; ++r)
+          if (r != cm->rank)
+            {
+              cudaIpcMemHandle_t h;
+              memcpy(&h, all_handles + size_t(r) * 64, 64);
+              void *ptr = nullptr;
+              GF_CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+              cm->win[r] = static_cast<unsigned char *>(ptr);
+            }
+        GF_CUDA_CHECK(cudaMalloc((void **)&cm->blk_counter, gf::P2P_MAX_RANKS * sizeof(unsigned)));
+        GF_CUDA_CHECK(cudaMemset(cm->blk_counter, 0, gf::P2P_MAX_RANKS * sizeof(unsigned)));
+        GF_CUDA_CHECK(cudaMalloc((void **)&cm->gather_epoch_dev, sizeof(unsigned long long)));
+        GF_CUDA_CHECK(cudaMemset(cm->gather_epoch_dev, 0, sizeof(unsigned long long)));
+        GF_CUDA_CHECK(cudaHostAlloc((void **)&cm->h_err, sizeof(int), cudaHostAllocMapped));
+        *cm->h_err = 0;
+        GF_CUDA_CHECK(cudaHostGetDevicePointer((void **)&cm->d_err, cm->h_err, 0));
+        GF_CUDA_CHECK(cudaDeviceSynchronize());
+        cm->p2p = true;
         return GF_OK;
       }
     catch (gf::Error &e)

@@ -204,8 +204,13 @@ namespace gf
   constexpr size_t P2P_AR_SLOT    = 1024;    // double [2][P2P_MAX_RANKS][P2P_AR_MAX]
   constexpr size_t P2P_MAILBOX    = 4096;    // double [2][P2P_MAX_RANKS][P2P_HALO_CAP]
   constexpr size_t P2P_HALO_CAP   = size_t(1) << 19; // doubles per (parity, sender): 4 MiB
-  constexpr size_t P2P_WINDOW_BYTES =
+  // all-gather of the reduction-chunk partial sums (reduce.cuh): every rank stores its segment of
+  // the GLOBAL chunk list into every window, double [2][3][P2P_GATHER_MAX]
+  constexpr size_t P2P_GATHER_FLAG = 512;    // uint64 [2][P2P_MAX_RANKS]
+  constexpr size_t P2P_GATHER_MAX  = 32768;  // chunks of all ranks together
+  constexpr size_t P2P_GATHER =
     P2P_MAILBOX + 2 * size_t(P2P_MAX_RANKS) * P2P_HALO_CAP * sizeof(double);
+  constexpr size_t P2P_WINDOW_BYTES = P2P_GATHER + 2 * 3 * P2P_GATHER_MAX * sizeof(double);
 } // namespace gf
 
 struct gf_comm_s
@@ -217,6 +222,7 @@ struct gf_comm_s
   unsigned char *win[gf::P2P_MAX_RANKS] = {}; // win[rank] = own allocation, others IPC-mapped
   unsigned long long halo_epoch[gf::P2P_MAX_RANKS] = {}; // per neighbour pair (symmetric counts)
   unsigned long long ar_epoch = 0;
+  unsigned long long *gather_epoch_dev = nullptr; // device: executed gathers (reduce.cuh)
   unsigned *     blk_counter = nullptr; // device [P2P_MAX_RANKS]: last-block detection of the push
   int *          h_err = nullptr;       // mapped pinned: set by a kernel whose flag wait timed out
   int *          d_err = nullptr;       // device alias of h_err
@@ -307,6 +313,24 @@ struct gf_context
   int  operator_kind  = 0;
   bool lin_assembled  = false;
 
+  // partition-independent reductions (pattern.cu, reduce.cu): owned nodes are grouped into node
+  // planes orthogonal to the slab axis (contiguous in the internal numbering) and into chunks of
+  // <= red_chunk_nodes nodes that never cross a plane; every dot product / norm is the fixed tree
+  // over the GLOBAL chunk list, so its bits do not depend on the number of ranks
+  int                  slab_axis = 0;  // gf_desc.slab_axis (0: not given -> one plane per rank)
+  int                  axis_dir  = -1; // reference-cell direction of the slab axis
+  std::vector<int32_t> h_plane_ptr;    // [n_planes+1] owned node ranges
+  gf::DevBuf<int64_t>  node_gkey;      // [n_nodes] partition-independent id of a node
+  gf::DevBuf<int32_t>  red_chunk_ptr;  // [n_red_chunks+1] owned node ranges
+  int                  red_chunk_nodes = 1024;
+  int                  n_red_chunks = 0;        // this rank
+  int                  red_stride = 0;          // distance between the partial sums of two quantities
+  int64_t              red_chunk_base = 0;      // global index of this rank's first chunk
+  int64_t              n_red_chunks_global = 0;
+  std::vector<int>     red_rank_chunks;         // chunks per rank (NCCL transport: padded all-gather)
+  gf::DevBuf<double>   red_gather;              // NCCL transport: gathered partials
+  gf::DevBuf<int>      red_rank_off;            // NCCL transport: chunk offsets of the ranks
+
   // multi-GPU
   gf_comm             comm = nullptr;
   std::vector<int>    nbr_rank;
@@ -327,7 +351,10 @@ struct gf_context
   gf_context *       mg_finer = nullptr; // back link (for safe destruction in any order)
   int                mg_level = 0;   // 0 = finest
   gf::DevBuf<double> mg_b, mg_x, mg_r, mg_d, mg_v, mg_e; // rhs, solution, residual, direction, A d, eigvec
-  double             mg_lmax = 0.0;  // estimate of lambda_max(D^-1 A) of the current operator
+  gf::DevBuf<double> mg_lmax_dev;    // estimate of lambda_max(D^-1 A) of the current operator: lives
+                                     // on the device, never waited for by the host
+  double *           h_lmax = nullptr; // pinned copy (async), validated at the next CG poll
+  bool               mg_ops_valid = false; // operators and smoothers built since the attach
   bool               mg_e_valid = false;
   gf::DevBuf<double> mg_e_saved;     // checkpoint copy of mg_e (gf_state_save / gf_state_restore)
   bool               mg_e_saved_valid = false;

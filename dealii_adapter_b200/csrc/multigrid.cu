@@ -24,8 +24,7 @@
 //              runs redundantly with no communication at all.
 #include <cmath>
 
-#include "gf_context.h"
-#include "kernel_utils.cuh"
+#include "reduce.cuh"
 
 namespace gf
 {
@@ -140,7 +139,11 @@ namespace gf
     }
 
     // b_c = P^T r_f in gather form: one warp per coarse node; lanes sweep the non-zero
-    // (child, fine local node) pairs of each parent cell around the node; fixed order
+    // (child, fine local node) pairs of each parent cell around the node; fixed order.
+    // Partition independence: the contributions of fine nodes BEYOND the coarse node's plane along
+    // the slab axis (bit 30 of rl_ka) are summed separately from the rest and added last. At a
+    // slab cut those are exactly the fine nodes the upper rank owns, so the owner's
+    // "own part + received part" is the same two numbers added in the same order as here.
     template <int DIM>
     __global__ void __launch_bounds__(NT)
       restrict_kernel(const int64_t n_coarse_nodes, const int npc, const int n_child,
@@ -156,10 +159,10 @@ namespace gf
       const int64_t B    = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
       if (B >= n_coarse_nodes)
         return;
-      double acc[DIM];
+      double acc[DIM], acc_hi[DIM];
 #pragma unroll
       for (int cc = 0; cc < DIM; ++cc)
-        acc[cc] = 0.0;
+        acc[cc] = acc_hi[cc] = 0.0;
       for (int64_t s = nc_ptr_c[B]; s < nc_ptr_c[B + 1]; ++s)
         {
           const int32_t src = nc_src_c[s];
@@ -167,7 +170,9 @@ namespace gf
           const int     l0 = rl_ptr[b], l1 = rl_ptr[b + 1];
           for (int l = l0 + lane; l < l1; l += 32)
             {
-              const int32_t ka = rl_ka[l];
+              const int32_t kah = rl_ka[l];
+              const bool    hi  = (kah >> 30) & 1;
+              const int32_t ka  = kah & 0x3fffffff;
               const int32_t fc = child_cells[int64_t(pc) * n_child + ka / npc];
               if (fc < 0)
                 continue;
@@ -176,14 +181,23 @@ namespace gf
                 continue;
               const int64_t nf = cell_nodes_f[fi];
               const double  w  = rl_w[l];
+              if (hi)
+                {
 #pragma unroll
-              for (int cc = 0; cc < DIM; ++cc)
-                acc[cc] = fma(w, r_f[nf * DIM + cc], acc[cc]);
+                  for (int cc = 0; cc < DIM; ++cc)
+                    acc_hi[cc] = fma(w, r_f[nf * DIM + cc], acc_hi[cc]);
+                }
+              else
+                {
+#pragma unroll
+                  for (int cc = 0; cc < DIM; ++cc)
+                    acc[cc] = fma(w, r_f[nf * DIM + cc], acc[cc]);
+                }
             }
         }
 #pragma unroll
       for (int cc = 0; cc < DIM; ++cc)
-        acc[cc] = warp_sum(acc[cc]);
+        acc[cc] = warp_sum(acc[cc]) + warp_sum(acc_hi[cc]);
       if (lane == 0)
 #pragma unroll
         for (int cc = 0; cc < DIM; ++cc)
@@ -192,13 +206,17 @@ namespace gf
 
     // one Chebyshev step on node blocks:
     //   r = r_in - v (v optional) ; d = c_d d + c_r D^-1 r ; x = (x_zero ? 0 : x) + d
+    // c_r = c_r_unit / lmax with lmax read from device memory: the eigenvalue estimate never
+    // travels to the host (no stream synchronisation per level and assembly)
     template <int DIM>
     __global__ void __launch_bounds__(NT)
       cheb_step_kernel(const int64_t n_nodes, const double *__restrict__ r_in,
                        const double *__restrict__ v, const double *__restrict__ dinv,
-                       const double c_d, const double c_r, const bool x_zero,
-                       double *__restrict__ r_out, double *__restrict__ d, double *__restrict__ x)
+                       const double c_d, const double c_r_unit, const double *__restrict__ lmax,
+                       const bool x_zero, double *__restrict__ r_out, double *__restrict__ d,
+                       double *__restrict__ x)
     {
+      const double c_r = c_r_unit / *lmax;
       for (int64_t A = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; A < n_nodes;
            A += int64_t(gridDim.x) * blockDim.x)
         {
@@ -244,15 +262,15 @@ namespace gf
 
     // power iteration pieces: t = D^-1 v with partial sums of t.t ; e = t / sqrt(sum)
     template <int DIM>
-    __global__ void __launch_bounds__(NT)
-      pw_apply_kernel(const int64_t n_nodes, const double *__restrict__ v,
+    __global__ void __launch_bounds__(RED_THREADS)
+      pw_apply_kernel(const int32_t *__restrict__ chunk_ptr, const double *__restrict__ v,
                       const double *__restrict__ dinv, double *__restrict__ t,
                       double *__restrict__ partials)
     {
       __shared__ double sm[32];
       double            acc[1] = {0.0};
-      for (int64_t A = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; A < n_nodes;
-           A += int64_t(gridDim.x) * blockDim.x)
+      const int64_t     n0 = chunk_ptr[blockIdx.x], n1 = chunk_ptr[blockIdx.x + 1];
+      for (int64_t A = n0 + threadIdx.x; A < n1; A += RED_THREADS)
         {
 #pragma unroll
           for (int i = 0; i < DIM; ++i)
@@ -269,16 +287,11 @@ namespace gf
       if (threadIdx.x == 0)
         partials[blockIdx.x] = acc[0];
     }
-    __global__ void sum_partials_kernel(const double *__restrict__ partials, const int n,
-                                        double *out)
+    // lmax = 1.2 * sqrt(||D^-1 A e||^2): the power iteration converges from below, safety factor
+    // as in deal.II's Chebyshev preconditioner
+    __global__ void lmax_store_kernel(const double *__restrict__ sumsq, double *lmax)
     {
-      __shared__ double sm[32];
-      double            acc[1] = {0.0};
-      for (int j = threadIdx.x; j < n; j += blockDim.x)
-        acc[0] += partials[j];
-      block_sum<1>(acc, sm);
-      if (threadIdx.x == 0)
-        out[0] = acc[0];
+      *lmax = 1.2 * sqrt(sumsq[0]);
     }
     __global__ void pw_scale_kernel(const int64_t n, const double *__restrict__ t,
                                     const double *__restrict__ sumsq, double *__restrict__ e)
@@ -288,14 +301,16 @@ namespace gf
            i += int64_t(gridDim.x) * blockDim.x)
         e[i] = t[i] * s;
     }
-    // deterministic start vector (splitmix64 of the dof index), zero on constrained dofs
-    __global__ void pw_init_kernel(const int64_t n, const uint8_t *__restrict__ constrained,
-                                   double *__restrict__ e)
+    // deterministic start vector (splitmix64 of the partition-independent id of the node and the
+    // component), zero on constrained dofs
+    __global__ void pw_init_kernel(const int64_t n, const int dim,
+                                   const int64_t *__restrict__ node_gkey,
+                                   const uint8_t *__restrict__ constrained, double *__restrict__ e)
     {
       for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n;
            i += int64_t(gridDim.x) * blockDim.x)
         {
-          uint64_t z = uint64_t(i) + 0x9E3779B97F4A7C15ull;
+          uint64_t z = uint64_t(node_gkey[i / dim]) * 4ull + uint64_t(i % dim) + 0x9E3779B97F4A7C15ull;
           z          = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
           z          = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
           z          = z ^ (z >> 31);
@@ -334,19 +349,21 @@ namespace gf
     }
 
     template <int DIM>
-    void cheb_step(gf_context &c, const double *r_in, const double *v, double c_d, double c_r,
+    void cheb_step(gf_context &c, const double *r_in, const double *v, double c_d, double c_r_unit,
                    bool x_zero, double *x)
     {
       ProfScope ps(c, Profile::MG_VEC);
       cheb_step_kernel<DIM><<<vec_grid(c, c.n_owned_nodes), NT, 0, c.stream>>>(
-        c.n_owned_nodes, r_in, v, c.dinv.p, c_d, c_r, x_zero, c.mg_r.p, c.mg_d.p, x);
+        c.n_owned_nodes, r_in, v, c.dinv.p, c_d, c_r_unit, c.mg_lmax_dev.p, x_zero, c.mg_r.p,
+        c.mg_d.p, x);
       GF_CUDA_CHECK(cudaGetLastError());
     }
 
-    // Chebyshev iteration for D^-1 A on [lmax/ratio, lmax] (Saad, Iterative Methods, alg. 12.1)
+    // Chebyshev iteration for D^-1 A on [lmax/ratio, lmax] (Saad, Iterative Methods, alg. 12.1);
+    // the coefficients are computed for lmax = 1 and scaled by the device-resident estimate
     void smooth(gf_context &c, const double *b, double *x, bool x_zero, int degree, double ratio)
     {
-      const double bb = c.mg_lmax, aa = bb / ratio;
+      const double bb = 1.0, aa = bb / ratio;
       const double theta = 0.5 * (bb + aa), delta = 0.5 * (bb - aa), sigma = theta / delta;
       double       rho = 1.0 / sigma;
       const double *v  = nullptr;
@@ -450,13 +467,13 @@ namespace gf
     // lambda_max(D^-1 A) by power iteration, warm-started from the previous operator's vector
     void estimate_lmax(gf_context &c)
     {
-      const int     g = vec_grid(c, c.n_owned_nodes);
       const int64_t n = c.n_local;
       int           n_it = 4; // warm start: the operator changed little since the last assembly
       if (!c.mg_e_valid)
         {
           ProfScope ps(c, Profile::MG_VEC);
-          pw_init_kernel<<<vec_grid(c, n), NT, 0, c.stream>>>(n, c.constrained.p, c.mg_e.p);
+          pw_init_kernel<<<vec_grid(c, n), NT, 0, c.stream>>>(n, c.dim, c.node_gkey.p,
+                                                              c.constrained.p, c.mg_e.p);
           c.mg_e_valid = true;
           n_it         = 24;
         }
@@ -464,28 +481,28 @@ namespace gf
         {
           apply_operator(c, c.mg_e.p, c.mg_v.p);
           ProfScope ps(c, Profile::MG_VEC, 3);
-          if (c.dim == 3)
-            pw_apply_kernel<3><<<g, NT, 0, c.stream>>>(c.n_owned_nodes, c.mg_v.p, c.dinv.p,
-                                                       c.mg_r.p, c.partials.p);
-          else
-            pw_apply_kernel<2><<<g, NT, 0, c.stream>>>(c.n_owned_nodes, c.mg_v.p, c.dinv.p,
-                                                       c.mg_r.p, c.partials.p);
-          sum_partials_kernel<<<1, 1024, 0, c.stream>>>(c.partials.p, g, c.norm_out.p + 1);
-          if (c.comm)
-            allreduce_sum(c, c.norm_out.p + 1, 1);
+          if (c.n_red_chunks > 0)
+            {
+              if (c.dim == 3)
+                pw_apply_kernel<3><<<c.n_red_chunks, RED_THREADS, 0, c.stream>>>(
+                  c.red_chunk_ptr.p, c.mg_v.p, c.dinv.p, c.mg_r.p, c.partials.p);
+              else
+                pw_apply_kernel<2><<<c.n_red_chunks, RED_THREADS, 0, c.stream>>>(
+                  c.red_chunk_ptr.p, c.mg_v.p, c.dinv.p, c.mg_r.p, c.partials.p);
+            }
+          reduce_sums(c, 1, -1, false);
           // the first pass only normalises the start vector; afterwards ||e|| = 1 and
           // ||D^-1 A e|| is the eigenvalue estimate
           pw_scale_kernel<<<vec_grid(c, c.n_owned), NT, 0, c.stream>>>(c.n_owned, c.mg_r.p,
-                                                                       c.norm_out.p + 1, c.mg_e.p);
+                                                                       red_sums(c), c.mg_e.p);
           GF_CUDA_CHECK(cudaGetLastError());
         }
-      GF_CUDA_CHECK(cudaMemcpyAsync(c.h_norm + 1, c.norm_out.p + 1, sizeof(double),
+      // the estimate stays on the device (cheb_step_kernel / coarse_cheb_kernel read it there); a
+      // copy goes to the pinned host slot asynchronously and is validated at the next CG poll
+      lmax_store_kernel<<<1, 1, 0, c.stream>>>(red_sums(c), c.mg_lmax_dev.p);
+      GF_CUDA_CHECK(cudaMemcpyAsync(c.h_lmax, c.mg_lmax_dev.p, sizeof(double),
                                     cudaMemcpyDeviceToHost, c.stream));
-      GF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
-      const double lam = std::sqrt(c.h_norm[1]);
-      GF_REQUIRE(lam > 0.0 && std::isfinite(lam), GF_ERR_NOT_CONVERGED,
-                 "multigrid: eigenvalue estimate of the smoother failed");
-      c.mg_lmax = 1.2 * lam; // power iteration converges from below: safety factor as in deal.II
+      c.mg_ops_valid = true;
     }
 
     void assemble_level_tangent(gf_context &c, const double *u_total)
@@ -597,7 +614,13 @@ namespace gf
               const double w = E[(size_t(k) * npc + a) * npc + b];
               if (w != 0.0)
                 {
-                  rl_ka.push_back(k * npc + a);
+                  // beyond the coarse node's plane along the slab axis? (positions in the parent
+                  // cell, in units of 1/(2p))
+                  bool hi = false;
+                  if (f.axis_dir >= 0)
+                    hi = lex[a * 3 + f.axis_dir] + p * ((k >> f.axis_dir) & 1) >
+                         2 * lex[b * 3 + f.axis_dir];
+                  rl_ka.push_back((k * npc + a) | (hi ? (1 << 30) : 0));
                   rl_w.push_back(w);
                 }
             }
@@ -642,6 +665,12 @@ namespace gf
             l->owns_stream = false;
             l->prof_sink   = f.prof_sink;
             l->mg_matrix_precision = f.mg_matrix_precision;
+          }
+        if (!l->mg_lmax_dev.p)
+          {
+            l->mg_lmax_dev.alloc_zero(1, s);
+            GF_CUDA_CHECK(cudaMallocHost((void **)&l->h_lmax, sizeof(double)));
+            *l->h_lmax = 1.0;
           }
         if (!l->mg_r.p)
           {

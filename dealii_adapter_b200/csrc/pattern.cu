@@ -9,6 +9,7 @@
 #include <thrust/sequence.h>
 #include <thrust/sort.h>
 
+#include <algorithm>
 #include <cmath>
 
 #include "gf_context.h"
@@ -29,7 +30,8 @@ namespace gf
     // one warp per owned node; candidates = all nodes of all cells around the node
     template <bool FILL>
     __global__ void pattern_kernel(int64_t n_owned_nodes, int npc, const int64_t *nc_ptr,
-                                   const int32_t *nc_src, const int32_t *cell_nodes, int *row_nb,
+                                   const int32_t *nc_src, const int32_t *cell_nodes,
+                                   const int32_t *node_rank, int *row_nb,
                                    const int32_t *brow_ptr, const int64_t *cand_ptr, int32_t *bcol,
                                    uint16_t *src_off, int32_t *row_src, int *overflow)
     {
@@ -40,7 +42,7 @@ namespace gf
       if (A >= n_owned_nodes)
         return;
       const int max_cand = MAX_CELLS_PER_NODE * npc;
-      int32_t * cand     = smem + warp * 2 * max_cand;
+      int32_t * cand     = smem + warp * 3 * max_cand;
       const int64_t s0   = nc_ptr[A];
       const int     ncell = int(nc_ptr[A + 1] - s0);
       if (ncell > MAX_CELLS_PER_NODE)
@@ -56,6 +58,12 @@ namespace gf
           const int32_t cell = s / npc;
           cand[j]            = cell_nodes[int64_t(cell) * npc + j % npc];
         }
+      __syncwarp();
+      // blocks of a row are ordered by node_rank = the node's position in the partition-independent
+      // (node plane, global id) order, NOT by the local index (ghosts are numbered last locally)
+      int32_t *rk = cand + 2 * max_cand;
+      for (int j = lane; j < ncand; j += 32)
+        rk[j] = node_rank[cand[j]];
       __syncwarp();
       int32_t *is_first = cand + max_cand;
       int      n_first  = 0;
@@ -74,11 +82,11 @@ namespace gf
           __syncwarp();
           for (int j = lane; j < ncand; j += 32)
             {
-              const int32_t v = cand[j];
+              const int32_t v = rk[j];
               int           less = 0, dup = 0, first_less = 0;
               for (int i = 0; i < ncand; ++i)
                 {
-                  const int32_t u = cand[i];
+                  const int32_t u = rk[i];
                   less += (u < v);
                   first_less += (u < v) & is_first[i];
                   dup += (u == v) & (i < j);
@@ -87,7 +95,7 @@ namespace gf
                 {
                   // rank among distinct values = number of distinct values < v
                   const int64_t blk = int64_t(brow_ptr[A]) + first_less;
-                  bcol[blk]         = v;
+                  bcol[blk]         = cand[j];
                   src_off[blk]      = uint16_t(less);
                 }
               const int32_t s                    = nc_src[s0 + j / npc];
@@ -122,25 +130,131 @@ namespace gf
     const int64_t n_ext = d.n_dofs, n_cells = d.n_cells;
     cudaStream_t  s = c.stream;
 
-    // ---- host: nodes = distinct x-component dofs, ascending (keeps owned nodes first) ----------
+    // ---- host: nodes = distinct x-component dofs. Internal order: owned nodes first; inside
+    // each group by (node plane orthogonal to the slab axis, partition-independent id), so that a
+    // node plane is a contiguous range (reduction chunks, x-gather locality of the SpMV) ----------
+    GF_REQUIRE(d.slab_axis >= 0 && d.slab_axis <= dim, GF_ERR_INVALID_ARG,
+               "slab_axis must be 0 (not given) or 1 + a coordinate axis");
+    c.slab_axis = d.slab_axis;
     std::vector<int32_t> node_of_x(n_ext, -1);
+    std::vector<double>  coord_of_x; // coordinate of the node along the slab axis
+    int                  axis_dir = -1;
+    double               h_min    = 0.0;
+    if (c.slab_axis > 0)
+      coord_of_x.assign(n_ext, 0.0);
+    const int              ax  = c.slab_axis - 1;
+    const std::vector<int> &lex = c.tables.local_lex;
     for (int64_t cell = 0; cell < n_cells; ++cell)
-      for (int a = 0; a < npc; ++a)
-        {
-          const int32_t xd = d.cell_dofs[cell * dpc + a * dim];
-          GF_REQUIRE(xd >= 0 && xd < n_ext, GF_ERR_INVALID_ARG, "cell_dofs entry out of range");
-          node_of_x[xd] = 0;
-        }
-    int64_t n_nodes = 0, n_owned_nodes = 0;
+      {
+        double Jax[3] = {0, 0, 0}, v0 = 0;
+        if (c.slab_axis > 0)
+          {
+            const double *v = d.cell_vertices + cell * (int64_t(1) << dim) * dim;
+            v0              = v[ax];
+            int    best  = 0;
+            double scale = 0;
+            for (int j = 0; j < dim; ++j)
+              {
+                Jax[j] = v[(int64_t(1) << j) * dim + ax] - v[ax];
+                if (std::fabs(Jax[j]) > std::fabs(Jax[best]))
+                  best = j;
+                for (int i = 0; i < dim; ++i)
+                  scale = std::max(scale, std::fabs(v[(int64_t(1) << j) * dim + i] - v[i]));
+              }
+            bool ok = Jax[best] > 0 && (axis_dir < 0 || axis_dir == best);
+            for (int j = 0; j < dim; ++j)
+              ok = ok && (j == best || std::fabs(Jax[j]) <= 1e-10 * scale);
+            GF_REQUIRE(ok, GF_ERR_UNSUPPORTED,
+                       "slab_axis needs cells of one common orientation with edges along the axis");
+            axis_dir = best;
+            h_min    = (cell == 0) ? Jax[best] : std::min(h_min, Jax[best]);
+          }
+        for (int a = 0; a < npc; ++a)
+          {
+            const int32_t xd = d.cell_dofs[cell * dpc + a * dim];
+            GF_REQUIRE(xd >= 0 && xd < n_ext, GF_ERR_INVALID_ARG, "cell_dofs entry out of range");
+            if (node_of_x[xd] < 0 && c.slab_axis > 0)
+              coord_of_x[xd] = v0 + Jax[axis_dir] * (double(lex[a * 3 + axis_dir]) / c.p);
+            node_of_x[xd] = 0;
+          }
+      }
+    c.axis_dir = axis_dir;
+    std::vector<int32_t> xdofs; // distinct x-dofs, ascending caller id
     for (int64_t i = 0; i < n_ext; ++i)
       if (node_of_x[i] == 0)
-        {
-          node_of_x[i] = int32_t(n_nodes++);
-          if (i < c.n_ext_owned)
-            n_owned_nodes = n_nodes;
-        }
+        xdofs.push_back(int32_t(i));
+    const int64_t n_nodes = int64_t(xdofs.size());
     GF_REQUIRE(n_nodes * dim == n_ext, GF_ERR_INVALID_ARG,
                "n_dofs is not dim * (number of distinct nodes in cell_dofs)");
+    // node planes: runs of (nearly) equal coordinates
+    std::vector<int32_t> plane_of(n_nodes, 0);
+    if (c.slab_axis > 0)
+      {
+        std::vector<int32_t> by_coord(n_nodes);
+        for (int64_t k = 0; k < n_nodes; ++k)
+          by_coord[k] = int32_t(k);
+        std::sort(by_coord.begin(), by_coord.end(), [&](int32_t a, int32_t b) {
+          return coord_of_x[xdofs[a]] < coord_of_x[xdofs[b]];
+        });
+        const double tol = 1e-6 * h_min / c.p;
+        int32_t      pl  = 0;
+        for (int64_t k = 0; k < n_nodes; ++k)
+          {
+            if (k > 0 && coord_of_x[xdofs[by_coord[k]]] - coord_of_x[xdofs[by_coord[k - 1]]] > tol)
+              ++pl;
+            plane_of[by_coord[k]] = pl;
+          }
+      }
+    // order of all local nodes by (plane, global id): the partition-independent order
+    struct NodeKey
+    {
+      int32_t plane;
+      int64_t gkey;
+      int32_t k; // index into xdofs
+    };
+    std::vector<NodeKey> keys(n_nodes);
+    for (int64_t k = 0; k < n_nodes; ++k)
+      keys[k] = {plane_of[k], d.dof_global ? d.dof_global[xdofs[k]] : int64_t(xdofs[k]), int32_t(k)};
+    std::sort(keys.begin(), keys.end(), [](const NodeKey &a, const NodeKey &b) {
+      return a.plane != b.plane ? a.plane < b.plane : a.gkey < b.gkey;
+    });
+    for (int64_t k = 1; k < n_nodes; ++k)
+      GF_REQUIRE(keys[k].plane != keys[k - 1].plane || keys[k].gkey != keys[k - 1].gkey,
+                 GF_ERR_INVALID_ARG, "dof_global is not unique");
+    // internal node index: owned nodes in that order, then the ghosts in that order
+    int64_t              n_owned_nodes = 0;
+    std::vector<int32_t> h_node_rank(n_nodes);
+    std::vector<int64_t> h_node_gkey(n_nodes);
+    c.h_plane_ptr.clear();
+    for (int pass = 0; pass < 2; ++pass)
+      {
+        int64_t next = pass == 0 ? 0 : n_owned_nodes;
+        int32_t last_plane = -1;
+        for (int64_t r = 0; r < n_nodes; ++r)
+          {
+            const int32_t xd    = xdofs[keys[r].k];
+            const bool    owned = xd < c.n_ext_owned;
+            if (owned != (pass == 0))
+              continue;
+            if (pass == 0 && keys[r].plane != last_plane)
+              {
+                c.h_plane_ptr.push_back(int32_t(next));
+                last_plane = keys[r].plane;
+              }
+            node_of_x[xd]     = int32_t(next);
+            h_node_rank[next] = int32_t(r);
+            h_node_gkey[next] = keys[r].gkey;
+            ++next;
+          }
+        if (pass == 0)
+          {
+            n_owned_nodes = next;
+            c.h_plane_ptr.push_back(int32_t(next));
+          }
+      }
+    DevBuf<int32_t> node_rank;
+    node_rank.upload(h_node_rank.data(), h_node_rank.size(), s);
+    c.node_gkey.upload(h_node_gkey.data(), h_node_gkey.size(), s);
     c.n_nodes       = n_nodes;
     c.n_owned_nodes = n_owned_nodes;
     c.n_local       = n_nodes * dim;
@@ -169,8 +283,8 @@ namespace gf
     for (int64_t i = 0; i < n_ext; ++i)
       GF_REQUIRE(c.h_perm_e2i[i] >= 0 && c.h_perm_i2e[i] >= 0, GF_ERR_INVALID_ARG,
                  "dof not referenced by any cell");
-    for (int64_t i = 0; i < c.n_owned; ++i)
-      GF_REQUIRE(c.h_perm_i2e[i] < c.n_ext_owned, GF_ERR_INVALID_ARG,
+    for (int64_t i = 0; i < n_ext; ++i)
+      GF_REQUIRE((c.h_perm_i2e[i] < c.n_ext_owned) == (i < c.n_owned), GF_ERR_INVALID_ARG,
                  "owned node has a non-owned component dof");
     c.perm_e2i.upload(c.h_perm_e2i.data(), n_ext, s);
     c.perm_i2e.upload(c.h_perm_i2e.data(), n_ext, s);
@@ -275,11 +389,12 @@ namespace gf
     row_nb.alloc_zero(n_rows + 1, s);
     overflow.alloc_zero(1, s);
     const int    wpb  = 4;
-    const size_t smem = size_t(wpb) * 2 * MAX_CELLS_PER_NODE * npc * sizeof(int32_t);
+    const size_t smem = size_t(wpb) * 3 * MAX_CELLS_PER_NODE * npc * sizeof(int32_t);
     const unsigned grid = unsigned((n_rows + wpb - 1) / wpb);
     pattern_kernel<false><<<grid, wpb * 32, smem, s>>>(n_rows, npc, c.nc_ptr.p, c.nc_src.p,
-                                                       c.cell_nodes.p, row_nb.p, nullptr, nullptr,
-                                                       nullptr, nullptr, nullptr, overflow.p);
+                                                       c.cell_nodes.p, node_rank.p, row_nb.p, nullptr,
+                                                       nullptr, nullptr, nullptr, nullptr,
+                                                       overflow.p);
     GF_CUDA_CHECK(cudaGetLastError());
     int h_overflow = 0;
     GF_CUDA_CHECK(
@@ -320,9 +435,9 @@ namespace gf
     c.src_off.alloc(c.n_blocks);
     c.row_src.alloc(c.n_cand);
     pattern_kernel<true><<<grid, wpb * 32, smem, s>>>(n_rows, npc, c.nc_ptr.p, c.nc_src.p,
-                                                      c.cell_nodes.p, nullptr, c.brow_ptr.p,
-                                                      c.cand_ptr.p, c.bcol.p, c.src_off.p,
-                                                      c.row_src.p, overflow.p);
+                                                      c.cell_nodes.p, node_rank.p, nullptr,
+                                                      c.brow_ptr.p, c.cand_ptr.p, c.bcol.p,
+                                                      c.src_off.p, c.row_src.p, overflow.p);
     GF_CUDA_CHECK(cudaGetLastError());
     GF_CUDA_CHECK(cudaStreamSynchronize(s));
 

@@ -2,8 +2,7 @@
 // scheme linear_elasticity.cc:390-420,584-585), masked l2 norms (nonlinear:549-576), and the
 // interface gather/scatter bodies of the Adapter (adapter.h:401-416, 427-442). All HBM-bound
 // streaming kernels; norms use the fixed-order two-stage reduction of cg.cu.
-#include "gf_context.h"
-#include "kernel_utils.cuh"
+#include "reduce.cuh"
 
 namespace gf
 {
@@ -59,31 +58,25 @@ namespace gf
         if (con[i])
           v[i] = 0.0;
     }
-    __global__ void __launch_bounds__(NT)
-      norm_partials_kernel(int64_t n, const double *__restrict__ v, const uint8_t *__restrict__ con,
-                           bool mask, double *__restrict__ partials)
+    // one CTA per reduction chunk (reduce.cuh): partition-independent partial sums
+    template <int DIM>
+    __global__ void __launch_bounds__(RED_THREADS)
+      norm_chunks_kernel(const int32_t *__restrict__ chunk_ptr, const double *__restrict__ v,
+                         const uint8_t *__restrict__ con, bool mask, double *__restrict__ partials)
     {
       __shared__ double sm[32];
       double            acc[1] = {0.0};
-      for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n;
-           i += int64_t(gridDim.x) * blockDim.x)
-        {
-          const double x = (mask && con[i]) ? 0.0 : v[i];
-          acc[0]         = fma(x, x, acc[0]);
-        }
+      const int64_t     n0 = chunk_ptr[blockIdx.x], n1 = chunk_ptr[blockIdx.x + 1];
+      for (int64_t A = n0 + threadIdx.x; A < n1; A += RED_THREADS)
+#pragma unroll
+        for (int i = 0; i < DIM; ++i)
+          {
+            const double x = (mask && con[A * DIM + i]) ? 0.0 : v[A * DIM + i];
+            acc[0]         = fma(x, x, acc[0]);
+          }
       block_sum<1>(acc, sm);
       if (threadIdx.x == 0)
         partials[blockIdx.x] = acc[0];
-    }
-    __global__ void norm_final_kernel(const double *__restrict__ partials, int n, double *out)
-    {
-      __shared__ double sm[32];
-      double            acc[1] = {0.0};
-      for (int j = threadIdx.x; j < n; j += blockDim.x)
-        acc[0] += partials[j];
-      block_sum<1>(acc, sm);
-      if (threadIdx.x == 0)
-        out[0] = acc[0];
     }
     __global__ void iface_scatter_kernel(int64_t n_nodes, int dim, const int32_t *__restrict__ dofs,
                                          const double *__restrict__ buf, double *__restrict__ v)
@@ -157,18 +150,22 @@ namespace gf
   }
   double vec_masked_norm(gf_context &c, const double *v, bool mask_constrained)
   {
-    const int g = grid_for(c, c.n_owned);
     {
       ProfScope ps(c, Profile::UPDATE, 2);
-      norm_partials_kernel<<<g, NT, 0, c.stream>>>(c.n_owned, v, c.constrained.p, mask_constrained,
-                                                   c.partials.p);
-      norm_final_kernel<<<1, 1024, 0, c.stream>>>(c.partials.p, g, c.norm_out.p);
+      if (c.n_red_chunks > 0)
+        {
+          if (c.dim == 3)
+            norm_chunks_kernel<3><<<c.n_red_chunks, RED_THREADS, 0, c.stream>>>(
+              c.red_chunk_ptr.p, v, c.constrained.p, mask_constrained, c.partials.p);
+          else
+            norm_chunks_kernel<2><<<c.n_red_chunks, RED_THREADS, 0, c.stream>>>(
+              c.red_chunk_ptr.p, v, c.constrained.p, mask_constrained, c.partials.p);
+        }
+      GF_CUDA_CHECK(cudaGetLastError());
+      reduce_sums(c, 1, -1, false);
     }
-    GF_CUDA_CHECK(cudaGetLastError());
-    if (c.comm)
-      allreduce_sum(c, c.norm_out.p, 1);
     GF_CUDA_CHECK(
-      cudaMemcpyAsync(c.h_norm, c.norm_out.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+      cudaMemcpyAsync(c.h_norm, red_sums(c), sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     GF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
     comm_check(c);
     return std::sqrt(c.h_norm[0]);

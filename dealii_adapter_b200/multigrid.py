@@ -72,8 +72,10 @@ class Hierarchy:
                                                      replicate_below_dofs)
         self.partitions = [p.mesh.partition(axis, world, rank) if (world > 1 and not rep) else None
                            for p, rep in zip(self.problems, self.replicated)]
+        # slab_axis on every level and for every world size (1 included): all sums then run over
+        # the same partition-independent tree, so the run is bitwise the same for any `world`
         self.handles = [capi.Handle(p, device=device, partition=part,
-                                    comm=comm if part is not None else None)
+                                    comm=comm if part is not None else None, slab_axis=axis)
                         for p, part in zip(self.problems, self.partitions)]
         for l in range(len(self.handles) - 1):
             fine, coarse = self.problems[l], self.problems[l + 1]

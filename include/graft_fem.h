@@ -76,6 +76,23 @@ extern "C"
     const int32_t *send_dofs; /* owned dofs whose values neighbour k needs */
     const int64_t *recv_ptr;  /* [n_neighbors+1] */
     const int32_t *recv_dofs; /* ghost dofs filled from neighbour k (same order as its send list) */
+    /* --- partition-independent arithmetic (optional; zero-initialise to leave unset) ---
+     * Every floating-point sum that crosses ranks is taken over a tree that does not depend on the
+     * number of ranks when both fields are given, so Newton AND CG histories of a partitioned run
+     * are bitwise those of the single-GPU run (the reference is serial, adapter.h:152-154):
+     *   dof_global[n_dofs]  a partition-independent id per dof (deal.II: the global_dof_index of
+     *                       the distributed DoFHandler). NULL: the caller's ids are global already.
+     *                       Only ORDERS things: blocks inside a matrix row, nodes inside a node
+     *                       plane, the start vector of the smoothers' eigenvalue estimate.
+     *   slab_axis           1 + the coordinate axis the mesh is cut along (0: not given). Owned
+     *                       nodes are grouped into node planes orthogonal to it (a rank owns whole
+     *                       planes, ranks are ordered along the axis) and into fixed chunks inside
+     *                       a plane; dot products / norms sum chunk by chunk in global order, the
+     *                       multigrid restriction splits its sums at the coarse node's plane.
+     *                       Cells must share one orientation (subdivided_hyper_rectangle +
+     *                       refine_global: nonlinear_elasticity.cc:237-246). */
+    const int64_t *dof_global;
+    int32_t        slab_axis;
   } gf_desc;
 
   /* DoF vectors addressable through gf_get_vector / gf_set_vector.
@@ -195,6 +212,13 @@ extern "C"
   int  gf_comm_unique_id(uint8_t id[128]);
   int  gf_comm_create(const uint8_t id[128], int rank, int n_ranks, int device, gf_comm *out);
   void gf_comm_destroy(gf_comm c);
+  /* The same communicator without NCCL: the library's peer-window transport only needs every
+   * rank's 64-byte cudaIpc window handle. begin allocates this rank's window and returns its
+   * handle; the host all-gathers the handles over any channel it has (MPI, torch.distributed/
+   * gloo); finish maps the peers. There is no fallback transport on such a communicator. Several
+   * ranks may share one device (the multi-rank parity tests do: NCCL refuses that). */
+  int gf_comm_ipc_begin(int rank, int n_ranks, int device, gf_comm *out, uint8_t handle[64]);
+  int gf_comm_ipc_finish(gf_comm c, const uint8_t *all_handles /* [n_ranks*64] */);
   /* which transport carries the halo exchange and the scalar all-reduce: peer windows = every
    * rank's mailbox/flag window is mapped into all peers with cudaIpc and the library's own kernels
    * store ghost values / partial sums straight into the neighbour's HBM over NVLink (default);

@@ -1,0 +1,141 @@
+"""Worker of tests/test_gpu_multirank.py (one process per rank, started by torch.distributed.run).
+
+Runs coupled windows of both solver classes on a slab-partitioned mesh and writes what rank 0
+gathered (Newton table incl. CG iteration counts and residuals, interface displacement of every
+written step, transport counters) to --out. Two bootstraps:
+  --mode ipc   torch.distributed "gloo" + gf_comm_ipc_begin/_finish: the library's peer-window
+               transport with the 64-byte window handles moved by the host. Ranks share GPUs when
+               there are fewer devices than ranks (device = local_rank % device_count) - that is
+               how the suite covers P = 2, 4 on the one-GPU test box.
+  --mode nccl  one GPU per rank, NCCL communicator (gf_comm_create), as bench.py does.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CASES = {
+    # name: (model, preconditioner, reps, replicate_below_dofs)
+    "nl_jacobi": ("neo-Hookean", "jacobi", [3, 16, 2], None),
+    "lin_jacobi": ("linear", "jacobi", [3, 16, 2], None),
+    "nl_mg": ("neo-Hookean", "mg", [4, 32, 4], 80000),          # small levels replicated (default)
+    "lin_mg": ("linear", "mg", [4, 32, 4], 80000),
+    "nl_mg_partitioned_coarse": ("neo-Hookean", "mg", [4, 32, 4], 0),   # halos on every level
+}
+N_STEPS = 3
+LOAD = (1500.0, 0.0, 100.0)
+
+
+def make_case(name):
+    from dealii_adapter_b200.problem import SolverParameters, make_problem
+    model, precond, reps, rep_below = CASES[name]
+    p = SolverParameters(model=model, type_lin="CG", poly_degree=2, scenario="PF", delta_t=0.01,
+                         mu=0.5e6, nu=0.4, rho=1000.0, tol_lin=1e-8, max_iterations_lin=2.0)
+    return make_problem(p, 3, reps=reps, numbering="lexicographic"), model, precond, rep_below
+
+
+def run_case(name, world, rank, device, comm):
+    """Returns (history, written) of this rank; history rows = the Newton table (nonlinear) or the
+    (iterations, residual) pairs of the linear model."""
+    from dealii_adapter_b200 import capi, multigrid, solvers
+    prob, model, precond, rep_below = make_case(name)
+    H = None
+    if precond == "mg":
+        H = multigrid.Hierarchy(prob, device=device, world=world, rank=rank, comm=comm, axis=1,
+                                replicate_below_dofs=rep_below)
+        h = H.fine
+    else:
+        part = prob.mesh.partition(1, world, rank) if world > 1 else None
+        h = capi.Handle(prob, device=device, partition=part, comm=comm, slab_axis=1)
+    n_if = h.n_iface_nodes
+    buf = np.tile(LOAD, n_if)
+    fp = solvers.FakeParticipant(3, N_STEPS, prob.params.delta_t, lambda t, it: buf)
+    cls = solvers.Solid if model == "neo-Hookean" else solvers.ElastoDynamics
+    s = cls(prob, fp, handle=h)
+    s.adapter.n_interface_nodes = n_if
+    s.adapter.interface_nodes_ids = np.arange(n_if, dtype=np.int32)
+    if model == "linear":
+        h.lin_assemble_once()
+    for k in range(N_STEPS):
+        s.step()
+    vis = getattr(h, "iface_visible", None)
+    written = []
+    for (w, it, data) in fp.written:
+        full = np.full(prob.n_iface_nodes * 3, np.nan)
+        if vis is None:
+            full[:] = data
+        else:
+            full[np.repeat(vis, 3)] = data
+        written.append(full)
+    hist = [np.array(rows, dtype=np.float64) for rows in s.history] if model == "neo-Hookean" \
+        else [np.array(s.history, dtype=np.float64)]
+    levels = (H.n_levels, list(H.replicated)) if H else (1, [False])
+    (H or h).close()
+    return hist, np.array(written), levels
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--mode", default="ipc", choices=["ipc", "nccl"])
+    ap.add_argument("--cases", default=",".join(CASES))
+    args = ap.parse_args()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    lr = int(os.environ["LOCAL_RANK"])
+    import torch
+    import torch.distributed as dist
+    from dealii_adapter_b200 import capi
+    n_dev = torch.cuda.device_count()
+    if args.mode == "nccl":
+        device = lr
+        torch.cuda.set_device(device)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(capi.Comm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        comm = capi.Comm(bytes(idt.cpu().numpy().tobytes()), rank, world, device)
+    else:
+        device = lr % n_dev
+        dist.init_process_group("gloo")
+
+        def all_gather(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        comm = capi.Comm.from_ipc(rank, world, device, all_gather)
+    result = {"world": world, "mode": args.mode, "shared_device": n_dev < world}
+    for name in args.cases.split(","):
+        hist, written, levels = run_case(name, world, rank, device, comm)
+        allw = [None] * world
+        dist.all_gather_object(allw, written)
+        allh = [None] * world
+        dist.all_gather_object(allh, hist)
+        if rank == 0:
+            # every interface node is visible on at least one rank; ranks that see the same node
+            # must agree bit for bit (ghost values are copies of the owner's)
+            merged = np.full_like(allw[0], np.nan)
+            for w in allw:
+                m = ~np.isnan(w)
+                both = m & ~np.isnan(merged)
+                assert np.array_equal(w[both], merged[both]), "ranks disagree on a shared node"
+                merged[m] = w[m]
+            assert not np.isnan(merged).any()
+            for h in allh[1:]:     # the scalars of the Newton table are replicated
+                assert all(np.array_equal(a, b) for a, b in zip(h, allh[0])), "histories differ"
+            result[name] = {"written": merged, "history": allh[0], "levels": levels}
+    if rank == 0:
+        result["transport"] = comm.transport()
+        import pickle
+        with open(args.out, "wb") as f:
+            pickle.dump(result, f)
+    comm.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
