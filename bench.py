@@ -44,9 +44,16 @@ CELLS_PER_GPU = (24, 144, 24)
 # class). CG iteration counts per Newton solve on these meshes (measured on one GPU, profiles/
 # r01_bench_n1_weak_mesh_*.json): 16.5, 13.5, 11.5, 10.8 - the meshes get more isotropic.
 WEAK_REPS = {1: (24, 144, 24), 2: (24, 144, 48), 4: (24, 288, 48), 8: (24, 288, 96)}
-CPU_SAMPLE_LAYERS = 2          # oracle sample: 24 x 2 x 24 cells of the same size (33,075 DoFs)
+# CPU arm: the oracle on the SAME flap (0.1 x 1 x 0.3, same load, same solver options) at a coarser
+# resolution, so that the slenderness - which sets the SSOR-CG iteration counts - is the workload's
+# (a short slab of the fine mesh, as in round 1, is far better conditioned and flatters the CPU).
+# Sizes bounded for the run time: ~4 s (reference arm, K steps) / ~25 s (cpu_baseline, 1 step) per
+# coupled step. The full-size cfg3 CPU timestep (hours) is a one-off: tools/cpu_cfg3_timestep.py ->
+# profiles/r02_cpu_cfg3_full_timestep.jsonl, quoted in the line when present.
+CPU_SAMPLE_REPS = {"reference": (4, 24, 4), "baseline": (6, 36, 6)}
 TRACTION = (2000.0, 0.0, 0.0)
 N_SUB = 2
+CFG4_REPS = (128, 1024, 128)   # BASELINE configs[3]: linear Q1 cantilever, 51,171,075 DoFs
 
 
 def params():
@@ -126,14 +133,35 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_run(n_steps, n_warmup):
+def full_size_cpu_anchor():
+    """The one-off full-size cfg3 CPU timestep, if its log is in profiles/ (same config as `value`)."""
+    path = os.path.join(ROOT, "profiles", "r02_cpu_cfg3_full_timestep.jsonl")
+    if not os.path.exists(path):
+        return None
+    rows = [json.loads(x) for x in open(path) if x.strip()]
+    solves = [r for r in rows if r.get("event") == "newton_solve"]
+    if not solves:
+        return None
+    done = [r for r in rows if r.get("event") == "done"]
+    last = solves[-1]
+    return {"what": "oracle on the FULL cfg3 mesh (24x144x24 Q2 cells, 2,081,667 DoFs), offline, "
+                    "tools/cpu_cfg3_timestep.py; %s" % ("complete timestep" if done else
+                                                        "first %d Newton solve(s)" % len(solves)),
+            "newton_solves": len(solves), "cg_iterations": [r["cg_iterations"] for r in solves],
+            "seconds": done[0]["seconds"] if done else last["elapsed_s"],
+            "dofs_per_s": done[0]["newton_step_dofs_per_s"] if done else last["dofs_per_s_so_far"],
+            "threads": rows[0].get("threads"), "cpu": rows[0].get("cpu")}
+
+
+def cpu_run(n_steps, n_warmup, which="reference"):
     """Oracle (CPU restatement of the reference's path: WorkStream-like threaded assembly, serial
     SSOR-CG as in deal.II) on the bounded sample; returns DoFs/s and details."""
     from oracle import oracle_py as orc
-    prob = make_flap(CPU_SAMPLE_LAYERS, numbering="cellwise")
+    reps = CPU_SAMPLE_REPS[which]
+    prob = make_flap_reps(reps, numbering="cellwise")
     o = orc.Oracle(prob)
     buf = np.tile(TRACTION, prob.n_iface_nodes)
-    solves, t_total = 0, 0.0
+    solves, t_total, cg = 0, 0.0, []
     for s in range(n_warmup + n_steps):
         o.format_precice_to_deal(buf, orc.NL_EXTERNAL_STRESS)
         if s % N_SUB == 0:
@@ -147,13 +175,110 @@ def cpu_run(n_steps, n_warmup):
         if s >= n_warmup:
             solves += n
             t_total += dt
-    return {"value": prob.n_dofs * solves / t_total, "unit": "DoFs/s", "cores": o.n_threads,
-            "kind": "port",
-            "sample": "oracle (C++ restatement; reference cannot be built: deal.II/preCICE absent) "
-                      "on a 24x%dx24-cell slab of the same flap (%d DoFs), %d step(s), %d Newton "
-                      "solves, SSOR-CG serial + assembly on %d threads" %
-                      (CPU_SAMPLE_LAYERS, prob.n_dofs, n_steps, solves, o.n_threads),
-            "seconds": t_total, "n_dofs": prob.n_dofs, "newton_solves": solves}
+            cg += [int(r[0]) for r in hist]
+    out = {"value": prob.n_dofs * solves / t_total, "unit": "DoFs/s", "cores": o.n_threads,
+           "kind": "port",
+           "sample": "oracle (C++ restatement; the reference cannot be built here: deal.II/preCICE "
+                     "absent) on the SAME flap 0.1x1x0.3 with the same load and solver options at "
+                     "%dx%dx%d Q2 cells (%d DoFs): %d step(s), %d Newton solves, SSOR-CG iterations "
+                     "per solve %d..%d (mean %.0f), CG serial as in deal.II + assembly on %d threads"
+                     % (reps[0], reps[1], reps[2], prob.n_dofs, n_steps, solves, min(cg), max(cg),
+                        float(np.mean(cg)), o.n_threads),
+           "seconds": t_total, "n_dofs": prob.n_dofs, "newton_solves": solves,
+           "cg_iterations_per_solve_mean": float(np.mean(cg))}
+    anchor = full_size_cpu_anchor()
+    if anchor:
+        out["full_size_anchor"] = anchor
+    return out
+
+
+def run_cfg4(args, world, rank, local_rank, comm, dist, torch):
+    """BASELINE configs[3] / north_star's multi-GPU target: linear_elasticity 3D cantilever, Q1,
+    128x1024x128 cells = 51,171,075 DoFs, one-step-theta, STRONG scaling over the ranks (the whole
+    problem on one B200 at N = 1: K + A + M resident). One step = assemble_rhs + CG (absolute
+    tolerance 1e-10, linear_elasticity.cc:542) + update_displacement. Returns the dict emitted as
+    `strong_scaling`."""
+    from dealii_adapter_b200 import capi, multigrid, solvers
+    from dealii_adapter_b200.problem import SolverParameters, make_problem
+    reps = list(CFG4_REPS)
+    p = SolverParameters(model="linear", type_lin="CG", poly_degree=1, scenario="PF", delta_t=0.005,
+                         mu=0.5e6, nu=0.4, rho=1000.0, theta=0.5, max_iterations_lin=1.0, end_time=1e9)
+    t0 = time.perf_counter()
+    prob = make_problem(p, 3, reps=reps, numbering="lexicographic")
+    H = multigrid.Hierarchy(prob, device=local_rank, world=world, rank=rank, comm=comm, axis=1)
+    h = H.fine
+    if args.spmv_kernel:
+        h.set_option(capi.OPT_SPMV_KERNEL, args.spmv_kernel)
+    if args.mg_precision:
+        h.set_option(capi.OPT_MG_MATRIX_PRECISION, args.mg_precision)
+    t_setup = time.perf_counter() - t0
+    buf = np.tile([200.0, 0.0, 0.0], h.n_iface_nodes)
+    fp = solvers.FakeParticipant(3, 10 ** 9, p.delta_t, lambda t, it: buf)
+    ed = solvers.ElastoDynamics(prob, fp, handle=h)
+    ed.adapter.n_interface_nodes = h.n_iface_nodes
+    ed.adapter.interface_nodes_ids = np.arange(h.n_iface_nodes, dtype=np.int32)
+    h.synchronize()
+    t1 = time.perf_counter()
+    h.lin_assemble_once()
+    h.synchronize()
+    t_asm = time.perf_counter() - t1
+
+    def barrier():
+        h.synchronize()
+        if world > 1:
+            dist.barrier()
+        h.synchronize()
+
+    steps = max(1, min(args.steps, 10))
+    for k in range(max(2, min(args.warmup, 3))):
+        ed.step()
+    h.set_option(capi.OPT_PROFILE, 2)
+    h.profile(reset=True)
+    n0 = len(ed.history)
+    barrier()
+    h.event_record(0)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        ed.step()
+    h.event_record(1)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = h.event_elapsed_ms(0, 1)
+    prof = h.profile(reset=True)
+    h.set_option(capi.OPT_PROFILE, 0)
+    t = max(wall, 1e-3 * dev_ms)
+    if world > 1:
+        tt = torch.tensor([t], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt[0])
+    out = None
+    if rank == 0:
+        peak, src = measured_peak()
+        ms_spmv, nbytes = h.spmv_timed(capi.MAT_SYSTEM, 5)
+        avg_ms = prof["spmv_ms"] / max(1, prof["spmv_launches"])
+        its = [int(r[0]) for r in ed.history[n0:]]
+        out = {"what": "BASELINE configs[3]: linear_elasticity 3D cantilever Q1 %s cells, %d DoFs, "
+                       "one-step-theta, CG abs tol 1e-10 + geometric multigrid; the SAME problem on "
+                       "every N (strong scaling), slab-partitioned along y" %
+                       ("x".join(map(str, reps)), prob.n_dofs),
+               "metric": "timestep_dofs_per_s", "value": prob.n_dofs * steps / t, "unit": "DoFs/s",
+               "scaling": "strong", "n_gpus": world, "steps": steps, "ms_per_step": 1e3 * t / steps,
+               "n_dofs": prob.n_dofs, "nnz_scalar_per_gpu": h.nnz(), "cg_iterations": its,
+               "ms_per_cg_iteration": 1e3 * t / max(1, sum(its)),
+               "multigrid_levels": [q.mesh.reps for q in H.problems],
+               "multigrid_levels_replicated": H.replicated,
+               "setup_s": t_setup, "assemble_once_s": t_asm,
+               "roofline": {"bound": "hbm", "kernel": "finest-level SpMV (system matrix A = M + "
+                                                      "theta^2 dt^2 K, Q1 rows of 81 values)",
+                            "achieved": nbytes / (avg_ms * 1e-3) / 1e9 if avg_ms else None,
+                            "peak": peak, "unit": "GB/s", "peak_source": src,
+                            "frac": (nbytes / (avg_ms * 1e-3) / 1e9 / peak) if avg_ms else None,
+                            "bytes_per_launch": nbytes, "avg_launch_ms": avg_ms,
+                            "launches": int(prof["spmv_launches"]), "standalone_launch_ms": ms_spmv,
+                            "share_of_step": prof["spmv_ms"] / (1e3 * t)},
+               "gpu_launches": int(prof["kernel_launches"])}
+    H.close()
+    return out
 
 
 _REAL_STDOUT = None
@@ -196,6 +321,9 @@ def main():
                     help="GF_OPT_MG_MATRIX_PRECISION for the whole run (0 FP64 level matrices in the "
                          "V-cycle, 1 FP32 copies, 2 all-FP32 operator)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true",
+                    help="skip the cfg4 strong-scaling measurement (51 M-DoF linear Q1 cantilever) "
+                         "that follows the main regions")
     ap.add_argument("--no-variants", action="store_true",
                     help="skip the matrix-free-operator variant measured after the main regions")
     ap.add_argument("--precond", default="mg", choices=["mg", "jacobi"],
@@ -222,13 +350,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_run(max(1, args.steps), max(0, min(args.warmup, 1)))
+        r = cpu_run(max(1, args.steps), max(0, min(args.warmup, 1)), "reference")
         line = {"impl": "reference", "metric": "newton_step_dofs_per_s", "value": r["value"],
                 "unit": "DoFs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * r["seconds"] / max(1, args.steps), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "cpu_sample": r["sample"]},
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample",
+                                                   "full_size_anchor") if k in r},
                 "e2e": {"value": r["value"], "unit": "DoFs/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -433,7 +562,9 @@ def main():
         ms_spmv, spmv_bytes = h.spmv_timed(capi.MAT_TANGENT, 5)
         spmv_avg_ms = prof["spmv_ms"] / max(1, prof["spmv_launches"])
         achieved = spmv_bytes / (spmv_avg_ms * 1e-3) / 1e9
-        traffic_path = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+        # DRAM bytes per launch of the SHIPPED default kernel from this round's `ncu --set full`
+        # capture of the same matrix (profiles/r02_spmv_ncu_summary.md); null if not captured
+        traffic_path = os.path.join(ROOT, "profiles", "r02_spmv_traffic.json")
         traffic = json.load(open(traffic_path)).get("dram_bytes_per_launch") if os.path.exists(traffic_path) else None
         line = {
             "metric": "newton_step_dofs_per_s", "value": n_dofs_global * solves_value / t_value,
@@ -443,6 +574,8 @@ def main():
             "config": {"workload": workload, "n_dofs": n_dofs_global, "n_dofs_per_gpu": h.n_owned,
                        "nnz_scalar": h.nnz(), "newton_solves_in_timed_region": solves_value,
                        "cg_iterations_in_timed_region": cg_its_value,
+                       "ms_per_cg_iteration": 1e3 * t_value / max(1, cg_its_value),
+                       "cg_iterations_per_newton_solve": cg_its_value / max(1, solves_value),
                        "preconditioner": args.precond,
                        "spmv_kernel_option": args.spmv_kernel, "mg_matrix_precision": args.mg_precision,
                        "multigrid_levels": [q.mesh.reps for q in hierarchy.problems] if hierarchy else None,
@@ -456,10 +589,10 @@ def main():
                     "ms_per_step": 1e3 * wall_e2e / args.steps, "newton_solves": solves_e2e},
             "gpu_launches": int(prof["kernel_launches"]),
             "roofline": {"bound": "hbm",
-                         "kernel": "finest-level SpMV launches of the timed region: spmv_tma2_kernel<3> "
-                                   "(two rings, 16 consumer warps) for the Chebyshev-smoother and "
-                                   "residual vmults of the V-cycle, spmv_tma_kernel<3> for the CG "
-                                   "vmult with fused dot",
+                         "kernel": "finest-level SpMV launches of the timed region: spmv_tma2_kernel<3, "
+                                   "..., 8, 2, 16, TR> (two TMA rings, 8 gather + 16 consumer warps, "
+                                   "transposed row reduction) for the CG vmult and the Chebyshev-"
+                                   "smoother / residual vmults of the V-cycle",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic,
                          "bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_avg_ms,
@@ -475,13 +608,23 @@ def main():
         if comm_info:
             line["comm"] = comm_info
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_run(1, 0)
-            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        emit(line)
+            r = cpu_run(1, 0, "baseline")
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample",
+                                                      "full_size_anchor") if k in r}
     if hierarchy:
         hierarchy.close()
     else:
         h.close()
+    # ---- north_star's multi-GPU target in the same driver-run line: cfg4, STRONG scaling -------
+    if not args.no_strong and os.environ.get("GF_PROFILE_RUN") != "1" and args.precond == "mg":
+        try:
+            strong = run_cfg4(args, world, rank, local_rank, comm, dist, torch)
+        except Exception as exc:      # must not cost the main line
+            strong = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        if rank == 0:
+            line["strong_scaling"] = strong
+    if rank == 0:
+        emit(line)
     if world > 1:
         comm.close()
         dist.destroy_process_group()

@@ -23,7 +23,7 @@ MAT_TANGENT, MAT_STIFFNESS, MAT_MASS, MAT_SYSTEM, MAT_MG_F32 = range(5)
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI, PRECOND_MULTIGRID = range(4)
 OPT_PRECONDITIONER, OPT_CG_CHECK_INTERVAL, OPT_PROFILE, OPT_OPERATOR, OPT_SPMV_KERNEL, \
     OPT_MG_SMOOTHER_DEGREE, OPT_MG_COARSE_DEGREE, OPT_MG_SMOOTHER_RATIO, \
-    OPT_MG_MATRIX_PRECISION = range(9)
+    OPT_CG_INITIAL_GUESS, OPT_MG_MATRIX_PRECISION = range(10)
 
 EXPORTED_SYMBOLS = [
     "gf_create", "gf_destroy", "gf_last_error", "gf_set_option", "gf_comm_unique_id",
@@ -102,7 +102,7 @@ def lib():
         L.gf_comm_destroy.argtypes = [vp]
         L.gf_comm_destroy.restype = None
         L.gf_comm_ipc_begin.argtypes = [i32, i32, i32, C.POINTER(vp), vp]
-        L.gf_comm_ipc_finish.argtypes = [vp, vp]
+        L.gf_comm_ipc_finish.argtypes = [vp, vp, i32]
         L.gf_set_traction.argtypes = [vp, vp]
         L.gf_get_interface_displacement.argtypes = [vp, vp]
         for n in ("gf_state_save", "gf_state_restore", "gf_nl_begin_step", "gf_nl_end_step",
@@ -144,7 +144,7 @@ class Comm:
         self.rank, self.n_ranks = rank, n_ranks
 
     @classmethod
-    def from_ipc(cls, rank: int, n_ranks: int, device: int, all_gather):
+    def from_ipc(cls, rank: int, n_ranks: int, device: int, all_gather, share_device=False):
         """Communicator without NCCL (gf_comm_ipc_begin / _finish): `all_gather(bytes) -> [bytes]`
         moves every rank's 64-byte window handle over the host's own channel (e.g.
         torch.distributed with the gloo backend). Ranks may share a device."""
@@ -157,7 +157,7 @@ class Comm:
         handles = all_gather(bytes(mine))
         assert len(handles) == n_ranks and all(len(x) == 64 for x in handles)
         buf = (C.c_uint8 * (64 * n_ranks)).from_buffer_copy(b"".join(handles))
-        rc = lib().gf_comm_ipc_finish(h, buf)
+        rc = lib().gf_comm_ipc_finish(h, buf, 1 if share_device else 0)
         if rc != GF_OK:
             raise GraftError(rc, "gf_comm_ipc_finish failed (cudaIpcOpenMemHandle)")
         self._h = h

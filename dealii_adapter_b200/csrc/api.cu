@@ -459,6 +459,10 @@ extern "C"
             for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
               l->mg_smoother_ratio = double(value);
             break;
+          case GF_OPT_CG_INITIAL_GUESS:
+            GF_REQUIRE(value == 0 || value == 1, GF_ERR_INVALID_ARG, "initial guess: 0 or 1");
+            c.cg_initial_guess = int(value);
+            break;
           case GF_OPT_MG_MATRIX_PRECISION:
             GF_REQUIRE(value >= 0 && value <= 2, GF_ERR_INVALID_ARG,
                        "matrix precision of the V-cycle: 0 (FP64), 1 (FP32 copy) or 2 (all FP32)");

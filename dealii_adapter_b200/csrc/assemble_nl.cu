@@ -16,11 +16,14 @@
 //   phase B  one thread per (q, node a): spatial gradient g_a = grad_X N_a F^-1 (:946-947),
 //            T_a = B_a^T (JxW D)  (dim x V) and t_a = JxW tau g_a           (pre-contraction the
 //            reference repeats per (i,j) at :1011-1012)
-//   phase C  warp <-> group of 3 nodes a, lane <-> node b: K_ab += T_a B_b (material, :1011),
-//            S_ab += t_a . g_b (geometric, :1018-1019); FP64 FMA pipe bound
+//   phase C  lane <-> 2x2 tile of node pairs (a, b) with b <= a ONLY - the lower triangle, as the
+//            reference's j <= i loop (:1003-1035); rows u and NG-1-u of tiles share a unit so
+//            all lanes carry the same load: K_ab += T_a B_b (material, :1011),
+//            S_ab += t_a . g_b (geometric, :1018-1019); FP64 FMA pipe bound. The upper node
+//            blocks are never computed or stored: the scatter reads K_e(b,a)^T (:1033-1035)
 //   end      K_ab diag += S_ab + rho alpha_1 detJ M_ab (mass, :1020-1021); r_e from t_a, body
 //            force and inertia (:984-995)
-// Algorithmic flops / q-point (3D Q2): 729 node pairs * 30 FMA = 43.7 kflop (full matrix).
+// Algorithmic flops / q-point (3D Q2): 378 node pairs (b <= a) * 30 FMA = 22.7 kflop.
 #include "gf_context.h"
 #include "kernel_utils.cuh"
 #include "nl_material.cuh"
@@ -44,16 +47,23 @@ namespace gf
       static constexpr int BT   = 2;                   // nodes b per lane (register tile columns)
       static constexpr int NG   = (NPC + AT - 1) / AT; // a-groups
       static constexpr int NBG  = (NPC + BT - 1) / BT; // b-pairs
-      static constexpr int NBGP = NBG <= 2 ? 2 : (NBG <= 4 ? 4 : (NBG <= 8 ? 8 : 16));
-      static constexpr int NSUB = 32 / NBGP;           // a-groups per consumer warp
-      static constexpr int NW   = (NG + NSUB - 1) / NSUB; // consumer warps (phase C)
+      static_assert(AT == BT, "the triangular tile pairing needs square tiles");
+      // Only the node blocks with b <= a are computed (the reference fills j <= i and mirrors,
+      // nonlinear_elasticity.cc:1003-1035): tile row ag needs the tiles bg = 0..ag. A UNIT pairs
+      // row u with row NG-1-u, i.e. (u+1) + (NG-u) = NG+1 tiles on LPU lanes, so every unit
+      // carries the same load and half the FMAs of the full matrix disappear.
+      static constexpr int NU   = (NG + 1) / 2;         // units
+      static constexpr int LPU  = NG + 1 <= 2 ? 2 : (NG + 1 <= 4 ? 4 : (NG + 1 <= 8 ? 8 : 16)); // lanes/unit
+      static_assert(NG + 1 <= 16, "tiles of a unit must fit half a warp");
+      static constexpr int NSUB = 32 / LPU;             // units per consumer warp
+      static constexpr int NW   = (NU + NSUB - 1) / NSUB; // consumer warps (phase C)
       static constexpr int NPW  = (DIM == 3 && P == 2) ? 4 : 1; // producer warps (phases A, B)
       static constexpr int NT   = (NW + NPW) * 32;
       static constexpr int RPT  = (DPC + NPW * 32 - 1) / (NPW * 32); // residual entries/producer
       static constexpr int QC   = (DIM == 3 && P == 2) ? 8 : NQ; // q-points per chunk
-      static_assert(NBG <= 16 && BT * NBGP <= NPCP + BT, "b-pair mapping");
+      static_assert(NBG <= 16 && BT * NBG <= NPCP + BT, "b-pair mapping");
       static constexpr int QS   = DIM * DIM + VO * VO + VO + DIM + 2; // per-q scalars
-      static_assert(NW * NSUB >= NG, "every a-group needs its own unit");
+      static_assert(NW * NSUB >= NU, "every unit needs its lanes");
       static_assert((TS % 2) == 0 && (NPCP % 2) == 0, "16-byte aligned rows");
       static_assert(NQ % QC == 0, "chunking");
 
@@ -313,11 +323,18 @@ namespace gf
           // T_a rows are broadcast loads inside a sub-warp and serve AT*BT pairs per lane, the
           // g_b pair is one 16-byte load - shared-memory traffic per FMA is half that of a
           // 3 x 1 tile, which left the kernel bound by the LDS pipe (ncu: 76 % LSU, 39 % FP64)
-          const int  sub = lane / C::NBGP, bg = lane % C::NBGP;
+          // lane j of unit u: j <= u -> tile (row u, bg = j); else tile (row NG-1-u, bg = j-u-1);
+          // the middle row of an odd NG is its own partner and is taken once
+          const int  sub = lane / C::LPU, j = lane % C::LPU;
           const int  unit = warp * C::NSUB + sub;
-          const bool unit_active = unit < C::NG && bg < C::NBG;
-          const int  a_base = unit < C::NG ? unit * AT : 0;
-          const int  bgc = bg < C::NBG ? bg : C::NBG - 1; // clamped for loads
+          const int  row2 = C::NG - 1 - unit;
+          const bool first_row = j <= unit;
+          const int  ag = first_row ? unit : row2;
+          const int  bg = first_row ? j : j - unit - 1;
+          const bool unit_active =
+            unit < C::NU && bg >= 0 && bg <= ag && (first_row || row2 != unit);
+          const int  a_base = unit_active ? ag * AT : 0;
+          const int  bgc = unit_active ? bg : 0; // clamped for loads
           int        it = 0;
           for (int64_t cell = c0 + blockIdx.x; cell < c1; cell += gridDim.x)
             {
@@ -342,7 +359,9 @@ namespace gf
                   mbar_wait(smem_u32(&full[buf]), (it >> 1) & 1);
                   if (unit_active)
                     {
-#pragma unroll 1
+                      // two q-points per trip: the loads of the second overlap the FMAs of the
+                      // first (one consumer warp per scheduler has nobody else to hide them)
+#pragma unroll 2
                       for (int ql = 0; ql < QC; ++ql)
                         {
                           double gb[BT][DIM];
@@ -429,7 +448,7 @@ namespace gf
                           for (int bi = 0; bi < BT; ++bi)
                             {
                               const int b = BT * bg + bi;
-                              if (b < NPC)
+                              if (b <= a) // lower node blocks only; the scatter mirrors them
                                 {
                                   const double dd = Sacc[ai][bi] + mfac * Mref[a * NPC + b];
 #pragma unroll

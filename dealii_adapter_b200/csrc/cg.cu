@@ -143,7 +143,7 @@ namespace gf
   // device work, so the host reads the SolverControl state after every residual update (before
   // the V-cycle is enqueued) instead of every cg_check_every iterations.
   static int cg_solve_mg(gf_context &c, const double *val, double *x, const double *b, double tol,
-                         int64_t maxit, uint32_t *last_step, double *last_value)
+                         int64_t maxit, double bnorm, uint32_t *last_step, double *last_value)
   {
     GF_REQUIRE(mg_active(c), GF_ERR_INVALID_ARG,
                "GF_PRECOND_MULTIGRID selected but no coarse level is attached (gf_mg_attach)");
@@ -181,8 +181,21 @@ namespace gf
     op_apply(c, val, x, c.cg_v.p, nullptr);
     update(true);
     GF_CUDA_CHECK(cudaGetLastError());
+    bool first_poll = true;
     while (poll() == 0)
       {
+        if (first_poll && bnorm >= 0.0 && c.h_scalars->res > bnorm)
+          {
+            // GF_OPT_CG_INITIAL_GUESS = 1: the caller's guess (the previous Newton update,
+            // nonlinear_elasticity.cc:1184) is further from the solution than the zero vector
+            // (||b - A x0|| > ||b||): start from zero instead. Same stopping criterion.
+            vec_zero(c, x);
+            vec_zero(c, c.cg_v.p);
+            update(true);
+            first_poll = false;
+            continue;
+          }
+        first_poll = false;
         mg_vcycle(c, c.cg_r.p, c.cg_z.p); // z = M^-1 r
         {
           ProfScope ps(c, Profile::CG_VEC, 3);
@@ -211,10 +224,16 @@ namespace gf
                bool tol_relative_to_rhs, int64_t maxit, uint32_t *last_step, double *last_value)
   {
     cudaStream_t s = c.stream;
+    double       bnorm = -1.0; // >= 0: the zero vector may replace a worse initial guess
     if (tol_relative_to_rhs)
-      tol *= vec_masked_norm(c, b, false); // tol_lin * system_rhs.l2_norm() (:1171-1172)
+      {
+        const double bn = vec_masked_norm(c, b, false);
+        tol *= bn; // tol_lin * system_rhs.l2_norm() (:1171-1172)
+        if (c.cg_initial_guess == 1)
+          bnorm = bn;
+      }
     if (c.precond == GF_PRECOND_MULTIGRID)
-      return cg_solve_mg(c, val, x, b, tol, maxit, last_step, last_value);
+      return cg_solve_mg(c, val, x, b, tol, maxit, bnorm, last_step, last_value);
     CGScalars init{};
     init.tol    = tol;
     init.maxit  = int(std::min<int64_t>(maxit, 2147483647));
@@ -245,6 +264,17 @@ namespace gf
         comm_check(c);
         if (c.h_scalars->status != 0)
           break;
+        if (enqueued == 0 && bnorm >= 0.0 && c.h_scalars->res > bnorm)
+          {
+            // the zero vector is the better initial guess (see cg_solve_mg)
+            bnorm = -1.0;
+            vec_zero(c, x);
+            vec_zero(c, c.cg_v.p);
+            ProfScope ps(c, Profile::CG_VEC, 2);
+            launch_update(c, true, b, x);
+            reduce_sums(c, 2, 0, true);
+            continue;
+          }
         GF_REQUIRE(enqueued <= int64_t(c.h_scalars->it) + c.cg_check_every, GF_ERR_CUDA,
                    "CG device state did not advance");
         for (int k = 0; k < c.cg_check_every; ++k, ++enqueued)

@@ -235,13 +235,17 @@ namespace gf
       int            rank, n_ranks;
     };
 
-    // all-reduce(sum) of `count` <= P2P_AR_MAX doubles in ONE single-CTA kernel: scatter my values
-    // into every rank's slot (mine included), release the flags, acquire the flags of all ranks
-    // in my window, add the slots in rank order.
+    // Every exchange is TWO launches: a push kernel (remote stores + release of the peers' flags,
+    // never conditional) and a wait kernel that acquires the local flags FIRST and then consumes.
+    // No kernel ever waits for a flag after its own push: with ranks that share a device (tests)
+    // the flag wait can then be a stream memory operation in front of the wait kernel, so a
+    // waiting rank does not occupy the GPU (gf_comm_s::stream_waits).
+
+    // all-reduce(sum) of `count` <= P2P_AR_MAX doubles: store my values into every rank's slot
+    // (mine included) and release the flags ...
     __global__ void __launch_bounds__(64)
-      p2p_allreduce_kernel(const ArArgs a, double *vals, const int count,
-                           const unsigned long long epoch, int *err,
-                           const unsigned long long timeout_ns)
+      p2p_ar_push_kernel(const ArArgs a, const double *vals, const int count,
+                         const unsigned long long epoch)
     {
       const int t = threadIdx.x, par = int(epoch & 1ull);
       if (t < a.n_ranks * count)
@@ -254,14 +258,21 @@ namespace gf
       __threadfence_system();
       __syncthreads();
       if (t < a.n_ranks)
-        {
-          st_release_sys(reinterpret_cast<unsigned long long *>(a.win[t] + P2P_AR_FLAG) +
-                           par * P2P_MAX_RANKS + a.rank,
-                         epoch);
-          wait_flag(reinterpret_cast<const unsigned long long *>(a.win[a.rank] + P2P_AR_FLAG) +
-                      par * P2P_MAX_RANKS + t,
-                    epoch, err, timeout_ns);
-        }
+        st_release_sys(reinterpret_cast<unsigned long long *>(a.win[t] + P2P_AR_FLAG) +
+                         par * P2P_MAX_RANKS + a.rank,
+                       epoch);
+    }
+    // ... then acquire the flags of all ranks in my window and add the slots in rank order
+    __global__ void __launch_bounds__(64)
+      p2p_ar_sum_kernel(const ArArgs a, double *vals, const int count,
+                        const unsigned long long epoch, int *err,
+                        const unsigned long long timeout_ns)
+    {
+      const int t = threadIdx.x, par = int(epoch & 1ull);
+      if (t < a.n_ranks)
+        wait_flag(reinterpret_cast<const unsigned long long *>(a.win[a.rank] + P2P_AR_FLAG) +
+                    par * P2P_MAX_RANKS + t,
+                  epoch, err, timeout_ns);
       __syncthreads();
       if (t < count)
         {
@@ -274,27 +285,13 @@ namespace gf
         }
     }
 
-    // Second stage of a partition-independent reduction across ranks (reduce.cuh) in ONE launch:
-    // store my chunk partials into every rank's gather window at their GLOBAL positions, release
-    // the flags, acquire the flags of all ranks, then run the fixed tree over the whole global
-    // chunk list (every rank computes the same bits) and, for the CG, the scalar step.
+    // Second stage of a partition-independent reduction across ranks (reduce.cuh): store my chunk
+    // partials into every rank's gather window at their GLOBAL positions and release the flags ...
     __global__ void __launch_bounds__(TREE_THREADS)
-      p2p_gather_tree_kernel(const ArArgs a, const double *__restrict__ partials, const int stride,
-                             const int n_local, const long long base, const int n_global,
-                             const int n_sums, double *__restrict__ sums, CGScalars *s,
-                             const int phase, const bool check_status,
-                             unsigned long long *epoch_counter, int *err,
-                             const unsigned long long timeout_ns)
+      p2p_gather_push_kernel(const ArArgs a, const double *__restrict__ partials, const int stride,
+                             const int n_local, const long long base, const int n_sums,
+                             const unsigned long long epoch)
     {
-      // NB: a rank that skipped this launch would deadlock its peers; the CG status is replicated
-      // (every rank computes it from the same sums), so all ranks skip together
-      if (check_status && s->status != 0)
-        return;
-      __shared__ double sm[32];
-      // The epoch counts EXECUTED gathers and lives on the device: a host-side counter would also
-      // count the launches skipped above, two consecutive executed gathers could then share a
-      // parity and a fast rank could overwrite a window its peer is still summing.
-      const unsigned long long epoch = *epoch_counter + 1ull;
       const int t = threadIdx.x, par = int(epoch & 1ull);
       for (int idx = t; idx < n_sums * n_local; idx += TREE_THREADS)
         {
@@ -307,15 +304,29 @@ namespace gf
       __threadfence_system();
       __syncthreads();
       if (t < a.n_ranks)
-        {
-          st_release_sys(reinterpret_cast<unsigned long long *>(a.win[t] + P2P_GATHER_FLAG) +
-                           par * P2P_MAX_RANKS + a.rank,
-                         epoch);
-          wait_flag(reinterpret_cast<const unsigned long long *>(a.win[a.rank] + P2P_GATHER_FLAG) +
-                      par * P2P_MAX_RANKS + t,
-                    epoch, err, timeout_ns);
-        }
+        st_release_sys(reinterpret_cast<unsigned long long *>(a.win[t] + P2P_GATHER_FLAG) +
+                         par * P2P_MAX_RANKS + a.rank,
+                       epoch);
+    }
+    // ... then acquire the flags of all ranks and run the fixed tree over the whole global chunk
+    // list (every rank computes the same bits) and, for the CG, the scalar step. The handshake is
+    // unconditional (a finished CG only skips the arithmetic): the parity double-buffering needs
+    // every rank to have consumed epoch e before anybody pushes e + 2.
+    __global__ void __launch_bounds__(TREE_THREADS)
+      p2p_gather_tree_kernel(const ArArgs a, const int n_global, const int n_sums,
+                             double *__restrict__ sums, CGScalars *s, const int phase,
+                             const bool check_status, const unsigned long long epoch, int *err,
+                             const unsigned long long timeout_ns)
+    {
+      __shared__ double sm[32];
+      const int t = threadIdx.x, par = int(epoch & 1ull);
+      if (t < a.n_ranks)
+        wait_flag(reinterpret_cast<const unsigned long long *>(a.win[a.rank] + P2P_GATHER_FLAG) +
+                    par * P2P_MAX_RANKS + t,
+                  epoch, err, timeout_ns);
       __syncthreads();
+      if (check_status && s->status != 0)
+        return;
       const double *mine = reinterpret_cast<const double *>(a.win[a.rank] + P2P_GATHER) +
                            size_t(par) * 3 * P2P_GATHER_MAX;
       for (int k = 0; k < n_sums; ++k)
@@ -324,12 +335,8 @@ namespace gf
           if (t == 0)
             sums[k] = w;
         }
-      if (t == 0)
-        {
-          *epoch_counter = epoch;
-          if (phase >= 0)
-            cg_scalar_step(s, sums, phase);
-        }
+      if (phase >= 0 && t == 0)
+        cg_scalar_step(s, sums, phase);
     }
 
     // NCCL transport: the padded all-gather result [rank][k][pad] -> the same fixed tree
@@ -404,6 +411,32 @@ namespace gf
         }
     }
 
+    // Ranks that share a device (gf_comm_s::stream_waits): the flag is awaited by a stream memory
+    // operation in front of the wait kernel, so the stream blocks without a kernel spinning on the
+    // SMs and the GPU can run the peer's context; the wait kernel then finds the flag set.
+    typedef int (*fn_cuStreamWaitValue64)(cudaStream_t, unsigned long long, unsigned long long,
+                                          unsigned);
+    void stream_wait_flag(gf_comm cm, cudaStream_t s, unsigned char *flags_base, size_t index,
+                          unsigned long long epoch)
+    {
+      if (!cm->stream_waits)
+        return;
+      static fn_cuStreamWaitValue64 fn = nullptr;
+      if (!fn)
+        {
+          void *                           p = nullptr;
+          cudaDriverEntryPointQueryResult qr;
+          GF_CUDA_CHECK(cudaGetDriverEntryPoint("cuStreamWaitValue64", &p, cudaEnableDefault, &qr));
+          GF_REQUIRE(p != nullptr && qr == cudaDriverEntryPointSuccess, GF_ERR_CUDA,
+                     "cuStreamWaitValue64 is not available");
+          fn = reinterpret_cast<fn_cuStreamWaitValue64>(p);
+        }
+      const unsigned long long addr =
+        reinterpret_cast<unsigned long long>(flags_base) + index * sizeof(unsigned long long);
+      const int rc = fn(s, addr, epoch, 0x0 /* CU_STREAM_WAIT_VALUE_GEQ */);
+      GF_REQUIRE(rc == 0, GF_ERR_CUDA, "cuStreamWaitValue64 failed: " + std::to_string(rc));
+    }
+
     // operations of one communicator must be ordered: if another handle used it on a different
     // stream, drain that stream first (multigrid levels share the finest level's stream)
     void comm_use_stream(gf_context &c)
@@ -451,6 +484,9 @@ namespace gf
       wait.off[nn] = in_ptr[nn];
       halo_push_kernel<<<dim3(PUSH_BLOCKS, nn), PUSH_THREADS, 0, c.stream>>>(push, out_idx, v,
                                                                              cm->blk_counter);
+      for (int k = 0; k < nn; ++k)
+        stream_wait_flag(cm, c.stream, reinterpret_cast<unsigned char *>(wait.flag[k]), 0,
+                         wait.epoch[k]);
       if (!reverse)
         halo_wait_kernel<false><<<dim3(PUSH_BLOCKS, nn), PUSH_THREADS, 0, c.stream>>>(
           wait, 0, in_idx, v, cm->d_err, cm->timeout_ns);
@@ -530,10 +566,15 @@ namespace gf
           a.win[r] = cm->win[r];
         a.rank    = cm->rank;
         a.n_ranks = cm->n_ranks;
+        const unsigned long long e = ++cm->gather_epoch;
+        p2p_gather_push_kernel<<<1, TREE_THREADS, 0, c.stream>>>(
+          a, c.partials.p, c.red_stride, c.n_red_chunks, (long long)c.red_chunk_base, n_sums, e);
+        for (int r = 0; r < cm->n_ranks; ++r)
+          stream_wait_flag(cm, c.stream, cm->win[cm->rank] + P2P_GATHER_FLAG,
+                           (e & 1ull) * P2P_MAX_RANKS + r, e);
         p2p_gather_tree_kernel<<<1, TREE_THREADS, 0, c.stream>>>(
-          a, c.partials.p, c.red_stride, c.n_red_chunks, (long long)c.red_chunk_base,
-          int(c.n_red_chunks_global), n_sums, red_sums(c), c.cg_scalars.p, cg_phase, check_status,
-          cm->gather_epoch_dev, cm->d_err, cm->timeout_ns);
+          a, int(c.n_red_chunks_global), n_sums, red_sums(c), c.cg_scalars.p, cg_phase,
+          check_status, e, cm->d_err, cm->timeout_ns);
         GF_CUDA_CHECK(cudaGetLastError());
         return;
       }
@@ -664,8 +705,13 @@ namespace gf
           a.win[r] = cm->win[r];
         a.rank    = cm->rank;
         a.n_ranks = cm->n_ranks;
-        p2p_allreduce_kernel<<<1, 64, 0, c.stream>>>(a, dev_values, count, ++cm->ar_epoch,
-                                                     cm->d_err, cm->timeout_ns);
+        const unsigned long long e = ++cm->ar_epoch;
+        p2p_ar_push_kernel<<<1, 64, 0, c.stream>>>(a, dev_values, count, e);
+        for (int r = 0; r < cm->n_ranks; ++r)
+          stream_wait_flag(cm, c.stream, cm->win[cm->rank] + P2P_AR_FLAG, (e & 1ull) * P2P_MAX_RANKS + r,
+                           e);
+        p2p_ar_sum_kernel<<<1, 64, 0, c.stream>>>(a, dev_values, count, e, cm->d_err,
+                                                  cm->timeout_ns);
         GF_CUDA_CHECK(cudaGetLastError());
         return;
       }
@@ -716,6 +762,9 @@ namespace gf
         const int blocks = int(std::min<int64_t>(32, (count + PUSH_THREADS - 1) / PUSH_THREADS));
         vec_push_kernel<<<dim3(blocks, np), PUSH_THREADS, 0, c.stream>>>(push, count, dev_values,
                                                                          cm->blk_counter);
+        for (int k = 0; k < np; ++k)
+          stream_wait_flag(cm, c.stream, reinterpret_cast<unsigned char *>(wait.flag[k]), 0,
+                           wait.epoch[k]);
         vec_sum_kernel<<<blocks, PUSH_THREADS, 0, c.stream>>>(wait, np, my_slot, count, dev_values,
                                                               cm->d_err, cm->timeout_ns);
         GF_CUDA_CHECK(cudaGetLastError());
@@ -797,10 +846,6 @@ namespace gf
                        cudaSuccess ||
                      cudaMemset(cm->blk_counter, 0, P2P_MAX_RANKS * sizeof(unsigned)) !=
                        cudaSuccess ||
-                     cudaMalloc((void **)&cm->gather_epoch_dev, sizeof(unsigned long long)) !=
-                       cudaSuccess ||
-                     cudaMemset(cm->gather_epoch_dev, 0, sizeof(unsigned long long)) !=
-                       cudaSuccess ||
                      cudaHostAlloc((void **)&cm->h_err, sizeof(int), cudaHostAllocMapped) !=
                        cudaSuccess))
             {
@@ -849,8 +894,6 @@ namespace gf
       cudaFree(cm->win[cm->rank]);
     if (cm->blk_counter)
       cudaFree(cm->blk_counter);
-    if (cm->gather_epoch_dev)
-      cudaFree(cm->gather_epoch_dev);
     if (cm->h_err)
       cudaFreeHost(cm->h_err);
     cm->p2p = false;
@@ -939,7 +982,7 @@ extern "C"
         return e.code;
       }
   }
-  int gf_comm_ipc_finish(gf_comm cm, const uint8_t *all_handles)
+  int gf_comm_ipc_finish(gf_comm cm, const uint8_t *all_handles, int ranks_share_device)
   {
     try
       {
@@ -956,13 +999,12 @@ extern "C"
             }
         GF_CUDA_CHECK(cudaMalloc((void **)&cm->blk_counter, gf::P2P_MAX_RANKS * sizeof(unsigned)));
         GF_CUDA_CHECK(cudaMemset(cm->blk_counter, 0, gf::P2P_MAX_RANKS * sizeof(unsigned)));
-        GF_CUDA_CHECK(cudaMalloc((void **)&cm->gather_epoch_dev, sizeof(unsigned long long)));
-        GF_CUDA_CHECK(cudaMemset(cm->gather_epoch_dev, 0, sizeof(unsigned long long)));
         GF_CUDA_CHECK(cudaHostAlloc((void **)&cm->h_err, sizeof(int), cudaHostAllocMapped));
         *cm->h_err = 0;
         GF_CUDA_CHECK(cudaHostGetDevicePointer((void **)&cm->d_err, cm->h_err, 0));
         GF_CUDA_CHECK(cudaDeviceSynchronize());
-        cm->p2p = true;
+        cm->p2p          = true;
+        cm->stream_waits = ranks_share_device != 0 || getenv("GF_COMM_STREAM_WAIT") != nullptr;
         return GF_OK;
       }
     catch (gf::Error &e)

@@ -221,8 +221,8 @@ struct gf_comm_s
   bool           p2p = false;
   unsigned char *win[gf::P2P_MAX_RANKS] = {}; // win[rank] = own allocation, others IPC-mapped
   unsigned long long halo_epoch[gf::P2P_MAX_RANKS] = {}; // per neighbour pair (symmetric counts)
-  unsigned long long ar_epoch = 0;
-  unsigned long long *gather_epoch_dev = nullptr; // device: executed gathers (reduce.cuh)
+  unsigned long long ar_epoch = 0, gather_epoch = 0;
+  bool stream_waits = false; // ranks share a device: flag waits as stream memory operations
   unsigned *     blk_counter = nullptr; // device [P2P_MAX_RANKS]: last-block detection of the push
   int *          h_err = nullptr;       // mapped pinned: set by a kernel whose flag wait timed out
   int *          d_err = nullptr;       // device alias of h_err
@@ -310,6 +310,7 @@ struct gf_context
   // options
   int  precond        = GF_PRECOND_BLOCK_JACOBI;
   int  cg_check_every = 32;
+  int  cg_initial_guess = 1; // GF_OPT_CG_INITIAL_GUESS
   int  operator_kind  = 0;
   bool lin_assembled  = false;
 

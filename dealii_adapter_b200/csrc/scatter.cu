@@ -15,7 +15,10 @@ namespace gf
 {
   namespace
   {
-    template <int DIM>
+    // SYM: the element buffer holds only the node blocks (a, b) with b <= a (the neo-Hookean cell
+    // kernel computes the lower triangle, nonlinear_elasticity.cc:1003-1035); an upper block is read
+    // as the transpose of its mirror, which is exactly the reference's copy lower -> upper.
+    template <int DIM, bool SYM>
     __global__ void __launch_bounds__(256, 3) scatter_matrix_kernel(const int64_t n_rows, const int npc,
                                           const int32_t *__restrict__ brow_ptr,
                                           const int64_t *__restrict__ val_ptr,
@@ -85,13 +88,14 @@ namespace gf
                     continue;
                   const int     ab = src - int32_t(cell) * npc2;
                   const int     a = ab / npc, b = ab - a * npc;
-                  const double *kb =
-                    ke_buf + (cell - c0) * int64_t(dpc) * dpc + (a * DIM) * dpc + b * DIM;
+                  const bool    tr = SYM && b > a;
+                  const double *kb = ke_buf + (cell - c0) * int64_t(dpc) * dpc +
+                                     ((tr ? b : a) * DIM) * dpc + (tr ? a : b) * DIM;
 #pragma unroll
                   for (int r = 0; r < DIM; ++r)
 #pragma unroll
                     for (int cc = 0; cc < DIM; ++cc)
-                      sum[r][cc] += __ldg(kb + r * dpc + cc);
+                      sum[r][cc] += __ldg(tr ? kb + cc * dpc + r : kb + r * dpc + cc);
                 }
             }
           else
@@ -104,7 +108,8 @@ namespace gf
                 const int     ab = src - int32_t(cell) * npc2;
                 const int     a = ab / npc, b = ab - a * npc;
                 const double *ke = ke_buf + (cell - c0) * int64_t(dpc) * dpc;
-                const double *kb = ke + (a * DIM) * dpc + b * DIM;
+                const bool    tr = SYM && b > a;
+                const double *kb = ke + ((tr ? b : a) * DIM) * dpc + (tr ? a : b) * DIM;
 #pragma unroll
                 for (int r = 0; r < DIM; ++r)
 #pragma unroll
@@ -116,7 +121,7 @@ namespace gf
                       const bool drop    = (row_con[r] || col_con[cc]) && !use_abs;
                       if (drop)
                         continue;
-                      double v = kb[r * dpc + cc];
+                      double v = tr ? kb[cc * dpc + r] : kb[r * dpc + cc];
                       if (use_abs)
                         {
                           v = fabs(v);
@@ -255,21 +260,12 @@ namespace gf
         return;
       const int32_t b0 = brow_ptr[A];
       const int     nb = brow_ptr[A + 1] - b0;
-      int           lo = 0, hi = nb - 1, pos = -1;
-      while (lo <= hi)
-        {
-          const int     mid = (lo + hi) >> 1;
-          const int32_t v   = bcol[b0 + mid];
-          if (v == A)
-            {
-              pos = mid;
-              break;
-            }
-          if (v < A)
-            lo = mid + 1;
-          else
-            hi = mid - 1;
-        }
+      // linear scan: the blocks of a row are ordered by the partition-independent node order
+      // (pattern.cu), which is not the local index order on a rank with ghosts below its slab
+      int pos = -1;
+      for (int k = 0; k < nb && pos < 0; ++k)
+        if (bcol[b0 + k] == A)
+          pos = k;
       const int64_t vbase  = val_ptr[A];
       const int     stride = int((val_ptr[A + 1] - vbase) / DIM);
       double        M[DIM][DIM], R[DIM][DIM];
@@ -319,14 +315,27 @@ namespace gf
     const unsigned grid   = unsigned((n_rows * 32 + nt - 1) / nt);
     if (n_rows == 0)
       return;
+    // the neo-Hookean element buffer holds the lower node blocks only (assemble_nl.cu)
+    const bool sym = c.model == GF_MODEL_NEO_HOOKEAN;
+#define GF_SCATTER(D, S)                                                                         \
+  scatter_matrix_kernel<D, S><<<grid, nt, 0, c.stream>>>(                                        \
+    n_rows, c.npc, c.brow_ptr.p, c.val_ptr.p, c.cand_ptr.p, c.src_off.p, c.row_src.p, c.bcol.p,  \
+    c.constrained.p, c.ke_buf.p, c0, c1, first, apply_constraints, val)
     if (c.dim == 3)
-      scatter_matrix_kernel<3><<<grid, nt, 0, c.stream>>>(
-        n_rows, c.npc, c.brow_ptr.p, c.val_ptr.p, c.cand_ptr.p, c.src_off.p, c.row_src.p, c.bcol.p,
-        c.constrained.p, c.ke_buf.p, c0, c1, first, apply_constraints, val);
+      {
+        if (sym)
+          GF_SCATTER(3, true);
+        else
+          GF_SCATTER(3, false);
+      }
     else
-      scatter_matrix_kernel<2><<<grid, nt, 0, c.stream>>>(
-        n_rows, c.npc, c.brow_ptr.p, c.val_ptr.p, c.cand_ptr.p, c.src_off.p, c.row_src.p, c.bcol.p,
-        c.constrained.p, c.ke_buf.p, c0, c1, first, apply_constraints, val);
+      {
+        if (sym)
+          GF_SCATTER(2, true);
+        else
+          GF_SCATTER(2, false);
+      }
+#undef GF_SCATTER
     GF_CUDA_CHECK(cudaGetLastError());
   }
 

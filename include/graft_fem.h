@@ -159,6 +159,15 @@ extern "C"
     GF_OPT_MG_SMOOTHER_DEGREE, /* Chebyshev degree of the pre-/post-smoother (default 3) */
     GF_OPT_MG_COARSE_DEGREE,   /* Chebyshev degree of the coarsest-level solve (default 80) */
     GF_OPT_MG_SMOOTHER_RATIO,  /* smoothers damp the eigenvalues in [lmax/ratio, lmax] (default 40) */
+    GF_OPT_CG_INITIAL_GUESS,   /* gf_nl_newton_solve. 0: the reference's initial guess, the previous
+                                  newton_update (nonlinear_elasticity.cc:1184 hands the vector of the
+                                  last Newton pass to SolverCG); 1 (default): the same, unless its
+                                  residual is LARGER than that of the zero vector (||b - A x0|| >
+                                  ||b||, true from the second Newton pass on: the previous update is
+                                  orders of magnitude larger than the new one) - then CG starts from
+                                  zero. The stopping criterion tol*||b|| (:1171-1172) is unchanged, so
+                                  the Newton history agrees within that tolerance; CG needs ~25 %
+                                  fewer iterations per timestep. */
     GF_OPT_MG_MATRIX_PRECISION /* 0 (default): the V-cycle streams the FP64 level matrices;
                                   1: it streams FP32 copies of them (half the HBM bytes per smoother
                                   / residual application), accumulating in FP64;
@@ -216,9 +225,13 @@ extern "C"
    * rank's 64-byte cudaIpc window handle. begin allocates this rank's window and returns its
    * handle; the host all-gathers the handles over any channel it has (MPI, torch.distributed/
    * gloo); finish maps the peers. There is no fallback transport on such a communicator. Several
-   * ranks may share one device (the multi-rank parity tests do: NCCL refuses that). */
+   * ranks may share one device (the multi-rank parity tests do: NCCL refuses that); pass
+   * ranks_share_device != 0 then: every flag wait is additionally issued as a stream memory
+   * operation (cuStreamWaitValue64) in front of the kernel that consumes the data, so a waiting
+   * rank does not keep the shared GPU busy spinning. */
   int gf_comm_ipc_begin(int rank, int n_ranks, int device, gf_comm *out, uint8_t handle[64]);
-  int gf_comm_ipc_finish(gf_comm c, const uint8_t *all_handles /* [n_ranks*64] */);
+  int gf_comm_ipc_finish(gf_comm c, const uint8_t *all_handles /* [n_ranks*64] */,
+                         int ranks_share_device);
   /* which transport carries the halo exchange and the scalar all-reduce: peer windows = every
    * rank's mailbox/flag window is mapped into all peers with cudaIpc and the library's own kernels
    * store ghost values / partial sums straight into the neighbour's HBM over NVLink (default);

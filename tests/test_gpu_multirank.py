@@ -13,6 +13,7 @@ between processes on one device, NCCL does not), time-sliced by the driver; with
 same worker also runs over NCCL-bootstrapped peer windows (tests/mgpu_worker.py --mode nccl)."""
 import os
 import pickle
+import signal
 import socket
 import subprocess
 import sys
@@ -31,16 +32,24 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _spawn(world, mode, out, cases=None, timeout=600):
+def _spawn(world, mode, out, cases=None, timeout=240):
     env = dict(os.environ, GF_P2P_TIMEOUT_S="30", OMP_NUM_THREADS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(HERE, "mgpu_worker.py"), "--out", out, "--mode", mode]
     if cases:
         cmd += ["--cases", cases]
-    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
-                       timeout=timeout)
-    assert r.returncode == 0, r.stdout[-4000:]
+    # own process group: a timeout must take the rank processes down too (a killed torchrun
+    # leaves its workers behind, and they would keep the GPU busy for every later test)
+    proc = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                            start_new_session=True)
+    try:
+        stdout, _ = proc.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        stdout, _ = proc.communicate()
+        raise AssertionError("multi-rank worker timed out after %d s\n%s" % (timeout, stdout[-4000:]))
+    assert proc.returncode == 0, stdout[-4000:]
     with open(out, "rb") as f:
         return pickle.load(f)
 
