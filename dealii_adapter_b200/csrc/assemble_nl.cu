@@ -43,18 +43,35 @@ namespace gf
       static constexpr int VO   = DIM * (DIM + 1) / 2;
       static constexpr int TS   = (DIM * VO + DIM + 1) & ~1; // T (DIM x VO) + t (DIM), even
       static constexpr int NPCP = NPC <= 4 ? 4 : (NPC <= 8 ? 8 : (NPC <= 16 ? 16 : 32));
-      static constexpr int AT   = 2;                   // nodes a per lane (register tile rows)
+      static constexpr int AT   = 1;                   // nodes a per lane (register tile rows)
       static constexpr int BT   = 2;                   // nodes b per lane (register tile columns)
-      static constexpr int NG   = (NPC + AT - 1) / AT; // a-groups
+      static constexpr int NG   = (NPC + AT - 1) / AT; // tile rows (a-groups)
       static constexpr int NBG  = (NPC + BT - 1) / BT; // b-pairs
-      static_assert(AT == BT, "the triangular tile pairing needs square tiles");
       // Only the node blocks with b <= a are computed (the reference fills j <= i and mirrors,
-      // nonlinear_elasticity.cc:1003-1035): tile row ag needs the tiles bg = 0..ag. A UNIT pairs
-      // row u with row NG-1-u, i.e. (u+1) + (NG-u) = NG+1 tiles on LPU lanes, so every unit
-      // carries the same load and half the FMAs of the full matrix disappear.
+      // nonlinear_elasticity.cc:1003-1035): tile row ag needs the b-pairs bg with BT*bg <= last a
+      // of the row. A UNIT pairs row u with row NG-1-u so that every unit carries (nearly) the
+      // same number of tiles on its LPU lanes; half the FMAs of the full matrix disappear. The
+      // 1 x 2 tile (3D Q2: 196 tiles = 7 consumer warps) keeps two consumer warps per scheduler:
+      // with the 2 x 2 tile (105 tiles = 4 warps) the FP64 pipe idled 64 % of the time on
+      // dependent-issue latency (ncu, profiles/r02_assembly_ncu_summary.md).
+      static constexpr int tiles_in_row(int ag)
+      {
+        return (AT * ag + AT - 1) / BT + 1 < NBG ? (AT * ag + AT - 1) / BT + 1 : NBG;
+      }
+      static constexpr int unit_tiles(int u)
+      {
+        return tiles_in_row(u) + (NG - 1 - u != u ? tiles_in_row(NG - 1 - u) : 0);
+      }
+      static constexpr int max_unit_tiles(int u = 0)
+      {
+        return u >= (NG + 1) / 2 ? 0 :
+                                   (unit_tiles(u) > max_unit_tiles(u + 1) ? unit_tiles(u) :
+                                                                            max_unit_tiles(u + 1));
+      }
       static constexpr int NU   = (NG + 1) / 2;         // units
-      static constexpr int LPU  = NG + 1 <= 2 ? 2 : (NG + 1 <= 4 ? 4 : (NG + 1 <= 8 ? 8 : 16)); // lanes/unit
-      static_assert(NG + 1 <= 16, "tiles of a unit must fit half a warp");
+      static constexpr int MUT  = max_unit_tiles();
+      static constexpr int LPU  = MUT <= 2 ? 2 : (MUT <= 4 ? 4 : (MUT <= 8 ? 8 : 16)); // lanes/unit
+      static_assert(MUT <= 16, "tiles of a unit must fit half a warp");
       static constexpr int NSUB = 32 / LPU;             // units per consumer warp
       static constexpr int NW   = (NU + NSUB - 1) / NSUB; // consumer warps (phase C)
       static constexpr int NPW  = (DIM == 3 && P == 2) ? 4 : 1; // producer warps (phases A, B)
@@ -323,16 +340,17 @@ namespace gf
           // T_a rows are broadcast loads inside a sub-warp and serve AT*BT pairs per lane, the
           // g_b pair is one 16-byte load - shared-memory traffic per FMA is half that of a
           // 3 x 1 tile, which left the kernel bound by the LDS pipe (ncu: 76 % LSU, 39 % FP64)
-          // lane j of unit u: j <= u -> tile (row u, bg = j); else tile (row NG-1-u, bg = j-u-1);
-          // the middle row of an odd NG is its own partner and is taken once
+          // lane j of unit u: the tiles of row u first, then those of row NG-1-u; the middle row
+          // of an odd NG is its own partner and is taken once
           const int  sub = lane / C::LPU, j = lane % C::LPU;
           const int  unit = warp * C::NSUB + sub;
           const int  row2 = C::NG - 1 - unit;
-          const bool first_row = j <= unit;
+          const int  n_first = unit < C::NU ? C::tiles_in_row(unit) : 0;
+          const bool first_row = j < n_first;
           const int  ag = first_row ? unit : row2;
-          const int  bg = first_row ? j : j - unit - 1;
-          const bool unit_active =
-            unit < C::NU && bg >= 0 && bg <= ag && (first_row || row2 != unit);
+          const int  bg = first_row ? j : j - n_first;
+          const bool unit_active = unit < C::NU && (first_row || (row2 != unit && row2 >= 0 &&
+                                                                   bg < C::tiles_in_row(row2)));
           const int  a_base = unit_active ? ag * AT : 0;
           const int  bgc = unit_active ? bg : 0; // clamped for loads
           int        it = 0;
@@ -359,8 +377,6 @@ namespace gf
                   mbar_wait(smem_u32(&full[buf]), (it >> 1) & 1);
                   if (unit_active)
                     {
-                      // two q-points per trip: the loads of the second overlap the FMAs of the
-                      // first (one consumer warp per scheduler has nobody else to hide them)
 #pragma unroll 2
                       for (int ql = 0; ql < QC; ++ql)
                         {

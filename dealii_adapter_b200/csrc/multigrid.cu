@@ -664,7 +664,12 @@ namespace gf
             l->stream      = f.stream;
             l->owns_stream = false;
             l->prof_sink   = f.prof_sink;
+            // options set on the finest handle BEFORE the attach apply to the whole chain too
             l->mg_matrix_precision = f.mg_matrix_precision;
+            l->spmv_kernel_kind    = f.spmv_kernel_kind;
+            l->mg_smoother_degree  = f.mg_smoother_degree;
+            l->mg_smoother_ratio   = f.mg_smoother_ratio;
+            l->mg_coarse_degree    = f.mg_coarse_degree;
           }
         if (!l->mg_lmax_dev.p)
           {

@@ -3,6 +3,7 @@
 // and turn into exit code 1. DIM is a compile-time choice (-DDIM, CMakeLists.txt:15-18).
 #include <sys/stat.h>
 
+#include <cerrno>
 #include <iostream>
 #include <string>
 
@@ -25,8 +26,23 @@ int main(int argc, char **argv)
                 << std::endl;
       std::string parameter_file = argc > 1 ? argv[1] : "parameters.prm";
       const Parameters::AllParameters prm(parameter_file);
+      // "Output folder" is created component by component; a component that can neither be
+      // created nor exists ends the run with the reference's message (elasticity.cc:57-81)
       if (!prm.output_folder.empty())
-        mkdir(prm.output_folder.c_str(), 0777); // elasticity.cc:51-81
+        {
+          std::string path = prm.output_folder;
+          if (path.back() != '/')
+            path += '/';
+          for (size_t pos = path.find('/'); pos != std::string::npos; pos = path.find('/', pos + 1))
+            {
+              const std::string sub = path.substr(0, pos);
+              if (sub.empty())
+                continue; // leading '/'
+              if (mkdir(sub.c_str(), S_IRWXU | S_IRGRP | S_IXGRP | S_IROTH | S_IXOTH) != 0 &&
+                  errno != EEXIST)
+                throw std::runtime_error("Can't create: " + path);
+            }
+        }
       if (prm.model == "neo-Hookean")
         {
           Nonlinear_Elasticity::Solid<DIM> solid(parameter_file);

@@ -13,6 +13,28 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
 
 
+def _cuda_device_count():
+    import ctypes
+    for name in ("libcudart.so", "libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so"):
+        try:
+            rt = ctypes.CDLL(name)
+        except OSError:
+            continue
+        n = ctypes.c_int(0)
+        return n.value if rt.cudaGetDeviceCount(ctypes.byref(n)) == 0 else 0
+    return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """`pytest tests` on a machine without a GPU: the gpu-marked tests are skipped (they have no
+    CPU fallback to run), everything else runs."""
+    if any(item.get_closest_marker("gpu") for item in items) and _cuda_device_count() == 0:
+        skip = pytest.mark.skip(reason="no CUDA device (the hot path has no CPU fallback)")
+        for item in items:
+            if item.get_closest_marker("gpu"):
+                item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def native_libs():
     """Build (if stale) the host scaffolding and the oracle once per session."""
