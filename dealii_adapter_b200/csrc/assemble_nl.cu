@@ -74,12 +74,18 @@ namespace gf
       static_assert(MUT <= 16, "tiles of a unit must fit half a warp");
       static constexpr int NSUB = 32 / LPU;             // units per consumer warp
       static constexpr int NW   = (NU + NSUB - 1) / NSUB; // consumer warps (phase C)
-      static constexpr int NPW  = (DIM == 3 && P == 2) ? 4 : 1; // producer warps (phases A, B)
+      // producer warps (phases A, B). ncu of the 4-warp version (profiles/r02_assembly_ncu_summary
+      // .md): the consumers spent their time waiting for the `full` barrier - the producers, not
+      // the FP64 contraction, bounded the kernel once only the lower triangle was computed.
+      static constexpr int NPW  = (DIM == 3 && P == 2) ? 8 : 1;
       static constexpr int NT   = (NW + NPW) * 32;
+      // phase A: PA threads share a quadrature point (each sums every PA-th node, then a
+      // butterfly over the PA lanes), so all producer threads work on the 27-node loops
+      static constexpr int PA   = (NPW * 32) / NQ >= 4 ? 4 : ((NPW * 32) / NQ >= 2 ? 2 : 1);
       static constexpr int RPT  = (DPC + NPW * 32 - 1) / (NPW * 32); // residual entries/producer
       static constexpr int QC   = (DIM == 3 && P == 2) ? 8 : NQ; // q-points per chunk
       static_assert(NBG <= 16 && BT * NBG <= NPCP + BT, "b-pair mapping");
-      static constexpr int QS   = DIM * DIM + VO * VO + VO + DIM + 2; // per-q scalars
+      static constexpr int QS   = (((VO * VO + 1) & ~1) + ((VO + 1) & ~1) + DIM * DIM + DIM + 1 + 1) & ~1; // per-q scalars
       static_assert(NW * NSUB >= NU, "every unit needs its lanes");
       static_assert((TS % 2) == 0 && (NPCP % 2) == 0, "16-byte aligned rows");
       static_assert(NQ % QC == 0, "chunking");
@@ -97,12 +103,13 @@ namespace gf
       static_assert(SMEM_D * 8 <= 227 * 1024, "shared memory budget");
       static constexpr size_t SMEM_BYTES = size_t(SMEM_D) * sizeof(double);
       // offsets inside a per-q record
-      static constexpr int Q_C   = 0;                 // C = Jinv * Finv            [DIM*DIM]
-      static constexpr int Q_D   = Q_C + DIM * DIM;   // JxW * Jc (Voigt)           [VO*VO]
-      static constexpr int Q_TAU = Q_D + VO * VO;     // JxW * tau (Voigt)          [VO]
-      static constexpr int Q_A   = Q_TAU + VO;        // rho * JxW * sumN * acc     [DIM]
+      // (D and tau first: even offsets, so phase B fetches them as 16-byte loads)
+      static constexpr int Q_D   = 0;                 // JxW * Jc (Voigt)           [VO*VO]
+      static constexpr int Q_TAU = Q_D + ((VO * VO + 1) & ~1); // JxW * tau (Voigt)  [VO]
+      static constexpr int Q_C   = Q_TAU + ((VO + 1) & ~1);    // C = Jinv * Finv    [DIM*DIM]
+      static constexpr int Q_A   = Q_C + DIM * DIM;   // rho * JxW * sumN * acc     [DIM]
       static constexpr int Q_W   = Q_A + DIM;         // JxW
-      static constexpr int Q_X   = Q_W + 1;           // spare
+      static constexpr int Q_END = Q_W + 1;
     };
 
     template <int DIM, int P>
@@ -164,8 +171,16 @@ namespace gf
                 }
               named_bar_sync(1, NPT);
               // ------------- phase A: kinematics + material per quadrature point ---------------
-              for (int q = ptid; q < NQ; q += NPT)
+              // PA lanes per q-point: lane `part` sums the nodes a = part, part + PA, ...; the
+              // partial sums are combined by a butterfly (fixed order), then every lane of the
+              // group holds the same H / acc and evaluates the material; each writes 1/PA of the
+              // record
+              constexpr int PA = C::PA;
+              constexpr int NQA = ((NQ * PA + 31) / 32) * 32; // whole warps take part in the shuffles
+              for (int qq = ptid; qq < NQA; qq += NPT)
                 {
+                  const bool valid = qq < NQ * PA;
+                  const int  q = valid ? qq / PA : NQ - 1, part = qq % PA;
                   double Hr[DIM][DIM], acc[DIM];
                   double sumN = 0;
 #pragma unroll
@@ -176,7 +191,7 @@ namespace gf
                       for (int j = 0; j < DIM; ++j)
                         Hr[i][j] = 0;
                     }
-                  for (int a = 0; a < NPC; ++a)
+                  for (int a = part; a < NPC; a += PA)
                     {
                       const double Na = sN[q * NPC + a];
                       sumN += Na;
@@ -190,6 +205,21 @@ namespace gf
                             Hr[cc][e] += ua * sdN[(q * NPC + a) * DIM + e];
                         }
                     }
+#pragma unroll
+                  for (int o = 1; o < PA; o <<= 1)
+                    {
+                      sumN += __shfl_xor_sync(0xffffffffu, sumN, o);
+#pragma unroll
+                      for (int i = 0; i < DIM; ++i)
+                        {
+                          acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+#pragma unroll
+                          for (int j = 0; j < DIM; ++j)
+                            Hr[i][j] += __shfl_xor_sync(0xffffffffu, Hr[i][j], o);
+                        }
+                    }
+                  if (!valid)
+                    continue;
                   double F[DIM][DIM];
 #pragma unroll
                   for (int i = 0; i < DIM; ++i)
@@ -223,6 +253,14 @@ namespace gf
                   neo_hooke<DIM>(prm.kappa, prm.mu, detF, bbar, tau, D); // :958-961
                   const double JxW = detJ * tabw[q];
                   double *     rec = sQ + q * QS;
+                  // the PA lanes hold identical values; lane `part` stores every PA-th entry
+#define GF_REC(idx, val)                                                                         \
+  do                                                                                             \
+    {                                                                                            \
+      if (PA == 1 || ((idx) % PA) == part)                                                       \
+        rec[idx] = (val);                                                                        \
+    }                                                                                            \
+  while (0)
 #pragma unroll
                   for (int e = 0; e < DIM; ++e)
 #pragma unroll
@@ -232,20 +270,21 @@ namespace gf
 #pragma unroll
                         for (int d = 0; d < DIM; ++d)
                           v += Jinv[e][d] * Finv[d][l];
-                        rec[C::Q_C + e * DIM + l] = v;
+                        GF_REC(C::Q_C + e * DIM + l, v);
                       }
 #pragma unroll
                   for (int k = 0; k < VO; ++k)
                     {
-                      rec[C::Q_TAU + k] = tau[k] * JxW;
+                      GF_REC(C::Q_TAU + k, tau[k] * JxW);
 #pragma unroll
                       for (int l = 0; l < VO; ++l)
-                        rec[C::Q_D + k * VO + l] = D[k][l] * JxW;
+                        GF_REC(C::Q_D + k * VO + l, D[k][l] * JxW);
                     }
 #pragma unroll
                   for (int cc = 0; cc < DIM; ++cc)
-                    rec[C::Q_A + cc] = prm.rho * sumN * acc[cc] * JxW; // :993-995 summed over j
-                  rec[C::Q_W] = JxW;
+                    GF_REC(C::Q_A + cc, prm.rho * sumN * acc[cc] * JxW); // :993-995 summed over j
+                  GF_REC(C::Q_W, JxW);
+#undef GF_REC
                 }
               named_bar_sync(1, NPT);
 
@@ -265,14 +304,45 @@ namespace gf
                     {
                       const int     ql = item / NPC, a = item % NPC, q = qc + ql;
                       const double *rec = sQ + q * QS;
-                      double        g[DIM];
+                      // every operand of the item is fetched up front (16-byte loads where the
+                      // layout allows): the FMAs then run without waiting on shared memory (ncu of
+                      // the previous version: 37 % of all stalls were short-scoreboard, i.e. LDS
+                      // latency, in this block)
+                      double Dq[VO * VO], tq[VO], Cq[DIM * DIM], dn[DIM];
+                      if constexpr (((VO * VO) % 2) == 0)
+                        {
+#pragma unroll
+                          for (int k = 0; k < VO * VO; k += 2)
+                            {
+                              const double2 v =
+                                *reinterpret_cast<const double2 *>(rec + C::Q_D + k);
+                              Dq[k]     = v.x;
+                              Dq[k + 1] = v.y;
+                            }
+                        }
+                      else
+                        {
+#pragma unroll
+                          for (int k = 0; k < VO * VO; ++k)
+                            Dq[k] = rec[C::Q_D + k];
+                        }
+#pragma unroll
+                      for (int k = 0; k < VO; ++k)
+                        tq[k] = rec[C::Q_TAU + k];
+#pragma unroll
+                      for (int k = 0; k < DIM * DIM; ++k)
+                        Cq[k] = rec[C::Q_C + k];
+#pragma unroll
+                      for (int e = 0; e < DIM; ++e)
+                        dn[e] = sdN[(q * NPC + a) * DIM + e];
+                      double g[DIM];
 #pragma unroll
                       for (int l = 0; l < DIM; ++l)
                         {
                           double v = 0;
 #pragma unroll
                           for (int e = 0; e < DIM; ++e)
-                            v += sdN[(q * NPC + a) * DIM + e] * rec[C::Q_C + e * DIM + l];
+                            v += dn[e] * Cq[e * DIM + l];
                           g[l] = v;
                           sG[(ql * DIM + l) * NPCP + a] = v;
                         }
@@ -281,19 +351,33 @@ namespace gf
                       for (int ci = 0; ci < DIM; ++ci)
                         {
                           // engineering strain of dof (a,ci): eps_(ci,l) = g[l]
+                          double Tr[VO];
 #pragma unroll
                           for (int k = 0; k < VO; ++k)
                             {
                               double v = 0;
 #pragma unroll
                               for (int l = 0; l < DIM; ++l)
-                                v += g[l] * rec[C::Q_D + voigt_index<DIM>(ci, l) * VO + k];
-                              T[ci * VO + k] = v;
+                                v += g[l] * Dq[voigt_index<DIM>(ci, l) * VO + k];
+                              Tr[k] = v;
+                            }
+                          if constexpr ((VO % 2) == 0)
+                            {
+#pragma unroll
+                              for (int k = 0; k < VO; k += 2)
+                                *reinterpret_cast<double2 *>(T + ci * VO + k) =
+                                  make_double2(Tr[k], Tr[k + 1]);
+                            }
+                          else
+                            {
+#pragma unroll
+                              for (int k = 0; k < VO; ++k)
+                                T[ci * VO + k] = Tr[k];
                             }
                           double t = 0;
 #pragma unroll
                           for (int l = 0; l < DIM; ++l)
-                            t += rec[C::Q_TAU + voigt_index<DIM>(ci, l)] * g[l];
+                            t += tq[voigt_index<DIM>(ci, l)] * g[l];
                           T[DIM * VO + ci] = t;
                         }
                     }
