@@ -532,7 +532,51 @@ def main():
                 variants["spmv_kernel_kinds"] = dict(
                     kinds, what="GF_OPT_SPMV_KERNEL: stand-alone y = A x launches (no fused dot), "
                                 "bitwise equal results for all kinds")
+                h.set_option(capi.OPT_MG_MATRIX_PRECISION, 2)
+                for k in range(N_SUB):
+                    resident_pass(k)
+                s0 = solid.newton_solves
+                h0v = len(solid.history)
+                barrier()
+                h.event_record(2)
+                t0 = time.perf_counter()
+                for k in range(N_SUB):
+                    resident_pass(k)
+                h.event_record(3)
+                barrier()
+                tv = max(time.perf_counter() - t0, 1e-3 * h.event_elapsed_ms(2, 3))
+                ms32, bytes32 = h.spmv_timed(capi.MAT_MG_F32, 5)
+                variants["vcycle_all_fp32_operator"] = {
+                    "what": "GF_OPT_MG_MATRIX_PRECISION = 2: the V-cycle's operator applications in "
+                            "single precision throughout (FP32 matrix copy, x staged and accumulated "
+                            "in FP32; vectors in HBM, the CG operator, its residual test and the "
+                            "Newton tolerances stay FP64)",
+                    "value": n_dofs_global * (solid.newton_solves - s0) / tv, "unit": "DoFs/s",
+                    "steps": N_SUB, "newton_solves": solid.newton_solves - s0,
+                    "cg_iterations": cg_iterations(h0v), "operator_apply_ms": ms32,
+                    "operator_gbs": bytes32 / ms32 / 1e6}
                 h.set_option(capi.OPT_MG_MATRIX_PRECISION, args.mg_precision)
+                # "Solver type = Direct" (the shipped default, parameters.prm:43): the stand-in is
+                # the same CG from a zero guess to 1e-13 relative; its cost with the V-cycle
+                solid.parameters.type_lin = "Direct"
+                for k in range(N_SUB):
+                    resident_pass(k)
+                s0 = solid.newton_solves
+                barrier()
+                h.event_record(2)
+                t0 = time.perf_counter()
+                for k in range(N_SUB):
+                    resident_pass(k)
+                h.event_record(3)
+                barrier()
+                tv = max(time.perf_counter() - t0, 1e-3 * h.event_elapsed_ms(2, 3))
+                variants["direct_solver_stand_in"] = {
+                    "what": "type_lin = Direct: UMFPACK (nonlinear_elasticity.cc:1192-1200) is replaced "
+                            "by the multigrid-preconditioned CG run to 1e-13 relative from a zero guess",
+                    "value": n_dofs_global * (solid.newton_solves - s0) / tv, "unit": "DoFs/s",
+                    "steps": N_SUB, "newton_solves": solid.newton_solves - s0,
+                    "ms_per_newton_solve": 1e3 * tv / max(1, solid.newton_solves - s0)}
+                solid.parameters.type_lin = "CG"
                 for k in range(N_SUB):      # the run's operators again for the stand-alone SpMV timing
                     resident_pass(k)
         except Exception as exc:      # a failing side measurement must not cost the main line

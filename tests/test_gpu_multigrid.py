@@ -178,3 +178,32 @@ def test_attach_rejects_bad_hierarchies(libs):
     # levels may be destroyed in any order
     hc.close()
     hf.close()
+
+
+def test_better_initial_guess_keeps_the_newton_history_and_saves_cg_iterations(libs):
+    """GF_OPT_CG_INITIAL_GUESS: 0 = the reference's guess (previous newton_update,
+    nonlinear_elasticity.cc:1184), 1 (default) = the zero vector whenever its residual is smaller.
+    Same stopping criterion, so Newton counts and displacements agree within the solver tolerance;
+    the default needs clearly fewer CG iterations from the second Newton pass on."""
+    capi, solvers, mg = libs[:3]
+    p = nl_params(poly_degree=2, scenario="PF", type_lin="CG", delta_t=0.01, max_iterations_lin=1.0)
+    prob = make_problem(p, 3, reps=[4, 16, 4], numbering="lexicographic")
+    n = prob.n_iface_nodes
+    traction = lambda t, it: np.tile(np.array([1500.0, 0.0, 0.0]) * min(1.0, t / 0.02), n)
+    out = {}
+    for guess in (0, 1):
+        H = mg.Hierarchy(prob)
+        H.fine.set_option(capi.OPT_CG_INITIAL_GUESS, guess)
+        part = solvers.FakeParticipant(3, 2, p.delta_t, traction)
+        solid = solvers.Solid(prob, part, handle=H.fine)
+        solid.run()
+        out[guess] = ([[int(r[0]) for r in rows] for rows in solid.history],
+                      [d for (w, it, d) in part.written])
+        H.close()
+    assert [len(r) for r in out[0][0]] == [len(r) for r in out[1][0]]          # Newton counts
+    for a, b in zip(out[0][1], out[1][1]):
+        assert rel_err(a, b) < 1e-7
+    for ref, new in zip(out[0][0], out[1][0]):
+        assert new[0] == ref[0]                                                # first pass: same guess (zero)
+        assert all(x <= y for x, y in zip(new, ref))
+    assert sum(map(sum, out[1][0])) < 0.9 * sum(map(sum, out[0][0]))
