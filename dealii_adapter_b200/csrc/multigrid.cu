@@ -588,6 +588,47 @@ namespace gf
     f.mg.n_child = n_child;
     f.mg.parent.upload(parent.data(), parent.size(), s);
     f.mg.child_cells.upload(child_cells, size_t(co.n_cells) * n_child, s);
+    // ---- which directions does this level pair refine? Isotropic refinement (refine_global)
+    // halves every edge; a SEMI-COARSENED pair (the host halves only the even repetition counts
+    // to get below a large coarsest level) keeps some directions. Read off the geometry: edge
+    // length of a parent cell over that of one of its children, per reference direction.
+    bool refined[3] = {true, true, true};
+    {
+      int64_t pc0 = -1, fc0 = -1;
+      for (int64_t pc = 0; pc < co.n_cells && pc0 < 0; ++pc)
+        for (int k = 0; k < n_child; ++k)
+          if (child_cells[pc * n_child + k] >= 0)
+            {
+              pc0 = pc;
+              fc0 = child_cells[pc * n_child + k];
+              break;
+            }
+      GF_REQUIRE(pc0 >= 0, GF_ERR_INVALID_ARG, "no coarse cell has a local child");
+      const int gs = dim * dim + 1;
+      double    gc[10], gf_[10];
+      GF_CUDA_CHECK(cudaMemcpy(gc, co.geom.p + pc0 * gs, gs * sizeof(double), cudaMemcpyDeviceToHost));
+      GF_CUDA_CHECK(cudaMemcpy(gf_, f.geom.p + fc0 * gs, gs * sizeof(double), cudaMemcpyDeviceToHost));
+      // rows of J^-1 are the gradients of the reference coordinates: |row d| = 1 / edge length
+      for (int d = 0; d < dim; ++d)
+        {
+          double nc = 0, nf = 0;
+          for (int j = 0; j < dim; ++j)
+            {
+              nc += gc[d * dim + j] * gc[d * dim + j];
+              nf += gf_[d * dim + j] * gf_[d * dim + j];
+            }
+          refined[d] = std::sqrt(nf / nc) > 1.5;
+        }
+      int n_ref = 0;
+      for (int d = 0; d < dim; ++d)
+        n_ref += refined[d];
+      GF_REQUIRE(n_ref >= 1, GF_ERR_INVALID_ARG, "coarse level is not coarser than the fine level");
+      for (int64_t pc = 0; pc < co.n_cells; ++pc)
+        for (int k = 0; k < n_child; ++k)
+          for (int d = 0; d < dim; ++d)
+            GF_REQUIRE(refined[d] || !((k >> d) & 1) || child_cells[pc * n_child + k] < 0,
+                       GF_ERR_INVALID_ARG, "child index uses a direction that is not refined");
+    }
     // ---- embedding matrices: coarse shape functions at the nodes of child k ---------------------
     const std::vector<int> &lex = f.tables.local_lex;
     std::vector<double>     E(size_t(n_child) * npc * npc, 0.0);
@@ -598,7 +639,9 @@ namespace gf
             double w = 1.0;
             for (int d = 0; d < dim; ++d)
               {
-                const double xi = 0.5 * (double(lex[a * 3 + d]) / p + double((k >> d) & 1));
+                const double xi = refined[d] ?
+                                    0.5 * (double(lex[a * 3 + d]) / p + double((k >> d) & 1)) :
+                                    double(lex[a * 3 + d]) / p;
                 w *= lagrange1d(p, lex[b * 3 + d], xi);
               }
             E[(size_t(k) * npc + a) * npc + b] = std::fabs(w) < 1e-14 ? 0.0 : w;
@@ -618,8 +661,10 @@ namespace gf
                   // cell, in units of 1/(2p))
                   bool hi = false;
                   if (f.axis_dir >= 0)
-                    hi = lex[a * 3 + f.axis_dir] + p * ((k >> f.axis_dir) & 1) >
-                         2 * lex[b * 3 + f.axis_dir];
+                    hi = refined[f.axis_dir] ?
+                           lex[a * 3 + f.axis_dir] + p * ((k >> f.axis_dir) & 1) >
+                             2 * lex[b * 3 + f.axis_dir] :
+                           lex[a * 3 + f.axis_dir] > lex[b * 3 + f.axis_dir];
                   rl_ka.push_back((k * npc + a) | (hi ? (1 << 30) : 0));
                   rl_w.push_back(w);
                 }
@@ -629,6 +674,11 @@ namespace gf
         int k = 0, la[3] = {0, 0, 0};
         for (int d = 0; d < dim; ++d)
           {
+            if (!refined[d])
+              {
+                la[d] = lex[b * 3 + d];
+                continue;
+              }
             const int t  = 2 * lex[b * 3 + d];
             const int kd = t > p ? 1 : 0;
             k |= kd << d;

@@ -12,27 +12,45 @@ from . import capi
 from .problem import make_problem
 
 
-def coarsen_problem(problem):
-    """The next coarser level of `problem` (every direction halved) or None if a repetition is odd."""
+# A coarsest level larger than this is semi-coarsened further (only the directions with an even
+# repetition count are halved). Every rank solves the coarsest level redundantly, and beyond ~2 k
+# nodes its Chebyshev(80) no longer fits the single-launch solver's shared-memory staging: on the
+# 8-GPU weak-scaling mesh (24x288x96 -> 3x36x12 = 12,775 nodes) it cost 1.9 ms per V-cycle.
+SEMI_COARSEN_ABOVE_NODES = 3000
+
+
+def coarsen_problem(problem, allow_semi=True):
+    """The next coarser level of `problem`: every direction halved (what refine_global undoes) while
+    all repetition counts are even; else, if the level is still large, the even directions only
+    (semi-coarsening); None when nothing can or needs to be coarsened."""
     mesh = problem.mesh
-    if any(r % 2 for r in mesh.reps) or min(mesh.reps) < 2:
+    even = [r % 2 == 0 and r >= 2 for r in mesh.reps]
+    if all(even):
+        reps = [r // 2 for r in mesh.reps]
+    elif allow_semi and any(even) and mesh.n_nodes > SEMI_COARSEN_ABOVE_NODES:
+        reps = [r // 2 if e else r for r, e in zip(mesh.reps, even)]
+    else:
         return None
-    reps = [r // 2 for r in mesh.reps]
     return make_problem(problem.params, problem.dim, reps=reps, numbering=mesh.numbering,
                         box=(mesh.p0, mesh.p1))
 
 
 def child_table(coarse_mesh, fine_mesh):
-    """[n_coarse_cells, 2^dim] GLOBAL fine cell index of child k (cells are lexicographic)."""
+    """[n_coarse_cells, 2^dim] GLOBAL fine cell index of child k = kx + 2 ky + 4 kz (cells are
+    lexicographic); -1 where the level pair does not refine that direction."""
     dim = coarse_mesh.dim
     rc = list(coarse_mesh.reps) + [1] * (3 - dim)
     rf = list(fine_mesh.reps) + [1] * (3 - dim)
+    fac = [f // c for f, c in zip(rf, rc)]                   # 2 (refined) or 1 per direction
+    assert all(x in (1, 2) for x in fac) and [c * x for c, x in zip(rc, fac)] == rf
     k, j, i = np.meshgrid(np.arange(rc[2]), np.arange(rc[1]), np.arange(rc[0]), indexing="ij")
     i, j, k = i.reshape(-1), j.reshape(-1), k.reshape(-1)   # coarse cell index = (k*ry + j)*rx + i
-    out = np.zeros((len(i), 1 << dim), dtype=np.int64)
+    out = -np.ones((len(i), 1 << dim), dtype=np.int64)
     for c in range(1 << dim):
-        fi, fj = 2 * i + (c & 1), 2 * j + ((c >> 1) & 1)
-        fk = 2 * k + ((c >> 2) & 1) if dim == 3 else k
+        bits = [c & 1, (c >> 1) & 1, (c >> 2) & 1]
+        if any(b and fac[d] == 1 for d, b in enumerate(bits)):
+            continue
+        fi, fj, fk = fac[0] * i + bits[0], fac[1] * j + bits[1], fac[2] * k + bits[2]
         out[:, c] = (fk * rf[1] + fj) * rf[0] + fi
     return out
 
@@ -85,7 +103,8 @@ class Hierarchy:
                 g2l = -np.ones(fine.mesh.n_cells, dtype=np.int64)
                 g2l[pf.local_cell_global] = np.arange(pf.n_local_cells)
                 # replicated coarse level: all coarse cells, children that are not local -> -1
-                tab = g2l[tab[pc.local_cell_global]] if pc is not None else g2l[tab]
+                sel = tab[pc.local_cell_global] if pc is not None else tab
+                tab = np.where(sel >= 0, g2l[np.maximum(sel, 0)], -1)
                 covered = np.zeros(pf.n_local_cells, dtype=bool)
                 covered[tab[tab >= 0]] = True
                 if not covered.all():

@@ -207,3 +207,44 @@ def test_better_initial_guess_keeps_the_newton_history_and_saves_cg_iterations(l
         assert new[0] == ref[0]                                                # first pass: same guess (zero)
         assert all(x <= y for x, y in zip(new, ref))
     assert sum(map(sum, out[1][0])) < 0.9 * sum(map(sum, out[0][0]))
+
+
+def test_semi_coarsened_levels_below_a_large_coarsest_level(libs):
+    """Repetitions 3 x 36 x 12 cannot be halved isotropically (3 is odd) and the level has 12,775
+    nodes - the host hierarchy then halves the even directions only (3x18x6, 3x9x3) and
+    gf_mg_attach reads the refined directions off the cell geometry. The V-cycle must stay a
+    symmetric positive definite preconditioner, CG must need few iterations, and the Newton run
+    must agree with the block-Jacobi CG on the same mesh."""
+    capi, solvers, mg = libs[:3]
+    p = nl_params(poly_degree=2, scenario="PF", type_lin="CG", delta_t=0.01, max_iterations_lin=1.0,
+                  tol_lin=1e-8)
+    prob = make_problem(p, 3, reps=[3, 36, 12], numbering="lexicographic")
+    H = mg.Hierarchy(prob)
+    assert [q.mesh.reps for q in H.problems] == [[3, 36, 12], [3, 18, 6], [3, 9, 3]]
+    n = prob.n_iface_nodes
+    buf = np.tile([1500.0, 0.0, 50.0], n)
+    out = {}
+    for use_mg in (True, False):
+        h = H.fine if use_mg else capi.Handle(prob)
+        part = solvers.FakeParticipant(3, 1, p.delta_t, lambda t, it: buf)
+        solid = solvers.Solid(prob, part, handle=h)
+        solid.run()
+        out[use_mg] = ([[int(r[0]) for r in rows] for rows in solid.history], part.written[0][2])
+        if use_mg:
+            # symmetry of the V-cycle: x . M y == y . M x
+            rng = np.random.RandomState(1)
+            free = prob.constrained == 0
+            x, y = rng.uniform(-1, 1, prob.n_dofs) * free, rng.uniform(-1, 1, prob.n_dofs) * free
+            h.set_vector(capi.VEC_SCRATCH0, x)
+            h.mg_vcycle(capi.VEC_SCRATCH0, capi.VEC_SCRATCH1)
+            Mx = h.get_vector(capi.VEC_SCRATCH1)
+            h.set_vector(capi.VEC_SCRATCH0, y)
+            h.mg_vcycle(capi.VEC_SCRATCH0, capi.VEC_SCRATCH1)
+            My = h.get_vector(capi.VEC_SCRATCH1)
+            assert abs(x @ My - y @ Mx) <= 1e-10 * abs(x @ Mx) and x @ Mx > 0
+        else:
+            h.close()
+    H.close()
+    assert [len(r) for r in out[True][0]] == [len(r) for r in out[False][0]]
+    assert max(map(max, out[True][0])) <= 40 < min(map(min, out[False][0]))
+    assert rel_err(out[True][1], out[False][1]) < 1e-7

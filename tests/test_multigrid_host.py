@@ -87,3 +87,27 @@ def test_level_plan_for_partitioned_runs_replicates_the_small_levels(native_libs
     for w in (2, 3, 4, 8):
         _, rep = mg.plan_levels(prob, world=w, axis=1)
         assert rep == sorted(rep)
+
+
+def test_semi_coarsening_below_a_large_level_with_an_odd_repetition(native_libs):
+    """3 x 36 x 12 (12,775 Q2 nodes) cannot be halved in x: the even directions are halved alone
+    until the level is small; children along the unrefined direction do not exist (-1)."""
+    p = nl_params(poly_degree=2)
+    fine = make_problem(p, 3, reps=[3, 36, 12], numbering="lexicographic")
+    problems, replicated = mg.plan_levels(fine)
+    assert [q.mesh.reps for q in problems] == [[3, 36, 12], [3, 18, 6], [3, 9, 3]]
+    assert mg.coarsen_problem(problems[1], allow_semi=False) is None
+    tab = mg.child_table(problems[1].mesh, fine.mesh)
+    assert tab.shape == (3 * 18 * 6, 8)
+    assert np.all(tab[:, 1::2] == -1)                               # kx = 1 children do not exist
+    assert sorted(tab[:, 0::2].reshape(-1)) == list(range(fine.mesh.n_cells))
+    fv = fine.mesh.cell_vertices.reshape(-1, 8, 3)
+    cv = problems[1].mesh.cell_vertices.reshape(-1, 8, 3)
+    for pc in (0, 17, 200):
+        for k in (0, 2, 4, 6):
+            lo, hi = fv[tab[pc, k], 0], fv[tab[pc, k], 7]
+            assert np.all(lo >= cv[pc, 0] - 1e-12) and np.all(hi <= cv[pc, 7] + 1e-12)
+            assert np.isclose(hi[0] - lo[0], cv[pc, 7][0] - cv[pc, 0][0])      # full width in x
+    # small meshes keep the round-1 behaviour: no semi-coarsening below the threshold
+    small = make_problem(p, 3, reps=[3, 18, 3], numbering="lexicographic")
+    assert mg.coarsen_problem(small) is None
