@@ -97,9 +97,12 @@ namespace gf
       static constexpr int OFF_ACC = OFF_U + DPC;
       static constexpr int OFF_Q   = OFF_ACC + DPC;          // [NQ][QS]
       static constexpr int OFF_T   = OFF_Q + NQ * QS;            // 2 x [QC][NPC][TS]
-      static constexpr int OFF_G   = OFF_T + 2 * QC * NPC * TS;  // 2 x [QC][DIM][NPCP]
-      static constexpr int OFF_BAR = OFF_G + 2 * QC * DIM * NPCP; // 4 mbarriers
-      static constexpr int SMEM_D  = OFF_BAR + 4;
+      // ring depth: 3 buffers for 3D Q2 (218 KB of shared memory): the producers may run 24
+      // q-points ahead, which covers phase A of the next cell
+      static constexpr int NB      = (DIM == 3 && P == 2) ? 3 : 2;
+      static constexpr int OFF_G   = OFF_T + NB * QC * NPC * TS;  // NB x [QC][DIM][NPCP]
+      static constexpr int OFF_BAR = OFF_G + NB * QC * DIM * NPCP; // 2 NB mbarriers
+      static constexpr int SMEM_D  = OFF_BAR + 2 * NB;
       static_assert(SMEM_D * 8 <= 227 * 1024, "shared memory budget");
       static constexpr size_t SMEM_BYTES = size_t(SMEM_D) * sizeof(double);
       // offsets inside a per-q record
@@ -129,7 +132,7 @@ namespace gf
       double *sN = sm + C::OFF_N, *sdN = sm + C::OFF_DN, *su = sm + C::OFF_U,
              *sacc = sm + C::OFF_ACC, *sQ = sm + C::OFF_Q;
       uint64_t *bars = reinterpret_cast<uint64_t *>(sm + C::OFF_BAR);
-      uint64_t *full = bars, *empty = bars + 2; // per T/G buffer
+      uint64_t *full = bars, *empty = bars + C::NB; // per T/G buffer
       const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
       for (int i = tid; i < NQ * NPC; i += C::NT)
         sN[i] = tabN[i];
@@ -137,7 +140,7 @@ namespace gf
         sdN[i] = tabdN[i];
       if (tid == 0)
         {
-          for (int k = 0; k < 2; ++k)
+          for (int k = 0; k < C::NB; ++k)
             {
               mbar_init(smem_u32(&full[k]), C::NPW);  // one arrive per producer warp
               mbar_init(smem_u32(&empty[k]), C::NW);  // one arrive per consumer warp
@@ -294,11 +297,11 @@ namespace gf
                 r_i[k] = 0;
               for (int qc = 0; qc < NQ; qc += QC, ++it)
                 {
-                  const int buf = it & 1;
+                  const int buf = it % C::NB;
                   double *  sT  = sm + C::OFF_T + buf * (QC * NPC * TS);
                   double *  sG  = sm + C::OFF_G + buf * (QC * DIM * NPCP);
-                  if (it >= 2) // the consumers released this buffer (chunk it - 2)
-                    mbar_wait(smem_u32(&empty[buf]), ((it >> 1) - 1) & 1);
+                  if (it >= C::NB) // the consumers released this buffer (chunk it - NB)
+                    mbar_wait(smem_u32(&empty[buf]), ((it / C::NB) - 1) & 1);
                   // ---------- phase B: g_a, T_a = B_a^T (JxW D), t_a = JxW tau g_a -------------
                   for (int item = ptid; item < QC * NPC; item += NPT)
                     {
@@ -455,10 +458,10 @@ namespace gf
                   }
               for (int qc = 0; qc < NQ; qc += QC, ++it)
                 {
-                  const int     buf = it & 1;
+                  const int     buf = it % C::NB;
                   const double *sT  = sm + C::OFF_T + buf * (QC * NPC * TS);
                   const double *sG  = sm + C::OFF_G + buf * (QC * DIM * NPCP);
-                  mbar_wait(smem_u32(&full[buf]), (it >> 1) & 1);
+                  mbar_wait(smem_u32(&full[buf]), (it / C::NB) & 1);
                   if (unit_active)
                     {
 #pragma unroll 2

@@ -27,7 +27,9 @@
 //   0  (default) kind 6 for every launch, with and without the fused dot product.
 //   1  spmv_kernel (LDG): one warp per row with streaming loads; also the fallback when a row
 //      does not fit a tile.
-// The fused dot product needs only gridDim.x partial sums (fixed order => reproducible).
+// (The kernels still carry a DOT template parameter: a fused x . A x with one partial per CTA. The
+// CG stopped using it in round 2 - partial sums per CTA depend on the partition - and DOT = true
+// is no longer instantiated.)
 //
 // Value type VT: double for every operator application whose result the reference defines (CG
 // vmult, assemble_rhs vmults). VT = float streams a single-precision COPY of the same array
@@ -812,65 +814,35 @@ namespace gf
     const int64_t n_rows = c.n_owned_nodes;
     if (n_rows == 0)
       return;
-    const int *st   = dot_partials ? &c.cg_scalars.p->status : nullptr;
-    const int  kind = effective_kind(c, dot_partials != nullptr);
+    // the CG's dot products are chunked reductions (reduce.cuh) since round 2: the fused variants
+    // summed per CTA, i.e. partition dependent, and are no longer instantiated
+    GF_REQUIRE(dot_partials == nullptr, GF_ERR_INVALID_ARG, "fused dot product is not available");
+    const int kind = effective_kind(c, false);
     if (c.n_tiles > 0 && (kind == 3 || kind == 6))
       {
         if (c.dim == 3)
-          {
-            if (dot_partials)
-              launch_tma2_t<3, true, double>(c, kind, val, x, y, dot_partials, st);
-            else
-              launch_tma2_t<3, false, double>(c, kind, val, x, y, nullptr, nullptr);
-          }
+          launch_tma2_t<3, false, double>(c, kind, val, x, y, nullptr, nullptr);
         else
-          {
-            if (dot_partials)
-              launch_tma2_t<2, true, double>(c, kind, val, x, y, dot_partials, st);
-            else
-              launch_tma2_t<2, false, double>(c, kind, val, x, y, nullptr, nullptr);
-          }
+          launch_tma2_t<2, false, double>(c, kind, val, x, y, nullptr, nullptr);
         GF_CUDA_CHECK(cudaGetLastError());
         return;
       }
     if (c.n_tiles > 0 && kind == 5)
       {
         if (c.dim == 3)
-          {
-            if (dot_partials)
-              launch_tma_t<3, true, double>(c, val, x, y, dot_partials, st);
-            else
-              launch_tma_t<3, false, double>(c, val, x, y, nullptr, nullptr);
-          }
+          launch_tma_t<3, false, double>(c, val, x, y, nullptr, nullptr);
         else
-          {
-            if (dot_partials)
-              launch_tma_t<2, true, double>(c, val, x, y, dot_partials, st);
-            else
-              launch_tma_t<2, false, double>(c, val, x, y, nullptr, nullptr);
-          }
+          launch_tma_t<2, false, double>(c, val, x, y, nullptr, nullptr);
         GF_CUDA_CHECK(cudaGetLastError());
         return;
       }
     const int grid = spmv_dot_partials(c);
     if (c.dim == 3)
-      {
-        if (dot_partials)
-          spmv_kernel<3, true, double><<<grid, SPMV_THREADS, 0, c.stream>>>(
-            n_rows, c.brow_ptr.p, c.val_ptr.p, c.bcol.p, val, x, y, dot_partials, st);
-        else
-          spmv_kernel<3, false, double><<<grid, SPMV_THREADS, 0, c.stream>>>(
-            n_rows, c.brow_ptr.p, c.val_ptr.p, c.bcol.p, val, x, y, nullptr, nullptr);
-      }
+      spmv_kernel<3, false, double><<<grid, SPMV_THREADS, 0, c.stream>>>(
+        n_rows, c.brow_ptr.p, c.val_ptr.p, c.bcol.p, val, x, y, nullptr, nullptr);
     else
-      {
-        if (dot_partials)
-          spmv_kernel<2, true, double><<<grid, SPMV_THREADS, 0, c.stream>>>(
-            n_rows, c.brow_ptr.p, c.val_ptr.p, c.bcol.p, val, x, y, dot_partials, st);
-        else
-          spmv_kernel<2, false, double><<<grid, SPMV_THREADS, 0, c.stream>>>(
-            n_rows, c.brow_ptr.p, c.val_ptr.p, c.bcol.p, val, x, y, nullptr, nullptr);
-      }
+      spmv_kernel<2, false, double><<<grid, SPMV_THREADS, 0, c.stream>>>(
+        n_rows, c.brow_ptr.p, c.val_ptr.p, c.bcol.p, val, x, y, nullptr, nullptr);
     GF_CUDA_CHECK(cudaGetLastError());
   }
 

@@ -84,9 +84,10 @@ def test_two_ring_kernel_reproduces_a_coupled_run_bit_for_bit(libs):
         assert np.array_equal(out[0, prec][1], out[6, prec][1])
 
 
-def test_sixteen_consumer_warps_with_fused_dot(libs):
-    """Kinds 3 / 6 (= the default) against the single-ring kernel: the dot partials are summed over
-    16 instead of 8 warps, so the CG history may differ in the last bits but nothing else may."""
+def test_kernel_kinds_keep_cg_counts_and_displacements(libs):
+    """Kinds 3 / 6 (= the default) against the single-ring kernel in whole coupled runs: y = A x is
+    bitwise the same and the dot products are kernel-independent chunked reductions, so the CG
+    history must agree (iteration counts exactly, displacements to rounding)."""
     capi, solvers, mg = libs
     p = nl_params(poly_degree=2, scenario="PF", type_lin="CG", delta_t=0.01,
                   max_iterations_lin=1.0)
