@@ -39,8 +39,30 @@ namespace
                GF_ERR_INVALID_ARG, "vector id not available for this model");
     return c.vec[which].p;
   }
+  // Deferred half of assemble_system. The reference assembles tangent AND residual in every
+  // Newton pass, also in the last one, where the convergence test (:459-463) only needs the
+  // residual and no solve follows. gf_nl_newton_assemble therefore runs the cell kernel (element
+  // matrices + residual) and stops; scattering K_e into the matrix, the block-Jacobi inverse and
+  // the multigrid re-discretisation happen here, on the first use of the tangent - the solve, or
+  // an export / vmult. The element buffer keeps the K_e of the whole mesh until then (single
+  // chunk on every rank: agreed at gf_create, since the multigrid update is collective).
+  void finish_tangent(gf_context &c)
+  {
+    if (!c.tangent_pending)
+      return;
+    c.tangent_pending = false;
+    double *K = c.mat[GF_MAT_TANGENT].val.p;
+    gf::launch_scatter_matrix(c, K, 0, c.n_cells, true, true);
+    c.mat[GF_MAT_TANGENT].valid = true;
+    gf::launch_build_precond(c, K);
+    if (gf::mg_active(c))
+      gf::mg_update_operators(c, c.tmp0.p); // coarse tangents at the injected state + smoothers
+  }
+
   double *mat_ptr(gf_context &c, int which)
   {
+    if (which == GF_MAT_TANGENT)
+      finish_tangent(c);
     GF_REQUIRE(which >= 0 && which < gf::N_MATRICES && which != GF_MAT_MASS &&
                  c.mat[which].val.p != nullptr,
                GF_ERR_INVALID_ARG, "matrix id not available for this model");
@@ -336,6 +358,23 @@ extern "C"
             c->n_global_dofs_for_maxit = int64_t(*c->h_norm + 0.5);
           }
         gf::build_reduction_plan(*c); // chunk size is a function of the GLOBAL size
+        // deferred tangent completion needs the K_e of the whole mesh in ONE chunk on every rank
+        {
+          double multi = c->ke_chunk_cells < c->n_cells ? 1.0 : 0.0;
+          if (c->comm)
+            {
+              *c->h_norm = multi;
+              GF_CUDA_CHECK(cudaMemcpyAsync(c->norm_out.p, c->h_norm, sizeof(double),
+                                            cudaMemcpyHostToDevice, c->stream));
+              gf::allreduce_sum(*c, c->norm_out.p, 1);
+              GF_CUDA_CHECK(cudaMemcpyAsync(c->h_norm, c->norm_out.p, sizeof(double),
+                                            cudaMemcpyDeviceToHost, c->stream));
+              GF_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+              multi = *c->h_norm;
+            }
+          c->defer_tangent = c->model == GF_MODEL_NEO_HOOKEAN && multi < 0.5 &&
+                             getenv("GF_NO_DEFERRED_TANGENT") == nullptr;
+        }
         // the pointers inside desc are caller-owned: never dereference them after create
         c->desc.cell_dofs = nullptr;
         c->desc.cell_vertices = nullptr;
@@ -435,6 +474,7 @@ extern "C"
               {
                 c.mf_valid                     = false; // re-assemble before the next solve
                 c.mat[GF_MAT_TANGENT].valid    = false;
+                c.tangent_pending              = false;
               }
             c.operator_kind = int(value);
             break;
@@ -500,6 +540,7 @@ extern "C"
     return guarded(h, [&](gf_context &c) {
       double *b = vec_ptr(c, which_b), *x = vec_ptr(c, which_x);
       GF_REQUIRE(b != x, GF_ERR_INVALID_ARG, "b and x must differ");
+      finish_tangent(c);
       GF_REQUIRE(c.mg.coarse != nullptr && c.mg_ops_valid, GF_ERR_INVALID_ARG,
                  "multigrid hierarchy not attached / operators not assembled");
       gf::mg_vcycle(c, b, x);
@@ -602,25 +643,38 @@ extern "C"
       gf::vec_axpby(c, c.tmp0.p, 1.0, c.vec[GF_NL_SOLUTION_DELTA].p, 1.0);
       GF_CUDA_CHECK(cudaMemsetAsync(c.err_flag.p, 0, sizeof(int), c.stream));
       double *K = c.mat[GF_MAT_TANGENT].val.p;
+      c.tangent_pending = false;
       if (c.operator_kind == 1)
         // matrix-free: quadrature-point data, r_e and the diagonal blocks; no element matrices
         gf::mf_setup(c, c.tmp0.p, c.vec[GF_NL_ACCELERATION].p);
       else
         {
-          for (int64_t c0 = 0; c0 < c.n_cells; c0 += c.ke_chunk_cells)
+          if (c.defer_tangent)
             {
-              const int64_t c1 = std::min(c.n_cells, c0 + c.ke_chunk_cells);
-              gf::launch_nl_cells(c, c.tmp0.p, c.vec[GF_NL_ACCELERATION].p, c0, c1);
-              gf::launch_scatter_matrix(c, K, c0, c1, c0 == 0, true);
+              gf::launch_nl_cells(c, c.tmp0.p, c.vec[GF_NL_ACCELERATION].p, 0, c.n_cells);
+              c.mat[GF_MAT_TANGENT].valid = false;
+              c.tangent_pending           = true; // finish_tangent() on first use
             }
-          c.mat[GF_MAT_TANGENT].valid = true;
+          else
+            {
+              for (int64_t c0 = 0; c0 < c.n_cells; c0 += c.ke_chunk_cells)
+                {
+                  const int64_t c1 = std::min(c.n_cells, c0 + c.ke_chunk_cells);
+                  gf::launch_nl_cells(c, c.tmp0.p, c.vec[GF_NL_ACCELERATION].p, c0, c1);
+                  gf::launch_scatter_matrix(c, K, c0, c1, c0 == 0, true);
+                }
+              c.mat[GF_MAT_TANGENT].valid = true;
+            }
         }
       gf::launch_nl_faces(c, c.tmp0.p, c.vec[GF_NL_EXTERNAL_STRESS].p);
       gf::launch_scatter_rhs(c, c.vec[GF_NL_SYSTEM_RHS].p, true);
-      if (c.operator_kind == 0)
-        gf::launch_build_precond(c, K);
-      if (gf::mg_active(c))
-        gf::mg_update_operators(c, c.tmp0.p); // coarse tangents at the injected state + smoothers
+      if (!c.tangent_pending)
+        {
+          if (c.operator_kind == 0)
+            gf::launch_build_precond(c, K);
+          if (gf::mg_active(c))
+            gf::mg_update_operators(c, c.tmp0.p); // coarse tangents at the injected state + smoothers
+        }
       const double r = gf::vec_masked_norm(c, c.vec[GF_NL_SYSTEM_RHS].p, true); // :449
       GF_CUDA_CHECK(
         cudaMemcpyAsync(c.h_err, c.err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
@@ -652,6 +706,7 @@ extern "C"
       GF_REQUIRE(c.model == GF_MODEL_NEO_HOOKEAN, GF_ERR_INVALID_ARG, "not a neo-Hookean handle");
       GF_REQUIRE(type_lin == 0 || type_lin == 1, GF_ERR_INVALID_ARG,
                  "Linear solver type not implemented");
+      finish_tangent(c); // scatter + preconditioner + multigrid update of the last assembly
       double * x   = c.vec[GF_NL_NEWTON_UPDATE].p;
       uint32_t it  = 0;
       double   res = 0;
@@ -993,6 +1048,7 @@ extern "C"
     return guarded(h, [&](gf_context &c) {
       double *x = vec_ptr(c, which_x), *y = vec_ptr(c, which_y);
       GF_REQUIRE(x != y, GF_ERR_INVALID_ARG, "x and y must differ");
+      finish_tangent(c);
       if (c.comm)
         gf::halo_exchange(c, x);
       if (which_matrix == GF_MAT_MASS)
@@ -1024,6 +1080,7 @@ extern "C"
   {
     return guarded(h, [&](gf_context &c) {
       GF_REQUIRE(n_reps >= 1, GF_ERR_INVALID_ARG, "n_reps must be >= 1");
+      finish_tangent(c);
       const bool f32 = which_matrix == GF_MAT_MG_F32;
       GF_REQUIRE(!f32 || c.mg_val32_valid, GF_ERR_INVALID_ARG,
                  "no FP32 operator copy (GF_OPT_MG_MATRIX_PRECISION = 1, then assemble)");

@@ -313,6 +313,8 @@ struct gf_context
   int  cg_initial_guess = 1; // GF_OPT_CG_INITIAL_GUESS
   int  operator_kind  = 0;
   bool lin_assembled  = false;
+  bool defer_tangent  = false; // scatter / preconditioner / multigrid update on first use
+  bool tangent_pending = false; // K_e of the last assembly not yet scattered (api.cu)
 
   // partition-independent reductions (pattern.cu, reduce.cu): owned nodes are grouped into node
   // planes orthogonal to the slab axis (contiguous in the internal numbering) and into chunks of

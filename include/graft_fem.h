@@ -259,7 +259,12 @@ extern "C"
   int gf_nl_begin_step(gf_handle h);
   /* one Newton pass up to the convergence test: update_acceleration (:444), assemble_system
    * (:446 -> :1044-1087, cell kernel :872-1036, Neumann :791-859, constrained scatter :760-774),
-   * get_error_residual (:449 -> :549-560). *res_abs = error_residual.u */
+   * get_error_residual (:449 -> :549-560). *res_abs = error_residual.u
+   * The element matrices and the residual are computed here; SCATTERING the element matrices
+   * into tangent_matrix, the preconditioner and the multigrid re-discretisation are completed on
+   * the first use of the tangent (gf_nl_newton_solve, gf_export_*, gf_spmv): the reference also
+   * assembles the tangent in the LAST Newton pass, where the convergence test (:459-463) ends the
+   * loop without a solve - that completion work is then never done. */
   int gf_nl_newton_assemble(gf_handle h, double *res_abs);
   /* solve_linear_system (:473 -> :1153-1211): CG with tol = tol_lin*||rhs||, at most
    * n_dofs*max_iterations_lin steps, initial guess = previous newton_update; distribute (:1208);
