@@ -20,8 +20,10 @@ for k in range(8):
     s.step()
 h.state_save()                  # every configuration starts from the same state
 rows = []
-configs = [(3, 20, 40), (2, 40, 40), (2, 80, 40), (2, 40, 80), (2, 80, 80), (1, 20, 40), (1, 40, 40),
-           (1, 80, 40), (1, 40, 80), (2, 30, 60), (3, 40, 40), (3, 20, 80), (2, 160, 40)]
+configs = [(3, 40, 80), (3, 40, 60), (3, 40, 40), (3, 40, 30), (3, 20, 60), (3, 30, 60), (3, 60, 60),
+           (2, 30, 60), (2, 40, 80), (4, 40, 60), (4, 60, 60), (3, 40, 80)]
+if os.environ.get("GF_SWEEP_CONFIGS"):
+    configs = [tuple(int(x) for x in c.split(",")) for c in os.environ["GF_SWEEP_CONFIGS"].split(";")]
 for deg, ratio, cdeg in configs:
     h.set_option(capi.OPT_MG_SMOOTHER_DEGREE, deg)
     h.set_option(capi.OPT_MG_SMOOTHER_RATIO, ratio)
