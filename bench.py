@@ -54,6 +54,7 @@ CPU_SAMPLE_REPS = {"reference": (4, 24, 4), "baseline": (6, 36, 6)}
 TRACTION = (2000.0, 0.0, 0.0)
 N_SUB = 2
 CFG4_REPS = (128, 1024, 128)   # BASELINE configs[3]: linear Q1 cantilever, 51,171,075 DoFs
+STRONG_TIMEOUT_S = 480         # watchdog of the cfg4 part (normally ~40 s incl. set-up)
 
 
 def params():
@@ -282,6 +283,22 @@ def run_cfg4(args, world, rank, local_rank, comm, dist, torch):
 
 
 _REAL_STDOUT = None
+
+
+def arm_watchdog(seconds, on_timeout):
+    """The side measurements after the main regions (cfg4 strong scaling) must never cost the
+    main line: if they have not finished after `seconds`, rank 0 emits the line it has and every
+    rank leaves. Returns the function that disarms it."""
+    done = threading.Event()
+
+    def run():
+        if not done.wait(seconds):
+            try:
+                on_timeout()
+            finally:
+                os._exit(0)
+    threading.Thread(target=run, daemon=True).start()
+    return done.set
 
 
 def emit(line):
@@ -661,10 +678,16 @@ def main():
         h.close()
     # ---- north_star's multi-GPU target in the same driver-run line: cfg4, STRONG scaling -------
     if not args.no_strong and os.environ.get("GF_PROFILE_RUN") != "1" and args.precond == "mg":
+        def give_up():
+            if rank == 0:
+                line["strong_scaling"] = {"error": "did not finish within %d s" % STRONG_TIMEOUT_S}
+                emit(line)
+        disarm = arm_watchdog(STRONG_TIMEOUT_S, give_up)
         try:
             strong = run_cfg4(args, world, rank, local_rank, comm, dist, torch)
         except Exception as exc:      # must not cost the main line
             strong = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        disarm()
         if rank == 0:
             line["strong_scaling"] = strong
     if rank == 0:

@@ -46,7 +46,12 @@ namespace
   // the multigrid re-discretisation happen here, on the first use of the tangent - the solve, or
   // an export / vmult. The element buffer keeps the K_e of the whole mesh until then (single
   // chunk on every rank: agreed at gf_create, since the multigrid update is collective).
-  void finish_tangent(gf_context &c)
+  // Two halves, because the second one is COLLECTIVE on a partitioned handle (halo exchanges and
+  // reductions of the coarse levels) and must only run inside entry points that every rank calls:
+  //   finish_tangent_local  scatter + block-Jacobi inverse: rank-local, legal anywhere (a single
+  //                         rank may export rows or time the SpMV of its own matrix)
+  //   finish_tangent        + multigrid update: gf_nl_newton_solve / gf_mg_vcycle only
+  void finish_tangent_local(gf_context &c)
   {
     if (!c.tangent_pending)
       return;
@@ -55,14 +60,22 @@ namespace
     gf::launch_scatter_matrix(c, K, 0, c.n_cells, true, true);
     c.mat[GF_MAT_TANGENT].valid = true;
     gf::launch_build_precond(c, K);
-    if (gf::mg_active(c))
-      gf::mg_update_operators(c, c.tmp0.p); // coarse tangents at the injected state + smoothers
+    c.mg_update_pending = gf::mg_active(c);
+  }
+  void finish_tangent(gf_context &c)
+  {
+    finish_tangent_local(c);
+    if (c.mg_update_pending)
+      {
+        c.mg_update_pending = false;
+        gf::mg_update_operators(c, c.tmp0.p); // coarse tangents at the injected state + smoothers
+      }
   }
 
   double *mat_ptr(gf_context &c, int which)
   {
     if (which == GF_MAT_TANGENT)
-      finish_tangent(c);
+      finish_tangent_local(c);
     GF_REQUIRE(which >= 0 && which < gf::N_MATRICES && which != GF_MAT_MASS &&
                  c.mat[which].val.p != nullptr,
                GF_ERR_INVALID_ARG, "matrix id not available for this model");
@@ -475,6 +488,7 @@ extern "C"
                 c.mf_valid                     = false; // re-assemble before the next solve
                 c.mat[GF_MAT_TANGENT].valid    = false;
                 c.tangent_pending              = false;
+                c.mg_update_pending            = false;
               }
             c.operator_kind = int(value);
             break;
@@ -643,7 +657,8 @@ extern "C"
       gf::vec_axpby(c, c.tmp0.p, 1.0, c.vec[GF_NL_SOLUTION_DELTA].p, 1.0);
       GF_CUDA_CHECK(cudaMemsetAsync(c.err_flag.p, 0, sizeof(int), c.stream));
       double *K = c.mat[GF_MAT_TANGENT].val.p;
-      c.tangent_pending = false;
+      c.tangent_pending   = false;
+      c.mg_update_pending = false;
       if (c.operator_kind == 1)
         // matrix-free: quadrature-point data, r_e and the diagonal blocks; no element matrices
         gf::mf_setup(c, c.tmp0.p, c.vec[GF_NL_ACCELERATION].p);
@@ -1048,7 +1063,10 @@ extern "C"
     return guarded(h, [&](gf_context &c) {
       double *x = vec_ptr(c, which_x), *y = vec_ptr(c, which_y);
       GF_REQUIRE(x != y, GF_ERR_INVALID_ARG, "x and y must differ");
-      finish_tangent(c);
+      finish_tangent_local(c);
+      if (which_matrix == GF_MAT_MG_F32 && (c.mg_update_pending || !c.mg_val32_valid))
+        gf::mg_refresh_f32_level(c); // this level's FP32 copy follows the matrix (rank-local);
+                                     // the coarse levels follow with the multigrid update
       if (c.comm)
         gf::halo_exchange(c, x);
       if (which_matrix == GF_MAT_MASS)
@@ -1080,7 +1098,9 @@ extern "C"
   {
     return guarded(h, [&](gf_context &c) {
       GF_REQUIRE(n_reps >= 1, GF_ERR_INVALID_ARG, "n_reps must be >= 1");
-      finish_tangent(c);
+      finish_tangent_local(c); // rank-local: bench.py times the SpMV on rank 0 only
+      if (which_matrix == GF_MAT_MG_F32 && (c.mg_update_pending || !c.mg_val32_valid))
+        gf::mg_refresh_f32_level(c);
       const bool f32 = which_matrix == GF_MAT_MG_F32;
       GF_REQUIRE(!f32 || c.mg_val32_valid, GF_ERR_INVALID_ARG,
                  "no FP32 operator copy (GF_OPT_MG_MATRIX_PRECISION = 1, then assemble)");

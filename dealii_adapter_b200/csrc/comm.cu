@@ -158,6 +158,10 @@ namespace gf
     {
       if (ld_acquire_sys(flag) >= epoch)
         return;
+      // sticky: once one wait has timed out every later wait returns at once, so the error
+      // reaches the host's next comm_check instead of costing a timeout per exchange
+      if (*reinterpret_cast<volatile int *>(err) != 0)
+        return;
       const unsigned long long t0 = global_timer_ns();
       while (ld_acquire_sys(flag) < epoch)
         {

@@ -226,7 +226,7 @@ struct gf_comm_s
   unsigned *     blk_counter = nullptr; // device [P2P_MAX_RANKS]: last-block detection of the push
   int *          h_err = nullptr;       // mapped pinned: set by a kernel whose flag wait timed out
   int *          d_err = nullptr;       // device alias of h_err
-  unsigned long long timeout_ns = 60ull * 1000000000ull;
+  unsigned long long timeout_ns = 30ull * 1000000000ull;
   cudaStream_t   last_stream = nullptr; // ops of one communicator are ordered on one stream
   int64_t        n_halo = 0, n_allreduce = 0; // operations issued (diagnostics)
 };
@@ -315,6 +315,7 @@ struct gf_context
   bool lin_assembled  = false;
   bool defer_tangent  = false; // scatter / preconditioner / multigrid update on first use
   bool tangent_pending = false; // K_e of the last assembly not yet scattered (api.cu)
+  bool mg_update_pending = false; // tangent scattered, multigrid update (collective) still due
 
   // partition-independent reductions (pattern.cu, reduce.cu): owned nodes are grouped into node
   // planes orthogonal to the slab axis (contiguous in the internal numbering) and into chunks of
@@ -445,6 +446,7 @@ namespace gf
   void mg_update_operators(gf_context &c, const double *u_total); // after the finest assembly
   void mg_vcycle(gf_context &c, const double *b, double *x);      // x = MG(b)
   void mg_refresh_f32(gf_context &c); // FP32 operator copies of all levels below and incl. c
+  void mg_refresh_f32_level(gf_context &c); // this level only (rank-local)
   bool mg_active(const gf_context &c);
   // coarse_solve.cu
   bool coarse_solve_single_launch(gf_context &c, const double *val, const double *b, double *x,

@@ -524,30 +524,34 @@ namespace gf
   // The outer CG keeps applying the FP64 matrix, so the solve converges to the same tolerance on
   // the same residual; only the (fixed, SPD) preconditioner changes. A level whose copy does not
   // fit the free memory simply stays FP64.
+  // one level (rank-local: a conversion kernel, no communication)
+  void mg_refresh_f32_level(gf_context &lv)
+  {
+    gf_context *l     = &lv;
+    l->mg_val32_valid = false;
+    if (l->mg_matrix_precision == 0 || !level_is_assembled(*l))
+      return;
+    const double *A = level_matrix(*l);
+    if (A == nullptr || l->n_val == 0)
+      return;
+    if (l->model == GF_MODEL_NEO_HOOKEAN ? !l->mat[GF_MAT_TANGENT].valid : !l->lin_assembled)
+      return;
+    if (!l->mg_val32.p)
+      {
+        size_t free_b = 0, total_b = 0;
+        GF_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = size_t(l->n_val + 4) * sizeof(float);
+        if (need + (size_t(1) << 30) > free_b)
+          return;
+        l->mg_val32.alloc_zero(size_t(l->n_val + 4), l->stream);
+      }
+    launch_convert_f32(*l, A, l->mg_val32.p);
+    l->mg_val32_valid = true;
+  }
   void mg_refresh_f32(gf_context &c)
   {
     for (gf_context *l = &c; l != nullptr; l = l->mg.coarse)
-      {
-        l->mg_val32_valid = false;
-        if (l->mg_matrix_precision == 0 || !level_is_assembled(*l))
-          continue;
-        const double *A = level_matrix(*l);
-        if (A == nullptr || l->n_val == 0)
-          continue;
-        if (l->model == GF_MODEL_NEO_HOOKEAN ? !l->mat[GF_MAT_TANGENT].valid : !l->lin_assembled)
-          continue;
-        if (!l->mg_val32.p)
-          {
-            size_t free_b = 0, total_b = 0;
-            GF_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-            const size_t need = size_t(l->n_val + 4) * sizeof(float);
-            if (need + (size_t(1) << 30) > free_b)
-              continue;
-            l->mg_val32.alloc_zero(size_t(l->n_val + 4), l->stream);
-          }
-        launch_convert_f32(*l, A, l->mg_val32.p);
-        l->mg_val32_valid = true;
-      }
+      mg_refresh_f32_level(*l);
   }
 
   bool mg_active(const gf_context &c)
