@@ -80,9 +80,10 @@ def build_cuda(force=False):
 def build_host(force=False):
     """Mesh/DoF scaffolding only (no CUDA dependency): used by the Python binding, tests, oracle."""
     srcs = [os.path.join(HOST, "structured_mesh.cc"), os.path.join(HOST, "vtk_output.cc")]
-    deps = srcs + [os.path.join(HOST, "structured_mesh.h"), os.path.join(HOST, "vtk_output.h")]
+    deps = srcs + [os.path.join(HOST, "structured_mesh.h"), os.path.join(HOST, "vtk_output.h"),
+                   os.path.join(CSRC, "fe_basis.h")]
     if force or _newer(LIB_HOST, deps):
-        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", HOST,
+        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", HOST, "-I", CSRC,
               "-o", LIB_HOST] + srcs)
     return LIB_HOST
 
@@ -93,13 +94,13 @@ def build_elasticity(force=False):
     build_cuda()
     srcs = _sources(HOST, (".cc",))
     deps = srcs + _sources(HOST, (".h",)) + _sources(os.path.join(HOST, "adapter"), (".h",)) \
-        + _sources(INCLUDE, (".h",)) + [LIB_CUDA]
+        + _sources(INCLUDE, (".h",)) + [LIB_CUDA, os.path.join(CSRC, "fe_basis.h")]
     outs = []
     for dim in (2, 3):
         exe = os.path.join(PKG_DIR, "elasticity_%dd" % dim)
         if force or _newer(exe, deps):
             _run(["g++", "-O2", "-std=c++17", "-Wall", "-DDIM=%d" % dim, "-I", INCLUDE, "-I", HOST,
-                  "-o", exe] + srcs + ["-L", PKG_DIR, "-lgraftfem", "-Wl,-rpath,$ORIGIN",
+                  "-I", CSRC, "-o", exe] + srcs + ["-L", PKG_DIR, "-lgraftfem", "-Wl,-rpath,$ORIGIN",
                                        "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
         outs.append(exe)
     return outs

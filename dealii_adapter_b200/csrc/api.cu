@@ -323,8 +323,12 @@ extern "C"
     try
       {
         GF_REQUIRE(d->dim == 2 || d->dim == 3, GF_ERR_INVALID_ARG, "dim must be 2 or 3");
-        GF_REQUIRE(d->degree == 1 || d->degree == 2, GF_ERR_UNSUPPORTED,
-                   "polynomial degree must be 1 or 2");
+        // "Polynomial degree" (parameters.cc:110-113): the shipped files ask for 3 and 4
+        // (parameters.prm:21, nonlinear_elasticity.prm:24). Degrees 1 and 2 run the tuned kernels,
+        // higher ones the generic-degree kernels; the bound keeps the per-CTA shared-memory
+        // tables and the 16-bit scatter offsets in range.
+        GF_REQUIRE(d->degree >= 1 && d->degree <= (d->dim == 2 ? GF_MAX_DEGREE_2D : GF_MAX_DEGREE_3D),
+                   GF_ERR_UNSUPPORTED, "polynomial degree must be 1..6 (2D) / 1..3 (3D)");
         GF_REQUIRE(d->model == GF_MODEL_LINEAR || d->model == GF_MODEL_NEO_HOOKEAN,
                    GF_ERR_INVALID_ARG, "unknown model");
         GF_REQUIRE(d->n_dofs > 0 && d->n_cells > 0 && d->cell_dofs && d->cell_vertices &&
@@ -480,9 +484,10 @@ extern "C"
             break;
           case GF_OPT_OPERATOR:
             GF_REQUIRE(value == 0 || value == 1, GF_ERR_INVALID_ARG, "unknown operator kind");
-            GF_REQUIRE(value == 0 || (c.model == GF_MODEL_NEO_HOOKEAN && c.dim == 3),
+            GF_REQUIRE(value == 0 || (c.model == GF_MODEL_NEO_HOOKEAN && c.dim == 3 && c.p <= 2),
                        GF_ERR_UNSUPPORTED,
-                       "the matrix-free operator is available for the 3D neo-Hookean model");
+                       "the matrix-free operator is available for the 3D neo-Hookean model, "
+                       "polynomial degree 1 or 2");
             if (c.operator_kind != int(value))
               {
                 c.mf_valid                     = false; // re-assemble before the next solve

@@ -168,6 +168,20 @@ namespace gf
       return;
     const int    grid = int(std::min<int64_t>(n, int64_t(c.sm_count) * 8));
     const size_t smem = (size_t(c.tables.nq) * c.npc * c.dim + c.tables.nq) * sizeof(double);
+    // beyond the 48 KB default from 3D Q3 on (64 q-points x 64 nodes x 3 gradients: 98 KB)
+    static size_t configured[2] = {48 * 1024, 48 * 1024};
+    if (smem > configured[c.dim - 2])
+      {
+        GF_REQUIRE(smem <= 227 * 1024, GF_ERR_UNSUPPORTED,
+                   "polynomial degree too high for the linear cell kernel's shared memory");
+        if (c.dim == 3)
+          GF_CUDA_CHECK(cudaFuncSetAttribute(
+            lin_cells_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        else
+          GF_CUDA_CHECK(cudaFuncSetAttribute(
+            lin_cells_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured[c.dim - 2] = smem;
+      }
     if (c.dim == 3)
       lin_cells_kernel<3><<<grid, 256, smem, c.stream>>>(
         c0, c1, c.npc, c.tables.nq, c.geom.p, c.tables.dN.p, c.tables.w.p, c.tables.Mref.p, lambda,

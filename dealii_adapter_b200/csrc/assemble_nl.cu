@@ -24,6 +24,7 @@
 //   end      K_ab diag += S_ab + rho alpha_1 detJ M_ab (mass, :1020-1021); r_e from t_a, body
 //            force and inertia (:984-995)
 // Algorithmic flops / q-point (3D Q2): 378 node pairs (b <= a) * 30 FMA = 22.7 kflop.
+#include "assemble_nl_generic.cuh"
 #include "gf_context.h"
 #include "kernel_utils.cuh"
 #include "nl_material.cuh"
@@ -740,6 +741,49 @@ namespace gf
         c.re_buf.p, c.err_flag.p);
       GF_CUDA_CHECK(cudaGetLastError());
     }
+    // generic-degree kernels (assemble_nl_generic.cuh): every (dim, degree) without a tuned
+    // instantiation, i.e. degree >= 3
+    template <int DIM>
+    void launch_cells_generic(gf_context &c, const double *u_total, const double *accel, int64_t c0,
+                              int64_t c1)
+    {
+      const size_t  smem = size_t(NLGen<DIM>::smem_doubles(c.npc)) * sizeof(double);
+      static size_t configured = 48 * 1024;
+      if (smem > configured)
+        {
+          GF_REQUIRE(smem <= 227 * 1024, GF_ERR_UNSUPPORTED,
+                     "polynomial degree too high for the generic cell kernel's shared memory");
+          GF_CUDA_CHECK(cudaFuncSetAttribute(nl_cells_generic_kernel<DIM>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+          configured = smem;
+        }
+      const int64_t n = c1 - c0;
+      if (n <= 0)
+        return;
+      const int     nt   = 256;
+      const int     grid = int(std::min<int64_t>(n, int64_t(c.sm_count) * 2));
+      const NLParams prm = make_nl_params(c.desc);
+      nl_cells_generic_kernel<DIM><<<grid, nt, smem, c.stream>>>(
+        c0, c1, c.npc, c.tables.nq, c.cell_nodes.p, c.geom.p, u_total, accel, c.tables.N.p,
+        c.tables.dN.p, c.tables.w.p, c.tables.Mref.p, prm, c.ke_buf.p, c.re_buf.p, c.err_flag.p);
+      GF_CUDA_CHECK(cudaGetLastError());
+    }
+
+    template <int DIM>
+    void launch_faces_generic(gf_context &c, const double *u_total, const double *stress)
+    {
+      if (c.n_iface_cells == 0)
+        return;
+      const size_t smem =
+        size_t(nl_faces_generic_smem_doubles<DIM>(c.npc, c.tables.nqf)) * sizeof(double);
+      GF_REQUIRE(smem <= 48 * 1024, GF_ERR_UNSUPPORTED,
+                 "polynomial degree too high for the generic face kernel's shared memory");
+      nl_faces_generic_kernel<DIM><<<unsigned(c.n_iface_cells), 128, smem, c.stream>>>(
+        int(c.n_iface_cells), c.npc, c.tables.nqf, c.iface_cell_list.p, c.iface_face_ptr.p,
+        c.iface_face_no.p, c.cell_nodes.p, c.geom.p, u_total, stress, c.tables.dN.p, c.tables.Nf.p,
+        c.tables.wf.p, c.re_buf.p, c.err_flag.p);
+      GF_CUDA_CHECK(cudaGetLastError());
+    }
   } // namespace
 
   void launch_nl_cells(gf_context &c, const double *u_total, const double *accel, int64_t c0,
@@ -752,8 +796,12 @@ namespace gf
       launch_cells_t<3, 1>(c, u_total, accel, c0, c1);
     else if (c.dim == 2 && c.p == 2)
       launch_cells_t<2, 2>(c, u_total, accel, c0, c1);
-    else
+    else if (c.dim == 2 && c.p == 1)
       launch_cells_t<2, 1>(c, u_total, accel, c0, c1);
+    else if (c.dim == 3)
+      launch_cells_generic<3>(c, u_total, accel, c0, c1);
+    else
+      launch_cells_generic<2>(c, u_total, accel, c0, c1);
   }
 
   void launch_nl_faces(gf_context &c, const double *u_total, const double *stress)
@@ -765,7 +813,11 @@ namespace gf
       launch_faces_t<3, 1>(c, u_total, stress);
     else if (c.dim == 2 && c.p == 2)
       launch_faces_t<2, 2>(c, u_total, stress);
-    else
+    else if (c.dim == 2 && c.p == 1)
       launch_faces_t<2, 1>(c, u_total, stress);
+    else if (c.dim == 3)
+      launch_faces_generic<3>(c, u_total, stress);
+    else
+      launch_faces_generic<2>(c, u_total, stress);
   }
 } // namespace gf

@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 
+#include "fe_tables_host.h"
 #include "graft_fem.h"
 
 namespace gf
@@ -99,20 +100,14 @@ namespace gf
   constexpr int N_MATRICES  = 4;
 
   // reference-cell tables (device) shared by all kernels
-  struct FETables
+  struct FETables : FETablesHost
   {
-    int dim = 0, p = 0, npc = 0, dpc = 0, nq1 = 0, nq = 0, nqf = 0, nv = 0;
     DevBuf<double> N;    // [nq][npc]
     DevBuf<double> dN;   // [nq][npc][dim]  unit-cell gradients
     DevBuf<double> w;    // [nq]
     DevBuf<double> Nf;   // [2*dim][nqf][npc]
     DevBuf<double> wf;   // [nqf]
     DevBuf<double> Mref; // [npc][npc] sum_q w N_a N_b
-    std::vector<double> hN, hdN, hw, hNf, hwf;
-    std::vector<int>    local_lex; // [npc][3]
-    // 1D factors of the tensor-product tables (matrix-free sum factorisation, matfree.cu)
-    std::vector<double> h1N, h1D, h1w; // [nq1][p+1] values / derivatives at the 1D Gauss points, [nq1]
-    std::vector<int>    lex2hier;      // lexicographic local node -> FE_Q hierarchical local node
   };
 
   // CG scalars living on the device; the host polls `status` every check interval

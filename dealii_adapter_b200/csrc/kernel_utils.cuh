@@ -62,6 +62,7 @@ namespace gf
       }
   }
 
+#ifndef GF_CUDA_EMULATION // PTX and warp-level helpers: not for kernels that also run in tests/cuda_emu
   // ---- shared-memory mbarriers (producer/consumer pipelines: spmv.cu, assemble_nl.cu) -----------
   __device__ __forceinline__ uint32_t smem_u32(const void *p)
   {
@@ -166,4 +167,5 @@ namespace gf
           }
       }
   }
+#endif // GF_CUDA_EMULATION
 } // namespace gf

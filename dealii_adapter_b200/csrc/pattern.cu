@@ -144,6 +144,8 @@ namespace gf
       coord_of_x.assign(n_ext, 0.0);
     const int              ax  = c.slab_axis - 1;
     const std::vector<int> &lex = c.tables.local_lex;
+    // cell_dofs is in the caller's FESystem local order: entry of (local node a, component comp)
+    const std::vector<int> &loc_of = c.tables.loc_of;
     for (int64_t cell = 0; cell < n_cells; ++cell)
       {
         double Jax[3] = {0, 0, 0}, v0 = 0;
@@ -171,10 +173,12 @@ namespace gf
           }
         for (int a = 0; a < npc; ++a)
           {
-            const int32_t xd = d.cell_dofs[cell * dpc + a * dim];
+            const int32_t xd = d.cell_dofs[cell * dpc + loc_of[a * dim]];
             GF_REQUIRE(xd >= 0 && xd < n_ext, GF_ERR_INVALID_ARG, "cell_dofs entry out of range");
             if (node_of_x[xd] < 0 && c.slab_axis > 0)
-              coord_of_x[xd] = v0 + Jax[axis_dir] * (double(lex[a * 3 + axis_dir]) / c.p);
+              coord_of_x[xd] =
+                v0 + Jax[axis_dir] * (c.p <= 2 ? double(lex[a * 3 + axis_dir]) / c.p :
+                                                 c.tables.support_1d[lex[a * 3 + axis_dir]]);
             node_of_x[xd] = 0;
           }
       }
@@ -196,7 +200,8 @@ namespace gf
         std::sort(by_coord.begin(), by_coord.end(), [&](int32_t a, int32_t b) {
           return coord_of_x[xdofs[a]] < coord_of_x[xdofs[b]];
         });
-        const double tol = 1e-6 * h_min / c.p;
+            // the closest two support points of a cell are more than h / p^2 apart (Gauss-Lobatto)
+        const double tol = c.p <= 2 ? 1e-6 * h_min / c.p : 1e-6 * h_min / (c.p * c.p);
         int32_t      pl  = 0;
         for (int64_t k = 0; k < n_nodes; ++k)
           {
@@ -267,11 +272,11 @@ namespace gf
     for (int64_t cell = 0; cell < n_cells; ++cell)
       for (int a = 0; a < npc; ++a)
         {
-          const int32_t node          = node_of_x[d.cell_dofs[cell * dpc + a * dim]];
+          const int32_t node          = node_of_x[d.cell_dofs[cell * dpc + loc_of[a * dim]]];
           cell_nodes[cell * npc + a] = node;
           for (int comp = 0; comp < dim; ++comp)
             {
-              const int32_t e = d.cell_dofs[cell * dpc + a * dim + comp];
+              const int32_t e = d.cell_dofs[cell * dpc + loc_of[a * dim + comp]];
               GF_REQUIRE(e >= 0 && e < n_ext, GF_ERR_INVALID_ARG, "cell_dofs entry out of range");
               const int32_t i = node * dim + comp;
               GF_REQUIRE(c.h_perm_e2i[e] == -1 || c.h_perm_e2i[e] == i, GF_ERR_INVALID_ARG,

@@ -16,20 +16,6 @@ namespace gf
 {
   namespace
   {
-    double lag1(int p, int i, double x)
-    {
-      if (p == 1)
-        return i == 0 ? 1.0 - x : x;
-      return i == 0 ? 2.0 * (x - 0.5) * (x - 1.0) :
-                      (i == 1 ? -4.0 * x * (x - 1.0) : 2.0 * x * (x - 0.5));
-    }
-    double dlag1(int p, int i, double x)
-    {
-      if (p == 1)
-        return i == 0 ? -1.0 : 1.0;
-      return i == 0 ? 4.0 * x - 3.0 : (i == 1 ? -8.0 * x + 4.0 : 4.0 * x - 1.0);
-    }
-
     template <int DIM>
     __global__ void __launch_bounds__(256)
       postprocess_kernel(const int64_t c0, const int64_t n_cells, const int npc,
@@ -125,6 +111,9 @@ namespace gf
         // shape values / unit-cell gradients of the hierarchical FE_Q nodes at the lexicographic
         // patch points xi = (i, j, k) / p
         const std::vector<int> &lex = c.tables.local_lex;
+        const gf_fe::Basis1D    basis(p); // FE_Q(p) on its Gauss-Lobatto support points
+        auto lag1  = [&](int, int i, double x) { return basis.value(i, x); };
+        auto dlag1 = [&](int, int i, double x) { return basis.derivative(i, x); };
         std::vector<double>     N(size_t(npc) * npc), dN(size_t(npc) * npc * dim);
         for (int pt = 0; pt < npc; ++pt)
           {

@@ -2,6 +2,8 @@
 // (reference: nonlinear_elasticity.cc:171-380, linear_elasticity.cc:79-244).
 #include "structured_mesh.h"
 
+#include "fe_basis.h"
+
 #include <algorithm>
 #include <cassert>
 #include <map>
@@ -9,50 +11,16 @@
 
 namespace gfh
 {
-  // deal.II FE_Q hierarchical local node order (vertices, lines, quads, hex) expressed in
-  // local lexicographic coordinates 0..p per direction. p <= 2 (one node per entity).
+  // deal.II FE_Q hierarchical local node order (vertices, lines, quads, hex; every entity with
+  // its interior nodes in lexicographic order) expressed in local lexicographic coordinates
+  // 0..p per direction: csrc/fe_basis.h restates FETools::hierarchic_to_lexicographic_numbering
   static void build_local_nodes(int dim, int p, std::vector<std::array<int, 3>> &out)
   {
+    std::vector<int> lex;
+    gf_fe::local_nodes(dim, p, lex);
     out.clear();
-    const int nv = 1 << dim;
-    for (int v = 0; v < nv; ++v)
-      out.push_back({(v & 1) * p, ((v >> 1) & 1) * p, dim == 3 ? ((v >> 2) & 1) * p : 0});
-    if (p < 2)
-      return;
-    const int m = 1; // single interior position for p == 2
-    if (dim == 2)
-      {
-        // lines: 0:x=0, 1:x=1, 2:y=0, 3:y=1 ; then the quad
-        out.push_back({0, m, 0});
-        out.push_back({p, m, 0});
-        out.push_back({m, 0, 0});
-        out.push_back({m, p, 0});
-        out.push_back({m, m, 0});
-      }
-    else
-      {
-        // lines 0-3 on z=0, 4-7 on z=1 (x=0,x=1,y=0,y=1 each), 8-11 vertical at vertices 0..3
-        for (int z = 0; z <= p; z += p)
-          {
-            out.push_back({0, m, z});
-            out.push_back({p, m, z});
-            out.push_back({m, 0, z});
-            out.push_back({m, p, z});
-          }
-        out.push_back({0, 0, m});
-        out.push_back({p, 0, m});
-        out.push_back({0, p, m});
-        out.push_back({p, p, m});
-        // quads 0..5 = x-,x+,y-,y+,z-,z+
-        out.push_back({0, m, m});
-        out.push_back({p, m, m});
-        out.push_back({m, 0, m});
-        out.push_back({m, p, m});
-        out.push_back({m, m, 0});
-        out.push_back({m, m, p});
-        // hex
-        out.push_back({m, m, m});
-      }
+    for (size_t a = 0; a < lex.size() / 3; ++a)
+      out.push_back({lex[3 * a], lex[3 * a + 1], lex[3 * a + 2]});
   }
 
   StructuredMesh::StructuredMesh(int dim_, int degree_, const int *reps_, const double *p0_,
@@ -63,8 +31,9 @@ namespace gfh
   {
     if (dim != 2 && dim != 3)
       throw std::invalid_argument("StructuredMesh: dim must be 2 or 3");
-    if (degree != 1 && degree != 2)
-      throw std::invalid_argument("StructuredMesh: polynomial degree must be 1 or 2");
+    if (degree < 1 || degree > max_degree)
+      throw std::invalid_argument("StructuredMesh: polynomial degree must be 1.." +
+                                  std::to_string(max_degree));
     for (int d = 0; d < dim; ++d)
       {
         reps[d] = reps_[d];
@@ -90,6 +59,11 @@ namespace gfh
     if (n_dofs >= (int64_t(1) << 31))
       throw std::invalid_argument("StructuredMesh: more than 2^31 dofs");
     build_local_nodes(dim, p, local_node_lex);
+    {
+      std::vector<int> node_of, comp_of;
+      gf_fe::system_numbering(dim, p, node_of, comp_of, local_dof_of);
+    }
+    unit_support_1d = gf_fe::gauss_lobatto01(p + 1); // FE_Q(p): equidistant for p <= 2
 
     // node numbering
     grid_to_node.assign(n_nodes, -1);
@@ -142,7 +116,8 @@ namespace gfh
                               gz = int64_t(k) * p + l[2];
                 const int64_t g  = (gz * grid_nodes[1] + gy) * grid_nodes[0] + gx;
                 for (int comp = 0; comp < dim; ++comp)
-                  cell_dofs[c * dofs_per_cell + a * dim + comp] = dof_of(grid_to_node[g], comp);
+                  cell_dofs[c * dofs_per_cell + local_dof_of[a * dim + comp]] =
+                    dof_of(grid_to_node[g], comp);
               }
             for (int v = 0; v < nv; ++v)
               for (int d = 0; d < dim; ++d)
@@ -164,7 +139,10 @@ namespace gfh
         for (int comp = 0; comp < dim; ++comp)
           for (int d = 0; d < dim; ++d)
             support_points[int64_t(dof_of(n, comp)) * dim + d] =
-              gi[d] == grid_nodes[d] - 1 ? p1[d] : p0[d] + gi[d] * (h[d] / p);
+              gi[d] == grid_nodes[d] - 1 ?
+                p1[d] :
+                (p <= 2 ? p0[d] + gi[d] * (h[d] / p) :
+                          p0[d] + (double(gi[d] / p) + unit_support_1d[gi[d] % p]) * h[d]);
       }
   }
 
@@ -288,7 +266,7 @@ namespace gfh
       for (int64_t c : cells)
         for (int a = 0; a < mesh.nodes_per_cell; ++a)
           {
-            const int32_t d0 = mesh.cell_dofs[c * mesh.dofs_per_cell + a * dim];
+            const int32_t d0 = mesh.cell_dofs[c * mesh.dofs_per_cell + mesh.local_dof_of[a * dim]];
             const int64_t n  = mesh.numbering == numbering_component_wise ? d0 : d0 / dim;
             if (seen[n])
               continue;
@@ -321,10 +299,10 @@ namespace gfh
         const int64_t c = cells[lc];
         for (int a = 0; a < mesh.nodes_per_cell; ++a)
           {
-            const int32_t d0 = mesh.cell_dofs[c * mesh.dofs_per_cell + a * dim];
+            const int32_t d0 = mesh.cell_dofs[c * mesh.dofs_per_cell + mesh.local_dof_of[a * dim]];
             const int64_t n  = mesh.numbering == numbering_component_wise ? d0 : d0 / dim;
             for (int comp = 0; comp < dim; ++comp)
-              part.cell_dofs[lc * mesh.dofs_per_cell + a * dim + comp] =
+              part.cell_dofs[lc * mesh.dofs_per_cell + mesh.local_dof_of[a * dim + comp]] =
                 int32_t(local_node[n] * dim + comp);
           }
         std::copy(mesh.cell_vertices.begin() + c * nv * dim,
@@ -487,5 +465,33 @@ extern "C"
         case 8: return p->recv_dofs.data();
       }
     return nullptr;
+  }
+
+  // ---- csrc/fe_basis.h seen from the tests (tests/test_fe_basis.py compares it with numpy) ----
+  void gfh_fe_support_points(int p, double *out)
+  {
+    const std::vector<double> x = gf_fe::gauss_lobatto01(p + 1);
+    std::copy(x.begin(), x.end(), out);
+  }
+  void gfh_fe_basis_eval(int p, int n_points, const double *x, double *values, double *derivatives)
+  {
+    const gf_fe::Basis1D b(p);
+    for (int k = 0; k < n_points; ++k)
+      for (int i = 0; i <= p; ++i)
+        {
+          values[k * (p + 1) + i]      = b.value(i, x[k]);
+          derivatives[k * (p + 1) + i] = b.derivative(i, x[k]);
+        }
+  }
+  // lex[npc * 3], node_of / comp_of [npc * dim]; returns npc
+  int gfh_fe_numbering(int dim, int p, int *lex, int *node_of, int *comp_of)
+  {
+    std::vector<int> l, n, c, inv;
+    gf_fe::local_nodes(dim, p, l);
+    gf_fe::system_numbering(dim, p, n, c, inv);
+    std::copy(l.begin(), l.end(), lex);
+    std::copy(n.begin(), n.end(), node_of);
+    std::copy(c.begin(), c.end(), comp_of);
+    return int(l.size() / 3);
   }
 }

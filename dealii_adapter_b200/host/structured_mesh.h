@@ -5,7 +5,8 @@
 // (reference call sites: nonlinear_elasticity.cc:237-241, linear_elasticity.cc:143-147):
 //   * cells in lexicographic order (x fastest), vertices in deal.II order (x fastest),
 //   * the FESystem(FE_Q(p),dim) LOCAL DoF order: vertex dofs (vertex-major, component-minor),
-//     then line, quad, hex dofs (entity-major, component-minor),
+//     then line, quad, hex dofs (entity-major, then component, then the entity's scalar DoFs),
+//     any polynomial degree (support points: Gauss-Lobatto for p >= 3 as FE_Q does),
 //   * colorize boundary ids 0..5 = x-,x+,y-,y+,z-,z+  (used at nonlinear_elasticity.cc:200-230),
 //   * DoFTools::extract_boundary_dofs per component as ascending index lists (adapter.h:247-275),
 //   * boundary support points (dof_tools_extension.h:18-75).
@@ -43,6 +44,12 @@ namespace gfh
 
     // hierarchical (deal.II FE_Q) local scalar node -> local lexicographic (lx,ly,lz)
     std::vector<std::array<int, 3>> local_node_lex;
+    // FESystem local DoF of (hierarchical node a, component c): local_dof_of[a * dim + c]
+    // (= a * dim + c for p <= 2; entity-major / component / entity DoF beyond)
+    std::vector<int> local_dof_of;
+    // the p + 1 support points of FE_Q(p) on [0, 1] (Gauss-Lobatto; equidistant for p <= 2)
+    std::vector<double> unit_support_1d;
+    static constexpr int max_degree = 8;
 
     std::vector<int32_t> cell_dofs;     // [n_cells*dofs_per_cell]
     std::vector<double>  cell_vertices; // [n_cells*2^dim*dim]
@@ -120,4 +127,12 @@ extern "C"
   // which: 0 cell_dofs(i32) 1 cell_vertices(f64) 2 local_cell_global(i64) 3 local_to_global(i32)
   //        4 nbr_rank(i32) 5 send_ptr(i64) 6 recv_ptr(i64) 7 send_dofs(i32) 8 recv_dofs(i32)
   const void *gfh_partition_array(const void *p, int which);
+
+  // csrc/fe_basis.h for the tests: FE_Q(p) support points [p + 1]; basis values / derivatives
+  // [n_points][p + 1]; hierarchical node -> lexicographic triple and FESystem local DoF ->
+  // (node, component)
+  void gfh_fe_support_points(int p, double *out);
+  void gfh_fe_basis_eval(int p, int n_points, const double *x, double *values,
+                         double *derivatives);
+  int  gfh_fe_numbering(int dim, int p, int *lex, int *node_of, int *comp_of);
 }

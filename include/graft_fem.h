@@ -37,6 +37,9 @@ extern "C"
 #define GF_MODEL_LINEAR 0      /* Linear_Elasticity::ElastoDynamics (one-step-theta) */
 #define GF_MODEL_NEO_HOOKEAN 1 /* Nonlinear_Elasticity::Solid (Newmark + Newton) */
 
+#define GF_MAX_DEGREE_2D 6
+#define GF_MAX_DEGREE_3D 3
+
   typedef struct gf_context *gf_handle;
   typedef struct gf_comm_s * gf_comm;
 
@@ -46,7 +49,13 @@ extern "C"
   typedef struct
   {
     int32_t dim;    /* 2 | 3  (-DDIM, CMakeLists.txt:15-18) */
-    int32_t degree; /* FE_Q degree, 1 | 2 ("Polynomial degree", parameters.cc:110-113) */
+    int32_t degree; /* FE_Q degree ("Polynomial degree", parameters.cc:110-113; the shipped files
+                       use 3 and 4: parameters.prm:21, nonlinear_elasticity.prm:24): 1..
+                       GF_MAX_DEGREE_2D / GF_MAX_DEGREE_3D. cell_dofs is in FESystem(FE_Q(degree),
+                       dim)'s local order (vertices, lines, quads, hex; inside an entity component
+                       by component). Degrees 1 and 2 run the tuned kernels; from 3 on the
+                       generic-degree kernels, block-Jacobi CG only (gf_mg_attach and the
+                       matrix-free operator answer GF_ERR_UNSUPPORTED) */
     int32_t model;  /* GF_MODEL_* ("Model", parameters.cc:61-64) */
     int64_t n_dofs; /* dofs visible to this rank: owned first, then ghosts */
     int64_t n_cells;

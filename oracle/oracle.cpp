@@ -348,7 +348,7 @@ namespace
   };
 
   // ------------------------------------------------------------------------------------------
-  // [deal.II] FE_Q(p) (p<=2, equidistant = Gauss-Lobatto support points), QGauss, QProjector
+  // [deal.II] FE_Q(p) (Gauss-Lobatto support points, equidistant for p<=2), QGauss, QProjector
   // ------------------------------------------------------------------------------------------
   void gauss_legendre_01(int n, std::vector<double> &x, std::vector<double> &w)
   {
@@ -403,7 +403,68 @@ namespace
         default: return 4.0 * x - 1.0;
       }
   }
-  // hierarchical FE_Q local node -> lexicographic (lx,ly,lz), p<=2; same convention as SURVEY 8a
+  // [deal.II] FE_Q(p), p >= 3: Lagrange polynomials on the Gauss-Lobatto points (QGaussLobatto(p+1)
+  // mapped to [0,1]): 0, 1 and the roots of P'_p, each bracketed by two neighbouring Gauss points
+  // (the roots of P_p interlace those of P'_p) and found by bisection
+  std::vector<double> gauss_lobatto_01(int n)
+  {
+    const int           p = n - 1;
+    std::vector<double> pts(n, 0.0), gx, gw;
+    pts[n - 1] = 1.0;
+    if (p < 2)
+      return pts;
+    gauss_legendre_01(p, gx, gw);
+    auto dlegendre = [p](long double z) { // P'_p(z), z in (-1, 1)
+      long double p0 = 1.0L, p1 = z;
+      for (int k = 2; k <= p; ++k)
+        {
+          const long double pk = ((2 * k - 1) * z * p1 - (k - 1) * p0) / k;
+          p0                   = p1;
+          p1                   = pk;
+        }
+      return p * (z * p1 - p0) / (z * z - 1.0L);
+    };
+    for (int i = 1; i < p; ++i)
+      {
+        long double lo = 2.0L * gx[i - 1] - 1.0L, hi = 2.0L * gx[i] - 1.0L;
+        const bool  lo_positive = dlegendre(lo) > 0;
+        for (int it = 0; it < 200 && hi - lo > 1e-19L; ++it)
+          {
+            const long double mid = 0.5L * (lo + hi);
+            if ((dlegendre(mid) > 0) == lo_positive)
+              lo = mid;
+            else
+              hi = mid;
+          }
+        pts[i] = double(0.5L + 0.25L * (lo + hi));
+      }
+    return pts;
+  }
+  inline double lagrange_on(const std::vector<double> &nodes, int i, double x)
+  {
+    double v = 1.0;
+    for (size_t j = 0; j < nodes.size(); ++j)
+      if (int(j) != i)
+        v *= (x - nodes[j]) / (nodes[i] - nodes[j]);
+    return v;
+  }
+  inline double dlagrange_on(const std::vector<double> &nodes, int i, double x)
+  {
+    double s = 0.0;
+    for (size_t k = 0; k < nodes.size(); ++k)
+      if (int(k) != i)
+        {
+          double v = 1.0 / (nodes[i] - nodes[k]);
+          for (size_t j = 0; j < nodes.size(); ++j)
+            if (int(j) != i && j != k)
+              v *= (x - nodes[j]) / (nodes[i] - nodes[j]);
+          s += v;
+        }
+    return s;
+  }
+  // [deal.II] hierarchical FE_Q local node -> lexicographic (lx,ly,lz): vertices, lines, quads,
+  // hex; the interior nodes of an entity in the entity's own lexicographic order
+  // (FETools::hierarchic_to_lexicographic_numbering; y-faces run z fastest); SURVEY 8a
   void build_local_nodes(int dim, int p, std::vector<int> &lex)
   {
     lex.clear();
@@ -417,36 +478,87 @@ namespace
       push((v & 1) * p, ((v >> 1) & 1) * p, dim == 3 ? ((v >> 2) & 1) * p : 0);
     if (p < 2)
       return;
-    const int m = 1;
     if (dim == 2)
       {
-        push(0, m, 0);
-        push(p, m, 0);
-        push(m, 0, 0);
-        push(m, p, 0);
-        push(m, m, 0);
+        for (int m = 1; m < p; ++m)
+          push(0, m, 0);
+        for (int m = 1; m < p; ++m)
+          push(p, m, 0);
+        for (int m = 1; m < p; ++m)
+          push(m, 0, 0);
+        for (int m = 1; m < p; ++m)
+          push(m, p, 0);
+        for (int my = 1; my < p; ++my)
+          for (int mx = 1; mx < p; ++mx)
+            push(mx, my, 0);
       }
     else
       {
         for (int z = 0; z <= p; z += p)
           {
-            push(0, m, z);
-            push(p, m, z);
-            push(m, 0, z);
-            push(m, p, z);
+            for (int m = 1; m < p; ++m)
+              push(0, m, z);
+            for (int m = 1; m < p; ++m)
+              push(p, m, z);
+            for (int m = 1; m < p; ++m)
+              push(m, 0, z);
+            for (int m = 1; m < p; ++m)
+              push(m, p, z);
           }
-        push(0, 0, m);
-        push(p, 0, m);
-        push(0, p, m);
-        push(p, p, m);
-        push(0, m, m);
-        push(p, m, m);
-        push(m, 0, m);
-        push(m, p, m);
-        push(m, m, 0);
-        push(m, m, p);
-        push(m, m, m);
+        for (int m = 1; m < p; ++m)
+          push(0, 0, m);
+        for (int m = 1; m < p; ++m)
+          push(p, 0, m);
+        for (int m = 1; m < p; ++m)
+          push(0, p, m);
+        for (int m = 1; m < p; ++m)
+          push(p, p, m);
+        for (int x = 0; x <= p; x += p)
+          for (int mz = 1; mz < p; ++mz)
+            for (int my = 1; my < p; ++my)
+              push(x, my, mz);
+        for (int y = 0; y <= p; y += p)
+          for (int mx = 1; mx < p; ++mx)
+            for (int mz = 1; mz < p; ++mz)
+              push(mx, y, mz);
+        for (int z = 0; z <= p; z += p)
+          for (int my = 1; my < p; ++my)
+            for (int mx = 1; mx < p; ++mx)
+              push(mx, my, z);
+        for (int mz = 1; mz < p; ++mz)
+          for (int my = 1; my < p; ++my)
+            for (int mx = 1; mx < p; ++mx)
+              push(mx, my, mz);
       }
+  }
+  // [deal.II] FESystem(FE_Q(p), dim)::system_to_component_index: entity by entity, inside an
+  // entity all DoFs of component 0, then component 1, ... (FESystem::build_cell_tables). For
+  // p <= 2 (one scalar DoF per entity) this is i -> (i / dim, i % dim).
+  void build_system_numbering(int dim, int p, std::vector<int> &node_of, std::vector<int> &comp_of,
+                              std::vector<int> &loc_of)
+  {
+    node_of.clear();
+    comp_of.clear();
+    std::vector<int> entity_dofs;
+    entity_dofs.insert(entity_dofs.end(), size_t(1) << dim, 1);
+    entity_dofs.insert(entity_dofs.end(), dim == 2 ? 4 : 12, p - 1);
+    entity_dofs.insert(entity_dofs.end(), dim == 2 ? 1 : 6, (p - 1) * (p - 1));
+    if (dim == 3)
+      entity_dofs.push_back((p - 1) * (p - 1) * (p - 1));
+    int first = 0;
+    for (int count : entity_dofs)
+      {
+        for (int c = 0; c < dim; ++c)
+          for (int k = 0; k < count; ++k)
+            {
+              node_of.push_back(first + k);
+              comp_of.push_back(c);
+            }
+        first += count;
+      }
+    loc_of.assign(node_of.size(), -1);
+    for (size_t i = 0; i < node_of.size(); ++i)
+      loc_of[node_of[i] * dim + comp_of[i]] = int(i);
   }
 
   struct CSR
@@ -595,6 +707,9 @@ namespace
     std::vector<std::vector<double>> old_state_data;
     // reference-cell tables
     std::vector<int>    local_lex;           // npc*3
+    std::vector<int>    node_of, comp_of;    // system_to_component_index of local DoF i
+    std::vector<int>    loc_of;              // local DoF of (node a, component c): [a*dim + c]
+    std::vector<double> support_1d;          // FE_Q(p) support points on [0,1]
     std::vector<double> qx, qw;              // cell quadrature (unit cell) nq*dim, nq
     std::vector<double> N, dN;               // [nq*npc], [nq*npc*dim] reference gradients
     std::vector<double> fqx, fqw;            // face quadrature on unit face, nqf*(dim-1), nqf
@@ -633,8 +748,8 @@ namespace
       const orc_desc &d = desc;
       rt_dim            = dim;
       p                 = d.degree;
-      if (p != 1 && p != 2)
-        throw std::invalid_argument("oracle: degree must be 1 or 2");
+      if (p < 1 || p > 8)
+        throw std::invalid_argument("oracle: degree must be 1..8");
       npc = 1;
       for (int k = 0; k < dim; ++k)
         npc *= (p + 1);
@@ -655,6 +770,8 @@ namespace
       iface_face_no.assign(d.iface_face_no, d.iface_face_no + d.n_iface_faces);
       iface_dofs.assign(d.iface_dofs, d.iface_dofs + d.n_iface_nodes * dim);
       build_local_nodes(dim, p, local_lex);
+      build_system_numbering(dim, p, node_of, comp_of, loc_of);
+      support_1d = gauss_lobatto_01(p + 1);
       build_tables();
       build_pattern();
       mats.assign(5, std::vector<double>());
@@ -687,7 +804,8 @@ namespace
     {
       double v = 1;
       for (int k = 0; k < dim; ++k)
-        v *= lagrange(p, local_lex[a * 3 + k], xi[k]);
+        v *= p <= 2 ? lagrange(p, local_lex[a * 3 + k], xi[k]) :
+                      lagrange_on(support_1d, local_lex[a * 3 + k], xi[k]);
       return v;
     }
     void shape_grad(int a, const double *xi, double *g) const
@@ -696,8 +814,14 @@ namespace
         {
           double v = 1;
           for (int l = 0; l < dim; ++l)
-            v *= (l == k) ? dlagrange(p, local_lex[a * 3 + l], xi[l]) :
-                            lagrange(p, local_lex[a * 3 + l], xi[l]);
+            {
+              const int i = local_lex[a * 3 + l];
+              if (p <= 2)
+                v *= (l == k) ? dlagrange(p, i, xi[l]) : lagrange(p, i, xi[l]);
+              else
+                v *= (l == k) ? dlagrange_on(support_1d, i, xi[l]) :
+                                lagrange_on(support_1d, i, xi[l]);
+            }
           g[k] = v;
         }
     }
@@ -948,7 +1072,7 @@ namespace
       for (int q = 0; q < nq; ++q)
         for (int k = 0; k < dpc; ++k)
           {
-            const int    a = k / dim, c = k % dim;
+            const int    a = node_of[k], c = comp_of[k];
             const double uk =
               u_local_override ? u_local_override[k] : solution_total[local_dof_indices[k]];
             const double ak =
@@ -985,7 +1109,7 @@ namespace
 
           for (int k = 0; k < dpc; ++k) // :939-955
             {
-              const int a = k / dim, c = k % dim;
+              const int a = node_of[k], c = comp_of[k];
               Ten2<dim> grad_ref; // fe_values_ref[u_fe].gradient(k,q): only row c non-zero
               for (int dd = 0; dd < dim; ++dd)
                 grad_ref.d[c][dd] = geom.grad[(q_point * npc + a) * dim + dd];
@@ -1004,10 +1128,10 @@ namespace
 
           for (int i = 0; i < dpc; ++i) // :973
             {
-              const int component_i = i % dim;
+              const int component_i = comp_of[i];
               // :984-988
               cell_rhs[i] -= ((symm_grad_Nx[i] * tau) -
-                              (body_force[component_i] * rho * N[q_point * npc + i / dim])) *
+                              (body_force[component_i] * rho * N[q_point * npc + node_of[i]])) *
                              JxW;
               // :993-995
               for (int j = 0; j < dpc; ++j)
@@ -1019,7 +1143,7 @@ namespace
                 }
               for (int j = 0; j <= i; ++j) // :1001
                 {
-                  const int component_j = j % dim;
+                  const int component_j = comp_of[j];
                   // :1011-1012
                   cell_matrix[i * dpc + j] += ((symm_grad_Nx[i] * Jc) * symm_grad_Nx[j]) * JxW;
                   if (component_i == component_j) // :1015-1023
@@ -1059,8 +1183,8 @@ namespace
           std::vector<Ten1<dim>> local_stress(nqf);
           for (int q = 0; q < nqf; ++q) // :815-816
             for (int k = 0; k < dpc; ++k)
-              local_stress[q].d[k % dim] +=
-                external_stress[local_dof_indices[k]] * Nf[(face * nqf + q) * npc + k / dim];
+              local_stress[q].d[comp_of[k]] +=
+                external_stress[local_dof_indices[k]] * Nf[(face * nqf + q) * npc + node_of[k]];
           for (int f_q_point = 0; f_q_point < nqf; ++f_q_point)
             {
               // :825-827 — cell-quadrature gradient indexed by the face q-point (as written)
@@ -1086,8 +1210,8 @@ namespace
                 referential_stress.d[i] = local_stress[f_q_point].d[i] * n_star_norm;
               for (int i = 0; i < dpc; ++i) // :839-856
                 {
-                  const int    component_i = i % dim;
-                  const double Ni          = Nf[(face * nqf + f_q_point) * npc + i / dim];
+                  const int    component_i = comp_of[i];
+                  const double Ni          = Nf[(face * nqf + f_q_point) * npc + node_of[i]];
                   const double JxW         = JxWf[f_q_point];
                   cell_rhs[i] += (Ni * referential_stress.d[component_i]) * JxW;
                 }
@@ -1343,10 +1467,10 @@ namespace
           reinit_cell(cell, geom);
           for (int i = 0; i < dpc; ++i) // :289-323
             {
-              const int component_i = i % dim, ai = i / dim;
+              const int component_i = comp_of[i], ai = node_of[i];
               for (int j = 0; j < dpc; ++j)
                 {
-                  const int component_j = j % dim, aj = j / dim;
+                  const int component_j = comp_of[j], aj = node_of[j];
                   for (int q = 0; q < nq; ++q)
                     {
                       const double *gi = &geom.grad[(q * npc + ai) * dim];
@@ -1382,7 +1506,7 @@ namespace
               {
                 double s = 0;
                 for (int q = 0; q < nq; ++q)
-                  s += (desc.rho * desc.body_force[i % dim]) * N[q * npc + i / dim] * geom.JxW[q];
+                  s += (desc.rho * desc.body_force[comp_of[i]]) * N[q * npc + node_of[i]] * geom.JxW[q];
                 bf[ids[i]] += s;
               }
         }
@@ -1415,12 +1539,12 @@ namespace
               std::vector<double> local_stress(nqf * dim, 0.); // :499
               for (int q = 0; q < nqf; ++q)
                 for (int k = 0; k < dpc; ++k)
-                  local_stress[q * dim + k % dim] +=
-                    stress[ids[k]] * Nf[(face * nqf + q) * npc + k / dim];
+                  local_stress[q * dim + comp_of[k]] +=
+                    stress[ids[k]] * Nf[(face * nqf + q) * npc + node_of[k]];
               for (int q = 0; q < nqf; ++q) // :501-511
                 for (int i = 0; i < dpc; ++i)
-                  cell_rhs[i] += Nf[(face * nqf + q) * npc + i / dim] *
-                                 local_stress[q * dim + i % dim] * JxWf[q];
+                  cell_rhs[i] += Nf[(face * nqf + q) * npc + node_of[i]] *
+                                 local_stress[q * dim + comp_of[i]] * JxWf[q];
             }
           for (int i = 0; i < dpc; ++i) // :516-519
             system_rhs[ids[i]] += cell_rhs[i];
@@ -1586,9 +1710,9 @@ namespace
                   shape_grad(a, xi, g);
                   for (int c = 0; c < dim; ++c)
                     {
-                      val[c] += Na * u_local[a * dim + c];
+                      val[c] += Na * u_local[loc_of[a * dim + c]];
                       for (int k = 0; k < dim; ++k)
-                        Gxi.d[c][k] += g[k] * u_local[a * dim + c];
+                        Gxi.d[c][k] += g[k] * u_local[loc_of[a * dim + c]];
                     }
                 }
               for (int i = 0; i < dim; ++i)

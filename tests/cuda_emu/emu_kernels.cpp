@@ -1,0 +1,82 @@
+// The generic-degree kernels of the product (dealii_adapter_b200/csrc/assemble_nl_generic.cuh),
+// compiled UNCHANGED with g++ against the CUDA stand-in in this directory and driven with the
+// product's own host tables (csrc/fe_tables_host.h). Test infrastructure only.
+#include <cstring>
+
+#include "assemble_nl_generic.cuh"
+#include "fe_tables_host.h"
+
+namespace
+{
+  template <int DIM>
+  int run_cells(int p, int64_t n_cells, const int32_t *cell_nodes, const double *geom,
+                const double *u_total, const double *accel, const gf::NLParams &prm,
+                unsigned grid, unsigned block, double *ke, double *re)
+  {
+    gf::FETablesHost t;
+    gf::build_host_tables(t, DIM, p, true);
+    int          err  = 0;
+    const size_t smem = size_t(gf::NLGen<DIM>::smem_doubles(t.npc)) * sizeof(double);
+    gf_emu::launch(grid, block, smem, [&] {
+      gf::nl_cells_generic_kernel<DIM>(0, n_cells, t.npc, t.nq, cell_nodes, geom, u_total, accel,
+                                       t.hN.data(), t.hdN.data(), t.hw.data(), t.hMref.data(), prm,
+                                       ke, re, &err);
+    });
+    return err;
+  }
+
+  template <int DIM>
+  int run_faces(int p, int n_iface_cells, const int32_t *cell_list, const int32_t *face_ptr,
+                const int32_t *face_no, const int32_t *cell_nodes, const double *geom,
+                const double *u_total, const double *stress, unsigned block, double *re)
+  {
+    gf::FETablesHost t;
+    gf::build_host_tables(t, DIM, p, true);
+    int          err  = 0;
+    const size_t smem = size_t(gf::nl_faces_generic_smem_doubles<DIM>(t.npc, t.nqf)) * sizeof(double);
+    gf_emu::launch(unsigned(n_iface_cells), block, smem, [&] {
+      gf::nl_faces_generic_kernel<DIM>(n_iface_cells, t.npc, t.nqf, cell_list, face_ptr, face_no,
+                                       cell_nodes, geom, u_total, stress, t.hdN.data(),
+                                       t.hNf.data(), t.hwf.data(), re, &err);
+    });
+    return err;
+  }
+} // namespace
+
+extern "C"
+{
+  // params: kappa, mu, rho, alpha_1, body_force[3]. ke: [n_cells][dpc][dpc] (only the node blocks
+  // b <= a are written), re: [n_cells][dpc]. Returns the det F error flag.
+  int emu_nl_cells(int dim, int p, int64_t n_cells, const int32_t *cell_nodes, const double *geom,
+                   const double *u_total, const double *accel, const double *params, unsigned grid,
+                   unsigned block, double *ke, double *re)
+  {
+    gf::NLParams prm;
+    prm.kappa   = params[0];
+    prm.mu      = params[1];
+    prm.rho     = params[2];
+    prm.alpha_1 = params[3];
+    for (int k = 0; k < 3; ++k)
+      prm.body_force[k] = params[4 + k];
+    return dim == 3 ? run_cells<3>(p, n_cells, cell_nodes, geom, u_total, accel, prm, grid, block, ke, re) :
+                      run_cells<2>(p, n_cells, cell_nodes, geom, u_total, accel, prm, grid, block, ke, re);
+  }
+  int emu_nl_faces(int dim, int p, int n_iface_cells, const int32_t *cell_list,
+                   const int32_t *face_ptr, const int32_t *face_no, const int32_t *cell_nodes,
+                   const double *geom, const double *u_total, const double *stress, unsigned block,
+                   double *re)
+  {
+    return dim == 3 ? run_faces<3>(p, n_iface_cells, cell_list, face_ptr, face_no, cell_nodes, geom,
+                                   u_total, stress, block, re) :
+                      run_faces<2>(p, n_iface_cells, cell_list, face_ptr, face_no, cell_nodes, geom,
+                                   u_total, stress, block, re);
+  }
+  // the product's host tables, for the tests: loc_of [npc * dim]
+  int emu_loc_of(int dim, int p, int *loc_of)
+  {
+    gf::FETablesHost t;
+    gf::build_host_tables(t, dim, p, true);
+    std::memcpy(loc_of, t.loc_of.data(), t.loc_of.size() * sizeof(int));
+    return t.npc;
+  }
+}

@@ -27,10 +27,7 @@ def smooth_field(problem, amp, seed=0):
     k = rng.uniform(1.0, 3.0, size=(dim, dim))
     ph = rng.uniform(0, 1.0, size=dim)
     # component of each dof: recover from iface-independent rule via cell_dofs local order
-    comp = np.zeros(problem.n_dofs, dtype=np.int64)
-    cd = problem.mesh.cell_dofs.reshape(-1, problem.mesh.dofs_per_cell)
-    for c in range(dim):
-        comp[cd[:, c::dim].reshape(-1)] = c
+    comp = dof_components(problem)
     L = np.array(problem.mesh.p1) - np.array(problem.mesh.p0)
     xi = (x - np.array(problem.mesh.p0)) / L
     for c in range(dim):
@@ -40,11 +37,18 @@ def smooth_field(problem, amp, seed=0):
     return n_nodes_lookup
 
 
+def local_components(dim, degree):
+    """component of every FESystem(FE_Q(degree), dim) local DoF: entity by entity, inside an entity
+    component by component (node-major / component-minor only for degree <= 2)."""
+    counts = [1] * (1 << dim) + [degree - 1] * (4 if dim == 2 else 12) + \
+        [(degree - 1) ** 2] * (1 if dim == 2 else 6) + ([(degree - 1) ** 3] if dim == 3 else [])
+    return np.array([c for cnt in counts for c in range(dim) for _ in range(cnt)], dtype=np.int64)
+
+
 def dof_components(problem):
     comp = np.zeros(problem.n_dofs, dtype=np.int64)
     cd = problem.mesh.cell_dofs.reshape(-1, problem.mesh.dofs_per_cell)
-    for c in range(problem.dim):
-        comp[cd[:, c::problem.dim].reshape(-1)] = c
+    comp[cd.reshape(-1)] = np.tile(local_components(problem.dim, problem.degree), len(cd))
     return comp
 
 

@@ -76,9 +76,18 @@ def gauss01(n):
     return 0.5 * (x + 1.0), 0.5 * w
 
 
+def support_points_1d(p):
+    """FE_Q(p) support points on [0,1]: Gauss-Lobatto (deal.II: QGaussLobatto(p+1)); for p <= 2 these
+    are the equidistant points."""
+    if p <= 2:
+        return np.linspace(0.0, 1.0, p + 1)
+    inner = np.polynomial.legendre.Legendre.basis(p).deriv().roots()
+    return np.concatenate([[0.0], 0.5 * (np.sort(inner.real) + 1.0), [1.0]])
+
+
 def lagrange_1d(p, x):
-    """values and derivatives (n_pts, p+1) of the equidistant Lagrange basis on [0,1]."""
-    nodes = np.linspace(0.0, 1.0, p + 1)
+    """values and derivatives (n_pts, p+1) of the Lagrange basis on the FE_Q support points."""
+    nodes = support_points_1d(p)
     x = np.atleast_1d(x)
     val = np.ones((len(x), p + 1))
     der = np.zeros((len(x), p + 1))
@@ -98,20 +107,53 @@ def lagrange_1d(p, x):
 
 
 def hierarchical_nodes(dim, p):
-    """deal.II FE_Q local node order as lexicographic (lx,ly,lz): vertices, lines, quads, hex."""
-    assert p in (1, 2)
-    nodes = []
-    for v in range(1 << dim):
-        nodes.append(tuple(((v >> d) & 1) * p for d in range(dim)))
-    if p == 2:
-        if dim == 2:
-            nodes += [(0, 1), (2, 1), (1, 0), (1, 2), (1, 1)]
-        else:
-            for z in (0, 2):
-                nodes += [(0, 1, z), (2, 1, z), (1, 0, z), (1, 2, z)]
-            nodes += [(0, 0, 1), (2, 0, 1), (0, 2, 1), (2, 2, 1)]
-            nodes += [(0, 1, 1), (2, 1, 1), (1, 0, 1), (1, 2, 1), (1, 1, 0), (1, 1, 2), (1, 1, 1)]
-    return nodes
+    """deal.II FE_Q local node order as lexicographic (lx,ly,lz): vertices, lines, quads, hex, written
+    with the index formulas of FETools::hierarchic_to_lexicographic_numbering (n = p + 1 points per
+    direction, lexicographic index = lx + n ly + n^2 lz)."""
+    n, m = p + 1, p - 1
+    h2l = []
+    if dim == 2:
+        h2l += [0, n - 1, n * (n - 1), n * n - 1]
+        h2l += [(1 + i) * n for i in range(m)]                  # line 0: x = 0
+        h2l += [(2 + i) * n - 1 for i in range(m)]              # line 1: x = 1
+        h2l += [1 + i for i in range(m)]                        # line 2: y = 0
+        h2l += [n * (n - 1) + i + 1 for i in range(m)]          # line 3: y = 1
+        h2l += [n * (i + 1) + j + 1 for i in range(m) for j in range(m)]
+    else:
+        h2l += [0, n - 1, n * (n - 1), n * n - 1]
+        h2l += [x + n * n * (n - 1) for x in h2l[:4]]
+        for off in (0, n * n * (n - 1)):                        # bottom, top face lines
+            h2l += [off + (1 + i) * n for i in range(m)]
+            h2l += [off + n - 1 + (i + 1) * n for i in range(m)]
+            h2l += [off + 1 + i for i in range(m)]
+            h2l += [off + 1 + i + n * (n - 1) for i in range(m)]
+        h2l += [(1 + i) * n * n for i in range(m)]              # lines in z direction
+        h2l += [n - 1 + (i + 1) * n * n for i in range(m)]
+        h2l += [n * (n - 1) + (i + 1) * n * n for i in range(m)]
+        h2l += [n * n - 1 + (i + 1) * n * n for i in range(m)]
+        h2l += [(i + 1) * n * n + n * (j + 1) for i in range(m) for j in range(m)]            # x = 0
+        h2l += [(i + 1) * n * n + n - 1 + n * (j + 1) for i in range(m) for j in range(m)]    # x = 1
+        h2l += [(j + 1) * n * n + i + 1 for i in range(m) for j in range(m)]                  # y = 0
+        h2l += [(j + 1) * n * n + i + 1 + n * (n - 1) for i in range(m) for j in range(m)]    # y = 1
+        h2l += [n * (i + 1) + j + 1 for i in range(m) for j in range(m)]                      # z = 0
+        h2l += [n * n * (n - 1) + n * (i + 1) + j + 1 for i in range(m) for j in range(m)]    # z = 1
+        h2l += [n * n * (i + 1) + n * (j + 1) + k + 1
+                for i in range(m) for j in range(m) for k in range(m)]
+    assert sorted(h2l) == list(range(n ** dim))
+    return [tuple((l // n ** d) % n for d in range(dim)) for l in h2l]
+
+
+def system_to_node_component(dim, p):
+    """FESystem(FE_Q(p), dim) local DoF -> (hierarchical scalar node, component): entity by entity
+    (vertices, lines, quads, hex), inside an entity component by component
+    (FESystem::build_cell_tables)."""
+    counts = [1] * (1 << dim) + [p - 1] * (4 if dim == 2 else 12) + \
+        [(p - 1) ** 2] * (1 if dim == 2 else 6) + ([(p - 1) ** 3] if dim == 3 else [])
+    out, first = [], 0
+    for cnt in counts:
+        out += [(first + k, c) for c in range(dim) for k in range(cnt)]
+        first += cnt
+    return out
 
 
 def cell_tables(dim, p, nq1):
@@ -138,9 +180,11 @@ def cell_tables(dim, p, nq1):
 
 def element_energy(u_local, h, dim, p, nq1, mu, nu):
     """Pi(u) = sum_q Psi(I + grad u) JxW on a Cartesian cell with edge lengths h.
-    u_local in FESystem order (node-major, component-minor)."""
+    u_local in FESystem local order (system_to_node_component)."""
     N, dN, w = cell_tables(dim, p, nq1)
-    u = np.asarray(u_local).reshape(-1, dim)            # [a, c]
+    u = np.zeros((N.shape[1], dim))                     # [a, c]
+    for i, (a, c) in enumerate(system_to_node_component(dim, p)):
+        u[a, c] = u_local[i]
     grad = dN / np.asarray(h)[None, None, :]            # real-space gradients
     H = np.einsum("ac,qad->qcd", u, grad)               # H[q,c,d] = du_c/dX_d
     vol = np.prod(h)

@@ -1,0 +1,131 @@
+"""The generic-degree kernels (dealii_adapter_b200/csrc/assemble_nl_generic.cuh: the reference's
+shipped parameter files ask for polynomial degree 3 and 4, parameters.prm:21,
+nonlinear_elasticity.prm:24) were written in a session without GPU access. The SAME source is
+therefore also compiled with g++ against the CUDA stand-in of tests/cuda_emu/ (a CTA = CPU threads +
+a barrier) and checked here against the oracle: element tangents (lower node blocks) and element
+residuals of assemble_system_tangent_residual_one_cell (nonlinear_elasticity.cc:872-1036), and the
+assembled right-hand side including assemble_neumann_contribution_one_cell (:791-859).
+The GPU run of the same kernels is tests/test_gpu_zzz_high_degree.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import nl_params, smooth_field
+from dealii_adapter_b200.problem import make_problem
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "cuda_emu")
+
+
+@pytest.fixture(scope="module")
+def emu(native_libs):
+    out = os.path.join(EMU, "_build", "libgf_emu.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    csrc = os.path.join(ROOT, "dealii_adapter_b200", "csrc")
+    srcs = [os.path.join(EMU, "emu_kernels.cpp"), os.path.join(EMU, "cuda_runtime.h")] + \
+        [os.path.join(csrc, f) for f in ("assemble_nl_generic.cuh", "emu_compat.cuh",
+                                         "kernel_utils.cuh", "nl_material.cuh", "fe_tables_host.h",
+                                         "fe_basis.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        subprocess.run(["g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-Wall",
+                        "-Wno-unknown-pragmas", "-DGF_CUDA_EMULATION", "-I", EMU, "-I", csrc,
+                        "-I", os.path.join(ROOT, "include"), "-o", out, srcs[0], "-lpthread"],
+                       check=True)
+    lib = C.CDLL(out)
+    lib.emu_nl_cells.restype = C.c_int
+    lib.emu_nl_cells.argtypes = [C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 5 + \
+        [C.c_uint, C.c_uint, C.c_void_p, C.c_void_p]
+    lib.emu_nl_faces.restype = C.c_int
+    lib.emu_nl_faces.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_uint, C.c_void_p]
+    lib.emu_loc_of.restype = C.c_int
+    lib.emu_loc_of.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    return lib
+
+
+def device_view(prob, emu):
+    """What gf_create derives from the mesh description: internal node numbering (any bijection
+    will do here), cell -> node table in hierarchical local order, affine geometry records."""
+    dim, p, mesh = prob.dim, prob.degree, prob.mesh
+    npc = (p + 1) ** dim
+    loc_of = np.zeros(npc * dim, dtype=np.int32)
+    assert emu.emu_loc_of(dim, p, loc_of.ctypes.data) == npc
+    cd = mesh.cell_dofs.reshape(mesh.n_cells, npc * dim)
+    xdofs = cd[:, loc_of[0::dim]]                         # [cell, a]: global x-dof of local node a
+    ids, cell_nodes = np.unique(xdofs.reshape(-1), return_inverse=True)
+    cell_nodes = cell_nodes.reshape(mesh.n_cells, npc).astype(np.int32)
+    # internal dof (node, c) -> caller's global dof
+    i2e = np.zeros((len(ids), dim), dtype=np.int64)
+    for c in range(dim):
+        i2e[cell_nodes.reshape(-1), c] = cd[:, loc_of[c::dim]].reshape(-1)
+    cv = mesh.cell_vertices.reshape(mesh.n_cells, 1 << dim, dim)
+    h = cv[:, -1, :] - cv[:, 0, :]
+    geom = np.zeros((mesh.n_cells, dim * dim + 1))
+    for d in range(dim):
+        geom[:, d * dim + d] = 1.0 / h[:, d]
+    geom[:, -1] = np.prod(h, axis=1)
+    return loc_of, cell_nodes, i2e.reshape(-1), geom
+
+
+CASES = [(2, 3, [3, 2]), (2, 4, [2, 2]), (2, 5, [2, 1]), (3, 3, [2, 1, 2]), (2, 2, [3, 2]),
+         (3, 2, [2, 2, 1])]
+
+
+@pytest.mark.parametrize("dim,p,reps", CASES)
+@pytest.mark.parametrize("block", [32, 96])
+def test_generic_cell_and_face_kernels_match_oracle(emu, dim, p, reps, block):
+    from oracle import oracle_py as orc
+    prm = nl_params(poly_degree=p, body_force=(1.5, -9.81, 0.5), scenario="PF")
+    prob = make_problem(prm, dim, reps=reps, numbering="cellwise")
+    prob.constrained[:] = 0
+    mesh = prob.mesh
+    npc, dpc, nc = (p + 1) ** dim, dim * (p + 1) ** dim, mesh.n_cells
+    loc_of, cell_nodes, i2e, geom = device_view(prob, emu)
+    L = (np.array(mesh.p1) - np.array(mesh.p0)).min()
+    u = smooth_field(prob, 0.05 * L, seed=5)
+    acc = smooth_field(prob, 40.0, seed=6)
+    rng = np.random.RandomState(7)
+    stress = 2000.0 * rng.uniform(-1, 1, prob.n_dofs)
+    o = orc.Oracle(prob, n_threads=1)
+    kappa = (2.0 * prm.mu * (1.0 + prm.nu)) / (3.0 * (1.0 - 2.0 * prm.nu))
+    alpha_1 = 1.0 / (prm.beta * prm.delta_t ** 2)
+    params = np.array([kappa, prm.mu, prm.rho, alpha_1] + list(prm.body_force), dtype=np.float64)
+    u_i, acc_i, stress_i = (np.ascontiguousarray(v[i2e]) for v in (u, acc, stress))
+    ke = np.full((nc, dpc, dpc), np.nan)
+    re = np.full((nc, dpc), np.nan)
+    grid = 2 if nc > 2 else 1          # grid-stride loop over the cells
+    err = emu.emu_nl_cells(dim, p, nc, cell_nodes.ctypes.data, geom.ctypes.data, u_i.ctypes.data,
+                           acc_i.ctypes.data, params.ctypes.data, grid, block, ke.ctypes.data,
+                           re.ctypes.data)
+    assert err == 0
+    cd = mesh.cell_dofs.reshape(nc, dpc)
+    node = np.arange(dpc) // dim
+    lower = node[:, None] >= node[None, :]              # node blocks b <= a
+    for cell in range(nc):
+        K, r = o.nl_cell(cell, u[cd[cell]], acc[cd[cell]])
+        K_int = K[np.ix_(loc_of, loc_of)]               # internal order (a, c) -> a * dim + c
+        scale = np.abs(K).max()
+        assert np.abs(ke[cell][lower] - K_int[lower]).max() <= 1e-12 * scale
+        assert np.isnan(ke[cell][~lower]).all()         # the upper blocks are never written
+        assert np.abs(re[cell] - r[loc_of]).max() <= 1e-12 * np.abs(r).max()
+    # interface faces on top (K2g), then the assembled right-hand side against the oracle's
+    icells, first = np.unique(prob.iface_cell, return_index=True)
+    order = np.lexsort((prob.iface_face_no, prob.iface_cell))
+    face_no = prob.iface_face_no[order].astype(np.int32)
+    face_ptr = np.concatenate([np.searchsorted(prob.iface_cell[order], icells),
+                               [len(order)]]).astype(np.int32)
+    cell_list = icells.astype(np.int32)
+    err = emu.emu_nl_faces(dim, p, len(cell_list), cell_list.ctypes.data, face_ptr.ctypes.data,
+                           face_no.ctypes.data, cell_nodes.ctypes.data, geom.ctypes.data,
+                           u_i.ctypes.data, stress_i.ctypes.data, block, re.ctypes.data)
+    assert err == 0
+    rhs = np.zeros(prob.n_dofs)
+    np.add.at(rhs, cd[:, loc_of].reshape(-1), re.reshape(-1))
+    o.set(orc.NL_TOTAL_DISPLACEMENT, u)
+    o.set(orc.NL_ACCELERATION, acc)
+    o.set(orc.NL_EXTERNAL_STRESS, stress)
+    o.nl_assemble_system()
+    ref = o.get(orc.NL_SYSTEM_RHS)
+    assert np.abs(rhs - ref).max() <= 1e-12 * np.abs(ref).max()

@@ -56,7 +56,7 @@ def test_tau_is_derivative_of_reference_psi(orc, dim):
     assert rel_err(tau, rf.to_voigt2(0.5 * (tau_fd + tau_fd.T))) < 1e-7
 
 
-@pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (3, 1), (3, 2)])
+@pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (3, 1), (3, 2), (2, 3), (2, 4), (3, 3)])
 def test_cell_residual_and_tangent_are_derivatives_of_element_energy(orc, dim, degree):
     # nonlinear_elasticity.cc:984-985 (internal force) and :1011-1023 (tangent) against finite
     # differences of Pi(u) = sum_q Psi(F_q) JxW built from the reference's Psi. rho = 0 removes the
@@ -90,28 +90,29 @@ def test_cell_residual_and_tangent_are_derivatives_of_element_energy(orc, dim, d
     assert rel_err(K, Kfd) < 1e-6
 
 
-@pytest.mark.parametrize("dim", [2, 3])
-def test_rigid_motion_gives_zero_internal_force(orc, dim):
-    p = nl_params(poly_degree=2, rho=0.0)
+@pytest.mark.parametrize("dim,degree", [(2, 2), (3, 2), (2, 3), (2, 4), (3, 3)])
+def test_rigid_motion_gives_zero_internal_force(orc, dim, degree):
+    p = nl_params(poly_degree=degree, rho=0.0)
     prob = make_problem(p, dim, reps=[1] * dim)
     o = orc.Oracle(prob, n_threads=1)
     dpc = prob.mesh.dofs_per_cell
-    nodes = np.array(rf.hierarchical_nodes(dim, 2), dtype=float) / 2.0
+    nodes = rf.support_points_1d(degree)[np.array(rf.hierarchical_nodes(dim, degree))]
     h = np.array(prob.mesh.p1) - np.array(prob.mesh.p0)
     X = nodes * h
     th = 0.3
     R = np.eye(dim)
     R[0, 0], R[0, 1], R[1, 0], R[1, 1] = np.cos(th), -np.sin(th), np.sin(th), np.cos(th)
-    u = (X @ R.T - X + 0.01).reshape(-1)
+    un = X @ R.T - X + 0.01                                  # [node, component]
+    u = np.array([un[a, c] for a, c in rf.system_to_node_component(dim, degree)])
     K, r = o.nl_cell(0, u, np.zeros(dpc))
     assert np.abs(r).max() < 1e-9 * MU * h.max() ** (dim - 1)
 
 
-def test_nonlinear_tangent_at_zero_equals_linear_stiffness_plus_mass_3d(orc):
+@pytest.mark.parametrize("degree,reps", [(2, [2, 3, 2]), (3, [1, 2, 1])])
+def test_nonlinear_tangent_at_zero_equals_linear_stiffness_plus_mass_3d(orc, degree, reps):
     # K_nl(u=0) - alpha_1 M == K_lin in 3D (lambda_eff = kappa - 2mu/3 = lambda)
-    reps = [2, 3, 2]
-    pn = nl_params(poly_degree=2)
-    pl = lin_params(poly_degree=2, delta_t=pn.delta_t)
+    pn = nl_params(poly_degree=degree)
+    pl = lin_params(poly_degree=degree, delta_t=pn.delta_t)
     probn = make_problem(pn, 3, reps=reps)
     probl = make_problem(pl, 3, reps=reps)
     # no constraints so that both matrices are the raw sums
@@ -130,11 +131,12 @@ def test_nonlinear_tangent_at_zero_equals_linear_stiffness_plus_mass_3d(orc):
     assert abs(M.sum() - 3 * pl.rho * vol) < 1e-10 * pl.rho * vol
 
 
-def test_neumann_load_integrates_traction_over_interface(orc):
+@pytest.mark.parametrize("degree", [2, 3, 4])
+def test_neumann_load_integrates_traction_over_interface(orc, degree):
     # nonlinear_elasticity.cc:791-859 at u=0 (pull-back factor = 1): sum of nodal loads per
     # component = traction * interface area ; same for the linear consistent loading :458-521
-    for dim in (2, 3):
-        pn = nl_params(poly_degree=2)
+    for dim in ((2, 3) if degree < 4 else (2,)):
+        pn = nl_params(poly_degree=degree)
         prob = make_problem(pn, dim, reps=[2, 3, 2][:dim])
         prob.constrained[:] = 0
         o = orc.Oracle(prob)
@@ -151,7 +153,7 @@ def test_neumann_load_integrates_traction_over_interface(orc):
         comp = dof_components(prob)
         for c in range(dim):
             assert abs(rhs[comp == c].sum() - t[c] * area) < 1e-12 * abs(t).max() * area
-        pl = lin_params(poly_degree=2)
+        pl = lin_params(poly_degree=degree)
         probl = make_problem(pl, dim, reps=[2, 3, 2][:dim])
         ol = orc.Oracle(probl)
         ol.format_precice_to_deal(buf, orc.LIN_STRESS)
