@@ -101,6 +101,10 @@ namespace gfh
     const char *env = std::getenv("GF_PRECONDITIONER");
     if (env && std::string(env) == "block-jacobi")
       return 1;
+    // the device's transfer operators need nested support points: FE_Q(1), FE_Q(2). The shipped
+    // parameter files (degree 3 / 4) run the block-Jacobi CG
+    if (prm.poly_degree > 2)
+      return 1;
     HostProblem *fine = this;
     while (true)
       {

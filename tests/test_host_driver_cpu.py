@@ -214,3 +214,26 @@ def test_timer_summary_keeps_the_reference_sections(env, tmp_path):
     rows = {l.split("|")[1].strip(): int(l.split("|")[2]) for l in r.stdout.splitlines()
             if l.startswith("| ") and l.count("|") == 5 and l.split("|")[2].strip().isdigit()}
     assert rows == {"Output results": 1, "Assemble rhs": 3, "Solve system": 3, "Advance adapter": 3}
+
+
+def test_shipped_parameter_file_degree_3_reaches_the_device_with_the_right_mesh(env, tmp_path):
+    """The reference's own parameters.prm (linear, FSI3, degree 3, Direct): the C++ host builds
+    the Q3 mesh (18 x 3 cells -> 55 x 10 nodes), hands it to gf_create and runs the linear call
+    sequence; no multigrid attach above degree 2. The participant configuration is read from the
+    file name the prm asks for (precice-config.xml)."""
+    from test_zz_gpu_high_degree import SHIPPED_PARAMETERS_PRM
+    exes, lib = env
+    (tmp_path / "parameters.prm").write_text(SHIPPED_PARAMETERS_PRM)
+    (tmp_path / "precice-config.xml").write_text(
+        FAKE_CFG.format(windows=3, sub=1).replace("time-window-size = 0.01", "time-window-size = 0.005"))
+    e = dict(os.environ, LD_PRELOAD=lib, GF_FAKE_LOG=str(tmp_path / "calls.log"))
+    r = subprocess.run([exes[0], "parameters.prm"], cwd=tmp_path, capture_output=True, text=True,
+                       timeout=120, env=e)
+    assert r.returncode == 0, r.stderr
+    log = (tmp_path / "calls.log").read_text().splitlines()
+    assert log[0].startswith("create dim=2 degree=3 model=0 n_dofs=%d n_cells=54" % (55 * 10 * 2))
+    calls = [l.split()[0] for l in log]
+    assert "mg_attach" not in calls
+    assert calls == ["create", "postprocess", "lin_assemble_once"] + \
+        ["set_traction", "lin_step", "get_interface_displacement"] * 3 + ["destroy"]
+    assert "Polynomial degree: 3" in r.stdout

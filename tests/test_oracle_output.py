@@ -42,7 +42,7 @@ def patch_reference_points(prob):
     return pts
 
 
-@pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (3, 1), (3, 2)])
+@pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (3, 1), (3, 2), (2, 3), (2, 4), (3, 3)])
 def test_uniform_stretch_and_rigid_rotation(orc, dim, degree):
     p = nl_params(poly_degree=degree)
     prob = make_problem(p, dim, reps=[2, 3, 2][:dim])

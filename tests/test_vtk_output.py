@@ -74,7 +74,8 @@ def parse_vtk(path):
     return out
 
 
-@pytest.mark.parametrize("dim,degree,reps", [(2, 2, [4, 3]), (3, 2, [3, 3, 3]), (3, 1, [3, 4, 3])])
+@pytest.mark.parametrize("dim,degree,reps", [(2, 2, [4, 3]), (3, 2, [3, 3, 3]), (3, 1, [3, 4, 3]),
+                                           (2, 3, [4, 3]), (2, 4, [3, 3]), (3, 3, [3, 3, 3])])
 def test_written_file_round_trips_the_oracle_fields(native_libs, tmp_path, dim, degree, reps):
     from oracle import oracle_py as orc
     prob = make_problem(nl_params(poly_degree=degree), dim, reps=reps)
