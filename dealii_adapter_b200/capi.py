@@ -23,7 +23,7 @@ MAT_TANGENT, MAT_STIFFNESS, MAT_MASS, MAT_SYSTEM, MAT_MG_F32 = range(5)
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI, PRECOND_MULTIGRID = range(4)
 OPT_PRECONDITIONER, OPT_CG_CHECK_INTERVAL, OPT_PROFILE, OPT_OPERATOR, OPT_SPMV_KERNEL, \
     OPT_MG_SMOOTHER_DEGREE, OPT_MG_COARSE_DEGREE, OPT_MG_SMOOTHER_RATIO, \
-    OPT_CG_INITIAL_GUESS, OPT_MG_MATRIX_PRECISION = range(10)
+    OPT_CG_INITIAL_GUESS, OPT_MG_MATRIX_PRECISION, OPT_DIRECT_SOLVER = range(11)
 
 EXPORTED_SYMBOLS = [
     "gf_create", "gf_destroy", "gf_last_error", "gf_set_option", "gf_comm_unique_id",
@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "gf_set_vector", "gf_nnz", "gf_export_csr", "gf_spmv", "gf_spmv_timed", "gf_profile_get",
     "gf_synchronize", "gf_event_record", "gf_event_elapsed_ms", "gf_mg_attach", "gf_mg_vcycle",
     "gf_comm_transport", "gf_comm_timed", "gf_postprocess", "gf_export_rows", "gf_comm_ipc_begin",
-    "gf_comm_ipc_finish",
+    "gf_comm_ipc_finish", "gf_direct_info",
 ]
 
 
@@ -402,6 +402,16 @@ class Handle:
         f.restype = C.c_int
         self._check(f(self._h, n_reps, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def direct_info(self):
+        """(solves answered by the band Cholesky, half bandwidth, last relative residual);
+        GraftError(GF_ERR_UNSUPPORTED) with the reason when the CG stand-in runs instead."""
+        n, w, r = C.c_int64(), C.c_int64(), C.c_double()
+        f = lib().gf_direct_info
+        f.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+        f.restype = C.c_int
+        self._check(f(self._h, C.byref(n), C.byref(w), C.byref(r)))
+        return n.value, w.value, r.value
 
     def profile(self, reset=False):
         p = GfProfile()

@@ -72,6 +72,64 @@ namespace
       }
   }
 
+  // x = A^-1 b by the band Cholesky (+ one step of iterative refinement with the FP64 matrix, as
+  // UMFPACK does by default). false: not available here (partitioned handle, band beyond the
+  // memory budget, matrix-free operator, GF_OPT_DIRECT_SOLVER = 2, A not positive definite) - the
+  // caller then runs the tight CG. `constant_matrix`: reuse the factor of the previous call.
+  bool direct_apply(gf_context &c, const double *A, const double *b, double *x,
+                    const bool constant_matrix)
+  {
+    if (c.operator_kind != 0 || !gf::direct_available(c))
+      return false;
+    try
+      {
+        if (!(constant_matrix && c.direct.factored && c.direct.factor_is_system_matrix))
+          {
+            if (!gf::direct_factor(c, A))
+              {
+                GF_REQUIRE(c.direct_mode != 1, GF_ERR_NOT_CONVERGED,
+                           "direct solver: the matrix is not positive definite");
+                return false;
+              }
+            c.direct.factor_is_system_matrix = constant_matrix;
+          }
+        gf::direct_solve(c, b, x);
+        gf::launch_spmv(c, A, x, c.cg_v.p, nullptr);
+        gf::vec_copy(c, c.cg_r.p, b);
+        gf::vec_axpby(c, c.cg_r.p, -1.0, c.cg_v.p, 1.0); // r = b - A x
+        gf::direct_solve(c, c.cg_r.p, c.cg_z.p);
+        gf::vec_axpby(c, x, 1.0, c.cg_z.p, 1.0);
+        // the answer is checked before it is used: ||b - A x|| <= 1e-10 ||b|| (the CG stand-in
+        // stops at 1e-13 ||b||; a factorisation of an ill-conditioned tangent that cannot reach
+        // this is discarded in favour of the CG)
+        gf::launch_spmv(c, A, x, c.cg_v.p, nullptr);
+        gf::vec_copy(c, c.cg_r.p, b);
+        gf::vec_axpby(c, c.cg_r.p, -1.0, c.cg_v.p, 1.0);
+        const double rn = gf::vec_masked_norm(c, c.cg_r.p, false);
+        const double bn = gf::vec_masked_norm(c, b, false);
+        c.direct.last_residual = bn > 0 ? rn / bn : rn;
+        if (!(rn <= 1e-10 * bn))
+          {
+            GF_REQUIRE(c.direct_mode != 1, GF_ERR_NOT_CONVERGED,
+                       "direct solver: residual check failed");
+            return false;
+          }
+        c.direct.n_solves++;
+        return true;
+      }
+    catch (gf::Error &e)
+      {
+        if (c.direct_mode == 1)
+          throw;
+        // first run of this path on a new device / size: never let it cost the solve
+        cudaGetLastError();
+        c.direct.usable   = false;
+        c.direct.factored = false;
+        c.direct.why      = e.msg;
+        return false;
+      }
+  }
+
   double *mat_ptr(gf_context &c, int which)
   {
     if (which == GF_MAT_TANGENT)
@@ -307,6 +365,7 @@ namespace gf
     if (std::sqrt(bn) > 1e-15) // body_force_enabled :62
       launch_body_force(c, c.vec[GF_LIN_BODY_FORCE].p);
     c.lin_assembled = true;
+    c.direct.factored = false; // a new system matrix: the band Cholesky factor is stale
   }
 } // namespace gf
 
@@ -392,6 +451,9 @@ extern "C"
           c->defer_tangent = c->model == GF_MODEL_NEO_HOOKEAN && multi < 0.5 &&
                              getenv("GF_NO_DEFERRED_TANGENT") == nullptr;
         }
+        // GF_DIRECT_SOLVER = auto | cholesky | cg presets GF_OPT_DIRECT_SOLVER (0 | 1 | 2)
+        if (const char *env = getenv("GF_DIRECT_SOLVER"))
+          c->direct_mode = std::string(env) == "cg" ? 2 : (std::string(env) == "cholesky" ? 1 : 0);
         // the pointers inside desc are caller-owned: never dereference them after create
         c->desc.cell_dofs = nullptr;
         c->desc.cell_vertices = nullptr;
@@ -496,6 +558,10 @@ extern "C"
                 c.mg_update_pending            = false;
               }
             c.operator_kind = int(value);
+            break;
+          case GF_OPT_DIRECT_SOLVER:
+            GF_REQUIRE(value >= 0 && value <= 2, GF_ERR_INVALID_ARG, "unknown direct solver mode");
+            c.direct_mode = int(value);
             break;
           case GF_OPT_SPMV_KERNEL:
             GF_REQUIRE(value == 0 || value == 1 || value == 3 || value == 5 || value == 6,
@@ -736,10 +802,16 @@ extern "C"
                           true, cg_max_iterations(c, max_iterations_lin), &it, &res);
       else
         {
-          gf::vec_zero(c, x);
-          rc = gf::cg_solve(c, c.mat[GF_MAT_TANGENT].val.p, x, c.vec[GF_NL_SYSTEM_RHS].p, 1e-13,
-                            true, 10 * cg_max_iterations(c, std::max(1.0, max_iterations_lin)), &it,
-                            &res);
+          // SparseDirectUMFPACK (:1192-1200): band Cholesky of the tangent on the device where
+          // the band fits (direct.cu), else the CG run to 1e-13 from a zero guess
+          rc = GF_OK;
+          if (!direct_apply(c, c.mat[GF_MAT_TANGENT].val.p, c.vec[GF_NL_SYSTEM_RHS].p, x, false))
+            {
+              gf::vec_zero(c, x);
+              rc = gf::cg_solve(c, c.mat[GF_MAT_TANGENT].val.p, x, c.vec[GF_NL_SYSTEM_RHS].p, 1e-13,
+                                true, 10 * cg_max_iterations(c, std::max(1.0, max_iterations_lin)),
+                                &it, &res);
+            }
           it  = 1; // :1198-1199
           res = 0.0;
         }
@@ -838,6 +910,8 @@ extern "C"
       if (type_lin == 0)
         rc = gf::cg_solve(c, c.mat[GF_MAT_SYSTEM].val.p, vel, rhs, 1.e-10, false,
                           cg_max_iterations(c, max_iterations_lin), &it, &res); // :540-551
+      else if (direct_apply(c, c.mat[GF_MAT_SYSTEM].val.p, rhs, vel, true))
+        rc = GF_OK; // SparseDirectUMFPACK (:556-563); A is constant: factorised once
       else
         {
           uint32_t it2;
@@ -1186,6 +1260,26 @@ extern "C"
         *halo_us = 1e3 * double(ms_h) / n_reps;
       if (allreduce_us)
         *allreduce_us = 1e3 * double(ms_a) / n_reps;
+      return GF_OK;
+    });
+  }
+
+  int gf_direct_info(gf_handle h, int64_t *n_solves, int64_t *half_bandwidth,
+                     double *last_residual)
+  {
+    return guarded(h, [&](gf_context &c) {
+      const bool ok = c.operator_kind == 0 && gf::direct_available(c);
+      GF_REQUIRE(ok, GF_ERR_UNSUPPORTED,
+                 "direct solver not in use: " +
+                   (c.direct_mode == 2 ? std::string("GF_OPT_DIRECT_SOLVER = 2") :
+                                         (c.operator_kind != 0 ? std::string("matrix-free operator") :
+                                                                 c.direct.why)));
+      if (n_solves)
+        *n_solves = c.direct.n_solves;
+      if (half_bandwidth)
+        *half_bandwidth = c.direct.w;
+      if (last_residual)
+        *last_residual = c.direct.last_residual;
       return GF_OK;
     });
   }

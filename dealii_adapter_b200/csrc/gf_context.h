@@ -110,6 +110,20 @@ namespace gf
     DevBuf<double> Mref; // [npc][npc] sum_q w N_a N_b
   };
 
+  // band Cholesky for 'Solver type = Direct' (direct.cu, direct_band.cuh)
+  struct DirectBand
+  {
+    bool        analysed = false, usable = false, factored = false;
+    bool        factor_is_system_matrix = false; // linear model: A is constant, factor once
+    std::string why;                             // why it is not usable
+    int64_t     n = 0, w = 0, ld = 0;            // scalar size, half bandwidth, band leading dim
+    int64_t     n_solves = 0;                    // solves answered by the band Cholesky
+    double      last_residual = 0;               // ||b - A x|| / ||b|| of the last one
+    DevBuf<int32_t> node_new;                    // [n_nodes] reverse Cuthill-McKee: old -> new
+    DevBuf<double>  band, xp, tmp;
+    DevBuf<int>     info;
+  };
+
   // CG scalars living on the device; the host polls `status` every check interval
   struct CGScalars
   {
@@ -308,6 +322,8 @@ struct gf_context
   int  cg_initial_guess = 1; // GF_OPT_CG_INITIAL_GUESS
   int  operator_kind  = 0;
   bool lin_assembled  = false;
+  int  direct_mode    = 0;     // GF_OPT_DIRECT_SOLVER: 0 auto, 1 band Cholesky or error, 2 tight CG
+  gf::DirectBand direct;
   bool defer_tangent  = false; // scatter / preconditioner / multigrid update on first use
   bool tangent_pending = false; // K_e of the last assembly not yet scattered (api.cu)
   bool mg_update_pending = false; // tangent scattered, multigrid update (collective) still due
@@ -443,6 +459,10 @@ namespace gf
   void mg_refresh_f32(gf_context &c); // FP32 operator copies of all levels below and incl. c
   void mg_refresh_f32_level(gf_context &c); // this level only (rank-local)
   bool mg_active(const gf_context &c);
+  // direct.cu: 'Solver type = Direct'
+  bool direct_available(gf_context &c);                  // ordering + memory check (cached)
+  bool direct_factor(gf_context &c, const double *A);    // false: not positive definite
+  void direct_solve(gf_context &c, const double *b, double *x);
   // coarse_solve.cu
   bool coarse_solve_single_launch(gf_context &c, const double *val, const double *b, double *x,
                                   int degree, double ratio);

@@ -177,7 +177,7 @@ extern "C"
                                   zero. The stopping criterion tol*||b|| (:1171-1172) is unchanged, so
                                   the Newton history agrees within that tolerance; CG needs ~25 %
                                   fewer iterations per timestep. */
-    GF_OPT_MG_MATRIX_PRECISION /* 0 (default): the V-cycle streams the FP64 level matrices;
+    GF_OPT_MG_MATRIX_PRECISION, /* 0 (default): the V-cycle streams the FP64 level matrices;
                                   1: it streams FP32 copies of them (half the HBM bytes per smoother
                                   / residual application), accumulating in FP64;
                                   2: FP32 copies, x staged and accumulated in FP32 as well (vectors
@@ -185,6 +185,15 @@ extern "C"
                                   The outer CG (operator, residual, tolerance: nonlinear:1171-1187,
                                   linear:540-552) stays FP64 in every case, so the solve converges
                                   to the same tolerance; only the SSOR replacement changes. */
+    GF_OPT_DIRECT_SOLVER        /* 'Solver type = Direct' (type_lin = 1; SparseDirectUMFPACK,
+                                  nonlinear_elasticity.cc:1192-1200, linear_elasticity.cc:556-563).
+                                  0 (default): band Cholesky of the SPD matrix on the device in a
+                                  reverse Cuthill-McKee ordering + one refinement step, where the
+                                  band fits 40 % of the free memory (GF_DIRECT_BUDGET_MB lowers the
+                                  budget), the system has at most 400,000 DoFs (GF_DIRECT_MAX_DOFS)
+                                  and the handle is not partitioned; else the CG run to
+                                  1e-13 from a zero guess. 1: band Cholesky or GF_ERR_UNSUPPORTED /
+                                  GF_ERR_NOT_CONVERGED (not positive definite). 2: always the CG. */
   };
 
   /* device-time breakdown accumulated while GF_OPT_PROFILE = 1 (CUDA events on the library's
@@ -331,6 +340,13 @@ extern "C"
    * all-reduces, each batch bracketed by CUDA events; average microseconds per operation */
   int gf_comm_timed(gf_handle h, int n_reps, double *halo_us, double *allreduce_us);
   int gf_profile_get(gf_handle h, gf_profile *out, int reset);
+  /* 'Solver type = Direct' diagnostics (GF_OPT_DIRECT_SOLVER): solves answered by the band
+   * Cholesky so far, half bandwidth of the matrix in the reverse Cuthill-McKee ordering (scalar
+   * rows), ||b - A x|| / ||b|| of the last such solve. Returns GF_ERR_UNSUPPORTED with the reason
+   * in gf_last_error() when the handle runs the CG stand-in instead (partitioned handle, band
+   * beyond the memory budget, ...). Any pointer may be NULL. */
+  int gf_direct_info(gf_handle h, int64_t *n_solves, int64_t *half_bandwidth,
+                     double *last_residual);
   int gf_synchronize(gf_handle h);
   /* CUDA events on the library's own stream (torch.cuda.Event only sees torch's stream):
    * record slot 0..7, then elapsed milliseconds between two recorded slots (synchronises). */

@@ -4,7 +4,9 @@
 #include <cstring>
 
 #include "assemble_nl_generic.cuh"
+#include "direct_band.cuh"
 #include "fe_tables_host.h"
+#include "rcm.h"
 
 namespace
 {
@@ -43,8 +45,52 @@ namespace
   }
 } // namespace
 
+namespace
+{
+  // kernel<<<grid, block, smem>>>(args...) of the product's drivers (db_factor, db_solve)
+  struct EmuLaunch
+  {
+    template <class... KA, class... A>
+    void operator()(unsigned grid, unsigned block, size_t smem, void (*kernel)(KA...), A... args)
+    {
+      gf_emu::launch(grid, block, smem, [&] { kernel(args...); });
+    }
+  };
+} // namespace
+
 extern "C"
 {
+  // 'Solver type = Direct': reverse Cuthill-McKee + band Cholesky + substitution on a matrix in the
+  // library's block-row format. Returns the info flag of the factorisation (0 = positive definite);
+  // w_out: [0] = half bandwidth (scalar) in the RCM ordering, [1] = in the given ordering.
+  int emu_direct_solve(int64_t n_nodes, int dim, const int32_t *brow_ptr, const int64_t *val_ptr,
+                       const int32_t *bcol, const double *val, const double *b, double *x,
+                       int64_t *w_out)
+  {
+    std::vector<int32_t> node_new;
+    const int64_t        wn = gf::rcm_order(n_nodes, brow_ptr, bcol, node_new);
+    int64_t              w0 = 0;
+    for (int64_t a = 0; a < n_nodes; ++a)
+      for (int32_t k = brow_ptr[a]; k < brow_ptr[a + 1]; ++k)
+        w0 = std::max<int64_t>(w0, std::abs(a - int64_t(bcol[k])));
+    const int64_t n = n_nodes * dim, w = wn * dim + dim - 1, ld = w + gf::DB_NB;
+    w_out[0]        = w;
+    w_out[1]        = w0 * dim + dim - 1;
+    std::vector<double> band(size_t(n) * ld, 0.0), xp(n, 0.0), tmp(gf::DB_NB, 0.0);
+    std::vector<double> bb(b, b + n);
+    int                 info = 0;
+    EmuLaunch           launch;
+    launch(unsigned(std::min<int64_t>(n_nodes, 7)), 64u, size_t(0), gf::db_fill_kernel, n_nodes, dim,
+           brow_ptr, val_ptr, bcol, val, (const int32_t *)node_new.data(), ld, band.data());
+    gf::db_factor(launch, n, w, ld, band.data(), &info);
+    launch(3u, 64u, size_t(0), gf::db_permute_kernel, n_nodes, dim,
+           (const int32_t *)node_new.data(), true, bb.data(), xp.data());
+    gf::db_solve(launch, n, w, ld, (const double *)band.data(), xp.data(), tmp.data());
+    launch(3u, 64u, size_t(0), gf::db_permute_kernel, n_nodes, dim,
+           (const int32_t *)node_new.data(), false, x, xp.data());
+    return info;
+  }
+
   // params: kappa, mu, rho, alpha_1, body_force[3]. ke: [n_cells][dpc][dpc] (only the node blocks
   // b <= a are written), re: [n_cells][dpc]. Returns the det F error flag.
   int emu_nl_cells(int dim, int p, int64_t n_cells, const int32_t *cell_nodes, const double *geom,

@@ -129,3 +129,69 @@ def test_generic_cell_and_face_kernels_match_oracle(emu, dim, p, reps, block):
     o.nl_assemble_system()
     ref = o.get(orc.NL_SYSTEM_RHS)
     assert np.abs(rhs - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+# ------------------------------------------------------------------------------------------------
+# 'Solver type = Direct' (parameters.prm:43): csrc/direct_band.cuh + rcm.h, same source on the CPU
+# ------------------------------------------------------------------------------------------------
+def block_row_format(A, dim):
+    """scipy CSR (dof = node * dim + c) -> the library's block-row arrays (gf_context.h)."""
+    n_nodes = A.shape[0] // dim
+    brow_ptr, bcol, val_ptr, vals = [0], [], [0], []
+    Ad = A.tocsr()
+    for a in range(n_nodes):
+        cols = np.unique(np.concatenate([Ad.indices[Ad.indptr[a * dim + r]:Ad.indptr[a * dim + r + 1]] // dim
+                                         for r in range(dim)]))
+        stride = (len(cols) * dim + 1) & ~1
+        rows = np.zeros((dim, stride))
+        dense = Ad[a * dim:(a + 1) * dim, :].toarray()
+        for k, bnode in enumerate(cols):
+            rows[:, k * dim:(k + 1) * dim] = dense[:, bnode * dim:(bnode + 1) * dim]
+        bcol += list(cols)
+        brow_ptr.append(len(bcol))
+        vals.append(rows.reshape(-1))
+        val_ptr.append(val_ptr[-1] + dim * stride)
+    return (np.array(brow_ptr, dtype=np.int32), np.array(val_ptr, dtype=np.int64),
+            np.array(bcol, dtype=np.int32), np.concatenate(vals))
+
+
+@pytest.mark.parametrize("dim,p,reps,numbering", [(2, 2, [9, 3], "lexicographic"),
+                                                  (2, 3, [6, 2], "cellwise"),
+                                                  (3, 1, [3, 7, 2], "lexicographic"),
+                                                  (3, 2, [2, 4, 1], "cellwise")])
+def test_band_cholesky_solves_the_tangent_system(emu, dim, p, reps, numbering):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from oracle import oracle_py as orc
+    emu.emu_direct_solve.restype = C.c_int
+    emu.emu_direct_solve.argtypes = [C.c_int64, C.c_int] + [C.c_void_p] * 7
+    prob = make_problem(nl_params(poly_degree=p), dim, reps=reps, numbering=numbering)
+    o = orc.Oracle(prob)
+    L = (np.array(prob.mesh.p1) - np.array(prob.mesh.p0)).min()
+    o.set(orc.NL_TOTAL_DISPLACEMENT, smooth_field(prob, 0.03 * L, seed=2))
+    o.format_precice_to_deal(np.tile([1500.0, -300.0, 200.0][:dim], prob.n_iface_nodes),
+                             orc.NL_EXTERNAL_STRESS)
+    o.nl_assemble_system()
+    rowptr, col = o.pattern()
+    n = prob.n_dofs
+    A = sp.csr_matrix((o.values(orc.MAT_TANGENT), col, rowptr), shape=(n, n))
+    b = o.get(orc.NL_SYSTEM_RHS)
+    brow_ptr, val_ptr, bcol, val = block_row_format(A, dim)
+    x = np.zeros(n)
+    w = np.zeros(2, dtype=np.int64)
+    info = emu.emu_direct_solve(n // dim, dim, brow_ptr.ctypes.data, val_ptr.ctypes.data,
+                                bcol.ctypes.data, val.ctypes.data, b.ctypes.data, x.ctypes.data,
+                                w.ctypes.data)
+    assert info == 0
+    ref = spla.spsolve(A.tocsc(), b)
+    assert np.abs(x - ref).max() <= 1e-9 * np.abs(ref).max()
+    assert np.abs(A @ x - b).max() <= 1e-10 * np.abs(b).max()
+    assert w[0] <= w[1]                 # RCM never widens these meshes' band
+    # an indefinite matrix is reported, not factorised silently
+    val_bad = val.copy()
+    val_bad[0] = -abs(val_bad[0])       # first diagonal entry (node 0 couples to itself first)
+    assert bcol[0] == 0
+    info = emu.emu_direct_solve(n // dim, dim, brow_ptr.ctypes.data, val_ptr.ctypes.data,
+                                bcol.ctypes.data, val_bad.ctypes.data, b.ctypes.data, x.ctypes.data,
+                                w.ctypes.data)
+    assert info > 0

@@ -248,8 +248,9 @@ def test_shipped_parameter_file_runs_unchanged_through_the_cpp_driver(tmp_path, 
         "dimensions = 2\ntime-window-size = 0.005\nmax-time-windows = 5\nsub-iterations = 1\n"
         "traction = 0.0,-20.0\nramp-time = 0.0\nwatch-point = 0.6,0.2\n"
         "watch-point-file = watchpoint.log\n")
+    import os
     r = subprocess.run([exe, "parameters.prm"], cwd=tmp_path, capture_output=True, text=True,
-                       timeout=600)
+                       timeout=600, env=dict(os.environ, GF_DIRECT_SOLVER="auto"))
     assert r.returncode == 0, r.stderr + r.stdout[-2000:]
     assert "Polynomial degree: 3" in r.stdout
     vtk = (tmp_path / "dealii-output" / "solution-000.vtk").read_text()
@@ -269,3 +270,84 @@ def test_shipped_parameter_file_runs_unchanged_through_the_cpp_driver(tmp_path, 
         o.lin_step()
         d = o.format_deal_to_precice(orc.LIN_DISPLACEMENT).reshape(-1, 2)[k]
         assert rel_err(log[step, 4:6], d) < 1e-8
+
+
+# ------------------------------------------------------------------------------------------------
+# 'Solver type = Direct' (the shipped default, parameters.prm:43): band Cholesky on the device
+# (csrc/direct_band.cuh; CPU emulation: tests/test_cuda_emulation.py). Also first run on hardware.
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,degree,scenario,reps,load", [
+    (2, 2, "FSI3", [18, 3], (0.0, -1500.0)),
+    (3, 2, "PF", [3, 6, 2], (1500.0, 0.0, 0.0)),
+    (2, 3, "FSI3", [18, 3], (0.0, -1500.0)),
+])
+def test_direct_solver_band_cholesky_nonlinear(libs, dim, degree, scenario, reps, load):
+    capi, solvers, orc = libs
+    p = nl_params(poly_degree=degree, scenario=scenario, type_lin="Direct", delta_t=0.01)
+    prob = make_problem(p, dim, reps=reps)
+    n = prob.n_iface_nodes
+    traction = lambda t, it: np.tile(np.array(load) * min(1.0, t / 0.03), n)
+    part = solvers.FakeParticipant(dim, 3, p.delta_t, traction)
+    solid = solvers.Solid(prob, part)
+    solid.handle.set_option(capi.OPT_DIRECT_SOLVER, 0)         # auto: band Cholesky where it fits
+    solid.run()
+    n_solves, w, res = solid.handle.direct_info()
+    assert n_solves == sum(len(r) for r in solid.history)      # every solve by the factorisation
+    assert res <= 1e-10 and 0 < w < prob.n_dofs
+    o, counts, written = run_oracle_nonlinear(orc, prob, 3, traction)
+    assert [len(r) for r in solid.history] == counts
+    for (w_, it, data), ref in zip(part.written, written):
+        assert rel_err(data, ref) < 1e-8
+    # the CG stand-in (GF_OPT_DIRECT_SOLVER = 2) gives the same displacements
+    part2 = solvers.FakeParticipant(dim, 3, p.delta_t, traction)
+    solid2 = solvers.Solid(prob, part2)
+    solid2.handle.set_option(capi.OPT_DIRECT_SOLVER, 2)
+    solid2.run()
+    with pytest.raises(capi.GraftError) as e:
+        solid2.handle.direct_info()
+    assert e.value.code == capi.GF_ERR_UNSUPPORTED
+    for a, b in zip(part.written, part2.written):
+        assert rel_err(a[2], b[2]) < 1e-9
+    solid.handle.close()
+    solid2.handle.close()
+
+
+def test_direct_solver_linear_factorises_once_and_falls_back_beyond_the_budget(libs, monkeypatch):
+    capi, solvers, orc = libs
+    p = lin_params(poly_degree=2, type_lin="Direct")
+    prob = make_problem(p, 2, reps=[6, 36])
+    n = prob.n_iface_nodes
+    traction = lambda t, it: np.tile(np.array([50.0, 0.0]), n)
+    o = orc.Oracle(prob)
+    o.lin_assemble_system()
+    refs = []
+    for step in range(4):
+        o.format_precice_to_deal(traction(0, 0), orc.LIN_STRESS)
+        o.lin_step()
+        refs.append(o.format_deal_to_precice(orc.LIN_DISPLACEMENT))
+    part = solvers.FakeParticipant(2, 4, p.delta_t, traction)
+    ed = solvers.ElastoDynamics(prob, part)
+    ed.handle.set_option(capi.OPT_DIRECT_SOLVER, 0)
+    ed.run()
+    n_solves, w, res = ed.handle.direct_info()
+    assert n_solves == 4 and res <= 1e-10
+    for step in range(4):
+        assert rel_err(part.written[step][2], refs[step]) < 1e-8
+    ed.handle.close()
+    # band beyond the memory budget: the handle answers with the CG stand-in, same results
+    monkeypatch.setenv("GF_DIRECT_BUDGET_MB", "0.01")
+    part = solvers.FakeParticipant(2, 4, p.delta_t, traction)
+    ed = solvers.ElastoDynamics(prob, part)
+    ed.handle.set_option(capi.OPT_DIRECT_SOLVER, 0)
+    ed.run()
+    with pytest.raises(capi.GraftError) as e:
+        ed.handle.direct_info()
+    assert e.value.code == capi.GF_ERR_UNSUPPORTED and "budget" in str(e.value)
+    for step in range(4):
+        assert rel_err(part.written[step][2], refs[step]) < 1e-8
+    # ... and GF_OPT_DIRECT_SOLVER = 1 insists
+    ed.handle.set_option(capi.OPT_DIRECT_SOLVER, 1)
+    with pytest.raises(capi.GraftError) as e:
+        ed.handle.lin_step(1, 1.0)
+    assert e.value.code == capi.GF_ERR_UNSUPPORTED
+    ed.handle.close()
