@@ -115,6 +115,7 @@ int run(unsigned npc, unsigned nq, unsigned nqf, unsigned n_faces)
       fprintf(stderr, "ref_assembler_driver: short input\n");
       return 2;
     }
+  read_shim_numbering(std::cin, dpc); // optional: FESystem numbering of degree >= 3
 
   Solid<dim, double> solid;
   solid.fe.dofs_per_cell      = dpc;

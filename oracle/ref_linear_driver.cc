@@ -62,6 +62,7 @@ int run(unsigned npc, unsigned nq, unsigned nqf, unsigned n_faces)
       fprintf(stderr, "ref_linear_driver: short input\n");
       return 2;
     }
+  read_shim_numbering(std::cin, dofs_per_cell); // optional: FESystem numbering of degree >= 3
   FESystem<dim> fe;
   fe.dofs_per_cell = dofs_per_cell;
   const typename DoFHandler<dim>::active_cell_iterator cell = &cell_object;

@@ -103,19 +103,56 @@ namespace dealii
       throw std::runtime_error("not part of the stand-in");
     }
   };
+  // system_to_component_index of local dof i: (node, component); empty tables = node-major
+  struct ShimNumbering
+  {
+    std::vector<unsigned> node_of, comp_of;
+    static ShimNumbering &get()
+    {
+      static ShimNumbering n;
+      return n;
+    }
+  };
+  template <int dim>
+  inline unsigned shim_node(unsigned i)
+  {
+    const auto &n = ShimNumbering::get();
+    return n.node_of.empty() ? i / dim : n.node_of[i];
+  }
+  template <int dim>
+  inline unsigned shim_component(unsigned i)
+  {
+    const auto &n = ShimNumbering::get();
+    return n.comp_of.empty() ? i % dim : n.comp_of[i];
+  }
+  // optional tail of a driver's input: node_of[dpc] comp_of[dpc]
+  inline void read_shim_numbering(std::istream &in, unsigned dpc)
+  {
+    auto &              n = ShimNumbering::get();
+    std::vector<unsigned> a(dpc), b(dpc);
+    for (unsigned i = 0; i < dpc; ++i)
+      if (!(in >> a[i]))
+        return;
+    for (unsigned i = 0; i < dpc; ++i)
+      if (!(in >> b[i]))
+        return;
+    n.node_of = a;
+    n.comp_of = b;
+  }
   template <int dim>
   class FiniteElement
   {
   public:
     unsigned dofs_per_cell = 0;
-    // FESystem(FE_Q(p), dim): one base element, dof i = node * dim + component
+    // FESystem(FE_Q(p), dim): one base element; dof i = node * dim + component up to degree 2,
+    // the table of the driver's input (entity-major numbering) beyond
     std::pair<std::pair<unsigned, unsigned>, unsigned> system_to_base_index(unsigned i) const
     {
-      return {{0u, i % dim}, i / dim};
+      return {{0u, shim_component<dim>(i)}, shim_node<dim>(i)};
     }
     std::pair<unsigned, unsigned> system_to_component_index(unsigned i) const
     {
-      return {i % dim, i / dim};
+      return {shim_component<dim>(i), shim_node<dim>(i)};
     }
   };
   template <int dim>
@@ -222,7 +259,7 @@ namespace dealii
     double shape_value(unsigned i, unsigned q) const
     {
       const auto &t = ShimTables<dim>::get();
-      return face_values ? t.Nf[face][q * t.npc + i / dim] : t.N[q * t.npc + i / dim];
+      return face_values ? t.Nf[face][q * t.npc + shim_node<dim>(i)] : t.N[q * t.npc + shim_node<dim>(i)];
     }
     // gradient of the only non-zero component of shape function i (FEValues::shape_grad)
     Tensor<1, dim> shape_grad(unsigned i, unsigned q) const
@@ -230,7 +267,7 @@ namespace dealii
       const auto &   t = ShimTables<dim>::get();
       Tensor<1, dim> g;
       for (int d = 0; d < dim; ++d)
-        g[d] = t.gradN[(q * t.npc + i / dim) * dim + d];
+        g[d] = t.gradN[(q * t.npc + shim_node<dim>(i)) * dim + d];
       return g;
     }
     // FEValuesBase::get_function_values for a vector-valued element
@@ -242,7 +279,7 @@ namespace dealii
           for (int d = 0; d < dim; ++d)
             out[q][d] = 0.0;
           for (unsigned k = 0; k < dofs_per_cell; ++k)
-            out[q][k % dim] += global(cell->dofs[k]) * shape_value(k, q);
+            out[q][shim_component<dim>(k)] += global(cell->dofs[k]) * shape_value(k, q);
         }
     }
     double JxW(unsigned q) const
@@ -261,11 +298,11 @@ namespace dealii
     struct View
     {
       const FEValuesShim &fv;
-      // value / gradient of vector-valued shape function k: only component k % dim is non-zero
+      // value / gradient of vector-valued shape function k: only its own component is non-zero
       Tensor<1, dim> value(unsigned k, unsigned q) const
       {
         Tensor<1, dim> r;
-        r[k % dim] = fv.shape_value(k, q);
+        r[shim_component<dim>(k)] = fv.shape_value(k, q);
         return r;
       }
       Tensor<2, dim> gradient(unsigned k, unsigned q) const
@@ -273,7 +310,7 @@ namespace dealii
         const auto &   t = ShimTables<dim>::get();
         Tensor<2, dim> r;
         for (int d = 0; d < dim; ++d)
-          r[k % dim][d] = t.gradN[(q * t.npc + k / dim) * dim + d];
+          r[shim_component<dim>(k)][d] = t.gradN[(q * t.npc + shim_node<dim>(k)) * dim + d];
         return r;
       }
       template <class V>
@@ -283,7 +320,7 @@ namespace dealii
           {
             out[q] = Tensor<1, dim>();
             for (unsigned k = 0; k < fv.dofs_per_cell; ++k)
-              out[q][k % dim] += global(fv.cell->dofs[k]) * fv.shape_value(k, q);
+              out[q][shim_component<dim>(k)] += global(fv.cell->dofs[k]) * fv.shape_value(k, q);
           }
       }
       template <class V>
@@ -296,7 +333,7 @@ namespace dealii
               {
                 const Tensor<2, dim> g = gradient(k, q);
                 for (int d = 0; d < dim; ++d)
-                  out[q][k % dim][d] += global(fv.cell->dofs[k]) * g[k % dim][d];
+                  out[q][shim_component<dim>(k)][d] += global(fv.cell->dofs[k]) * g[shim_component<dim>(k)][d];
               }
           }
       }

@@ -119,7 +119,11 @@ def assembly_cases():
             (2, 2, [0.02, 0.03], [0, 1, 3], (0.0, -9.81, 0.0)),
             (3, 1, [0.1, 0.2, 0.15], [0, 1, 3], (0.0, 0.0, 0.0)),
             (3, 2, [0.05, 0.04, 0.06], [0, 1, 3], (1.5, -9.81, 0.5)),
-            (3, 2, [0.004, 0.007, 0.0125], [], (0.0, 0.0, 0.0))]
+            (3, 2, [0.004, 0.007, 0.0125], [], (0.0, 0.0, 0.0)),
+            # degrees of the shipped parameter files (parameters.prm:21, nonlinear_elasticity.prm:24)
+            (2, 3, [0.03, 0.02], [0, 1, 3], (0.0, -9.81, 0.0)),
+            (2, 4, [0.05, 0.04], [0, 1, 3], (0.0, 0.0, 0.0)),
+            (3, 3, [0.05, 0.04, 0.06], [0, 1, 3], (1.5, -9.81, 0.5))]
 
 
 def run_assembly_case(k, dim, p, h, faces, body_force):
@@ -135,7 +139,8 @@ def run_assembly_case(k, dim, p, h, faces, body_force):
     JxW = w * np.prod(h)
     mu, nu, rho, beta, dt = 0.5e6, 0.4, 1000.0, 0.25, 0.01
     alpha_1 = 1.0 / (beta * dt * dt)
-    u = 0.15 * min(h) * rng.uniform(-1, 1, dpc)
+    # random nodal values: smaller for the closely spaced Gauss-Lobatto nodes (det F must stay > 0)
+    u = (0.15 if p <= 2 else 0.15 / (p * p)) * min(h) * rng.uniform(-1, 1, dpc)
     acc = 50.0 * rng.uniform(-1, 1, dpc)
     stress = 2000.0 * rng.uniform(-1, 1, dpc)
     ft = face_tables(dim, p, nq1, h, faces)
@@ -145,6 +150,9 @@ def run_assembly_case(k, dim, p, h, faces, body_force):
         Nf, JxWf, normal = ft[f]
         words += [f, 7] + list(Nf.reshape(-1)) + list(JxWf) + list(normal.reshape(-1))
     words += list(u) + list(acc) + list(stress)
+    if p > 2:       # FESystem local numbering beyond node-major (system_to_component_index)
+        s2c = rf.system_to_node_component(dim, p)
+        words += [a for a, c in s2c] + [c for a, c in s2c]
     text = " ".join(repr(float(x)) if isinstance(x, (float, np.floating)) else str(int(x)) for x in words)
     res = subprocess.run([ASM_DRIVER], input=text, capture_output=True, text=True, check=True).stdout
     rows = [l.split() for l in res.strip().split("\n")]
@@ -177,6 +185,9 @@ def run_linear_case(k, dim, p, h, faces):
         Nf, JxWf, normal = ft[f]
         words += [f, 6] + list(Nf.reshape(-1)) + list(JxWf)
     words += list(stress)
+    if p > 2:
+        s2c = rf.system_to_node_component(dim, p)
+        words += [a for a, c in s2c] + [c for a, c in s2c]
     text = " ".join(repr(float(x)) if isinstance(x, (float, np.floating)) else str(int(x)) for x in words)
     res = subprocess.run([LIN_DRIVER], input=text, capture_output=True, text=True, check=True).stdout
     rows = [l.split() for l in res.strip().split("\n")]
@@ -188,7 +199,9 @@ def run_linear_case(k, dim, p, h, faces):
 
 def linear_cases():
     return [(2, 1, [0.1, 0.05], [0, 1, 3]), (2, 2, [0.1 / 3, 1.0 / 18], [0, 1, 3]),
-            (3, 1, [0.1, 0.2, 0.15], [0, 1, 3]), (3, 2, [0.05, 0.04, 0.06], [0, 1, 3])]
+            (3, 1, [0.1, 0.2, 0.15], [0, 1, 3]), (3, 2, [0.05, 0.04, 0.06], [0, 1, 3]),
+            (2, 3, [0.1 / 3, 1.0 / 18], [0, 1, 3]), (2, 4, [0.05, 0.04], [0, 1, 3]),
+            (3, 3, [0.05, 0.04, 0.06], [0, 1, 3])]
 
 
 def fmt(words):

@@ -92,8 +92,18 @@ def one_cell_oracle(orc, dim, degree, h, faces, body_force, mu, nu, rho, beta, d
     if not len(faces):
         prob.iface_cell = prob.iface_cell[:0]
         prob.iface_face_no = prob.iface_face_no[:0]
-    assert np.array_equal(prob.mesh.cell_dofs.reshape(-1), np.arange(prob.n_dofs))   # global = local
+    # the reference block works in the cell's local numbering: local dof i = global dof cd[i]
+    # (the identity up to degree 2, where the FESystem numbering is node-major)
+    cd = prob.mesh.cell_dofs.reshape(-1)
+    assert sorted(cd.tolist()) == list(range(prob.n_dofs))
+    assert degree > 2 or np.array_equal(cd, np.arange(prob.n_dofs))
     return prob, orc.Oracle(prob, n_threads=1)
+
+
+def to_global(prob, v_local):
+    out = np.zeros(prob.n_dofs)
+    out[prob.mesh.cell_dofs.reshape(-1)] = v_local
+    return out
 
 
 def test_oracle_cell_assembly_equals_the_reference_assembly_block(native_libs, ref):
@@ -102,7 +112,7 @@ def test_oracle_cell_assembly_equals_the_reference_assembly_block(native_libs, r
     against the oracle assembling the same one-cell problem."""
     from oracle import oracle_py as orc
     n = int(ref["n_assembly"])
-    assert n == 5
+    assert n == 8                       # 5 cases of degree 1-2, then 2D Q3, 2D Q4, 3D Q3
     for k in range(n):
         meta = ref["asm%d_meta" % k]
         dim, degree = int(meta[0]), int(meta[1])
@@ -110,13 +120,14 @@ def test_oracle_cell_assembly_equals_the_reference_assembly_block(native_libs, r
         mu, nu, rho, beta, dt = meta[8:13]
         faces = ref["asm%d_faces" % k]
         prob, o = one_cell_oracle(orc, dim, degree, h, faces, body_force, mu, nu, rho, beta, dt)
-        o.set(orc.NL_TOTAL_DISPLACEMENT, ref["asm%d_u" % k])
+        cd = prob.mesh.cell_dofs.reshape(-1)
+        o.set(orc.NL_TOTAL_DISPLACEMENT, to_global(prob, ref["asm%d_u" % k]))
         o.set(orc.NL_SOLUTION_DELTA, np.zeros(prob.n_dofs))
-        o.set(orc.NL_ACCELERATION, ref["asm%d_acc" % k])
-        o.set(orc.NL_EXTERNAL_STRESS, ref["asm%d_stress" % k])
+        o.set(orc.NL_ACCELERATION, to_global(prob, ref["asm%d_acc" % k]))
+        o.set(orc.NL_EXTERNAL_STRESS, to_global(prob, ref["asm%d_stress" % k]))
         o.nl_assemble_system()
-        K = o.csr(orc.MAT_TANGENT).toarray()
-        r = o.get(orc.NL_SYSTEM_RHS)
+        K = o.csr(orc.MAT_TANGENT).toarray()[np.ix_(cd, cd)]
+        r = o.get(orc.NL_SYSTEM_RHS)[cd]
         K_ref, r_ref = ref["asm%d_K" % k], ref["asm%d_r" % k]
         assert np.abs(K - K_ref).max() <= 1e-12 * np.abs(K_ref).max(), k
         assert np.abs(r - r_ref).max() <= 1e-12 * np.abs(r_ref).max(), k
@@ -124,10 +135,10 @@ def test_oracle_cell_assembly_equals_the_reference_assembly_block(native_libs, r
         if len(faces):
             # the Neumann term is really in there: without the faces the residual differs
             prob2, o2 = one_cell_oracle(orc, dim, degree, h, [], body_force, mu, nu, rho, beta, dt)
-            o2.set(orc.NL_TOTAL_DISPLACEMENT, ref["asm%d_u" % k])
-            o2.set(orc.NL_ACCELERATION, ref["asm%d_acc" % k])
+            o2.set(orc.NL_TOTAL_DISPLACEMENT, to_global(prob, ref["asm%d_u" % k]))
+            o2.set(orc.NL_ACCELERATION, to_global(prob, ref["asm%d_acc" % k]))
             o2.nl_assemble_system()
-            assert np.abs(o2.get(orc.NL_SYSTEM_RHS) - r_ref).max() > 1e-6 * np.abs(r_ref).max()
+            assert np.abs(o2.get(orc.NL_SYSTEM_RHS)[cd] - r_ref).max() > 1e-6 * np.abs(r_ref).max()
 
 
 def one_cell_linear_problem(dim, degree, h, mu, nu):
@@ -137,7 +148,7 @@ def one_cell_linear_problem(dim, degree, h, mu, nu):
                         box=([0.0] * dim, list(h[:dim])))
     prob.constrained = np.zeros_like(prob.constrained)
     assert sorted(prob.iface_face_no.tolist()) == [0, 1, 3]
-    assert np.array_equal(prob.mesh.cell_dofs.reshape(-1), np.arange(prob.n_dofs))
+    assert degree > 2 or np.array_equal(prob.mesh.cell_dofs.reshape(-1), np.arange(prob.n_dofs))
     return prob
 
 
@@ -145,22 +156,23 @@ def test_oracle_linear_cell_matrix_and_loading_equal_the_reference_loops(native_
     """linear_elasticity.cc:289-323 (local stiffness) and :487-512 (consistent loading on the
     interface faces), the reference's own statements on one cell, against the oracle."""
     from oracle import oracle_py as orc
-    assert int(ref["n_linear"]) == 4
-    for k in range(4):
+    assert int(ref["n_linear"]) == 7    # 4 cases of degree 1-2, then 2D Q3, 2D Q4, 3D Q3
+    for k in range(7):
         meta = ref["lin%d_meta" % k]
         dim, degree, h, mu, nu = int(meta[0]), int(meta[1]), meta[2:5], meta[5], meta[6]
         prob = one_cell_linear_problem(dim, degree, h, mu, nu)
+        cd = prob.mesh.cell_dofs.reshape(-1)
         o = orc.Oracle(prob, n_threads=1)
         o.lin_assemble_system()
-        K = o.csr(orc.MAT_STIFFNESS).toarray()
+        K = o.csr(orc.MAT_STIFFNESS).toarray()[np.ix_(cd, cd)]
         K_ref, F_ref = ref["lin%d_K" % k], ref["lin%d_F" % k]
         assert np.abs(K - K_ref).max() <= 1e-12 * np.abs(K_ref).max(), k
-        o.set(orc.LIN_STRESS, ref["lin%d_stress" % k])
+        o.set(orc.LIN_STRESS, to_global(prob, ref["lin%d_stress" % k]))
         o.lin_assemble_rhs()                    # old_stress <- the consistent loading (:405-409)
-        F = o.get(orc.LIN_OLD_STRESS)
+        F = o.get(orc.LIN_OLD_STRESS)[cd]
         assert np.abs(F - F_ref).max() <= 1e-12 * np.abs(F_ref).max(), k
         dt, theta = prob.params.delta_t, prob.params.theta
-        assert np.abs(o.get(orc.LIN_SYSTEM_RHS) - dt * theta * F_ref).max() <= 1e-12 * dt * theta * np.abs(F_ref).max()
+        assert np.abs(o.get(orc.LIN_SYSTEM_RHS)[cd] - dt * theta * F_ref).max() <= 1e-12 * dt * theta * np.abs(F_ref).max()
 
 
 def test_oracle_newmark_updates_and_norms_equal_the_reference_members(native_libs, ref):

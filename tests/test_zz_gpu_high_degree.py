@@ -351,3 +351,77 @@ def test_direct_solver_linear_factorises_once_and_falls_back_beyond_the_budget(l
         ed.handle.lin_step(1, 1.0)
     assert e.value.code == capi.GF_ERR_UNSUPPORTED
     ed.handle.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's OWN assembly blocks at degree 3 / 4 (tests/golden/reference_vectors.npz, cases
+# added with the high-degree support; CPU: tests/test_reference_pins.py pins the oracle with them)
+# ------------------------------------------------------------------------------------------------
+def _golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                "reference_vectors.npz"))
+
+
+def _to_global(prob, v_local):
+    out = np.zeros(prob.n_dofs)
+    out[prob.mesh.cell_dofs.reshape(-1)] = v_local
+    return out
+
+
+@pytest.mark.parametrize("case", [5, 6, 7])
+def test_device_cell_assembly_equals_the_reference_assembly_block(libs, case):
+    import scipy.sparse as sp
+    capi, solvers, orc = libs
+    ref = _golden()
+    meta = ref["asm%d_meta" % case]
+    dim, degree = int(meta[0]), int(meta[1])
+    h, body_force = meta[2:5], meta[5:8]
+    mu, nu, rho, beta, dt = meta[8:13]
+    assert degree >= 3 and sorted(ref["asm%d_faces" % case].tolist()) == [0, 1, 3]
+    p = nl_params(poly_degree=degree, scenario="PF", mu=mu, nu=nu, rho=rho, beta=beta, delta_t=dt,
+                  body_force=tuple(body_force))
+    prob = make_problem(p, dim, reps=[1] * dim, numbering="cellwise",
+                        box=([0.0] * dim, list(h[:dim])))
+    prob.constrained = np.zeros_like(prob.constrained)
+    cd = prob.mesh.cell_dofs.reshape(-1)       # local dof i of the reference block = global cd[i]
+    hd = capi.Handle(prob)
+    hd.set_vector(capi.NL_TOTAL_DISPLACEMENT, _to_global(prob, ref["asm%d_u" % case]))
+    hd.set_vector(capi.NL_EXTERNAL_STRESS, _to_global(prob, ref["asm%d_stress" % case]))
+    alpha_3 = (1 - 2 * beta) / (2 * beta)      # update_acceleration (:592-599) with v_old = 0
+    hd.set_vector(capi.NL_ACCELERATION_OLD, _to_global(prob, -ref["asm%d_acc" % case] / alpha_3))
+    hd.nl_begin_step()
+    hd.nl_newton_assemble()
+    rowptr, col, val = hd.export_csr(capi.MAT_TANGENT)
+    K = sp.csr_matrix((val, col, rowptr), shape=(prob.n_dofs, prob.n_dofs)).toarray()[np.ix_(cd, cd)]
+    r = hd.get_vector(capi.NL_SYSTEM_RHS)[cd]
+    K_ref, r_ref = ref["asm%d_K" % case], ref["asm%d_r" % case]
+    assert np.abs(K - K_ref).max() <= 1e-12 * np.abs(K_ref).max()
+    assert np.abs(r - r_ref).max() <= 1e-12 * np.abs(r_ref).max()
+    hd.close()
+
+
+@pytest.mark.parametrize("case", [4, 5, 6])
+def test_device_linear_stiffness_and_loading_equal_the_reference_loops(libs, case):
+    import scipy.sparse as sp
+    capi, solvers, orc = libs
+    ref = _golden()
+    meta = ref["lin%d_meta" % case]
+    dim, degree, h, mu, nu = int(meta[0]), int(meta[1]), meta[2:5], meta[5], meta[6]
+    assert degree >= 3
+    p = lin_params(poly_degree=degree, scenario="PF", mu=mu, nu=nu, type_lin="CG")
+    prob = make_problem(p, dim, reps=[1] * dim, numbering="cellwise",
+                        box=([0.0] * dim, list(h[:dim])))
+    prob.constrained = np.zeros_like(prob.constrained)
+    cd = prob.mesh.cell_dofs.reshape(-1)
+    hd = capi.Handle(prob)
+    hd.lin_assemble_once()
+    rowptr, col, val = hd.export_csr(capi.MAT_STIFFNESS)
+    K = sp.csr_matrix((val, col, rowptr), shape=(prob.n_dofs, prob.n_dofs)).toarray()[np.ix_(cd, cd)]
+    K_ref, F_ref = ref["lin%d_K" % case], ref["lin%d_F" % case]
+    assert np.abs(K - K_ref).max() <= 1e-12 * np.abs(K_ref).max()
+    hd.set_vector(capi.LIN_STRESS, _to_global(prob, ref["lin%d_stress" % case]))
+    hd.lin_step(0, 20.0)                      # old_stress <- the consistent loading (:405-409)
+    F = hd.get_vector(capi.LIN_OLD_STRESS)[cd]
+    assert np.abs(F - F_ref).max() <= 1e-12 * np.abs(F_ref).max()
+    hd.close()
