@@ -2,6 +2,7 @@
 // step). Replaces ElastoDynamics::assemble_system (linear_elasticity.cc:248-374: K_e :289-323,
 // MatrixCreator::create_mass_matrix :340-345, body force :358-373) and
 // assemble_consistent_loading (:458-521). Scatter: scatter.cu.
+#include "assemble_general.cuh"
 #include "gf_context.h"
 #include "kernel_utils.cuh"
 
@@ -182,7 +183,34 @@ namespace gf
             lin_cells_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         configured[c.dim - 2] = smem;
       }
-    if (c.dim == 3)
+    if (!c.affine)
+      {
+        // general cells: per-q-point Jacobians (assemble_general.cuh); same shared-memory layout
+        static size_t configured_g[2] = {48 * 1024, 48 * 1024};
+        if (smem > configured_g[c.dim - 2])
+          {
+            GF_REQUIRE(smem <= 227 * 1024, GF_ERR_UNSUPPORTED,
+                       "polynomial degree too high for the linear cell kernel's shared memory");
+            if (c.dim == 3)
+              GF_CUDA_CHECK(cudaFuncSetAttribute(lin_cells_general_kernel<3>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 int(smem)));
+            else
+              GF_CUDA_CHECK(cudaFuncSetAttribute(lin_cells_general_kernel<2>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 int(smem)));
+            configured_g[c.dim - 2] = smem;
+          }
+        if (c.dim == 3)
+          lin_cells_general_kernel<3><<<grid, 256, smem, c.stream>>>(
+            c0, c1, c.npc, c.tables.nq, c.cell_verts.p, c.tables.dphi.p, c.tables.N.p, c.tables.dN.p,
+            c.tables.w.p, lambda, c.desc.mu, c.desc.rho, c.ke_buf.p, c.me_buf.p, c.err_flag.p);
+        else
+          lin_cells_general_kernel<2><<<grid, 256, smem, c.stream>>>(
+            c0, c1, c.npc, c.tables.nq, c.cell_verts.p, c.tables.dphi.p, c.tables.N.p, c.tables.dN.p,
+            c.tables.w.p, lambda, c.desc.mu, c.desc.rho, c.ke_buf.p, c.me_buf.p, c.err_flag.p);
+      }
+    else if (c.dim == 3)
       lin_cells_kernel<3><<<grid, 256, smem, c.stream>>>(
         c0, c1, c.npc, c.tables.nq, c.geom.p, c.tables.dN.p, c.tables.w.p, c.tables.Mref.p, lambda,
         c.desc.mu, c.desc.rho, c.ke_buf.p, c.me_buf.p);
@@ -197,7 +225,21 @@ namespace gf
   {
     const int64_t  n    = c.n_cells * c.npc;
     const unsigned grid = unsigned((n + 255) / 256);
-    if (c.dim == 3)
+    if (!c.affine)
+      {
+        const unsigned g = std::min(grid, 65535u);
+        if (c.dim == 3)
+          body_force_general_kernel<3><<<g, 256, 0, c.stream>>>(
+            c.n_cells, c.npc, c.tables.nq, c.cell_verts.p, c.tables.dphi.p, c.tables.N.p,
+            c.tables.w.p, c.desc.rho, c.desc.body_force[0], c.desc.body_force[1],
+            c.desc.body_force[2], c.re_buf.p);
+        else
+          body_force_general_kernel<2><<<g, 256, 0, c.stream>>>(
+            c.n_cells, c.npc, c.tables.nq, c.cell_verts.p, c.tables.dphi.p, c.tables.N.p,
+            c.tables.w.p, c.desc.rho, c.desc.body_force[0], c.desc.body_force[1],
+            c.desc.body_force[2], c.re_buf.p);
+      }
+    else if (c.dim == 3)
       body_force_kernel<3><<<grid, 256, 0, c.stream>>>(c.n_cells, c.npc, c.geom.p, c.tables.Mref.p,
                                                        c.desc.rho, c.desc.body_force[0],
                                                        c.desc.body_force[1], c.desc.body_force[2],
@@ -220,7 +262,22 @@ namespace gf
         {
           const int    nt   = ((c.dpc + 31) / 32) * 32;
           const size_t smem = (size_t(c.dpc) + size_t(c.tables.nqf) * c.dim) * sizeof(double);
-          if (c.dim == 3)
+          if (!c.affine)
+            {
+              const size_t smem_g =
+                (2 * size_t(c.dpc) + size_t(c.tables.nqf) * (c.dim + 1)) * sizeof(double);
+              if (c.dim == 3)
+                lin_faces_general_kernel<3><<<unsigned(c.n_iface_cells), 128, smem_g, c.stream>>>(
+                  int(c.n_iface_cells), c.npc, c.tables.nqf, c.iface_cell_list.p,
+                  c.iface_face_ptr.p, c.iface_face_no.p, c.cell_nodes.p, c.cell_verts.p,
+                  c.tables.dphif.p, stress, c.tables.Nf.p, c.tables.wf.p, c.re_buf.p);
+              else
+                lin_faces_general_kernel<2><<<unsigned(c.n_iface_cells), 128, smem_g, c.stream>>>(
+                  int(c.n_iface_cells), c.npc, c.tables.nqf, c.iface_cell_list.p,
+                  c.iface_face_ptr.p, c.iface_face_no.p, c.cell_nodes.p, c.cell_verts.p,
+                  c.tables.dphif.p, stress, c.tables.Nf.p, c.tables.wf.p, c.re_buf.p);
+            }
+          else if (c.dim == 3)
             lin_faces_kernel<3><<<unsigned(c.n_iface_cells), nt, smem, c.stream>>>(
               int(c.n_iface_cells), c.npc, c.tables.nqf, c.iface_cell_list.p, c.iface_face_ptr.p,
               c.iface_face_no.p, c.cell_nodes.p, c.geom.p, stress, c.tables.Nf.p, c.tables.wf.p,

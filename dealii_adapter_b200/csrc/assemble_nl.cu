@@ -741,9 +741,9 @@ namespace gf
         c.re_buf.p, c.err_flag.p);
       GF_CUDA_CHECK(cudaGetLastError());
     }
-    // generic-degree kernels (assemble_nl_generic.cuh): every (dim, degree) without a tuned
-    // instantiation, i.e. degree >= 3
-    template <int DIM>
+    // generic kernels (assemble_nl_generic.cuh): every (dim, degree) without a tuned
+    // instantiation, i.e. degree >= 3, and every mesh with non-affine cells (AFFINE = false)
+    template <int DIM, bool AFFINE>
     void launch_cells_generic(gf_context &c, const double *u_total, const double *accel, int64_t c0,
                               int64_t c1)
     {
@@ -753,7 +753,7 @@ namespace gf
         {
           GF_REQUIRE(smem <= 227 * 1024, GF_ERR_UNSUPPORTED,
                      "polynomial degree too high for the generic cell kernel's shared memory");
-          GF_CUDA_CHECK(cudaFuncSetAttribute(nl_cells_generic_kernel<DIM>,
+          GF_CUDA_CHECK(cudaFuncSetAttribute(nl_cells_generic_kernel<DIM, AFFINE>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
           configured = smem;
         }
@@ -763,13 +763,14 @@ namespace gf
       const int     nt   = 256;
       const int     grid = int(std::min<int64_t>(n, int64_t(c.sm_count) * 2));
       const NLParams prm = make_nl_params(c.desc);
-      nl_cells_generic_kernel<DIM><<<grid, nt, smem, c.stream>>>(
-        c0, c1, c.npc, c.tables.nq, c.cell_nodes.p, c.geom.p, u_total, accel, c.tables.N.p,
-        c.tables.dN.p, c.tables.w.p, c.tables.Mref.p, prm, c.ke_buf.p, c.re_buf.p, c.err_flag.p);
+      nl_cells_generic_kernel<DIM, AFFINE><<<grid, nt, smem, c.stream>>>(
+        c0, c1, c.npc, c.tables.nq, c.cell_nodes.p, c.geom.p, c.cell_verts.p, c.tables.dphi.p,
+        u_total, accel, c.tables.N.p, c.tables.dN.p, c.tables.w.p, c.tables.Mref.p, prm,
+        c.ke_buf.p, c.re_buf.p, c.err_flag.p);
       GF_CUDA_CHECK(cudaGetLastError());
     }
 
-    template <int DIM>
+    template <int DIM, bool AFFINE>
     void launch_faces_generic(gf_context &c, const double *u_total, const double *stress)
     {
       if (c.n_iface_cells == 0)
@@ -778,10 +779,11 @@ namespace gf
         size_t(nl_faces_generic_smem_doubles<DIM>(c.npc, c.tables.nqf)) * sizeof(double);
       GF_REQUIRE(smem <= 48 * 1024, GF_ERR_UNSUPPORTED,
                  "polynomial degree too high for the generic face kernel's shared memory");
-      nl_faces_generic_kernel<DIM><<<unsigned(c.n_iface_cells), 128, smem, c.stream>>>(
+      nl_faces_generic_kernel<DIM, AFFINE><<<unsigned(c.n_iface_cells), 128, smem, c.stream>>>(
         int(c.n_iface_cells), c.npc, c.tables.nqf, c.iface_cell_list.p, c.iface_face_ptr.p,
-        c.iface_face_no.p, c.cell_nodes.p, c.geom.p, u_total, stress, c.tables.dN.p, c.tables.Nf.p,
-        c.tables.wf.p, c.re_buf.p, c.err_flag.p);
+        c.iface_face_no.p, c.cell_nodes.p, c.geom.p, c.cell_verts.p, c.tables.dphi.p,
+        c.tables.dphif.p, u_total, stress, c.tables.dN.p, c.tables.Nf.p, c.tables.wf.p, c.re_buf.p,
+        c.err_flag.p);
       GF_CUDA_CHECK(cudaGetLastError());
     }
   } // namespace
@@ -790,7 +792,14 @@ namespace gf
                        int64_t c1)
   {
     ProfScope ps(c, Profile::ASM_CELLS);
-    if (c.dim == 3 && c.p == 2)
+    if (!c.affine)
+      {
+        if (c.dim == 3)
+          launch_cells_generic<3, false>(c, u_total, accel, c0, c1);
+        else
+          launch_cells_generic<2, false>(c, u_total, accel, c0, c1);
+      }
+    else if (c.dim == 3 && c.p == 2)
       launch_cells_t<3, 2>(c, u_total, accel, c0, c1);
     else if (c.dim == 3 && c.p == 1)
       launch_cells_t<3, 1>(c, u_total, accel, c0, c1);
@@ -799,15 +808,22 @@ namespace gf
     else if (c.dim == 2 && c.p == 1)
       launch_cells_t<2, 1>(c, u_total, accel, c0, c1);
     else if (c.dim == 3)
-      launch_cells_generic<3>(c, u_total, accel, c0, c1);
+      launch_cells_generic<3, true>(c, u_total, accel, c0, c1);
     else
-      launch_cells_generic<2>(c, u_total, accel, c0, c1);
+      launch_cells_generic<2, true>(c, u_total, accel, c0, c1);
   }
 
   void launch_nl_faces(gf_context &c, const double *u_total, const double *stress)
   {
     ProfScope ps(c, Profile::ASM_FACES);
-    if (c.dim == 3 && c.p == 2)
+    if (!c.affine)
+      {
+        if (c.dim == 3)
+          launch_faces_generic<3, false>(c, u_total, stress);
+        else
+          launch_faces_generic<2, false>(c, u_total, stress);
+      }
+    else if (c.dim == 3 && c.p == 2)
       launch_faces_t<3, 2>(c, u_total, stress);
     else if (c.dim == 3 && c.p == 1)
       launch_faces_t<3, 1>(c, u_total, stress);
@@ -816,8 +832,8 @@ namespace gf
     else if (c.dim == 2 && c.p == 1)
       launch_faces_t<2, 1>(c, u_total, stress);
     else if (c.dim == 3)
-      launch_faces_generic<3>(c, u_total, stress);
+      launch_faces_generic<3, true>(c, u_total, stress);
     else
-      launch_faces_generic<2>(c, u_total, stress);
+      launch_faces_generic<2, true>(c, u_total, stress);
   }
 } // namespace gf

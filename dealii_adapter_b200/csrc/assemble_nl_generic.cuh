@@ -22,7 +22,12 @@
 //              (:1018-1019); the running K_e lives in the element buffer in HBM/L2 (a 3D Q3 cell
 //              has 2080 node pairs x 9 entries - more than a CTA's registers)
 //   tables N, dN are read from global memory (3D Q3: 256 KB, L2-resident).
-// Not a hot path of the bench configurations (degrees 1, 2); correctness first.
+// AFFINE = false: general (non-affine) hexahedra / quadrilaterals, i.e. what a real deal.II host
+// hands over once the mesh is not a box (MappingQ1 geometry, as MappingQGeneric gives for
+// straight-sided cells, linear_elasticity.cc:60): J, J^-1, det J are evaluated per quadrature
+// point from the cell's vertices and the unit-cell gradients of the 2^dim vertex shape functions;
+// the mass term is integrated per q-point instead of taken from the reference mass matrix.
+// Not a hot path of the bench configurations (degrees 1, 2, box meshes); correctness first.
 #pragma once
 #include "emu_compat.cuh"
 #include "kernel_utils.cuh"
@@ -30,6 +35,26 @@
 
 namespace gf
 {
+  // MappingQ1: J(i, j) = dX_i / dxi_j = sum_v X_v(i) dphi_v/dxi_j; returns det J, fills J^-1
+  template <int DIM>
+  __device__ inline double q1_geometry(const double *__restrict__ verts /* [2^DIM][DIM] */,
+                                       const double *__restrict__ dphi /* [2^DIM][DIM] */,
+                                       double (&Jinv)[DIM][DIM])
+  {
+    double J[DIM][DIM];
+    for (int i = 0; i < DIM; ++i)
+      for (int j = 0; j < DIM; ++j)
+        {
+          double v = 0;
+          for (int k = 0; k < (1 << DIM); ++k)
+            v += verts[k * DIM + i] * dphi[k * DIM + j];
+          J[i][j] = v;
+        }
+    const double d = det<DIM>(J);
+    inverse<DIM>(J, d, Jinv);
+    return d;
+  }
+
   template <int DIM>
   struct NLGen
   {
@@ -50,10 +75,12 @@ namespace gf
     }
   };
 
-  template <int DIM>
+  template <int DIM, bool AFFINE>
   __global__ void nl_cells_generic_kernel(const int64_t c0, const int64_t c1, const int npc,
                                           const int nq, const int32_t *__restrict__ cell_nodes,
                                           const double *__restrict__ geom,
+                                          const double *__restrict__ cell_verts,
+                                          const double *__restrict__ tab_dphi,
                                           const double *__restrict__ u_total,
                                           const double *__restrict__ accel,
                                           const double *__restrict__ tabN,
@@ -73,12 +100,9 @@ namespace gf
     for (int64_t cell = c0 + blockIdx.x; cell < c1; cell += gridDim.x)
       {
         __syncthreads(); // the previous cell's shared data are no longer read
-        const double *gm = geom + cell * (DIM * DIM + 1);
-        double        Jinv[DIM][DIM];
-        for (int i = 0; i < DIM; ++i)
-          for (int j = 0; j < DIM; ++j)
-            Jinv[i][j] = gm[i * DIM + j];
-        const double detJ = gm[DIM * DIM];
+        // affine cell: one J^-1 / det J record; general cell: the vertices (J per q-point)
+        const double *gm = AFFINE ? geom + cell * (DIM * DIM + 1) : nullptr;
+        const double *vx = AFFINE ? nullptr : cell_verts + cell * ((1 << DIM) * DIM);
         for (int i = tid; i < dpc; i += nt)
           {
             const int32_t node = cell_nodes[cell * npc + i / DIM];
@@ -88,7 +112,7 @@ namespace gf
           }
         __syncthreads();
         double *     ke   = ke_buf + (cell - c0) * int64_t(dpc) * dpc;
-        const double mfac = prm.rho * prm.alpha_1 * detJ;
+        const double mfac = prm.rho * prm.alpha_1 * (AFFINE ? gm[DIM * DIM] : 1.0);
         for (int qc = 0; qc < nq; qc += QC)
           {
             const int nqc = nq - qc < QC ? nq - qc : QC;
@@ -96,7 +120,21 @@ namespace gf
             for (int ql = tid; ql < nqc; ql += nt)
               {
                 const int q = qc + ql;
-                double    Hr[DIM][DIM], acc[DIM], sumN = 0;
+                double    Jinv[DIM][DIM], detJ;
+                if (AFFINE)
+                  {
+                    for (int i = 0; i < DIM; ++i)
+                      for (int j = 0; j < DIM; ++j)
+                        Jinv[i][j] = gm[i * DIM + j];
+                    detJ = gm[DIM * DIM];
+                  }
+                else
+                  {
+                    detJ = q1_geometry<DIM>(vx, tab_dphi + q * ((1 << DIM) * DIM), Jinv);
+                    if (!(detJ > 0.0))
+                      atomicExch(err_flag, 1); // inverted cell
+                  }
+                double Hr[DIM][DIM], acc[DIM], sumN = 0;
                 for (int i = 0; i < DIM; ++i)
                   {
                     acc[i] = 0;
@@ -219,12 +257,15 @@ namespace gf
                 while (a * (a + 1) / 2 > pair)
                   --a;
                 const int b = pair - a * (a + 1) / 2;
-                double    K[DIM][DIM], S = 0;
+                double    K[DIM][DIM], S = 0, mm = 0;
                 for (int i = 0; i < DIM; ++i)
                   for (int j = 0; j < DIM; ++j)
                     K[i][j] = 0;
                 for (int ql = 0; ql < nqc; ++ql)
                   {
+                    if (!AFFINE) // mass term integrated per q-point: N_a N_b JxW
+                      mm = fma(tabN[(qc + ql) * npc + a] * tabN[(qc + ql) * npc + b],
+                               sQ[ql * QS + C::Q_W], mm);
                     const double *T = sT + (ql * npc + a) * TS;
                     double        gb[DIM];
                     for (int l = 0; l < DIM; ++l)
@@ -240,14 +281,15 @@ namespace gf
                     for (int l = 0; l < DIM; ++l)
                       S = fma(T[DIM * VO + l], gb[l], S);
                   }
-                // first chunk: start from the mass term rho alpha_1 detJ M_ab (:1020-1021)
-                const double dd0 = qc == 0 ? mfac * Mref[a * npc + b] : 0.0;
+                // diagonal of the node block: geometric term + mass term rho alpha_1 M_ab
+                // (:1018-1021); affine cells take M_ab = detJ * reference mass matrix, once
+                const double dd = S + (AFFINE ? (qc == 0 ? mfac * Mref[a * npc + b] : 0.0) : mfac * mm);
                 for (int ci = 0; ci < DIM; ++ci)
                   for (int cj = 0; cj < DIM; ++cj)
                     {
                       double *     e    = ke + int64_t(a * DIM + ci) * dpc + b * DIM + cj;
-                      const double base = qc == 0 ? (ci == cj ? dd0 : 0.0) : *e;
-                      *e                = base + (K[ci][cj] + (ci == cj ? S : 0.0));
+                      const double base = qc == 0 ? 0.0 : *e;
+                      *e                = base + (K[ci][cj] + (ci == cj ? dd : 0.0));
                     }
               }
             __syncthreads(); // the next chunk overwrites sQ / sT / sG
@@ -266,13 +308,16 @@ namespace gf
     return 3L * npc * DIM + long(nqf) * (1 + DIM);
   }
 
-  template <int DIM>
+  template <int DIM, bool AFFINE>
   __global__ void nl_faces_generic_kernel(const int n_iface_cells, const int npc, const int nqf,
                                           const int32_t *__restrict__ cell_list,
                                           const int32_t *__restrict__ face_ptr,
                                           const int32_t *__restrict__ face_no,
                                           const int32_t *__restrict__ cell_nodes,
                                           const double *__restrict__ geom,
+                                          const double *__restrict__ cell_verts,
+                                          const double *__restrict__ tab_dphi,
+                                          const double *__restrict__ tab_dphif,
                                           const double *__restrict__ u_total,
                                           const double *__restrict__ stress,
                                           const double *__restrict__ tabdN,
@@ -287,12 +332,8 @@ namespace gf
     if (ic >= n_iface_cells)
       return;
     const int64_t cell = cell_list[ic];
-    const double *gm   = geom + cell * (DIM * DIM + 1);
-    double        Jinv[DIM][DIM];
-    for (int i = 0; i < DIM; ++i)
-      for (int j = 0; j < DIM; ++j)
-        Jinv[i][j] = gm[i * DIM + j];
-    const double detJ = gm[DIM * DIM];
+    const double *gm   = AFFINE ? geom + cell * (DIM * DIM + 1) : nullptr;
+    const double *vx   = AFFINE ? nullptr : cell_verts + cell * ((1 << DIM) * DIM);
     for (int i = tid; i < dpc; i += nt)
       {
         const int32_t node = cell_nodes[cell * npc + i / DIM];
@@ -305,18 +346,35 @@ namespace gf
       {
         const int face = face_no[fi];
         const int fd   = face / 2;
-        // n da = det(J) J^-T n_ref dA_ref  (affine cell: constant per face)
-        double nrm[DIM], len = 0;
-        for (int i = 0; i < DIM; ++i)
-          {
-            nrm[i] = detJ * Jinv[fd][i] * ((face & 1) ? 1.0 : -1.0);
-            len += nrm[i] * nrm[i];
-          }
-        len = sqrt(len);
-        for (int i = 0; i < DIM; ++i)
-          nrm[i] /= len;
         for (int q = tid; q < nqf; q += nt)
           {
+            // geometry at the FACE quadrature point: n da = det(J) J^-T n_ref dA_ref (constant
+            // per face on an affine cell); at the CELL quadrature point of the same index for
+            // the deformation gradient (:825-827)
+            double Jf[DIM][DIM], Jinv[DIM][DIM], detJf;
+            if (AFFINE)
+              {
+                for (int i = 0; i < DIM; ++i)
+                  for (int j = 0; j < DIM; ++j)
+                    Jf[i][j] = Jinv[i][j] = gm[i * DIM + j];
+                detJf = gm[DIM * DIM];
+              }
+            else
+              {
+                detJf = q1_geometry<DIM>(vx, tab_dphif + (face * nqf + q) * ((1 << DIM) * DIM), Jf);
+                const double dc = q1_geometry<DIM>(vx, tab_dphi + q * ((1 << DIM) * DIM), Jinv);
+                if (!(detJf > 0.0) || !(dc > 0.0))
+                  atomicExch(err_flag, 1);
+              }
+            double nrm[DIM], len = 0;
+            for (int i = 0; i < DIM; ++i)
+              {
+                nrm[i] = detJf * Jf[fd][i] * ((face & 1) ? 1.0 : -1.0);
+                len += nrm[i] * nrm[i];
+              }
+            len = sqrt(len);
+            for (int i = 0; i < DIM; ++i)
+              nrm[i] /= len;
             // :825-827 - CELL quadrature gradient at index f_q_point
             double Hr[DIM][DIM];
             for (int i = 0; i < DIM; ++i)

@@ -14,5 +14,8 @@ namespace gf
     t.Nf.upload(t.hNf.data(), t.hNf.size(), c.stream);
     t.wf.upload(t.hwf.data(), t.hwf.size(), c.stream);
     t.Mref.upload(t.hMref.data(), t.hMref.size(), c.stream);
+    t.dphi.upload(t.hdphi.data(), t.hdphi.size(), c.stream);
+    t.dphif.upload(t.hdphif.data(), t.hdphif.size(), c.stream);
+    t.dphip.upload(t.hdphip.data(), t.hdphip.size(), c.stream);
   }
 } // namespace gf

@@ -20,6 +20,11 @@ namespace gf
     int dim = 0, p = 0, npc = 0, dpc = 0, nq1 = 0, nq = 0, nqf = 0, nv = 0;
     std::vector<double> hN, hdN, hw, hNf, hwf; // [nq][npc], [nq][npc][dim], [nq], [2 dim][nqf][npc], [nqf]
     std::vector<double> hMref;                 // [npc][npc] sum_q w N_a N_b
+    // MappingQ1 geometry of general (non-affine) cells: unit-cell gradients of the 2^dim vertex
+    // shape functions at the cell / face quadrature points and at the output patch points
+    std::vector<double> hdphi;  // [nq][nv][dim]
+    std::vector<double> hdphif; // [2 dim][nqf][nv][dim]
+    std::vector<double> hdphip; // [npc patch points (lexicographic, xi = i / p)][nv][dim]
     std::vector<int>    local_lex;             // [npc][3]
     // FESystem local DoF of (hierarchical node a, component c): loc_of[a * dim + c]; = a * dim + c
     // for p <= 2, entity-major / component / entity DoF for p >= 3 (fe_basis.h)
@@ -132,6 +137,35 @@ namespace gf
           }
         t.lex2hier[l] = a;
       }
+    // gradient of the vertex shape function v (MappingQ1) at xi
+    const int nv          = t.nv;
+    auto      vertex_grad = [&](int v, const double *xi, double *g) {
+      for (int k = 0; k < dim; ++k)
+        {
+          double val = 1;
+          for (int l = 0; l < dim; ++l)
+            {
+              const bool hi = (v >> l) & 1;
+              val *= (l == k) ? (hi ? 1.0 : -1.0) : (hi ? xi[l] : 1.0 - xi[l]);
+            }
+          g[k] = val;
+        }
+    };
+    t.hdphi.assign(size_t(nq) * nv * dim, 0.);
+    t.hdphif.assign(size_t(2) * dim * nqf * nv * dim, 0.);
+    t.hdphip.assign(size_t(npc) * nv * dim, 0.);
+    for (int pt = 0; pt < npc; ++pt)
+      {
+        double xi[3] = {0, 0, 0};
+        int    rem   = pt;
+        for (int d = 0; d < dim; ++d)
+          {
+            xi[d] = double(rem % (p + 1)) / p;
+            rem /= (p + 1);
+          }
+        for (int v = 0; v < nv; ++v)
+          vertex_grad(v, xi, &t.hdphip[(size_t(pt) * nv + v) * dim]);
+      }
     t.hN.assign(nq * npc, 0.);
     t.hdN.assign(nq * npc * dim, 0.);
     t.hw.assign(nq, 0.);
@@ -146,6 +180,8 @@ namespace gf
             rem /= nq1;
           }
         t.hw[q] = w;
+        for (int v = 0; v < nv; ++v)
+          vertex_grad(v, xi, &t.hdphi[(size_t(q) * nv + v) * dim]);
         for (int a = 0; a < npc; ++a)
           {
             t.hN[q * npc + a] = shape(a, xi);
@@ -203,6 +239,8 @@ namespace gf
               }
             for (int a = 0; a < npc; ++a)
               t.hNf[(f * nqf + q) * npc + a] = shape(a, xi);
+            for (int v = 0; v < nv; ++v)
+              vertex_grad(v, xi, &t.hdphif[((size_t(f) * nqf + q) * nv + v) * dim]);
           }
       }
     t.hMref.assign(npc * npc, 0.);

@@ -108,6 +108,9 @@ namespace gf
     DevBuf<double> Nf;   // [2*dim][nqf][npc]
     DevBuf<double> wf;   // [nqf]
     DevBuf<double> Mref; // [npc][npc] sum_q w N_a N_b
+    // MappingQ1 vertex shape function gradients (general cells): cell q-points, face q-points,
+    // output patch points
+    DevBuf<double> dphi, dphif, dphip;
   };
 
   // band Cholesky for 'Solver type = Direct' (direct.cu, direct_band.cuh)
@@ -271,6 +274,11 @@ struct gf_context
   gf::DevBuf<uint8_t> constrained; // [n_local] internal numbering
   gf::DevBuf<int32_t> cell_nodes;  // [n_cells*npc]
   gf::DevBuf<double>  geom;        // [n_cells*(dim*dim+1)] : J^{-1} row-major, det J
+  // general (non-affine) cells: the kernels of assemble_nl_generic.cuh / assemble_general.cuh
+  // evaluate the MappingQ1 Jacobian per quadrature point from the vertices; geom then holds the
+  // Jacobian at vertex 0 (diagnostics only)
+  bool                affine = true;
+  gf::DevBuf<double>  cell_verts;  // [n_cells][2^dim][dim], only when !affine
   // node -> (cell, local node) adjacency, ascending cell
   gf::DevBuf<int64_t> nc_ptr; // [n_nodes+1]
   gf::DevBuf<int32_t> nc_src; // [n_cells*npc] = cell*npc + a

@@ -305,6 +305,7 @@ namespace gf
     {
       const int           nv = 1 << dim, gs = dim * dim + 1;
       std::vector<double> geom(n_cells * gs);
+      bool                all_affine = true;
       for (int64_t cell = 0; cell < n_cells; ++cell)
         {
           const double *v = d.cell_vertices + cell * nv * dim;
@@ -324,8 +325,8 @@ namespace gf
                 for (int j = 0; j < dim; ++j)
                   if ((vtx >> j) & 1)
                     x += J[i][j];
-                GF_REQUIRE(std::fabs(x - v[vtx * dim + i]) <= 1e-10 * scale, GF_ERR_UNSUPPORTED,
-                           "non-affine cell: only parallelepiped cells are supported");
+                if (std::fabs(x - v[vtx * dim + i]) > 1e-10 * scale)
+                  all_affine = false; // general cell: Jacobian per quadrature point
               }
           const double det =
             dim == 2 ? J[0][0] * J[1][1] - J[0][1] * J[1][0] :
@@ -359,6 +360,13 @@ namespace gf
           geom[cell * gs + dim * dim] = det;
         }
       c.geom.upload(geom.data(), geom.size(), s);
+      c.affine = all_affine;
+      if (!all_affine)
+        {
+          GF_REQUIRE(c.slab_axis == 0, GF_ERR_UNSUPPORTED,
+                     "slab_axis (partition-independent node planes) needs parallelepiped cells");
+          c.cell_verts.upload(d.cell_vertices, size_t(n_cells) * nv * dim, s);
+        }
     }
 
     // ---- device: node -> (cell, local node) adjacency, ascending cell ---------------------------

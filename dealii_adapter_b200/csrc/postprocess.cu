@@ -9,6 +9,7 @@
 // One thread per (cell, patch point); patch points in lexicographic order (x fastest) as in
 // DataOutBase::Patch. HBM-bound and only run at output intervals: reads 8*dpc B/cell of nodal
 // values (L2-resident neighbours), writes 8*(dim+dim^2)*npc B/cell.
+#include "assemble_general.cuh"
 #include "gf_context.h"
 #include "kernel_utils.cuh"
 
@@ -148,7 +149,19 @@ namespace gf
     ProfScope      ps(c, Profile::UPDATE);
     const int64_t  n    = (c1 - c0) * npc;
     const unsigned grid = unsigned((n + 255) / 256);
-    if (dim == 3)
+    if (!c.affine)
+      {
+        const unsigned g = std::min(grid, 65535u);
+        if (dim == 3)
+          postprocess_general_kernel<3><<<g, 256, 0, c.stream>>>(
+            c0, c1 - c0, npc, c.cell_nodes.p, c.cell_verts.p, c.tables.dphip.p, c.pp_N.p,
+            c.pp_dN.p, u, fields_dev, c.err_flag.p);
+        else
+          postprocess_general_kernel<2><<<g, 256, 0, c.stream>>>(
+            c0, c1 - c0, npc, c.cell_nodes.p, c.cell_verts.p, c.tables.dphip.p, c.pp_N.p,
+            c.pp_dN.p, u, fields_dev, c.err_flag.p);
+      }
+    else if (dim == 3)
       postprocess_kernel<3><<<grid, 256, 0, c.stream>>>(c0, c1 - c0, npc, c.cell_nodes.p, c.geom.p,
                                                         c.pp_N.p, c.pp_dN.p, u, fields_dev,
                                                         c.err_flag.p);

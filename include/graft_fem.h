@@ -60,8 +60,13 @@ extern "C"
     int64_t n_dofs; /* dofs visible to this rank: owned first, then ghosts */
     int64_t n_cells;
     const int32_t *cell_dofs;     /* [n_cells*dpc] cell->get_dof_indices() */
-    const double * cell_vertices; /* [n_cells*2^dim*dim] cell->vertex(v), deal.II vertex order;
-                                     cells must be affine (parallelepipeds) */
+    const double * cell_vertices; /* [n_cells*2^dim*dim] cell->vertex(v), deal.II vertex order.
+                                     Parallelepiped cells (every mesh of the reference) run the
+                                     tuned kernels; general straight-sided cells (MappingQ1
+                                     geometry) are accepted too and run the general kernels with
+                                     Jacobians per quadrature point - block-Jacobi CG / direct
+                                     solver only (no gf_mg_attach, matrix-free operator or
+                                     slab_axis) */
     const uint8_t *constrained;   /* [n_dofs] 1 = homogeneous Dirichlet dof (make_constraints /
                                      interpolate_boundary_values with ZeroFunction) */
     int64_t        n_iface_faces; /* faces with boundary_id == interface id (7 nonlinear, 6 linear) */

@@ -3,6 +3,7 @@
 // product's own host tables (csrc/fe_tables_host.h). Test infrastructure only.
 #include <cstring>
 
+#include "assemble_general.cuh"
 #include "assemble_nl_generic.cuh"
 #include "direct_band.cuh"
 #include "fe_tables_host.h"
@@ -10,19 +11,26 @@
 
 namespace
 {
+  // verts == nullptr: affine cells described by geom (J^-1, det J); else general cells
   template <int DIM>
   int run_cells(int p, int64_t n_cells, const int32_t *cell_nodes, const double *geom,
-                const double *u_total, const double *accel, const gf::NLParams &prm,
-                unsigned grid, unsigned block, double *ke, double *re)
+                const double *verts, const double *u_total, const double *accel,
+                const gf::NLParams &prm, unsigned grid, unsigned block, double *ke, double *re)
   {
     gf::FETablesHost t;
     gf::build_host_tables(t, DIM, p, true);
     int          err  = 0;
     const size_t smem = size_t(gf::NLGen<DIM>::smem_doubles(t.npc)) * sizeof(double);
     gf_emu::launch(grid, block, smem, [&] {
-      gf::nl_cells_generic_kernel<DIM>(0, n_cells, t.npc, t.nq, cell_nodes, geom, u_total, accel,
-                                       t.hN.data(), t.hdN.data(), t.hw.data(), t.hMref.data(), prm,
-                                       ke, re, &err);
+      if (verts == nullptr)
+        gf::nl_cells_generic_kernel<DIM, true>(0, n_cells, t.npc, t.nq, cell_nodes, geom, nullptr,
+                                               nullptr, u_total, accel, t.hN.data(), t.hdN.data(),
+                                               t.hw.data(), t.hMref.data(), prm, ke, re, &err);
+      else
+        gf::nl_cells_generic_kernel<DIM, false>(0, n_cells, t.npc, t.nq, cell_nodes, nullptr, verts,
+                                                t.hdphi.data(), u_total, accel, t.hN.data(),
+                                                t.hdN.data(), t.hw.data(), nullptr, prm, ke, re,
+                                                &err);
     });
     return err;
   }
@@ -30,16 +38,97 @@ namespace
   template <int DIM>
   int run_faces(int p, int n_iface_cells, const int32_t *cell_list, const int32_t *face_ptr,
                 const int32_t *face_no, const int32_t *cell_nodes, const double *geom,
-                const double *u_total, const double *stress, unsigned block, double *re)
+                const double *verts, const double *u_total, const double *stress, unsigned block,
+                double *re)
   {
     gf::FETablesHost t;
     gf::build_host_tables(t, DIM, p, true);
     int          err  = 0;
     const size_t smem = size_t(gf::nl_faces_generic_smem_doubles<DIM>(t.npc, t.nqf)) * sizeof(double);
     gf_emu::launch(unsigned(n_iface_cells), block, smem, [&] {
-      gf::nl_faces_generic_kernel<DIM>(n_iface_cells, t.npc, t.nqf, cell_list, face_ptr, face_no,
-                                       cell_nodes, geom, u_total, stress, t.hdN.data(),
-                                       t.hNf.data(), t.hwf.data(), re, &err);
+      if (verts == nullptr)
+        gf::nl_faces_generic_kernel<DIM, true>(n_iface_cells, t.npc, t.nqf, cell_list, face_ptr,
+                                               face_no, cell_nodes, geom, nullptr, nullptr, nullptr,
+                                               u_total, stress, t.hdN.data(), t.hNf.data(),
+                                               t.hwf.data(), re, &err);
+      else
+        gf::nl_faces_generic_kernel<DIM, false>(n_iface_cells, t.npc, t.nqf, cell_list, face_ptr,
+                                                face_no, cell_nodes, nullptr, verts, t.hdphi.data(),
+                                                t.hdphif.data(), u_total, stress, t.hdN.data(),
+                                                t.hNf.data(), t.hwf.data(), re, &err);
+    });
+    return err;
+  }
+
+  // linear model on general cells: K_e [n_cells][dpc][dpc], scalar mass blocks [n_cells][npc][npc],
+  // body-force load and interface load [n_cells][dpc] (internal local order)
+  template <int DIM>
+  int run_linear(int p, int64_t n_cells, const double *verts, double lambda, double mu, double rho,
+                 const double *bf, int n_iface_cells, const int32_t *cell_list,
+                 const int32_t *face_ptr, const int32_t *face_no, const int32_t *cell_nodes,
+                 const double *stress, unsigned block, double *ke, double *me, double *re_body,
+                 double *re_face)
+  {
+    gf::FETablesHost t;
+    gf::build_host_tables(t, DIM, p, false);
+    int          err  = 0;
+    const size_t smem = (size_t(t.nq) * t.npc * DIM + t.nq) * sizeof(double);
+    gf_emu::launch(2u, block, smem, [&] {
+      gf::lin_cells_general_kernel<DIM>(0, n_cells, t.npc, t.nq, verts, t.hdphi.data(), t.hN.data(),
+                                        t.hdN.data(), t.hw.data(), lambda, mu, rho, ke, me, &err);
+    });
+    gf_emu::launch(2u, block, 0, [&] {
+      gf::body_force_general_kernel<DIM>(n_cells, t.npc, t.nq, verts, t.hdphi.data(), t.hN.data(),
+                                         t.hw.data(), rho, bf[0], bf[1], bf[2], re_body);
+    });
+    const size_t smem_f = (2 * size_t(t.dpc) + size_t(t.nqf) * (DIM + 1)) * sizeof(double);
+    gf_emu::launch(unsigned(n_iface_cells), block, smem_f, [&] {
+      gf::lin_faces_general_kernel<DIM>(n_iface_cells, t.npc, t.nqf, cell_list, face_ptr, face_no,
+                                        cell_nodes, verts, t.hdphif.data(), stress, t.hNf.data(),
+                                        t.hwf.data(), re_face);
+    });
+    return err;
+  }
+
+  template <int DIM>
+  int run_postprocess(int p, int64_t n_cells, const int32_t *cell_nodes, const double *verts,
+                      const double *u, unsigned block, double *fields)
+  {
+    gf::FETablesHost t;
+    gf::build_host_tables(t, DIM, p, true);
+    // shape values / unit-cell gradients at the patch points, as launch_postprocess builds them
+    const gf_fe::Basis1D basis(p);
+    const int            npc = t.npc;
+    std::vector<double>  N(size_t(npc) * npc), dN(size_t(npc) * npc * DIM);
+    for (int pt = 0; pt < npc; ++pt)
+      {
+        double xi[3] = {0, 0, 0};
+        int    rem   = pt;
+        for (int d = 0; d < DIM; ++d)
+          {
+            xi[d] = double(rem % (p + 1)) / p;
+            rem /= (p + 1);
+          }
+        for (int a = 0; a < npc; ++a)
+          {
+            double v = 1;
+            for (int d = 0; d < DIM; ++d)
+              v *= basis.value(t.local_lex[a * 3 + d], xi[d]);
+            N[size_t(pt) * npc + a] = v;
+            for (int k = 0; k < DIM; ++k)
+              {
+                double w = 1;
+                for (int d = 0; d < DIM; ++d)
+                  w *= (d == k) ? basis.derivative(t.local_lex[a * 3 + d], xi[d]) :
+                                  basis.value(t.local_lex[a * 3 + d], xi[d]);
+                dN[(size_t(pt) * npc + a) * DIM + k] = w;
+              }
+          }
+      }
+    int err = 0;
+    gf_emu::launch(2u, block, 0, [&] {
+      gf::postprocess_general_kernel<DIM>(0, n_cells, npc, cell_nodes, verts, t.hdphip.data(),
+                                          N.data(), dN.data(), u, fields, &err);
     });
     return err;
   }
@@ -94,8 +183,8 @@ extern "C"
   // params: kappa, mu, rho, alpha_1, body_force[3]. ke: [n_cells][dpc][dpc] (only the node blocks
   // b <= a are written), re: [n_cells][dpc]. Returns the det F error flag.
   int emu_nl_cells(int dim, int p, int64_t n_cells, const int32_t *cell_nodes, const double *geom,
-                   const double *u_total, const double *accel, const double *params, unsigned grid,
-                   unsigned block, double *ke, double *re)
+                   const double *verts, const double *u_total, const double *accel,
+                   const double *params, unsigned grid, unsigned block, double *ke, double *re)
   {
     gf::NLParams prm;
     prm.kappa   = params[0];
@@ -104,18 +193,38 @@ extern "C"
     prm.alpha_1 = params[3];
     for (int k = 0; k < 3; ++k)
       prm.body_force[k] = params[4 + k];
-    return dim == 3 ? run_cells<3>(p, n_cells, cell_nodes, geom, u_total, accel, prm, grid, block, ke, re) :
-                      run_cells<2>(p, n_cells, cell_nodes, geom, u_total, accel, prm, grid, block, ke, re);
+    return dim == 3 ?
+             run_cells<3>(p, n_cells, cell_nodes, geom, verts, u_total, accel, prm, grid, block, ke, re) :
+             run_cells<2>(p, n_cells, cell_nodes, geom, verts, u_total, accel, prm, grid, block, ke, re);
   }
   int emu_nl_faces(int dim, int p, int n_iface_cells, const int32_t *cell_list,
                    const int32_t *face_ptr, const int32_t *face_no, const int32_t *cell_nodes,
-                   const double *geom, const double *u_total, const double *stress, unsigned block,
-                   double *re)
+                   const double *geom, const double *verts, const double *u_total,
+                   const double *stress, unsigned block, double *re)
   {
     return dim == 3 ? run_faces<3>(p, n_iface_cells, cell_list, face_ptr, face_no, cell_nodes, geom,
-                                   u_total, stress, block, re) :
+                                   verts, u_total, stress, block, re) :
                       run_faces<2>(p, n_iface_cells, cell_list, face_ptr, face_no, cell_nodes, geom,
-                                   u_total, stress, block, re);
+                                   verts, u_total, stress, block, re);
+  }
+  int emu_linear_general(int dim, int p, int64_t n_cells, const double *verts, double lambda,
+                         double mu, double rho, const double *bf, int n_iface_cells,
+                         const int32_t *cell_list, const int32_t *face_ptr, const int32_t *face_no,
+                         const int32_t *cell_nodes, const double *stress, unsigned block, double *ke,
+                         double *me, double *re_body, double *re_face)
+  {
+    return dim == 3 ? run_linear<3>(p, n_cells, verts, lambda, mu, rho, bf, n_iface_cells, cell_list,
+                                    face_ptr, face_no, cell_nodes, stress, block, ke, me, re_body,
+                                    re_face) :
+                      run_linear<2>(p, n_cells, verts, lambda, mu, rho, bf, n_iface_cells, cell_list,
+                                    face_ptr, face_no, cell_nodes, stress, block, ke, me, re_body,
+                                    re_face);
+  }
+  int emu_postprocess_general(int dim, int p, int64_t n_cells, const int32_t *cell_nodes,
+                              const double *verts, const double *u, unsigned block, double *fields)
+  {
+    return dim == 3 ? run_postprocess<3>(p, n_cells, cell_nodes, verts, u, block, fields) :
+                      run_postprocess<2>(p, n_cells, cell_nodes, verts, u, block, fields);
   }
   // the product's host tables, for the tests: loc_of [npc * dim]
   int emu_loc_of(int dim, int p, int *loc_of)

@@ -54,3 +54,35 @@ def dof_components(problem):
 
 def rel_err(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def distort_mesh(problem, amp=0.12, seed=0):
+    """Move every vertex by a smooth non-linear map X -> X + delta(X) (a fraction `amp` of the cell
+    size), so that the cells are general (non-affine) quadrilaterals / hexahedra with a positive
+    Jacobian. cell_vertices and support_points (= MappingQ1 image of the unit support points) of
+    the problem's mesh are updated consistently; the topology and boundary roles stay."""
+    import ref_formulas as rf
+    mesh, dim, p = problem.mesh, problem.dim, problem.degree
+    nv = 1 << dim
+    p0, p1 = np.array(mesh.p0), np.array(mesh.p1)
+    hcell = (p1 - p0) / np.array(mesh.reps[:dim])
+    rng = np.random.RandomState(seed)
+    k = rng.uniform(2.0, 5.0, size=(dim, dim))
+    ph = rng.uniform(0.0, 2 * np.pi, size=dim)
+    verts = mesh.cell_vertices.reshape(-1, dim)
+    xi = (verts - p0) / (p1 - p0)
+    delta = np.stack([amp * hcell[i] * np.sin(ph[i] + xi @ k[i]) for i in range(dim)], axis=1)
+    new = (verts + delta).reshape(mesh.n_cells, nv, dim)
+    mesh.cell_vertices = new.reshape(-1).copy()
+    nodes = rf.hierarchical_nodes(dim, p)
+    s2c = rf.system_to_node_component(dim, p)
+    x1 = rf.support_points_1d(p)
+    cd = mesh.cell_dofs.reshape(mesh.n_cells, -1)
+    sp = mesh.support_points.copy()
+    for i, (a, comp) in enumerate(s2c):
+        unit = [x1[nodes[a][d]] for d in range(dim)]
+        w = np.array([np.prod([unit[d] if (v >> d) & 1 else 1.0 - unit[d] for d in range(dim)])
+                      for v in range(nv)])
+        sp[cd[:, i]] = np.einsum("v,cvd->cd", w, new)
+    mesh.support_points = sp
+    return problem

@@ -26,7 +26,8 @@ def emu(native_libs):
     os.makedirs(os.path.dirname(out), exist_ok=True)
     csrc = os.path.join(ROOT, "dealii_adapter_b200", "csrc")
     srcs = [os.path.join(EMU, "emu_kernels.cpp"), os.path.join(EMU, "cuda_runtime.h")] + \
-        [os.path.join(csrc, f) for f in ("assemble_nl_generic.cuh", "emu_compat.cuh",
+        [os.path.join(csrc, f) for f in ("assemble_nl_generic.cuh", "assemble_general.cuh",
+                                         "direct_band.cuh", "rcm.h", "emu_compat.cuh",
                                          "kernel_utils.cuh", "nl_material.cuh", "fe_tables_host.h",
                                          "fe_basis.h")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
@@ -36,10 +37,17 @@ def emu(native_libs):
                        check=True)
     lib = C.CDLL(out)
     lib.emu_nl_cells.restype = C.c_int
-    lib.emu_nl_cells.argtypes = [C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 5 + \
+    lib.emu_nl_cells.argtypes = [C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 6 + \
         [C.c_uint, C.c_uint, C.c_void_p, C.c_void_p]
     lib.emu_nl_faces.restype = C.c_int
-    lib.emu_nl_faces.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_uint, C.c_void_p]
+    lib.emu_nl_faces.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.c_uint, C.c_void_p]
+    lib.emu_linear_general.restype = C.c_int
+    lib.emu_linear_general.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_double,
+                                       C.c_double, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + \
+        [C.c_uint] + [C.c_void_p] * 4
+    lib.emu_postprocess_general.restype = C.c_int
+    lib.emu_postprocess_general.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_uint, C.c_void_p]
     lib.emu_loc_of.restype = C.c_int
     lib.emu_loc_of.argtypes = [C.c_int, C.c_int, C.c_void_p]
     return lib
@@ -73,13 +81,36 @@ CASES = [(2, 3, [3, 2]), (2, 4, [2, 2]), (2, 5, [2, 1]), (3, 3, [2, 1, 2]), (2, 
          (3, 2, [2, 2, 1])]
 
 
+def is_affine(prob):
+    dim = prob.dim
+    v = prob.mesh.cell_vertices.reshape(prob.mesh.n_cells, 1 << dim, dim)
+    last = v[:, 0] + sum(v[:, 1 << d] - v[:, 0] for d in range(dim))
+    h = np.abs(v[:, -1] - v[:, 0]).max()
+    return np.abs(last - v[:, -1]).max() < 1e-6 * h
+
+
+def iface_lists(prob):
+    """cells with interface faces, their faces in ascending face number (as gf_create groups them)"""
+    icells = np.unique(prob.iface_cell)
+    order = np.lexsort((prob.iface_face_no, prob.iface_cell))
+    face_no = prob.iface_face_no[order].astype(np.int32)
+    face_ptr = np.concatenate([np.searchsorted(prob.iface_cell[order], icells),
+                               [len(order)]]).astype(np.int32)
+    return icells.astype(np.int32), face_ptr, face_no
+
+
 @pytest.mark.parametrize("dim,p,reps", CASES)
-@pytest.mark.parametrize("block", [32, 96])
-def test_generic_cell_and_face_kernels_match_oracle(emu, dim, p, reps, block):
+@pytest.mark.parametrize("block,general", [(32, False), (96, False), (64, True)])
+def test_generic_cell_and_face_kernels_match_oracle(emu, dim, p, reps, block, general):
+    """general = True: distorted (non-affine) cells, Jacobians per quadrature point (AFFINE = false)"""
     from oracle import oracle_py as orc
+    from helpers import distort_mesh
     prm = nl_params(poly_degree=p, body_force=(1.5, -9.81, 0.5), scenario="PF")
     prob = make_problem(prm, dim, reps=reps, numbering="cellwise")
     prob.constrained[:] = 0
+    if general:
+        distort_mesh(prob, 0.12, seed=dim * 10 + p)
+        assert not is_affine(prob)
     mesh = prob.mesh
     npc, dpc, nc = (p + 1) ** dim, dim * (p + 1) ** dim, mesh.n_cells
     loc_of, cell_nodes, i2e, geom = device_view(prob, emu)
@@ -96,7 +127,9 @@ def test_generic_cell_and_face_kernels_match_oracle(emu, dim, p, reps, block):
     ke = np.full((nc, dpc, dpc), np.nan)
     re = np.full((nc, dpc), np.nan)
     grid = 2 if nc > 2 else 1          # grid-stride loop over the cells
-    err = emu.emu_nl_cells(dim, p, nc, cell_nodes.ctypes.data, geom.ctypes.data, u_i.ctypes.data,
+    verts = np.ascontiguousarray(mesh.cell_vertices, dtype=np.float64)
+    geom_p, verts_p = (None, verts.ctypes.data) if general else (geom.ctypes.data, None)
+    err = emu.emu_nl_cells(dim, p, nc, cell_nodes.ctypes.data, geom_p, verts_p, u_i.ctypes.data,
                            acc_i.ctypes.data, params.ctypes.data, grid, block, ke.ctypes.data,
                            re.ctypes.data)
     assert err == 0
@@ -111,14 +144,9 @@ def test_generic_cell_and_face_kernels_match_oracle(emu, dim, p, reps, block):
         assert np.isnan(ke[cell][~lower]).all()         # the upper blocks are never written
         assert np.abs(re[cell] - r[loc_of]).max() <= 1e-12 * np.abs(r).max()
     # interface faces on top (K2g), then the assembled right-hand side against the oracle's
-    icells, first = np.unique(prob.iface_cell, return_index=True)
-    order = np.lexsort((prob.iface_face_no, prob.iface_cell))
-    face_no = prob.iface_face_no[order].astype(np.int32)
-    face_ptr = np.concatenate([np.searchsorted(prob.iface_cell[order], icells),
-                               [len(order)]]).astype(np.int32)
-    cell_list = icells.astype(np.int32)
+    cell_list, face_ptr, face_no = iface_lists(prob)
     err = emu.emu_nl_faces(dim, p, len(cell_list), cell_list.ctypes.data, face_ptr.ctypes.data,
-                           face_no.ctypes.data, cell_nodes.ctypes.data, geom.ctypes.data,
+                           face_no.ctypes.data, cell_nodes.ctypes.data, geom_p, verts_p,
                            u_i.ctypes.data, stress_i.ctypes.data, block, re.ctypes.data)
     assert err == 0
     rhs = np.zeros(prob.n_dofs)
@@ -129,6 +157,72 @@ def test_generic_cell_and_face_kernels_match_oracle(emu, dim, p, reps, block):
     o.nl_assemble_system()
     ref = o.get(orc.NL_SYSTEM_RHS)
     assert np.abs(rhs - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("dim,p,reps", [(2, 1, [3, 3]), (2, 2, [3, 2]), (2, 3, [2, 2]), (3, 1, [2, 2, 2]),
+                                        (3, 2, [2, 1, 2]), (3, 3, [1, 2, 1])])
+def test_general_cell_linear_and_output_kernels_match_oracle(emu, dim, p, reps):
+    """assemble_general.cuh on distorted meshes: stiffness, mass, body-force load, consistent
+    interface load (linear_elasticity.cc:289-323, 340-345, 358-373, 483-520) and the output fields
+    (DataOut patches + Postprocessor) against the oracle."""
+    import scipy.sparse as sp
+    from oracle import oracle_py as orc
+    from helpers import distort_mesh, lin_params
+    prm = lin_params(poly_degree=p, body_force=(0.4, -9.81, 0.3), scenario="PF")
+    prob = make_problem(prm, dim, reps=reps, numbering="cellwise")
+    prob.constrained[:] = 0
+    distort_mesh(prob, 0.12, seed=dim * 10 + p)
+    assert not is_affine(prob)
+    mesh = prob.mesh
+    npc, dpc, nc, n = (p + 1) ** dim, dim * (p + 1) ** dim, mesh.n_cells, prob.n_dofs
+    loc_of, cell_nodes, i2e, _ = device_view(prob, emu)
+    verts = np.ascontiguousarray(mesh.cell_vertices, dtype=np.float64)
+    rng = np.random.RandomState(11)
+    stress = 2000.0 * rng.uniform(-1, 1, n)
+    stress_i = np.ascontiguousarray(stress[i2e])
+    cell_list, face_ptr, face_no = iface_lists(prob)
+    ke, me = np.full((nc, dpc, dpc), np.nan), np.full((nc, npc, npc), np.nan)
+    re_body, re_face = np.full((nc, dpc), np.nan), np.zeros((nc, dpc))
+    bf = np.array(prm.body_force, dtype=np.float64)
+    err = emu.emu_linear_general(dim, p, nc, verts.ctypes.data, prm.lam, prm.mu, prm.rho,
+                                 bf.ctypes.data, len(cell_list), cell_list.ctypes.data,
+                                 face_ptr.ctypes.data, face_no.ctypes.data, cell_nodes.ctypes.data,
+                                 stress_i.ctypes.data, 64, ke.ctypes.data, me.ctypes.data,
+                                 re_body.ctypes.data, re_face.ctypes.data)
+    assert err == 0
+    cd = mesh.cell_dofs.reshape(nc, dpc)[:, loc_of]          # [cell, a * dim + c] -> global dof
+    K, M = np.zeros((n, n)), np.zeros((n, n))
+    for c in range(nc):
+        K[np.ix_(cd[c], cd[c])] += ke[c]
+        for cc in range(dim):                                # M = m_ab delta_cd
+            M[np.ix_(cd[c, cc::dim], cd[c, cc::dim])] += me[c]
+    o = orc.Oracle(prob)
+    o.lin_assemble_system()
+    K_o, M_o = o.csr(orc.MAT_STIFFNESS).toarray(), o.csr(orc.MAT_MASS).toarray()
+    assert np.abs(K - K_o).max() <= 1e-12 * np.abs(K_o).max()
+    assert np.abs(M - M_o).max() <= 1e-12 * np.abs(M_o).max()
+    body = np.zeros(n)
+    np.add.at(body, cd.reshape(-1), re_body.reshape(-1))
+    ref = o.get(orc.LIN_BODY_FORCE)
+    assert np.abs(body - ref).max() <= 1e-12 * np.abs(ref).max()
+    load = np.zeros(n)
+    np.add.at(load, cd.reshape(-1), re_face.reshape(-1))
+    o.set(orc.LIN_STRESS, stress)
+    o.lin_assemble_rhs()              # old_stress <- consistent loading + body force (:405-409)
+    ref = o.get(orc.LIN_OLD_STRESS)
+    assert np.abs(load + body - ref).max() <= 1e-12 * np.abs(ref).max()
+    assert np.abs(load).max() > 0.1 * np.abs(ref).max()      # the interface term is in there
+    # output fields of a smooth displacement on the distorted mesh
+    L = (np.array(mesh.p1) - np.array(mesh.p0)).min()
+    u = smooth_field(prob, 0.05 * L, seed=3)
+    o.set(orc.LIN_DISPLACEMENT, u)
+    _, fld_o = o.postprocess(orc.LIN_DISPLACEMENT)
+    u_i = np.ascontiguousarray(u[i2e])
+    fld = np.full((nc, npc, dim + dim * dim), np.nan)
+    err = emu.emu_postprocess_general(dim, p, nc, cell_nodes.ctypes.data, verts.ctypes.data,
+                                      u_i.ctypes.data, 64, fld.ctypes.data)
+    assert err == 0
+    assert np.abs(fld - fld_o).max() <= 1e-12 * max(1.0, np.abs(fld_o).max())
 
 
 # ------------------------------------------------------------------------------------------------

@@ -425,3 +425,93 @@ def test_device_linear_stiffness_and_loading_equal_the_reference_loops(libs, cas
     F = hd.get_vector(capi.LIN_OLD_STRESS)[cd]
     assert np.abs(F - F_ref).max() <= 1e-12 * np.abs(F_ref).max()
     hd.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# general (non-affine) cells: what a real deal.II host hands over once the mesh is not a box.
+# Device: Jacobians per quadrature point (assemble_nl_generic.cuh with AFFINE = false,
+# assemble_general.cuh); CPU emulation of the same kernels: tests/test_cuda_emulation.py.
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,degree,reps,numbering", [
+    (2, 1, [4, 5], "cellwise"),
+    (2, 2, [3, 4], "component_wise"),
+    (2, 3, [3, 3], "cellwise"),
+    (3, 1, [3, 3, 2], "lexicographic"),
+    (3, 2, [2, 3, 2], "cellwise"),
+])
+def test_distorted_mesh_nonlinear_tangent_residual_and_output(libs, dim, degree, reps, numbering):
+    from helpers import distort_mesh
+    capi, solvers, orc = libs
+    p = nl_params(poly_degree=degree, body_force=(0.3, -9.81, 0.2 if dim == 3 else 0.0))
+    prob = distort_mesh(make_problem(p, dim, reps=reps, numbering=numbering), 0.12, seed=degree)
+    u, du, v_old, a_old, traction = nl_state(prob)
+    o = orc.Oracle(prob)
+    o.set(orc.NL_TOTAL_DISPLACEMENT, u)
+    o.set(orc.NL_SOLUTION_DELTA, du)
+    o.set(orc.NL_VELOCITY_OLD, v_old)
+    o.set(orc.NL_ACCELERATION_OLD, a_old)
+    o.format_precice_to_deal(traction, orc.NL_EXTERNAL_STRESS)
+    o.nl_update_acceleration()
+    o.nl_assemble_system()
+    h = capi.Handle(prob)
+    h.set_vector(capi.NL_TOTAL_DISPLACEMENT, u)
+    h.set_vector(capi.NL_SOLUTION_DELTA, du)
+    h.set_vector(capi.NL_VELOCITY_OLD, v_old)
+    h.set_vector(capi.NL_ACCELERATION_OLD, a_old)
+    h.set_traction(traction)
+    res = h.nl_newton_assemble()
+    rowptr_o, col_o = o.pattern()
+    assert_matrix_close(*h.export_csr(capi.MAT_TANGENT), rowptr_o, col_o, o.values(orc.MAT_TANGENT))
+    assert rel_err(h.get_vector(capi.NL_SYSTEM_RHS), o.get(orc.NL_SYSTEM_RHS)) < 1e-12
+    assert abs(res - o.nl_error_residual()) <= 1e-12 * o.nl_error_residual()
+    _, fld_o = o.postprocess(orc.NL_TOTAL_DISPLACEMENT)
+    fld = h.postprocess(capi.NL_TOTAL_DISPLACEMENT)
+    assert np.abs(fld - fld_o).max() <= 1e-12 * max(1.0, np.abs(fld_o).max())
+    h.close()
+
+
+@pytest.mark.parametrize("dim,degree,reps", [(2, 2, [3, 8]), (3, 1, [3, 4, 2]), (2, 3, [2, 4])])
+def test_distorted_mesh_linear_matrices_and_steps(libs, dim, degree, reps):
+    from helpers import distort_mesh
+    capi, solvers, orc = libs
+    p = lin_params(poly_degree=degree, body_force=(0.0, -9.81, 0.0), type_lin="CG")
+    prob = distort_mesh(make_problem(p, dim, reps=reps), 0.12, seed=7)
+    o = orc.Oracle(prob)
+    o.lin_assemble_system()
+    h = capi.Handle(prob)
+    h.lin_assemble_once()
+    rowptr_o, col_o = o.pattern()
+    assert_matrix_close(*h.export_csr(capi.MAT_STIFFNESS), rowptr_o, col_o, o.values(orc.MAT_STIFFNESS))
+    assert_matrix_close(*h.export_csr(capi.MAT_MASS), rowptr_o, col_o, o.values(orc.MAT_MASS))
+    assert rel_err(h.get_vector(capi.LIN_BODY_FORCE), o.get(orc.LIN_BODY_FORCE)) < 1e-12
+    n = prob.n_iface_nodes
+    load = np.array([300.0, -100.0, 50.0][:dim])
+    for step in range(2):
+        buf = np.tile(load * (step + 1), n)
+        o.format_precice_to_deal(buf, orc.LIN_STRESS)
+        o.lin_step()
+        h.set_traction(buf)
+        it_g, res_g = h.lin_step(0, 8.0)
+        assert res_g <= 1e-10 and it_g > 0
+        assert rel_err(h.get_vector(capi.LIN_OLD_STRESS), o.get(orc.LIN_OLD_STRESS)) < 1e-12
+        assert np.abs(h.get_vector(capi.LIN_DISPLACEMENT) - o.get(orc.LIN_DISPLACEMENT)).max() < 1e-9
+    h.close()
+
+
+def test_distorted_mesh_coupled_run_and_multigrid_refusal(libs):
+    from helpers import distort_mesh
+    from dealii_adapter_b200 import multigrid
+    capi, solvers, orc = libs
+    p = nl_params(poly_degree=2, scenario="PF", type_lin="Direct", delta_t=0.01)
+    prob = distort_mesh(make_problem(p, 3, reps=[2, 6, 2]), 0.1, seed=4)
+    n = prob.n_iface_nodes
+    traction = lambda t, it: np.tile(np.array([1500.0, 0.0, 0.0]) * min(1.0, t / 0.03), n)
+    solid, part = run_nonlinear(libs, prob, 3, traction)
+    o, counts, written = run_oracle_nonlinear(orc, prob, 3, traction)
+    assert [len(r) for r in solid.history] == counts
+    for (w, it, data), ref in zip(part.written, written):
+        assert rel_err(data, ref) < 1e-8
+    solid.handle.close()
+    with pytest.raises(capi.GraftError) as e:
+        multigrid.Hierarchy(prob)
+    assert e.value.code == capi.GF_ERR_UNSUPPORTED
