@@ -15,6 +15,28 @@ from test_gpu_parity import (assert_matrix_close, nl_state, run_nonlinear, run_o
 
 pytestmark = pytest.mark.gpu
 
+# The driver runs `pytest -x`: one failing test would hide every later one. These tests are the
+# FIRST execution of new kernels on hardware, so each of them records a failure (reported as
+# xfailed, with the reason) and lets the run continue; the last test of the file then fails with
+# the complete list. Nothing is hidden: a green file means every test below passed.
+_FIRST_RUN_FAILURES = []
+
+
+def first_run(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        try:
+            return fn(*args, **kwargs)
+        except (pytest.skip.Exception, KeyboardInterrupt):
+            raise
+        except BaseException as exc:     # assertion, GraftError, subprocess failure ...
+            _FIRST_RUN_FAILURES.append("%s%s: %s" % (fn.__name__, tuple(kwargs.get(k) for k in
+                                       ("dim", "degree", "case") if k in kwargs), repr(exc)[:400]))
+            pytest.xfail("first hardware run failed: %s" % repr(exc)[:300])
+    return wrapper
+
 
 @pytest.fixture(scope="module")
 def libs(native_libs):
@@ -32,6 +54,7 @@ def libs(native_libs):
     (3, 3, [2, 2, 1], "cellwise"),
     (3, 3, [1, 2, 2], "lexicographic"),
 ])
+@first_run
 def test_nonlinear_tangent_and_residual_match_oracle(libs, dim, degree, reps, numbering):
     capi, solvers, orc = libs
     p = nl_params(poly_degree=degree, body_force=(0.3, -9.81, 0.2 if dim == 3 else 0.0))
@@ -76,6 +99,7 @@ def test_nonlinear_tangent_and_residual_match_oracle(libs, dim, degree, reps, nu
     (2, 4, [2, 4], "lexicographic"),
     (3, 3, [2, 2, 1], "component_wise"),
 ])
+@first_run
 def test_linear_matrices_and_steps_match_oracle(libs, dim, degree, reps, numbering):
     capi, solvers, orc = libs
     p = lin_params(poly_degree=degree, body_force=(0.0, -9.81, 0.0), type_lin="CG")
@@ -106,6 +130,7 @@ def test_linear_matrices_and_steps_match_oracle(libs, dim, degree, reps, numberi
     h.close()
 
 
+@first_run
 def test_shipped_default_linear_degree3_fsi3_direct(libs):
     """parameters.prm as shipped: linear model, FSI3, degree 3, Solver type = Direct, dt 0.005,
     nu 0.4, mu 0.5e6, rho 1000 (lines 9, 21, 25-31, 40-43, 63); 2D build."""
@@ -127,6 +152,7 @@ def test_shipped_default_linear_degree3_fsi3_direct(libs):
     ed.handle.close()
 
 
+@first_run
 def test_shipped_default_nonlinear_degree4_fsi3_direct(libs):
     """source/nonlinear_elasticity/nonlinear_elasticity.prm as shipped: neo-Hookean, FSI3, degree 4,
     Solver type = Direct (lines 24, 46-49, 65): identical Newton counts, interface displacement
@@ -148,6 +174,7 @@ def test_shipped_default_nonlinear_degree4_fsi3_direct(libs):
     solid.handle.close()
 
 
+@first_run
 def test_cg_path_degree3_3d(libs):
     """'Solver type = CG' on 3D Q3 hexahedra (rows of up to 343 node blocks): device block-Jacobi
     CG vs the oracle's SSOR-CG, same Newton counts, displacements to the inexact-Newton level."""
@@ -165,6 +192,7 @@ def test_cg_path_degree3_3d(libs):
 
 
 @pytest.mark.parametrize("dim,degree,reps", [(2, 3, [3, 2]), (3, 3, [1, 2, 1])])
+@first_run
 def test_output_fields_match_oracle(libs, dim, degree, reps):
     """gf_postprocess (DataOut patches through MappingQEulerian + Postprocessor) at degree 3."""
     capi, solvers, orc = libs
@@ -180,6 +208,7 @@ def test_output_fields_match_oracle(libs, dim, degree, reps):
     h.close()
 
 
+@first_run
 def test_multigrid_and_matrix_free_are_refused_above_degree_2(libs):
     capi, solvers, orc = libs
     from dealii_adapter_b200 import multigrid
@@ -235,6 +264,7 @@ end
 """
 
 
+@first_run
 def test_shipped_parameter_file_runs_unchanged_through_the_cpp_driver(tmp_path, native_libs):
     """elasticity_2d with the reference's own parameters.prm (degree 3): the scripted participant
     is configured by a file of the name the prm asks for; 5 time windows of 0.005; watch point vs
@@ -281,6 +311,7 @@ def test_shipped_parameter_file_runs_unchanged_through_the_cpp_driver(tmp_path, 
     (3, 2, "PF", [3, 6, 2], (1500.0, 0.0, 0.0)),
     (2, 3, "FSI3", [18, 3], (0.0, -1500.0)),
 ])
+@first_run
 def test_direct_solver_band_cholesky_nonlinear(libs, dim, degree, scenario, reps, load):
     capi, solvers, orc = libs
     p = nl_params(poly_degree=degree, scenario=scenario, type_lin="Direct", delta_t=0.01)
@@ -312,6 +343,7 @@ def test_direct_solver_band_cholesky_nonlinear(libs, dim, degree, scenario, reps
     solid2.handle.close()
 
 
+@first_run
 def test_direct_solver_linear_factorises_once_and_falls_back_beyond_the_budget(libs, monkeypatch):
     capi, solvers, orc = libs
     p = lin_params(poly_degree=2, type_lin="Direct")
@@ -370,6 +402,7 @@ def _to_global(prob, v_local):
 
 
 @pytest.mark.parametrize("case", [5, 6, 7])
+@first_run
 def test_device_cell_assembly_equals_the_reference_assembly_block(libs, case):
     import scipy.sparse as sp
     capi, solvers, orc = libs
@@ -402,6 +435,7 @@ def test_device_cell_assembly_equals_the_reference_assembly_block(libs, case):
 
 
 @pytest.mark.parametrize("case", [4, 5, 6])
+@first_run
 def test_device_linear_stiffness_and_loading_equal_the_reference_loops(libs, case):
     import scipy.sparse as sp
     capi, solvers, orc = libs
@@ -439,6 +473,7 @@ def test_device_linear_stiffness_and_loading_equal_the_reference_loops(libs, cas
     (3, 1, [3, 3, 2], "lexicographic"),
     (3, 2, [2, 3, 2], "cellwise"),
 ])
+@first_run
 def test_distorted_mesh_nonlinear_tangent_residual_and_output(libs, dim, degree, reps, numbering):
     from helpers import distort_mesh
     capi, solvers, orc = libs
@@ -471,6 +506,7 @@ def test_distorted_mesh_nonlinear_tangent_residual_and_output(libs, dim, degree,
 
 
 @pytest.mark.parametrize("dim,degree,reps", [(2, 2, [3, 8]), (3, 1, [3, 4, 2]), (2, 3, [2, 4])])
+@first_run
 def test_distorted_mesh_linear_matrices_and_steps(libs, dim, degree, reps):
     from helpers import distort_mesh
     capi, solvers, orc = libs
@@ -498,6 +534,7 @@ def test_distorted_mesh_linear_matrices_and_steps(libs, dim, degree, reps):
     h.close()
 
 
+@first_run
 def test_distorted_mesh_coupled_run_and_multigrid_refusal(libs):
     from helpers import distort_mesh
     from dealii_adapter_b200 import multigrid
@@ -515,3 +552,8 @@ def test_distorted_mesh_coupled_run_and_multigrid_refusal(libs):
     with pytest.raises(capi.GraftError) as e:
         multigrid.Hierarchy(prob)
     assert e.value.code == capi.GF_ERR_UNSUPPORTED
+
+
+
+def test_zzz_every_first_run_test_above_passed():
+    assert not _FIRST_RUN_FAILURES, "\n".join(_FIRST_RUN_FAILURES)
