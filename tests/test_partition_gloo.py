@@ -22,12 +22,12 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, reps, numbering, out):
+def _worker(rank, world, port, reps, numbering, out, degree=2):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        prob = make_problem(nl_params(poly_degree=2), 3, reps=reps, numbering=numbering)
+        prob = make_problem(nl_params(poly_degree=degree), 3, reps=reps, numbering=numbering)
         part = prob.mesh.partition(1, world, rank)
         rng = np.random.RandomState(42)
         g = rng.uniform(-1, 1, prob.n_dofs)              # same global vector on every rank
@@ -59,6 +59,10 @@ def _worker(rank, world, port, reps, numbering, out):
         # owned node are local)
         cells_g = set(part.local_cell_global.tolist())
         cd = prob.mesh.cell_dofs.reshape(-1, prob.mesh.dofs_per_cell)
+        # the local cell -> dof table is the global one in local numbering, entry by entry (the
+        # FESystem local order must survive the renumbering, also above degree 2)
+        lcd = part.cell_dofs.reshape(-1, prob.mesh.dofs_per_cell)
+        ok = ok and np.array_equal(part.local_to_global[lcd], cd[part.local_cell_global])
         owned_g = set(part.local_to_global[:part.n_owned_dofs].tolist())
         for c in range(prob.mesh.n_cells):
             if c not in cells_g and owned_g.intersection(cd[c].tolist()):
@@ -68,12 +72,14 @@ def _worker(rank, world, port, reps, numbering, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,reps,numbering", [(2, [2, 4, 2], "cellwise"),
-                                                  (3, [1, 5, 2], "component_wise")])
-def test_halo_exchange_lists_with_gloo(native_libs, world, reps, numbering):
+@pytest.mark.parametrize("world,reps,numbering,degree", [(2, [2, 4, 2], "cellwise", 2),
+                                                         (3, [1, 5, 2], "component_wise", 2),
+                                                         (2, [1, 4, 2], "cellwise", 3)])
+def test_halo_exchange_lists_with_gloo(native_libs, world, reps, numbering, degree):
     out = mp.get_context("spawn").Array("i", [0] * world)
     port = _free_port()
-    procs = [mp.get_context("spawn").Process(target=_worker, args=(r, world, port, reps, numbering, out))
+    procs = [mp.get_context("spawn").Process(target=_worker,
+                                             args=(r, world, port, reps, numbering, out, degree))
              for r in range(world)]
     for p in procs:
         p.start()
