@@ -26,14 +26,24 @@ CASES = {
     "lin_mg": ("linear", "mg", [4, 32, 4], 80000),
     "nl_mg_partitioned_coarse": ("neo-Hookean", "mg", [4, 32, 4], 0),   # halos on every level
 }
+# run only on request (--cases): first hardware run in tests/test_zz_gpu_high_degree.py
+EXTRA_CASES = {
+    # name: (model, preconditioner, reps, replicate_below_dofs, polynomial degree)
+    "nl_jacobi_q3": ("neo-Hookean", "jacobi", [1, 6, 1], None, 3),
+    "lin_jacobi_q3": ("linear", "jacobi", [1, 6, 1], None, 3),
+}
 N_STEPS = 2
 LOAD = (1500.0, 0.0, 100.0)
 
 
 def make_case(name):
     from dealii_adapter_b200.problem import SolverParameters, make_problem
-    model, precond, reps, rep_below = CASES[name]
-    p = SolverParameters(model=model, type_lin="CG", poly_degree=2, scenario="PF", delta_t=0.01,
+    degree = 2
+    if name in CASES:
+        model, precond, reps, rep_below = CASES[name]
+    else:
+        model, precond, reps, rep_below, degree = EXTRA_CASES[name]
+    p = SolverParameters(model=model, type_lin="CG", poly_degree=degree, scenario="PF", delta_t=0.01,
                          mu=0.5e6, nu=0.4, rho=1000.0, tol_lin=1e-6, max_iterations_lin=2.0)
     return make_problem(p, 3, reps=reps, numbering="lexicographic"), model, precond, rep_below
 

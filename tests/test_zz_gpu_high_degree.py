@@ -555,5 +555,22 @@ def test_distorted_mesh_coupled_run_and_multigrid_refusal(libs):
 
 
 
+@first_run
+def test_partitioned_run_at_degree_3_reproduces_the_single_rank_run(native_libs, tmp_path):
+    """Slab partition at degree 3 (node planes on Gauss-Lobatto coordinates, halo of p = 3 planes):
+    2 ranks on one device through the NCCL-free bootstrap, block-Jacobi CG, against one rank -
+    identical Newton and CG counts, bitwise displacements (partition-independent reductions)."""
+    native_libs.build_cuda()
+    import mgpu_worker as w
+    from test_gpu_multirank import _compare, _spawn
+    ref = {}
+    for name in w.EXTRA_CASES:
+        hist, written, levels = w.run_case(name, 1, 0, 0, None)
+        ref[name] = {"written": written, "history": hist, "levels": levels}
+    got = _spawn(2, "ipc", str(tmp_path / "q3.pkl"), cases=",".join(w.EXTRA_CASES))
+    for name in w.EXTRA_CASES:
+        _compare(ref, got, name, True)
+
+
 def test_zzz_every_first_run_test_above_passed():
     assert not _FIRST_RUN_FAILURES, "\n".join(_FIRST_RUN_FAILURES)
