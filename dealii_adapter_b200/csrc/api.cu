@@ -99,19 +99,23 @@ namespace
         gf::vec_axpby(c, c.cg_r.p, -1.0, c.cg_v.p, 1.0); // r = b - A x
         gf::direct_solve(c, c.cg_r.p, c.cg_z.p);
         gf::vec_axpby(c, x, 1.0, c.cg_z.p, 1.0);
-        // the answer is checked before it is used: ||b - A x|| <= 1e-10 ||b|| (the CG stand-in
-        // stops at 1e-13 ||b||; a factorisation of an ill-conditioned tangent that cannot reach
-        // this is discarded in favour of the CG)
+        // the answer is checked before it is used. Forward error: the refinement step must have
+        // been a small correction, ||dx|| <= 1e-6 ||x|| (then the refined x is good to ~1e-12;
+        // a broken or hopelessly ill-conditioned factorisation gives dx ~ x). Residual: the
+        // attainable ||b - A x|| / ||b|| is eps ||A|| ||x|| / ||b||, 1e-14 .. 1e-12 on the test
+        // meshes and growing like h^-2, so only a loose bound is imposed on it.
         gf::launch_spmv(c, A, x, c.cg_v.p, nullptr);
         gf::vec_copy(c, c.cg_r.p, b);
         gf::vec_axpby(c, c.cg_r.p, -1.0, c.cg_v.p, 1.0);
         const double rn = gf::vec_masked_norm(c, c.cg_r.p, false);
         const double bn = gf::vec_masked_norm(c, b, false);
+        const double zn = gf::vec_masked_norm(c, c.cg_z.p, false);
+        const double xn = gf::vec_masked_norm(c, x, false);
         c.direct.last_residual = bn > 0 ? rn / bn : rn;
-        if (!(rn <= 1e-10 * bn))
+        if (!(zn <= 1e-6 * xn && rn <= 1e-6 * bn))
           {
             GF_REQUIRE(c.direct_mode != 1, GF_ERR_NOT_CONVERGED,
-                       "direct solver: residual check failed");
+                       "direct solver: refinement / residual check failed");
             return false;
           }
         c.direct.n_solves++;

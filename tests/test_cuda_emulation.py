@@ -280,7 +280,7 @@ def test_band_cholesky_solves_the_tangent_system(emu, dim, p, reps, numbering):
     ref = spla.spsolve(A.tocsc(), b)
     assert np.abs(x - ref).max() <= 1e-9 * np.abs(ref).max()
     assert np.abs(A @ x - b).max() <= 1e-10 * np.abs(b).max()
-    assert w[0] <= w[1]                 # RCM never widens these meshes' band
+    assert w[0] <= w[1]                 # the better of RCM and the given numbering
     # an indefinite matrix is reported, not factorised silently
     val_bad = val.copy()
     val_bad[0] = -abs(val_bad[0])       # first diagonal entry (node 0 couples to itself first)
