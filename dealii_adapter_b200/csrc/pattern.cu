@@ -200,7 +200,7 @@ namespace gf
         std::sort(by_coord.begin(), by_coord.end(), [&](int32_t a, int32_t b) {
           return coord_of_x[xdofs[a]] < coord_of_x[xdofs[b]];
         });
-            // the closest two support points of a cell are more than h / p^2 apart (Gauss-Lobatto)
+        // the closest two support points of a cell are more than h / p^2 apart (Gauss-Lobatto)
         const double tol = c.p <= 2 ? 1e-6 * h_min / c.p : 1e-6 * h_min / (c.p * c.p);
         int32_t      pl  = 0;
         for (int64_t k = 0; k < n_nodes; ++k)
