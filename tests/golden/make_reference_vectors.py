@@ -113,6 +113,101 @@ def face_tables(dim, p, nq1, h, faces):
     return out
 
 
+def q1_vertex_basis(dim, xi):
+    """values and unit-cell gradients [nv], [nv, dim] of the MappingQ1 vertex shape functions"""
+    nv = 1 << dim
+    val, grad = np.ones(nv), np.ones((nv, dim))
+    for v in range(nv):
+        for l in range(dim):
+            hi = (v >> l) & 1
+            val[v] *= xi[l] if hi else 1.0 - xi[l]
+            for k in range(dim):
+                grad[v, k] *= (1.0 if hi else -1.0) if l == k else (xi[l] if hi else 1.0 - xi[l])
+    return val, grad
+
+
+def distorted_assembly_cases():
+    """One GENERAL (non-affine) cell each: (dim, degree, vertices [nv, dim], interface faces, body
+    force). The reference block is geometry-agnostic (it reads FEValues); the tables it gets here
+    are those of MappingQ1 on the distorted cell, computed with numpy."""
+    rng = np.random.RandomState(77)
+    out = []
+    for dim, p, h, bf in ((2, 2, [0.03, 0.02], (0.0, -9.81, 0.0)), (3, 1, [0.05, 0.04, 0.06], (1.5, -9.81, 0.5)),
+                          (2, 3, [0.04, 0.05], (0.0, 0.0, 0.0))):
+        nv = 1 << dim
+        verts = np.array([[((v >> d) & 1) * h[d] for d in range(dim)] for v in range(nv)], dtype=float)
+        verts += 0.15 * np.array(h) * rng.uniform(-1, 1, size=(nv, dim))
+        out.append((dim, p, verts, [0, 1, 3], bf))
+    return out
+
+
+def run_distorted_assembly_case(k, dim, p, verts, faces, body_force):
+    import ref_formulas as rf
+    rng = np.random.RandomState(300 + k)
+    nq1 = p + 2
+    N, dN, w = rf.cell_tables(dim, p, nq1)
+    x1, w1 = rf.gauss01(nq1)
+    npc, nq, nqf = N.shape[1], len(w), nq1 ** (dim - 1)
+    dpc = npc * dim
+    gradN, JxW = np.zeros_like(dN), np.zeros(nq)
+    for q in range(nq):
+        xi = [x1[(q // nq1 ** d) % nq1] for d in range(dim)]
+        _, g = q1_vertex_basis(dim, xi)
+        J = verts.T @ g                                     # J[i, j] = dX_i / dxi_j
+        gradN[q] = dN[q] @ np.linalg.inv(J)
+        JxW[q] = np.linalg.det(J) * w[q]
+    assert JxW.min() > 0
+    nodes = rf.hierarchical_nodes(dim, p)
+    mu, nu, rho, beta, dt = 0.5e6, 0.4, 1000.0, 0.25, 0.01
+    alpha_1 = 1.0 / (beta * dt * dt)
+    hmin = np.abs(verts[-1] - verts[0]).min()
+    u = (0.1 if p <= 2 else 0.1 / (p * p)) * hmin * rng.uniform(-1, 1, dpc)
+    acc = 50.0 * rng.uniform(-1, 1, dpc)
+    stress = 2000.0 * rng.uniform(-1, 1, dpc)
+    words = [dim, npc, nq, nqf, len(faces), mu, nu, rho, alpha_1] + list(body_force) + [7]
+    words += list(N.reshape(-1)) + list(gradN.reshape(-1)) + list(JxW)
+    for f in faces:
+        d, c = f // 2, float(f % 2)
+        Nf, JxWf, normal = np.zeros((nqf, npc)), np.zeros(nqf), np.zeros((nqf, dim))
+        for q in range(nqf):
+            fi = [(q // nq1 ** kk) % nq1 for kk in range(dim - 1)]
+            fq = [x1[i] for i in fi]
+            wq = np.prod([w1[i] for i in fi])
+            if dim == 2:
+                xi = [0.0, 0.0]
+                xi[d], xi[1 - d] = c, fq[0]
+            elif d == 0:
+                xi = [c, fq[0], fq[1]]
+            elif d == 1:
+                xi = [fq[1], c, fq[0]]
+            else:
+                xi = [fq[0], fq[1], c]
+            v1 = [rf.lagrange_1d(p, xi[kk])[0][0] for kk in range(dim)]
+            for a, lex in enumerate(nodes):
+                Nf[q, a] = np.prod([v1[kk][lex[kk]] for kk in range(dim)])
+            _, g = q1_vertex_basis(dim, xi)
+            J = verts.T @ g
+            n_ref = np.zeros(dim)
+            n_ref[d] = 1.0 if f % 2 else -1.0
+            nda = np.linalg.det(J) * np.linalg.inv(J).T @ n_ref      # Nanson: n da
+            JxWf[q] = np.linalg.norm(nda) * wq
+            normal[q] = nda / np.linalg.norm(nda)
+        words += [f, 7] + list(Nf.reshape(-1)) + list(JxWf) + list(normal.reshape(-1))
+    words += list(u) + list(acc) + list(stress)
+    if p > 2:
+        s2c = rf.system_to_node_component(dim, p)
+        words += [a for a, c in s2c] + [c for a, c in s2c]
+    text = " ".join(repr(float(x)) if isinstance(x, (float, np.floating)) else str(int(x)) for x in words)
+    res = subprocess.run([ASM_DRIVER], input=text, capture_output=True, text=True, check=True).stdout
+    rows = [l.split() for l in res.strip().split("\n")]
+    K = np.array(rows[:dpc], dtype=float)
+    r = np.array(rows[dpc], dtype=float)
+    meta = np.array([dim, p, 0.0, 0.0, 0.0] + list(body_force) + [mu, nu, rho, beta, dt])
+    return {"asm%d_meta" % k: meta, "asm%d_faces" % k: np.array(faces, dtype=np.int64),
+            "asm%d_verts" % k: verts, "asm%d_u" % k: u, "asm%d_acc" % k: acc,
+            "asm%d_stress" % k: stress, "asm%d_K" % k: K, "asm%d_r" % k: r}
+
+
 def assembly_cases():
     """One Cartesian cell each: (dim, degree, edge lengths, interface faces, body force)."""
     return [(2, 1, [0.1, 0.05], [0, 1, 3], (0.0, 0.0, 0.0)),
@@ -487,7 +582,10 @@ def generate():
     cases = assembly_cases()
     for k, c in enumerate(cases):
         out.update(run_assembly_case(k, *c))
-    out["n_assembly"] = np.array(len(cases))
+    dcases = distorted_assembly_cases()
+    for k, c in enumerate(dcases):
+        out.update(run_distorted_assembly_case(len(cases) + k, *c))
+    out["n_assembly"] = np.array(len(cases) + len(dcases))
     # ---- material -------------------------------------------------------------------------
     rows = []
     for k, (dim, mu, nu, J, bv) in enumerate(material_cases()):

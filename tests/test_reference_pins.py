@@ -80,12 +80,15 @@ def test_fixture_is_what_the_reference_produces():
     assert r.returncode == 0, r.stdout + r.stderr
 
 
-def one_cell_oracle(orc, dim, degree, h, faces, body_force, mu, nu, rho, beta, dt):
-    """Oracle on a single unconstrained Cartesian cell whose interface faces are `faces`."""
+def one_cell_oracle(orc, dim, degree, h, faces, body_force, mu, nu, rho, beta, dt, verts=None):
+    """Oracle on a single unconstrained cell whose interface faces are `faces`: Cartesian with
+    edge lengths h, or the general cell with the given vertices."""
     p = nl_params(poly_degree=degree, scenario="PF", mu=mu, nu=nu, rho=rho, beta=beta, delta_t=dt,
                   body_force=tuple(body_force))
-    prob = make_problem(p, dim, reps=[1] * dim, numbering="cellwise",
-                        box=([0.0] * dim, list(h[:dim])))
+    box = list(h[:dim]) if verts is None else [1.0] * dim
+    prob = make_problem(p, dim, reps=[1] * dim, numbering="cellwise", box=([0.0] * dim, box))
+    if verts is not None:
+        prob.mesh.cell_vertices = np.ascontiguousarray(verts, dtype=np.float64).reshape(-1)
     prob.constrained = np.zeros_like(prob.constrained)
     # PF marks x-, x+, y+ (faces 0, 1, 3) as interface: keep or drop them all
     assert sorted(prob.iface_face_no.tolist()) == [0, 1, 3]
@@ -112,14 +115,17 @@ def test_oracle_cell_assembly_equals_the_reference_assembly_block(native_libs, r
     against the oracle assembling the same one-cell problem."""
     from oracle import oracle_py as orc
     n = int(ref["n_assembly"])
-    assert n == 8                       # 5 cases of degree 1-2, then 2D Q3, 2D Q4, 3D Q3
+    # 5 cases of degree 1-2, then 2D Q3, 2D Q4, 3D Q3, then three GENERAL (non-affine) cells
+    assert n == 11
     for k in range(n):
         meta = ref["asm%d_meta" % k]
         dim, degree = int(meta[0]), int(meta[1])
         h, body_force = meta[2:5], meta[5:8]
         mu, nu, rho, beta, dt = meta[8:13]
         faces = ref["asm%d_faces" % k]
-        prob, o = one_cell_oracle(orc, dim, degree, h, faces, body_force, mu, nu, rho, beta, dt)
+        verts = ref["asm%d_verts" % k] if "asm%d_verts" % k in ref.files else None
+        prob, o = one_cell_oracle(orc, dim, degree, h, faces, body_force, mu, nu, rho, beta, dt,
+                                  verts)
         cd = prob.mesh.cell_dofs.reshape(-1)
         o.set(orc.NL_TOTAL_DISPLACEMENT, to_global(prob, ref["asm%d_u" % k]))
         o.set(orc.NL_SOLUTION_DELTA, np.zeros(prob.n_dofs))
@@ -134,7 +140,8 @@ def test_oracle_cell_assembly_equals_the_reference_assembly_block(native_libs, r
         assert np.array_equal(K_ref, K_ref.T)            # the reference mirrors the lower triangle
         if len(faces):
             # the Neumann term is really in there: without the faces the residual differs
-            prob2, o2 = one_cell_oracle(orc, dim, degree, h, [], body_force, mu, nu, rho, beta, dt)
+            prob2, o2 = one_cell_oracle(orc, dim, degree, h, [], body_force, mu, nu, rho, beta, dt,
+                                        verts)
             o2.set(orc.NL_TOTAL_DISPLACEMENT, to_global(prob, ref["asm%d_u" % k]))
             o2.set(orc.NL_ACCELERATION, to_global(prob, ref["asm%d_acc" % k]))
             o2.nl_assemble_system()

@@ -401,9 +401,10 @@ def _to_global(prob, v_local):
     return out
 
 
-@pytest.mark.parametrize("case", [5, 6, 7])
+@pytest.mark.parametrize("case", [5, 6, 7, 8, 9, 10])
 @first_run
 def test_device_cell_assembly_equals_the_reference_assembly_block(libs, case):
+    """cases 5-7: degree 3 / 4 on Cartesian cells; 8-10: GENERAL (non-affine) cells of degree 2, 1, 3"""
     import scipy.sparse as sp
     capi, solvers, orc = libs
     ref = _golden()
@@ -411,11 +412,14 @@ def test_device_cell_assembly_equals_the_reference_assembly_block(libs, case):
     dim, degree = int(meta[0]), int(meta[1])
     h, body_force = meta[2:5], meta[5:8]
     mu, nu, rho, beta, dt = meta[8:13]
-    assert degree >= 3 and sorted(ref["asm%d_faces" % case].tolist()) == [0, 1, 3]
+    verts = ref["asm%d_verts" % case] if "asm%d_verts" % case in ref.files else None
+    assert (degree >= 3 or verts is not None) and sorted(ref["asm%d_faces" % case].tolist()) == [0, 1, 3]
     p = nl_params(poly_degree=degree, scenario="PF", mu=mu, nu=nu, rho=rho, beta=beta, delta_t=dt,
                   body_force=tuple(body_force))
     prob = make_problem(p, dim, reps=[1] * dim, numbering="cellwise",
-                        box=([0.0] * dim, list(h[:dim])))
+                        box=([0.0] * dim, list(h[:dim]) if verts is None else [1.0] * dim))
+    if verts is not None:
+        prob.mesh.cell_vertices = np.ascontiguousarray(verts, dtype=np.float64).reshape(-1)
     prob.constrained = np.zeros_like(prob.constrained)
     cd = prob.mesh.cell_dofs.reshape(-1)       # local dof i of the reference block = global cd[i]
     hd = capi.Handle(prob)
