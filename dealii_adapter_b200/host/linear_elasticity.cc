@@ -50,6 +50,17 @@ namespace Linear_Elasticity
               << (n_mg_levels > 1 ? "geometric multigrid, " + std::to_string(n_mg_levels) + " levels" :
                                     std::string("block-Jacobi"))
               << std::endl;
+    if (parameters.type_lin == "Direct")
+      {
+        // SparseDirectUMFPACK's replacement: band Cholesky on the device where it fits
+        int64_t   half_bandwidth = 0;
+        const int rc = gf_direct_info(host.handle, nullptr, &half_bandwidth, nullptr);
+        std::cout << "\t Direct solver: "
+                  << (rc == GF_OK ? "band Cholesky on the device, half bandwidth " +
+                                      std::to_string(half_bandwidth) :
+                                    std::string("CG to 1e-13 (") + gf_last_error(host.handle) + ")")
+                  << std::endl;
+      }
     auto vec         = [&](int id) { return VectorType{host.handle, id}; };
     old_velocity     = vec(GF_LIN_OLD_VELOCITY);
     velocity         = vec(GF_LIN_VELOCITY);

@@ -70,6 +70,14 @@ int gf_create(const gf_desc *d, gf_handle *out)
 void        gf_destroy(gf_handle h) { LOG("destroy\n"); free(h); }
 const char *gf_last_error(gf_handle h) { (void)h; return "fake device error"; }
 int gf_set_option(gf_handle h, int o, int64_t v) { (void)h; LOG("set_option %d %lld\n", o, (long long)v); return GF_OK; }
+int gf_direct_info(gf_handle h, int64_t *n, int64_t *w, double *r)
+{
+  (void)h;
+  if (n) *n = 0;
+  if (w) *w = 7;
+  if (r) *r = 0.0;
+  return GF_OK;
+}
 int gf_mg_attach(gf_handle f, gf_handle c, const int32_t *t) { (void)f; (void)c; (void)t; LOG("mg_attach\n"); return GF_OK; }
 int gf_set_traction(gf_handle h, const double *b) { LOG("set_traction %.17g\n", h->n_iface_nodes ? b[h->dim > 1 ? 1 : 0] : 0.0); return GF_OK; }
 int gf_get_interface_displacement(gf_handle h, double *b)

@@ -283,6 +283,7 @@ def test_shipped_parameter_file_runs_unchanged_through_the_cpp_driver(tmp_path, 
                        timeout=600, env=dict(os.environ, GF_DIRECT_SOLVER="auto"))
     assert r.returncode == 0, r.stderr + r.stdout[-2000:]
     assert "Polynomial degree: 3" in r.stdout
+    assert "Direct solver: band Cholesky on the device" in r.stdout
     vtk = (tmp_path / "dealii-output" / "solution-000.vtk").read_text()
     assert "POINTS %d double" % (54 * 16) in vtk          # one order-3 Lagrange quad per cell
     log = np.loadtxt(tmp_path / "watchpoint.log")
