@@ -59,6 +59,8 @@ class GfDesc(C.Structure):
         ("send_ptr", C.c_void_p), ("send_dofs", C.c_void_p),
         ("recv_ptr", C.c_void_p), ("recv_dofs", C.c_void_p),
         ("dof_global", C.c_void_p), ("slab_axis", C.c_int32),
+        ("n_constraint_lines", C.c_int64), ("line_dof", C.c_void_p), ("line_ptr", C.c_void_p),
+        ("line_master", C.c_void_p), ("line_weight", C.c_void_p),
     ]
 
 
@@ -264,6 +266,19 @@ class Handle:
                            np.ascontiguousarray(partition.recv_dofs, dtype=np.int32)]
             d.nbr_rank, d.send_ptr, d.send_dofs, d.recv_ptr, d.recv_dofs = (
                 a.ctypes.data for a in keep_alive[-5:])
+        # hanging-node constraint lines (problem.extra["constraint_lines"] = (dof, ptr, master,
+        # weight) in the caller's numbering; the structured stand-in meshes have none)
+        lines = getattr(problem, "extra", {}).get("constraint_lines")
+        if lines is not None:
+            if partition is not None:
+                raise ValueError("hanging-node constraints need a serial handle")
+            keep_alive += [np.ascontiguousarray(lines[0], dtype=np.int32),
+                           np.ascontiguousarray(lines[1], dtype=np.int64),
+                           np.ascontiguousarray(lines[2], dtype=np.int32),
+                           np.ascontiguousarray(lines[3], dtype=np.float64)]
+            d.n_constraint_lines = len(keep_alive[-4])
+            d.line_dof, d.line_ptr, d.line_master, d.line_weight = (
+                a.ctypes.data for a in keep_alive[-4:])
         h = C.c_void_p()
         rc = L.gf_create(C.byref(d), C.byref(h))
         if rc != GF_OK:

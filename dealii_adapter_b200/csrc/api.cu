@@ -79,8 +79,8 @@ namespace
   bool direct_apply(gf_context &c, const double *A, const double *b, double *x,
                     const bool constant_matrix)
   {
-    if (c.operator_kind != 0 || !gf::direct_available(c))
-      return false;
+    if (c.operator_kind != 0 || c.lines.n > 0 || !gf::direct_available(c))
+      return false; // (the band holds A, not the condensed C^T A C)
     try
       {
         if (!(constant_matrix && c.direct.factored && c.direct.factor_is_system_matrix))
@@ -425,6 +425,7 @@ extern "C"
         setup_halo(*c, *d);
         gf::comm_setup_context(*c);
         allocate_state(*c);
+        gf::setup_lines(*c, *d);
         c->n_global_dofs_for_maxit = c->n_owned;
         if (c->comm)
           {
@@ -466,6 +467,9 @@ extern "C"
         c->desc.nbr_rank = c->desc.send_dofs = c->desc.recv_dofs = nullptr;
         c->desc.send_ptr = c->desc.recv_ptr = nullptr;
         c->desc.dof_global = nullptr;
+        c->desc.line_dof = c->desc.line_master = nullptr;
+        c->desc.line_ptr = nullptr;
+        c->desc.line_weight = nullptr;
         GF_CUDA_CHECK(cudaStreamSynchronize(c->stream));
         *out = c;
         return GF_OK;
@@ -550,8 +554,8 @@ extern "C"
             break;
           case GF_OPT_OPERATOR:
             GF_REQUIRE(value == 0 || value == 1, GF_ERR_INVALID_ARG, "unknown operator kind");
-            GF_REQUIRE(value == 0 ||
-                         (c.model == GF_MODEL_NEO_HOOKEAN && c.dim == 3 && c.p <= 2 && c.affine),
+            GF_REQUIRE(value == 0 || (c.model == GF_MODEL_NEO_HOOKEAN && c.dim == 3 && c.p <= 2 &&
+                                      c.affine && c.lines.n == 0),
                        GF_ERR_UNSUPPORTED,
                        "the matrix-free operator is available for the 3D neo-Hookean model, "
                        "polynomial degree 1 or 2, parallelepiped cells");
@@ -766,6 +770,12 @@ extern "C"
           if (gf::mg_active(c))
             gf::mg_update_operators(c, c.tmp0.p); // coarse tangents at the injected state + smoothers
         }
+      if (c.lines.n > 0)
+        {
+          // condensed right-hand side C^T r (distribute_local_to_global :769-773)
+          gf::lines_condense(c, c.vec[GF_NL_SYSTEM_RHS].p);
+          gf::vec_zero_constrained(c, c.vec[GF_NL_SYSTEM_RHS].p);
+        }
       const double r = gf::vec_masked_norm(c, c.vec[GF_NL_SYSTEM_RHS].p, true); // :449
       GF_CUDA_CHECK(
         cudaMemcpyAsync(c.h_err, c.err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
@@ -832,6 +842,7 @@ extern "C"
       if (c.comm)
         gf::halo_exchange(c, x);
       const double u = gf::vec_masked_norm(c, x, true); // :476
+      gf::lines_distribute(c, x);                        // hanging nodes: constraints.distribute
       if (upd_abs)
         *upd_abs = u;
       gf::vec_axpby(c, c.vec[GF_NL_SOLUTION_DELTA].p, 1.0, x, 1.0); // :487
@@ -906,6 +917,8 @@ extern "C"
                       nullptr); // :419-420
       gf::vec_axpby(c, rhs, -dt, c.tmp1.p, 1.0);
       // MatrixTools::apply_boundary_values with zero values (:448-451): rhs and solution
+      if (c.lines.n > 0)
+        gf::lines_condense(c, rhs); // hanging_node_constraints.condense(system_rhs) :422
       gf::vec_zero_constrained(c, rhs);
       gf::vec_zero_constrained(c, vel);
       // ---- solve :525-575
@@ -941,6 +954,7 @@ extern "C"
                               std::to_string(res) + "."};
       if (c.comm)
         gf::halo_exchange(c, vel);
+      gf::lines_distribute(c, vel); // hanging_node_constraints.distribute(velocity) :571-572
       // ---- update_displacement :579-586
       gf::vec_axpby(c, c.vec[GF_LIN_DISPLACEMENT].p, dt * theta, vel, 1.0);
       gf::vec_axpby(c, c.vec[GF_LIN_DISPLACEMENT].p, dt * (1 - theta),
@@ -1273,12 +1287,14 @@ extern "C"
                      double *last_residual)
   {
     return guarded(h, [&](gf_context &c) {
-      const bool ok = c.operator_kind == 0 && gf::direct_available(c);
+      const bool ok = c.operator_kind == 0 && c.lines.n == 0 && gf::direct_available(c);
       GF_REQUIRE(ok, GF_ERR_UNSUPPORTED,
                  "direct solver not in use: " +
-                   (c.direct_mode == 2 ? std::string("GF_OPT_DIRECT_SOLVER = 2") :
-                                         (c.operator_kind != 0 ? std::string("matrix-free operator") :
-                                                                 c.direct.why)));
+                   (c.direct_mode == 2 ?
+                      std::string("GF_OPT_DIRECT_SOLVER = 2") :
+                      (c.operator_kind != 0 ? std::string("matrix-free operator") :
+                                              (c.lines.n > 0 ? std::string("hanging-node constraints") :
+                                                               c.direct.why))));
       if (n_solves)
         *n_solves = c.direct.n_solves;
       if (half_bandwidth)

@@ -113,6 +113,19 @@ namespace gf
     DevBuf<double> dphi, dphif, dphip;
   };
 
+  // hanging-node constraint lines (constraints.cu): internal dof numbering
+  struct ConstraintLines
+  {
+    int64_t         n = 0, n_masters = 0;
+    DevBuf<int32_t> dof, master;    // [n], [ptr[n]]
+    DevBuf<int64_t> ptr;            // [n + 1]
+    DevBuf<double>  weight;
+    DevBuf<int32_t> mdof, slave;    // transposed: distinct masters, their constrained dofs
+    DevBuf<int64_t> mptr;
+    DevBuf<double>  mweight;
+    DevBuf<uint8_t> norm_mask;      // Dirichlet or hanging: skipped by the Newton norms
+  };
+
   // band Cholesky for 'Solver type = Direct' (direct.cu, direct_band.cuh)
   struct DirectBand
   {
@@ -330,6 +343,7 @@ struct gf_context
   int  cg_initial_guess = 1; // GF_OPT_CG_INITIAL_GUESS
   int  operator_kind  = 0;
   bool lin_assembled  = false;
+  gf::ConstraintLines lines;   // gf_desc.line_*: hanging-node constraints (empty on box meshes)
   int  direct_mode    = 0;     // GF_OPT_DIRECT_SOLVER: 0 auto, 1 band Cholesky or error, 2 tight CG
   gf::DirectBand direct;
   bool defer_tangent  = false; // scatter / preconditioner / multigrid update on first use
@@ -467,6 +481,10 @@ namespace gf
   void mg_refresh_f32(gf_context &c); // FP32 operator copies of all levels below and incl. c
   void mg_refresh_f32_level(gf_context &c); // this level only (rank-local)
   bool mg_active(const gf_context &c);
+  // constraints.cu: hanging-node constraint lines (no-ops without lines)
+  void setup_lines(gf_context &c, const gf_desc &d);
+  void lines_distribute(gf_context &c, double *x); // x_s = sum w x_m
+  void lines_condense(gf_context &c, double *y);   // y_m += sum w y_s ; y_s = 0
   // direct.cu: 'Solver type = Direct'
   bool direct_available(gf_context &c);                  // ordering + memory check (cached)
   bool direct_factor(gf_context &c, const double *A);    // false: not positive definite

@@ -573,6 +573,8 @@ namespace gf
     GF_REQUIRE(child_cells != nullptr, GF_ERR_INVALID_ARG, "null child_cells");
     // the transfer below relies on nested support points (injection of the state, restriction
     // weights on the half-step grid): true for equidistant nodes only, i.e. FE_Q(1), FE_Q(2)
+    GF_REQUIRE(f.lines.n == 0 && co.lines.n == 0, GF_ERR_UNSUPPORTED,
+               "geometric multigrid does not take hanging-node constraints (block-Jacobi CG)");
     GF_REQUIRE(f.affine && co.affine, GF_ERR_UNSUPPORTED,
                "geometric multigrid needs parallelepiped cells (general cells: block-Jacobi CG)");
     GF_REQUIRE(f.p <= 2, GF_ERR_UNSUPPORTED,

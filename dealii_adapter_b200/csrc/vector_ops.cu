@@ -150,16 +150,18 @@ namespace gf
   }
   double vec_masked_norm(gf_context &c, const double *v, bool mask_constrained)
   {
+    // constraints.is_constrained(i): Dirichlet dofs and, where the mesh has them, hanging nodes
+    const uint8_t *mask = c.lines.n > 0 ? c.lines.norm_mask.p : c.constrained.p;
     {
       ProfScope ps(c, Profile::UPDATE, 2);
       if (c.n_red_chunks > 0)
         {
           if (c.dim == 3)
             norm_chunks_kernel<3><<<c.n_red_chunks, RED_THREADS, 0, c.stream>>>(
-              c.red_chunk_ptr.p, v, c.constrained.p, mask_constrained, c.partials.p);
+              c.red_chunk_ptr.p, v, mask, mask_constrained, c.partials.p);
           else
             norm_chunks_kernel<2><<<c.n_red_chunks, RED_THREADS, 0, c.stream>>>(
-              c.red_chunk_ptr.p, v, c.constrained.p, mask_constrained, c.partials.p);
+              c.red_chunk_ptr.p, v, mask, mask_constrained, c.partials.p);
         }
       GF_CUDA_CHECK(cudaGetLastError());
       reduce_sums(c, 1, -1, false);

@@ -107,6 +107,22 @@ extern "C"
      *                       refine_global: nonlinear_elasticity.cc:237-246). */
     const int64_t *dof_global;
     int32_t        slab_axis;
+    /* --- hanging-node constraints (optional; zero-initialise to leave unset) ---
+     * The lines DoFTools::make_hanging_node_constraints puts into the AffineConstraints object
+     * (linear_elasticity.cc:196-207; nonlinear: the same object as the Dirichlet constraints):
+     * u[line_dof[k]] = sum_j line_weight[j] * u[line_master[j]], j in [line_ptr[k], line_ptr[k+1]),
+     * zero inhomogeneity, chains resolved (AffineConstraints::close()), masters and constrained
+     * dofs disjoint. On the reference's meshes (refine_global only) the set is empty. The library
+     * assembles the unconstrained operator A and solves the condensed system C^T A C (what
+     * condense() / distribute_local_to_global produce) by applying x -> C^T (A (C x)) inside the
+     * CG and condensing the right-hand sides; `distribute()` follows every solve. Serial handles,
+     * CG with block-Jacobi (gf_mg_attach, the matrix-free operator and the band Cholesky answer
+     * GF_ERR_UNSUPPORTED / fall back); gf_export_csr returns the UNcondensed matrix. */
+    int64_t        n_constraint_lines;
+    const int32_t *line_dof;    /* [n_constraint_lines] */
+    const int64_t *line_ptr;    /* [n_constraint_lines + 1] */
+    const int32_t *line_master; /* [line_ptr[n_constraint_lines]] */
+    const double * line_weight;
   } gf_desc;
 
   /* DoF vectors addressable through gf_get_vector / gf_set_vector.

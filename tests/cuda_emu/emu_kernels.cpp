@@ -5,6 +5,7 @@
 
 #include "assemble_general.cuh"
 #include "assemble_nl_generic.cuh"
+#include "constraints.cuh"
 #include "direct_band.cuh"
 #include "fe_tables_host.h"
 #include "rcm.h"
@@ -225,6 +226,16 @@ extern "C"
   {
     return dim == 3 ? run_postprocess<3>(p, n_cells, cell_nodes, verts, u, block, fields) :
                       run_postprocess<2>(p, n_cells, cell_nodes, verts, u, block, fields);
+  }
+  // hanging-node constraint lines: x <- C x (distribute), y <- C^T y (condense + zero)
+  void emu_lines(int64_t n_lines, const int32_t *dof, const int64_t *ptr, const int32_t *master,
+                 const double *weight, int64_t n_masters, const int32_t *mdof, const int64_t *mptr,
+                 const int32_t *slave, const double *mweight, double *x, double *y)
+  {
+    gf_emu::launch(2u, 32u, 0, [&] { gf::lines_distribute_kernel(n_lines, dof, ptr, master, weight, x); });
+    gf_emu::launch(2u, 32u, 0,
+                   [&] { gf::lines_condense_kernel(n_masters, mdof, mptr, slave, mweight, y); });
+    gf_emu::launch(2u, 32u, 0, [&] { gf::lines_zero_kernel(n_lines, dof, y); });
   }
   // the product's host tables, for the tests: loc_of [npc * dim]
   int emu_loc_of(int dim, int p, int *loc_of)

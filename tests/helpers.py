@@ -86,3 +86,157 @@ def distort_mesh(problem, amp=0.12, seed=0):
         sp[cd[:, i]] = np.einsum("v,cvd->cd", w, new)
     mesh.support_points = sp
     return problem
+
+
+def hanging_node_problem(params, degree):
+    """A 2D mesh WITH hanging nodes, which the structured stand-in cannot produce: the domain
+    [0,2] x [0,1], left half one cell, right half refined once (4 cells). The nodes of the fine
+    cells on the edge x = 1 that the coarse cell does not own hang; their constraint lines are the
+    coarse edge's 1D shape functions at their positions (what
+    DoFTools::make_hanging_node_constraints produces, linear_elasticity.cc:196-207).
+    Roles: x = 0 clamped, y = 1 and x = 2 interface, y = 0 free. degree 1 or 2 (equidistant nodes).
+    Returns a Problem whose `extra["constraint_lines"]` = (dof, ptr, master, weight)."""
+    from types import SimpleNamespace
+    import ref_formulas as rf
+    from dealii_adapter_b200.problem import MODEL_LINEAR, MODEL_NEO_HOOKEAN, Problem
+    dim, p = 2, degree
+    assert p in (1, 2)
+    boxes = [((0.0, 0.0), (1.0, 1.0))] + [((1.0 + 0.5 * i, 0.5 * j), (1.5 + 0.5 * i, 0.5 + 0.5 * j))
+                                            for j in range(2) for i in range(2)]
+    nodes = rf.hierarchical_nodes(dim, p)
+    s2c = rf.system_to_node_component(dim, p)
+    ids, coords, cell_dofs, cell_vertices = {}, [], [], []
+    for lo, hi in boxes:
+        for v in range(4):
+            cell_vertices += [hi[0] if v & 1 else lo[0], hi[1] if v & 2 else lo[1]]
+        row = []
+        for a, c in s2c:
+            x = tuple(round(lo[d] + (hi[d] - lo[d]) * nodes[a][d] / p, 12) for d in range(dim))
+            if x not in ids:
+                ids[x] = len(ids)
+                coords.append(x)
+            row.append(ids[x] * dim + c)
+        cell_dofs += row
+    n_nodes = len(ids)
+    n_dofs = n_nodes * dim
+    coords = np.array(coords)
+    support_points = np.repeat(coords, dim, axis=0)
+    # hanging nodes: on x = 1, 0 < y < 1, not a node of the coarse cell
+    coarse_y = np.linspace(0.0, 1.0, p + 1)
+    dof, ptr, master, weight = [], [0], [], []
+    for x, n in ids.items():
+        if abs(x[0] - 1.0) < 1e-12 and not np.any(np.abs(coarse_y - x[1]) < 1e-12):
+            w = rf.lagrange_1d(p, np.array([x[1]]))[0][0]           # coarse edge basis at y
+            for c in range(dim):
+                dof.append(n * dim + c)
+                for k, yk in enumerate(coarse_y):
+                    if abs(w[k]) > 1e-14:
+                        master.append(ids[(1.0, round(float(yk), 12))] * dim + c)
+                        weight.append(float(w[k]))
+                ptr.append(len(master))
+    constrained = np.zeros(n_dofs, dtype=np.uint8)
+    constrained[np.repeat(np.abs(coords[:, 0]) < 1e-12, dim)] = 1
+    # interface faces: y = 1 (face 3) of cells 0, 3, 4 and x = 2 (face 1) of cells 2, 4
+    iface = [(0, 3), (3, 3), (4, 3), (2, 1), (4, 1)]
+    on_if = (np.abs(coords[:, 1] - 1.0) < 1e-12) | (np.abs(coords[:, 0] - 2.0) < 1e-12)
+    if_nodes = np.nonzero(on_if)[0]
+    iface_dofs = np.stack([if_nodes * dim + c for c in range(dim)]).astype(np.int32)
+    mesh = SimpleNamespace(dim=dim, degree=p, n_cells=len(boxes), n_dofs=n_dofs, n_nodes=n_nodes,
+                           dofs_per_cell=dim * (p + 1) ** dim, reps=[2, 1], p0=[0.0, 0.0],
+                           p1=[2.0, 1.0], numbering="custom",
+                           cell_dofs=np.array(cell_dofs, dtype=np.int32),
+                           cell_vertices=np.array(cell_vertices, dtype=np.float64),
+                           support_points=support_points)
+    model = MODEL_NEO_HOOKEAN if params.model == "neo-Hookean" else MODEL_LINEAR
+    prob = Problem(dim, p, model, params, mesh, constrained,
+                   np.array([c for c, f in iface], dtype=np.int32),
+                   np.array([f for c, f in iface], dtype=np.int32), iface_dofs)
+    prob.extra["constraint_lines"] = (np.array(dof, dtype=np.int32), np.array(ptr, dtype=np.int64),
+                                      np.array(master, dtype=np.int32), np.array(weight))
+    return prob
+
+
+def constraint_matrix(prob):
+    """C [n_dofs, n_dofs] (scipy): identity on unconstrained dofs, the weights in the rows of the
+    hanging dofs (whose own columns are empty)."""
+    import scipy.sparse as sp
+    dof, ptr, master, weight = prob.extra["constraint_lines"]
+    n = prob.n_dofs
+    C = sp.lil_matrix((n, n))
+    hanging = set(dof.tolist())
+    for i in range(n):
+        if i not in hanging:
+            C[i, i] = 1.0
+    for k, s in enumerate(dof):
+        for j in range(ptr[k], ptr[k + 1]):
+            C[s, master[j]] = weight[j]
+    return C.tocsr()
+
+
+def reference_linear_steps(orc, prob, buffers):
+    """ElastoDynamics time steps 'by definition' with scipy on top of the oracle's UNcondensed
+    K, M and consistent loading: assemble_rhs (:378-454) incl. hanging_node_constraints.condense,
+    apply_boundary_values, the solve as a sparse LU, distribute (:571-572), update_displacement
+    (:579-586). `buffers`: one interface traction buffer per step. Returns the displacement vectors.
+    Without constraint lines this is the oracle's own lin_step (a CPU test checks that)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    p, n = prob.params, prob.n_dofs
+    dt, th = p.delta_t, p.theta
+    o = orc.Oracle(prob)
+    o.lin_assemble_system()
+    K, M = o.csr(orc.MAT_STIFFNESS), o.csr(orc.MAT_MASS)
+    body = o.get(orc.LIN_BODY_FORCE)
+    Cm = constraint_matrix(prob) if prob.extra.get("constraint_lines") is not None else sp.identity(n, format="csr")
+    hanging = np.zeros(n, dtype=bool)
+    if prob.extra.get("constraint_lines") is not None:
+        hanging[prob.extra["constraint_lines"][0]] = True
+    fixed = (prob.constrained != 0) | hanging
+    free = np.nonzero(~fixed)[0]
+    A = (Cm.T @ (M + (th * dt) ** 2 * K) @ Cm).tocsr()[free][:, free].tocsc()
+    lu = spla.splu(A)
+    v, d, F_old = np.zeros(n), np.zeros(n), np.zeros(n)
+    out = []
+    for buf in buffers:
+        o.format_precice_to_deal(buf, orc.LIN_STRESS)
+        o.set(orc.LIN_OLD_STRESS, np.zeros(n))
+        o.set(orc.LIN_VELOCITY, np.zeros(n))
+        o.set(orc.LIN_DISPLACEMENT, np.zeros(n))
+        o.lin_assemble_rhs()
+        F = o.get(orc.LIN_OLD_STRESS)          # consistent loading + body force of this step
+        rhs = dt * th * F + dt * (1 - th) * F_old + M @ v - th * (1 - th) * dt * dt * (K @ v) - dt * (K @ d)
+        rhs = Cm.T @ rhs
+        v_new = np.zeros(n)
+        v_new[free] = lu.solve(rhs[free])
+        v_new = Cm @ v_new
+        d = d + dt * th * v_new + dt * (1 - th) * v
+        v, F_old = v_new, F
+        out.append(d.copy())
+    return out
+
+
+def reference_nonlinear_step(orc, prob, buf, n_newton=8):
+    """One Solid time step from rest 'by definition': Newton iterations on top of the oracle's
+    UNcondensed tangent / residual (Dirichlet rows already eliminated), condensed with the
+    constraint matrix, solved by a sparse LU, distributed. Returns the total displacement."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    n = prob.n_dofs
+    o = orc.Oracle(prob)
+    o.format_precice_to_deal(buf, orc.NL_EXTERNAL_STRESS)
+    Cm = constraint_matrix(prob) if prob.extra.get("constraint_lines") is not None else sp.identity(n, format="csr")
+    hanging = np.zeros(n, dtype=bool)
+    if prob.extra.get("constraint_lines") is not None:
+        hanging[prob.extra["constraint_lines"][0]] = True
+    free = np.nonzero(~((prob.constrained != 0) | hanging))[0]
+    delta = np.zeros(n)
+    for it in range(n_newton):
+        o.set(orc.NL_SOLUTION_DELTA, delta)
+        o.nl_update_acceleration()
+        o.nl_assemble_system()
+        A, b = o.csr(orc.MAT_TANGENT), o.get(orc.NL_SYSTEM_RHS)
+        At = (Cm.T @ A @ Cm).tocsr()[free][:, free].tocsc()
+        x = np.zeros(n)
+        x[free] = spla.splu(At).solve((Cm.T @ b)[free])
+        delta = delta + Cm @ x
+    return delta

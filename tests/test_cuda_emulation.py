@@ -27,7 +27,8 @@ def emu(native_libs):
     csrc = os.path.join(ROOT, "dealii_adapter_b200", "csrc")
     srcs = [os.path.join(EMU, "emu_kernels.cpp"), os.path.join(EMU, "cuda_runtime.h")] + \
         [os.path.join(csrc, f) for f in ("assemble_nl_generic.cuh", "assemble_general.cuh",
-                                         "direct_band.cuh", "rcm.h", "emu_compat.cuh",
+                                         "direct_band.cuh", "rcm.h", "constraints.cuh",
+                                         "emu_compat.cuh",
                                          "kernel_utils.cuh", "nl_material.cuh", "fe_tables_host.h",
                                          "fe_basis.h")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
@@ -223,6 +224,38 @@ def test_general_cell_linear_and_output_kernels_match_oracle(emu, dim, p, reps):
                                       u_i.ctypes.data, 64, fld.ctypes.data)
     assert err == 0
     assert np.abs(fld - fld_o).max() <= 1e-12 * max(1.0, np.abs(fld_o).max())
+
+
+def test_constraint_line_kernels(emu):
+    """constraints.cuh: x <- C x on the hanging dofs, y <- C^T y (+ zero) against scipy, on the
+    hanging-node mesh of tests/helpers.py (Q2: two hanging nodes, three masters each)."""
+    from helpers import constraint_matrix, hanging_node_problem, lin_params
+    emu.emu_lines.restype = None
+    emu.emu_lines.argtypes = [C.c_int64] + [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 6
+    for p in (1, 2):
+        prob = hanging_node_problem(lin_params(poly_degree=p), p)
+        dof, ptr, master, weight = prob.extra["constraint_lines"]
+        Cm = constraint_matrix(prob)
+        # transposed lists as constraints.cu builds them: masters ascending, lines in order
+        by_master = {}
+        for k, s_ in enumerate(dof):
+            for j in range(ptr[k], ptr[k + 1]):
+                by_master.setdefault(int(master[j]), []).append((int(s_), float(weight[j])))
+        mdof = np.array(sorted(by_master), dtype=np.int32)
+        mptr = np.concatenate([[0], np.cumsum([len(by_master[m]) for m in mdof])]).astype(np.int64)
+        slave = np.array([s_ for m in mdof for s_, _ in by_master[m]], dtype=np.int32)
+        mweight = np.array([w for m in mdof for _, w in by_master[m]])
+        rng = np.random.RandomState(p)
+        x, y = rng.uniform(-1, 1, prob.n_dofs), rng.uniform(-1, 1, prob.n_dofs)
+        x_ref = x.copy()
+        x_ref[dof] = 0.0
+        x_ref = Cm @ x_ref                     # masters keep their values, hanging dofs interpolate
+        y_ref = Cm.T @ y                       # hanging entries of C^T y are empty rows -> 0
+        emu.emu_lines(len(dof), dof.ctypes.data, ptr.ctypes.data, master.ctypes.data,
+                      weight.ctypes.data, len(mdof), mdof.ctypes.data, mptr.ctypes.data,
+                      slave.ctypes.data, mweight.ctypes.data, x.ctypes.data, y.ctypes.data)
+        assert np.abs(x - x_ref).max() < 1e-15
+        assert np.abs(y - y_ref).max() < 1e-15 and np.all(y[dof] == 0.0)
 
 
 # ------------------------------------------------------------------------------------------------

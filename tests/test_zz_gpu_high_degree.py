@@ -577,5 +577,62 @@ def test_partitioned_run_at_degree_3_reproduces_the_single_rank_run(native_libs,
         _compare(ref, got, name, True)
 
 
+# ------------------------------------------------------------------------------------------------
+# hanging-node constraints (gf_desc.line_*): make_hanging_node_constraints / condense / distribute
+# of linear_elasticity.cc:196-207,355,422,571 and the AffineConstraints object of the nonlinear
+# solver. Mesh: tests/helpers.py::hanging_node_problem; reference: condensation by definition
+# (helpers.reference_*; tests/test_hanging_node_reference.py checks it on the CPU).
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("degree", [1, 2])
+@first_run
+def test_hanging_nodes_linear_steps(libs, degree):
+    from helpers import constraint_matrix, hanging_node_problem, reference_linear_steps
+    capi, solvers, orc = libs
+    p = lin_params(poly_degree=degree, type_lin="CG", body_force=(0.0, -9.81, 0.0),
+                   max_iterations_lin=20.0)
+    prob = hanging_node_problem(p, degree)
+    n = prob.n_iface_nodes
+    bufs = [np.tile([40.0 * (k + 1), -200.0], n) for k in range(3)]
+    ref = reference_linear_steps(orc, prob, bufs)
+    part = solvers.FakeParticipant(2, 3, p.delta_t, lambda t, it: bufs[min(2, int(round(t / p.delta_t)) - 1)])
+    ed = solvers.ElastoDynamics(prob, part)
+    ed.run()
+    d = ed.handle.get_vector(capi.LIN_DISPLACEMENT)
+    assert rel_err(d, ref[-1]) < 1e-6
+    dof = prob.extra["constraint_lines"][0]
+    m = d.copy()
+    m[dof] = 0.0
+    assert np.abs(constraint_matrix(prob) @ m - d).max() <= 1e-14 * np.abs(d).max()   # conforming
+    for k in range(3):
+        assert rel_err(part.written[k][2], ref[k][prob.iface_dofs.T].reshape(-1)) < 1e-6
+    ed.handle.close()
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+@first_run
+def test_hanging_nodes_nonlinear_step_and_refusals(libs, degree):
+    from helpers import constraint_matrix, hanging_node_problem, reference_nonlinear_step
+    capi, solvers, orc = libs
+    p = nl_params(poly_degree=degree, type_lin="Direct", scenario="PF", delta_t=0.01)
+    prob = hanging_node_problem(p, degree)
+    buf = np.tile([0.0, -1500.0], prob.n_iface_nodes)
+    ref = reference_nonlinear_step(orc, prob, buf)
+    part = solvers.FakeParticipant(2, 1, p.delta_t, lambda t, it: buf)
+    solid = solvers.Solid(prob, part)
+    solid.handle.set_option(capi.OPT_DIRECT_SOLVER, 0)   # auto: lines -> the CG stand-in runs
+    solid.run()
+    u = solid.handle.get_vector(capi.NL_TOTAL_DISPLACEMENT)
+    assert 3 <= len(solid.history[0]) <= 7
+    assert rel_err(u, ref) < 1e-8
+    dof = prob.extra["constraint_lines"][0]
+    m = u.copy()
+    m[dof] = 0.0
+    assert np.abs(constraint_matrix(prob) @ m - u).max() <= 1e-14 * np.abs(u).max()
+    with pytest.raises(capi.GraftError) as e:
+        solid.handle.direct_info()                       # the band Cholesky does not take lines
+    assert e.value.code == capi.GF_ERR_UNSUPPORTED and "hanging" in str(e.value)
+    solid.handle.close()
+
+
 def test_zzz_every_first_run_test_above_passed():
     assert not _FIRST_RUN_FAILURES, "\n".join(_FIRST_RUN_FAILURES)
