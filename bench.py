@@ -55,6 +55,7 @@ TRACTION = (2000.0, 0.0, 0.0)
 N_SUB = 2
 CFG4_REPS = (128, 1024, 128)   # BASELINE configs[3]: linear Q1 cantilever, 51,171,075 DoFs
 STRONG_TIMEOUT_S = 480         # watchdog of the cfg4 part (normally ~40 s incl. set-up)
+SIDE_TIMEOUT_S = 420           # watchdog of variants + cpu_baseline (normally ~60 s)
 
 
 def params():
@@ -486,8 +487,99 @@ def main():
     prof_full = h.profile(reset=True)
     solves_full = solid.newton_solves - s0
     h.set_option(capi.OPT_PROFILE, 0)
-    # ---- variants benchmarked alongside (north_star: matrix-free operator beside the SpMV) ------
+    comm_info = None
+    if world > 1:
+        kind, n_halo, n_ar = comm.transport()
+        halo_us, ar_us = h.comm_timed(50)
+        comm_info = {"transport": kind, "halo_exchange_us": halo_us, "allreduce_us": ar_us,
+                     "halo_exchanges_issued": n_halo, "allreduces_issued": n_ar,
+                     "halo_ms_per_newton_solve_diag": prof_full["halo_ms"] / max(1, solves_full)}
+
+    t_value = max(wall_value, dev_ms * 1e-3)
+    if world > 1:
+        t = torch.tensor([t_value, wall_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_value, wall_e2e = float(t[0]), float(t[1])
+    ms_spmv, spmv_bytes = h.spmv_timed(capi.MAT_TANGENT, 5)   # on every rank: see run_cfg4
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        spmv_avg_ms = prof["spmv_ms"] / max(1, prof["spmv_launches"])
+        achieved = spmv_bytes / (spmv_avg_ms * 1e-3) / 1e9
+        # DRAM bytes per launch of the SHIPPED default kernel from this round's `ncu --set full`
+        # capture of the same matrix (profiles/r02_spmv_ncu_summary.md); null if not captured
+        traffic_path = os.path.join(ROOT, "profiles", "r02_spmv_traffic.json")
+        traffic = json.load(open(traffic_path)).get("dram_bytes_per_launch") if os.path.exists(traffic_path) else None
+        line = {
+            "metric": "newton_step_dofs_per_s", "value": n_dofs_global * solves_value / t_value,
+            "unit": "DoFs/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
+            "ms_per_step": 1e3 * t_value / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "n_dofs": n_dofs_global, "n_dofs_per_gpu": h.n_owned,
+                       "nnz_scalar": h.nnz(), "newton_solves_in_timed_region": solves_value,
+                       "cg_iterations_in_timed_region": cg_its_value,
+                       "ms_per_cg_iteration": 1e3 * t_value / max(1, cg_its_value),
+                       "cg_iterations_per_newton_solve": cg_its_value / max(1, solves_value),
+                       "preconditioner": args.precond,
+                       "spmv_kernel_option": args.spmv_kernel, "mg_matrix_precision": args.mg_precision,
+                       "multigrid_levels": [q.mesh.reps for q in hierarchy.problems] if hierarchy else None,
+                       "multigrid_levels_replicated": hierarchy.replicated if hierarchy else None,
+                       "l2_policy": "inputs larger than L2 (matrix %.2f GB per GPU streamed every "
+                                    "CG iteration)" % (spmv_bytes / 1e9),
+                       "device_ms": dev_ms, "parallelism": "slab%d" % world},
+            "clocks": clocks,
+            "e2e": {"value": n_dofs_global * solves_e2e / wall_e2e, "unit": "DoFs/s",
+                    "h2d_bytes_per_step": int(buf.nbytes), "d2h_bytes_per_step": int(buf.nbytes),
+                    "ms_per_step": 1e3 * wall_e2e / args.steps, "newton_solves": solves_e2e},
+            "gpu_launches": int(prof["kernel_launches"]),
+            "roofline": {"bound": "hbm",
+                         "kernel": "finest-level SpMV launches of the timed region: spmv_tma2_kernel<3, "
+                                   "..., 8, 2, 16, TR> (two TMA rings, 8 gather + 16 consumer warps, "
+                                   "transposed row reduction) for the CG vmult and the Chebyshev-"
+                                   "smoother / residual vmults of the V-cycle",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": traffic,
+                         "bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_avg_ms,
+                         "launches": int(prof["spmv_launches"]),
+                         "standalone_launch_ms": ms_spmv,
+                         "share_of_step": prof["spmv_ms"] / (1e3 * t_value)},
+            "phase_ms_per_newton_solve": dict(
+                {k: v / max(1, solves_full) for k, v in prof_full.items() if k.endswith("_ms")},
+                note="diagnostic pass of %d steps outside the timed regions, every kernel class "
+                     "bracketed with CUDA events (adds launch gaps to the small kernels)" % N_SUB),
+            "variants": {},
+        }
+        if comm_info:
+            line["comm"] = comm_info
+    # ---- from here on the main line exists; everything below is a side measurement that must never
+    # cost it: exceptions are recorded in the line, and a watchdog emits the line as it stands if
+    # the side measurements hang (rank 0 prints, every rank leaves)
     variants = {}
+    snapshot = None
+    if rank == 0:
+        line["variants"] = variants
+        snapshot = json.dumps(line)
+
+    emitted = []
+
+    def emit_line(note=None):
+        if rank != 0 or emitted:
+            return
+        emitted.append(True)
+        for attempt in range(3):          # the main thread may be mutating `line` (watchdog call)
+            try:
+                if note:
+                    line["side_measurements"] = note
+                emit(line)
+                return
+            except Exception:
+                time.sleep(0.05)
+        fallback = json.loads(snapshot)
+        fallback["side_measurements"] = note or "line emitted from the snapshot taken after the main regions"
+        emit(fallback)
+
+    disarm = arm_watchdog(SIDE_TIMEOUT_S, lambda: emit_line(
+        "variants / cpu_baseline did not finish within %d s" % SIDE_TIMEOUT_S))
+    # ---- variants benchmarked alongside (north_star: matrix-free operator beside the SpMV) ------
     if not args.no_variants and world == 1 and os.environ.get("GF_PROFILE_RUN") != "1":
         try:
             h.set_option(capi.OPT_OPERATOR, 1)
@@ -596,8 +688,6 @@ def main():
                     "steps": N_SUB, "newton_solves": solid.newton_solves - s0,
                     "ms_per_newton_solve": 1e3 * tv / max(1, solid.newton_solves - s0)}
                 solid.parameters.type_lin = "CG"
-                for k in range(N_SUB):      # the run's operators again for the stand-alone SpMV timing
-                    resident_pass(k)
         except Exception as exc:      # a failing side measurement must not cost the main line
             variants["error"] = "%s: %s" % (type(exc).__name__, exc)
             for opt, val in ((capi.OPT_OPERATOR, 0), (capi.OPT_SPMV_KERNEL, args.spmv_kernel),
@@ -607,83 +697,28 @@ def main():
                 except Exception:
                     pass
 
-    comm_info = None
-    if world > 1:
-        kind, n_halo, n_ar = comm.transport()
-        halo_us, ar_us = h.comm_timed(50)
-        comm_info = {"transport": kind, "halo_exchange_us": halo_us, "allreduce_us": ar_us,
-                     "halo_exchanges_issued": n_halo, "allreduces_issued": n_ar,
-                     "halo_ms_per_newton_solve_diag": prof_full["halo_ms"] / max(1, solves_full)}
-
-    t_value = max(wall_value, dev_ms * 1e-3)
-    if world > 1:
-        t = torch.tensor([t_value, wall_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_value, wall_e2e = float(t[0]), float(t[1])
-    ms_spmv, spmv_bytes = h.spmv_timed(capi.MAT_TANGENT, 5)   # on every rank: see run_cfg4
-    if rank == 0:
-        peak, peak_src = measured_peak()
-        spmv_avg_ms = prof["spmv_ms"] / max(1, prof["spmv_launches"])
-        achieved = spmv_bytes / (spmv_avg_ms * 1e-3) / 1e9
-        # DRAM bytes per launch of the SHIPPED default kernel from this round's `ncu --set full`
-        # capture of the same matrix (profiles/r02_spmv_ncu_summary.md); null if not captured
-        traffic_path = os.path.join(ROOT, "profiles", "r02_spmv_traffic.json")
-        traffic = json.load(open(traffic_path)).get("dram_bytes_per_launch") if os.path.exists(traffic_path) else None
-        line = {
-            "metric": "newton_step_dofs_per_s", "value": n_dofs_global * solves_value / t_value,
-            "unit": "DoFs/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
-            "ms_per_step": 1e3 * t_value / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "n_dofs": n_dofs_global, "n_dofs_per_gpu": h.n_owned,
-                       "nnz_scalar": h.nnz(), "newton_solves_in_timed_region": solves_value,
-                       "cg_iterations_in_timed_region": cg_its_value,
-                       "ms_per_cg_iteration": 1e3 * t_value / max(1, cg_its_value),
-                       "cg_iterations_per_newton_solve": cg_its_value / max(1, solves_value),
-                       "preconditioner": args.precond,
-                       "spmv_kernel_option": args.spmv_kernel, "mg_matrix_precision": args.mg_precision,
-                       "multigrid_levels": [q.mesh.reps for q in hierarchy.problems] if hierarchy else None,
-                       "multigrid_levels_replicated": hierarchy.replicated if hierarchy else None,
-                       "l2_policy": "inputs larger than L2 (matrix %.2f GB per GPU streamed every "
-                                    "CG iteration)" % (spmv_bytes / 1e9),
-                       "device_ms": dev_ms, "parallelism": "slab%d" % world},
-            "clocks": clocks,
-            "e2e": {"value": n_dofs_global * solves_e2e / wall_e2e, "unit": "DoFs/s",
-                    "h2d_bytes_per_step": int(buf.nbytes), "d2h_bytes_per_step": int(buf.nbytes),
-                    "ms_per_step": 1e3 * wall_e2e / args.steps, "newton_solves": solves_e2e},
-            "gpu_launches": int(prof["kernel_launches"]),
-            "roofline": {"bound": "hbm",
-                         "kernel": "finest-level SpMV launches of the timed region: spmv_tma2_kernel<3, "
-                                   "..., 8, 2, 16, TR> (two TMA rings, 8 gather + 16 consumer warps, "
-                                   "transposed row reduction) for the CG vmult and the Chebyshev-"
-                                   "smoother / residual vmults of the V-cycle",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": traffic,
-                         "bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_avg_ms,
-                         "launches": int(prof["spmv_launches"]),
-                         "standalone_launch_ms": ms_spmv,
-                         "share_of_step": prof["spmv_ms"] / (1e3 * t_value)},
-            "phase_ms_per_newton_solve": dict(
-                {k: v / max(1, solves_full) for k, v in prof_full.items() if k.endswith("_ms")},
-                note="diagnostic pass of %d steps outside the timed regions, every kernel class "
-                     "bracketed with CUDA events (adds launch gaps to the small kernels)" % N_SUB),
-            "variants": variants,
-        }
-        if comm_info:
-            line["comm"] = comm_info
-        if world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
             r = cpu_run(1, 0, "baseline")
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample",
                                                       "full_size_anchor") if k in r}
-    if hierarchy:
-        hierarchy.close()
-    else:
-        h.close()
+        except Exception as exc:
+            line["cpu_baseline"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    disarm()
+    try:
+        if hierarchy:
+            hierarchy.close()
+        else:
+            h.close()
+    except Exception as exc:
+        if rank == 0:
+            line["close_error"] = "%s: %s" % (type(exc).__name__, exc)
     # ---- north_star's multi-GPU target in the same driver-run line: cfg4, STRONG scaling -------
     if not args.no_strong and os.environ.get("GF_PROFILE_RUN") != "1" and args.precond == "mg":
         def give_up():
             if rank == 0:
                 line["strong_scaling"] = {"error": "did not finish within %d s" % STRONG_TIMEOUT_S}
-                emit(line)
+            emit_line()
         disarm = arm_watchdog(STRONG_TIMEOUT_S, give_up)
         try:
             strong = run_cfg4(args, world, rank, local_rank, comm, dist, torch)
@@ -692,8 +727,7 @@ def main():
         disarm()
         if rank == 0:
             line["strong_scaling"] = strong
-    if rank == 0:
-        emit(line)
+    emit_line()
     if world > 1:
         comm.close()
         dist.destroy_process_group()
