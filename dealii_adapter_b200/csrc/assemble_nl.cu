@@ -33,6 +33,9 @@ namespace gf
 {
   namespace
   {
+#ifndef GF_CUDA_EMULATION // tuned kernels (mbarrier pipelines, warp shuffles): hardware only; the
+                          // CPU stand-in of tests/cuda_emu runs every (dim, degree) on the
+                          // generic kernels below
     template <int DIM, int P>
     struct NLCfg
     {
@@ -741,6 +744,7 @@ namespace gf
         c.re_buf.p, c.err_flag.p);
       GF_CUDA_CHECK(cudaGetLastError());
     }
+#endif // GF_CUDA_EMULATION
     // generic kernels (assemble_nl_generic.cuh): every (dim, degree) without a tuned
     // instantiation, i.e. degree >= 3, and every mesh with non-affine cells (AFFINE = false)
     template <int DIM, bool AFFINE>
@@ -799,6 +803,7 @@ namespace gf
         else
           launch_cells_generic<2, false>(c, u_total, accel, c0, c1);
       }
+#ifndef GF_CUDA_EMULATION
     else if (c.dim == 3 && c.p == 2)
       launch_cells_t<3, 2>(c, u_total, accel, c0, c1);
     else if (c.dim == 3 && c.p == 1)
@@ -807,6 +812,7 @@ namespace gf
       launch_cells_t<2, 2>(c, u_total, accel, c0, c1);
     else if (c.dim == 2 && c.p == 1)
       launch_cells_t<2, 1>(c, u_total, accel, c0, c1);
+#endif
     else if (c.dim == 3)
       launch_cells_generic<3, true>(c, u_total, accel, c0, c1);
     else
@@ -823,6 +829,7 @@ namespace gf
         else
           launch_faces_generic<2, false>(c, u_total, stress);
       }
+#ifndef GF_CUDA_EMULATION
     else if (c.dim == 3 && c.p == 2)
       launch_faces_t<3, 2>(c, u_total, stress);
     else if (c.dim == 3 && c.p == 1)
@@ -831,6 +838,7 @@ namespace gf
       launch_faces_t<2, 2>(c, u_total, stress);
     else if (c.dim == 2 && c.p == 1)
       launch_faces_t<2, 1>(c, u_total, stress);
+#endif
     else if (c.dim == 3)
       launch_faces_generic<3, true>(c, u_total, stress);
     else

@@ -6,6 +6,7 @@
 // primitives, no mbarriers / TMA.
 #pragma once
 #ifdef GF_CUDA_EMULATION
+#include <cuda_runtime.h> // the stand-in of tests/cuda_emu (-I tests/cuda_emu)
 #define GF_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(gf_emu::dynamic_smem())
 #else
 #define GF_DYN_SMEM(type, name)                                                                  \

@@ -470,7 +470,8 @@ namespace gf
   void mf_apply(gf_context &c, const double *x, double *y, double *dot_partials);
   int  mf_dot_partials(const gf_context &c);
   double mf_bytes(const gf_context &c);
-  // operator of the CG / smoothers on this level: assembled SpMV or the matrix-free tangent
+  // operator.cu: operator of the CG / smoothers on this level (assembled SpMV or the matrix-free
+  // tangent, condensed where the handle has hanging-node constraint lines)
   void   op_apply(gf_context &c, const double *val, const double *x, double *y,
                   double *dot_partials);
   int    op_dot_partials(const gf_context &c);

@@ -62,7 +62,7 @@ namespace gf
       }
   }
 
-#ifndef GF_CUDA_EMULATION // PTX and warp-level helpers: not for kernels that also run in tests/cuda_emu
+#ifndef GF_CUDA_EMULATION // PTX helpers: not for kernels that also run in tests/cuda_emu
   // ---- shared-memory mbarriers (producer/consumer pipelines: spmv.cu, assemble_nl.cu) -----------
   __device__ __forceinline__ uint32_t smem_u32(const void *p)
   {
@@ -100,7 +100,9 @@ namespace gf
   {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
   }
+#endif // GF_CUDA_EMULATION
 
+  // (the emulation provides __shfl_xor_sync among the 32 CPU threads of a warp)
   __device__ __forceinline__ double warp_sum(double v)
   {
 #pragma unroll
@@ -167,5 +169,4 @@ namespace gf
           }
       }
   }
-#endif // GF_CUDA_EMULATION
 } // namespace gf

@@ -141,6 +141,7 @@ namespace gf
     }
 
 
+#ifndef GF_CUDA_EMULATION // TMA / mbarrier kernels: hardware only (tests/cuda_emu runs the LDG kernel)
     // ------------------------------------------------------------------------------------------
     // TMA-tiled kernel: producer warp (TMA) -> gather warps (x) -> consumer warps (FMA)
     // ------------------------------------------------------------------------------------------
@@ -752,6 +753,26 @@ namespace gf
         int(c.n_tiles), c.tile_desc.p, c.tile_meta.p, c.bcol.p, val, x, y, dot_partials, st);
     }
 
+#else  // GF_CUDA_EMULATION: the CPU stand-in of tests/cuda_emu has no TMA; every launch takes
+       // the LDG kernel (kind 1), the tile lists are still built (pattern.cu)
+    int effective_kind(const gf_context &, bool) { return 1; }
+    template <int DIM, bool DOT, typename VT>
+    void launch_tma2_t(gf_context &, int, const VT *, const double *, double *, double *, const int *)
+    {
+      throw Error{GF_ERR_UNSUPPORTED, "TMA SpMV kernels do not exist in the CPU emulation"};
+    }
+    template <int DIM, bool DOT, typename VT>
+    void launch_tma_t(gf_context &, const VT *, const double *, double *, double *, const int *)
+    {
+      throw Error{GF_ERR_UNSUPPORTED, "TMA SpMV kernels do not exist in the CPU emulation"};
+    }
+    template <int DIM, bool DOT, typename VT, typename XT, int GW, int GG, int CW, bool TR = false>
+    void launch_tma2_w(gf_context &, const VT *, const double *, double *, double *, const int *)
+    {
+      throw Error{GF_ERR_UNSUPPORTED, "TMA SpMV kernels do not exist in the CPU emulation"};
+    }
+#endif // GF_CUDA_EMULATION
+
     // FP64 array -> FP32 copy with the same indexing (n even: every scalar row is padded)
     __global__ void convert_f32_kernel(const int64_t n_pairs, const double2 *__restrict__ in,
                                        float2 *__restrict__ out)
@@ -885,7 +906,7 @@ namespace gf
   // matrices without tiles fall back to the FP32-value / FP64-accumulate kernels
   void launch_spmv_f32x(gf_context &c, const float *val32, const double *x, double *y)
   {
-    if (c.n_tiles == 0 || c.spmv_kernel_kind == 1 || c.n_owned_nodes == 0)
+    if (c.n_tiles == 0 || effective_kind(c, false) == 1 || c.n_owned_nodes == 0)
       {
         launch_spmv_f32(c, val32, x, y);
         return;
