@@ -15,7 +15,8 @@ multigrid and the communicators do not exist in it (GF_ERR_UNSUPPORTED) and stay
 every (dim, degree) takes the generic cell kernels here, every SpMV the LDG kernel.
 
 Default: a subset that runs in about two minutes. GF_EMU_FULL=1: every body of both GPU files that
-needs a serial handle only (about 35 minutes)."""
+needs a serial handle only (about 35 minutes); the files covered: test_gpu_parity,
+test_zz_gpu_high_degree, test_gpu_zz_output, test_gpu_zz_reference_pins."""
 import importlib
 import inspect
 import os
@@ -74,6 +75,10 @@ def _all_cases(module):
 
 
 HD, GP = "test_zz_gpu_high_degree", "test_gpu_parity"
+OUT, PINS = "test_gpu_zz_output", "test_gpu_zz_reference_pins"
+# what each GPU file's own `libs` fixture hands to its tests, out of (capi, solvers, oracle)
+LIBS_SHAPE = {HD: lambda c, s, o: (c, s, o), GP: lambda c, s, o: (c, s, o),
+              OUT: lambda c, s, o: (c, o), PINS: lambda c, s, o: c}
 FAST = [
     # ---- degree >= 3 (generic kernels, FESystem numbering map, pattern with (2p+1)^dim blocks)
     (HD, "test_nonlinear_tangent_and_residual_match_oracle", dict(dim=2, degree=3, reps=[3, 4], numbering="cellwise")),
@@ -116,8 +121,16 @@ FAST = [
     (GP, "test_partitioned_assembly_matches_global_rows", {}),
     (GP, "test_newton_counts_and_watchpoint_match_oracle", dict(dim=2, scenario="FSI3", reps=[6, 1], load=(0.0, -1500.0))),
     (GP, "test_newton_counts_and_watchpoint_match_oracle", dict(dim=3, scenario="PF", reps=[1, 3, 1], load=(1500.0, 0.0, 0.0))),
+    # ---- output path (DataOut patches + Postprocessor) and the reference pins of round 1
+    (OUT, "test_postprocess_matches_oracle", dict(model="nl", dim=3, degree=2, reps=[2, 3, 2], numbering="lexicographic")),
+    (OUT, "test_postprocess_matches_oracle", dict(model="lin", dim=2, degree=1, reps=[5, 7], numbering="cellwise")),
+    (OUT, "test_postprocess_rejects_an_inverted_displaced_cell", {}),
+    (PINS, "test_device_cell_assembly_equals_the_reference_assembly_block", dict(case=1)),
+    (PINS, "test_device_linear_stiffness_and_loading_equal_the_reference_loops", dict(case=2)),
+    (PINS, "test_device_newmark_updates_equal_the_reference_members", dict(case=0)),
+    (PINS, "test_device_theta_scheme_rhs_equals_the_reference_block", dict(case=1)),
 ]
-CASES = (_all_cases(HD) + _all_cases(GP)) if FULL else FAST
+CASES = (_all_cases(HD) + _all_cases(GP) + _all_cases(OUT) + _all_cases(PINS)) if FULL else FAST
 
 
 def _id(case):
@@ -132,7 +145,23 @@ def test_gpu_test_body_on_the_emulated_library(emu_libs, monkeypatch, case):
     kwargs = dict(params)
     if "monkeypatch" in inspect.signature(body).parameters:
         kwargs["monkeypatch"] = monkeypatch
-    body(emu_libs, **kwargs)
+    body(LIBS_SHAPE[module](*emu_libs), **kwargs)
+
+
+def test_cpp_host_driver_on_the_emulated_library(emu_lib_path, native_libs, tmp_path, monkeypatch):
+    """The C++ drop-in driver (elasticity_2d: Parameters / Time / Adapter / Solid / ElastoDynamics
+    mirrors) end to end without a GPU: the emulation build is LD_PRELOADed under the executable,
+    so its gf_* calls resolve there. Bodies of the GPU tests: the reference's shipped
+    parameters.prm (linear, degree 3, Direct -> band Cholesky) and the neo-Hookean FSI3 run, both
+    against the oracle's watch point."""
+    monkeypatch.setenv("LD_PRELOAD", emu_lib_path)
+    monkeypatch.setenv("GF_DIRECT_SOLVER", "auto")
+    exes = native_libs.build_elasticity()
+    a, b = tmp_path / "shipped", tmp_path / "nonlinear"
+    a.mkdir()
+    b.mkdir()
+    _body(HD, "test_shipped_parameter_file_runs_unchanged_through_the_cpp_driver")(a, native_libs)
+    _body("test_host_driver", "test_coupled_nonlinear_run_matches_oracle_watchpoint")(exes, b, native_libs)
 
 
 def test_hardware_only_parts_are_refused_not_faked(emu_libs):
