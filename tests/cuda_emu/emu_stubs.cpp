@@ -1,7 +1,8 @@
 // TEST INFRASTRUCTURE ONLY. The CPU emulation build of the library (make_emu_library.py) covers
-// the serial handle with the assembled operator and the block-Jacobi CG; the parts that need the
-// hardware (TMA / mbarrier kernels of the matrix-free operator, the multigrid smoothers' single
-// launch solver, NVLink peer windows) answer GF_ERR_UNSUPPORTED here.
+// the serial handle; what needs the hardware is stood in for here: the single-launch coarsest-level
+// solver (a grid-wide spin barrier: blocks run one after another in the emulation) reports "not
+// applicable", so the multigrid takes its multi-launch fallback, and everything that needs a
+// communicator (NVLink peer windows, NCCL) answers GF_ERR_UNSUPPORTED.
 #include "gf_context.h"
 #include "reduce.cuh"
 
@@ -14,16 +15,6 @@ namespace gf
       throw Error{GF_ERR_UNSUPPORTED, std::string(what) + " does not exist in the CPU emulation"};
     }
   } // namespace
-  void   mf_setup(gf_context &, const double *, const double *) { no("the matrix-free operator"); }
-  void   mf_apply(gf_context &, const double *, double *, double *) { no("the matrix-free operator"); }
-  int    mf_dot_partials(const gf_context &) { return 1; }
-  double mf_bytes(const gf_context &) { return 0.0; }
-  void   mg_attach(gf_context &, gf_context &, const int32_t *) { no("the multigrid hierarchy"); }
-  void   mg_update_operators(gf_context &, const double *) {}
-  void   mg_vcycle(gf_context &, const double *, double *) { no("the multigrid V-cycle"); }
-  void   mg_refresh_f32(gf_context &) {}
-  void   mg_refresh_f32_level(gf_context &) {}
-  bool   mg_active(const gf_context &) { return false; }
   bool   coarse_solve_single_launch(gf_context &, const double *, const double *, double *, int, double)
   {
     return false;

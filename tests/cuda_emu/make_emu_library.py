@@ -7,8 +7,8 @@ rewrites g++ cannot do without:
     extern __shared__ T name[];                   ->  T *name = reinterpret_cast<T *>(gf_emu::dynamic_smem());
 Hardware-only parts are compiled out by the sources' own `#ifndef GF_CUDA_EMULATION` (tuned
 neo-Hookean kernels -> generic kernels, TMA SpMV -> LDG SpMV) or replaced by emu_stubs.cpp
-(matrix-free operator, multigrid, communicators: GF_ERR_UNSUPPORTED). The product never loads
-this library; it has no CPU path."""
+(single-launch coarsest-level solver -> multi-launch fallback; communicators:
+GF_ERR_UNSUPPORTED). The product never loads this library; it has no CPU path."""
 import os
 import re
 import subprocess
@@ -17,11 +17,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "dealii_adapter_b200", "csrc")
-OUT_DIR = os.path.join(HERE, "_build")
+OUT_DIR = os.environ.get("GF_EMU_BUILD_DIR", os.path.join(HERE, "_build"))
 LIB = os.path.join(OUT_DIR, "libgraftfem_emu.so")
 SOURCES = ["api.cu", "pattern.cu", "scatter.cu", "assemble_nl.cu", "assemble_lin.cu", "cg.cu",
            "reduce.cu", "vector_ops.cu", "constraints.cu", "direct.cu", "postprocess.cu",
-           "fe_tables.cu", "spmv.cu", "operator.cu"]
+           "fe_tables.cu", "spmv.cu", "operator.cu", "multigrid.cu", "matfree.cu"]
 
 
 def _matching(text, i, open_ch, close_ch):

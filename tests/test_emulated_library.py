@@ -10,13 +10,15 @@ kernels were checked in isolation (tests/test_cuda_emulation.py); this file also
 between the C-ABI and the kernels - numbering and sparsity pattern, scatter map, reductions, CG,
 Newton / theta-scheme entry points, export, output - before the first run on hardware.
 What it is NOT: a product path. Nothing outside tests/ can load the emulation build; the tuned
-kernels (TMA SpMV, the mbarrier-pipelined neo-Hookean kernels), the matrix-free operator, the
-multigrid and the communicators do not exist in it (GF_ERR_UNSUPPORTED) and stay GPU-tested only:
-every (dim, degree) takes the generic cell kernels here, every SpMV the LDG kernel.
+kernels (TMA SpMV, the mbarrier-pipelined neo-Hookean kernels), the single-launch coarsest-level
+solver and the communicators do not exist in it and stay GPU-tested only: every (dim, degree)
+takes the generic cell kernels here, every SpMV the LDG kernel, the coarsest multigrid level its
+multi-launch fallback.
 
 Default: a subset that runs in about two minutes. GF_EMU_FULL=1: every body of both GPU files that
-needs a serial handle only (about 35 minutes); the files covered: test_gpu_parity,
-test_zz_gpu_high_degree, test_gpu_zz_output, test_gpu_zz_reference_pins."""
+needs a serial handle only (about 90 minutes); the files covered: test_gpu_parity,
+test_zz_gpu_high_degree, test_gpu_zz_output, test_gpu_zz_reference_pins, test_gpu_multigrid,
+test_gpu_matfree - and bench.py itself."""
 import importlib
 import inspect
 import os
@@ -76,9 +78,16 @@ def _all_cases(module):
 
 HD, GP = "test_zz_gpu_high_degree", "test_gpu_parity"
 OUT, PINS = "test_gpu_zz_output", "test_gpu_zz_reference_pins"
+MG, MF = "test_gpu_multigrid", "test_gpu_matfree"
 # what each GPU file's own `libs` fixture hands to its tests, out of (capi, solvers, oracle)
 LIBS_SHAPE = {HD: lambda c, s, o: (c, s, o), GP: lambda c, s, o: (c, s, o),
-              OUT: lambda c, s, o: (c, o), PINS: lambda c, s, o: c}
+              OUT: lambda c, s, o: (c, o), PINS: lambda c, s, o: c,
+              MG: lambda c, s, o: (c, s, _multigrid(), o), MF: lambda c, s, o: (c, s, _multigrid(), o)}
+
+
+def _multigrid():
+    from dealii_adapter_b200 import multigrid
+    return multigrid
 FAST = [
     # ---- degree >= 3 (generic kernels, FESystem numbering map, pattern with (2p+1)^dim blocks)
     (HD, "test_nonlinear_tangent_and_residual_match_oracle", dict(dim=2, degree=3, reps=[3, 4], numbering="cellwise")),
@@ -129,8 +138,19 @@ FAST = [
     (PINS, "test_device_linear_stiffness_and_loading_equal_the_reference_loops", dict(case=2)),
     (PINS, "test_device_newmark_updates_equal_the_reference_members", dict(case=0)),
     (PINS, "test_device_theta_scheme_rhs_equals_the_reference_block", dict(case=1)),
+    # ---- geometric multigrid (transfer, Chebyshev smoothers, level operators; the coarsest level
+    #      by its multi-launch fallback) and the matrix-free tangent
+    (MG, "test_vcycle_is_symmetric_positive_definite", dict(dim=3, degree=2, reps=[4, 8, 4], numbering="lexicographic")),
+    (MG, "test_vcycle_is_symmetric_positive_definite", dict(dim=2, degree=2, reps=[8, 16], numbering="component_wise")),
+    (MG, "test_vcycle_approximates_the_inverse", {}),
+    (MG, "test_attach_rejects_bad_hierarchies", {}),
+    (MG, "test_multigrid_linear_model_matches_block_jacobi", {}),
+    (MF, "test_matrix_free_operator_matches_assembled_tangent", dict(degree=2, reps=[2, 5, 3], numbering="component_wise")),
+    (MF, "test_matrix_free_operator_matches_assembled_tangent", dict(degree=1, reps=[4, 5, 3], numbering="lexicographic")),
+    (MF, "test_matrix_free_rejected_where_unsupported", {}),
 ]
-CASES = (_all_cases(HD) + _all_cases(GP) + _all_cases(OUT) + _all_cases(PINS)) if FULL else FAST
+CASES = (_all_cases(HD) + _all_cases(GP) + _all_cases(OUT) + _all_cases(PINS) + _all_cases(MG) +
+         _all_cases(MF)) if FULL else FAST
 
 
 def _id(case):
@@ -164,28 +184,63 @@ def test_cpp_host_driver_on_the_emulated_library(emu_lib_path, native_libs, tmp_
     _body("test_host_driver", "test_coupled_nonlinear_run_matches_oracle_watchpoint")(exes, b, native_libs)
 
 
+def test_bench_py_end_to_end_on_the_emulated_library(emu_libs, monkeypatch):
+    """bench.py itself - Hierarchy, Solid, the timed regions, the stand-alone SpMV timing after a
+    deferred tangent, the cfg4 strong-scaling part (and, with GF_EMU_FULL=1, every variant) -
+    driving the REAL library source on a tiny flap: the plumbing of the round-end driver run,
+    executed. The numbers mean nothing here; that there is exactly one well-formed line does."""
+    import io
+    import json
+    import torch
+    bench = importlib.import_module("bench")
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(bench, "CFG4_REPS", (2, 4, 2))
+    monkeypatch.setattr(bench, "CPU_SAMPLE_REPS", {"reference": (1, 3, 1), "baseline": (1, 3, 1)})
+    monkeypatch.setattr(bench.ClockSampler, "start", lambda self: None)
+    monkeypatch.setattr(bench.ClockSampler, "stop", lambda self: {"sm_mhz": None, "sm_max_mhz": None,
+                                                                 "reasons": [], "samples": 0})
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "GF_PROFILE_RUN"):
+        monkeypatch.delenv(k, raising=False)
+    argv = ["bench.py", "--reps", "2,2,2", "--steps", "1"]
+    if not FULL:
+        argv += ["--no-variants", "--no-cpu-baseline"]
+    monkeypatch.setattr(sys, "argv", argv)
+    r, w = os.pipe()
+    saved1 = os.dup(1)
+    os.dup2(w, 1)
+    try:
+        bench.main()
+    finally:
+        os.dup2(saved1, 1)
+        os.close(saved1)
+        os.close(w)
+        if bench._REAL_STDOUT is not None:
+            os.close(bench._REAL_STDOUT)
+            bench._REAL_STDOUT = None
+    with os.fdopen(r) as f:
+        lines = [x for x in f.read().split("\n") if x.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["metric"] == "newton_step_dofs_per_s" and line["value"] > 0 and line["e2e"]["value"] > 0
+    assert line["config"]["multigrid_levels"] == [[2, 2, 2], [1, 1, 1]]
+    assert line["config"]["newton_solves_in_timed_region"] >= 3
+    assert line["gpu_launches"] > 100 and line["roofline"]["launches"] > 10
+    assert 0 < line["roofline"]["share_of_step"] < 1
+    assert "error" not in line["strong_scaling"] and line["strong_scaling"]["cg_iterations"][0] > 0
+    assert "close_error" not in line and "side_measurements" not in line
+    if FULL:
+        assert "error" not in line["variants"]
+        assert set(line["variants"]) >= {"matrix_free_operator", "vcycle_fp32_matrices",
+                                         "vcycle_all_fp32_operator", "direct_solver_stand_in"}
+
+
 def test_hardware_only_parts_are_refused_not_faked(emu_libs):
-    """The emulation build must not pretend: multigrid, matrix-free operator and communicators
-    answer GF_ERR_UNSUPPORTED, and the binding is restored to the product library afterwards."""
+    """The emulation build must not pretend: communicators (NVLink peer windows / NCCL) do not
+    exist in it, and a partitioned handle cannot be created."""
     capi, solvers, orc = emu_libs
-    import numpy as np
-    from helpers import nl_params
-    from dealii_adapter_b200.problem import make_problem
-    prob = make_problem(nl_params(poly_degree=2), 3, reps=[2, 2, 2])
-    h = capi.Handle(prob)
-    with pytest.raises(capi.GraftError) as e:
-        h.set_option(capi.OPT_OPERATOR, 1)
-        h.nl_newton_assemble()
-    assert e.value.code == capi.GF_ERR_UNSUPPORTED
-    h.set_option(capi.OPT_OPERATOR, 0)
-    coarse = capi.Handle(make_problem(nl_params(poly_degree=2), 3, reps=[1, 1, 1]))
-    with pytest.raises(capi.GraftError) as e:
-        h.mg_attach(coarse, np.arange(8, dtype=np.int64).reshape(1, 8))
-    assert e.value.code == capi.GF_ERR_UNSUPPORTED
     with pytest.raises(Exception):
         capi.Comm.unique_id()
-    coarse.close()
-    h.close()
 
 
 def test_binding_is_back_on_the_product_library():
