@@ -92,6 +92,14 @@ def build(force=False):
     gen.append(os.path.join(HERE, "emu_stubs.cpp"))
     flags = ["-O1", "-g", "-std=c++20", "-fPIC", "-pthread", "-DGF_CUDA_EMULATION",
              "-Wno-unknown-pragmas", "-I", HERE, "-I", CSRC, "-I", os.path.join(ROOT, "include")]
+    # GF_EMU_SANITIZE=address: "device" buffers are plain heap blocks, so AddressSanitizer sees
+    # every out-of-bounds access of a kernel (run python with LD_PRELOAD=$(g++ -print-file-name=
+    # libasan.so) ASAN_OPTIONS=detect_leaks=0)
+    san = os.environ.get("GF_EMU_SANITIZE")
+    link = []
+    if san:
+        flags += ["-fsanitize=" + san, "-fno-omit-frame-pointer"]
+        link = ["-fsanitize=" + san]
     objs, procs = [], []
     for g in gen:
         obj = os.path.join(OUT_DIR, "gen", os.path.basename(g)[:-4] + ".o")
@@ -106,7 +114,7 @@ def build(force=False):
             sys.stderr.write("---- %s\n%s\n" % (g, log[-6000:]))
     if failed:
         raise RuntimeError("emulation build failed")
-    subprocess.check_call(["g++", "-shared", "-pthread", "-o", LIB] + objs)
+    subprocess.check_call(["g++", "-shared", "-pthread", "-o", LIB] + link + objs)
     return LIB
 
 
