@@ -78,11 +78,15 @@ def _all_cases(module):
 
 HD, GP = "test_zz_gpu_high_degree", "test_gpu_parity"
 OUT, PINS = "test_gpu_zz_output", "test_gpu_zz_reference_pins"
-MG, MF = "test_gpu_multigrid", "test_gpu_matfree"
+MG, MF, F32 = "test_gpu_multigrid", "test_gpu_matfree", "test_gpu_zz_mg_f32"
 # what each GPU file's own `libs` fixture hands to its tests, out of (capi, solvers, oracle)
 LIBS_SHAPE = {HD: lambda c, s, o: (c, s, o), GP: lambda c, s, o: (c, s, o),
               OUT: lambda c, s, o: (c, o), PINS: lambda c, s, o: c,
-              MG: lambda c, s, o: (c, s, _multigrid(), o), MF: lambda c, s, o: (c, s, _multigrid(), o)}
+              MG: lambda c, s, o: (c, s, _multigrid(), o), MF: lambda c, s, o: (c, s, _multigrid(), o),
+              F32: lambda c, s, o: (c, s, _multigrid())}
+# the all-FP32 operator (x staged and accumulated in FP32) exists as a TMA kernel only
+HARDWARE_ONLY = {"test_all_fp32_operator_is_a_single_precision_spmv",
+                 "test_all_fp32_vcycle_keeps_newton_counts_and_displacements"}
 
 
 def _multigrid():
@@ -148,9 +152,13 @@ FAST = [
     (MF, "test_matrix_free_operator_matches_assembled_tangent", dict(degree=2, reps=[2, 5, 3], numbering="component_wise")),
     (MF, "test_matrix_free_operator_matches_assembled_tangent", dict(degree=1, reps=[4, 5, 3], numbering="lexicographic")),
     (MF, "test_matrix_free_rejected_where_unsupported", {}),
+    # ---- FP32 copies of the level operators inside the V-cycle (GF_OPT_MG_MATRIX_PRECISION = 1)
+    (F32, "test_f32_operator_copy_matches_fp64_to_single_precision", dict(dim=3, degree=2, reps=[4, 8, 4], numbering="lexicographic")),
+    (F32, "test_f32_vcycle_is_symmetric_positive_definite_and_close_to_fp64", {}),
 ]
-CASES = (_all_cases(HD) + _all_cases(GP) + _all_cases(OUT) + _all_cases(PINS) + _all_cases(MG) +
-         _all_cases(MF)) if FULL else FAST
+CASES = [c for c in (_all_cases(HD) + _all_cases(GP) + _all_cases(OUT) + _all_cases(PINS) +
+                     _all_cases(MG) + _all_cases(MF) + _all_cases(F32))
+         if c[1] not in HARDWARE_ONLY] if FULL else FAST
 
 
 def _id(case):
