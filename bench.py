@@ -548,6 +548,25 @@ def main():
                      "bracketed with CUDA events (adds launch gaps to the small kernels)" % N_SUB),
             "variants": {},
         }
+        # second roofline: the cell kernel K1 against the MEASURED FP64 (DFMA) peak. Algorithmic
+        # flops = what the reference's j <= i loop needs after the pre-contraction T_a = B_a^T D:
+        # lower node-block pairs x (27 + 3) FMA x q-points; duration = average K1
+        # launch of the diagnostic pass (events around every launch)
+        fp64_path = os.path.join(ROOT, "profiles", "fp64_peak.json")
+        n_k1 = int(prof_full.get("assemble_cells_launches", 0))
+        if prob.dim == 3 and n_k1 > 0 and os.path.exists(fp64_path):
+            npc, nq = (prob.degree + 1) ** 3, (prob.degree + 2) ** 3
+            flops = 2.0 * 30.0 * (npc * (npc + 1) // 2) * nq * h.n_cells
+            k1_ms = prof_full["assemble_cells_ms"] / n_k1
+            dfma = float(json.load(open(fp64_path))["dfma_tflops"])
+            line["roofline_assembly"] = {
+                "bound": "fp64", "kernel": "nl_cells_kernel<3, %d> (K1: element tangents + residuals)"
+                                           % prob.degree,
+                "achieved": flops / (k1_ms * 1e-3) / 1e12 if k1_ms else None, "peak": dfma,
+                "unit": "TFLOP/s", "frac": (flops / (k1_ms * 1e-3) / 1e12 / dfma) if k1_ms else None,
+                "peak_source": "measured DFMA peak (profiles/fp64_peak.json, tools/fp64_peak.cu)",
+                "flops_per_launch": flops, "avg_launch_ms": k1_ms, "launches": n_k1,
+                "cells_per_launch": int(h.n_cells)}
         if comm_info:
             line["comm"] = comm_info
     # ---- from here on the main line exists; everything below is a side measurement that must never

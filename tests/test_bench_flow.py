@@ -166,6 +166,7 @@ def test_one_line_with_the_contract_keys(bench, monkeypatch):
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["newton_solves"] == 6
     assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
+    assert line["roofline_assembly"]["bound"] == "fp64" and line["roofline_assembly"]["frac"] > 0
     assert set(line["variants"]) >= {"matrix_free_operator", "vcycle_fp32_matrices",
                                      "vcycle_all_fp32_operator", "direct_solver_stand_in"}
     assert line["strong_scaling"]["scaling"] == "strong" and line["strong_scaling"]["value"] > 0
