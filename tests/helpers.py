@@ -88,27 +88,34 @@ def distort_mesh(problem, amp=0.12, seed=0):
     return problem
 
 
-def hanging_node_problem(params, degree):
-    """A 2D mesh WITH hanging nodes, which the structured stand-in cannot produce: the domain
-    [0,2] x [0,1], left half one cell, right half refined once (4 cells). The nodes of the fine
-    cells on the edge x = 1 that the coarse cell does not own hang; their constraint lines are the
-    coarse edge's 1D shape functions at their positions (what
+def hanging_node_problem(params, degree, dim=2):
+    """A mesh WITH hanging nodes, which the structured stand-in cannot produce: the domain
+    [0,2] x [0,1] (x [0,1]), left half one cell, right half refined once (2^dim cells). The nodes
+    of the fine cells on the face x = 1 that the coarse cell does not own hang; their constraint
+    lines are the coarse face's shape functions at their positions (what
     DoFTools::make_hanging_node_constraints produces, linear_elasticity.cc:196-207).
-    Roles: x = 0 clamped, y = 1 and x = 2 interface, y = 0 free. degree 1 or 2 (equidistant nodes).
-    Returns a Problem whose `extra["constraint_lines"]` = (dof, ptr, master, weight)."""
+    Roles: x = 0 clamped, y = 1 and x = 2 interface, the rest free. degree 1 or 2 (equidistant
+    nodes). Returns a Problem whose `extra["constraint_lines"]` = (dof, ptr, master, weight)."""
+    import itertools
     from types import SimpleNamespace
     import ref_formulas as rf
     from dealii_adapter_b200.problem import MODEL_LINEAR, MODEL_NEO_HOOKEAN, Problem
-    dim, p = 2, degree
-    assert p in (1, 2)
-    boxes = [((0.0, 0.0), (1.0, 1.0))] + [((1.0 + 0.5 * i, 0.5 * j), (1.5 + 0.5 * i, 0.5 + 0.5 * j))
-                                            for j in range(2) for i in range(2)]
+    p = degree
+    assert p in (1, 2) and dim in (2, 3)
+    boxes = [((0.0,) * dim, (1.0,) * dim)]
+    fine_index = {}
+    for idx in itertools.product(range(2), repeat=dim - 1):          # (k,) j slowest .. x fastest
+        for i in range(2):
+            ijk = (i,) + tuple(reversed(idx))                        # (i, j[, k])
+            fine_index[ijk] = len(boxes)
+            lo = (1.0 + 0.5 * ijk[0],) + tuple(0.5 * t for t in ijk[1:])
+            boxes.append((lo, tuple(x + 0.5 for x in lo)))
     nodes = rf.hierarchical_nodes(dim, p)
     s2c = rf.system_to_node_component(dim, p)
     ids, coords, cell_dofs, cell_vertices = {}, [], [], []
     for lo, hi in boxes:
-        for v in range(4):
-            cell_vertices += [hi[0] if v & 1 else lo[0], hi[1] if v & 2 else lo[1]]
+        for v in range(1 << dim):
+            cell_vertices += [hi[d] if (v >> d) & 1 else lo[d] for d in range(dim)]
         row = []
         for a, c in s2c:
             x = tuple(round(lo[d] + (hi[d] - lo[d]) * nodes[a][d] / p, 12) for d in range(dim))
@@ -121,29 +128,35 @@ def hanging_node_problem(params, degree):
     n_dofs = n_nodes * dim
     coords = np.array(coords)
     support_points = np.repeat(coords, dim, axis=0)
-    # hanging nodes: on x = 1, 0 < y < 1, not a node of the coarse cell
-    coarse_y = np.linspace(0.0, 1.0, p + 1)
+    # hanging nodes: on the face x = 1 and not a node of the coarse cell
+    coarse_1d = np.linspace(0.0, 1.0, p + 1)
+    on_grid = lambda t: bool(np.any(np.abs(coarse_1d - t) < 1e-12))
     dof, ptr, master, weight = [], [0], [], []
     for x, n in ids.items():
-        if abs(x[0] - 1.0) < 1e-12 and not np.any(np.abs(coarse_y - x[1]) < 1e-12):
-            w = rf.lagrange_1d(p, np.array([x[1]]))[0][0]           # coarse edge basis at y
+        if abs(x[0] - 1.0) < 1e-12 and not all(on_grid(t) for t in x[1:]):
+            w1 = [rf.lagrange_1d(p, np.array([t]))[0][0] for t in x[1:]]   # coarse face basis at x
             for c in range(dim):
                 dof.append(n * dim + c)
-                for k, yk in enumerate(coarse_y):
-                    if abs(w[k]) > 1e-14:
-                        master.append(ids[(1.0, round(float(yk), 12))] * dim + c)
-                        weight.append(float(w[k]))
+                for ks in itertools.product(range(p + 1), repeat=dim - 1):
+                    w = float(np.prod([w1[d][k] for d, k in enumerate(ks)]))
+                    if abs(w) > 1e-14:
+                        m = (1.0,) + tuple(round(float(coarse_1d[k]), 12) for k in ks)
+                        master.append(ids[m] * dim + c)
+                        weight.append(w)
                 ptr.append(len(master))
     constrained = np.zeros(n_dofs, dtype=np.uint8)
     constrained[np.repeat(np.abs(coords[:, 0]) < 1e-12, dim)] = 1
-    # interface faces: y = 1 (face 3) of cells 0, 3, 4 and x = 2 (face 1) of cells 2, 4
-    iface = [(0, 3), (3, 3), (4, 3), (2, 1), (4, 1)]
+    # interface faces: y = 1 (face 3) of the coarse cell and of the fine cells with j = 1, x = 2
+    # (face 1) of the fine cells with i = 1
+    iface = [(0, 3)] + [(c, 3) for ijk, c in fine_index.items() if ijk[1] == 1] + \
+        [(c, 1) for ijk, c in fine_index.items() if ijk[0] == 1]
+    iface.sort()
     on_if = (np.abs(coords[:, 1] - 1.0) < 1e-12) | (np.abs(coords[:, 0] - 2.0) < 1e-12)
     if_nodes = np.nonzero(on_if)[0]
     iface_dofs = np.stack([if_nodes * dim + c for c in range(dim)]).astype(np.int32)
     mesh = SimpleNamespace(dim=dim, degree=p, n_cells=len(boxes), n_dofs=n_dofs, n_nodes=n_nodes,
-                           dofs_per_cell=dim * (p + 1) ** dim, reps=[2, 1], p0=[0.0, 0.0],
-                           p1=[2.0, 1.0], numbering="custom",
+                           dofs_per_cell=dim * (p + 1) ** dim, reps=[2] + [1] * (dim - 1),
+                           p0=[0.0] * dim, p1=[2.0] + [1.0] * (dim - 1), numbering="custom",
                            cell_dofs=np.array(cell_dofs, dtype=np.int32),
                            cell_vertices=np.array(cell_vertices, dtype=np.float64),
                            support_points=support_points)

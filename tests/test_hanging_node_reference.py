@@ -37,12 +37,13 @@ def test_references_reproduce_the_oracle_without_constraint_lines(orc):
     assert rel_err(ref, o.get(orc.NL_TOTAL_DISPLACEMENT)) < 1e-8
 
 
-@pytest.mark.parametrize("degree", [1, 2])
-def test_hanging_node_solution_is_conforming(orc, degree):
-    prob = hanging_node_problem(lin_params(poly_degree=degree, type_lin="Direct"), degree)
+@pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (3, 1), (3, 2)])
+def test_hanging_node_solution_is_conforming(orc, dim, degree):
+    prob = hanging_node_problem(lin_params(poly_degree=degree, type_lin="Direct"), degree, dim)
     dof, ptr, master, weight = prob.extra["constraint_lines"]
-    assert len(dof) == 2 * degree                        # degree hanging nodes, two components
-    bufs = [np.tile([0.0, -200.0], prob.n_iface_nodes)] * 2
+    # fine nodes of the face x = 1 minus the coarse ones, dim components each
+    assert len(dof) == dim * ((2 * degree + 1) ** (dim - 1) - (degree + 1) ** (dim - 1))
+    bufs = [np.tile([0.0, -200.0, 50.0][:dim], prob.n_iface_nodes)] * 2
     d = reference_linear_steps(orc, prob, bufs)[-1]
     Cm = constraint_matrix(prob)
     masters_only = d.copy()
@@ -50,8 +51,8 @@ def test_hanging_node_solution_is_conforming(orc, degree):
     assert np.abs(Cm @ masters_only - d).max() <= 1e-15 * np.abs(d).max()   # u = C u_masters
     assert np.abs(d[dof]).max() > 0
     pn = nl_params(poly_degree=degree, type_lin="Direct")
-    prob = hanging_node_problem(pn, degree)
-    u = reference_nonlinear_step(orc, prob, np.tile([0.0, -1500.0], prob.n_iface_nodes))
+    prob = hanging_node_problem(pn, degree, dim)
+    u = reference_nonlinear_step(orc, prob, np.tile([0.0, -1500.0, 300.0][:dim], prob.n_iface_nodes))
     m = u.copy()
     m[dof] = 0.0
     assert np.abs(Cm @ m - u).max() <= 1e-15 * np.abs(u).max() and np.abs(u[dof]).max() > 0

@@ -583,18 +583,18 @@ def test_partitioned_run_at_degree_3_reproduces_the_single_rank_run(native_libs,
 # solver. Mesh: tests/helpers.py::hanging_node_problem; reference: condensation by definition
 # (helpers.reference_*; tests/test_hanging_node_reference.py checks it on the CPU).
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("degree", [1, 2])
+@pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (3, 1), (3, 2)])
 @first_run
-def test_hanging_nodes_linear_steps(libs, degree):
+def test_hanging_nodes_linear_steps(libs, degree, dim=2):
     from helpers import constraint_matrix, hanging_node_problem, reference_linear_steps
     capi, solvers, orc = libs
     p = lin_params(poly_degree=degree, type_lin="CG", body_force=(0.0, -9.81, 0.0),
                    max_iterations_lin=20.0)
-    prob = hanging_node_problem(p, degree)
+    prob = hanging_node_problem(p, degree, dim)
     n = prob.n_iface_nodes
-    bufs = [np.tile([40.0 * (k + 1), -200.0], n) for k in range(3)]
+    bufs = [np.tile([40.0 * (k + 1), -200.0, 30.0][:dim], n) for k in range(3)]
     ref = reference_linear_steps(orc, prob, bufs)
-    part = solvers.FakeParticipant(2, 3, p.delta_t, lambda t, it: bufs[min(2, int(round(t / p.delta_t)) - 1)])
+    part = solvers.FakeParticipant(dim, 3, p.delta_t, lambda t, it: bufs[min(2, int(round(t / p.delta_t)) - 1)])
     ed = solvers.ElastoDynamics(prob, part)
     ed.run()
     d = ed.handle.get_vector(capi.LIN_DISPLACEMENT)
@@ -608,16 +608,16 @@ def test_hanging_nodes_linear_steps(libs, degree):
     ed.handle.close()
 
 
-@pytest.mark.parametrize("degree", [1, 2])
+@pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (3, 1), (3, 2)])
 @first_run
-def test_hanging_nodes_nonlinear_step_and_refusals(libs, degree):
+def test_hanging_nodes_nonlinear_step_and_refusals(libs, degree, dim=2):
     from helpers import constraint_matrix, hanging_node_problem, reference_nonlinear_step
     capi, solvers, orc = libs
     p = nl_params(poly_degree=degree, type_lin="Direct", scenario="PF", delta_t=0.01)
-    prob = hanging_node_problem(p, degree)
-    buf = np.tile([0.0, -1500.0], prob.n_iface_nodes)
+    prob = hanging_node_problem(p, degree, dim)
+    buf = np.tile([0.0, -1500.0, 300.0][:dim], prob.n_iface_nodes)
     ref = reference_nonlinear_step(orc, prob, buf)
-    part = solvers.FakeParticipant(2, 1, p.delta_t, lambda t, it: buf)
+    part = solvers.FakeParticipant(dim, 1, p.delta_t, lambda t, it: buf)
     solid = solvers.Solid(prob, part)
     solid.handle.set_option(capi.OPT_DIRECT_SOLVER, 0)   # auto: lines -> the CG stand-in runs
     solid.run()
