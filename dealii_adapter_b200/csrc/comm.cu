@@ -22,6 +22,10 @@
 //   NCCL (fallback, GF_COMM_P2P=0 or if IPC mapping fails on any rank): pack + grouped
 //       ncclSend/ncclRecv + unpack, ncclAllReduce.
 #include <dlfcn.h>
+#ifdef GF_CUDA_EMULATION
+#include <sched.h>
+#include <time.h>
+#endif
 
 #include <cstdlib>
 #include <cstring>
@@ -135,6 +139,7 @@ namespace gf
   {
     constexpr int PUSH_BLOCKS = 8, PUSH_THREADS = 512;
 
+#ifndef GF_CUDA_EMULATION
     __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
     {
       asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -151,6 +156,23 @@ namespace gf
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       return t;
     }
+#else // tests/cuda_emu: ranks are processes, the windows shared-memory files
+    inline void st_release_sys(unsigned long long *p, unsigned long long v)
+    {
+      __atomic_store_n(p, v, __ATOMIC_RELEASE);
+    }
+    inline unsigned long long ld_acquire_sys(const unsigned long long *p)
+    {
+      return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+    }
+    inline unsigned long long global_timer_ns()
+    {
+      timespec ts;
+      clock_gettime(CLOCK_MONOTONIC, &ts);
+      return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+    }
+    inline void __nanosleep(unsigned) { sched_yield(); }
+#endif
     // spin until *flag >= epoch; a peer that never arrives sets *err instead of hanging the GPU
     __device__ __forceinline__ void wait_flag(const unsigned long long *flag,
                                               unsigned long long epoch, int *err,

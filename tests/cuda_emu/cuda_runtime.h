@@ -9,7 +9,11 @@
 //             so that an unset double reads as NaN and an unset index as -1), streams and events do
 //             nothing but keep time
 #pragma once
+#include <fcntl.h>
 #include <math.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -17,6 +21,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <string>
+#include <type_traits>
 #include <memory>
 #include <vector>
 
@@ -162,9 +169,10 @@ namespace gf_emu
   }
 
   // kernel<<<grid, block, smem_bytes>>>(args...) -> launch(grid, block, smem_bytes, [&] { kernel(args...); })
-  inline void launch(unsigned grid, unsigned block, size_t smem_bytes,
+  inline void launch(dim3 grid3, unsigned block, size_t smem_bytes,
                      const std::function<void()> &kernel)
   {
+    const unsigned grid = grid3.x * grid3.y * grid3.z; // blocks run one after another, x fastest
     ++n_launches;
     const unsigned      n_warps = (block + 31) / 32;
     std::vector<Fiber>  fibers(block);
@@ -174,9 +182,9 @@ namespace gf_emu
     for (unsigned b = 0; b < grid; ++b)
       {
         std::fill(smem.begin(), smem.end(), nan("")); // uninitialised shared memory is not zero
-        blk.block_idx = {b, 0, 0};
+        blk.block_idx = {b % grid3.x, (b / grid3.x) % grid3.y, b / (grid3.x * grid3.y)};
         blk.block_dim = dim3(block);
-        blk.grid_dim  = dim3(grid);
+        blk.grid_dim  = grid3;
         blk.bar       = Bar{block, 0, 0};
         blk.smem      = reinterpret_cast<unsigned char *>(smem.data());
         for (unsigned w = 0; w < n_warps; ++w)
@@ -222,7 +230,10 @@ namespace gf_emu
   inline void launch4(G grid, B block, S smem_bytes, St /*stream*/,
                       const std::function<void()> &kernel)
   {
-    launch(unsigned(grid), unsigned(block), size_t(smem_bytes), kernel);
+    if constexpr (std::is_same_v<G, dim3>)
+      launch(grid, unsigned(block), size_t(smem_bytes), kernel);
+    else
+      launch(dim3(unsigned(grid)), unsigned(block), size_t(smem_bytes), kernel);
   }
 } // namespace gf_emu
 
@@ -252,6 +263,10 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask)
 }
 inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v)
 {
   return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST);
@@ -326,8 +341,61 @@ inline cudaError_t cudaMemGetInfo(size_t *free_b, size_t *total_b)
   *total_b = size_t(8) << 30;
   return cudaSuccess;
 }
+// Blocks of >= 1 MiB live in named shared-memory files, so that a peer rank - another PROCESS - can
+// map them (cudaIpcGetMemHandle / cudaIpcOpenMemHandle: the peer windows of comm.cu)
+struct cudaIpcMemHandle_t
+{
+  char reserved[64];
+};
+constexpr unsigned cudaIpcMemLazyEnablePeerAccess = 1;
+constexpr unsigned cudaHostAllocMapped            = 2;
+namespace gf_emu
+{
+  struct Shared
+  {
+    std::string name;
+    size_t      bytes;
+    bool        owner;
+  };
+  inline std::map<void *, Shared> &shared_blocks()
+  {
+    static std::map<void *, Shared> m;
+    return m;
+  }
+  inline void *map_shared(const std::string &name, size_t n, bool create)
+  {
+    const int fd = shm_open(name.c_str(), create ? (O_CREAT | O_EXCL | O_RDWR) : O_RDWR, 0600);
+    if (fd < 0)
+      return nullptr;
+    if (create && ftruncate(fd, off_t(n)) != 0)
+      {
+        close(fd);
+        return nullptr;
+      }
+    if (!create)
+      {
+        struct stat st;
+        fstat(fd, &st);
+        n = size_t(st.st_size);
+      }
+    void *p = mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED)
+      return nullptr;
+    shared_blocks()[p] = Shared{name, n, create};
+    return p;
+  }
+} // namespace gf_emu
 inline cudaError_t cudaMalloc(void **p, size_t n)
 {
+  if (n >= (size_t(1) << 20))
+    {
+      static int  counter = 0;
+      const std::string name =
+        "/gf_emu_" + std::to_string(long(getpid())) + "_" + std::to_string(counter++);
+      *p = gf_emu::map_shared(name, n, true); // zero pages; large blocks are memset by their owners
+      return *p ? cudaSuccess : cudaErrorUnknown;
+    }
   *p = std::malloc(n ? n : 1);
   if (*p == nullptr)
     return cudaErrorUnknown;
@@ -336,7 +404,56 @@ inline cudaError_t cudaMalloc(void **p, size_t n)
 }
 inline cudaError_t cudaFree(void *p)
 {
+  auto it = gf_emu::shared_blocks().find(p);
+  if (it != gf_emu::shared_blocks().end())
+    {
+      munmap(p, it->second.bytes);
+      if (it->second.owner)
+        shm_unlink(it->second.name.c_str());
+      gf_emu::shared_blocks().erase(it);
+      return cudaSuccess;
+    }
   std::free(p);
+  return cudaSuccess;
+}
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p)
+{
+  auto it = gf_emu::shared_blocks().find(p);
+  if (it == gf_emu::shared_blocks().end() || it->second.name.size() >= sizeof(h->reserved))
+    return cudaErrorUnknown;
+  std::memset(h->reserved, 0, sizeof(h->reserved));
+  std::memcpy(h->reserved, it->second.name.c_str(), it->second.name.size());
+  return cudaSuccess;
+}
+inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned)
+{
+  h.reserved[sizeof(h.reserved) - 1] = 0;
+  *p = gf_emu::map_shared(h.reserved, 0, false);
+  return *p ? cudaSuccess : cudaErrorUnknown;
+}
+inline cudaError_t cudaIpcCloseMemHandle(void *p) { return cudaFree(p); }
+inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned)
+{
+  *p = std::calloc(n ? n : 1, 1);
+  return *p ? cudaSuccess : cudaErrorUnknown;
+}
+inline cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned)
+{
+  *d = h;
+  return cudaSuccess;
+}
+// cuStreamWaitValue64 (ranks sharing a device): not in the emulation - every rank is its own device
+enum cudaDriverEntryPointQueryResult
+{
+  cudaDriverEntryPointSuccess = 0,
+  cudaDriverEntryPointSymbolNotFound = 1
+};
+constexpr unsigned long long cudaEnableDefault = 0;
+inline cudaError_t cudaGetDriverEntryPoint(const char *, void **fn, unsigned long long,
+                                           cudaDriverEntryPointQueryResult *qr)
+{
+  *fn = nullptr;
+  *qr = cudaDriverEntryPointSymbolNotFound;
   return cudaSuccess;
 }
 inline cudaError_t cudaMallocHost(void **p, size_t n)

@@ -21,7 +21,7 @@ OUT_DIR = os.environ.get("GF_EMU_BUILD_DIR", os.path.join(HERE, "_build"))
 LIB = os.path.join(OUT_DIR, "libgraftfem_emu.so")
 SOURCES = ["api.cu", "pattern.cu", "scatter.cu", "assemble_nl.cu", "assemble_lin.cu", "cg.cu",
            "reduce.cu", "vector_ops.cu", "constraints.cu", "direct.cu", "postprocess.cu",
-           "fe_tables.cu", "spmv.cu", "operator.cu", "multigrid.cu", "matfree.cu"]
+           "fe_tables.cu", "spmv.cu", "operator.cu", "multigrid.cu", "matfree.cu", "comm.cu"]
 
 
 def _matching(text, i, open_ch, close_ch):
@@ -114,7 +114,7 @@ def build(force=False):
             sys.stderr.write("---- %s\n%s\n" % (g, log[-6000:]))
     if failed:
         raise RuntimeError("emulation build failed")
-    subprocess.check_call(["g++", "-shared", "-pthread", "-o", LIB] + link + objs)
+    subprocess.check_call(["g++", "-shared", "-pthread", "-o", LIB] + link + objs + ["-lrt", "-ldl"])
     return LIB
 
 

@@ -26,11 +26,15 @@ CASES = {
     "lin_mg": ("linear", "mg", [4, 32, 4], 80000),
     "nl_mg_partitioned_coarse": ("neo-Hookean", "mg", [4, 32, 4], 0),   # halos on every level
 }
-# run only on request (--cases): first hardware run in tests/test_zz_gpu_high_degree.py
+# run only on request (--cases): first hardware run in tests/test_zz_gpu_high_degree.py; the *_small
+# cases are sized for the CPU emulation of the library (tests/test_emulated_library.py)
 EXTRA_CASES = {
     # name: (model, preconditioner, reps, replicate_below_dofs, polynomial degree)
     "nl_jacobi_q3": ("neo-Hookean", "jacobi", [1, 6, 1], None, 3),
     "lin_jacobi_q3": ("linear", "jacobi", [1, 6, 1], None, 3),
+    "nl_mg_small": ("neo-Hookean", "mg", [2, 8, 2], 80000, 2),             # coarse level replicated
+    "lin_mg_small": ("linear", "mg", [2, 8, 2], 80000, 2),
+    "nl_mg_small_partitioned_coarse": ("neo-Hookean", "mg", [2, 8, 2], 0, 2),   # halos on both levels
 }
 N_STEPS = 2
 LOAD = (1500.0, 0.0, 100.0)
@@ -115,6 +119,15 @@ def main():
     import torch.distributed as dist
     from dealii_adapter_b200 import capi
     n_dev = torch.cuda.device_count()
+    emu = os.environ.get("GF_TEST_EMU_LIB")
+    if emu:
+        # tests/test_emulated_library.py: the CPU emulation build of the library, every rank its
+        # own "device"; the peer windows are shared-memory files (tests/cuda_emu/cuda_runtime.h)
+        from dealii_adapter_b200 import build
+        assert args.mode == "ipc" and os.path.basename(emu) == "libgraftfem_emu.so"
+        build.LIB_CUDA, capi._lib = emu, None
+        capi.lib()
+        n_dev = world
     if args.mode == "nccl":
         device = lr
         torch.cuda.set_device(device)
@@ -125,7 +138,7 @@ def main():
         dist.broadcast(idt, 0)
         comm = capi.Comm(bytes(idt.cpu().numpy().tobytes()), rank, world, device)
     else:
-        device = lr % n_dev
+        device = 0 if emu else lr % n_dev
         dist.init_process_group("gloo")
 
         def all_gather(b):

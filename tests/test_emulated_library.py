@@ -11,9 +11,9 @@ between the C-ABI and the kernels - numbering and sparsity pattern, scatter map,
 Newton / theta-scheme entry points, export, output - before the first run on hardware.
 What it is NOT: a product path. Nothing outside tests/ can load the emulation build; the tuned
 kernels (TMA SpMV, the mbarrier-pipelined neo-Hookean kernels), the single-launch coarsest-level
-solver and the communicators do not exist in it and stay GPU-tested only: every (dim, degree)
+solver and the NCCL transport do not exist in it and stay GPU-tested only: every (dim, degree)
 takes the generic cell kernels here, every SpMV the LDG kernel, the coarsest multigrid level its
-multi-launch fallback.
+multi-launch fallback; ranks are processes whose peer windows are shared-memory files.
 
 Default: a subset that runs in about two minutes. GF_EMU_FULL=1: every body of both GPU files that
 needs a serial handle only (about 90 minutes); the files covered: test_gpu_parity,
@@ -246,12 +246,40 @@ def test_bench_py_end_to_end_on_the_emulated_library(emu_libs, monkeypatch):
                                          "vcycle_all_fp32_operator", "direct_solver_stand_in"}
 
 
-def test_hardware_only_parts_are_refused_not_faked(emu_libs):
-    """The emulation build must not pretend: communicators (NVLink peer windows / NCCL) do not
-    exist in it, and a partitioned handle cannot be created."""
-    capi, solvers, orc = emu_libs
-    with pytest.raises(Exception):
-        capi.Comm.unique_id()
+MULTIRANK_CASES = ["nl_jacobi", "lin_jacobi", "nl_mg_small", "lin_mg_small",
+                   "nl_mg_small_partitioned_coarse"]
+
+
+@pytest.mark.parametrize("world", [2, 4] if FULL else [2])
+def test_partitioned_runs_on_emulated_ranks_reproduce_the_single_rank_run(emu_libs, emu_lib_path,
+                                                                          tmp_path, world):
+    """The multi-rank path without a GPU: the ranks are PROCESSES (torch.distributed.run, gloo for
+    the bootstrap) that each load the emulation build; comm.cu's peer windows - mailboxes, flags,
+    the push / wait kernels, the gather of the reduction partials - run as they are on
+    shared-memory files behind cudaIpcGetMemHandle / cudaIpcOpenMemHandle. Same worker and same
+    assertions as tests/test_gpu_multirank.py on meshes sized for the emulation: Newton and CG
+    counts identical and the written interface displacement BITWISE equal to the single-rank run,
+    with the coarse multigrid level replicated (vector all-reduce of the restricted residual) and
+    slab-partitioned (halos on both levels), through the deferred tangent completion."""
+    import mgpu_worker as w
+    from test_gpu_multirank import _compare, _spawn
+    cases = MULTIRANK_CASES if FULL else ["lin_mg_small", "nl_mg_small_partitioned_coarse"]
+    ref = {}
+    for name in cases:
+        hist, written, levels = w.run_case(name, 1, 0, 0, None)
+        ref[name] = {"written": written, "history": hist, "levels": levels}
+    os.environ["GF_TEST_EMU_LIB"] = emu_lib_path
+    os.environ["GF_WORKER_DEADLINE_S"] = "1500"
+    try:
+        got = _spawn(world, "ipc", str(tmp_path / "ranks.pkl"), cases=",".join(cases), timeout=1600)
+    finally:
+        del os.environ["GF_TEST_EMU_LIB"], os.environ["GF_WORKER_DEADLINE_S"]
+    assert got["transport"][0] == "peer_windows" and got["transport"][1] > 0
+    for name in cases:
+        _compare(ref, got, name, True)
+    if "lin_mg_small" in cases:
+        assert got["lin_mg_small"]["levels"] == (2, [False, True])          # coarse level replicated
+    assert got["nl_mg_small_partitioned_coarse"]["levels"] == (2, [False, False])
 
 
 def test_binding_is_back_on_the_product_library():
