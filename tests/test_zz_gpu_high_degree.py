@@ -585,7 +585,7 @@ def test_partitioned_run_at_degree_3_reproduces_the_single_rank_run(native_libs,
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (3, 1), (3, 2)])
 @first_run
-def test_hanging_nodes_linear_steps(libs, degree, dim=2):
+def test_hanging_nodes_linear_steps(libs, dim, degree):
     from helpers import constraint_matrix, hanging_node_problem, reference_linear_steps
     capi, solvers, orc = libs
     p = lin_params(poly_degree=degree, type_lin="CG", body_force=(0.0, -9.81, 0.0),
@@ -610,7 +610,7 @@ def test_hanging_nodes_linear_steps(libs, degree, dim=2):
 
 @pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (3, 1), (3, 2)])
 @first_run
-def test_hanging_nodes_nonlinear_step_and_refusals(libs, degree, dim=2):
+def test_hanging_nodes_nonlinear_step_and_refusals(libs, dim, degree):
     from helpers import constraint_matrix, hanging_node_problem, reference_nonlinear_step
     capi, solvers, orc = libs
     p = nl_params(poly_degree=degree, type_lin="Direct", scenario="PF", delta_t=0.01)
