@@ -168,6 +168,20 @@ namespace gf_emu
     return stacks[t];
   }
 
+  inline int schedule_mode()
+  {
+    const char *e = std::getenv("GF_EMU_SCHEDULE");
+    if (e == nullptr)
+      return 0;
+    return std::strncmp(e, "reverse", 7) == 0 ? 1 : (std::strncmp(e, "random", 6) == 0 ? 2 : 0);
+  }
+  inline unsigned long long schedule_seed()
+  {
+    const char *e = std::getenv("GF_EMU_SCHEDULE");
+    const char *c = e ? std::strchr(e, ':') : nullptr;
+    return c ? std::strtoull(c + 1, nullptr, 10) + 0x9E3779B97F4A7C15ull : 0x9E3779B97F4A7C15ull;
+  }
+
   // kernel<<<grid, block, smem_bytes>>>(args...) -> launch(grid, block, smem_bytes, [&] { kernel(args...); })
   inline void launch(dim3 grid3, unsigned block, size_t smem_bytes,
                      const std::function<void()> &kernel)
@@ -209,18 +223,35 @@ namespace gf_emu
               *--sp = nullptr;
             f.sp = sp;
           }
+        // Scheduling order of the fibers between two yields. In-order execution would HIDE a
+        // missing barrier of the kind "lower thread writes, higher thread reads", so the order is
+        // selectable: GF_EMU_SCHEDULE = forward (default) | reverse | random:<seed> (a new
+        // permutation every sweep). tests/test_emulated_library.py runs a subset under all three.
+        static const int          mode = schedule_mode();
+        static unsigned long long rng  = schedule_seed();
+        std::vector<unsigned>     order(block);
+        for (unsigned t = 0; t < block; ++t)
+          order[t] = mode == 1 ? block - 1 - t : t;
         unsigned alive = block;
         while (alive > 0)
-          for (unsigned t = 0; t < block; ++t)
-            {
-              Fiber &f = fibers[t];
-              if (f.done)
-                continue;
-              cur = &f;
-              switch_context(&sched_sp, f.sp);
-              if (f.done)
-                --alive;
-            }
+          {
+            if (mode == 2)
+              for (unsigned t = block; t > 1; --t)
+                {
+                  rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                  std::swap(order[t - 1], order[unsigned((rng >> 33) % t)]);
+                }
+            for (unsigned k = 0; k < block; ++k)
+              {
+                Fiber &f = fibers[order[k]];
+                if (f.done)
+                  continue;
+                cur = &f;
+                switch_context(&sched_sp, f.sp);
+                if (f.done)
+                  --alive;
+              }
+          }
       }
     cur = nullptr;
   }

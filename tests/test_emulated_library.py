@@ -325,6 +325,31 @@ def test_bench_py_on_emulated_ranks(emu_lib_path, tmp_path, world):
     assert "error" not in strong and strong["n_gpus"] == world and strong["cg_iterations"] == [11]
 
 
+SCHEDULE_SUBSET = ("tangent or hanging or distorted or output or cell_assembly or vcycle or "
+                   "matrix_free or spmv_and_cg or det_F or chunked")
+
+
+@pytest.mark.parametrize("schedule", ["reverse", "random:11", "random:12"] if FULL else ["reverse"])
+def test_kernels_do_not_depend_on_the_thread_schedule(emu_lib_path, schedule):
+    """The fibers of a CTA run in thread order between two barriers, which would HIDE a missing
+    __syncthreads of the kind 'a lower thread writes, a higher thread reads'. The same tests again
+    with the fibers scheduled in reverse / in a new random order every sweep (GF_EMU_SCHEDULE, read
+    once per process - hence the child process): same results, including the bitwise
+    run-to-run checks inside the bodies."""
+    import subprocess
+    if os.environ.get("GF_EMU_SCHEDULE"):
+        pytest.skip("already running under GF_EMU_SCHEDULE")
+    env = dict(os.environ, GF_EMU_SCHEDULE=schedule)
+    env.pop("GF_EMU_FULL", None)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider",
+                        os.path.join(HERE, "test_cuda_emulation.py"),
+                        os.path.join(HERE, "test_emulated_library.py"), "-k",
+                        "test_cuda_emulation or (test_gpu_test_body and (%s))" % SCHEDULE_SUBSET],
+                       env=env, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
+
+
 def test_binding_is_back_on_the_product_library():
     """Outside the fixture capi must not keep the emulation build (a GPU test that ran on it would
     prove nothing)."""
