@@ -246,7 +246,7 @@ def test_bench_py_end_to_end_on_the_emulated_library(emu_libs, monkeypatch):
 
 
 MULTIRANK_CASES = ["nl_jacobi", "lin_jacobi", "nl_mg_small", "lin_mg_small",
-                   "nl_mg_small_partitioned_coarse"]
+                   "nl_mg_small_partitioned_coarse", "nl_jacobi_q3", "lin_jacobi_q3"]
 
 
 @pytest.mark.parametrize("world", [2, 4] if FULL else [2])
