@@ -35,6 +35,7 @@ EXTRA_CASES = {
     "nl_mg_small": ("neo-Hookean", "mg", [2, 8, 2], 80000, 2),             # coarse level replicated
     "lin_mg_small": ("linear", "mg", [2, 8, 2], 80000, 2),
     "nl_mg_small_partitioned_coarse": ("neo-Hookean", "mg", [2, 8, 2], 0, 2),   # halos on both levels
+    "lin_mg_small_partitioned_coarse": ("linear", "mg", [2, 8, 2], 0, 2),
 }
 N_STEPS = 2
 LOAD = (1500.0, 0.0, 100.0)

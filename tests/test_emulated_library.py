@@ -246,7 +246,8 @@ def test_bench_py_end_to_end_on_the_emulated_library(emu_libs, monkeypatch):
 
 
 MULTIRANK_CASES = ["nl_jacobi", "lin_jacobi", "nl_mg_small", "lin_mg_small",
-                   "nl_mg_small_partitioned_coarse", "nl_jacobi_q3", "lin_jacobi_q3"]
+                   "nl_mg_small_partitioned_coarse", "lin_mg_small_partitioned_coarse",
+                   "nl_jacobi_q3", "lin_jacobi_q3"]
 
 
 @pytest.mark.parametrize("world", [2, 4] if FULL else [2])
@@ -262,9 +263,9 @@ def test_partitioned_runs_on_emulated_ranks_reproduce_the_single_rank_run(emu_li
     slab-partitioned (halos on both levels), through the deferred tangent completion."""
     import mgpu_worker as w
     from test_gpu_multirank import _compare, _spawn
-    # default: halos on both multigrid levels; the replicated coarse level runs in
-    # test_bench_py_on_emulated_ranks
-    cases = MULTIRANK_CASES if FULL else ["nl_mg_small_partitioned_coarse"]
+    # default: the linear model with halos on both multigrid levels; the neo-Hookean model, the
+    # deferred tangent and the replicated coarse level run in test_bench_py_on_emulated_ranks
+    cases = MULTIRANK_CASES if FULL else ["lin_mg_small_partitioned_coarse"]
     ref = {}
     for name in cases:
         hist, written, levels = w.run_case(name, 1, 0, 0, None)
@@ -280,7 +281,7 @@ def test_partitioned_runs_on_emulated_ranks_reproduce_the_single_rank_run(emu_li
         _compare(ref, got, name, True)
     if "lin_mg_small" in cases:
         assert got["lin_mg_small"]["levels"] == (2, [False, True])          # coarse level replicated
-    assert got["nl_mg_small_partitioned_coarse"]["levels"] == (2, [False, False])
+    assert got["lin_mg_small_partitioned_coarse"]["levels"] == (2, [False, False])
 
 
 @pytest.mark.parametrize("world", [2, 4] if FULL else [2])
