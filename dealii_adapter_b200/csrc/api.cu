@@ -79,8 +79,8 @@ namespace
   bool direct_apply(gf_context &c, const double *A, const double *b, double *x,
                     const bool constant_matrix)
   {
-    if (c.operator_kind != 0 || c.lines.n > 0 || !gf::direct_available(c))
-      return false; // (the band holds A, not the condensed C^T A C)
+    if (c.operator_kind != 0 || !gf::direct_available(c))
+      return false;
     try
       {
         if (!(constant_matrix && c.direct.factored && c.direct.factor_is_system_matrix))
@@ -92,6 +92,25 @@ namespace
                 return false;
               }
             c.direct.factor_is_system_matrix = constant_matrix;
+          }
+        if (c.lines.n > 0)
+          {
+            // hanging-node constraint lines: the band holds A, the system is the condensed
+            // C^T A C - the factor preconditions a CG on the condensed operator (cg.cu), which
+            // ends after a handful of iterations; tolerance as tight as the stand-in's
+            const double bn = gf::vec_masked_norm(c, b, false);
+            uint32_t     it  = 0;
+            double       res = 0;
+            const int    rc  = gf::cg_solve_direct_precond(c, A, x, b, 1e-13 * bn, 200, &it, &res);
+            if (rc != GF_OK && !(res <= 1e-10 * bn))
+              {
+                GF_REQUIRE(c.direct_mode != 1, GF_ERR_NOT_CONVERGED,
+                           "direct solver: the condensed iteration did not converge");
+                return false;
+              }
+            c.direct.last_residual = bn > 0 ? res / bn : res;
+            c.direct.n_solves++;
+            return true;
           }
         gf::direct_solve(c, b, x);
         gf::launch_spmv(c, A, x, c.cg_v.p, nullptr);
@@ -1287,14 +1306,12 @@ extern "C"
                      double *last_residual)
   {
     return guarded(h, [&](gf_context &c) {
-      const bool ok = c.operator_kind == 0 && c.lines.n == 0 && gf::direct_available(c);
+      const bool ok = c.operator_kind == 0 && gf::direct_available(c);
       GF_REQUIRE(ok, GF_ERR_UNSUPPORTED,
                  "direct solver not in use: " +
-                   (c.direct_mode == 2 ?
-                      std::string("GF_OPT_DIRECT_SOLVER = 2") :
-                      (c.operator_kind != 0 ? std::string("matrix-free operator") :
-                                              (c.lines.n > 0 ? std::string("hanging-node constraints") :
-                                                               c.direct.why))));
+                   (c.direct_mode == 2 ? std::string("GF_OPT_DIRECT_SOLVER = 2") :
+                                         (c.operator_kind != 0 ? std::string("matrix-free operator") :
+                                                                 c.direct.why)));
       if (n_solves)
         *n_solves = c.direct.n_solves;
       if (half_bandwidth)

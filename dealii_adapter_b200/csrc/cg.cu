@@ -220,6 +220,67 @@ namespace gf
     return c.h_scalars->status == 1 ? GF_OK : GF_ERR_NOT_CONVERGED;
   }
 
+  // 'Solver type = Direct' on a handle WITH hanging-node constraint lines: the band Cholesky
+  // holds the uncondensed A, the system is the condensed C^T A C (operator.cu). The factor is then
+  // the preconditioner of a CG on the condensed operator, z = A^-1 r (restricted to the
+  // unconstrained dofs this is the inverse of a Schur complement of A: SPD). C^T A C differs from
+  // that Schur complement by a term whose rank is bounded by the number of constrained dofs, so
+  // the iteration ends after a handful of steps. Same recurrences and device-resident
+  // SolverControl state as cg_solve_mg; x starts from zero; tol is absolute.
+  int cg_solve_direct_precond(gf_context &c, const double *val, double *x, const double *b,
+                              double tol, int64_t maxit, uint32_t *last_step, double *last_value)
+  {
+    GF_REQUIRE(c.comm == nullptr && c.direct.factored, GF_ERR_INVALID_ARG,
+               "cg_solve_direct_precond: serial handle with a factorisation");
+    cudaStream_t s = c.stream;
+    CGScalars    init{};
+    init.tol     = tol;
+    init.maxit   = int(std::min<int64_t>(maxit, 2147483647));
+    init.status  = 0;
+    *c.h_scalars = init;
+    GF_CUDA_CHECK(cudaMemcpyAsync(c.cg_scalars.p, c.h_scalars, sizeof(CGScalars),
+                                  cudaMemcpyHostToDevice, s));
+    GF_CUDA_CHECK(cudaMemsetAsync(c.cg_p.p, 0, c.n_local * sizeof(double), s));
+    const int dg = vec_grid(c, c.n_owned);
+    auto update = [&](bool startup) {
+      ProfScope ps(c, Profile::CG_VEC, 2);
+      launch_update(c, startup, b, x);
+      reduce_sums(c, 1, startup ? 3 : 4, true); // r.r -> residual check
+    };
+    auto poll = [&]() {
+      GF_CUDA_CHECK(cudaMemcpyAsync(c.h_scalars, c.cg_scalars.p, sizeof(CGScalars),
+                                    cudaMemcpyDeviceToHost, s));
+      GF_CUDA_CHECK(cudaStreamSynchronize(s));
+      return c.h_scalars->status;
+    };
+    vec_zero(c, x);
+    vec_zero(c, c.cg_v.p);
+    update(true); // r = b
+    GF_CUDA_CHECK(cudaGetLastError());
+    while (poll() == 0)
+      {
+        direct_solve(c, c.cg_r.p, c.cg_z.p); // z = A^-1 r
+        {
+          ProfScope ps(c, Profile::CG_VEC, 3);
+          launch_dot_chunks(c, c.cg_r.p, c.cg_z.p, true);
+          reduce_sums(c, 1, 5, true); // r.z, beta
+          cg_direction_kernel<<<dg, VEC_THREADS, 0, s>>>(c.n_owned, c.cg_scalars.p, c.cg_z.p,
+                                                         c.cg_p.p);
+        }
+        op_apply(c, val, c.cg_p.p, c.cg_v.p, nullptr);
+        {
+          ProfScope ps(c, Profile::CG_VEC, 2);
+          launch_dot_chunks(c, c.cg_p.p, c.cg_v.p, true);
+          reduce_sums(c, 1, 1, true); // p.Ap, alpha
+        }
+        update(false);
+        GF_CUDA_CHECK(cudaGetLastError());
+      }
+    *last_step  = uint32_t(c.h_scalars->it);
+    *last_value = c.h_scalars->res;
+    return c.h_scalars->status == 1 ? GF_OK : GF_ERR_NOT_CONVERGED;
+  }
+
   int cg_solve(gf_context &c, const double *val, double *x, const double *b, double tol,
                bool tol_relative_to_rhs, int64_t maxit, uint32_t *last_step, double *last_value)
   {

@@ -451,6 +451,8 @@ namespace gf
   // cg.cu
   int cg_solve(gf_context &c, const double *val, double *x, const double *b, double tol,
                bool tol_relative_to_rhs, int64_t maxit, uint32_t *last_step, double *last_value);
+  int cg_solve_direct_precond(gf_context &c, const double *val, double *x, const double *b,
+                              double tol, int64_t maxit, uint32_t *last_step, double *last_value);
   // vector_ops.cu
   void   vec_permute_in(gf_context &c, const double *ext_host, double *dst);
   void   vec_permute_out(gf_context &c, const double *src, double *ext_host);

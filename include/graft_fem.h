@@ -116,8 +116,10 @@ extern "C"
      * assembles the unconstrained operator A and solves the condensed system C^T A C (what
      * condense() / distribute_local_to_global produce) by applying x -> C^T (A (C x)) inside the
      * CG and condensing the right-hand sides; `distribute()` follows every solve. Serial handles,
-     * CG with block-Jacobi (gf_mg_attach, the matrix-free operator and the band Cholesky answer
-     * GF_ERR_UNSUPPORTED / fall back); gf_export_csr returns the UNcondensed matrix. */
+     * CG with block-Jacobi (gf_mg_attach and the matrix-free operator answer GF_ERR_UNSUPPORTED);
+     * `Solver type = Direct`: the band Cholesky factor of A preconditions the CG on the condensed
+     * operator, which then ends after a handful of iterations. gf_export_csr returns the
+     * UNcondensed matrix. */
     int64_t        n_constraint_lines;
     const int32_t *line_dof;    /* [n_constraint_lines] */
     const int64_t *line_ptr;    /* [n_constraint_lines + 1] */

@@ -118,9 +118,9 @@ FAST = [
     (HD, "test_hanging_nodes_linear_steps", dict(dim=2, degree=2)),
     (HD, "test_hanging_nodes_linear_steps", dict(dim=3, degree=1)),
     (HD, "test_hanging_nodes_linear_steps", dict(dim=3, degree=2)),
-    (HD, "test_hanging_nodes_nonlinear_step_and_refusals", dict(dim=2, degree=2)),
-    (HD, "test_hanging_nodes_nonlinear_step_and_refusals", dict(dim=3, degree=1)),
-    (HD, "test_hanging_nodes_nonlinear_step_and_refusals", dict(dim=3, degree=2)),
+    (HD, "test_hanging_nodes_nonlinear_step_direct_and_cg", dict(dim=2, degree=2)),
+    (HD, "test_hanging_nodes_nonlinear_step_direct_and_cg", dict(dim=3, degree=1)),
+    (HD, "test_hanging_nodes_nonlinear_step_direct_and_cg", dict(dim=3, degree=2)),
     # ---- 'Solver type = Direct': band Cholesky behind the Newton / theta-scheme entry points
     #      (smaller meshes than the GPU run of the same bodies)
     (HD, "test_direct_solver_band_cholesky_nonlinear", dict(dim=2, degree=3, scenario="FSI3", reps=[6, 1], load=(0.0, -1500.0))),

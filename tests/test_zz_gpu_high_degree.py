@@ -606,11 +606,23 @@ def test_hanging_nodes_linear_steps(libs, dim, degree):
     for k in range(3):
         assert rel_err(part.written[k][2], ref[k][prob.iface_dofs.T].reshape(-1)) < 1e-6
     ed.handle.close()
+    # 'Solver type = Direct' (linear_elasticity.cc:556-563): the factor of the constant system
+    # matrix, computed once, preconditions the CG on the condensed operator
+    pd = lin_params(poly_degree=degree, type_lin="Direct", body_force=(0.0, -9.81, 0.0))
+    probd = hanging_node_problem(pd, degree, dim)
+    partd = solvers.FakeParticipant(dim, 3, pd.delta_t, lambda t, it: bufs[min(2, int(round(t / pd.delta_t)) - 1)])
+    edd = solvers.ElastoDynamics(probd, partd)
+    edd.handle.set_option(capi.OPT_DIRECT_SOLVER, 0)
+    edd.run()
+    assert rel_err(edd.handle.get_vector(capi.LIN_DISPLACEMENT), ref[-1]) < 1e-9
+    n_solves, half_bw, res = edd.handle.direct_info()
+    assert n_solves == 3 and half_bw > 0 and res <= 1e-10
+    edd.handle.close()
 
 
 @pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (3, 1), (3, 2)])
 @first_run
-def test_hanging_nodes_nonlinear_step_and_refusals(libs, dim, degree):
+def test_hanging_nodes_nonlinear_step_direct_and_cg(libs, dim, degree):
     from helpers import constraint_matrix, hanging_node_problem, reference_nonlinear_step
     capi, solvers, orc = libs
     p = nl_params(poly_degree=degree, type_lin="Direct", scenario="PF", delta_t=0.01)
@@ -619,7 +631,9 @@ def test_hanging_nodes_nonlinear_step_and_refusals(libs, dim, degree):
     ref = reference_nonlinear_step(orc, prob, buf)
     part = solvers.FakeParticipant(dim, 1, p.delta_t, lambda t, it: buf)
     solid = solvers.Solid(prob, part)
-    solid.handle.set_option(capi.OPT_DIRECT_SOLVER, 0)   # auto: lines -> the CG stand-in runs
+    # auto: the band Cholesky factor of the uncondensed tangent preconditions a CG on the
+    # condensed operator (csrc/cg.cu: cg_solve_direct_precond)
+    solid.handle.set_option(capi.OPT_DIRECT_SOLVER, 0)
     solid.run()
     u = solid.handle.get_vector(capi.NL_TOTAL_DISPLACEMENT)
     assert 3 <= len(solid.history[0]) <= 7
@@ -628,10 +642,20 @@ def test_hanging_nodes_nonlinear_step_and_refusals(libs, dim, degree):
     m = u.copy()
     m[dof] = 0.0
     assert np.abs(constraint_matrix(prob) @ m - u).max() <= 1e-14 * np.abs(u).max()
-    with pytest.raises(capi.GraftError) as e:
-        solid.handle.direct_info()                       # the band Cholesky does not take lines
-    assert e.value.code == capi.GF_ERR_UNSUPPORTED and "hanging" in str(e.value)
+    n_solves, half_bw, res = solid.handle.direct_info()
+    assert n_solves == len(solid.history[0]) and half_bw > 0 and res <= 1e-10
     solid.handle.close()
+    # GF_OPT_DIRECT_SOLVER = 2: the tight block-Jacobi CG on the condensed operator, same answer
+    part2 = solvers.FakeParticipant(dim, 1, p.delta_t, lambda t, it: buf)
+    solid2 = solvers.Solid(prob, part2)
+    solid2.handle.set_option(capi.OPT_DIRECT_SOLVER, 2)
+    solid2.run()
+    assert len(solid2.history[0]) == len(solid.history[0])
+    assert rel_err(solid2.handle.get_vector(capi.NL_TOTAL_DISPLACEMENT), u) < 1e-9
+    with pytest.raises(capi.GraftError) as e:
+        solid2.handle.direct_info()
+    assert e.value.code == capi.GF_ERR_UNSUPPORTED
+    solid2.handle.close()
 
 
 def test_zzz_every_first_run_test_above_passed():
