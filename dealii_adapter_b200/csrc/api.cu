@@ -574,7 +574,7 @@ extern "C"
           case GF_OPT_OPERATOR:
             GF_REQUIRE(value == 0 || value == 1, GF_ERR_INVALID_ARG, "unknown operator kind");
             GF_REQUIRE(value == 0 || (c.model == GF_MODEL_NEO_HOOKEAN && c.dim == 3 && c.p <= 2 &&
-                                      c.affine && c.lines.n == 0),
+                                      c.affine),
                        GF_ERR_UNSUPPORTED,
                        "the matrix-free operator is available for the 3D neo-Hookean model, "
                        "polynomial degree 1 or 2, parallelepiped cells");

@@ -116,7 +116,8 @@ extern "C"
      * assembles the unconstrained operator A and solves the condensed system C^T A C (what
      * condense() / distribute_local_to_global produce) by applying x -> C^T (A (C x)) inside the
      * CG and condensing the right-hand sides; `distribute()` follows every solve. Serial handles,
-     * CG with block-Jacobi (gf_mg_attach and the matrix-free operator answer GF_ERR_UNSUPPORTED);
+     * CG with block-Jacobi, assembled or matrix-free operator (gf_mg_attach answers
+     * GF_ERR_UNSUPPORTED);
      * `Solver type = Direct`: the band Cholesky factor of A preconditions the CG on the condensed
      * operator, which then ends after a handful of iterations. gf_export_csr returns the
      * UNcondensed matrix. */

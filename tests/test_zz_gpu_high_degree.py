@@ -656,6 +656,15 @@ def test_hanging_nodes_nonlinear_step_direct_and_cg(libs, dim, degree):
         solid2.handle.direct_info()
     assert e.value.code == capi.GF_ERR_UNSUPPORTED
     solid2.handle.close()
+    if dim == 3:
+        # the matrix-free tangent takes the same condensation (operator.cu wraps either operator)
+        part3 = solvers.FakeParticipant(dim, 1, p.delta_t, lambda t, it: buf)
+        solid3 = solvers.Solid(prob, part3)
+        solid3.handle.set_option(capi.OPT_OPERATOR, 1)
+        solid3.run()
+        assert len(solid3.history[0]) == len(solid.history[0])
+        assert rel_err(solid3.handle.get_vector(capi.NL_TOTAL_DISPLACEMENT), u) < 1e-9
+        solid3.handle.close()
 
 
 def test_zzz_every_first_run_test_above_passed():
