@@ -351,6 +351,20 @@ def test_kernels_do_not_depend_on_the_thread_schedule(emu_lib_path, schedule):
     assert " passed" in r.stdout and "failed" not in r.stdout
 
 
+def test_the_product_library_contains_no_emulation_code(native_libs):
+    """GF_CUDA_EMULATION is a define of tests/cuda_emu/make_emu_library.py only: the product's build
+    recipe never sets it and libgraftfem.so carries no symbol of the stand-in."""
+    import subprocess
+    from dealii_adapter_b200 import build
+    recipe = open(build.__file__).read()
+    assert "GF_CUDA_EMULATION" not in recipe and "cuda_emu" not in recipe
+    assert not any("EMULATION" in f for f in build.NVCC_FLAGS)
+    lib = native_libs.build_cuda()
+    syms = subprocess.run(["nm", "-C", lib], capture_output=True, text=True).stdout
+    assert "gf_emu" not in syms and "switch_context" not in syms
+    assert "spmv_tma2_kernel" in syms            # the hardware kernels are what it is made of
+
+
 def test_binding_is_back_on_the_product_library():
     """Outside the fixture capi must not keep the emulation build (a GPU test that ran on it would
     prove nothing)."""
