@@ -88,13 +88,14 @@ def distort_mesh(problem, amp=0.12, seed=0):
     return problem
 
 
-def hanging_node_problem(params, degree, dim=2):
+def hanging_node_problem(params, degree, dim=2, clamp_axis=0):
     """A mesh WITH hanging nodes, which the structured stand-in cannot produce: the domain
     [0,2] x [0,1] (x [0,1]), left half one cell, right half refined once (2^dim cells). The nodes
     of the fine cells on the face x = 1 that the coarse cell does not own hang; their constraint
     lines are the coarse face's shape functions at their positions (what
     DoFTools::make_hanging_node_constraints produces, linear_elasticity.cc:196-207).
-    Roles: x = 0 clamped, y = 1 and x = 2 interface, the rest free. degree 1 or 2 (equidistant
+    Roles: x = 0 clamped (clamp_axis = 1: y = 0 instead, which makes masters of the hanging
+    nodes Dirichlet dofs), y = 1 and x = 2 interface, the rest free. degree 1 or 2 (equidistant
     nodes). Returns a Problem whose `extra["constraint_lines"]` = (dof, ptr, master, weight)."""
     import itertools
     from types import SimpleNamespace
@@ -145,7 +146,21 @@ def hanging_node_problem(params, degree, dim=2):
                         weight.append(w)
                 ptr.append(len(master))
     constrained = np.zeros(n_dofs, dtype=np.uint8)
-    constrained[np.repeat(np.abs(coords[:, 0]) < 1e-12, dim)] = 1
+    constrained[np.repeat(np.abs(coords[:, clamp_axis]) < 1e-12, dim)] = 1
+    # AffineConstraints::close(): chains are resolved - a master that is a Dirichlet dof (value 0)
+    # drops out of the line; a hanging dof ON the Dirichlet boundary ends up with an empty line,
+    # i.e. it is an ordinary Dirichlet dof (such lines go into `constrained`)
+    dof2, ptr2, master2, weight2 = [], [0], [], []
+    for k, s_ in enumerate(dof):
+        if constrained[s_]:
+            continue
+        for j in range(ptr[k], ptr[k + 1]):
+            if not constrained[master[j]]:
+                master2.append(master[j])
+                weight2.append(weight[j])
+        dof2.append(s_)
+        ptr2.append(len(master2))
+    dof, ptr, master, weight = dof2, ptr2, master2, weight2
     # interface faces: y = 1 (face 3) of the coarse cell and of the fine cells with j = 1, x = 2
     # (face 1) of the fine cells with i = 1
     iface = [(0, 3)] + [(c, 3) for ijk, c in fine_index.items() if ijk[1] == 1] + \

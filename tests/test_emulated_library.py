@@ -351,6 +351,31 @@ def test_kernels_do_not_depend_on_the_thread_schedule(emu_lib_path, schedule):
     assert " passed" in r.stdout and "failed" not in r.stdout
 
 
+@pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (3, 1), (3, 2)])
+def test_hanging_nodes_next_to_a_dirichlet_boundary(emu_libs, dim, degree):
+    """The clamp on y = 0 instead of x = 0: hanging nodes ON the clamped face are plain Dirichlet
+    dofs after AffineConstraints::close(), and lines of their neighbours lose the masters that are
+    Dirichlet dofs (tests/helpers.py mimics close()). Newton step against the by-definition
+    reference with the factor-preconditioned CG and with the tight block-Jacobi CG."""
+    import numpy as np
+    from helpers import hanging_node_problem, nl_params, reference_nonlinear_step, rel_err
+    capi, solvers, orc = emu_libs
+    p = nl_params(poly_degree=degree, type_lin="Direct", scenario="PF", delta_t=0.01)
+    prob = hanging_node_problem(p, degree, dim, clamp_axis=1)
+    dof, ptr, master, weight = prob.extra["constraint_lines"]
+    assert not prob.constrained[dof].any() and not prob.constrained[master].any()
+    assert (np.diff(ptr) < (degree + 1) ** (dim - 1)).any()      # some line lost a master
+    buf = np.tile([300.0, -1500.0, 300.0][:dim], prob.n_iface_nodes)
+    ref = reference_nonlinear_step(orc, prob, buf)
+    for mode in (0, 2):
+        part = solvers.FakeParticipant(dim, 1, p.delta_t, lambda t, it: buf)
+        solid = solvers.Solid(prob, part)
+        solid.handle.set_option(capi.OPT_DIRECT_SOLVER, mode)
+        solid.run()
+        assert rel_err(solid.handle.get_vector(capi.NL_TOTAL_DISPLACEMENT), ref) < 1e-8
+        solid.handle.close()
+
+
 def test_the_product_library_contains_no_emulation_code(native_libs):
     """GF_CUDA_EMULATION is a define of tests/cuda_emu/make_emu_library.py only: the product's build
     recipe never sets it and libgraftfem.so carries no symbol of the stand-in."""
