@@ -272,10 +272,12 @@ def test_partitioned_runs_on_emulated_ranks_reproduce_the_single_rank_run(emu_li
         ref[name] = {"written": written, "history": hist, "levels": levels}
     os.environ["GF_TEST_EMU_LIB"] = emu_lib_path
     os.environ["GF_WORKER_DEADLINE_S"] = "1500"
+    os.environ["GF_TEST_P2P_TIMEOUT_S"] = "120"     # CPU ranks on a possibly busy machine
     try:
         got = _spawn(world, "ipc", str(tmp_path / "ranks.pkl"), cases=",".join(cases), timeout=1600)
     finally:
         del os.environ["GF_TEST_EMU_LIB"], os.environ["GF_WORKER_DEADLINE_S"]
+        del os.environ["GF_TEST_P2P_TIMEOUT_S"]
     assert got["transport"][0] == "peer_windows" and got["transport"][1] > 0
     for name in cases:
         _compare(ref, got, name, True)
@@ -298,7 +300,7 @@ def test_bench_py_on_emulated_ranks(emu_lib_path, tmp_path, world):
     with socket.socket() as sock:
         sock.bind(("127.0.0.1", 0))
         port = sock.getsockname()[1]
-    env = dict(os.environ, GF_TEST_EMU_LIB=emu_lib_path, GF_P2P_TIMEOUT_S="30", OMP_NUM_THREADS="1")
+    env = dict(os.environ, GF_TEST_EMU_LIB=emu_lib_path, GF_P2P_TIMEOUT_S="120", OMP_NUM_THREADS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(HERE, "bench_emu_worker.py"), "--gpus", str(world), "--reps", "2,8,2",

@@ -33,7 +33,8 @@ def _free_port():
 
 
 def _spawn(world, mode, out, cases=None, timeout=240):
-    env = dict(os.environ, GF_P2P_TIMEOUT_S="30", OMP_NUM_THREADS="1")
+    env = dict(os.environ, GF_P2P_TIMEOUT_S=os.environ.get("GF_TEST_P2P_TIMEOUT_S", "30"),
+               OMP_NUM_THREADS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(HERE, "mgpu_worker.py"), "--out", out, "--mode", mode]
