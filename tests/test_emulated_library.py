@@ -328,6 +328,32 @@ def test_bench_py_on_emulated_ranks(emu_lib_path, tmp_path, world):
     assert "error" not in strong and strong["n_gpus"] == world and strong["cg_iterations"] == [11]
 
 
+def test_a_rank_that_calls_a_collective_alone_gets_an_error_not_a_hang(emu_lib_path, tmp_path):
+    """What hung the 8-GPU run of round 2 was a collective call made by one rank only. Since then a
+    peer-window wait gives up after GF_P2P_TIMEOUT_S, raises the communicator's (sticky) error flag
+    and the next comm_check of the host turns it into GF_ERR_NCCL. Never exercised on hardware;
+    here two emulated ranks do exactly that (tests/comm_timeout_worker.py)."""
+    import pickle
+    import socket
+    import subprocess
+    from dealii_adapter_b200 import capi
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    out = str(tmp_path / "report.pkl")
+    env = dict(os.environ, GF_TEST_EMU_LIB=emu_lib_path, GF_P2P_TIMEOUT_S="3", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                        "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+                        str(port), os.path.join(HERE, "comm_timeout_worker.py"), out],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    rep = pickle.load(open(out, "rb"))
+    code, msg, seconds = rep["first"]
+    assert code == capi.GF_ERR_NCCL and "timed out" in msg and 2.5 <= seconds < 60
+    code2, msg2, seconds2 = rep["second"]
+    assert code2 == capi.GF_ERR_NCCL and seconds2 < 2.5          # sticky: no second timeout
+
+
 SCHEDULE_SUBSET = ("tangent or hanging or distorted or output or cell_assembly or vcycle or "
                    "matrix_free or spmv_and_cg or det_F or chunked")
 
