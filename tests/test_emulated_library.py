@@ -15,7 +15,7 @@ solver and the NCCL transport do not exist in it and stay GPU-tested only: every
 takes the generic cell kernels here, every SpMV the LDG kernel, the coarsest multigrid level its
 multi-launch fallback; ranks are processes whose peer windows are shared-memory files.
 
-Default: a subset that runs in about two minutes. GF_EMU_FULL=1: every body of both GPU files that
+Default: a subset that runs in about four minutes (incl. bench.py on two emulated ranks). GF_EMU_FULL=1: every body of both GPU files that
 needs a serial handle only (118 tests, about 110 minutes); the files covered: test_gpu_parity,
 test_zz_gpu_high_degree, test_gpu_zz_output, test_gpu_zz_reference_pins, test_gpu_multigrid,
 test_gpu_matfree - and bench.py itself."""
